@@ -1,0 +1,192 @@
+"""ORACLE (test infrastructure only): ctypes front-end of oracle/postproc_oracle.c.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this.  See the header of postproc_oracle.c for what is restated and how it is
+pinned (reference goldens metrics.rs:406-646).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libpostproc_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "postproc_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "libpostproc_oracle.so"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_arc_length.restype = C.c_double
+        _lib.orc_box_score.restype = C.c_double
+        _lib.orc_min_area_bounding_box.restype = C.c_double
+        _lib.orc_approx_dp.restype = C.c_int64
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _pts(points):
+    a = np.ascontiguousarray(np.asarray(points, np.int32).reshape(-1, 2))
+    return a
+
+
+def binarize(pred, thresh=0.6):
+    pred = np.ascontiguousarray(pred, np.float32)
+    out = np.empty(pred.shape, np.uint8)
+    lib().orc_binarize(_p(pred, C.c_float), C.c_int64(pred.size), C.c_double(thresh), _p(out, C.c_uint8))
+    return out
+
+
+def find_contours(bitmap):
+    """-> (list of [n_i,2] int32 arrays (x,y), types uint8[n] 0=outer 1=hole)."""
+    bm = np.ascontiguousarray(bitmap, np.uint8)
+    H, W = bm.shape
+    cap_pts = W * H * 2 + 16
+    cap_c = W * H // 2 + 16
+    pts = np.empty((cap_pts, 2), np.int32)
+    offs = np.empty(cap_c + 1, np.int64)
+    types = np.empty(cap_c, np.uint8)
+    n = lib().orc_find_contours(_p(bm, C.c_uint8), W, H, _p(pts, C.c_int32), C.c_int64(cap_pts),
+                                _p(offs, C.c_int64), _p(types, C.c_uint8), cap_c)
+    if n < 0:
+        raise RuntimeError("oracle find_contours capacity")
+    return [pts[offs[i]:offs[i + 1]].copy() for i in range(n)], types[:n].copy()
+
+
+def arc_length(chain, closed=True):
+    c = _pts(chain)
+    return float(lib().orc_arc_length(_p(c, C.c_int32), C.c_int64(len(c)), int(closed)))
+
+
+def approx_dp(chain, eps, closed=True):
+    c = _pts(chain)
+    out = np.empty((len(c) + 2, 2), np.int32)
+    m = lib().orc_approx_dp(_p(c, C.c_int32), C.c_int64(len(c)), C.c_double(eps), int(closed), _p(out, C.c_int32))
+    return out[:m].copy()
+
+
+def dp_polygon(chain):
+    """metrics.rs:87-95: eps = 1% arc length (0 -> 0.01), DP, drop duplicated last point."""
+    eps = 0.01 * arc_length(chain, True)
+    if eps == 0.0:
+        eps = 0.01
+    p = approx_dp(chain, eps, True)
+    if len(p) > 1 and (p[0] == p[-1]).all():
+        p = p[:-1]
+    return p
+
+
+def box_score(pred, points, return_count=False):
+    pred = np.ascontiguousarray(pred, np.float32)
+    p = _pts(points)
+    cnt = C.c_int64(0)
+    s = lib().orc_box_score(_p(pred, C.c_float), pred.shape[-2], pred.shape[-1], _p(p, C.c_int32), len(p), C.byref(cnt))
+    return (float(s), cnt.value) if return_count else float(s)
+
+
+def offset_raw(points, delta):
+    p = _pts(points)
+    out = np.empty((3 * len(p) + 3, 2), np.int32)
+    m = lib().orc_offset_raw(_p(p, C.c_int32), len(p), C.c_double(delta), _p(out, C.c_int32))
+    return out[:m].copy()
+
+
+def expand_polygon(points, factor=2.0, return_distance=False):
+    """polygon.rs:51-56 -> [m,2] int32 or None."""
+    p = _pts(points)
+    cap = 12 * len(p) + 64
+    out = np.empty((cap, 2), np.int32)
+    d = C.c_double(0)
+    m = lib().orc_expand_polygon(_p(p, C.c_int32), len(p), C.c_double(factor), _p(out, C.c_int32), cap, C.byref(d))
+    res = out[:m].copy() if m > 0 else None
+    return (res, d.value) if return_distance else res
+
+
+def min_area_bounding_box(points):
+    """metrics.rs:133-148 -> (box [4,2] int32, short side f64)."""
+    p = _pts(points)
+    box = np.empty((4, 2), np.int32)
+    s = lib().orc_min_area_bounding_box(_p(p, C.c_int32), len(p), _p(box, C.c_int32))
+    return box, float(s)
+
+
+def polygons_from_bitmap(pred, bitmap, adjust=(1.0, 1.0), box_thresh=0.7, min_size=5.0,
+                         unclip=2.0, return_stats=False):
+    """metrics.rs:58-127 for one image -> (list of [m,2] uint32 arrays, scores f64[n])."""
+    pred = np.ascontiguousarray(pred, np.float32)
+    bm = np.ascontiguousarray(bitmap, np.uint8)
+    H, W = bm.shape
+    max_polys = W * H // 2 + 16
+    max_pts = 4 * W * H + 64
+    offs = np.empty(max_polys + 1, np.int64)
+    xy = np.empty((max_pts, 2), np.uint32)
+    scores = np.empty(max_polys, np.float64)
+    stats = np.zeros(5, np.int64)
+    n = lib().orc_polygons_from_bitmap(
+        _p(pred, C.c_float), _p(bm, C.c_uint8), H, W, C.c_double(adjust[0]), C.c_double(adjust[1]),
+        C.c_double(box_thresh), C.c_double(min_size), C.c_double(unclip), max_polys, C.c_int64(max_pts),
+        _p(offs, C.c_int64), _p(xy, C.c_uint32), _p(scores, C.c_double), _p(stats, C.c_int64))
+    if n < 0:
+        raise RuntimeError("oracle polygons_from_bitmap capacity")
+    polys = [xy[offs[i]:offs[i + 1]].copy() for i in range(n)]
+    if return_stats:
+        return polys, scores[:n].copy(), stats
+    return polys, scores[:n].copy()
+
+
+def boxes_and_box_scores(pred, adjust_values, thresh=0.6):
+    """metrics.rs:37-56: pred [B,1,H,W] f32, adjust [B,2] -> (polygons per image, scores per image)."""
+    pred = np.asarray(pred, np.float32)
+    seg = binarize(pred, thresh)
+    polys, scores = [], []
+    for b in range(pred.shape[0]):
+        p, s = polygons_from_bitmap(pred[b, 0], seg[b, 0], tuple(np.asarray(adjust_values, np.float64)[b]))
+        polys.append(p)
+        scores.append(s)
+    return polys, scores
+
+
+def preprocess(rgba, W, H, norm_first=False):
+    """image_ops.rs:188-220 minus the file decode: RGBA8 [h,w,4] -> (u8 [H,W], adjust_x, adjust_y)."""
+    rgba = np.ascontiguousarray(rgba, np.uint8)
+    sh, sw = rgba.shape[:2]
+    dst = np.empty((H, W), np.uint8)
+    rw, rh = C.c_int(0), C.c_int(0)
+    lib().orc_set_resize_variant(int(norm_first))
+    lib().orc_preprocess(_p(rgba, C.c_uint8), sw, sh, W, H, _p(dst, C.c_uint8), C.byref(rw), C.byref(rh))
+    return dst, rw.value / sw, rh.value / sh
+
+
+def polygon_iou(a, b):
+    """IoU of two simple polygons by even-odd rasterisation on a 4x supersampled grid
+    (host-side helper for the north_star 'IoU >= 0.99' check; exact clipping is
+    metrics.rs:382-394 territory and out of the kernel path)."""
+    import cv2
+    a = np.asarray(a, np.int64)
+    b = np.asarray(b, np.int64)
+    lo = np.minimum(a.min(0), b.min(0)) - 1
+    hi = np.maximum(a.max(0), b.max(0)) + 2
+    S = 4
+    size = ((hi - lo) * S).astype(int)
+    ma = np.zeros((size[1], size[0]), np.uint8)
+    mb = np.zeros_like(ma)
+    cv2.fillPoly(ma, [((a - lo) * S).astype(np.int32)], 1)
+    cv2.fillPoly(mb, [((b - lo) * S).astype(np.int32)], 1)
+    inter = np.logical_and(ma, mb).sum()
+    union = np.logical_or(ma, mb).sum()
+    return inter / union if union else 1.0

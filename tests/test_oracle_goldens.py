@@ -1,0 +1,112 @@
+"""CPU: pins the oracle against every golden vector / KAT the reference's own tests hold
+for this path."""
+import numpy as np
+import pytest
+
+import conftest as cf
+from oracle import postproc as pp
+
+
+def test_min_area_bounding_box_kat():
+    box, sside = pp.min_area_bounding_box(cf.KAT_MINRECT_IN)  # metrics.rs:406-424
+    assert box.tolist() == [list(p) for p in cf.KAT_MINRECT_BOX]
+    assert abs(sside - cf.KAT_MINRECT_SSIDE) < np.finfo(np.float64).eps
+
+
+@pytest.mark.parametrize("pts,expected", cf.KAT_BOX_SCORES)
+def test_box_score_kats(pts, expected):
+    assert pp.box_score(cf.KAT_MAP_5x5, pts) == expected  # metrics.rs:426-484 (assert_eq!)
+
+
+def test_binarize_kat():
+    # metrics.rs:486-508: the tensor is f64 there; value 0.57 vs thresh 0.57 -> 0 (strict >)
+    out = (cf.KAT_BINARIZE_IN > 0.57).astype(np.uint8)
+    assert (out == cf.KAT_BINARIZE_OUT).all()
+    # f32 map path (what the detector produces): threshold demoted to f32
+    out32 = pp.binarize(cf.KAT_BINARIZE_IN.astype(np.float32), 0.57)
+    assert (out32 == cf.KAT_BINARIZE_OUT).all()
+    assert pp.binarize(np.array([0.6], np.float32), 0.6)[0] == 0
+    assert pp.binarize(np.array([np.nextafter(np.float32(0.6), np.float32(1))], np.float32), 0.6)[0] == 1
+
+
+@pytest.mark.parametrize("adjust,expected", [((1.0, 1.0), cf.GOLDEN_POLYS_1X), ((2.0, 2.0), cf.GOLDEN_POLYS_2X)])
+def test_get_polygons_from_bitmap_golden(gt55, adjust, expected):
+    # metrics.rs:510-646: bitmap = img/255 as u8, pred = img/255 as float
+    pred = gt55.astype(np.float32)
+    polys, scores = pp.polygons_from_bitmap(pred, gt55, adjust)
+    assert [[tuple(int(v) for v in p) for p in poly] for poly in polys] == expected
+    assert scores.tolist() == cf.GOLDEN_SCORES
+
+
+def test_golden_intermediate_facts(gt55):
+    # blob 1 starts (444,80),(444,81) ... ends (445,80); 239 points
+    cs, types = pp.find_contours(gt55)
+    assert len(cs) == 4 and (types == 0).all()
+    assert cs[0][0].tolist() == [444, 80] and cs[0][1].tolist() == [444, 81] and cs[0][-1].tolist() == [445, 80]
+    assert len(cs[0]) == 239
+    assert pp.dp_polygon(cs[0]).tolist() == [[444, 80], [441, 94], [532, 97], [549, 97], [550, 86]]
+    # mask sizes behind the golden scores (1465/1492, 6414/6454, 1800/1816, 5186/5226)
+    pred = gt55.astype(np.float32)
+    counts = [pp.box_score(pred, pp.dp_polygon(c), True)[1] for c in cs]
+    assert counts == [1492, 6454, 1816, 5226]
+
+
+def test_contours_match_opencv_on_framed_images():
+    # Independent cross-check: with a 1-px zero frame, imageproc's contours are
+    # OpenCV's (RETR_CCOMP, CHAIN_APPROX_NONE) point for point: hole borders identical, outer
+    # borders with the same start but the opposite direction.
+    cv2 = pytest.importorskip("cv2")
+    from ocr_rs_b200 import synth
+    for seed in range(8):
+        bm = synth.make_random_bitmap(48, 64, seed, density=0.45, smooth=seed % 3)
+        bm[0, :] = bm[-1, :] = 0
+        bm[:, 0] = bm[:, -1] = 0
+        ours, types = pp.find_contours(bm)
+        theirs, hier = cv2.findContours(bm, cv2.RETR_CCOMP, cv2.CHAIN_APPROX_NONE)
+        expected = []
+        for c, h in zip(theirs, hier[0]):
+            pts = [tuple(p) for p in c[:, 0, :].tolist()]
+            is_hole = h[3] >= 0
+            expected.append((tuple(pts) if is_hole else tuple([pts[0]] + pts[:0:-1]), int(is_hole)))
+        got = [(tuple(map(tuple, c.tolist())), int(t)) for c, t in zip(ours, types)]
+        assert sorted(got) == sorted(expected), seed
+        # raster order of start pixels
+        starts = [c[0][1] * 64 + c[0][0] for c in ours]
+        assert starts == sorted(starts)
+
+
+def test_preprocess_fixtures(preprocessed):
+    # image_ops.rs:805-1008: preprocess_image(img55.jpg) == preprocessed_img55.png.  The JPEG
+    # was decoded with libjpeg instead of jpeg-decoder 0.1.20, so equality holds to decoder
+    # noise: >= 95 % of pixels exact, max |diff| 2; dims and adjust exact.
+    for name, adj, rows in (("img55", (800 / 300, 533 / 200), 533), ("img545", (537 / 184, 800 / 274), 800)):
+        out, ax, ay = pp.preprocess(preprocessed["src_" + name], 800, 800)
+        assert (ax, ay) == adj
+        exp = preprocessed["pre_" + name]
+        d = np.abs(out.astype(int) - exp.astype(int))
+        assert d.max() <= 2 and (d == 0).mean() >= 0.95
+        # zero padding is top-left aligned and exact
+        pad = exp == 0
+        assert (out[rows:, :] == 0).all() and (exp[rows:, :] == 0).all()
+
+
+def test_resize_identity_and_dims():
+    rng = np.random.default_rng(0)
+    rgba = rng.integers(0, 256, size=(800, 800, 4), dtype=np.uint8)
+    out, ax, ay = pp.preprocess(rgba, 800, 800)
+    luma = (np.float32(0.2126) * rgba[..., 0].astype(np.float32) + np.float32(0.7152) * rgba[..., 1].astype(np.float32)
+            + np.float32(0.0722) * rgba[..., 2].astype(np.float32)).astype(np.uint8)
+    assert (ax, ay) == (1.0, 1.0) and (out == luma).all()
+
+
+def test_expand_polygon_properties():
+    # convex square: miter join keeps it a square grown by d = area*2/perimeter
+    sq = [(10, 10), (10, 50), (50, 50), (50, 10)]
+    ex, d = pp.expand_polygon(sq, 2.0, True)
+    assert d == 1600 * 2 / 160
+    assert sorted(map(tuple, ex.tolist())) == sorted([(-10, -10), (-10, 70), (70, 70), (70, -10)])
+    # orientation-independent result
+    ex2 = pp.expand_polygon(sq[::-1], 2.0)
+    assert sorted(map(tuple, ex2.tolist())) == sorted(map(tuple, ex.tolist()))
+    # degenerate (zero area) -> None (reference panics, D11; we drop the candidate)
+    assert pp.expand_polygon([(0, 0), (10, 0), (20, 0), (10, 0)], 2.0) is None
