@@ -1,0 +1,180 @@
+/*
+ * ocrb.h — C ABI of the B200-native text-detection / glyph-recognition hot path.
+ *
+ * This is the drop-in boundary for lazareviczoran/ocr-rs: every entry point replaces one
+ * reference function (cited as file:line into the reference tree) and is what a Rust
+ * `ocrb-sys` crate (cc/bindgen) would bind — see INTEGRATION.md for the Rust side.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every call returns 0 (OCRB_OK) or a negative error code;
+ *     ocrb_last_error() gives the thread-local message.  Nothing throws across the ABI.
+ *   - one ocrb_ctx per (device, stream); one ctx per host thread; no hidden global state.
+ *   - every data pointer may be HOST memory (pageable or pinned) or DEVICE memory on the
+ *     ctx's device; the library inspects the pointer (cudaPointerGetAttributes) and stages
+ *     host buffers itself.  Calls are synchronous with respect to host-visible results.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     OCRB_ERR_CUDA.
+ *   - layouts follow the reference: images / maps are row-major [B][H][W]; points are
+ *     (x, y) pairs; weights are OIHW float32 under the reference's VarStore names
+ *     (SURVEY.md Appendix B).
+ */
+#ifndef OCRB_H
+#define OCRB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCRB_VERSION 100
+
+enum {
+  OCRB_OK = 0,
+  OCRB_ERR_INVALID = -1,   /* bad argument / shape / missing weight name */
+  OCRB_ERR_CUDA = -2,      /* CUDA runtime or driver error, or no device */
+  OCRB_ERR_CAPACITY = -3,  /* caller-provided output buffer too small */
+  OCRB_ERR_INTERNAL = -4
+};
+
+/* arithmetic mode of the detector (north_star tolerances: FP32 1e-4, BF16 1e-2) */
+enum { OCRB_MODE_FP32 = 0, OCRB_MODE_BF16 = 1 };
+/* element type of detector input images */
+enum { OCRB_U8 = 0, OCRB_F32 = 1 };
+
+typedef struct ocrb_ctx ocrb_ctx;
+typedef struct ocrb_det ocrb_det;
+typedef struct ocrb_rec ocrb_rec;
+typedef struct ocrb_polygons ocrb_polygons;
+
+/* ---- context ------------------------------------------------------------------------
+ * replaces the process-global `DEVICE` (main.rs:26-28) with an explicit handle */
+int ocrb_version(void);
+const char *ocrb_last_error(void);
+int ocrb_device_count(int *count);
+int ocrb_ctx_create(int device, ocrb_ctx **out);
+int ocrb_ctx_destroy(ocrb_ctx *ctx);
+int ocrb_ctx_synchronize(ocrb_ctx *ctx);
+void *ocrb_ctx_stream(ocrb_ctx *ctx); /* cudaStream_t the ctx launches on */
+int ocrb_ctx_device(ocrb_ctx *ctx);
+/* number of kernels this ctx has launched since creation (bench.py "gpu_launches") */
+int64_t ocrb_ctx_launch_count(ocrb_ctx *ctx);
+
+/* ---- image_ops ----------------------------------------------------------------------
+ * image_ops::preprocess_image (image_ops.rs:188-220) minus the file decode:
+ * RGBA8 [src_h][src_w][4] -> aspect-preserving Triangle resize (image 0.23.11) -> Rec.709
+ * luma (truncating) -> zero-padded top-left into [H][W] u8; adjust = resized / original. */
+int ocrb_resize_dims(int src_w, int src_h, int W, int H, int *resized_w, int *resized_h);
+int ocrb_preprocess_rgba(ocrb_ctx *ctx, const uint8_t *rgba, int src_w, int src_h, int W, int H,
+                         uint8_t *out_gray, double *adjust_x, double *adjust_y);
+/* image_ops::convert_image_to_tensor + to_kind(Float) (image_ops.rs:350-364,
+ * text_detection/mod.rs:46-49): u8 -> f32, no scaling. */
+int ocrb_convert_image_to_tensor(ocrb_ctx *ctx, const uint8_t *image, int64_t n, float *out);
+/* image_ops::convert_tensor_to_image (image_ops.rs:367-381): f32 -> u8 by truncation
+ * (to_kind(Uint8)); `scale` is applied first in f32 (mod.rs:57 uses 255). */
+int ocrb_convert_tensor_to_image(ocrb_ctx *ctx, const float *tensor, int64_t n, float scale, uint8_t *out);
+/* image_ops::load_image_as_tensor (image_ops.rs:73-85) minus the decode: u8 -> f32 / 255 */
+int ocrb_load_image_as_tensor(ocrb_ctx *ctx, const uint8_t *luma, int64_t n, float *out);
+
+/* ---- text_detection::model ----------------------------------------------------------
+ * resnet18(&vs.root()) + vs.load(file) (model.rs:65-156, text_detection/mod.rs:35-44):
+ * takes the 121 named OIHW float32 tensors; batch-norm is folded
+ * internally.  numel[i] is checked against the shape the name implies. */
+int ocrb_det_create(ocrb_ctx *ctx, int n_tensors, const char *const *names,
+                    const float *const *data, const int64_t *numel, int mode, ocrb_det **out);
+int ocrb_det_destroy(ocrb_det *det);
+/* net.forward_t(images.view(B,1,H,W), false) (text_detection/mod.rs:52-54, :196-197).
+ * images: [B][H][W] u8 or f32 raw grey levels 0..255 (no normalisation).
+ * H and W must be multiples of 32 (model.rs:126-137).  prob: [B][H][W] f32. */
+int ocrb_det_forward(ocrb_det *det, const void *images, int dtype, int B, int H, int W, float *prob);
+/* test hook: copies an intermediate feature map (NCHW f32) out of the last forward.
+ * name in {"stem","x1","x2","x3","x4","fuse","bin1"}; numel must match. */
+int ocrb_det_tap(ocrb_det *det, const char *name, float *out, int64_t numel);
+
+/* ---- text_detection::metrics --------------------------------------------------------
+ * binarize (metrics.rs:129-131): out = pred > (float)thresh, u8 {0,1}. */
+int ocrb_binarize(ocrb_ctx *ctx, const float *pred, int64_t n, double thresh, uint8_t *out);
+/* box_score_fast (metrics.rs:150-184): pred is [dim_m2][dim_m1] f32; xy = n_pts (x,y) u32-range
+ * points.  The reference's swapped w/h clamps are kept literally. */
+int ocrb_box_score_fast(ocrb_ctx *ctx, const float *pred, int dim_m2, int dim_m1,
+                        const int32_t *xy, int n_pts, double *score);
+/* get_min_area_bounding_box (metrics.rs:133-148): box_xy receives 4 (x,y) corners */
+int ocrb_min_area_bounding_box(ocrb_ctx *ctx, const int32_t *xy, int n_pts, int32_t *box_xy, double *sside);
+/* polygon::expand_polygon (polygon.rs:51-56). *n_out = 0 means None. */
+int ocrb_expand_polygon(ocrb_ctx *ctx, const int32_t *xy, int n_pts, double factor,
+                        int32_t *out_xy, int out_cap_pts, int *n_out);
+
+typedef struct ocrb_postproc_params {
+  double thresh;        /* 0.6  metrics.rs:38  */
+  double box_thresh;    /* 0.7  metrics.rs:64  */
+  double min_size;      /* 5.0  metrics.rs:66  */
+  double unclip_factor; /* 2.0  metrics.rs:103 */
+} ocrb_postproc_params;
+void ocrb_postproc_default_params(ocrb_postproc_params *p);
+
+/* get_boxes_and_box_scores (metrics.rs:37-56): pred [B][H][W] f32 (the reference's
+ * [B,1,H,W]), adjust [B][2] f64.  params == NULL selects the reference constants.
+ * The result handle owns host memory; free with ocrb_polygons_free. */
+int ocrb_get_boxes_and_box_scores(ocrb_ctx *ctx, const float *pred, const double *adjust,
+                                  int B, int H, int W, const ocrb_postproc_params *params,
+                                  ocrb_polygons **out);
+/* get_polygons_from_bitmap (metrics.rs:58-127): one image, caller-provided bitmap */
+int ocrb_get_polygons_from_bitmap(ocrb_ctx *ctx, const float *pred, const uint8_t *bitmap,
+                                  const double *adjust, int H, int W,
+                                  const ocrb_postproc_params *params, ocrb_polygons **out);
+/* PolygonScores accessors (metrics.rs:32-35).  Polygons of image b are
+ * [image_offsets[b], image_offsets[b+1]); polygon p owns points
+ * [point_offsets[p], point_offsets[p+1]) of xy (u32 x,y pairs); scores[p] is f64. */
+int ocrb_polygons_num_images(const ocrb_polygons *p);
+const int64_t *ocrb_polygons_image_offsets(const ocrb_polygons *p);
+const int64_t *ocrb_polygons_point_offsets(const ocrb_polygons *p);
+const uint32_t *ocrb_polygons_xy(const ocrb_polygons *p);
+const double *ocrb_polygons_scores(const ocrb_polygons *p);
+/* per image: contours, >=4 DP points, >= box_thresh, kept, dropped (empty offset, D11) */
+const int64_t *ocrb_polygons_stats(const ocrb_polygons *p);
+void ocrb_polygons_free(ocrb_polygons *p);
+
+/* fine-grained test hooks of the contour stage (imageproc find_contours at
+ * metrics.rs:78-81 and approximate_polygon_dp at :87-95) */
+/* 8-connected foreground labels, canonical raster-order numbering 1..n, 0 = background */
+int ocrb_ccl_labels(ocrb_ctx *ctx, const uint8_t *bitmap, int B, int H, int W, int32_t *labels, int32_t *n_components);
+/* all border chains of one bitmap, in the reference's order.  chain c owns points
+ * [offsets[c], offsets[c+1]) of xy; types[c] = 0 outer / 1 hole.  Pass NULL outputs with
+ * zero capacities to query sizes through n_contours / n_points. */
+int ocrb_find_contours(ocrb_ctx *ctx, const uint8_t *bitmap, int H, int W,
+                       int64_t *offsets, uint8_t *types, int64_t contour_cap,
+                       int32_t *xy, int64_t point_cap, int64_t *n_contours, int64_t *n_points);
+/* eps = 0.01 * arc_length (0 -> 0.01), DP, duplicated last point dropped (metrics.rs:87-95) */
+int ocrb_approx_polygon(ocrb_ctx *ctx, const int32_t *chain_xy, int64_t n_pts,
+                        int32_t *out_xy, int64_t out_cap_pts, int64_t *n_out);
+
+/* ---- char_recognition ---------------------------------------------------------------
+ * Net::new + vs.load (char_recognition/model.rs:12-25, mod.rs:43-45).  Names: canonical
+ * "conv1.weight" ... "fc2.bias" or the de-duplicated VarStore names. */
+int ocrb_rec_create(ocrb_ctx *ctx, int n_tensors, const char *const *names,
+                    const float *const *data, const int64_t *numel, ocrb_rec **out);
+int ocrb_rec_destroy(ocrb_rec *rec);
+/* Net::forward_t(xs, false) + softmax(-1, Double) + topk(1) (model.rs:27-39, mod.rs:53-56,
+ * utils.rs:28-43).  glyphs: [B][784] f32 in [0,1].  Any of logits [B][62] f32,
+ * argmax [B] i32, prob [B] f64 may be NULL. */
+int ocrb_rec_forward(ocrb_rec *rec, const float *glyphs, int B, float *logits, int32_t *argmax, double *prob);
+/* same on raw u8 glyphs (load_image_as_tensor's /255 fused in) */
+int ocrb_rec_forward_u8(ocrb_rec *rec, const uint8_t *glyphs, int B, float *logits, int32_t *argmax, double *prob);
+/* utils::VALUES (utils.rs:7): class index -> character */
+char ocrb_class_to_char(int cls);
+
+/* ---- pipeline -----------------------------------------------------------------------
+ * run_text_detection's device part for a batch (text_detection/mod.rs:46-67, :188-204):
+ * images u8 [B][H][W] -> detector -> post-processing; plus glyph recognition of
+ * `n_glyphs` 28x28 u8 crops in the same call (the reference has no crop glue).
+ * Host pointers are staged through pinned memory; result as above; argmax may be NULL. */
+int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, const double *adjust,
+                              int B, int H, int W, const ocrb_postproc_params *params,
+                              const uint8_t *glyphs, int n_glyphs, int32_t *glyph_argmax,
+                              ocrb_polygons **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCRB_H */

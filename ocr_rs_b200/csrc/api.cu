@@ -1,0 +1,195 @@
+// C ABI: context, error reporting and the image_ops / binarize / CCL entry points.
+// (detector: detector.cu, recognition: rec.cu, post-processing: postproc.cu)
+#include "common.cuh"
+
+namespace ocrb {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+int launch_binarize(ocrb_ctx *, const float *, int64_t, float, uint8_t *);
+int launch_u8_to_f32(ocrb_ctx *, const uint8_t *, int64_t, float, float *);
+int launch_f32_to_u8(ocrb_ctx *, const float *, int64_t, float, uint8_t *);
+int launch_preprocess(ocrb_ctx *, const uint8_t *, int, int, int, int, int, int, uint8_t *, uint8_t *);
+int ccl_canonical_labels(ocrb_ctx *, const uint8_t *, int, int, int, int *, int *);
+void free_pp(ocrb_ctx *);
+
+}  // namespace ocrb
+
+using namespace ocrb;
+
+extern "C" {
+
+int ocrb_version(void) { return OCRB_VERSION; }
+const char *ocrb_last_error(void) { return g_last_error.c_str(); }
+
+int ocrb_device_count(int *count) {
+  OCRB_REQUIRE(count, "null argument");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *count = 0;
+    set_error("cudaGetDeviceCount -> %s", cudaGetErrorString(e));
+    return OCRB_ERR_CUDA;
+  }
+  *count = n;
+  return OCRB_OK;
+}
+
+int ocrb_ctx_create(int device, ocrb_ctx **out) {
+  OCRB_REQUIRE(out, "null argument");
+  int n = 0;
+  OCRB_TRY(ocrb_device_count(&n));
+  if (n <= 0) {
+    set_error("no CUDA device: libocrb has no CPU fallback");
+    return OCRB_ERR_CUDA;
+  }
+  OCRB_REQUIRE(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+  OCRB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  OCRB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return OCRB_ERR_CUDA;
+  }
+  ocrb_ctx *ctx = new ocrb_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    set_error("cudaStreamCreate -> %s", cudaGetErrorString(e));
+    return OCRB_ERR_CUDA;
+  }
+  *out = ctx;
+  return OCRB_OK;
+}
+
+int ocrb_ctx_destroy(ocrb_ctx *ctx) {
+  if (!ctx) return OCRB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_pp(ctx);
+  for (auto &b : ctx->stage) b.release();
+  for (auto &b : ctx->pin) b.release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return OCRB_OK;
+}
+
+int ocrb_ctx_synchronize(ocrb_ctx *ctx) {
+  OCRB_REQUIRE(ctx, "null ctx");
+  return sync(ctx);
+}
+void *ocrb_ctx_stream(ocrb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int ocrb_ctx_device(ocrb_ctx *ctx) { return ctx ? ctx->device : -1; }
+int64_t ocrb_ctx_launch_count(ocrb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- image_ops -------------------------------------------------------------------------
+int ocrb_resize_dims(int sw, int sh, int W, int H, int *rw, int *rh) {
+  OCRB_REQUIRE(rw && rh && sw > 0 && sh > 0 && W > 0 && H > 0, "bad argument");
+  // image 0.23.11 resize_dimensions(fill = false): integer arithmetic
+  uint64_t ratio = (uint64_t)sw * (uint64_t)H, nratio = (uint64_t)W * (uint64_t)sh;
+  bool use_width = nratio <= ratio;
+  uint64_t inter = use_width ? (uint64_t)sh * (uint64_t)W / (uint64_t)sw : (uint64_t)sw * (uint64_t)H / (uint64_t)sh;
+  if (inter < 1) inter = 1;
+  if (use_width) { *rw = W; *rh = (int)inter; } else { *rw = (int)inter; *rh = H; }
+  return OCRB_OK;
+}
+
+int ocrb_preprocess_rgba(ocrb_ctx *ctx, const uint8_t *rgba, int sw, int sh, int W, int H, uint8_t *out_gray,
+                         double *adjust_x, double *adjust_y) {
+  OCRB_REQUIRE(ctx && rgba && out_gray && adjust_x && adjust_y, "null argument");
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  int rw, rh;
+  OCRB_TRY(ocrb_resize_dims(sw, sh, W, H, &rw, &rh));
+  *adjust_x = (double)rw / (double)sw;  // image_ops.rs:201-202
+  *adjust_y = (double)rh / (double)sh;
+  const void *src = nullptr;
+  void *dst = nullptr;
+  OCRB_TRY(to_device(ctx, 0, rgba, (size_t)sw * sh * 4, &src));
+  OCRB_TRY(out_device(ctx, 1, out_gray, (size_t)W * H, &dst));
+  OCRB_TRY(ctx->stage[2].reserve((size_t)sw * rh * 4));
+  OCRB_TRY(launch_preprocess(ctx, (const uint8_t *)src, sw, sh, rw, rh, W, H, ctx->stage[2].as<uint8_t>(), (uint8_t *)dst));
+  OCRB_TRY(finish_output(ctx, out_gray, dst, (size_t)W * H));
+  return sync(ctx);
+}
+
+int ocrb_convert_image_to_tensor(ocrb_ctx *ctx, const uint8_t *image, int64_t n, float *out) {
+  OCRB_REQUIRE(ctx && image && out && n >= 0, "bad argument");
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  const void *src = nullptr;
+  void *dst = nullptr;
+  OCRB_TRY(to_device(ctx, 0, image, (size_t)n, &src));
+  OCRB_TRY(out_device(ctx, 1, out, (size_t)n * 4, &dst));
+  OCRB_TRY(launch_u8_to_f32(ctx, (const uint8_t *)src, n, 1.0f, (float *)dst));
+  OCRB_TRY(finish_output(ctx, out, dst, (size_t)n * 4));
+  return sync(ctx);
+}
+
+int ocrb_load_image_as_tensor(ocrb_ctx *ctx, const uint8_t *luma, int64_t n, float *out) {
+  OCRB_REQUIRE(ctx && luma && out && n >= 0, "bad argument");
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  const void *src = nullptr;
+  void *dst = nullptr;
+  OCRB_TRY(to_device(ctx, 0, luma, (size_t)n, &src));
+  OCRB_TRY(out_device(ctx, 1, out, (size_t)n * 4, &dst));
+  OCRB_TRY(launch_u8_to_f32(ctx, (const uint8_t *)src, n, 255.0f, (float *)dst));
+  OCRB_TRY(finish_output(ctx, out, dst, (size_t)n * 4));
+  return sync(ctx);
+}
+
+int ocrb_convert_tensor_to_image(ocrb_ctx *ctx, const float *tensor, int64_t n, float scale, uint8_t *out) {
+  OCRB_REQUIRE(ctx && tensor && out && n >= 0, "bad argument");
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  const void *src = nullptr;
+  void *dst = nullptr;
+  OCRB_TRY(to_device(ctx, 0, tensor, (size_t)n * 4, &src));
+  OCRB_TRY(out_device(ctx, 1, out, (size_t)n, &dst));
+  OCRB_TRY(launch_f32_to_u8(ctx, (const float *)src, n, scale, (uint8_t *)dst));
+  OCRB_TRY(finish_output(ctx, out, dst, (size_t)n));
+  return sync(ctx);
+}
+
+// ---- metrics::binarize -----------------------------------------------------------------
+int ocrb_binarize(ocrb_ctx *ctx, const float *pred, int64_t n, double thresh, uint8_t *out) {
+  OCRB_REQUIRE(ctx && pred && out && n >= 0, "bad argument");
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  const void *src = nullptr;
+  void *dst = nullptr;
+  OCRB_TRY(to_device(ctx, 0, pred, (size_t)n * 4, &src));
+  OCRB_TRY(out_device(ctx, 1, out, (size_t)n, &dst));
+  OCRB_TRY(launch_binarize(ctx, (const float *)src, n, (float)thresh, (uint8_t *)dst));
+  OCRB_TRY(finish_output(ctx, out, dst, (size_t)n));
+  return sync(ctx);
+}
+
+int ocrb_ccl_labels(ocrb_ctx *ctx, const uint8_t *bitmap, int B, int H, int W, int32_t *labels, int32_t *n_components) {
+  OCRB_REQUIRE(ctx && bitmap && labels && B > 0 && H > 0 && W > 0, "bad argument");
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = (int64_t)B * H * W;
+  OCRB_REQUIRE(n < (int64_t)1 << 31, "B*H*W must be < 2^31");
+  const void *src = nullptr;
+  void *dst = nullptr;
+  OCRB_TRY(to_device(ctx, 0, bitmap, (size_t)n, &src));
+  OCRB_TRY(out_device(ctx, 1, labels, (size_t)n * 4, &dst));
+  OCRB_TRY(ccl_canonical_labels(ctx, (const uint8_t *)src, B, H, W, (int *)dst, n_components));
+  OCRB_TRY(finish_output(ctx, labels, dst, (size_t)n * 4));
+  return sync(ctx);
+}
+
+char ocrb_class_to_char(int cls) {
+  static const char *VALUES = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789";  // utils.rs:7
+  return (cls >= 0 && cls < 62) ? VALUES[cls] : '?';
+}
+
+}  // extern "C"

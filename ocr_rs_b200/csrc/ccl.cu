@@ -1,0 +1,208 @@
+// Connected-component labelling of a binary map: ONE union-find over both pixel classes
+// (foreground 8-connected, background 4-connected), block-local in shared memory with
+// warp-level run merges, followed by a global seam-merge pass and a flatten pass.
+//
+// Replaces the sequential raster scan inside imageproc::contours::find_contours
+// (called at metrics.rs:78-81): after flattening, label[i] is the raster-first pixel index
+// of i's component, which is exactly where Suzuki–Abe starts that component's outer border
+// (foreground) or — one pixel to the west — its hole border (background); SURVEY A.1.
+//
+// HBM traffic: reads the u8 bitmap (1 B/px) and writes i32 labels (4 B/px) in the local
+// pass; the seam and flatten passes touch labels again (documented in DESIGN.md).
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace ocrb {
+
+constexpr int CCL_TW = 32;  // tile width  (= warp size: one warp per tile row)
+constexpr int CCL_TH = 32;  // tile height
+
+__device__ __forceinline__ int uf_find(const int *L, int a) {
+  int p = L[a];
+  while (p != a) {
+    a = p;
+    p = L[a];
+  }
+  return a;
+}
+
+__device__ __forceinline__ int uf_find_volatile(volatile int *L, int a) {
+  int p = L[a];
+  while (p != a) {
+    a = p;
+    p = L[a];
+  }
+  return a;
+}
+
+// lock-free union keeping the smaller index as root
+__device__ __forceinline__ void uf_union(int *L, int a, int b) {
+  for (;;) {
+    a = uf_find_volatile(L, a);
+    b = uf_find_volatile(L, b);
+    if (a == b) return;
+    if (a > b) { int t = a; a = b; b = t; }
+    int old = atomicMin(&L[b], a);
+    if (old == b) return;
+    b = old;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// pass 1: tile-local.  1024 threads = 32 warps; warp r owns tile row r.
+// Warp-level merge: every pixel starts labelled with the first pixel of its horizontal run
+// (ballot + bit scan, no atomics).  Vertical / diagonal links are then united in shared
+// memory.  Output: parent = image-local linear index of the tile-local root.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CCL_TW *CCL_TH) ccl_local_kernel(const uint8_t *__restrict__ bitmap, int H, int W,
+                                                                  int tiles_x, int tiles_y, int *__restrict__ labels) {
+  __shared__ int L[CCL_TW * CCL_TH];
+  __shared__ uint32_t rowbits[CCL_TH + 1];
+  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int tile = blockIdx.x % (tiles_x * tiles_y), b = blockIdx.x / (tiles_x * tiles_y);
+  const int tx = tile % tiles_x, ty = tile / tiles_x;
+  const int x = tx * CCL_TW + lane, y = ty * CCL_TH + r;
+  const bool inside = x < W && y < H;
+  const uint8_t *bm = bitmap + (int64_t)b * H * W;
+  const int fg = inside ? (bm[(int64_t)y * W + x] != 0) : 0;
+  const uint32_t valid = __ballot_sync(0xffffffffu, inside);
+  const uint32_t bits = __ballot_sync(0xffffffffu, fg);
+  // run start of this lane within its row: pixels of the same class contiguous to the left
+  uint32_t same = fg ? bits : (~bits & valid);
+  uint32_t below = (~same) & ((1u << lane) - 1u);  // lanes to the left that break the run
+  int run_start = below ? (32 - __clz(below)) : 0;
+  L[threadIdx.x] = r * CCL_TW + run_start;
+  if (lane == 0) rowbits[r] = bits;
+  __syncthreads();
+  if (inside && r > 0) {
+    uint32_t up = rowbits[r - 1];
+    int n_fg = (up >> lane) & 1;
+    if (fg) {
+      if (n_fg) {
+        uf_union(L, threadIdx.x, threadIdx.x - CCL_TW);
+      } else {
+        if (lane > 0 && ((up >> (lane - 1)) & 1)) uf_union(L, threadIdx.x, threadIdx.x - CCL_TW - 1);
+        if (lane < 31 && ((up >> (lane + 1)) & 1)) uf_union(L, threadIdx.x, threadIdx.x - CCL_TW + 1);
+      }
+    } else if (!n_fg) {
+      uf_union(L, threadIdx.x, threadIdx.x - CCL_TW);
+    }
+  }
+  __syncthreads();
+  if (inside) {
+    int root = uf_find(L, threadIdx.x);
+    int rx = tx * CCL_TW + (root & 31), ry = ty * CCL_TH + (root >> 5);
+    labels[(int64_t)b * H * W + (int64_t)y * W + x] = ry * W + rx;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// pass 2: seams.  A pixel whose W / NW / N / NE neighbour lies in another tile unites with
+// it in global memory (same adjacency rules as pass 1).
+// ---------------------------------------------------------------------------------------
+__global__ void ccl_seam_kernel(const uint8_t *__restrict__ bitmap, int H, int W, int B, int *__restrict__ labels) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t HW = (int64_t)H * W;
+  if (idx >= HW * B) return;
+  int b = (int)(idx / HW);
+  int i = (int)(idx % HW);
+  int x = i % W, y = i / W;
+  bool on_left = (x % CCL_TW) == 0, on_right = (x % CCL_TW) == CCL_TW - 1, on_top = (y % CCL_TH) == 0;
+  if (!on_left && !on_top && !on_right) return;
+  const uint8_t *bm = bitmap + b * HW;
+  int *L = labels + b * HW;
+  int fg = bm[i] != 0;
+  if (on_left && x > 0 && (bm[i - 1] != 0) == fg) uf_union(L, i, i - 1);
+  if (y > 0) {
+    int n_fg = bm[i - W] != 0;
+    if (on_top && n_fg == fg) uf_union(L, i, i - W);
+    if (fg && !n_fg) {
+      if (x > 0 && (on_top || on_left) && bm[i - W - 1] != 0) uf_union(L, i, i - W - 1);
+      if (x + 1 < W && (on_top || on_right) && bm[i - W + 1] != 0) uf_union(L, i, i - W + 1);
+    }
+  }
+}
+
+// pass 3: flatten (every pixel points at its root = raster-first pixel of its component)
+__global__ void ccl_flatten_kernel(int H, int W, int B, int *__restrict__ labels) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t HW = (int64_t)H * W;
+  if (idx >= HW * B) return;
+  int b = (int)(idx / HW);
+  int i = (int)(idx % HW);
+  int *L = labels + b * HW;
+  int root = uf_find_volatile(L, i);
+  L[i] = root;
+}
+
+int launch_ccl(ocrb_ctx *ctx, const uint8_t *bitmap, int B, int H, int W, int *labels) {
+  int tiles_x = (int)cdiv(W, CCL_TW), tiles_y = (int)cdiv(H, CCL_TH);
+  int64_t blocks = (int64_t)tiles_x * tiles_y * B;
+  ccl_local_kernel<<<(unsigned)blocks, CCL_TW * CCL_TH, 0, ctx->stream>>>(bitmap, H, W, tiles_x, tiles_y, labels);
+  OCRB_TRY(check_launch(ctx, "ccl_local"));
+  int64_t n = (int64_t)B * H * W;
+  ccl_seam_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap, H, W, B, labels);
+  OCRB_TRY(check_launch(ctx, "ccl_seam"));
+  ccl_flatten_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(H, W, B, labels);
+  return check_launch(ctx, "ccl_flatten");
+}
+
+// ---------------------------------------------------------------------------------------
+// test hook: canonical numbering of the foreground components (1..n in raster order of
+// their first pixel, 0 = background) — what scipy.ndimage.label(structure=ones(3,3)) gives.
+// ---------------------------------------------------------------------------------------
+__global__ void ccl_fg_root_flag_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels, int64_t HW,
+                                        int64_t n, uint8_t *__restrict__ flag) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  int i = (int)(idx % HW);
+  flag[idx] = (bitmap[idx] != 0 && labels[idx] == i) ? 1 : 0;
+}
+
+__global__ void ccl_canonical_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels,
+                                     const int *__restrict__ rank, int64_t HW, int64_t n, int *__restrict__ out) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  int64_t b = idx / HW;
+  if (bitmap[idx] == 0) {
+    out[idx] = 0;
+    return;
+  }
+  int64_t root = b * HW + labels[idx];
+  out[idx] = rank[root] - rank[b * HW] + 1;
+}
+
+int ccl_canonical_labels(ocrb_ctx *ctx, const uint8_t *bitmap_dev, int B, int H, int W, int *labels_out_dev,
+                         int *n_components_host) {
+  int64_t n = (int64_t)B * H * W, HW = (int64_t)H * W;
+  DevBuf lab, flag, rank, scratch;
+  int rc = OCRB_OK;
+  do {
+    if ((rc = lab.reserve(n * 4)) || (rc = flag.reserve(n)) || (rc = rank.reserve((n + 1) * 4)) ||
+        (rc = scratch.reserve(scan_scratch_elems(n) * 4)))
+      break;
+    if ((rc = launch_ccl(ctx, bitmap_dev, B, H, W, lab.as<int>()))) break;
+    ccl_fg_root_flag_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap_dev, lab.as<int>(), HW, n, flag.as<uint8_t>());
+    if ((rc = check_launch(ctx, "ccl_fg_root_flag"))) break;
+    if ((rc = exclusive_scan<uint8_t, int>(ctx, flag.as<uint8_t>(), n, rank.as<int>(), scratch.as<int>()))) break;
+    ccl_canonical_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap_dev, lab.as<int>(), rank.as<int>(), HW, n, labels_out_dev);
+    if ((rc = check_launch(ctx, "ccl_canonical"))) break;
+    if (n_components_host) {
+      std::vector<int> r(B + 1);
+      for (int b = 0; b <= B && rc == OCRB_OK; ++b) {
+        cudaError_t e = cudaMemcpyAsync(&r[b], rank.as<int>() + (int64_t)b * HW, 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) { set_error("memcpy rank: %s", cudaGetErrorString(e)); rc = OCRB_ERR_CUDA; }
+      }
+      if (rc) break;
+      if ((rc = sync(ctx))) break;
+      for (int b = 0; b < B; ++b) n_components_host[b] = r[b + 1] - r[b];
+    } else {
+      rc = sync(ctx);
+    }
+  } while (0);
+  cudaStreamSynchronize(ctx->stream);
+  lab.release(); flag.release(); rank.release(); scratch.release();
+  return rc;
+}
+
+}  // namespace ocrb

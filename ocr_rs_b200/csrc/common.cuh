@@ -1,0 +1,170 @@
+// Shared host/device plumbing for libocrb (context, error reporting, workspace buffers).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ocrb.h"
+
+namespace ocrb {
+
+void set_error(const char *fmt, ...);
+
+#define OCRB_CUDA(call)                                                                    \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      ocrb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return OCRB_ERR_CUDA;                                                                \
+    }                                                                                      \
+  } while (0)
+
+#define OCRB_TRY(call)            \
+  do {                            \
+    int rc__ = (call);            \
+    if (rc__ != OCRB_OK) return rc__; \
+  } while (0)
+
+#define OCRB_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      ocrb::set_error(__VA_ARGS__);    \
+      return OCRB_ERR_INVALID;         \
+    }                                  \
+  } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return OCRB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e));
+      return OCRB_ERR_CUDA;
+    }
+    cap = want;
+    return OCRB_OK;
+  }
+  template <class T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// grow-only pinned host buffer
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return OCRB_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) {
+      set_error("cudaMallocHost(%zu) -> %s", want, cudaGetErrorString(e));
+      return OCRB_ERR_CUDA;
+    }
+    cap = want;
+    return OCRB_OK;
+  }
+  template <class T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct PostprocWorkspace;  // postproc.cu
+
+}  // namespace ocrb
+
+struct ocrb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  // staging for host-pointer arguments (indexed slots so one call can stage several)
+  ocrb::DevBuf stage[6];
+  ocrb::PinBuf pin[3];
+  ocrb::PostprocWorkspace *pp = nullptr;
+};
+
+namespace ocrb {
+
+inline bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Returns a device view of `p` (nbytes).  Host memory is copied into ctx->stage[slot].
+inline int to_device(ocrb_ctx *ctx, int slot, const void *p, size_t nbytes, const void **out) {
+  if (is_device_ptr(p)) {
+    *out = p;
+    return OCRB_OK;
+  }
+  OCRB_TRY(ctx->stage[slot].reserve(nbytes));
+  OCRB_CUDA(cudaMemcpyAsync(ctx->stage[slot].p, p, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  *out = ctx->stage[slot].p;
+  return OCRB_OK;
+}
+
+// Returns a device buffer to write results into; if `p` is host memory the buffer is
+// ctx->stage[slot] and finish_output() copies it back.
+inline int out_device(ocrb_ctx *ctx, int slot, void *p, size_t nbytes, void **out) {
+  if (is_device_ptr(p)) {
+    *out = p;
+    return OCRB_OK;
+  }
+  OCRB_TRY(ctx->stage[slot].reserve(nbytes));
+  *out = ctx->stage[slot].p;
+  return OCRB_OK;
+}
+
+inline int finish_output(ocrb_ctx *ctx, void *user, const void *dev, size_t nbytes) {
+  if (user != dev) OCRB_CUDA(cudaMemcpyAsync(user, dev, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return OCRB_OK;
+}
+
+inline int sync(ocrb_ctx *ctx) {
+  OCRB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OCRB_OK;
+}
+
+inline int check_launch(ocrb_ctx *ctx, const char *what) {
+  ctx->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("kernel launch %s -> %s", what, cudaGetErrorString(e));
+    return OCRB_ERR_CUDA;
+  }
+  return OCRB_OK;
+}
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace ocrb

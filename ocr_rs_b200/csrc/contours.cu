@@ -1,0 +1,352 @@
+// Border following on the GPU: where every Suzuki–Abe border of imageproc::find_contours
+// (metrics.rs:78-81) starts, the chains themselves, and their Douglas–Peucker polygons
+// (imageproc::approximate_polygon_dp at metrics.rs:87-95).
+//
+// The sequential sign-marking scan is replaced by facts derived from the component labels
+// (ccl.cu) — verified against the sequential algorithm on random images (tests/):
+//   * a foreground component whose raster-first pixel p0 has x > 0 gets ONE outer border,
+//     started at p0 coming from the west;
+//   * every background component that does not reach the image frame gets ONE hole border,
+//     started at the pixel west of its raster-first pixel, coming from the east;
+//   * a foreground component whose raster-first pixel lies in column 0 ("left-anchored":
+//     imageproc's `x > 0` guard suppresses the outer start there) is replayed sequentially,
+//     crack by crack, by one warp: the marks of the original algorithm reduce to "which
+//     borders of this component have been traced so far";
+//   * a chain is a pure function of (bitmap, start pixel, start direction).
+// Contours are emitted in raster order of their start pixel, like the reference.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace ocrb {
+
+enum : uint8_t { START_NONE = 0, START_OUTER = 1, START_HOLE = 2 };
+
+// ---------------------------------------------------------------------------------------
+// per-component facts: background components reaching the frame; bounding boxes of
+// left-anchored foreground components (keyed by the row of their root, which is in col 0)
+// ---------------------------------------------------------------------------------------
+__global__ void contour_props_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels, int H, int W,
+                                     int B, uint8_t *__restrict__ bg_open, int4 *__restrict__ anchored_bbox) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t HW = (int64_t)H * W;
+  if (idx >= HW * B) return;
+  int64_t b = idx / HW;
+  int i = (int)(idx % HW);
+  int x = i % W, y = i / W;
+  int root = labels[idx];
+  if (bitmap[idx] == 0) {
+    if (x == 0 || y == 0 || x == W - 1 || y == H - 1) bg_open[b * HW + root] = 1;
+  } else if (root % W == 0) {
+    int4 *bb = anchored_bbox + b * H + root / W;
+    atomicMin(&bb->x, x);
+    atomicMax(&bb->y, x);
+    atomicMin(&bb->z, y);
+    atomicMax(&bb->w, y);
+  }
+}
+
+__global__ void contour_bbox_init_kernel(int4 *bbox, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bbox[i] = make_int4(INT32_MAX, -1, INT32_MAX, -1);
+}
+
+// closed-form starts for ordinary components
+__global__ void contour_start_flags_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels, int H, int W,
+                                           int B, const uint8_t *__restrict__ bg_open, uint8_t *__restrict__ flags) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t HW = (int64_t)H * W;
+  if (idx >= HW * B) return;
+  int i = (int)(idx % HW);
+  int x = i % W;
+  uint8_t f = START_NONE;
+  if (bitmap[idx] != 0) {
+    int root = labels[idx];
+    if (root % W != 0) {  // not left-anchored
+      if (root == i) {
+        f = START_OUTER;  // x > 0 here because root % W != 0
+      } else if (x + 1 < W && bitmap[idx + 1] == 0 && labels[idx + 1] == i + 1 && !bg_open[idx + 1]) {
+        f = START_HOLE;
+      }
+    }
+  }
+  flags[idx] = f;
+}
+
+// sequential replay for left-anchored components; one warp per image row that holds a root
+// in column 0.  `hole_traced` is a zero-initialised byte per pixel (indexed by bg root).
+__global__ void __launch_bounds__(128) contour_anchored_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels,
+                                                               int H, int W, int B, const uint8_t *__restrict__ bg_open,
+                                                               const int4 *__restrict__ anchored_bbox,
+                                                               uint8_t *__restrict__ hole_traced, uint8_t *__restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (int64_t)B * H) return;
+  int64_t b = wid / H;
+  int row = (int)(wid % H);
+  int64_t HW = (int64_t)H * W;
+  const uint8_t *bm = bitmap + b * HW;
+  const int *L = labels + b * HW;
+  const uint8_t *open = bg_open + b * HW;
+  volatile uint8_t *traced = hole_traced + b * HW;
+  uint8_t *fl = flags + b * HW;
+  const int F = row * W;
+  if (bm[F] == 0 || L[F] != F) return;  // warp-uniform
+  int4 bb = anchored_bbox[b * H + row];
+  bool traced_inf = false;
+  for (int y = bb.z; y <= bb.w; ++y) {
+    for (int xb = bb.x; xb <= bb.y; xb += 32) {
+      int x = xb + lane;
+      bool in_f = x <= bb.y && bm[y * W + x] != 0 && L[y * W + x] == F;
+      bool wcr = in_f && x > 0 && bm[y * W + x - 1] == 0;
+      bool ecr = in_f && x + 1 < W && bm[y * W + x + 1] == 0;
+      uint32_t cand = __ballot_sync(0xffffffffu, wcr || ecr);
+      uint32_t wmask = __ballot_sync(0xffffffffu, wcr);
+      uint32_t emask = __ballot_sync(0xffffffffu, ecr);
+      while (cand) {
+        int l = __ffs(cand) - 1;
+        cand &= cand - 1;
+        int qx = xb + l, q = y * W + qx;
+        // labels of the 4-neighbour background pixels (-1 = outer background / out of image)
+        int lab[4];
+        const int dx[4] = {-1, 1, 0, 0}, dy[4] = {0, 0, -1, 1};
+        bool visited = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          int nx = qx + dx[k], ny = y + dy[k];
+          lab[k] = -2;  // not background
+          if (nx < 0 || ny < 0 || nx >= W || ny >= H) lab[k] = -1;
+          else if (bm[ny * W + nx] == 0) {
+            int r = L[ny * W + nx];
+            lab[k] = open[r] ? -1 : r;
+          }
+          if (lab[k] == -1) visited |= traced_inf;
+          else if (lab[k] >= 0) visited |= (traced[lab[k]] != 0);
+        }
+        bool has_w = (wmask >> l) & 1, has_e = (emask >> l) & 1;
+        if (has_w && !visited) {
+          if (lab[0] == -1) traced_inf = true;
+          else if (lane == 0) traced[lab[0]] = 1;
+          if (lane == 0) fl[q] = START_OUTER;
+        } else if (has_e) {
+          bool e_traced = lab[1] == -1 ? traced_inf : (traced[lab[1]] != 0);
+          if (!e_traced) {
+            if (lab[1] == -1) traced_inf = true;
+            else if (lane == 0) traced[lab[1]] = 1;
+            if (lane == 0) fl[q] = START_HOLE;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// flags -> contour records (start pixel as batch-global index, kind)
+__global__ void contour_records_kernel(const uint8_t *__restrict__ flags, const int *__restrict__ offs, int64_t n,
+                                       int64_t *__restrict__ start_idx, uint8_t *__restrict__ kind) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  uint8_t f = flags[idx];
+  if (f) {
+    int c = offs[idx];
+    start_idx[c] = idx;
+    kind[c] = f - 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// chain tracing.  Neighbour ring, clockwise on screen: W NW N NE E SE S SW.
+// ---------------------------------------------------------------------------------------
+// nibble tables: dx+1 for d=0..7 = {0,0,1,2,2,2,1,0}; dy+1 = {1,0,0,0,1,2,2,2}
+__device__ __forceinline__ void ring(int d, int &dx, int &dy) {
+  dx = (int)((0x01222100u >> (d * 4)) & 0xf) - 1;
+  dy = (int)((0x22210001u >> (d * 4)) & 0xf) - 1;
+}
+
+struct Tracer {
+  const uint8_t *bm;
+  int W, H;
+  __device__ __forceinline__ bool nz(int x, int y) const {
+    return x >= 0 && y >= 0 && x < W && y < H && bm[y * W + x] != 0;
+  }
+};
+
+// Walks one border; calls emit(x, y) for every chain point; returns the chain length.
+template <class Emit>
+__device__ __forceinline__ int64_t trace_border(const Tracer &t, int sx, int sy, int from, Emit emit) {
+  int d1 = -1;
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    int d = (from + k) & 7, dx, dy;
+    ring(d, dx, dy);
+    if (t.nz(sx + dx, sy + dy)) { d1 = d; break; }
+  }
+  if (d1 < 0) {
+    emit(sx, sy);
+    return 1;
+  }
+  int dx, dy;
+  ring(d1, dx, dy);
+  const int p1x = sx + dx, p1y = sy + dy;
+  int p3x = sx, p3y = sy;
+  int dp2 = d1;  // direction from p3 to p2
+  int64_t n = 0;
+  for (;;) {
+    emit(p3x, p3y);
+    ++n;
+    int d4 = dp2;
+#pragma unroll 1
+    for (int k = 1; k <= 8; ++k) {
+      int d = (dp2 - k) & 7;
+      ring(d, dx, dy);
+      if (t.nz(p3x + dx, p3y + dy)) { d4 = d; break; }
+    }
+    ring(d4, dx, dy);
+    int p4x = p3x + dx, p4y = p3y + dy;
+    if (p4x == sx && p4y == sy && p3x == p1x && p3y == p1y) break;
+    // next step: p2 <- p3, p3 <- p4; direction from new p3 back to new p2 is the opposite of d4
+    dp2 = (d4 + 4) & 7;
+    p3x = p4x;
+    p3y = p4y;
+  }
+  return n;
+}
+
+__global__ void trace_count_kernel(const uint8_t *__restrict__ bitmap, int H, int W, const int64_t *__restrict__ start_idx,
+                                   const uint8_t *__restrict__ kind, int64_t n_contours, int *__restrict__ lengths) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_contours) return;
+  int64_t HW = (int64_t)H * W;
+  int64_t g = start_idx[c];
+  int64_t b = g / HW;
+  int i = (int)(g % HW);
+  Tracer t{bitmap + b * HW, W, H};
+  int64_t n = trace_border(t, i % W, i / W, kind[c] ? 4 : 0, [](int, int) {});
+  lengths[c] = (int)n;
+}
+
+__global__ void trace_store_kernel(const uint8_t *__restrict__ bitmap, int H, int W, const int64_t *__restrict__ start_idx,
+                                   const uint8_t *__restrict__ kind, int64_t n_contours,
+                                   const int64_t *__restrict__ chain_off, ushort2 *__restrict__ chain) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_contours) return;
+  int64_t HW = (int64_t)H * W;
+  int64_t g = start_idx[c];
+  int64_t b = g / HW;
+  int i = (int)(g % HW);
+  Tracer t{bitmap + b * HW, W, H};
+  ushort2 *out = chain + chain_off[c];
+  int64_t k = 0;
+  trace_border(t, i % W, i / W, kind[c] ? 4 : 0, [&](int x, int y) { out[k++] = make_ushort2((unsigned short)x, (unsigned short)y); });
+}
+
+// ---------------------------------------------------------------------------------------
+// Douglas–Peucker exactly as imageproc does it, iteratively: the kept points
+// are the left ends of the leaf ranges plus the chain end; closed => the last one is
+// popped; metrics.rs:92-94 pops once more if first == last.  f64 arithmetic, first index
+// of the strictly largest distance, NaN (coincident range ends) never splits.
+// One thread per contour; `stack` shares the chain's arena offsets.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double dist_d(double ax, double ay, double bx, double by) {
+  double dx = ax - bx, dy = ay - by;
+  return sqrt(dx * dx + dy * dy);
+}
+
+__global__ void approx_dp_kernel(const ushort2 *__restrict__ chain, const int64_t *__restrict__ chain_off,
+                                 int64_t n_contours, int *__restrict__ stack, ushort2 *__restrict__ dp_out,
+                                 int *__restrict__ dp_count) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_contours) return;
+  const int64_t off = chain_off[c];
+  const int n = (int)(chain_off[c + 1] - off);
+  const ushort2 *p = chain + off;
+  ushort2 *out = dp_out + off;
+  if (n < 4) {  // cannot yield >= 4 polygon points; the caller's filter drops it
+    dp_count[c] = 0;
+    return;
+  }
+  // arc_length(closed = true)
+  double len = 0.0;
+  for (int i = 0; i + 1 < n; ++i) len += dist_d(p[i].x, p[i].y, p[i + 1].x, p[i + 1].y);
+  if (n > 2) len += dist_d(p[0].x, p[0].y, p[n - 1].x, p[n - 1].y);
+  double eps = 0.01 * len;
+  if (eps == 0.) eps = 0.01;
+  int *st = stack + off;  // holds the pending right ends
+  int sp = 0, m = 0;
+  int lo = 0, hi = n - 1;
+  for (;;) {
+    double x0 = p[lo].x, y0 = p[lo].y, x1 = p[hi].x, y1 = p[hi].y;
+    double a = y0 - y1, bq = x1 - x0, cc = x0 * y1 - x1 * y0;
+    double den = sqrt(a * a + bq * bq);
+    double dmax = 0.0;
+    int index = lo;
+    for (int i = lo + 1; i <= hi; ++i) {
+      double d = fabs(a * (double)p[i].x + bq * (double)p[i].y + cc) / den;
+      if (d > dmax) { index = i; dmax = d; }
+    }
+    if (dmax > eps) {
+      st[sp++] = hi;  // right part [index, hi] waits
+      hi = index;
+      continue;
+    }
+    out[m++] = p[lo];  // leaf range [lo, hi]
+    if (sp == 0) {
+      out[m++] = p[hi];
+      break;
+    }
+    lo = hi;
+    hi = st[--sp];
+  }
+  m -= 1;  // closed => pop
+  if (m > 1 && out[0].x == out[m - 1].x && out[0].y == out[m - 1].y) m -= 1;
+  dp_count[c] = m;
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------
+int launch_contour_starts(ocrb_ctx *ctx, const uint8_t *bitmap, const int *labels, int B, int H, int W,
+                          uint8_t *bg_open /*B*HW, zeroed here*/, uint8_t *hole_traced /*B*HW, zeroed here*/,
+                          int4 *anchored_bbox /*B*H*/, uint8_t *flags /*B*HW*/) {
+  int64_t n = (int64_t)B * H * W;
+  OCRB_CUDA(cudaMemsetAsync(bg_open, 0, n, ctx->stream));
+  OCRB_CUDA(cudaMemsetAsync(hole_traced, 0, n, ctx->stream));
+  contour_bbox_init_kernel<<<(unsigned)cdiv((int64_t)B * H, 256), 256, 0, ctx->stream>>>(anchored_bbox, (int64_t)B * H);
+  OCRB_TRY(check_launch(ctx, "contour_bbox_init"));
+  contour_props_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, anchored_bbox);
+  OCRB_TRY(check_launch(ctx, "contour_props"));
+  contour_start_flags_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, flags);
+  OCRB_TRY(check_launch(ctx, "contour_start_flags"));
+  int64_t warps = (int64_t)B * H;
+  contour_anchored_kernel<<<(unsigned)cdiv(warps * 32, 128), 128, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open,
+                                                                                    anchored_bbox, hole_traced, flags);
+  return check_launch(ctx, "contour_anchored");
+}
+
+int launch_contour_records(ocrb_ctx *ctx, const uint8_t *flags, const int *offs, int64_t n, int64_t *start_idx, uint8_t *kind) {
+  contour_records_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(flags, offs, n, start_idx, kind);
+  return check_launch(ctx, "contour_records");
+}
+
+int launch_trace_count(ocrb_ctx *ctx, const uint8_t *bitmap, int H, int W, const int64_t *start_idx, const uint8_t *kind,
+                       int64_t n_contours, int *lengths) {
+  if (n_contours <= 0) return OCRB_OK;
+  trace_count_kernel<<<(unsigned)cdiv(n_contours, 128), 128, 0, ctx->stream>>>(bitmap, H, W, start_idx, kind, n_contours, lengths);
+  return check_launch(ctx, "trace_count");
+}
+
+int launch_trace_store(ocrb_ctx *ctx, const uint8_t *bitmap, int H, int W, const int64_t *start_idx, const uint8_t *kind,
+                       int64_t n_contours, const int64_t *chain_off, ushort2 *chain) {
+  if (n_contours <= 0) return OCRB_OK;
+  trace_store_kernel<<<(unsigned)cdiv(n_contours, 128), 128, 0, ctx->stream>>>(bitmap, H, W, start_idx, kind, n_contours, chain_off, chain);
+  return check_launch(ctx, "trace_store");
+}
+
+int launch_approx_dp(ocrb_ctx *ctx, const ushort2 *chain, const int64_t *chain_off, int64_t n_contours, int *stack,
+                     ushort2 *dp_out, int *dp_count) {
+  if (n_contours <= 0) return OCRB_OK;
+  approx_dp_kernel<<<(unsigned)cdiv(n_contours, 128), 128, 0, ctx->stream>>>(chain, chain_off, n_contours, stack, dp_out, dp_count);
+  return check_launch(ctx, "approx_dp");
+}
+
+}  // namespace ocrb

@@ -1,0 +1,771 @@
+// Per-candidate geometry of the detection post-processing, on the GPU:
+//   box_score_fast            metrics.rs:150-184  (imageproc draw_polygon_mut mask, f64 mean)
+//   expand_polygon            polygon.rs:13-56    (ClipperOffset miter join + union clean-up)
+//   get_min_area_bounding_box metrics.rs:133-148  (imageproc min_area_rect)
+//   rescale / round / emit    metrics.rs:109-123
+// Compiled with -fmad=false: every f32/f64 expression must round like the reference's
+// scalar code.  Integer predicates are exact (int64 / __int128).
+#include "common.cuh"
+
+namespace ocrb {
+
+struct ipt { int x, y; };
+struct dpt { double x, y; };
+
+// =======================================================================================
+// box score: one CTA per candidate.  The polygon mask (scan-line fill with f32-rounded
+// crossings + Bresenham outline, union) is built as a bit mask in shared memory, in bands
+// of rows when the bounding box is larger than the shared-memory budget; the masked f32
+// probabilities are accumulated in f64 in a fixed order (deterministic).
+// HBM traffic: bbox_area * 4 B of the probability map, read once.
+// =======================================================================================
+constexpr int BS_THREADS = 256;
+constexpr int BS_MAX_PTS = 256;           // DP polygons with more vertices are rejected (flagged)
+constexpr int BS_MASK_WORDS = 8192;       // 32 KB of mask bits per band
+
+__device__ __forceinline__ int clampi(long long v, long long lo, long long hi) { return (int)(v < lo ? lo : (v > hi ? hi : v)); }
+
+__global__ void __launch_bounds__(BS_THREADS) box_score_kernel(const float *__restrict__ pred, int dim_m2, int dim_m1,
+                                                               int64_t image_stride, const int *__restrict__ cand_contour,
+                                                               const int64_t *__restrict__ start_idx,
+                                                               const int64_t *__restrict__ chain_off,
+                                                               const ushort2 *__restrict__ dp_pts, const int *__restrict__ dp_count,
+                                                               int n_cand, double *__restrict__ scores, int *__restrict__ err_flags) {
+  __shared__ uint32_t mask[BS_MASK_WORDS];
+  __shared__ int px[BS_MAX_PTS], py[BS_MAX_PTS];
+  __shared__ double red_s[BS_THREADS / 32];
+  __shared__ long long red_c[BS_THREADS / 32];
+  const int cand = blockIdx.x;
+  if (cand >= n_cand) return;
+  const int c = cand_contour ? cand_contour[cand] : cand;
+  const int n = dp_count[c];
+  if (n > BS_MAX_PTS || n < 1) {
+    if (threadIdx.x == 0) { scores[cand] = -1.0; if (n > BS_MAX_PTS) atomicOr(err_flags, 1); }
+    return;
+  }
+  const ushort2 *pts = dp_pts + chain_off[c];
+  const int64_t b = start_idx ? start_idx[c] / image_stride : 0;
+  const float *map = pred + b * image_stride;
+  // bounding box with the reference's clamps (x by size[-2]-1, y by size[-1]-1; D10)
+  long long mnx = 0xffffffffll, mxx = 0, mny = 0xffffffffll, mxy = 0;
+  for (int i = 0; i < n; ++i) {
+    int x = pts[i].x, y = pts[i].y;
+    mnx = x < mnx ? x : mnx; mxx = x > mxx ? x : mxx;
+    mny = y < mny ? y : mny; mxy = y > mxy ? y : mxy;
+  }
+  const int min_x = clampi(mnx, 0, dim_m2 - 1), max_x = clampi(mxx, 0, dim_m2 - 1);
+  const int min_y = clampi(mny, 0, dim_m1 - 1), max_y = clampi(mxy, 0, dim_m1 - 1);
+  const int mw = max_x - min_x + 1, mh = max_y - min_y + 1;
+  for (int i = threadIdx.x; i < n; i += BS_THREADS) { px[i] = (int)pts[i].x - min_x; py[i] = (int)pts[i].y - min_y; }
+  __syncthreads();
+  // polygon vertical range clipped to the canvas (draw_polygon_mut)
+  int y_min = INT32_MAX, y_max = INT32_MIN;
+  for (int i = 0; i < n; ++i) { y_min = min(y_min, py[i]); y_max = max(y_max, py[i]); }
+  y_min = max(0, min(y_min, mh - 1));
+  y_max = max(0, min(y_max, mh - 1));
+
+  const int row_words = (mw + 31) >> 5;
+  int band_rows = BS_MASK_WORDS / row_words;
+  if (band_rows < 1) {  // a single row does not fit (bbox wider than 262144 px): unsupported
+    if (threadIdx.x == 0) { scores[cand] = -1.0; atomicOr(err_flags, 2); }
+    return;
+  }
+  double acc = 0.0;
+  long long cnt = 0;
+  for (int yb0 = 0; yb0 < mh; yb0 += band_rows) {
+    const int yb1 = min(mh, yb0 + band_rows);
+    const int words = (yb1 - yb0) * row_words;
+    for (int i = threadIdx.x; i < words; i += BS_THREADS) mask[i] = 0;
+    __syncthreads();
+    // ---- scan-line fill: one thread per row ----
+    for (int y = max(yb0, y_min) + threadIdx.x; y <= min(yb1 - 1, y_max); y += BS_THREADS) {
+      uint32_t *rowm = mask + (y - yb0) * row_words;
+      // crossings in ascending order are consumed pairwise; selection by repeated minimum
+      // keeps memory O(1): k-th smallest with multiplicity via (value, rank) stepping.
+      // n is small (<= 256), so an O(n^2) pass per row is fine.
+      int last_v = INT32_MIN, last_taken = 0;  // how many copies of last_v already consumed
+      int span_from = 0;
+      bool have_from = false;
+      for (;;) {
+        // find the next crossing value >= last_v (respecting multiplicities)
+        int best = INT32_MAX, best_mult = 0, cur_mult = 0;
+        for (int e = 0; e < n; ++e) {
+          int x0 = px[e], y0 = py[e], x1 = px[e + 1 == n ? 0 : e + 1], y1 = py[e + 1 == n ? 0 : e + 1];
+          if (!((y0 <= y && y1 >= y) || (y1 <= y && y0 >= y))) continue;
+          int v[2], nv = 0;
+          if (y0 == y1) { v[nv++] = x0; v[nv++] = x1; }
+          else if (y0 == y || y1 == y) {
+            if (y1 > y) v[nv++] = x0;
+            if (y0 > y) v[nv++] = x1;
+          } else {
+            float fraction = (float)(y - y0) / (float)(y1 - y0);
+            float inter = (float)x0 + fraction * (float)(x1 - x0);
+            v[nv++] = (int)roundf(inter);
+          }
+          for (int q = 0; q < nv; ++q) {
+            if (v[q] == last_v) cur_mult++;
+            else if (v[q] > last_v) {
+              if (v[q] < best) { best = v[q]; best_mult = 1; }
+              else if (v[q] == best) best_mult++;
+            }
+          }
+        }
+        int val, avail;
+        if (last_v != INT32_MIN && cur_mult > last_taken) { val = last_v; avail = cur_mult - last_taken; }
+        else if (best != INT32_MAX) { val = best; avail = best_mult; last_v = best; last_taken = 0; }
+        else break;
+        // consume all `avail` copies of val
+        for (int k = 0; k < avail; ++k) {
+          if (!have_from) { span_from = val; have_from = true; }
+          else {
+            int from = min(span_from, mw), to = min(val, mw - 1);
+            if (from < mw && to >= 0) {
+              from = max(0, from); to = max(0, to);
+              for (int x = from; x <= to; ++x) rowm[x >> 5] |= 1u << (x & 31);
+            }
+            have_from = false;
+          }
+        }
+        last_taken += avail;
+      }
+    }
+    __syncthreads();
+    // ---- outline: one thread per edge, Bresenham exactly as imageproc (f32 state) ----
+    for (int e = threadIdx.x; e < n; e += BS_THREADS) {
+      float x0 = (float)px[e], y0 = (float)py[e];
+      float x1 = (float)px[e + 1 == n ? 0 : e + 1], y1 = (float)py[e + 1 == n ? 0 : e + 1];
+      bool steep = fabsf(y1 - y0) > fabsf(x1 - x0);
+      if (steep) { float t = x0; x0 = y0; y0 = t; t = x1; x1 = y1; y1 = t; }
+      if (x0 > x1) { float t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
+      float dx = x1 - x0, dy = fabsf(y1 - y0), error = dx / 2.0f;
+      int x = (int)x0, y = (int)y0, end_x = (int)x1, y_step = y0 < y1 ? 1 : -1;
+      while (x <= end_x) {
+        int qx = steep ? y : x, qy = steep ? x : y;
+        if (qx >= 0 && qx < mw && qy >= yb0 && qy < yb1) atomicOr(&mask[(qy - yb0) * row_words + (qx >> 5)], 1u << (qx & 31));
+        x += 1;
+        error -= dy;
+        if (error < 0.0f) { y += y_step; error += dx; }
+      }
+    }
+    __syncthreads();
+    // ---- masked sum ----
+    for (int i = threadIdx.x; i < words; i += BS_THREADS) {
+      uint32_t m = mask[i];
+      if (!m) continue;
+      int ry = i / row_words, wx = (i % row_words) << 5;
+      const float *rowp = map + (int64_t)(min_y + yb0 + ry) * dim_m1 + (min_x + wx);
+      cnt += __popc(m);
+      while (m) {
+        int bit = __ffs(m) - 1;
+        m &= m - 1;
+        acc += (double)rowp[bit];
+      }
+    }
+    __syncthreads();
+  }
+  // deterministic block reduction
+  for (int d = 16; d > 0; d >>= 1) {
+    acc += __shfl_down_sync(0xffffffffu, acc, d);
+    cnt += __shfl_down_sync(0xffffffffu, cnt, d);
+  }
+  if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = acc; red_c[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    long long k = 0;
+    for (int w = 0; w < BS_THREADS / 32; ++w) { s += red_s[w]; k += red_c[w]; }
+    scores[cand] = s / (double)k;
+  }
+}
+
+int launch_box_score(ocrb_ctx *ctx, const float *pred, int dim_m2, int dim_m1, int64_t image_stride,
+                     const int *cand_contour, const int64_t *start_idx, const int64_t *chain_off, const ushort2 *dp_pts,
+                     const int *dp_count, int n_cand, double *scores, int *err_flags) {
+  if (n_cand <= 0) return OCRB_OK;
+  box_score_kernel<<<n_cand, BS_THREADS, 0, ctx->stream>>>(pred, dim_m2, dim_m1, image_stride, cand_contour, start_idx,
+                                                           chain_off, dp_pts, dp_count, n_cand, scores, err_flags);
+  return check_launch(ctx, "box_score");
+}
+
+// =======================================================================================
+// unclip: ClipperOffset (miter limit 2) + union/pftPositive clean-up + min-area-rect.
+// One thread per candidate that passed the score filter; scratch slabs in global memory.
+// =======================================================================================
+__device__ __forceinline__ long long clip_round(double v) { return v < 0 ? (long long)(v - 0.5) : (long long)(v + 0.5); }
+__device__ __forceinline__ long long crossi(long long ax, long long ay, long long bx, long long by) { return ax * by - ay * bx; }
+__device__ __forceinline__ long long doti(long long ax, long long ay, long long bx, long long by) { return ax * bx + ay * by; }
+
+__device__ double clipper_area(const ipt *p, int n) {
+  if (n < 3) return 0;
+  double a = 0;
+  for (int i = 0, j = n - 1; i < n; ++i) {
+    a += ((double)p[j].x + (double)p[i].x) * ((double)p[j].y - (double)p[i].y);
+    j = i;
+  }
+  return -a * 0.5;
+}
+
+// src (n, cleaned + oriented in place) -> out raw offset path; returns count
+__device__ int clipper_offset_raw(ipt *src, int n_in, double delta, ipt *out) {
+  int hi = n_in - 1;
+  while (hi > 0 && src[0].x == src[hi].x && src[0].y == src[hi].y) hi--;
+  int n = 0;
+  for (int i = 0; i <= hi; ++i)
+    if (n == 0 || src[n - 1].x != src[i].x || src[n - 1].y != src[i].y) src[n++] = src[i];
+  if (n < 3) return 0;
+  if (!(clipper_area(src, n) >= 0))
+    for (int i = 0, j = n - 1; i < j; ++i, --j) { ipt t = src[i]; src[i] = src[j]; src[j] = t; }
+  int m = 0;
+  if (fabs(delta) < 1.0e-20) {
+    for (int i = 0; i < n; ++i) out[m++] = src[i];
+    return m;
+  }
+  const double miter_lim = 0.5;
+  // unit normal of edge j -> j+1
+  auto normal = [&](int j, double &nx, double &ny) {
+    ipt p1 = src[j], p2 = src[j + 1 == n ? 0 : j + 1];
+    if (p1.x == p2.x && p1.y == p2.y) { nx = 0; ny = 0; return; }
+    double dx = (double)(p2.x - p1.x), dy = (double)(p2.y - p1.y);
+    double f = 1.0 / sqrt(dx * dx + dy * dy);
+    dx *= f; dy *= f;
+    nx = dy; ny = -dx;
+  };
+  double nkx, nky;
+  normal(n - 1, nkx, nky);
+  for (int j = 0; j < n; ++j) {
+    double njx, njy;
+    normal(j, njx, njy);
+    double sinA = nkx * njy - njx * nky;
+    bool done = false;
+    if (fabs(sinA * delta) < 1.0) {
+      double cosA = nkx * njx + njy * nky;
+      if (cosA > 0) {
+        out[m].x = (int)clip_round(src[j].x + nkx * delta);
+        out[m].y = (int)clip_round(src[j].y + nky * delta);
+        m++; done = true;
+      }
+    } else if (sinA > 1.0) sinA = 1.0;
+    else if (sinA < -1.0) sinA = -1.0;
+    if (!done) {
+      if (sinA * delta < 0) {
+        out[m].x = (int)clip_round(src[j].x + nkx * delta);
+        out[m].y = (int)clip_round(src[j].y + nky * delta); m++;
+        out[m++] = src[j];
+        out[m].x = (int)clip_round(src[j].x + njx * delta);
+        out[m].y = (int)clip_round(src[j].y + njy * delta); m++;
+      } else {
+        double r = 1 + (njx * nkx + njy * nky);
+        if (r >= miter_lim) {
+          double q = delta / r;
+          out[m].x = (int)clip_round(src[j].x + (nkx + njx) * q);
+          out[m].y = (int)clip_round(src[j].y + (nky + njy) * q); m++;
+        } else {
+          double dx = tan(atan2(sinA, nkx * njx + nky * njy) / 4);
+          out[m].x = (int)clip_round(src[j].x + delta * (nkx - nky * dx));
+          out[m].y = (int)clip_round(src[j].y + delta * (nky + nkx * dx)); m++;
+          out[m].x = (int)clip_round(src[j].x + delta * (njx + njy * dx));
+          out[m].y = (int)clip_round(src[j].y + delta * (njy - njx * dx)); m++;
+        }
+      }
+    }
+    nkx = njx; nky = njy;
+  }
+  return m;
+}
+
+__device__ void clipper_intersect_point(ipt a0, ipt a1, ipt b0, ipt b1, ipt *ip) {
+  ipt abot, atop, bbot, btop;
+  if (a0.y >= a1.y) { abot = a0; atop = a1; } else { abot = a1; atop = a0; }
+  if (b0.y >= b1.y) { bbot = b0; btop = b1; } else { bbot = b1; btop = b0; }
+  const double HORIZ = -1.0E+40;
+  double adx = (atop.y == abot.y) ? HORIZ : (double)(atop.x - abot.x) / (double)(atop.y - abot.y);
+  double bdx = (btop.y == bbot.y) ? HORIZ : (double)(btop.x - bbot.x) / (double)(btop.y - bbot.y);
+  double b1_, b2_;
+  long long X, Y;
+  if (adx == bdx) { Y = abot.y; X = abot.x; }
+  else if (adx == 0) {
+    X = abot.x;
+    if (bdx == HORIZ) Y = bbot.y;
+    else { b2_ = bbot.y - (bbot.x / bdx); Y = clip_round(X / bdx + b2_); }
+  } else if (bdx == 0) {
+    X = bbot.x;
+    if (adx == HORIZ) Y = abot.y;
+    else { b1_ = abot.y - (abot.x / adx); Y = clip_round(X / adx + b1_); }
+  } else {
+    b1_ = abot.x - abot.y * adx;
+    b2_ = bbot.x - bbot.y * bdx;
+    double q = (b2_ - b1_) / (adx - bdx);
+    Y = clip_round(q);
+    if (fabs(adx) < fabs(bdx)) X = clip_round(adx * q + b1_);
+    else X = clip_round(bdx * q + b2_);
+  }
+  ip->x = (int)X; ip->y = (int)Y;
+}
+
+struct rat { long long num, den; };
+__device__ __forceinline__ bool rat_lt(rat a, rat b) { return (__int128)a.num * b.den < (__int128)b.num * a.den; }
+__device__ __forceinline__ bool rat_eq(rat a, rat b) { return (__int128)a.num * b.den == (__int128)b.num * a.den; }
+
+__device__ bool seg_hit(const ipt *Q, int m, int i, int j, int which, rat *t, rat *s) {
+  ipt a0 = Q[i], a1 = Q[i + 1 == m ? 0 : i + 1], b0 = Q[j], b1 = Q[j + 1 == m ? 0 : j + 1];
+  long long dix = a1.x - a0.x, diy = a1.y - a0.y, djx = b1.x - b0.x, djy = b1.y - b0.y;
+  long long wx = b0.x - a0.x, wy = b0.y - a0.y;
+  long long den = crossi(dix, diy, djx, djy);
+  if (den != 0) {
+    if (which != 0) return false;
+    long long tn = crossi(wx, wy, djx, djy), sn = crossi(wx, wy, dix, diy);
+    if (den < 0) { den = -den; tn = -tn; sn = -sn; }
+    if (tn < 0 || tn > den || sn < 0 || sn > den) return false;
+    t->num = tn; t->den = den; s->num = sn; s->den = den;
+    return true;
+  }
+  if (crossi(wx, wy, dix, diy) != 0) return false;
+  long long L = doti(dix, diy, dix, diy);
+  if (L == 0 || which == 0) return false;
+  ipt e = which == 1 ? b0 : b1;
+  long long tn = doti(e.x - a0.x, e.y - a0.y, dix, diy);
+  if (tn < 0 || tn > L) return false;
+  t->num = tn; t->den = L; s->num = which == 1 ? 0 : 1; s->den = 1;
+  return true;
+}
+
+__device__ __forceinline__ int half_of(long long rx, long long ry, long long dx, long long dy) {
+  long long c = crossi(rx, ry, dx, dy), d = doti(rx, ry, dx, dy);
+  if (c > 0) return 0;
+  if (c < 0) return 2;
+  return d < 0 ? 1 : 3;
+}
+__device__ __forceinline__ bool ccw_before(long long rx, long long ry, long long ax, long long ay, long long bx, long long by) {
+  int ha = half_of(rx, ry, ax, ay), hb = half_of(rx, ry, bx, by);
+  if (ha != hb) return ha < hb;
+  if (ha == 1 || ha == 3) return false;
+  return crossi(ax, ay, bx, by) > 0;
+}
+
+// outer boundary of {winding > 0} of the closed path Qin (see oracle/postproc_oracle.c for the
+// derivation of this restatement of Clipper's union).  Q: scratch for the de-duplicated path.
+__device__ int union_outer(const ipt *Qin, int m_in, ipt *Q, ipt *out, int cap) {
+  int m = 0;
+  for (int i = 0; i < m_in; ++i)
+    if (m == 0 || Q[m - 1].x != Qin[i].x || Q[m - 1].y != Qin[i].y) Q[m++] = Qin[i];
+  while (m > 1 && Q[0].x == Q[m - 1].x && Q[0].y == Q[m - 1].y) m--;
+  if (m < 3) return 0;
+  int sv = 0;
+  for (int i = 1; i < m; ++i)
+    if (Q[i].y < Q[sv].y || (Q[i].y == Q[sv].y && Q[i].x < Q[sv].x)) sv = i;
+  int best = -1;
+  for (int i = 0; i < m; ++i) {
+    if (Q[i].x != Q[sv].x || Q[i].y != Q[sv].y) continue;
+    if (best < 0) { best = i; continue; }
+    int i1 = i + 1 == m ? 0 : i + 1, b1 = best + 1 == m ? 0 : best + 1;
+    long long dx = Q[i1].x - Q[i].x, dy = Q[i1].y - Q[i].y;
+    long long bx = Q[b1].x - Q[best].x, by = Q[b1].y - Q[best].y;
+    if (crossi(bx, by, dx, dy) < 0) best = i;
+  }
+  int cur = best;
+  rat cur_t = {0, 1};
+  const int start_seg = cur;
+  int n_out = 0;
+  out[n_out++] = Q[cur];
+  int guard = 0;
+  const int max_iter = 8 * m + 64;
+  for (;;) {
+    if (++guard > max_iter) return 0;
+    rat t_best = {1, 1};
+    for (int j = 0; j < m; ++j) {
+      if (j == cur) continue;
+      for (int which = 0; which < 3; ++which) {
+        rat t, s;
+        if (!seg_hit(Q, m, cur, j, which, &t, &s)) continue;
+        if (!rat_lt(cur_t, t)) continue;
+        if (rat_lt(t, t_best)) t_best = t;
+      }
+    }
+    ipt c0 = Q[cur], c1 = Q[cur + 1 == m ? 0 : cur + 1];
+    long long ux = c1.x - c0.x, uy = c1.y - c0.y;
+    long long rx = -ux, ry = -uy;
+    int nxt = -1;
+    rat nxt_s = {0, 1};
+    long long bdx = 0, bdy = 0;
+    bool node_is_vertex = false;
+    ipt node_v = {0, 0};
+    if (t_best.num == t_best.den) { node_is_vertex = true; node_v = c1; }
+    else { nxt = cur; nxt_s = t_best; bdx = ux; bdy = uy; }
+    for (int j = 0; j < m; ++j) {
+      if (j == cur) continue;
+      for (int which = 0; which < 3; ++which) {
+        rat t, s;
+        if (!seg_hit(Q, m, cur, j, which, &t, &s)) continue;
+        if (!rat_eq(t, t_best)) continue;
+        int j1 = j + 1 == m ? 0 : j + 1;
+        if (s.num == 0) { node_is_vertex = true; node_v = Q[j]; }
+        if (s.num == s.den) { node_is_vertex = true; node_v = Q[j1]; continue; }
+        long long dx = Q[j1].x - Q[j].x, dy = Q[j1].y - Q[j].y;
+        if (nxt < 0 || ccw_before(rx, ry, dx, dy, bdx, bdy)) { nxt = j; nxt_s = s; bdx = dx; bdy = dy; }
+      }
+    }
+    if (nxt < 0) return 0;
+    if (nxt == start_seg && nxt_s.num == 0) break;
+    ipt node;
+    if (node_is_vertex) node = node_v;
+    else clipper_intersect_point(c0, c1, Q[nxt], Q[nxt + 1 == m ? 0 : nxt + 1], &node);
+    if (n_out >= cap) return 0;
+    out[n_out++] = node;
+    cur = nxt;
+    cur_t = nxt_s;
+  }
+  // FixupOutPolygon: drop duplicates and collinear middles until stable
+  bool changed = true;
+  while (changed && n_out >= 3) {
+    changed = false;
+    for (int i = 0; i < n_out && n_out >= 3; ++i) {
+      ipt p = out[(i + n_out - 1) % n_out], c = out[i], nn = out[(i + 1) % n_out];
+      bool dup = (c.x == nn.x && c.y == nn.y) || (c.x == p.x && c.y == p.y);
+      bool col = crossi(c.x - p.x, c.y - p.y, nn.x - c.x, nn.y - c.y) == 0;
+      if (dup || col) {
+        for (int k = i; k + 1 < n_out; ++k) out[k] = out[k + 1];
+        n_out--; changed = true; i--;
+      }
+    }
+  }
+  if (n_out < 3) return 0;
+  // BuildResult order: start right after the last top-most vertex (rotate in place via Q)
+  int top = 0;
+  for (int i = 1; i < n_out; ++i)
+    if (out[i].y < out[top].y || (out[i].y == out[top].y && out[i].x > out[top].x)) top = i;
+  int st = (top + 1) % n_out;
+  for (int i = 0; i < n_out; ++i) Q[i] = out[(st + i) % n_out];  // n_out <= cap <= capacity of Q region? see slab layout
+  for (int i = 0; i < n_out; ++i) out[i] = Q[i];
+  return n_out;
+}
+
+// ---- min-area rectangle (imageproc 0.22 min_area_rect + metrics.rs:133-148) -------------
+__device__ __forceinline__ int orient(dpt p, dpt q, dpt r) {
+  double val = (q.y - p.y) * (r.x - q.x) - (q.x - p.x) * (r.y - q.y);
+  if (val == 0.0) return 0;
+  return val > 0.0 ? 1 : 2;
+}
+__device__ __forceinline__ double ddist(dpt a, dpt b) { return sqrt((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y)); }
+__device__ __forceinline__ dpt rot(dpt p, double s, double c) { dpt r; r.x = p.x * c + p.y * s; r.y = p.y * c - p.x * s; return r; }
+__device__ __forceinline__ dpt irot(dpt p, double s, double c) { dpt r; r.x = p.x * c - p.y * s; r.y = p.y * c + p.x * s; return r; }
+__device__ __forceinline__ double pt_dist(ipt a, ipt b) {
+  double dx = (double)a.x - (double)b.x, dy = (double)a.y - (double)b.y;
+  return sqrt(dx * dx + dy * dy);
+}
+
+// work: >= n points, hull: >= n+1 points
+__device__ double min_area_bounding_box(const ipt *pts, int n, dpt *work, dpt *hull, ipt box_out[4]) {
+  ipt b[4];
+  for (int i = 0; i < n; ++i) { work[i].x = pts[i].x; work[i].y = pts[i].y; }
+  int s = 0;
+  for (int i = 1; i < n; ++i)
+    if (work[i].y < work[s].y || (work[i].y == work[s].y && work[i].x < work[s].x)) s = i;
+  dpt start = work[s];
+  work[s] = work[0];
+  dpt *rest = work + 1;
+  int nr = n - 1;
+  for (int i = 1; i < nr; ++i) {  // stable insertion sort by polar order around `start`
+    dpt key = rest[i];
+    int j = i - 1;
+    while (j >= 0) {
+      int o = orient(start, key, rest[j]);
+      bool less = (o == 0) ? (ddist(start, key) < ddist(start, rest[j])) : (o == 2);
+      if (!less) break;
+      rest[j + 1] = rest[j];
+      j--;
+    }
+    rest[j + 1] = key;
+  }
+  int nrem = 0;
+  for (int i = 0; i < nr;) {
+    int k = i;
+    while (k + 1 < nr && orient(start, rest[k], rest[k + 1]) == 0) k++;
+    rest[nrem++] = rest[k];
+    i = k + 1;
+  }
+  int h = 0;
+  hull[h++] = start;
+  for (int i = 0; i < nrem; ++i) {
+    while (h > 1 && orient(hull[h - 2], hull[h - 1], rest[i]) != 2) h--;
+    hull[h++] = rest[i];
+  }
+  if (h == 1) {
+    for (int i = 0; i < 4; ++i) { b[i].x = (int)hull[0].x; b[i].y = (int)hull[0].y; }
+  } else if (h == 2) {
+    b[0].x = (int)hull[0].x; b[0].y = (int)hull[0].y;
+    b[1].x = (int)hull[1].x; b[1].y = (int)hull[1].y;
+    b[2] = b[1]; b[3] = b[0];
+  } else {
+    const double PI = 3.14159265358979323846264338327950288;
+    double min_area = 1.7976931348623157e308;
+    dpt res[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    for (int e = 0; e + 1 < h; ++e) {
+      double ex = hull[e + 1].x - hull[e].x, ey = hull[e + 1].y - hull[e].y;
+      double angle = fabs(fmod(atan2(ey, ex) + PI, PI / 2.));
+      double sn = sin(angle), cs = cos(angle);
+      double min_x = 1.7976931348623157e308, max_x = -1.7976931348623157e308;
+      double min_y = 1.7976931348623157e308, max_y = -1.7976931348623157e308;
+      for (int i = 0; i < h; ++i) {
+        dpt r = rot(hull[i], sn, cs);
+        if (r.x < min_x) min_x = r.x;
+        if (r.x > max_x) max_x = r.x;
+        if (r.y < min_y) min_y = r.y;
+        if (r.y > max_y) max_y = r.y;
+      }
+      double area = (max_x - min_x) * (max_y - min_y);
+      if (area < min_area) {
+        min_area = area;
+        dpt a = {max_x, min_y}, bb = {min_x, min_y}, cc = {min_x, max_y}, d = {max_x, max_y};
+        res[0] = irot(a, sn, cs); res[1] = irot(bb, sn, cs); res[2] = irot(cc, sn, cs); res[3] = irot(d, sn, cs);
+      }
+    }
+    for (int i = 1; i < 4; ++i) {
+      dpt key = res[i]; int j = i - 1;
+      while (j >= 0 && key.x < res[j].x) { res[j + 1] = res[j]; j--; }
+      res[j + 1] = key;
+    }
+    int i1 = res[1].y > res[0].y ? 0 : 1;
+    int i2 = res[3].y > res[2].y ? 2 : 3;
+    int i3 = res[3].y > res[2].y ? 3 : 2;
+    int i4 = res[1].y > res[0].y ? 1 : 0;
+    b[0].x = (int)floor(res[i1].x); b[0].y = (int)floor(res[i1].y);
+    b[1].x = (int)ceil(res[i2].x);  b[1].y = (int)floor(res[i2].y);
+    b[2].x = (int)ceil(res[i3].x);  b[2].y = (int)ceil(res[i3].y);
+    b[3].x = (int)floor(res[i4].x); b[3].y = (int)ceil(res[i4].y);
+  }
+  for (int i = 1; i < 4; ++i) {
+    ipt key = b[i]; int j = i - 1;
+    while (j >= 0 && key.x < b[j].x) { b[j + 1] = b[j]; j--; }
+    b[j + 1] = key;
+  }
+  int i1 = b[1].y > b[0].y ? 0 : 1;
+  int i2 = b[3].y > b[2].y ? 2 : 3;
+  int i3 = b[3].y > b[2].y ? 3 : 2;
+  int i4 = b[1].y > b[0].y ? 1 : 0;
+  ipt r[4] = {b[i1], b[i2], b[i3], b[i4]};
+  if (box_out) for (int i = 0; i < 4; ++i) box_out[i] = r[i];
+  double w = pt_dist(r[0], r[1]), hh = pt_dist(r[0], r[3]);
+  return w < hh ? w : hh;
+}
+
+// slab layout per candidate (units of 8 bytes), n = DP vertex count:
+//   src  [n+1]         int2   DP polygon copy (cleaned / oriented in place)
+//   raw  [3n+3]        int2   raw offset path
+//   Q    [max(3n+3, cap)] int2 de-duplicated path / rotation scratch
+//   out  [cap]         int2   expanded polygon, cap = 6n+32
+//   work [cap] hull [cap+1]   double2 (2 units each)
+__host__ __device__ inline int unclip_cap(int n) { return 6 * n + 32; }
+__host__ __device__ inline int64_t unclip_slab_units(int n) {
+  int64_t cap = unclip_cap(n);
+  return (n + 1) + (3 * n + 3) + cap + cap + 2 * cap + 2 * (cap + 1);
+}
+
+__global__ void unclip_slab_size_kernel(const int *__restrict__ cand_contour, const int *__restrict__ dp_count, int n_cand,
+                                        int64_t *__restrict__ units) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand) return;
+  int n = dp_count[cand_contour ? cand_contour[i] : i];
+  units[i] = unclip_slab_units(n);
+}
+
+// status: 0 dropped by score, 1 kept, 2 dropped (empty offset, reference panics, D11),
+//         3 dropped by min_size
+__global__ void unclip_kernel(const int *__restrict__ cand_contour, const int64_t *__restrict__ chain_off,
+                              const ushort2 *__restrict__ dp_pts, const int *__restrict__ dp_count, int n_cand,
+                              const double *__restrict__ scores, double box_thresh, double min_size, double factor,
+                              const int64_t *__restrict__ slab_off, int2 *__restrict__ slabs, int *__restrict__ out_count,
+                              uint8_t *__restrict__ status, double *__restrict__ sside_out, int2 *__restrict__ box_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand) return;
+  out_count[i] = 0;
+  double score = scores[i];
+  if (score < 0.0 || box_thresh > score) {  // metrics.rs:100 (`score < 0` marks a rejected candidate)
+    status[i] = 0;
+    return;
+  }
+  const int c = cand_contour ? cand_contour[i] : i;
+  const int n = dp_count[c];
+  const ushort2 *pts = dp_pts + chain_off[c];
+  const int cap = unclip_cap(n);
+  ipt *src = reinterpret_cast<ipt *>(slabs + slab_off[i]);
+  ipt *raw = src + (n + 1);
+  ipt *Q = raw + (3 * n + 3);
+  ipt *out = Q + cap;
+  dpt *work = reinterpret_cast<dpt *>(out + cap);
+  dpt *hull = work + cap;
+  // geo: unsigned_area and euclidean_length of the closed ring
+  double twice = 0.0, perim = 0.0;
+  for (int k = 0; k < n; ++k) {
+    ushort2 a = pts[k], b = pts[k + 1 == n ? 0 : k + 1];
+    twice += (double)a.x * (double)b.y - (double)a.y * (double)b.x;
+    ipt ia = {a.x, a.y}, ib = {b.x, b.y};
+    perim += pt_dist(ia, ib);
+    src[k] = ia;
+  }
+  double area = fabs(twice / 2.0);
+  double distance = area * factor / perim;
+  int m = clipper_offset_raw(src, n, distance, raw);
+  int ne = m >= 3 ? union_outer(raw, m, Q, out, cap) : 0;
+  if (ne == 0) { status[i] = 2; return; }
+  ipt box[4];
+  double sside = min_area_bounding_box(out, ne, work, hull, box);
+  if (sside_out) sside_out[i] = sside;
+  if (box_out) for (int k = 0; k < 4; ++k) box_out[i * 4 + k] = make_int2(box[k].x, box[k].y);
+  if (sside < min_size) { status[i] = 3; out_count[i] = ne; return; }
+  status[i] = 1;
+  out_count[i] = ne;
+}
+
+int launch_unclip_slab_sizes(ocrb_ctx *ctx, const int *cand_contour, const int *dp_count, int n_cand, int64_t *units) {
+  if (n_cand <= 0) return OCRB_OK;
+  unclip_slab_size_kernel<<<(unsigned)cdiv(n_cand, 128), 128, 0, ctx->stream>>>(cand_contour, dp_count, n_cand, units);
+  return check_launch(ctx, "unclip_slab_size");
+}
+
+int launch_unclip(ocrb_ctx *ctx, const int *cand_contour, const int64_t *chain_off, const ushort2 *dp_pts,
+                  const int *dp_count, int n_cand, const double *scores, double box_thresh, double min_size, double factor,
+                  const int64_t *slab_off, int2 *slabs, int *out_count, uint8_t *status, double *sside_out, int2 *box_out) {
+  if (n_cand <= 0) return OCRB_OK;
+  unclip_kernel<<<(unsigned)cdiv(n_cand, 64), 64, 0, ctx->stream>>>(cand_contour, chain_off, dp_pts, dp_count, n_cand, scores,
+                                                                    box_thresh, min_size, factor, slab_off, slabs, out_count,
+                                                                    status, sside_out, box_out);
+  return check_launch(ctx, "unclip");
+}
+
+// expanded polygon location inside a candidate's slab
+__device__ __forceinline__ const int2 *slab_out_ptr(const int2 *slabs, int64_t off, int n) {
+  return slabs + off + (n + 1) + (3 * n + 3) + unclip_cap(n);
+}
+
+// kept polygons -> result arrays (metrics.rs:109-123: coordinate / adjust, round, as u32)
+__device__ __forceinline__ uint32_t sat_u32(double v) {
+  if (!(v == v)) return 0;
+  if (v <= 0.0) return 0;
+  if (v >= 4294967295.0) return 4294967295u;
+  return (uint32_t)v;
+}
+
+__global__ void emit_polygons_kernel(const int *__restrict__ cand_contour, const int *__restrict__ dp_count,
+                                     const int64_t *__restrict__ start_idx, int64_t image_stride, int n_cand,
+                                     const uint8_t *__restrict__ status, const int *__restrict__ kept_rank,
+                                     const int64_t *__restrict__ pt_off, const int64_t *__restrict__ slab_off,
+                                     const int2 *__restrict__ slabs, const int *__restrict__ out_count,
+                                     const double *__restrict__ scores, const double *__restrict__ adjust,
+                                     uint32_t *__restrict__ xy, double *__restrict__ out_scores,
+                                     int64_t *__restrict__ out_pt_off, int *__restrict__ out_image) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand || status[i] != 1) return;
+  const int c = cand_contour ? cand_contour[i] : i;
+  const int n = dp_count[c];
+  const int64_t b = start_idx ? start_idx[c] / image_stride : 0;
+  const double ax = adjust[b * 2], ay = adjust[b * 2 + 1];
+  const int2 *src = slab_out_ptr(slabs, slab_off[i], n);
+  const int r = kept_rank[i];
+  const int64_t po = pt_off[i];
+  const int ne = out_count[i];
+  for (int k = 0; k < ne; ++k) {
+    xy[2 * (po + k)] = sat_u32(round((double)src[k].x / ax));
+    xy[2 * (po + k) + 1] = sat_u32(round((double)src[k].y / ay));
+  }
+  out_scores[r] = scores[i];
+  out_pt_off[r] = po;
+  out_image[r] = (int)b;
+}
+
+int launch_emit_polygons(ocrb_ctx *ctx, const int *cand_contour, const int *dp_count, const int64_t *start_idx,
+                         int64_t image_stride, int n_cand, const uint8_t *status, const int *kept_rank,
+                         const int64_t *pt_off, const int64_t *slab_off, const int2 *slabs, const int *out_count,
+                         const double *scores, const double *adjust, uint32_t *xy, double *out_scores,
+                         int64_t *out_pt_off, int *out_image) {
+  if (n_cand <= 0) return OCRB_OK;
+  emit_polygons_kernel<<<(unsigned)cdiv(n_cand, 128), 128, 0, ctx->stream>>>(cand_contour, dp_count, start_idx, image_stride,
+                                                                            n_cand, status, kept_rank, pt_off, slab_off, slabs,
+                                                                            out_count, scores, adjust, xy, out_scores,
+                                                                            out_pt_off, out_image);
+  return check_launch(ctx, "emit_polygons");
+}
+
+// helper kernels for the compaction steps
+__global__ void flag_ge4_kernel(const int *__restrict__ dp_count, int64_t n, uint8_t *__restrict__ flag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = dp_count[i] >= 4 ? 1 : 0;
+}
+__global__ void compact_index_kernel(const uint8_t *__restrict__ flag, const int *__restrict__ rank, int64_t n, int *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) out[rank[i]] = (int)i;
+}
+__global__ void kept_sizes_kernel(const uint8_t *__restrict__ status, const int *__restrict__ out_count, int n,
+                                  uint8_t *__restrict__ kept_flag, int *__restrict__ kept_pts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool k = status[i] == 1;
+  kept_flag[i] = k ? 1 : 0;
+  kept_pts[i] = k ? out_count[i] : 0;
+}
+// per-image statistics: contours, >=4 dp points, >= box_thresh, kept, dropped(empty offset)
+__global__ void stats_contours_kernel(const int64_t *__restrict__ start_idx, const int *__restrict__ dp_count, int64_t n,
+                                      int64_t image_stride, unsigned long long *__restrict__ stats) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t b = start_idx[i] / image_stride;
+  atomicAdd(&stats[b * 5 + 0], 1ull);
+  if (dp_count[i] >= 4) atomicAdd(&stats[b * 5 + 1], 1ull);
+}
+__global__ void stats_cands_kernel(const int *__restrict__ cand_contour, const int64_t *__restrict__ start_idx, int n,
+                                   int64_t image_stride, const uint8_t *__restrict__ status,
+                                   unsigned long long *__restrict__ stats) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t b = start_idx[cand_contour[i]] / image_stride;
+  uint8_t s = status[i];
+  if (s != 0) atomicAdd(&stats[b * 5 + 2], 1ull);
+  if (s == 1) atomicAdd(&stats[b * 5 + 3], 1ull);
+  if (s == 2) atomicAdd(&stats[b * 5 + 4], 1ull);
+}
+
+int launch_flag_ge4(ocrb_ctx *ctx, const int *dp_count, int64_t n, uint8_t *flag) {
+  if (n <= 0) return OCRB_OK;
+  flag_ge4_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(dp_count, n, flag);
+  return check_launch(ctx, "flag_ge4");
+}
+int launch_compact_index(ocrb_ctx *ctx, const uint8_t *flag, const int *rank, int64_t n, int *out) {
+  if (n <= 0) return OCRB_OK;
+  compact_index_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(flag, rank, n, out);
+  return check_launch(ctx, "compact_index");
+}
+int launch_kept_sizes(ocrb_ctx *ctx, const uint8_t *status, const int *out_count, int n, uint8_t *kept_flag, int *kept_pts) {
+  if (n <= 0) return OCRB_OK;
+  kept_sizes_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(status, out_count, n, kept_flag, kept_pts);
+  return check_launch(ctx, "kept_sizes");
+}
+int launch_stats(ocrb_ctx *ctx, const int64_t *start_idx, const int *dp_count, int64_t n_contours, int64_t image_stride,
+                 const int *cand_contour, int n_cand, const uint8_t *status, unsigned long long *stats) {
+  if (n_contours > 0) {
+    stats_contours_kernel<<<(unsigned)cdiv(n_contours, 256), 256, 0, ctx->stream>>>(start_idx, dp_count, n_contours, image_stride, stats);
+    OCRB_TRY(check_launch(ctx, "stats_contours"));
+  }
+  if (n_cand > 0) {
+    stats_cands_kernel<<<(unsigned)cdiv(n_cand, 256), 256, 0, ctx->stream>>>(cand_contour, start_idx, n_cand, image_stride, status, stats);
+    OCRB_TRY(check_launch(ctx, "stats_cands"));
+  }
+  return OCRB_OK;
+}
+
+}  // namespace ocrb
+
+// ---- single-polygon test hooks (ocrb_min_area_bounding_box) ----------------------------
+namespace ocrb {
+__global__ void minrect_hook_kernel(const int2 *__restrict__ pts, int n, double2 *work, double2 *hull, int2 *box, double *sside) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  ipt b[4];
+  double s = min_area_bounding_box(reinterpret_cast<const ipt *>(pts), n, reinterpret_cast<dpt *>(work),
+                                   reinterpret_cast<dpt *>(hull), b);
+  for (int k = 0; k < 4; ++k) box[k] = make_int2(b[k].x, b[k].y);
+  *sside = s;
+}
+
+int launch_minrect_hook(ocrb_ctx *ctx, const int2 *pts, int n, double2 *work, double2 *hull, int2 *box, double *sside) {
+  minrect_hook_kernel<<<1, 32, 0, ctx->stream>>>(pts, n, work, hull, box, sside);
+  return check_launch(ctx, "minrect_hook");
+}
+}  // namespace ocrb

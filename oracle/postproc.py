@@ -109,7 +109,7 @@ def offset_raw(points, delta):
 def expand_polygon(points, factor=2.0, return_distance=False):
     """polygon.rs:51-56 -> [m,2] int32 or None."""
     p = _pts(points)
-    cap = 12 * len(p) + 64
+    cap = 6 * len(p) + 32
     out = np.empty((cap, 2), np.int32)
     d = C.c_double(0)
     m = lib().orc_expand_polygon(_p(p, C.c_int32), len(p), C.c_double(factor), _p(out, C.c_int32), cap, C.byref(d))

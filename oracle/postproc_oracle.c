@@ -743,7 +743,7 @@ int orc_polygons_from_bitmap(const float *pred, const uint8_t *bitmap, int H, in
     double score = orc_box_score(pred, H, W, dp, (int)nd, NULL);
     if (box_thresh > score) { free(dp); continue; }
     st[2]++;
-    int cap = (int)(12 * nd + 64);
+    int cap = (int)(6 * nd + 32); /* same bound as the CUDA path (geometry.cu unclip_cap) */
     ipt *ex = (ipt *)malloc(sizeof(ipt) * (size_t)cap);
     int ne = orc_expand_polygon(dp, (int)nd, unclip_factor, ex, cap, NULL);
     free(dp);
