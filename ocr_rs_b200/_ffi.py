@@ -1,0 +1,196 @@
+"""ctypes binding of include/ocrb.h (libocrb.so, built in-tree by ocr_rs_b200/csrc/Makefile).
+
+This is the same C ABI a Rust `ocrb-sys` crate would bind.  There is no
+CPU fallback: if the shared library is missing, importing a compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libocrb.so")
+
+OK = 0
+MODE_FP32, MODE_BF16 = 0, 1
+U8, F32 = 0, 1
+
+c_p = C.c_void_p
+i64 = C.c_int64
+
+
+class PostprocParams(C.Structure):
+    _fields_ = [("thresh", C.c_double), ("box_thresh", C.c_double), ("min_size", C.c_double),
+                ("unclip_factor", C.c_double)]
+
+
+# name -> (restype, argtypes); every symbol include/ocrb.h declares
+SIGNATURES = {
+    "ocrb_version": (C.c_int, []),
+    "ocrb_last_error": (C.c_char_p, []),
+    "ocrb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "ocrb_ctx_create": (C.c_int, [C.c_int, C.POINTER(c_p)]),
+    "ocrb_ctx_destroy": (C.c_int, [c_p]),
+    "ocrb_ctx_synchronize": (C.c_int, [c_p]),
+    "ocrb_ctx_stream": (c_p, [c_p]),
+    "ocrb_ctx_device": (C.c_int, [c_p]),
+    "ocrb_ctx_launch_count": (i64, [c_p]),
+    "ocrb_resize_dims": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int)] * 2),
+    "ocrb_preprocess_rgba": (C.c_int, [c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p,
+                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ocrb_convert_image_to_tensor": (C.c_int, [c_p, c_p, i64, c_p]),
+    "ocrb_convert_tensor_to_image": (C.c_int, [c_p, c_p, i64, C.c_float, c_p]),
+    "ocrb_load_image_as_tensor": (C.c_int, [c_p, c_p, i64, c_p]),
+    "ocrb_det_create": (C.c_int, [c_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_p), C.POINTER(i64), C.c_int,
+                                  C.POINTER(c_p)]),
+    "ocrb_det_destroy": (C.c_int, [c_p]),
+    "ocrb_det_forward": (C.c_int, [c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p]),
+    "ocrb_det_tap": (C.c_int, [c_p, C.c_char_p, c_p, i64]),
+    "ocrb_binarize": (C.c_int, [c_p, c_p, i64, C.c_double, c_p]),
+    "ocrb_box_score_fast": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, C.c_int, C.POINTER(C.c_double)]),
+    "ocrb_min_area_bounding_box": (C.c_int, [c_p, c_p, C.c_int, c_p, C.POINTER(C.c_double)]),
+    "ocrb_expand_polygon": (C.c_int, [c_p, c_p, C.c_int, C.c_double, c_p, C.c_int, C.POINTER(C.c_int)]),
+    "ocrb_postproc_default_params": (None, [C.POINTER(PostprocParams)]),
+    "ocrb_get_boxes_and_box_scores": (C.c_int, [c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.POINTER(PostprocParams),
+                                                C.POINTER(c_p)]),
+    "ocrb_get_polygons_from_bitmap": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.POINTER(PostprocParams),
+                                                C.POINTER(c_p)]),
+    "ocrb_polygons_num_images": (C.c_int, [c_p]),
+    "ocrb_polygons_image_offsets": (C.POINTER(i64), [c_p]),
+    "ocrb_polygons_point_offsets": (C.POINTER(i64), [c_p]),
+    "ocrb_polygons_xy": (C.POINTER(C.c_uint32), [c_p]),
+    "ocrb_polygons_scores": (C.POINTER(C.c_double), [c_p]),
+    "ocrb_polygons_stats": (C.POINTER(i64), [c_p]),
+    "ocrb_polygons_free": (None, [c_p]),
+    "ocrb_ccl_labels": (C.c_int, [c_p, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p]),
+    "ocrb_find_contours": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, c_p, i64, c_p, i64, C.POINTER(i64),
+                                     C.POINTER(i64)]),
+    "ocrb_approx_polygon": (C.c_int, [c_p, c_p, i64, c_p, i64, C.POINTER(i64)]),
+    "ocrb_rec_create": (C.c_int, [c_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_p), C.POINTER(i64), C.POINTER(c_p)]),
+    "ocrb_rec_destroy": (C.c_int, [c_p]),
+    "ocrb_rec_forward": (C.c_int, [c_p, c_p, C.c_int, c_p, c_p, c_p]),
+    "ocrb_rec_forward_u8": (C.c_int, [c_p, c_p, C.c_int, c_p, c_p, c_p]),
+    "ocrb_class_to_char": (C.c_char, [C.c_int]),
+    "ocrb_detect_and_recognize": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.POINTER(PostprocParams),
+                                            c_p, C.c_int, c_p, C.POINTER(c_p)]),
+}
+
+_lib = None
+
+
+class OcrbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libocrb error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Loads libocrb.so; raises (loudly) if it has not been built — no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(libocrb has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise OcrbError(rc, lib().ocrb_last_error().decode("utf-8", "replace"))
+
+
+def ptr(x):
+    """void* of a numpy array, a torch tensor (host or cuda) or a raw int address."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+        return x.ctypes.data
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous(), "tensor must be contiguous"
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+class Context:
+    """ocrb_ctx: one per (device, stream) and host thread (replaces main.rs:26-28 DEVICE)."""
+
+    def __init__(self, device=0):
+        self._h = c_p()
+        check(lib().ocrb_ctx_create(int(device), C.byref(self._h)))
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self):
+        check(lib().ocrb_ctx_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return lib().ocrb_ctx_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(lib().ocrb_ctx_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().ocrb_ctx_destroy(self._h)
+            self._h = c_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def weights_to_c(weights):
+    """dict name -> float32 array  =>  (n, names[], data[], numel[], keepalive)."""
+    names = list(weights.keys())
+    arrs = [np.ascontiguousarray(np.asarray(weights[k], dtype=np.float32)) for k in names]
+    n = len(names)
+    c_names = (C.c_char_p * n)(*[k.encode() for k in names])
+    c_data = (c_p * n)(*[a.ctypes.data for a in arrs])
+    c_numel = (i64 * n)(*[a.size for a in arrs])
+    return n, c_names, c_data, c_numel, arrs
+
+
+class Polygons:
+    """PolygonScores (metrics.rs:32-35) backed by an ocrb_polygons handle; converted eagerly."""
+
+    def __init__(self, handle):
+        L = lib()
+        nb = L.ocrb_polygons_num_images(handle)
+        io = np.ctypeslib.as_array(L.ocrb_polygons_image_offsets(handle), shape=(nb + 1,)).copy()
+        npoly = int(io[-1])
+        po = np.ctypeslib.as_array(L.ocrb_polygons_point_offsets(handle), shape=(npoly + 1,)).copy()
+        npts = int(po[-1])
+        xy = np.ctypeslib.as_array(L.ocrb_polygons_xy(handle), shape=(max(npts, 1) * 2,)).copy()[: npts * 2].reshape(-1, 2)
+        sc = np.ctypeslib.as_array(L.ocrb_polygons_scores(handle), shape=(max(npoly, 1),)).copy()[:npoly]
+        self.stats = np.ctypeslib.as_array(L.ocrb_polygons_stats(handle), shape=(nb * 5,)).copy().reshape(nb, 5)
+        L.ocrb_polygons_free(handle)
+        self.image_offsets, self.point_offsets, self.xy, self.all_scores = io, po, xy, sc
+        self.polygons = [[xy[po[p]:po[p + 1]] for p in range(io[b], io[b + 1])] for b in range(nb)]
+        self.scores = [sc[io[b]:io[b + 1]] for b in range(nb)]

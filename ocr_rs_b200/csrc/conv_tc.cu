@@ -1,0 +1,458 @@
+// BF16 mode of the detector: implicit-GEMM convolution on the 5th-generation tensor cores.
+//
+//   * activations NHWC bf16, weights [Cout][R*S*Cin] bf16 (K-major), fp32 accumulation in TMEM
+//   * one CTA = one output tile of TH x TW = 5 x 25 = 125 pixels (M = 128 rows of a UMMA tile;
+//     200, 100, 50 and 25 are all multiples of 25 and 5) times N_TILE output channels
+//   * per K block (one filter tap x 64 input channels) TMA loads the SHIFTED activation box
+//     {64 ch, TW, TH, 1} (hardware zero fill = the convolution padding; elementStrides = the
+//     convolution stride) and the weight box {64, N_TILE}, both 128B-swizzled, K-major
+//   * warp-specialised persistent kernel: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer
+//     (and TMEM owner), warps 2-5 = epilogue (tcgen05.ld -> BN scale/shift -> +residual ->
+//     ReLU -> bf16 -> global), two TMEM accumulator stages so the epilogue of tile i
+//     overlaps the MMAs of tile i+1
+//   * fused epilogues: FPN lateral "+ up2(x)" dual output, nearest-upsample replicate into a
+//     channel slice of the concat buffer, and the whole DB head tail
+//     (conv-transpose 2x2 + BN + ReLU + conv-transpose 2x2 + sigmoid + binarize).
+//
+// reference: model.rs:4-12, 40-55, 75-105, 126-150.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace ocrb {
+
+constexpr int TC_TW = 25, TC_TH = 5, TC_ROWS = TC_TW * TC_TH;  // 125 valid rows of 128
+constexpr int TC_A_BYTES = 128 * 128;                           // A stage: 128 rows x 64 bf16
+constexpr int TC_A_TX = TC_ROWS * 128;                          // bytes TMA actually writes
+constexpr int TC_THREADS = 192;
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a mis-programmed pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (SBO = 1024 B between 8-row groups)
+__device__ __forceinline__ uint64_t make_smem_desc(const void *p) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(p) >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162 *>(&u);
+  return __bfloat1622float2(h);
+}
+
+// ---------------------------------------------------------------------------------------
+// shared-memory carve-up
+// ---------------------------------------------------------------------------------------
+template <int N_TILE, int STAGES>
+struct TcSmem {
+  static constexpr int B_BYTES = N_TILE * 128;
+  static constexpr int OFF_B = STAGES * TC_A_BYTES;
+  static constexpr int OFF_BAR = OFF_B + STAGES * B_BYTES;       // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  static constexpr int OFF_TMEM = OFF_BAR + (2 * STAGES + 4) * 8;
+  static constexpr int OFF_SCALE = OFF_TMEM + 16;                // scale[512], shift[512], w2[256]
+  static constexpr int TOTAL = OFF_SCALE + (512 + 512 + 256) * 4;
+  static constexpr int DYN_BYTES = TOTAL + 1024;                 // slack for manual 1024 B alignment
+};
+
+template <int N_TILE, int STAGES, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+  using L = TcSmem<N_TILE, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sA = smem;
+  uint8_t *sB = smem + L::OFF_B;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::OFF_BAR);
+  uint64_t *empty = full + STAGES;
+  uint64_t *tfull = empty + STAGES;
+  uint64_t *tempty = tfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_TMEM);
+  float *s_scale = reinterpret_cast<float *>(smem + L::OFF_SCALE);
+  float *s_shift = s_scale + 512;
+  float *s_w2 = s_shift + 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64) ? 64 : (2 * N_TILE <= 128) ? 128 : (2 * N_TILE <= 256) ? 256 : 512;
+  const int num_kb = p.R * p.S * p.cin_chunks;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int num_m_tiles = tiles_per_img * p.B;
+  const int num_tiles = num_m_tiles * p.num_n_tiles;
+
+  // ---- one-time setup ----
+  const int n_sc = (EPI == EPI_HEAD) ? 64 : (p.Cout < 512 ? p.Cout : 512);
+  for (int i = threadIdx.x; i < n_sc; i += TC_THREADS) {
+    s_scale[i] = p.scale ? p.scale[i] : 1.0f;
+    s_shift[i] = p.shift ? p.shift[i] : 0.0f;
+  }
+  // rows 125..127 of every A stage are never written by TMA: keep them zero
+  for (int i = threadIdx.x; i < STAGES * 3 * 32; i += TC_THREADS) {
+    const int s = i / 96, w = i % 96;
+    reinterpret_cast<uint32_t *>(sA + s * TC_A_BYTES + TC_ROWS * 128)[w] = 0u;
+  }
+  fence_proxy_async();
+  if (EPI == EPI_HEAD)
+    for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_w2[i] = p.w2[i];
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile / num_m_tiles, m_tile = tile - n_tile * num_m_tiles;
+        const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
+        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        const int x_base = tx * TC_TW * p.stride - p.pad, y_base = ty * TC_TH * p.stride - p.pad;
+        for (int r = 0; r < p.R; ++r)
+          for (int s = 0; s < p.S; ++s)
+            for (int ck = 0; ck < p.cin_chunks; ++ck) {
+              mbar_wait(&empty[stage], phase ^ 1, p.err, 1);
+              mbar_expect_tx(&full[stage], TC_A_TX + L::B_BYTES);
+              tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], ck * 64, x_base + s, y_base + r, b);
+              tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full[stage], ((r * p.S + s) * p.cin_chunks + ck) * 64, n_tile * N_TILE);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc(N_TILE);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1, p.err, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase, p.err, 3);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = make_smem_desc(sA + stage * TC_A_BYTES);
+          const uint64_t bdesc = make_smem_desc(sB + stage * L::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle atom
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ================= epilogue =================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;
+    const int yl = m / TC_TW, xl = m - yl * TC_TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile / num_m_tiles, m_tile = tile - n_tile * num_m_tiles;
+      const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
+      const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+      const int y = ty * TC_TH + yl, x = tx * TC_TW + xl;
+      const bool valid = m < TC_ROWS && y < p.Ho && x < p.Wo;
+      mbar_wait(&tfull[acc], acc_phase, p.err, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE);
+      if (EPI == EPI_STD) {
+        const int64_t pix = ((int64_t)b * p.Ho + y) * p.Wo + x;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          if (valid) {
+            const int n = n_tile * N_TILE + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], s_scale[n + j], s_shift[n + j]);
+            if (p.residual) {
+              const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + pix * p.Cout + n);
+              uint4 r0 = rp[0], r1 = rp[1];
+              const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { float2 f = unpack_bf16(ru[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+            if (p.out) {
+              uint4 o0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+              uint4 o1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+              const int rep = p.rep;
+              const int64_t Wr = (int64_t)p.Wo * rep;
+              for (int ry = 0; ry < rep; ++ry)
+                for (int rx = 0; rx < rep; ++rx) {
+                  const int64_t opix = ((int64_t)b * p.Ho * rep + (int64_t)y * rep + ry) * Wr + (int64_t)x * rep + rx;
+                  uint4 *op = reinterpret_cast<uint4 *>(p.out + opix * p.out_ldc + p.out_coff + n);
+                  op[0] = o0;
+                  op[1] = o1;
+                }
+            }
+            if (p.sum_out) {
+              const int64_t upix = ((int64_t)b * (p.Ho / 2) + (y >> 1)) * (p.Wo / 2) + (x >> 1);
+              const uint4 *up = reinterpret_cast<const uint4 *>(p.up_src + upix * p.Cout + n);
+              uint4 u0 = up[0], u1 = up[1];
+              const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+              uint32_t so[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { float2 f = unpack_bf16(uu[j]); so[j] = pack_bf16(v[2 * j] + f.x, v[2 * j + 1] + f.y); }
+              uint4 *sp = reinterpret_cast<uint4 *>(p.sum_out + pix * p.Cout + n);
+              sp[0] = make_uint4(so[0], so[1], so[2], so[3]);
+              sp[1] = make_uint4(so[4], so[5], so[6], so[7]);
+            }
+          }
+        }
+      } else {
+        // DB head tail: columns n = tap(i,j)*64 + co of conv-transpose 1; per tap BN+ReLU then
+        // the 64 -> 4 dot products of conv-transpose 2, sigmoid, 4x4 block of the 4x map.
+        float o[4][4];
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap) {
+          float z[4] = {p.b2, p.b2, p.b2, p.b2};
+#pragma unroll 1
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + tap * 64 + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = c0 + j;
+              float h = fmaxf(fmaf(v[j], s_scale[co], s_shift[co]), 0.0f);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) z[q] = fmaf(h, s_w2[q * 64 + co], z[q]);
+            }
+          }
+          // tap = i*2 + j of conv-transpose 1; q = i'*2 + j' of conv-transpose 2
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[2 * (tap >> 1) + (q >> 1)][2 * (tap & 1) + (q & 1)] = 1.0f / (1.0f + expf(-z[q]));
+        }
+        if (valid) {
+          const int64_t Wp = (int64_t)p.Wo * 4;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int64_t off = ((int64_t)b * p.Ho * 4 + (int64_t)y * 4 + a) * Wp + (int64_t)x * 4;
+            *reinterpret_cast<float4 *>(p.prob + off) = make_float4(o[a][0], o[a][1], o[a][2], o[a][3]);
+            if (p.bitmap) {
+              uint32_t bits = (o[a][0] > p.thresh ? 1u : 0u) | (o[a][1] > p.thresh ? 0x100u : 0u) |
+                              (o[a][2] > p.thresh ? 0x10000u : 0u) | (o[a][3] > p.thresh ? 0x1000000u : 0u);
+              *reinterpret_cast<uint32_t *>(p.bitmap + off) = bits;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// activations NHWC bf16 [B][H][W][C] -> 4-D map {C, W, H, B}, box {64, TW*stride, TH*stride, 1}
+int make_act_tensor_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int stride) {
+  auto fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return OCRB_ERR_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(TC_TW * stride), (cuuint32_t)(TC_TH * stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(act %dx%dx%dx%d s%d) -> %d", B, H, W, C, stride, (int)r); return OCRB_ERR_CUDA; }
+  return OCRB_OK;
+}
+
+// weights [Cout][Ktot] bf16 -> 2-D map {Ktot, Cout}, box {64, n_tile}
+int make_weight_tensor_map(CUtensorMap *map, const void *base, int Cout, int Ktot, int n_tile) {
+  auto fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return OCRB_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)n_tile};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights %dx%d) -> %d", Cout, Ktot, (int)r); return OCRB_ERR_CUDA; }
+  return OCRB_OK;
+}
+
+template <int N_TILE, int STAGES, int EPI>
+static int launch_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvTcParams &p, int num_tiles) {
+  using L = TcSmem<N_TILE, STAGES>;
+  static bool attr_set[16] = {false};
+  auto kern = conv_tc_kernel<N_TILE, STAGES, EPI>;
+  if (!attr_set[ctx->device & 15]) {
+    OCRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    attr_set[ctx->device & 15] = true;
+  }
+  int grid = num_tiles < ctx->sm_count ? num_tiles : ctx->sm_count;
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, ctx->stream>>>(tmA, tmB, p);
+  return check_launch(ctx, "conv_tc");
+}
+
+int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, int epi) {
+  p.tiles_x = (int)cdiv(p.Wo, TC_TW);
+  p.tiles_y = (int)cdiv(p.Ho, TC_TH);
+  p.num_n_tiles = p.Cout / n_tile;
+  if (p.Cout % n_tile != 0 || p.Cout > 512) { set_error("conv_tc: Cout %d not a multiple of the N tile %d (or > 512)", p.Cout, n_tile); return OCRB_ERR_INVALID; }
+  const int num_tiles = p.tiles_x * p.tiles_y * p.B * p.num_n_tiles;
+  if (epi == EPI_HEAD) {
+    if (n_tile != 256) { set_error("conv_tc head needs N tile 256"); return OCRB_ERR_INVALID; }
+    return launch_one<256, 4, EPI_HEAD>(ctx, tmA, tmB, p, num_tiles);
+  }
+  switch (n_tile) {
+    case 64: return launch_one<64, 6, EPI_STD>(ctx, tmA, tmB, p, num_tiles);
+    case 128: return launch_one<128, 5, EPI_STD>(ctx, tmA, tmB, p, num_tiles);
+    case 256: return launch_one<256, 4, EPI_STD>(ctx, tmA, tmB, p, num_tiles);
+  }
+  set_error("conv_tc: unsupported N tile %d", n_tile);
+  return OCRB_ERR_INVALID;
+}
+
+}  // namespace ocrb

@@ -1,0 +1,37 @@
+// Interface of the tcgen05 implicit-GEMM convolution engine (conv_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ocrb {
+
+enum { EPI_STD = 0, EPI_HEAD = 1 };
+
+struct ConvTcParams {
+  // problem geometry (output side); tiles_x/tiles_y/num_n_tiles are filled by the launcher
+  int B = 0, Ho = 0, Wo = 0, Cout = 0;
+  int R = 1, S = 1, cin_chunks = 1, stride = 1, pad = 0;
+  int tiles_x = 0, tiles_y = 0, num_n_tiles = 0;
+  // standard epilogue: y = acc * scale[c] + shift[c] (+ residual) (ReLU)
+  const float *scale = nullptr, *shift = nullptr;
+  const __nv_bfloat16 *residual = nullptr;  // [B][Ho][Wo][Cout]
+  int relu = 0;
+  __nv_bfloat16 *out = nullptr;             // [B][Ho*rep][Wo*rep][out_ldc], channel offset out_coff
+  int out_ldc = 0, out_coff = 0, rep = 1;
+  const __nv_bfloat16 *up_src = nullptr;    // [B][Ho/2][Wo/2][Cout]
+  __nv_bfloat16 *sum_out = nullptr;         // [B][Ho][Wo][Cout] = y + up2(up_src)
+  // DB head tail
+  const float *w2 = nullptr;                // [4][64]
+  float b2 = 0.f, thresh = 0.6f;
+  float *prob = nullptr;                    // [B][4*Ho][4*Wo]
+  uint8_t *bitmap = nullptr;                // optional
+  int *err = nullptr;                       // device flag set before a pipeline-timeout trap
+};
+
+int make_act_tensor_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int stride);
+int make_weight_tensor_map(CUtensorMap *map, const void *base, int Cout, int Ktot, int n_tile);
+int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, int epi);
+
+}  // namespace ocrb

@@ -1,0 +1,677 @@
+// text_detection::model::resnet18 (model.rs:65-156) as a device-resident graph:
+// ResNet-18 (1-channel stem) -> 1x1 laterals -> non-cascaded FPN -> 3x3 "out"
+// convs -> x8/x4/x2 nearest upsample + concat -> DB probability head -> sigmoid.
+//
+// Two arithmetic modes behind one entry point (north_star tolerances):
+//   OCRB_MODE_FP32  CUDA-core fp32 kernels (conv_fp32.cu), 1e-4 class
+//   OCRB_MODE_BF16  tcgen05/TMEM implicit-GEMM engine (conv_tc.cu), bf16 operands, fp32
+//                   accumulation, batch-norm applied in the fp32 epilogue, 1e-2 class
+// Weights arrive as the reference's VarStore tensors (OIHW fp32).
+#include <cuda_bf16.h>
+
+#include <map>
+#include <string>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace ocrb {
+
+// conv_fp32.cu
+int launch_stem_fp32(ocrb_ctx *, const float *, int, int, int, const float *, const float *, const float *, float *);
+int launch_maxpool_fp32(ocrb_ctx *, const float *, int, int, int, int, float *);
+int launch_conv_fp32(ocrb_ctx *, const float *, int, int, int, int, const float *, int, int, int, int, const float *,
+                     const float *, const float *, int, float *);
+int launch_upsample2_add_fp32(ocrb_ctx *, const float *, const float *, int, int, int, int, float *);
+int launch_upsample_concat_fp32(ocrb_ctx *, const float *, int, int, int, int, int, int, int, float *);
+int launch_convt2x2_fp32(ocrb_ctx *, const float *, int, int, int, int, int, const float *, const float *, const float *, int, float *);
+int launch_convt2x2_sigmoid_fp32(ocrb_ctx *, const float *, int, int, int, int, const float *, float, float *);
+int launch_nhwc_to_nchw_fp32(ocrb_ctx *, const float *, int, int, int, int, int, float *);
+int launch_u8_to_f32(ocrb_ctx *, const uint8_t *, int64_t, float, float *);
+
+constexpr float BN_EPS = 1e-5f;  // tch nn::BatchNormConfig default
+
+// ---------------------------------------------------------------------------------------
+// BF16-mode stem: conv 7x7 s2 p3 (1 -> 64) + BN + ReLU + max_pool 3x3 s2 p1, fused; u8 or f32
+// grey levels in, NHWC bf16 [B][H/4][W/4][64] out.  CUDA cores (K = 49 is too thin for a UMMA
+// tile without an im2col staging pass).  CTA = 8 x 16 pooled pixels.
+// ---------------------------------------------------------------------------------------
+constexpr int ST_PH = 8, ST_PW = 16;                       // pooled tile
+constexpr int ST_CH = 2 * ST_PH + 1, ST_CW = 2 * ST_PW + 1;  // conv tile 17 x 33
+constexpr int ST_IH = 2 * ST_CH + 5, ST_IW = 2 * ST_CW + 5;  // input patch 39 x 71
+constexpr int ST_THREADS = 288;
+
+template <class TIn>
+__global__ void __launch_bounds__(ST_THREADS) stem_fused_bf16_kernel(const TIn *__restrict__ in, int B, int H, int W,
+                                                                     const float *__restrict__ w /*[49][64]*/,
+                                                                     const float *__restrict__ scale, const float *__restrict__ shift,
+                                                                     __nv_bfloat16 *__restrict__ out) {
+  __shared__ float s_in[ST_IH * ST_IW];
+  __shared__ __align__(16) float s_w[49 * 64];
+  __shared__ __nv_bfloat16 s_conv[ST_CH * ST_CW * 16];
+  const int Hc = H / 2, Wc = W / 2, Hp = H / 4, Wp = W / 4;
+  const int tiles_x = (Wp + ST_PW - 1) / ST_PW, tiles_y = (Hp + ST_PH - 1) / ST_PH;
+  const int b = blockIdx.x / (tiles_x * tiles_y), t = blockIdx.x % (tiles_x * tiles_y);
+  const int py0 = (t / tiles_x) * ST_PH, px0 = (t % tiles_x) * ST_PW;
+  const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;  // conv-grid origin of the tile (pool pad 1)
+  const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;  // input origin (conv pad 3)
+  const TIn *img = in + (int64_t)b * H * W;
+  for (int i = threadIdx.x; i < ST_IH * ST_IW; i += ST_THREADS) {
+    int yy = iy0 + i / ST_IW, xx = ix0 + i % ST_IW;
+    s_in[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (float)img[(int64_t)yy * W + xx] : 0.0f;
+  }
+  for (int i = threadIdx.x; i < 49 * 64; i += ST_THREADS) s_w[i] = w[i];
+  __syncthreads();
+  for (int cg = 0; cg < 4; ++cg) {  // 16 output channels at a time
+    for (int pos = threadIdx.x; pos < ST_CH * ST_CW; pos += ST_THREADS) {
+      const int cy = pos / ST_CW, cx = pos % ST_CW;
+      const bool in_grid = (cy0 + cy) >= 0 && (cy0 + cy) < Hc && (cx0 + cx) >= 0 && (cx0 + cx) < Wc;
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+      const float *ip = s_in + (2 * cy) * ST_IW + 2 * cx;
+#pragma unroll 1
+      for (int r = 0; r < 7; ++r) {
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+          const float v = ip[r * ST_IW + s];
+          const float4 *wp = reinterpret_cast<const float4 *>(s_w + (r * 7 + s) * 64 + cg * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 ww = wp[q];
+            acc[4 * q + 0] = fmaf(v, ww.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = cg * 16 + j;
+        // positions outside the conv grid are max-pool padding (-inf); ReLU output >= 0, so
+        // 0 would also be neutral only if a valid element exists -> use a large negative
+        float y = in_grid ? fmaxf(fmaf(acc[j], scale[c], shift[c]), 0.0f) : -3.0e38f;
+        s_conv[pos * 16 + j] = __float2bfloat16(y);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ST_PH * ST_PW * 16; i += ST_THREADS) {
+      const int j = i & 15, pp = i >> 4;
+      const int py = pp / ST_PW, px = pp % ST_PW;
+      if (py0 + py < Hp && px0 + px < Wp) {
+        float m = -3.0e38f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) m = fmaxf(m, __bfloat162float(s_conv[((2 * py + r) * ST_CW + 2 * px + s) * 16 + j]));
+        out[(((int64_t)b * Hp + py0 + py) * Wp + px0 + px) * 64 + cg * 16 + j] = __float2bfloat16(m);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void bf16_nhwc_to_nchw_f32_kernel(const __nv_bfloat16 *__restrict__ in, int B, int H, int W, int C, int ldc,
+                                             float *__restrict__ out) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)B * C * H * W;
+  if (idx >= total) return;
+  int x = (int)(idx % W), y = (int)((idx / W) % H), c = (int)((idx / ((int64_t)W * H)) % C);
+  int64_t b = idx / ((int64_t)W * H * C);
+  out[idx] = __bfloat162float(in[((b * H + y) * W + x) * ldc + c]);
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side weight preparation
+// ---------------------------------------------------------------------------------------
+struct HostWeights {
+  std::map<std::string, std::vector<float>> t;
+  const std::vector<float> *get(const std::string &n) const {
+    auto it = t.find(n);
+    return it == t.end() ? nullptr : &it->second;
+  }
+};
+
+struct ConvSpec {
+  std::string name, bn;  // weight name prefix, bn prefix ("" = none)
+  int cin, cout, k, stride, pad;
+};
+
+struct DevConv {
+  int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
+  DevBuf w32;    // fp32 [k*k][cin][cout]
+  DevBuf w16;    // bf16 [cout][k*k*cin]
+  DevBuf scale, shift;
+};
+
+static uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return (uint16_t)(u >> 16);
+}
+
+template <class T>
+static int upload(DevBuf &buf, const std::vector<T> &v) {
+  OCRB_TRY(buf.reserve(v.size() * sizeof(T)));
+  OCRB_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return OCRB_OK;
+}
+
+static int fold_bn(const HostWeights &hw, const std::string &bn, int c, const std::vector<float> *conv_bias,
+                   std::vector<float> &scale, std::vector<float> &shift) {
+  scale.assign(c, 1.0f);
+  shift.assign(c, 0.0f);
+  if (bn.empty()) {
+    if (conv_bias) shift = *conv_bias;
+    return OCRB_OK;
+  }
+  const auto *g = hw.get(bn + ".weight"), *b = hw.get(bn + ".bias"), *m = hw.get(bn + ".running_mean"), *v = hw.get(bn + ".running_var");
+  OCRB_REQUIRE(g && b && m && v, "missing batch-norm tensors for %s", bn.c_str());
+  OCRB_REQUIRE((int)g->size() == c && (int)b->size() == c && (int)m->size() == c && (int)v->size() == c, "bad batch-norm size for %s", bn.c_str());
+  for (int i = 0; i < c; ++i) {
+    float s = (*g)[i] / sqrtf((*v)[i] + BN_EPS);
+    scale[i] = s;
+    float cb = conv_bias ? (*conv_bias)[i] : 0.0f;
+    shift[i] = (*b)[i] + (cb - (*m)[i]) * s;
+  }
+  return OCRB_OK;
+}
+
+static int prep_conv(const HostWeights &hw, const ConvSpec &sp, bool want16, DevConv &dc) {
+  const auto *w = hw.get(sp.name + ".weight");
+  OCRB_REQUIRE(w, "missing weight tensor %s.weight", sp.name.c_str());
+  const int kk = sp.k * sp.k;
+  OCRB_REQUIRE((int64_t)w->size() == (int64_t)sp.cout * sp.cin * kk, "tensor %s.weight has %zu elements, expected %lld",
+               sp.name.c_str(), w->size(), (long long)sp.cout * sp.cin * kk);
+  dc.cin = sp.cin; dc.cout = sp.cout; dc.k = sp.k; dc.stride = sp.stride; dc.pad = sp.pad;
+  std::vector<float> scale, shift;
+  OCRB_TRY(fold_bn(hw, sp.bn, sp.cout, nullptr, scale, shift));
+  OCRB_TRY(upload(dc.scale, scale));
+  OCRB_TRY(upload(dc.shift, shift));
+  // OIHW -> [tap][ci][co] fp32
+  std::vector<float> w32((size_t)kk * sp.cin * sp.cout);
+  for (int co = 0; co < sp.cout; ++co)
+    for (int ci = 0; ci < sp.cin; ++ci)
+      for (int tp = 0; tp < kk; ++tp) w32[((size_t)tp * sp.cin + ci) * sp.cout + co] = (*w)[((size_t)co * sp.cin + ci) * kk + tp];
+  OCRB_TRY(upload(dc.w32, w32));
+  if (want16 && sp.cin % 64 == 0) {
+    // OIHW -> [co][tap][ci] bf16 (K-major rows)
+    std::vector<uint16_t> w16((size_t)sp.cout * kk * sp.cin);
+    for (int co = 0; co < sp.cout; ++co)
+      for (int tp = 0; tp < kk; ++tp)
+        for (int ci = 0; ci < sp.cin; ++ci) w16[((size_t)co * kk + tp) * sp.cin + ci] = f2bf((*w)[((size_t)co * sp.cin + ci) * kk + tp]);
+    OCRB_TRY(upload(dc.w16, w16));
+  }
+  return OCRB_OK;
+}
+
+}  // namespace ocrb
+
+using namespace ocrb;
+
+struct ocrb_det {
+  ocrb_ctx *ctx = nullptr;
+  int mode = OCRB_MODE_BF16;
+  // stem
+  DevBuf stem_w, stem_scale, stem_shift;
+  // body: index by name
+  std::map<std::string, DevConv> conv;
+  // head
+  DevBuf tr1_w32, tr1_scale, tr1_shift;  // fp32 path: [4][64][64]
+  DevBuf head_w16;                       // bf16 path: [256][64]
+  DevBuf tr2_w;                          // [4][64] fp32 (both paths)
+  float tr2_bias = 0.f;
+  // activations (grow-only), keyed by name
+  std::map<std::string, DevBuf> act;
+  DevBuf staged_in, staged_out, err;
+  // last forward (for taps)
+  int last_B = 0, last_H = 0, last_W = 0;
+  // tensor-map cache
+  struct Maps { int B = 0, H = 0, W = 0; std::map<std::string, CUtensorMap> m; } maps;
+};
+
+namespace ocrb {
+
+static const char *LAYER_NAMES[] = {"layer1", "layer2", "layer3", "layer4"};
+static const int LAYER_C[] = {64, 128, 256, 512};
+
+static int det_build(ocrb_det *d, const HostWeights &hw) {
+  const bool bf = d->mode == OCRB_MODE_BF16;
+  // stem
+  {
+    const auto *w = hw.get("conv1.weight");
+    OCRB_REQUIRE(w && w->size() == 64 * 49, "missing or mis-sized conv1.weight");
+    std::vector<float> wt(49 * 64), sc, sh;
+    for (int co = 0; co < 64; ++co)
+      for (int tp = 0; tp < 49; ++tp) wt[tp * 64 + co] = (*w)[co * 49 + tp];
+    OCRB_TRY(fold_bn(hw, "bn1", 64, nullptr, sc, sh));
+    OCRB_TRY(upload(d->stem_w, wt));
+    OCRB_TRY(upload(d->stem_scale, sc));
+    OCRB_TRY(upload(d->stem_shift, sh));
+  }
+  int cin = 64;
+  for (int li = 0; li < 4; ++li) {
+    const int c = LAYER_C[li];
+    for (int blk = 0; blk < 2; ++blk) {
+      std::string p = std::string(LAYER_NAMES[li]) + "." + std::to_string(blk);
+      const int bc_in = blk == 0 ? cin : c;
+      const int stride = (blk == 0 && li > 0) ? 2 : 1;
+      OCRB_TRY(prep_conv(hw, {p + ".conv1", p + ".bn1", bc_in, c, 3, stride, 1}, bf, d->conv[p + ".conv1"]));
+      OCRB_TRY(prep_conv(hw, {p + ".conv2", p + ".bn2", c, c, 3, 1, 1}, bf, d->conv[p + ".conv2"]));
+      if (blk == 0 && li > 0)
+        OCRB_TRY(prep_conv(hw, {p + ".downsample.0", p + ".downsample.1", bc_in, c, 1, stride, 0}, bf, d->conv[p + ".downsample"]));
+    }
+    cin = c;
+  }
+  OCRB_TRY(prep_conv(hw, {"in5", "", 512, 256, 1, 1, 0}, bf, d->conv["in5"]));
+  OCRB_TRY(prep_conv(hw, {"in4", "", 256, 256, 1, 1, 0}, bf, d->conv["in4"]));
+  OCRB_TRY(prep_conv(hw, {"in3", "", 128, 256, 1, 1, 0}, bf, d->conv["in3"]));
+  OCRB_TRY(prep_conv(hw, {"in2", "", 64, 256, 1, 1, 0}, bf, d->conv["in2"]));
+  for (const char *n : {"out5", "out4", "out3", "out2"}) OCRB_TRY(prep_conv(hw, {n, "", 256, 64, 3, 1, 1}, bf, d->conv[n]));
+  OCRB_TRY(prep_conv(hw, {"bin_conv1", "bin_bn1", 256, 64, 3, 1, 1}, bf, d->conv["bin_conv1"]));
+  // head: conv-transpose weights are [in][out][kh][kw]
+  {
+    const auto *w1 = hw.get("bin_conv_tr1.weight"), *b1 = hw.get("bin_conv_tr1.bias");
+    const auto *w2 = hw.get("bin_conv_tr2.weight"), *b2 = hw.get("bin_conv_tr2.bias");
+    OCRB_REQUIRE(w1 && b1 && w2 && b2, "missing bin_conv_tr1/2 tensors");
+    OCRB_REQUIRE(w1->size() == 64 * 64 * 4 && b1->size() == 64 && w2->size() == 64 * 4 && b2->size() == 1, "bad bin_conv_tr shapes");
+    std::vector<float> sc, sh;
+    OCRB_TRY(fold_bn(hw, "bin_bn2", 64, b1, sc, sh));
+    OCRB_TRY(upload(d->tr1_scale, sc));
+    OCRB_TRY(upload(d->tr1_shift, sh));
+    std::vector<float> w32(4 * 64 * 64);  // [tap][ci][co]
+    std::vector<uint16_t> w16(256 * 64);  // [tap*64+co][ci]
+    for (int ci = 0; ci < 64; ++ci)
+      for (int co = 0; co < 64; ++co)
+        for (int tp = 0; tp < 4; ++tp) {
+          float v = (*w1)[((size_t)ci * 64 + co) * 4 + tp];
+          w32[((size_t)tp * 64 + ci) * 64 + co] = v;
+          w16[((size_t)tp * 64 + co) * 64 + ci] = f2bf(v);
+        }
+    OCRB_TRY(upload(d->tr1_w32, w32));
+    if (bf) OCRB_TRY(upload(d->head_w16, w16));
+    std::vector<float> w2t(4 * 64);  // [tap][ci]
+    for (int ci = 0; ci < 64; ++ci)
+      for (int tp = 0; tp < 4; ++tp) w2t[tp * 64 + ci] = (*w2)[ci * 4 + tp];
+    OCRB_TRY(upload(d->tr2_w, w2t));
+    d->tr2_bias = (*b2)[0];
+  }
+  OCRB_TRY(d->err.reserve(4));
+  OCRB_CUDA(cudaMemset(d->err.p, 0, 4));
+  return OCRB_OK;
+}
+
+template <class T>
+static int act(ocrb_det *d, const std::string &name, int64_t elems, T **out) {
+  DevBuf &b = d->act[name];
+  OCRB_TRY(b.reserve((size_t)elems * sizeof(T)));
+  *out = b.as<T>();
+  return OCRB_OK;
+}
+
+// ------------------------------------------------------------------------------ FP32 graph
+static int forward_fp32(ocrb_det *d, const float *img /*[B][H][W] dev*/, int B, int H, int W, float *prob) {
+  ocrb_ctx *ctx = d->ctx;
+  const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
+  float *c1, *x0;
+  OCRB_TRY(act(d, "f.c1", (int64_t)B * H2 * W2 * 64, &c1));
+  OCRB_TRY(act(d, "f.stem", (int64_t)B * H4 * W4 * 64, &x0));
+  OCRB_TRY(launch_stem_fp32(ctx, img, B, H, W, d->stem_w.as<float>(), d->stem_scale.as<float>(), d->stem_shift.as<float>(), c1));
+  OCRB_TRY(launch_maxpool_fp32(ctx, c1, B, H2, W2, 64, x0));
+  auto conv = [&](const std::string &name, const float *in, int h, int w, const float *res, int relu, float *out) {
+    DevConv &c = d->conv[name];
+    return launch_conv_fp32(ctx, in, B, h, w, c.cin, c.w32.as<float>(), c.cout, c.k, c.stride, c.pad, c.scale.as<float>(),
+                            c.shift.as<float>(), res, relu, out);
+  };
+  const float *x = x0;
+  int h = H4, w = W4;
+  const float *feat[4];
+  int fh[4], fw[4];
+  for (int li = 0; li < 4; ++li) {
+    const int c = LAYER_C[li];
+    const int ho = li > 0 ? h / 2 : h, wo = li > 0 ? w / 2 : w;
+    for (int blk = 0; blk < 2; ++blk) {
+      std::string p = std::string(LAYER_NAMES[li]) + "." + std::to_string(blk);
+      float *t, *y, *ds = nullptr;
+      OCRB_TRY(act(d, "f." + p + ".t", (int64_t)B * ho * wo * c, &t));
+      OCRB_TRY(act(d, "f." + p + ".y", (int64_t)B * ho * wo * c, &y));
+      const int hin = blk == 0 ? h : ho, win = blk == 0 ? w : wo;
+      OCRB_TRY(conv(p + ".conv1", x, hin, win, nullptr, 1, t));
+      const float *res = x;
+      if (blk == 0 && li > 0) {
+        OCRB_TRY(act(d, "f." + p + ".ds", (int64_t)B * ho * wo * c, &ds));
+        OCRB_TRY(conv(p + ".downsample", x, hin, win, nullptr, 0, ds));
+        res = ds;
+      }
+      OCRB_TRY(conv(p + ".conv2", t, ho, wo, res, 1, y));
+      x = y;
+    }
+    h = ho; w = wo;
+    feat[li] = x; fh[li] = h; fw[li] = w;
+  }
+  float *in5, *in4, *in3, *in2, *s4, *s3, *s2, *p5, *p4, *p3, *fuse, *b1, *t1;
+  OCRB_TRY(act(d, "f.in5", (int64_t)B * fh[3] * fw[3] * 256, &in5));
+  OCRB_TRY(act(d, "f.in4", (int64_t)B * fh[2] * fw[2] * 256, &in4));
+  OCRB_TRY(act(d, "f.in3", (int64_t)B * fh[1] * fw[1] * 256, &in3));
+  OCRB_TRY(act(d, "f.in2", (int64_t)B * fh[0] * fw[0] * 256, &in2));
+  OCRB_TRY(act(d, "f.s4", (int64_t)B * fh[2] * fw[2] * 256, &s4));
+  OCRB_TRY(act(d, "f.s3", (int64_t)B * fh[1] * fw[1] * 256, &s3));
+  OCRB_TRY(act(d, "f.s2", (int64_t)B * fh[0] * fw[0] * 256, &s2));
+  OCRB_TRY(act(d, "f.p5", (int64_t)B * fh[3] * fw[3] * 64, &p5));
+  OCRB_TRY(act(d, "f.p4", (int64_t)B * fh[2] * fw[2] * 64, &p4));
+  OCRB_TRY(act(d, "f.p3", (int64_t)B * fh[1] * fw[1] * 64, &p3));
+  OCRB_TRY(act(d, "f.fuse", (int64_t)B * H4 * W4 * 256, &fuse));
+  OCRB_TRY(act(d, "f.bin1", (int64_t)B * H4 * W4 * 64, &b1));
+  OCRB_TRY(act(d, "f.t1", (int64_t)B * H2 * W2 * 64, &t1));
+  OCRB_TRY(conv("in5", feat[3], fh[3], fw[3], nullptr, 0, in5));
+  OCRB_TRY(conv("in4", feat[2], fh[2], fw[2], nullptr, 0, in4));
+  OCRB_TRY(conv("in3", feat[1], fh[1], fw[1], nullptr, 0, in3));
+  OCRB_TRY(conv("in2", feat[0], fh[0], fw[0], nullptr, 0, in2));
+  OCRB_TRY(launch_upsample2_add_fp32(ctx, in5, in4, B, fh[2], fw[2], 256, s4));
+  OCRB_TRY(launch_upsample2_add_fp32(ctx, in4, in3, B, fh[1], fw[1], 256, s3));
+  OCRB_TRY(launch_upsample2_add_fp32(ctx, in3, in2, B, fh[0], fw[0], 256, s2));
+  OCRB_TRY(conv("out5", in5, fh[3], fw[3], nullptr, 0, p5));
+  OCRB_TRY(conv("out4", s4, fh[2], fw[2], nullptr, 0, p4));
+  OCRB_TRY(conv("out3", s3, fh[1], fw[1], nullptr, 0, p3));
+  // out2 writes straight into its concat slice?  conv_fp32 has no pitch: use a temp + copy
+  float *p2;
+  OCRB_TRY(act(d, "f.p2", (int64_t)B * H4 * W4 * 64, &p2));
+  OCRB_TRY(conv("out2", s2, fh[0], fw[0], nullptr, 0, p2));
+  OCRB_TRY(launch_upsample_concat_fp32(ctx, p5, B, H4, W4, 64, 8, 0, 256, fuse));
+  OCRB_TRY(launch_upsample_concat_fp32(ctx, p4, B, H4, W4, 64, 4, 64, 256, fuse));
+  OCRB_TRY(launch_upsample_concat_fp32(ctx, p3, B, H4, W4, 64, 2, 128, 256, fuse));
+  OCRB_TRY(launch_upsample_concat_fp32(ctx, p2, B, H4, W4, 64, 1, 192, 256, fuse));
+  OCRB_TRY(conv("bin_conv1", fuse, H4, W4, nullptr, 1, b1));
+  OCRB_TRY(launch_convt2x2_fp32(ctx, b1, B, H4, W4, 64, 64, d->tr1_w32.as<float>(), d->tr1_scale.as<float>(),
+                                d->tr1_shift.as<float>(), 1, t1));
+  OCRB_TRY(launch_convt2x2_sigmoid_fp32(ctx, t1, B, H2, W2, 64, d->tr2_w.as<float>(), d->tr2_bias, prob));
+  return OCRB_OK;
+}
+
+// ------------------------------------------------------------------------------ BF16 graph
+static int get_map(ocrb_det *d, const std::string &key, const void *base, int B, int H, int W, int C, int stride, CUtensorMap **out) {
+  auto it = d->maps.m.find(key);
+  if (it == d->maps.m.end()) {
+    CUtensorMap m;
+    OCRB_TRY(make_act_tensor_map(&m, base, B, H, W, C, stride));
+    it = d->maps.m.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return OCRB_OK;
+}
+static int get_wmap(ocrb_det *d, const std::string &key, const void *base, int Cout, int Ktot, int n_tile, CUtensorMap **out) {
+  auto it = d->maps.m.find(key);
+  if (it == d->maps.m.end()) {
+    CUtensorMap m;
+    OCRB_TRY(make_weight_tensor_map(&m, base, Cout, Ktot, n_tile));
+    it = d->maps.m.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return OCRB_OK;
+}
+
+static int n_tile_for(int cout) { return cout >= 256 ? 256 : cout; }
+
+template <class TIn>
+static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float *prob, uint8_t *bitmap, float thresh) {
+  typedef __nv_bfloat16 bf;
+  ocrb_ctx *ctx = d->ctx;
+  const int H4 = H / 4, W4 = W / 4;
+  // All activation buffers are allocated first: cached tensor maps embed their addresses.
+  int fh[4], fw[4];
+  fh[0] = H4; fw[0] = W4;
+  for (int i = 1; i < 4; ++i) { fh[i] = fh[i - 1] / 2; fw[i] = fw[i - 1] / 2; }
+  size_t before = 0, after = 0;
+  for (auto &kv : d->act) before += kv.second.cap;
+  bf *x0;
+  OCRB_TRY(act(d, "b.stem", (int64_t)B * H4 * W4 * 64, &x0));
+  struct Blk { bf *t, *y, *ds; };
+  Blk blks[4][2];
+  for (int li = 0; li < 4; ++li)
+    for (int blk = 0; blk < 2; ++blk) {
+      std::string p = std::string(LAYER_NAMES[li]) + "." + std::to_string(blk);
+      const int64_t n = (int64_t)B * fh[li] * fw[li] * LAYER_C[li];
+      OCRB_TRY(act(d, "b." + p + ".t", n, &blks[li][blk].t));
+      OCRB_TRY(act(d, "b." + p + ".y", n, &blks[li][blk].y));
+      blks[li][blk].ds = nullptr;
+      if (blk == 0 && li > 0) OCRB_TRY(act(d, "b." + p + ".ds", n, &blks[li][blk].ds));
+    }
+  bf *in5, *in4, *in3, *s4, *s3, *s2, *fuse, *b1;
+  OCRB_TRY(act(d, "b.in5", (int64_t)B * fh[3] * fw[3] * 256, &in5));
+  OCRB_TRY(act(d, "b.in4", (int64_t)B * fh[2] * fw[2] * 256, &in4));
+  OCRB_TRY(act(d, "b.in3", (int64_t)B * fh[1] * fw[1] * 256, &in3));
+  OCRB_TRY(act(d, "b.s4", (int64_t)B * fh[2] * fw[2] * 256, &s4));
+  OCRB_TRY(act(d, "b.s3", (int64_t)B * fh[1] * fw[1] * 256, &s3));
+  OCRB_TRY(act(d, "b.s2", (int64_t)B * fh[0] * fw[0] * 256, &s2));
+  OCRB_TRY(act(d, "b.fuse", (int64_t)B * H4 * W4 * 256, &fuse));
+  OCRB_TRY(act(d, "b.bin1", (int64_t)B * H4 * W4 * 64, &b1));
+  for (auto &kv : d->act) after += kv.second.cap;
+  if (after != before || d->maps.B != B || d->maps.H != H || d->maps.W != W) {
+    d->maps.m.clear();  // some buffer moved or the shape changed: rebuild the descriptors
+    d->maps.B = B; d->maps.H = H; d->maps.W = W;
+  }
+
+  // stem
+  {
+    const int tiles = (int)(cdiv(W4, ST_PW) * cdiv(H4, ST_PH)) * B;
+    stem_fused_bf16_kernel<TIn><<<tiles, ST_THREADS, 0, ctx->stream>>>(img, B, H, W, d->stem_w.as<float>(), d->stem_scale.as<float>(),
+                                                                       d->stem_shift.as<float>(), x0);
+    OCRB_TRY(check_launch(ctx, "stem_fused_bf16"));
+  }
+  auto conv = [&](const std::string &name, const bf *in, int h, int w, ConvTcParams p) -> int {
+    DevConv &c = d->conv[name];
+    CUtensorMap *ma, *mb;
+    const int nt = n_tile_for(c.cout);
+    OCRB_TRY(get_map(d, "a." + name, in, B, h, w, c.cin, c.stride, &ma));
+    OCRB_TRY(get_wmap(d, "w." + name, c.w16.p, c.cout, c.k * c.k * c.cin, nt, &mb));
+    p.B = B;
+    p.Ho = (h + 2 * c.pad - c.k) / c.stride + 1;
+    p.Wo = (w + 2 * c.pad - c.k) / c.stride + 1;
+    p.Cout = c.cout;
+    p.R = c.k; p.S = c.k; p.cin_chunks = c.cin / 64; p.stride = c.stride; p.pad = c.pad;
+    p.scale = c.scale.as<float>(); p.shift = c.shift.as<float>();
+    if (p.out && p.out_ldc == 0) p.out_ldc = c.cout;
+    p.err = d->err.as<int>();
+    return launch_conv_tc(ctx, *ma, *mb, p, nt, EPI_STD);
+  };
+  const bf *x = x0;
+  int h = H4, w = W4;
+  const bf *feat[4];
+  for (int li = 0; li < 4; ++li) {
+    for (int blk = 0; blk < 2; ++blk) {
+      std::string p = std::string(LAYER_NAMES[li]) + "." + std::to_string(blk);
+      Blk &bk = blks[li][blk];
+      const int hin = blk == 0 ? h : fh[li], win = blk == 0 ? w : fw[li];
+      ConvTcParams q1;
+      q1.relu = 1; q1.out = bk.t;
+      OCRB_TRY(conv(p + ".conv1", x, hin, win, q1));
+      const bf *res = x;
+      if (bk.ds) {
+        ConvTcParams qd;
+        qd.relu = 0; qd.out = bk.ds;
+        OCRB_TRY(conv(p + ".downsample", x, hin, win, qd));
+        res = bk.ds;
+      }
+      ConvTcParams q2;
+      q2.relu = 1; q2.out = bk.y; q2.residual = res;
+      OCRB_TRY(conv(p + ".conv2", bk.t, fh[li], fw[li], q2));
+      x = bk.y;
+    }
+    h = fh[li]; w = fw[li];
+    feat[li] = x;
+  }
+  {  // laterals with the FPN "+ up2" fused (the RAW lateral of the level above is added)
+    ConvTcParams q;
+    q.out = in5;
+    OCRB_TRY(conv("in5", feat[3], fh[3], fw[3], q));
+    q = ConvTcParams(); q.out = in4; q.up_src = in5; q.sum_out = s4;
+    OCRB_TRY(conv("in4", feat[2], fh[2], fw[2], q));
+    q = ConvTcParams(); q.out = in3; q.up_src = in4; q.sum_out = s3;
+    OCRB_TRY(conv("in3", feat[1], fh[1], fw[1], q));
+    q = ConvTcParams(); q.out = nullptr; q.up_src = in3; q.sum_out = s2;
+    OCRB_TRY(conv("in2", feat[0], fh[0], fw[0], q));
+  }
+  {  // out convs write their (replicated) result into the concat buffer: cat([p5,p4,p3,p2], 1)
+    ConvTcParams q;
+    q.out = fuse; q.out_ldc = 256; q.out_coff = 0; q.rep = 8;
+    OCRB_TRY(conv("out5", in5, fh[3], fw[3], q));
+    q.out_coff = 64; q.rep = 4;
+    OCRB_TRY(conv("out4", s4, fh[2], fw[2], q));
+    q.out_coff = 128; q.rep = 2;
+    OCRB_TRY(conv("out3", s3, fh[1], fw[1], q));
+    q.out_coff = 192; q.rep = 1;
+    OCRB_TRY(conv("out2", s2, fh[0], fw[0], q));
+  }
+  {
+    ConvTcParams q;
+    q.relu = 1; q.out = b1;
+    OCRB_TRY(conv("bin_conv1", fuse, H4, W4, q));
+  }
+  {  // head tail
+    CUtensorMap *ma, *mb;
+    OCRB_TRY(get_map(d, "a.head", b1, B, H4, W4, 64, 1, &ma));
+    OCRB_TRY(get_wmap(d, "w.head", d->head_w16.p, 256, 64, 256, &mb));
+    ConvTcParams q;
+    q.B = B; q.Ho = H4; q.Wo = W4; q.Cout = 256; q.R = 1; q.S = 1; q.cin_chunks = 1; q.stride = 1; q.pad = 0;
+    q.scale = d->tr1_scale.as<float>(); q.shift = d->tr1_shift.as<float>();
+    q.w2 = d->tr2_w.as<float>(); q.b2 = d->tr2_bias; q.thresh = thresh;
+    q.prob = prob; q.bitmap = bitmap; q.err = d->err.as<int>();
+    OCRB_TRY(launch_conv_tc(ctx, *ma, *mb, q, 256, EPI_HEAD));
+  }
+  return OCRB_OK;
+}
+
+int det_forward_device(ocrb_det *det, const void *img_dev, int dtype, int B, int H, int W, float *prob_dev, uint8_t *bitmap_dev,
+                       float thresh) {
+  ocrb_ctx *ctx = det->ctx;
+  det->last_B = B; det->last_H = H; det->last_W = W;
+  if (det->mode == OCRB_MODE_BF16) {
+    if (dtype == OCRB_U8) return forward_bf16<uint8_t>(det, (const uint8_t *)img_dev, B, H, W, prob_dev, bitmap_dev, thresh);
+    return forward_bf16<float>(det, (const float *)img_dev, B, H, W, prob_dev, bitmap_dev, thresh);
+  }
+  const float *fimg = (const float *)img_dev;
+  if (dtype == OCRB_U8) {
+    float *tmp;
+    OCRB_TRY(act(det, "f.img", (int64_t)B * H * W, &tmp));
+    OCRB_TRY(launch_u8_to_f32(ctx, (const uint8_t *)img_dev, (int64_t)B * H * W, 1.0f, tmp));
+    fimg = tmp;
+  }
+  return forward_fp32(det, fimg, B, H, W, prob_dev);
+}
+
+}  // namespace ocrb
+
+extern "C" {
+
+int ocrb_det_create(ocrb_ctx *ctx, int n, const char *const *names, const float *const *data, const int64_t *numel, int mode,
+                    ocrb_det **out) {
+  OCRB_REQUIRE(ctx && names && data && numel && out && n > 0, "bad argument");
+  OCRB_REQUIRE(mode == OCRB_MODE_FP32 || mode == OCRB_MODE_BF16, "unknown mode %d", mode);
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  HostWeights hw;
+  for (int i = 0; i < n; ++i) {
+    OCRB_REQUIRE(names[i] && data[i] && numel[i] >= 0, "bad tensor %d", i);
+    hw.t[names[i]] = std::vector<float>(data[i], data[i] + numel[i]);
+  }
+  ocrb_det *d = new ocrb_det();
+  d->ctx = ctx;
+  d->mode = mode;
+  int rc = det_build(d, hw);
+  if (rc != OCRB_OK) {
+    ocrb_det_destroy(d);
+    return rc;
+  }
+  *out = d;
+  return OCRB_OK;
+}
+
+int ocrb_det_destroy(ocrb_det *d) {
+  if (!d) return OCRB_OK;
+  cudaSetDevice(d->ctx->device);
+  cudaStreamSynchronize(d->ctx->stream);
+  d->stem_w.release(); d->stem_scale.release(); d->stem_shift.release();
+  for (auto &kv : d->conv) { kv.second.w32.release(); kv.second.w16.release(); kv.second.scale.release(); kv.second.shift.release(); }
+  d->tr1_w32.release(); d->tr1_scale.release(); d->tr1_shift.release(); d->head_w16.release(); d->tr2_w.release();
+  for (auto &kv : d->act) kv.second.release();
+  d->staged_in.release(); d->staged_out.release(); d->err.release();
+  delete d;
+  return OCRB_OK;
+}
+
+int ocrb_det_forward(ocrb_det *det, const void *images, int dtype, int B, int H, int W, float *prob) {
+  OCRB_REQUIRE(det && images && prob, "null argument");
+  OCRB_REQUIRE(dtype == OCRB_U8 || dtype == OCRB_F32, "unknown dtype %d", dtype);
+  OCRB_REQUIRE(B > 0 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "H and W must be positive multiples of 32 (got %dx%d, B=%d)", H, W, B);
+  ocrb_ctx *ctx = det->ctx;
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  const size_t esz = dtype == OCRB_U8 ? 1 : 4;
+  const int64_t HW = (int64_t)H * W;
+  const int chunk = det->mode == OCRB_MODE_BF16 ? 64 : 4;
+  const bool in_dev = is_device_ptr(images), out_dev = is_device_ptr(prob);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bc = B - b0 < chunk ? B - b0 : chunk;
+    const uint8_t *src = (const uint8_t *)images + (size_t)b0 * HW * esz;
+    float *dst = prob + (size_t)b0 * HW;
+    const void *src_dev = src;
+    float *dst_dev = dst;
+    if (!in_dev) {
+      OCRB_TRY(det->staged_in.reserve((size_t)bc * HW * esz));
+      OCRB_CUDA(cudaMemcpyAsync(det->staged_in.p, src, (size_t)bc * HW * esz, cudaMemcpyHostToDevice, ctx->stream));
+      src_dev = det->staged_in.p;
+    }
+    if (!out_dev) {
+      OCRB_TRY(det->staged_out.reserve((size_t)bc * HW * 4));
+      dst_dev = det->staged_out.as<float>();
+    }
+    OCRB_TRY(det_forward_device(det, src_dev, dtype, bc, H, W, dst_dev, nullptr, 0.6f));
+    if (!out_dev) OCRB_CUDA(cudaMemcpyAsync(dst, dst_dev, (size_t)bc * HW * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    // host staging buffers are reused by the next chunk
+    if (!in_dev || !out_dev) OCRB_TRY(sync(ctx));
+  }
+  OCRB_TRY(sync(ctx));
+  int err = 0;
+  OCRB_CUDA(cudaMemcpy(&err, det->err.p, 4, cudaMemcpyDeviceToHost));
+  if (err) { set_error("conv_tc pipeline timeout (code %d)", err); return OCRB_ERR_INTERNAL; }
+  return OCRB_OK;
+}
+
+int ocrb_det_tap(ocrb_det *det, const char *name, float *out, int64_t numel) {
+  OCRB_REQUIRE(det && name && out, "null argument");
+  ocrb_ctx *ctx = det->ctx;
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  const int B = det->last_B, H4 = det->last_H / 4, W4 = det->last_W / 4;
+  OCRB_REQUIRE(B > 0, "no forward has run yet");
+  struct T { const char *tap, *key; int c, div; };
+  static const T table[] = {{"stem", "stem", 64, 1}, {"x1", "layer1.1.y", 64, 1}, {"x2", "layer2.1.y", 128, 2},
+                            {"x3", "layer3.1.y", 256, 4}, {"x4", "layer4.1.y", 512, 8}, {"fuse", "fuse", 256, 1},
+                            {"bin1", "bin1", 64, 1}};
+  for (const T &t : table) {
+    if (strcmp(t.tap, name) != 0) continue;
+    const int h = H4 / t.div, w = W4 / t.div;
+    const int64_t n = (int64_t)B * t.c * h * w;
+    OCRB_REQUIRE(n == numel, "tap %s has %lld elements, caller passed %lld", name, (long long)n, (long long)numel);
+    std::string key = std::string(det->mode == OCRB_MODE_BF16 ? "b." : "f.") + t.key;
+    auto it = det->act.find(key);
+    OCRB_REQUIRE(it != det->act.end(), "tap %s not available", name);
+    DevBuf tmp;
+    OCRB_TRY(tmp.reserve((size_t)n * 4));
+    if (det->mode == OCRB_MODE_BF16) {
+      bf16_nhwc_to_nchw_f32_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(it->second.as<__nv_bfloat16>(), B, h, w, t.c, t.c, tmp.as<float>());
+      OCRB_TRY(check_launch(ctx, "bf16_nhwc_to_nchw_f32"));
+    } else {
+      OCRB_TRY(launch_nhwc_to_nchw_fp32(ctx, it->second.as<float>(), B, h, w, t.c, t.c, tmp.as<float>()));
+    }
+    OCRB_CUDA(cudaMemcpyAsync(out, tmp.p, (size_t)n * 4, cudaMemcpyDefault, ctx->stream));
+    int rc = sync(ctx);
+    tmp.release();
+    return rc;
+  }
+  set_error("unknown tap %s", name);
+  return OCRB_ERR_INVALID;
+}
+
+}  // extern "C"

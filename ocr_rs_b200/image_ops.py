@@ -1,0 +1,65 @@
+"""image_ops.rs mirror (inference subset): same names, argument meaning and error behaviour.
+
+preprocess_image            image_ops.rs:188-220
+convert_image_to_tensor     image_ops.rs:350-364
+convert_tensor_to_image     image_ops.rs:367-381
+load_image_as_tensor        image_ops.rs:73-85
+File decoding (image::open) is out of the kernel path: these take
+decoded pixel arrays.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+
+def _ctx(ctx):
+    return ctx if ctx is not None else _ffi.default_context()
+
+
+def preprocess_image(rgba, target_dim, ctx=None):
+    """rgba: uint8 [h, w, 4] (DynamicImage::into_rgba), target_dim = (width, height)
+    -> (GrayImage uint8 [height, width], adjust_x, adjust_y)."""
+    ctx = _ctx(ctx)
+    rgba = np.ascontiguousarray(rgba, np.uint8)
+    if rgba.ndim != 3 or rgba.shape[2] != 4:
+        raise ValueError("expected an RGBA8 image [h, w, 4]")
+    W, H = int(target_dim[0]), int(target_dim[1])
+    sh, sw = rgba.shape[:2]
+    out = np.empty((H, W), np.uint8)
+    ax, ay = C.c_double(), C.c_double()
+    _ffi.check(_ffi.lib().ocrb_preprocess_rgba(ctx.handle, _ffi.ptr(rgba), sw, sh, W, H, _ffi.ptr(out),
+                                               C.byref(ax), C.byref(ay)))
+    return out, ax.value, ay.value
+
+
+def convert_image_to_tensor(image, ctx=None, out=None):
+    """GrayImage uint8 [H, W] -> float32 tensor [H, W] (the reference builds f64 then
+    .to_kind(Float); values are 0..255, no scaling)."""
+    ctx = _ctx(ctx)
+    image = np.ascontiguousarray(image, np.uint8)
+    if out is None:
+        out = np.empty(image.shape, np.float32)
+    _ffi.check(_ffi.lib().ocrb_convert_image_to_tensor(ctx.handle, _ffi.ptr(image), image.size, _ffi.ptr(out)))
+    return out
+
+
+def convert_tensor_to_image(tensor, scale=1.0, ctx=None):
+    """float32 [H, W] -> GrayImage uint8 by truncation; errors on > 2 dims like the reference."""
+    ctx = _ctx(ctx)
+    tensor = np.ascontiguousarray(tensor, np.float32)
+    if tensor.ndim > 2:
+        raise ValueError("tensor must be in 2 dimensions")  # image_ops.rs:369-371
+    out = np.empty(tensor.shape, np.uint8)
+    _ffi.check(_ffi.lib().ocrb_convert_tensor_to_image(ctx.handle, _ffi.ptr(tensor), tensor.size, float(scale), _ffi.ptr(out)))
+    return out
+
+
+def load_image_as_tensor(luma, ctx=None):
+    """luma uint8 [h, w] -> float32 [1, w*h] = pixel / 255 (image_ops.rs:79-83)."""
+    ctx = _ctx(ctx)
+    luma = np.ascontiguousarray(luma, np.uint8)
+    out = np.empty((1, luma.size), np.float32)
+    _ffi.check(_ffi.lib().ocrb_load_image_as_tensor(ctx.handle, _ffi.ptr(luma), luma.size, _ffi.ptr(out)))
+    return out
