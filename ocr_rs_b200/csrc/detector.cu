@@ -563,6 +563,15 @@ int det_forward_device(ocrb_det *det, const void *img_dev, int dtype, int B, int
   return forward_fp32(det, fimg, B, H, W, prob_dev);
 }
 
+ocrb_ctx *det_ctx(ocrb_det *det) { return det->ctx; }
+int det_mode(ocrb_det *det) { return det->mode; }
+int det_check_err(ocrb_det *det) {
+  int err = 0;
+  OCRB_CUDA(cudaMemcpy(&err, det->err.p, 4, cudaMemcpyDeviceToHost));
+  if (err) { set_error("conv_tc pipeline timeout (code %d)", err); return OCRB_ERR_INTERNAL; }
+  return OCRB_OK;
+}
+
 }  // namespace ocrb
 
 extern "C" {

@@ -237,6 +237,28 @@ static int run_postproc(ocrb_ctx *ctx, const float *pred, const uint8_t *bitmap,
   return OCRB_OK;
 }
 
+// pipeline.cu entry: pred / bitmap / adjust already on the device; appends nothing, fills `res`
+int postproc_device(ocrb_ctx *ctx, const float *pred_dev, const uint8_t *bitmap_dev, const double *adjust_dev, int B, int H,
+                    int W, const ocrb_postproc_params &prm, ocrb_polygons *res) {
+  return run_postproc(ctx, pred_dev, bitmap_dev, adjust_dev, B, H, W, prm, res);
+}
+
+// appends the polygons of `src` (a later chunk of images) to `dst`
+void polygons_append(ocrb_polygons *dst, const ocrb_polygons *src) {
+  if (dst->n_images == 0 && dst->image_offsets.empty()) {
+    dst->image_offsets.assign(1, 0);
+    dst->point_offsets.assign(1, 0);
+  }
+  const int64_t poly_base = dst->image_offsets.back(), pt_base = dst->point_offsets.back();
+  for (int b = 0; b < src->n_images; ++b) dst->image_offsets.push_back(poly_base + src->image_offsets[b + 1]);
+  for (size_t p = 1; p < src->point_offsets.size(); ++p) dst->point_offsets.push_back(pt_base + src->point_offsets[p]);
+  dst->xy.insert(dst->xy.end(), src->xy.begin(), src->xy.end());
+  dst->scores.insert(dst->scores.end(), src->scores.begin(), src->scores.end());
+  dst->stats.insert(dst->stats.end(), src->stats.begin(), src->stats.end());
+  dst->n_images += src->n_images;
+}
+ocrb_polygons *polygons_new() { return new ocrb_polygons(); }
+
 }  // namespace ocrb
 
 using namespace ocrb;

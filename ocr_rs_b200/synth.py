@@ -199,7 +199,7 @@ def make_document_images(n, h=800, w=800, seed=3, n_boxes=30):
     return out
 
 
-def make_blob_prob_map(h=800, w=800, n_blobs=40, seed=4, frame=1, ring_frac=0.1, near_thresh=64):
+def make_blob_prob_map(h=800, w=800, n_blobs=40, seed=4, frame=1, ring_frac=0.1, near_thresh=64, max_w=120, max_h=60):
     """Synthetic probability map (cfg 5 generator).
 
     Background U(0,0.5); blobs (rotated rectangles / ellipses / rings) with interior
@@ -213,7 +213,7 @@ def make_blob_prob_map(h=800, w=800, n_blobs=40, seed=4, frame=1, ring_frac=0.1,
     tries = 0
     while placed < n_blobs and tries < n_blobs * 30:
         tries += 1
-        bw, bh = rng.uniform(8, 120), rng.uniform(8, 60)
+        bw, bh = rng.uniform(8, max_w), rng.uniform(8, max_h)
         r = int(np.ceil(np.hypot(bw, bh) / 2)) + 3
         cx = int(rng.integers(r + frame, w - r - frame))
         cy = int(rng.integers(r + frame, h - r - frame))

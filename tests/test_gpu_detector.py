@@ -1,0 +1,97 @@
+"""GPU parity: detector forward (model.rs:65-156) through the C ABI vs the torch-CPU oracle.
+Tolerances are the north_star's: probability maps within 1e-4 abs in FP32 mode, 1e-2 in BF16
+mode.  The oracle forward is "parity unpinned" against ocr-rs itself (oracle/model_oracle.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+@pytest.fixture(scope="module")
+def env():
+    from ocr_rs_b200 import synth
+    from ocr_rs_b200.text_detection.model import resnet18
+    from oracle import model_oracle as mo
+    return synth, resnet18, mo
+
+
+def _nchw(t):
+    return t.numpy() if hasattr(t, "numpy") else t
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("variant", ["tch", "hard_bn"])
+def test_small_maps_and_taps(env, mode, variant):
+    synth, resnet18, mo = env
+    B, H, W = 2, 160, 224  # non-square, several tiles, H/32 and W/32 odd
+    w = synth.make_detector_weights(0, variant)
+    x = synth.make_noise_images(B, H, W, seed=2)
+    x[1] = synth.make_document_images(1, H, W, seed=3, n_boxes=5)[0]
+    net = resnet18(w, mode)
+    got = net.forward_t(x.reshape(B, 1, H, W))
+    ref, taps = mo.detector_forward(w, x.reshape(B, 1, H, W).astype(np.float32), return_taps=True)
+    ref = ref.numpy()
+    # intermediate taps localise a failure (relative to the tap's own scale)
+    for name in ("stem", "x1", "x2", "x3", "x4", "fuse", "bin1"):
+        t = taps[name].numpy()
+        g = net.tap(name, t.shape)
+        rel = np.abs(g - t).max() / max(np.abs(t).max(), 1e-6)
+        assert rel < (2e-5 if mode == "fp32" else 3e-2), (name, rel)
+    err = np.abs(got - ref).max()
+    print(f"{mode}/{variant}: max|dp| = {err:.3e}")
+    assert got.shape == ref.shape and err <= TOL[mode], err
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_config1_img55(env, preprocessed, mode):
+    """BASELINE config 1: preprocessed_img55.png, random-init weights, single image 800x800."""
+    synth, resnet18, mo = env
+    img = preprocessed["pre_img55"]
+    w = synth.make_detector_weights(0, "tch")
+    got = resnet18(w, mode).forward_t(img.reshape(1, 1, 800, 800))
+    ref = mo.detector_forward(w, img.reshape(1, 1, 800, 800).astype(np.float32)).numpy()
+    err = np.abs(got - ref).max()
+    print(f"config1 {mode}: max|dp| = {err:.3e}, mean {np.abs(got - ref).mean():.3e}")
+    assert err <= TOL[mode]
+
+
+def test_f32_input_equals_u8_input(env):
+    synth, resnet18, _ = env
+    w = synth.make_detector_weights(1, "tch")
+    x = synth.make_noise_images(1, 96, 128, seed=5)
+    for mode in ("fp32", "bf16"):
+        net = resnet18(w, mode)
+        a = net.forward_t(x.reshape(1, 1, 96, 128))
+        b = net.forward_t(x.reshape(1, 1, 96, 128).astype(np.float32))
+        assert (a == b).all()
+
+
+def test_batch_independence_and_chunking(env):
+    """Each image's map must not depend on its batch position (images are sharded by index)."""
+    synth, resnet18, _ = env
+    w = synth.make_detector_weights(2, "structured1")
+    x = synth.make_document_images(5, 96, 96, seed=7, n_boxes=4)
+    net = resnet18(w, "bf16")
+    full = net.forward_t(x.reshape(5, 1, 96, 96))
+    for b in range(5):
+        one = net.forward_t(x[b].reshape(1, 1, 96, 96))
+        assert (one[0] == full[b]).all()
+
+
+def test_bad_arguments(env):
+    synth, resnet18, _ = env
+    from ocr_rs_b200 import OcrbError
+    w = synth.make_detector_weights(0, "tch")
+    net = resnet18(w, "bf16")
+    with pytest.raises(OcrbError):  # FPN adds mis-shape unless H, W are multiples of 32 (model.rs:126-137)
+        net.forward_t(np.zeros((1, 1, 100, 100), np.uint8))
+    bad = dict(w)
+    del bad["layer3.0.downsample.0.weight"]
+    with pytest.raises(OcrbError):  # vs.load errors on a missing name
+        resnet18(bad, "bf16")
+    bad = dict(w)
+    bad["in4.weight"] = bad["in4.weight"][:, :128]
+    with pytest.raises(OcrbError):
+        resnet18(bad, "fp32")

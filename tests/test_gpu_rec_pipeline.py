@@ -1,0 +1,131 @@
+"""GPU parity: glyph recognition (char_recognition/model.rs:12-39, mod.rs:53-56) and the
+batched detect+recognize pipeline (text_detection/mod.rs:46-67, :188-204) through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from ocr_rs_b200 import _ffi, synth
+    from ocr_rs_b200.char_recognition.model import Net
+    from ocr_rs_b200.text_detection.model import resnet18
+    from oracle import model_oracle as mo
+    from oracle import postproc as pp
+    return _ffi, synth, Net, resnet18, mo, pp
+
+
+@pytest.mark.parametrize("kind,n", [("noise", 4096), ("strokes", 1000), ("noise", 1), ("strokes", 67)])
+def test_rec_logits_and_argmax(env, kind, n):
+    """BASELINE config 2 (28x28 glyphs): logits <= 1e-4, class argmax identical."""
+    _ffi, synth, Net, _, mo, _ = env
+    w = synth.make_rec_weights(1)
+    g = synth.make_glyphs(n, 1, kind)
+    net = Net(w)
+    logits, argmax, prob = net.predict(g)  # u8 path (x/255 fused)
+    x = g.astype(np.float32) / np.float32(255.0)
+    ref = mo.rec_forward(w, x)
+    want, want_p = mo.rec_top1(ref)
+    ref = ref.numpy()
+    assert np.abs(logits - ref).max() <= 1e-4
+    top2 = np.sort(ref, -1)[:, -2:]
+    ties = int(((top2[:, 1] - top2[:, 0]) < 1e-4).sum())
+    mism = int((argmax != want).sum())
+    print(f"rec {kind} n={n}: max|dlogit| = {np.abs(logits - ref).max():.2e}, top-2 gap < 1e-4 on {ties} glyphs, {mism} argmax mismatches")
+    assert mism == 0
+    assert np.abs(prob - want_p).max() <= 1e-6
+    # f32 entry point gives the same numbers as the u8 one
+    l2, a2, _ = net.predict(x)
+    assert (l2 == logits).all() and (a2 == argmax).all()
+
+
+def test_rec_varstore_aliases_and_errors(env):
+    _ffi, synth, Net, _, _, _ = env
+    from ocr_rs_b200 import OcrbError, utils
+    w = synth.make_rec_weights(3)
+    aliased = {a: w[n] for (n, _), a in zip(synth.REC_CANONICAL, synth.REC_VARSTORE_ALIASES)}
+    g = synth.make_glyphs(16, 2, "strokes")
+    assert (Net(w).predict(g)[1] == Net(aliased).predict(g)[1]).all()
+    bad = dict(w)
+    del bad["fc2.bias"]
+    with pytest.raises(OcrbError):
+        Net(bad)
+    assert "".join(utils.class_to_char(i) for i in range(62)) == utils.VALUES
+
+
+def _run_pipeline(_ffi, det, rec, imgs, adj, glyphs):
+    B, H, W = imgs.shape
+    am = np.empty(len(glyphs), np.int32)
+    h = _ffi.c_p()
+    _ffi.check(_ffi.lib().ocrb_detect_and_recognize(det._h, rec._h, _ffi.ptr(imgs), _ffi.ptr(adj), B, H, W, None,
+                                                    _ffi.ptr(glyphs), len(glyphs), _ffi.ptr(am), C.byref(h)))
+    return _ffi.Polygons(h), am
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_pipeline_structured_weights(env, mode):
+    """BASELINE config 3 shape at reduced batch: document images, structured head:
+    post-processing of the device's own map is identical to the oracle's; against the oracle's
+    own end-to-end path (torch map -> C post-proc) polygons agree at IoU >= 0.99 wherever no
+    pixel of the map sits within tolerance of a decision threshold."""
+    _ffi, synth, Net, resnet18, mo, pp = env
+    B, H, W = 3, 800, 800
+    wd = synth.make_detector_weights(0, "structured")
+    wr = synth.make_rec_weights(1)
+    imgs = synth.make_document_images(B, H, W, seed=3)
+    glyphs = synth.make_glyphs(256, 4, "strokes")
+    adj = np.array([[1.0, 1.0], [800 / 300, 533 / 200], [2.0, 0.5]])
+    det, rec = resnet18(wd, mode), Net(wr)
+    res, am = _run_pipeline(_ffi, det, rec, imgs, adj, glyphs)
+    prob = det.forward_t(imgs.reshape(B, 1, H, W))
+    total = 0
+    for b in range(B):
+        exp_p, exp_s = pp.polygons_from_bitmap(prob[b, 0], pp.binarize(prob[b, 0], 0.6), tuple(adj[b]))
+        assert len(res.polygons[b]) == len(exp_p)
+        for a, e in zip(res.polygons[b], exp_p):
+            assert a.shape == e.shape and (a == e).all()
+        assert np.abs(res.scores[b] - exp_s).max(initial=0.0) <= 1e-12
+        total += len(exp_p)
+    assert total > 0
+    want = mo.rec_top1(mo.rec_forward(wr, glyphs.astype(np.float32) / np.float32(255.0)))[0]
+    assert (am == want).all()
+    # end to end vs the oracle's own map
+    ref = mo.detector_forward(wd, imgs.reshape(B, 1, H, W).astype(np.float32)).numpy()
+    matched = unmatched = 0
+    for b in range(B):
+        exp_p, _ = pp.polygons_from_bitmap(ref[b, 0], pp.binarize(ref[b, 0], 0.6), tuple(adj[b]))
+        for e in exp_p:
+            best = max((pp.polygon_iou(e, a) for a in res.polygons[b]), default=0.0)
+            if best >= 0.99:
+                matched += 1
+            else:
+                unmatched += 1
+    print(f"pipeline {mode}: {total} polygons from the device map; vs oracle end-to-end {matched} matched at IoU>=0.99, {unmatched} not")
+    if mode == "fp32":
+        assert unmatched <= max(1, (matched + unmatched) // 50)
+
+
+def test_pipeline_chunking_and_device_pointers(env):
+    """More images than one chunk; device-resident inputs give the same result as host inputs."""
+    torch = pytest.importorskip("torch")
+    _ffi, synth, Net, resnet18, _, _ = env
+    B, H, W = 37, 96, 128
+    wd = synth.make_detector_weights(0, "structured")
+    imgs = synth.make_document_images(B, H, W, seed=11, n_boxes=3)
+    glyphs = synth.make_glyphs(8, 4, "strokes")
+    adj = np.ones((B, 2))
+    det, rec = resnet18(wd, "bf16"), Net(synth.make_rec_weights(1))
+    res, am = _run_pipeline(_ffi, det, rec, imgs, adj, glyphs)
+    res1 = [_run_pipeline(_ffi, det, rec, imgs[b:b + 1], adj[b:b + 1], glyphs)[0] for b in range(B)]
+    for b in range(B):
+        assert len(res.polygons[b]) == len(res1[b].polygons[0])
+        for a, e in zip(res.polygons[b], res1[b].polygons[0]):
+            assert (a == e).all()
+    dimgs = torch.from_numpy(imgs).cuda()
+    h = _ffi.c_p()
+    _ffi.check(_ffi.lib().ocrb_detect_and_recognize(det._h, None, _ffi.ptr(dimgs), _ffi.ptr(adj), B, H, W, None, None, 0, None, C.byref(h)))
+    res2 = _ffi.Polygons(h)
+    assert (res2.xy == res.xy).all() and (res2.image_offsets == res.image_offsets).all()
