@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric: 800x800 detection+recognition images/s on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                   (the CPU path: oracle port on the host cores)
+
+A "step" is one pass of the hot path (u8 images -> detector -> binarize -> contours -> box score
+-> unclip -> polygons, plus the glyph CNN on 4 crops per image) over BASELINE config 4's batch:
+1024 synthetic 800x800 images, sharded by contiguous index range over the N ranks (strong
+scaling, no data-path collective; host-side gather of the polygons only).
+
+  value  whole-job images/s with the shard already resident in HBM
+  e2e    the same call with pinned HOST buffers: H2D of the images inside the timed region,
+         D2H of polygons/scores/classes, and the host gather at N>1
+  roofline   the tcgen05 implicit-GEMM conv kernels (all launches of conv_tc_kernel):
+         algorithmic FLOPs / CUDA-event time per launch, against the measured bf16 peak
+  cpu_baseline  the oracle port (torch-CPU restatement of the reference's libtorch ops + the C
+         restatement of its imageproc/Clipper post-processing) on the box's host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOTAL_IMAGES = 1024
+H = W = 800
+GLYPHS_PER_IMAGE = 4
+METRIC = "800x800 det+rec images/sec"
+
+
+def tc_flops_per_image(h, w):
+    """2*MACs of every layer that runs on the tcgen05 kernel (model.rs:65-152; stem excluded:
+    it is a CUDA-core kernel, convT2 excluded: it is the head epilogue's FMA tail)."""
+    h4, w4 = h // 4, w // 4
+    f = 0
+    c_in = 64
+    for li, c in enumerate((64, 128, 256, 512)):
+        hh, ww = h4 >> li, w4 >> li
+        f += 2 * hh * ww * c * c_in * 9 + 3 * 2 * hh * ww * c * c * 9  # b0.conv1 + 3 more 3x3
+        if li > 0:
+            f += 2 * hh * ww * c * c_in  # downsample 1x1
+        f += 2 * hh * ww * 256 * c  # lateral in{2..5}
+        f += 2 * hh * ww * 64 * 256 * 9  # out{2..5}
+        c_in = c
+    f += 2 * h4 * w4 * 64 * 256 * 9  # bin_conv1
+    f += 2 * h4 * w4 * 256 * 64  # conv-transpose 1 as a 64 -> 4*64 GEMM
+    return f
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.rows = []
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.p:
+            return None
+        time.sleep(0.25)
+        self.p.terminate()
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.3 and len(r) >= 6] or [r for _, r in self.rows if len(r) >= 6]
+        if not rows:
+            return None
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_path(wd, wr, imgs, glyphs, adj, threads):
+    """The reference's CPU implementation of the path, restated (oracle/): returns #polygons."""
+    import torch
+    from oracle import model_oracle as mo
+    from oracle import postproc as pp
+    torch.set_num_threads(threads)
+    x = torch.from_numpy(imgs.reshape(-1, 1, imgs.shape[-2], imgs.shape[-1])).to(torch.float32)  # convert_image_to_tensor + to_kind(Float)
+    pred = mo.detector_forward(wd, x).numpy()
+    polys, _ = pp.boxes_and_box_scores(pred, adj)
+    g = torch.from_numpy(glyphs).to(torch.float32) / 255.0
+    mo.rec_top1(mo.rec_forward(wr, g))
+    return sum(len(p) for p in polys)
+
+
+def time_cpu_sample(n_images, budget_s, threads, seed_first=0):
+    from ocr_rs_b200 import synth
+    wd = synth.make_detector_weights(0, "structured")
+    wr = synth.make_rec_weights(1)
+    imgs = synth.document_image_shard(seed_first, n_images, H, W)
+    glyphs = synth.make_glyphs(n_images * GLYPHS_PER_IMAGE, 1, "strokes")
+    adj = np.ones((1, 2))
+    cpu_path(wd, wr, imgs[:1], glyphs[:GLYPHS_PER_IMAGE], adj, threads)  # warm-up
+    done, t0 = 0, time.time()
+    while done < n_images and (time.time() - t0 < budget_s or done == 0):
+        cpu_path(wd, wr, imgs[done:done + 1], glyphs[done * GLYPHS_PER_IMAGE:(done + 1) * GLYPHS_PER_IMAGE], adj, threads)
+        done += 1
+    dt = time.time() - t0
+    return done / dt, done, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = 4
+    times = []
+    total = args.warmup + args.steps
+    for s in range(total):
+        v, done, dt = time_cpu_sample(per_step, 1e9, threads)
+        if s >= args.warmup:
+            times.append(dt / done)
+    sec_per_img = statistics.mean(times)
+    value = 1.0 / sec_per_img
+    sample = f"{per_step} images 800x800 (+{GLYPHS_PER_IMAGE} glyphs each) per step, batch 1, torch {threads} threads + single-thread C post-proc"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * sec_per_img * per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg4: detect+recognize, 800x800 synthetic document images (bounded CPU sample of the 1024-image batch)",
+                   "images_per_step": per_step, "glyphs_per_image": GLYPHS_PER_IMAGE},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is Rust (tch/libtorch + imageproc + Clipper) and cannot be built in this image; this arm times the oracle port of its CPU path",
+    }))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=TOTAL_IMAGES)
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    assert args.warmup >= 3 or os.environ.get("BENCH_ALLOW_SHORT"), "timing rules: W >= 3"
+
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from ocr_rs_b200 import _ffi, sharding, synth
+    from ocr_rs_b200.char_recognition.model import Net
+    from ocr_rs_b200.text_detection.model import resnet18
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = _ffi.Context(local)
+    det = resnet18(synth.make_detector_weights(0, "structured"), args.mode, ctx)
+    rec = Net(synth.make_rec_weights(1), ctx)
+    first, count = sharding.shard_range(args.images, rank, world)
+    imgs = synth.document_image_shard(first, count, H, W)
+    glyphs = synth.make_glyphs(args.images * GLYPHS_PER_IMAGE, 1, "strokes")[first * GLYPHS_PER_IMAGE:(first + count) * GLYPHS_PER_IMAGE]
+    adj = np.ones((count, 2), np.float64)
+    n_gl = len(glyphs)
+
+    host_imgs = torch.from_numpy(imgs).pin_memory()
+    host_gl = torch.from_numpy(glyphs).pin_memory()
+    host_am = torch.empty(n_gl, dtype=torch.int32).pin_memory()
+    dev_imgs = host_imgs.cuda()
+    dev_gl = host_gl.cuda()
+    dev_am = torch.empty(n_gl, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    L = _ffi.lib()
+
+    def step(images, gl, am, keep=False):
+        h = _ffi.c_p()
+        _ffi.check(L.ocrb_detect_and_recognize(det._h, rec._h, _ffi.ptr(images), _ffi.ptr(adj), count, H, W, None,
+                                               _ffi.ptr(gl), n_gl, _ffi.ptr(am), C.byref(h)))
+        if keep:
+            return _ffi.Polygons(h)
+        n = int(L.ocrb_polygons_image_offsets(h)[count])
+        L.ocrb_polygons_free(h)
+        return n
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        with torch.cuda.stream(stream):
+            e0.record()
+        for _ in range(steps):
+            fn()
+        with torch.cuda.stream(stream):
+            e1.record()
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    # ---- value: device-resident inputs
+    for _ in range(args.warmup):
+        n_poly = step(dev_imgs, dev_gl, dev_am)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.launch_count
+    ms_dev, t0, t1 = timed(lambda: step(dev_imgs, dev_gl, dev_am), args.steps)
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    # ---- e2e: pinned host inputs, results to the host, host gather of the polygons
+    d2h = [0]
+
+    def e2e_step():
+        res = step(host_imgs, host_gl, host_am, keep=True)
+        d2h[0] = res.xy.nbytes + res.all_scores.nbytes + res.point_offsets.nbytes + res.image_offsets.nbytes + host_am.numel() * 4
+        sharding.gather_polygon_scores(res.polygons, res.scores)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    ms_e2e, _, _ = timed(e2e_step, args.steps)
+
+    # ---- per-kernel timeline of one more device-resident step (CUDA events on the ctx stream)
+    ctx.profile_begin()
+    step(dev_imgs, dev_gl, dev_am)
+    prof = ctx.profile_end()
+    tc_ms = sum(ms for k, (c, ms) in prof.items() if k.startswith("tc:"))
+    tc_n = sum(c for k, (c, ms) in prof.items() if k.startswith("tc:"))
+    all_ms = sum(ms for c, ms in prof.values())
+
+    lt = torch.tensor([float(launches)], device="cuda")
+    if world > 1:
+        dist.all_reduce(lt)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak_tf, peak_hbm, peak_src = peaks()
+    flops_step = tc_flops_per_image(H, W) * count
+    achieved = flops_step / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    groups = {}
+    for k, (c, ms) in prof.items():
+        g = "conv_tc (tcgen05)" if k.startswith("tc:") else k
+        cc, mm = groups.get(g, (0, 0.0))
+        groups[g] = (cc + c, mm + ms)
+    top = sorted(groups.items(), key=lambda kv: -kv[1][1])[:8]
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, done, dt = time_cpu_sample(48, 12.0, threads)
+        cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"{done} of the {args.images} images (+{GLYPHS_PER_IMAGE} glyphs each), batch 1, {dt:.1f} s: torch-CPU restatement ({threads} threads) + single-thread C post-proc"}
+
+    out = {
+        "metric": METRIC, "value": args.images * args.steps / (ms_dev * 1e-3), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": args.mode if args.mode == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"cfg4: end-to-end detect+recognize, {args.images} synthetic 800x800 document images sharded by index over {world} GPU(s); "
+                               "structured-head random weights (SURVEY 8d)", "images_per_step": args.images, "images_per_gpu": count,
+                   "glyphs_per_image": GLYPHS_PER_IMAGE, "l2": "inputs (0.64 MB/image) larger than L2; no flush needed",
+                   "polygons_per_step_rank0": n_poly},
+        "e2e": {"value": args.images * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
+                "h2d_bytes_per_step": int(host_imgs.numel() + host_gl.numel() + adj.nbytes) * world, "d2h_bytes_per_step": int(d2h[0]) * world},
+        "gpu_launches": int(lt.item()),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                     "traffic": None, "kernel": "conv_tc_kernel (all tcgen05 implicit-GEMM launches of one step)", "launches": tc_n,
+                     "avg_launch_ms": tc_ms / max(tc_n, 1), "flops_per_image": tc_flops_per_image(H, W), "peak_source": peak_src,
+                     "share_of_step": tc_ms / all_ms if all_ms else None},
+        "kernels_ms_per_step": {k: round(v[1], 3) for k, v in top},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

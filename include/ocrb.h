@@ -60,6 +60,13 @@ void *ocrb_ctx_stream(ocrb_ctx *ctx); /* cudaStream_t the ctx launches on */
 int ocrb_ctx_device(ocrb_ctx *ctx);
 /* number of kernels this ctx has launched since creation (bench.py "gpu_launches") */
 int64_t ocrb_ctx_launch_count(ocrb_ctx *ctx);
+/* per-launch CUDA-event timeline (replaces the measure_time! macro, macros.rs:46-71).
+ * begin: synchronise and start recording one event per launch/copy on the ctx stream.
+ * end: synchronise, stop, and write "name count total_ms\n" lines (one per kernel name, in
+ * first-seen order) into buf; *needed receives the byte count including the NUL — call with
+ * buf == NULL to size the buffer (the timeline is kept until the next begin). */
+int ocrb_ctx_profile_begin(ocrb_ctx *ctx);
+int ocrb_ctx_profile_end(ocrb_ctx *ctx, char *buf, size_t cap, size_t *needed);
 
 /* ---- image_ops ----------------------------------------------------------------------
  * image_ops::preprocess_image (image_ops.rs:188-220) minus the file decode:

@@ -37,6 +37,8 @@ SIGNATURES = {
     "ocrb_ctx_stream": (c_p, [c_p]),
     "ocrb_ctx_device": (C.c_int, [c_p]),
     "ocrb_ctx_launch_count": (i64, [c_p]),
+    "ocrb_ctx_profile_begin": (C.c_int, [c_p]),
+    "ocrb_ctx_profile_end": (C.c_int, [c_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ocrb_resize_dims": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int)] * 2),
     "ocrb_preprocess_rgba": (C.c_int, [c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p,
                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -144,6 +146,21 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().ocrb_ctx_launch_count(self._h))
+
+    def profile_begin(self):
+        check(lib().ocrb_ctx_profile_begin(self._h))
+
+    def profile_end(self):
+        """-> {kernel name: (launch count, total ms)} since profile_begin()."""
+        need = C.c_size_t(0)
+        check(lib().ocrb_ctx_profile_end(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(lib().ocrb_ctx_profile_end(self._h, buf, need.value, C.byref(need)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(" ", 2)
+            out[name] = (int(cnt), float(ms))
+        return out
 
     def close(self):
         if self._h:

@@ -94,6 +94,47 @@ void *ocrb_ctx_stream(ocrb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullpt
 int ocrb_ctx_device(ocrb_ctx *ctx) { return ctx ? ctx->device : -1; }
 int64_t ocrb_ctx_launch_count(ocrb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int ocrb_ctx_profile_begin(ocrb_ctx *ctx) {
+  OCRB_REQUIRE(ctx, "null ctx");
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  OCRB_TRY(sync(ctx));
+  ctx->prof.used = 0;
+  ctx->prof.on = true;
+  prof_mark(ctx, "begin");
+  return OCRB_OK;
+}
+
+int ocrb_ctx_profile_end(ocrb_ctx *ctx, char *buf, size_t cap, size_t *needed) {
+  OCRB_REQUIRE(ctx && needed, "null argument");
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  Profiler &pr = ctx->prof;
+  pr.on = false;
+  OCRB_TRY(sync(ctx));
+  // aggregate by name, keeping first-seen order
+  std::vector<std::string> order;
+  std::vector<double> total;
+  std::vector<long long> count;
+  for (size_t i = 1; i < pr.used; ++i) {
+    float ms = 0.f;
+    OCRB_CUDA(cudaEventElapsedTime(&ms, pr.ev[i - 1], pr.ev[i]));
+    size_t k = 0;
+    for (; k < order.size(); ++k)
+      if (order[k] == pr.names[i]) break;
+    if (k == order.size()) { order.push_back(pr.names[i]); total.push_back(0.0); count.push_back(0); }
+    total[k] += ms;
+    count[k] += 1;
+  }
+  std::string out;
+  char line[256];
+  for (size_t k = 0; k < order.size(); ++k) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", order[k].c_str(), count[k], total[k]);
+    out += line;
+  }
+  *needed = out.size() + 1;
+  if (buf && cap >= out.size() + 1) memcpy(buf, out.c_str(), out.size() + 1);
+  return OCRB_OK;
+}
+
 // ---- image_ops -------------------------------------------------------------------------
 int ocrb_resize_dims(int sw, int sh, int W, int H, int *rw, int *rh) {
   OCRB_REQUIRE(rw && rh && sw > 0 && sh > 0 && W > 0 && H > 0, "bad argument");

@@ -95,6 +95,17 @@ struct PinBuf {
 
 struct PostprocWorkspace;  // postproc.cu
 
+// per-launch CUDA-event timeline of one ctx (the B200 counterpart of the reference's
+// measure_time! macro, macros.rs:46-71): when enabled, check_launch()/prof_mark() record an
+// event after every launch or copy; the span between consecutive events is attributed to
+// the later one's name.  Off by default (zero cost: one branch per launch).
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> names;
+  size_t used = 0;
+};
+
 }  // namespace ocrb
 
 struct ocrb_ctx {
@@ -106,6 +117,7 @@ struct ocrb_ctx {
   ocrb::DevBuf stage[6];
   ocrb::PinBuf pin[3];
   ocrb::PostprocWorkspace *pp = nullptr;
+  ocrb::Profiler prof;
 };
 
 namespace ocrb {
@@ -155,8 +167,23 @@ inline int sync(ocrb_ctx *ctx) {
   return OCRB_OK;
 }
 
+inline void prof_mark(ocrb_ctx *ctx, const char *what) {
+  Profiler &pr = ctx->prof;
+  if (!pr.on) return;
+  if (pr.used == pr.ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { pr.on = false; return; }
+    pr.ev.push_back(e);
+    pr.names.emplace_back();
+  }
+  pr.names[pr.used] = what;
+  cudaEventRecord(pr.ev[pr.used], ctx->stream);
+  pr.used += 1;
+}
+
 inline int check_launch(ocrb_ctx *ctx, const char *what) {
   ctx->launches += 1;
+  prof_mark(ctx, what);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("kernel launch %s -> %s", what, cudaGetErrorString(e));

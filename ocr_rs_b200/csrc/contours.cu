@@ -261,8 +261,9 @@ __global__ void approx_dp_kernel(const ushort2 *__restrict__ chain, const int64_
   const int n = (int)(chain_off[c + 1] - off);
   const ushort2 *p = chain + off;
   ushort2 *out = dp_out + off;
-  if (n < 4) {  // cannot yield >= 4 polygon points; the caller's filter drops it
-    dp_count[c] = 0;
+  if (n == 1) {  // the open chain {p0, p0} minus the closing pop (the general loop would write 2 slots)
+    out[0] = p[0];
+    dp_count[c] = 1;
     return;
   }
   // arc_length(closed = true)

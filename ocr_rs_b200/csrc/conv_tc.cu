@@ -423,7 +423,7 @@ int make_weight_tensor_map(CUtensorMap *map, const void *base, int Cout, int Kto
 }
 
 template <int N_TILE, int STAGES, int EPI>
-static int launch_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvTcParams &p, int num_tiles) {
+static int launch_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvTcParams &p, int num_tiles, const char *tag) {
   using L = TcSmem<N_TILE, STAGES>;
   static bool attr_set[16] = {false};
   auto kern = conv_tc_kernel<N_TILE, STAGES, EPI>;
@@ -433,10 +433,10 @@ static int launch_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &
   }
   int grid = num_tiles < ctx->sm_count ? num_tiles : ctx->sm_count;
   kern<<<grid, TC_THREADS, L::DYN_BYTES, ctx->stream>>>(tmA, tmB, p);
-  return check_launch(ctx, "conv_tc");
+  return check_launch(ctx, tag);
 }
 
-int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, int epi) {
+int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, int epi, const char *tag) {
   p.tiles_x = (int)cdiv(p.Wo, TC_TW);
   p.tiles_y = (int)cdiv(p.Ho, TC_TH);
   p.num_n_tiles = p.Cout / n_tile;
@@ -444,12 +444,12 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
   const int num_tiles = p.tiles_x * p.tiles_y * p.B * p.num_n_tiles;
   if (epi == EPI_HEAD) {
     if (n_tile != 256) { set_error("conv_tc head needs N tile 256"); return OCRB_ERR_INVALID; }
-    return launch_one<256, 4, EPI_HEAD>(ctx, tmA, tmB, p, num_tiles);
+    return launch_one<256, 4, EPI_HEAD>(ctx, tmA, tmB, p, num_tiles, tag);
   }
   switch (n_tile) {
-    case 64: return launch_one<64, 6, EPI_STD>(ctx, tmA, tmB, p, num_tiles);
-    case 128: return launch_one<128, 5, EPI_STD>(ctx, tmA, tmB, p, num_tiles);
-    case 256: return launch_one<256, 4, EPI_STD>(ctx, tmA, tmB, p, num_tiles);
+    case 64: return launch_one<64, 6, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag);
+    case 128: return launch_one<128, 5, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag);
+    case 256: return launch_one<256, 4, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag);
   }
   set_error("conv_tc: unsupported N tile %d", n_tile);
   return OCRB_ERR_INVALID;

@@ -32,6 +32,6 @@ struct ConvTcParams {
 
 int make_act_tensor_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int stride);
 int make_weight_tensor_map(CUtensorMap *map, const void *base, int Cout, int Ktot, int n_tile);
-int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, int epi);
+int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, int epi, const char *tag = "tc:conv");
 
 }  // namespace ocrb

@@ -476,7 +476,8 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     p.scale = c.scale.as<float>(); p.shift = c.shift.as<float>();
     if (p.out && p.out_ldc == 0) p.out_ldc = c.cout;
     p.err = d->err.as<int>();
-    return launch_conv_tc(ctx, *ma, *mb, p, nt, EPI_STD);
+    const std::string tag = "tc:" + name;
+    return launch_conv_tc(ctx, *ma, *mb, p, nt, EPI_STD, tag.c_str());
   };
   const bf *x = x0;
   int h = H4, w = W4;
@@ -540,7 +541,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     q.scale = d->tr1_scale.as<float>(); q.shift = d->tr1_shift.as<float>();
     q.w2 = d->tr2_w.as<float>(); q.b2 = d->tr2_bias; q.thresh = thresh;
     q.prob = prob; q.bitmap = bitmap; q.err = d->err.as<int>();
-    OCRB_TRY(launch_conv_tc(ctx, *ma, *mb, q, 256, EPI_HEAD));
+    OCRB_TRY(launch_conv_tc(ctx, *ma, *mb, q, 256, EPI_HEAD, "tc:head"));
   }
   return OCRB_OK;
 }

@@ -199,6 +199,44 @@ def make_document_images(n, h=800, w=800, seed=3, n_boxes=30):
     return out
 
 
+def make_document_images_fast(n, h=800, w=800, seed=3, n_boxes=30):
+    """Same kind of image as make_document_images, drawn box-window by box-window (about
+    50x faster); used where hundreds of images are needed (bench.py, cfg 4)."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, h, w), np.uint8)
+    for i in range(n):
+        img = rng.integers(0, 40, size=(h, w), dtype=np.uint8)
+        for _ in range(n_boxes):
+            cx, cy = rng.uniform(40, w - 40), rng.uniform(40, h - 40)
+            bw, bh = rng.uniform(30, 160), rng.uniform(8, 40)
+            a = rng.uniform(-0.5, 0.5)
+            r = int(np.ceil(np.hypot(bw, bh) / 2)) + 1
+            x0, x1 = max(0, int(cx) - r), min(w, int(cx) + r + 1)
+            y0, y1 = max(0, int(cy) - r), min(h, int(cy) + r + 1)
+            yy, xx = np.mgrid[y0:y1, x0:x1].astype(np.float32)
+            ca, sa = np.cos(a), np.sin(a)
+            u = (xx - cx) * ca + (yy - cy) * sa
+            v = -(xx - cx) * sa + (yy - cy) * ca
+            m = (np.abs(u) < bw / 2) & (np.abs(v) < bh / 2)
+            img[y0:y1, x0:x1][m] = np.uint8(rng.uniform(150, 255))
+        out[i] = img
+    return out
+
+
+def document_image_shard(first, count, h=800, w=800, seed=3, unique=128):
+    """Images [first, first+count) of the endless synthetic 'document' set: image i is base
+    image i % unique rolled by a shift that depends on i // unique, so it is a function of the
+    global index only (identical no matter how the index range is sharded across GPUs)."""
+    base = make_document_images_fast(min(unique, first + count), h, w, seed)  # sequential rng: a prefix is stable
+    out = np.empty((count, h, w), np.uint8)
+    for k in range(count):
+        i = first + k
+        rep = i // unique
+        img = base[i % unique]
+        out[k] = img if rep == 0 else np.roll(img, (37 * rep % h, 53 * rep % w), (0, 1))
+    return out
+
+
 def make_blob_prob_map(h=800, w=800, n_blobs=40, seed=4, frame=1, ring_frac=0.1, near_thresh=64, max_w=120, max_h=60):
     """Synthetic probability map (cfg 5 generator).
 
