@@ -267,6 +267,9 @@ def main():
     tc_n = sum(c for k, (c, ms) in prof.items() if k.startswith("tc:"))
     all_ms = sum(ms for c, ms in prof.values())
 
+    if rank == 0 and os.environ.get("BENCH_LAYERS"):
+        for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {ms:9.3f} ms  x{c:5d}  {k}", file=sys.stderr)
     lt = torch.tensor([float(launches)], device="cuda")
     if world > 1:
         dist.all_reduce(lt)

@@ -1,0 +1,312 @@
+// 3x3 stride-1 convolution (model.rs:4-12 with k=3, s=1, p=1) as an implicit GEMM on tcgen05
+// with the input tile RESIDENT in shared memory across the nine filter taps.
+//
+// Why: with one TMA box per (tap, 64-channel chunk) the activation tile is fetched nine
+// times and a 64-wide output tile moves 24 KB through L2 per 128 MMA cycles — the first
+// version of the engine (conv_tc.cu) ran those layers at the L2 bandwidth, not the tensor
+// pipe.  Here:
+//   * per 64-channel chunk ONE TMA box {64 ch, PW, TH+2 rows} (hardware zero fill = padding)
+//     lands the halo'd tile as rows of 128 B, row index = y * PW + x (128B swizzle, K-major);
+//   * the GEMM M index runs LINEARLY over that padded tile (pitch PW = TW + 2; the two extra
+//     columns per row produce junk outputs that are never stored), so the A operand of tap
+//     (r, s) is the same tile shifted by (r * PW + s) rows — a pure start-address offset in
+//     the UMMA shared-memory descriptor, no data movement;
+//   * one CTA work unit = G sub-tiles of 128 rows x N_TILE channels, G accumulators in TMEM
+//     (two sets: the epilogue of unit i overlaps the MMAs of unit i+1), so every streamed
+//     weight tile [N_TILE x 64] feeds G * 4 MMAs.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue
+// (two warps per TMEM lane quarter, each taking half of the channels).
+// Epilogue = folded batch-norm scale/shift (+ residual) (+ ReLU) -> bf16 NHWC, optionally
+// replicated x rep into a channel slice of the concat buffer (model.rs:82-97, :140).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace ocrb {
+
+constexpr int HL_THREADS = 320;
+constexpr int HL_EPI_WARPS = 8;
+
+struct HaloGeom {
+  int PW, TH, TW;      // padded pitch, tile rows, valid tile columns (TW = PW - 2)
+  int a_stage_bytes;   // bytes of one A stage (multiple of 1024)
+  int a_tx_bytes;      // bytes one halo TMA box writes = (TH + 2) * PW * 128
+  int a_stages, b_stages;
+};
+
+template <int N_TILE, int G>
+__global__ void __launch_bounds__(HL_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p, const HaloGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int B_BYTES = N_TILE * 128;
+  uint8_t *sA = smem;
+  uint8_t *sB = smem + g.a_stages * g.a_stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + g.b_stages * B_BYTES);
+  uint64_t *a_full = bars, *a_empty = a_full + g.a_stages;
+  uint64_t *b_full = a_empty + g.a_stages, *b_empty = b_full + g.b_stages;
+  uint64_t *tfull = b_empty + g.b_stages, *tempty = tfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  float *s_scale = reinterpret_cast<float *>(tmem_slot + 4);
+  float *s_shift = s_scale + 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 2 * G * N_TILE <= 256 ? 256 : 512;
+  static_assert(2 * G * N_TILE <= 512, "accumulators do not fit TMEM");
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int num_m_tiles = tiles_per_img * p.B;
+  const int num_units = num_m_tiles * p.num_n_tiles;
+  const int chunks = p.cin_chunks;
+
+  for (int i = threadIdx.x; i < p.Cout && i < 512; i += HL_THREADS) {
+    s_scale[i] = p.scale ? p.scale[i] : 1.0f;
+    s_shift[i] = p.shift ? p.shift[i] : 0.0f;
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < g.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < g.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], HL_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int n_tile = unit / num_m_tiles, m_tile = unit - n_tile * num_m_tiles;
+        const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
+        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        for (int ck = 0; ck < chunks; ++ck) {
+          mbar_wait(&a_empty[as], aph ^ 1, p.err, 11);
+          mbar_expect_tx(&a_full[as], g.a_tx_bytes);
+          tma_load_4d(sA + as * g.a_stage_bytes, &tmA, &a_full[as], ck * 64, tx * g.TW - 1, ty * g.TH - 1, b);
+          if (++as == g.a_stages) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[bs], bph ^ 1, p.err, 12);
+            mbar_expect_tx(&b_full[bs], B_BYTES);
+            tma_load_2d(sB + bs * B_BYTES, &tmB, &b_full[bs], (tap * chunks + ck) * 64, n_tile * N_TILE);
+            if (++bs == g.b_stages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc(N_TILE);
+    int as = 0, bs = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, acc_phase = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1, p.err, 13);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)(acc * G * N_TILE);
+      for (int ck = 0; ck < chunks; ++ck) {
+        mbar_wait(&a_full[as], aph, p.err, 14);
+        const uint64_t a0 = make_smem_desc(sA + as * g.a_stage_bytes);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_full[bs], bph, p.err, 15);
+          tc_fence_after();
+          if (lane == 0) {
+            const int r = tap / 3, s = tap - 3 * r;
+            const uint64_t bdesc = make_smem_desc(sB + bs * B_BYTES);
+            const uint32_t row_off = (uint32_t)(r * g.PW + s);
+#pragma unroll
+            for (int gi = 0; gi < G; ++gi) {
+              // start address advances by whole 128 B rows: (gi*128 + row_off) * 128 B >> 4
+              const uint64_t adesc = a0 + (uint64_t)((gi * 128 + row_off) * 8);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_base + (uint32_t)(gi * N_TILE), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                          (ck | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&b_empty[bs]);
+            if (tap == 8) {
+              umma_commit(&a_empty[as]);
+              if (ck == chunks - 1) umma_commit(&tfull[acc]);
+            }
+          }
+          __syncwarp();
+          if (++bs == g.b_stages) { bs = 0; bph ^= 1; }
+        }
+        if (++as == g.a_stages) { as = 0; aph ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ================= epilogue =================
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;         // which half of the N_TILE columns
+    constexpr int NH = N_TILE / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int n_tile = unit / num_m_tiles, m_tile = unit - n_tile * num_m_tiles;
+      const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
+      const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+      mbar_wait(&tfull[acc], acc_phase, p.err, 16);
+      tc_fence_after();
+#pragma unroll 1
+      for (int gi = 0; gi < G; ++gi) {
+        const int m = gi * 128 + quarter * 32 + lane;
+        const int yl = m / g.PW, xl = m - yl * g.PW;
+        const int y = ty * g.TH + yl, x = tx * g.TW + xl;
+        const bool valid = yl < g.TH && xl < g.TW && y < p.Ho && x < p.Wo;
+        const int64_t pix = ((int64_t)b * p.Ho + y) * p.Wo + x;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * G + gi) * N_TILE + half * NH);
+        const int n0 = n_tile * N_TILE + half * NH;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NH; c0 += 32) {
+          // residual prefetch (issued before the TMEM load so its latency overlaps)
+          uint4 rr[4];
+          if (p.residual && valid) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + pix * p.Cout + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rr[j] = rp[j];
+          }
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          if (valid) {
+            const int n = n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_scale[n + j], s_shift[n + j]);
+            if (p.residual) {
+              const uint32_t ru[16] = {rr[0].x, rr[0].y, rr[0].z, rr[0].w, rr[1].x, rr[1].y, rr[1].z, rr[1].w,
+                                       rr[2].x, rr[2].y, rr[2].z, rr[2].w, rr[3].x, rr[3].y, rr[3].z, rr[3].w};
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { float2 f = unpack_bf16(ru[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+            uint4 o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            const int rep = p.rep;
+            const int64_t Wr = (int64_t)p.Wo * rep;
+            for (int ry = 0; ry < rep; ++ry)
+              for (int rx = 0; rx < rep; ++rx) {
+                const int64_t opix = ((int64_t)b * p.Ho * rep + (int64_t)y * rep + ry) * Wr + (int64_t)x * rep + rx;
+                uint4 *op = reinterpret_cast<uint4 *>(p.out + opix * p.out_ldc + p.out_coff + n);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) op[j] = o[j];
+              }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+// Picks the padded pitch / tile height for a Wo-wide map: TH * PW <= G * 128, valid fraction
+// (TW / PW) * (TH * PW / (G*128)) * (coverage of Wo and Ho by whole tiles) maximised.
+static void pick_geom(int Ho, int Wo, int G, int *PW, int *TH) {
+  double best = -1.0;
+  for (int tw = 8; tw <= 254 && tw <= Wo + 7; ++tw) {
+    const int pw = tw + 2;
+    int th = G * 128 / pw;
+    if (th > 254) th = 254;
+    if (th < 1) continue;
+    if (th > Ho) th = Ho;
+    const int tx = (Wo + tw - 1) / tw, ty = (Ho + th - 1) / th;
+    const double eff = (double)Ho * Wo / ((double)tx * ty * G * 128);
+    // A traffic per output grows with the halo: prefer taller tiles at equal efficiency
+    static const double halo_w = getenv("OCRB_HALO_W") ? atof(getenv("OCRB_HALO_W")) : 0.3;  // tuning knob
+    const double score = eff - halo_w * ((double)(th + 2) * pw / ((double)th * tw) - 1.0);
+    if (score > best) { best = score; *PW = pw; *TH = th; }
+  }
+}
+
+int halo_geometry(int Ho, int Wo, int n_tile, int G, HaloGeom *out) {
+  HaloGeom g;
+  pick_geom(Ho, Wo, G, &g.PW, &g.TH);
+  g.TW = g.PW - 2;
+  const int halo_rows = (g.TH + 2) * g.PW;
+  const int read_rows = G * 128 + 2 * g.PW + 2;  // last sub-tile, tap (2,2)
+  int rows = halo_rows > read_rows ? halo_rows : read_rows;
+  g.a_stage_bytes = ((rows * 128 + 1023) / 1024) * 1024;
+  g.a_tx_bytes = halo_rows * 128;
+  const int b_bytes = n_tile * 128;
+  const int budget = 227 * 1024 - 1024 /*align*/ - 4608 /*barriers + scale/shift*/;
+  g.a_stages = 2;
+  g.b_stages = (budget - g.a_stages * g.a_stage_bytes) / b_bytes;
+  if (g.b_stages > 8) {
+    // room to spare: a third A stage helps layers with many input chunks
+    if (budget - 3 * g.a_stage_bytes >= 6 * b_bytes) { g.a_stages = 3; g.b_stages = (budget - 3 * g.a_stage_bytes) / b_bytes; }
+    if (g.b_stages > 8) g.b_stages = 8;
+  }
+  if (g.b_stages < 2) { set_error("conv_halo: tile %dx%d does not fit shared memory", g.PW, g.TH); return OCRB_ERR_INTERNAL; }
+  *out = g;
+  return OCRB_OK;
+}
+
+int make_act_tensor_map_box(CUtensorMap *map, const void *base, int B, int H, int W, int C, int box_w, int box_h);
+
+int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G) {
+  HaloGeom g;
+  OCRB_TRY(halo_geometry(H, W, n_tile, G, &g));
+  return make_act_tensor_map_box(map, base, B, H, W, C, g.PW, g.TH + 2);
+}
+
+template <int N_TILE, int G>
+static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvTcParams &p, const HaloGeom &g,
+                           int num_units, const char *tag) {
+  static bool attr_set[16] = {false};
+  auto kern = conv_halo_kernel<N_TILE, G>;
+  if (!attr_set[ctx->device & 15]) {
+    OCRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[ctx->device & 15] = true;
+  }
+  const int smem = 1024 + g.a_stages * g.a_stage_bytes + g.b_stages * N_TILE * 128 + 4608;
+  const int grid = num_units < ctx->sm_count ? num_units : ctx->sm_count;
+  kern<<<grid, HL_THREADS, smem, ctx->stream>>>(tmA, tmB, p, g);
+  return check_launch(ctx, tag);
+}
+
+// 3x3 / stride 1 / pad 1 only; n_tile in {64 (G = 4), 128 (G = 2)}
+int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, const char *tag) {
+  if (p.R != 3 || p.S != 3 || p.stride != 1 || p.pad != 1 || p.sum_out || !p.out) { set_error("conv_halo: unsupported convolution"); return OCRB_ERR_INVALID; }
+  if (p.Cout % n_tile != 0 || p.Cout > 512) { set_error("conv_halo: Cout %d vs N tile %d", p.Cout, n_tile); return OCRB_ERR_INVALID; }
+  const int G = n_tile == 64 ? 4 : 2;
+  HaloGeom g;
+  OCRB_TRY(halo_geometry(p.Ho, p.Wo, n_tile, G, &g));
+  p.tiles_x = (int)cdiv(p.Wo, g.TW);
+  p.tiles_y = (int)cdiv(p.Ho, g.TH);
+  p.num_n_tiles = p.Cout / n_tile;
+  const int num_units = p.tiles_x * p.tiles_y * p.B * p.num_n_tiles;
+  if (n_tile == 64) return launch_halo_one<64, 4>(ctx, tmA, tmB, p, g, num_units, tag);
+  if (n_tile == 128) return launch_halo_one<128, 2>(ctx, tmA, tmB, p, g, num_units, tag);
+  set_error("conv_halo: unsupported N tile %d", n_tile);
+  return OCRB_ERR_INVALID;
+}
+
+}  // namespace ocrb

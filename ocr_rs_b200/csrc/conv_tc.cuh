@@ -34,4 +34,8 @@ int make_act_tensor_map(CUtensorMap *map, const void *base, int B, int H, int W,
 int make_weight_tensor_map(CUtensorMap *map, const void *base, int Cout, int Ktot, int n_tile);
 int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, int epi, const char *tag = "tc:conv");
 
+// conv_halo.cu: 3x3 stride-1 convolutions with the halo'd input tile resident in shared memory
+int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G);
+int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, const char *tag);
+
 }  // namespace ocrb

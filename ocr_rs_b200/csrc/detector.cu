@@ -462,12 +462,24 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
                                                                        d->stem_shift.as<float>(), x0);
     OCRB_TRY(check_launch(ctx, "stem_fused_bf16"));
   }
+  static const bool use_halo = !(getenv("OCRB_CONV") && strcmp(getenv("OCRB_CONV"), "tc") == 0);
   auto conv = [&](const std::string &name, const bf *in, int h, int w, ConvTcParams p) -> int {
     DevConv &c = d->conv[name];
     CUtensorMap *ma, *mb;
-    const int nt = n_tile_for(c.cout);
-    OCRB_TRY(get_map(d, "a." + name, in, B, h, w, c.cin, c.stride, &ma));
-    OCRB_TRY(get_wmap(d, "w." + name, c.w16.p, c.cout, c.k * c.k * c.cin, nt, &mb));
+    const bool halo = use_halo && c.k == 3 && c.stride == 1 && !p.sum_out && p.out;
+    const int nt = halo ? (c.cout == 64 ? 64 : 128) : n_tile_for(c.cout);
+    if (halo) {
+      auto it = d->maps.m.find("h." + name);
+      if (it == d->maps.m.end()) {
+        CUtensorMap m;
+        OCRB_TRY(make_halo_act_map(&m, in, B, h, w, c.cin, nt, nt == 64 ? 4 : 2));
+        it = d->maps.m.emplace("h." + name, m).first;
+      }
+      ma = &it->second;
+    } else {
+      OCRB_TRY(get_map(d, "a." + name, in, B, h, w, c.cin, c.stride, &ma));
+    }
+    OCRB_TRY(get_wmap(d, (halo ? "wh." : "w.") + name, c.w16.p, c.cout, c.k * c.k * c.cin, nt, &mb));
     p.B = B;
     p.Ho = (h + 2 * c.pad - c.k) / c.stride + 1;
     p.Wo = (w + 2 * c.pad - c.k) / c.stride + 1;
@@ -477,6 +489,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     if (p.out && p.out_ldc == 0) p.out_ldc = c.cout;
     p.err = d->err.as<int>();
     const std::string tag = "tc:" + name;
+    if (halo) return launch_conv_halo(ctx, *ma, *mb, p, nt, tag.c_str());
     return launch_conv_tc(ctx, *ma, *mb, p, nt, EPI_STD, tag.c_str());
   };
   const bf *x = x0;
