@@ -28,6 +28,8 @@ int launch_convt2x2_fp32(ocrb_ctx *, const float *, int, int, int, int, int, con
 int launch_convt2x2_sigmoid_fp32(ocrb_ctx *, const float *, int, int, int, int, const float *, float, float *);
 int launch_nhwc_to_nchw_fp32(ocrb_ctx *, const float *, int, int, int, int, int, float *);
 int launch_u8_to_f32(ocrb_ctx *, const uint8_t *, int64_t, float, float *);
+// stem_tc.cu
+int launch_stem_tc(ocrb_ctx *, const void *, int, int, int, int, const float *, const float *, const float *, __nv_bfloat16 *, int *);
 
 constexpr float BN_EPS = 1e-5f;  // tch nn::BatchNormConfig default
 
@@ -456,7 +458,11 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
   }
 
   // stem
-  {
+  static const bool stem_cuda_cores = getenv("OCRB_STEM") && strcmp(getenv("OCRB_STEM"), "cuda") == 0;
+  if (!stem_cuda_cores) {
+    OCRB_TRY(launch_stem_tc(ctx, img, sizeof(TIn) == 1, B, H, W, d->stem_w.as<float>(), d->stem_scale.as<float>(),
+                            d->stem_shift.as<float>(), x0, d->err.as<int>()));
+  } else {
     const int tiles = (int)(cdiv(W4, ST_PW) * cdiv(H4, ST_PH)) * B;
     stem_fused_bf16_kernel<TIn><<<tiles, ST_THREADS, 0, ctx->stream>>>(img, B, H, W, d->stem_w.as<float>(), d->stem_scale.as<float>(),
                                                                        d->stem_shift.as<float>(), x0);

@@ -1,0 +1,207 @@
+// Detector stem on the tensor cores (BF16 mode):
+//   conv 7x7 s2 p3 (1 -> 64, model.rs:68,109) + batch-norm + ReLU (:69,110-111) + max_pool2d
+//   3x3 s2 p1 (:112), fused; u8 or f32 grey levels in, NHWC bf16 [B][H/4][W/4][64] out.
+//
+// The 1-channel 7x7 convolution is an implicit GEMM with K = 7 rows x 8 columns (the 8th
+// column carries a zero weight) = 56, padded to 64: for conv pixel (cy, cx) the 16-byte K
+// chunk j is the 8 consecutive input pixels (2cy + j, 2cx .. 2cx + 7), so the A tile is a pure
+// 16-byte gather from a bf16 copy of the input patch — built by the CTA in shared memory in
+// the 128B-swizzled K-major layout UMMA expects (no im2col matrix ever touches HBM).
+// One CTA unit = 8 x 14 pooled pixels <- 17 x 29 conv pixels (493 GEMM rows = 4 MMA tiles of
+// 128, accumulators in TMEM) <- 39 x 64 input patch.  After the MMAs the A region is reused
+// as the bf16 conv tile from which the 3x3/s2 max-pool is taken.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace ocrb {
+
+constexpr int SK_PH = 8, SK_PW = 14;                       // pooled tile
+constexpr int SK_CH = 2 * SK_PH + 1, SK_CW = 2 * SK_PW + 1;  // conv tile 17 x 29
+constexpr int SK_ROWS = SK_CH * SK_CW;                     // 493 valid GEMM rows
+constexpr int SK_IH = 2 * SK_CH + 5, SK_IW = 64;           // input patch 39 x 64 (63 used + the zero-weight column)
+constexpr int SK_THREADS = 256;
+constexpr int SK_A_BYTES = 4 * 128 * 128;                  // 4 M tiles x 128 rows x 128 B
+constexpr int SK_OFF_B = SK_A_BYTES;                       // 64 x 128 B
+constexpr int SK_OFF_PATCH = SK_OFF_B + 64 * 128;          // bf16 [39][64]
+constexpr int SK_OFF_MISC = SK_OFF_PATCH + SK_IH * SK_IW * 2;
+constexpr int SK_SMEM = SK_OFF_MISC + 1024 + 1024;         // scale/shift/barrier + alignment slack
+
+template <class TIn>
+__global__ void __launch_bounds__(SK_THREADS, 2)
+stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__restrict__ w /*[49][64]*/,
+               const float *__restrict__ scale, const float *__restrict__ shift, __nv_bfloat16 *__restrict__ out, int *err) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sA = smem;
+  uint8_t *sB = smem + SK_OFF_B;
+  __nv_bfloat16 *s_patch = reinterpret_cast<__nv_bfloat16 *>(smem + SK_OFF_PATCH);
+  float *s_scale = reinterpret_cast<float *>(smem + SK_OFF_MISC);
+  float *s_shift = s_scale + 64;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(s_shift + 64);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Hc = H / 2, Wc = W / 2, Hp = H / 4, Wp = W / 4;
+  const int tiles_x = (Wp + SK_PW - 1) / SK_PW, tiles_y = (Hp + SK_PH - 1) / SK_PH;
+  const int units = tiles_x * tiles_y * B;
+
+  // ---- one-time setup: zero A (no NaN bit patterns under the zero weights), weights -> B, TMEM
+  for (int i = tid; i < SK_A_BYTES / 16; i += SK_THREADS) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 64 * 8; i += SK_THREADS) {  // (co, chunk j): k = 8j + s <-> tap (r = j, s)
+    const int co = i >> 3, j = i & 7;
+    uint32_t pk[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float a = 0.f, b = 0.f;
+      if (j < 7) {
+        a = w[(j * 7 + 2 * h) * 64 + co];
+        if (2 * h + 1 < 7) b = w[(j * 7 + 2 * h + 1) * 64 + co];
+      }
+      pk[h] = pack_bf16(a, b);
+    }
+    *reinterpret_cast<uint4 *>(sB + co * 128 + ((j ^ (co & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  if (tid < 64) { s_scale[tid] = scale[tid]; s_shift[tid] = shift[tid]; }
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t idesc = make_idesc(64);
+  uint32_t parity = 0;
+
+  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int b = unit / (tiles_x * tiles_y), t = unit - b * (tiles_x * tiles_y);
+    const int py0 = (t / tiles_x) * SK_PH, px0 = (t % tiles_x) * SK_PW;
+    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;  // conv-grid origin (pool pad 1)
+    const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;  // input origin (conv pad 3)
+    const TIn *img = in + (int64_t)b * H * W;
+    // ---- (a) input patch -> bf16 (u8 grey levels are exact in bf16)
+    for (int i = tid; i < SK_IH * SK_IW; i += SK_THREADS) {
+      const int yy = iy0 + (i >> 6), xx = ix0 + (i & 63);
+      const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (float)img[(int64_t)yy * W + xx] : 0.0f;
+      s_patch[i] = __float2bfloat16(v);
+    }
+    __syncthreads();
+    // ---- (b) A rows: chunk j of row (cy, cx) = patch[2cy + j][2cx .. 2cx + 7]
+    for (int m = tid; m < SK_ROWS; m += SK_THREADS) {
+      const int cy = m / SK_CW, cx = m - cy * SK_CW;
+      uint8_t *row = sA + m * 128;
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(s_patch + (2 * cy) * SK_IW + 2 * cx);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const uint32_t *s4 = src + j * (SK_IW / 2);
+        *reinterpret_cast<uint4 *>(row + ((j ^ (m & 7)) << 4)) = make_uint4(s4[0], s4[1], s4[2], s4[3]);
+      }
+      *reinterpret_cast<uint4 *>(row + ((7 ^ (m & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    // ---- (c) 4 M tiles x 4 K steps of UMMA 128 x 64 x 16
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t bdesc = make_smem_desc(sB);
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const uint64_t adesc = make_smem_desc(sA + mt * 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + mt * 64, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity, err, 21);
+    parity ^= 1;
+    tc_fence_after();
+    // ---- (d) epilogue: BN + ReLU -> bf16 conv tile over the A region (same swizzle)
+    {
+      const int q = warp & 3;
+#pragma unroll 1
+      for (int rep = 0; rep < 2; ++rep) {
+        const int mt = (warp >> 2) + 2 * rep;
+        const int m = mt * 128 + q * 32 + lane;
+        const int cy = m / SK_CW, cx = m - cy * SK_CW;
+        const bool in_grid = m < SK_ROWS && (cy0 + cy) >= 0 && (cy0 + cy) < Hc && (cx0 + cx) >= 0 && (cx0 + cx) < Wc;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          tmem_ld32(taddr + half * 32, v);
+          if (m < SK_ROWS) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const int c = half * 32 + j4 * 8 + 2 * h;
+                // outside the conv grid = max-pool padding (-inf): a large negative finite value
+                const float y0 = in_grid ? fmaxf(fmaf(v[j4 * 8 + 2 * h], s_scale[c], s_shift[c]), 0.0f) : -3.0e38f;
+                const float y1 = in_grid ? fmaxf(fmaf(v[j4 * 8 + 2 * h + 1], s_scale[c + 1], s_shift[c + 1]), 0.0f) : -3.0e38f;
+                pk[h] = pack_bf16(y0, y1);
+              }
+              const int chunk = half * 4 + j4;
+              *reinterpret_cast<uint4 *>(sA + m * 128 + ((chunk ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- (e) 3x3 / s2 max-pool from the conv tile -> global (16 B = 8 channels per thread)
+    for (int i = tid; i < SK_PH * SK_PW * 8; i += SK_THREADS) {
+      const int chunk = i & 7, pp = i >> 3;
+      const int py = pp / SK_PW, px = pp - py * SK_PW;
+      if (py0 + py < Hp && px0 + px < Wp) {
+        __nv_bfloat162 mx[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) mx[h] = __floats2bfloat162_rn(-3.0e38f, -3.0e38f);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int m = (2 * py + r) * SK_CW + 2 * px + s;
+            const uint4 u = *reinterpret_cast<const uint4 *>(sA + m * 128 + ((chunk ^ (m & 7)) << 4));
+            const __nv_bfloat162 *hv = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) mx[h] = __hmax2(mx[h], hv[h]);
+          }
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t *>(&mx[0]); o.y = *reinterpret_cast<uint32_t *>(&mx[1]);
+        o.z = *reinterpret_cast<uint32_t *>(&mx[2]); o.w = *reinterpret_cast<uint32_t *>(&mx[3]);
+        *reinterpret_cast<uint4 *>(out + (((int64_t)b * Hp + py0 + py) * Wp + px0 + px) * 64 + chunk * 8) = o;
+      }
+    }
+    __syncthreads();  // the conv tile / patch are rewritten by the next unit
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int launch_stem_tc(ocrb_ctx *ctx, const void *in, int is_u8, int B, int H, int W, const float *w, const float *scale,
+                   const float *shift, __nv_bfloat16 *out, int *err) {
+  static bool attr_set[16] = {false};
+  if (!attr_set[ctx->device & 15]) {
+    OCRB_CUDA(cudaFuncSetAttribute(stem_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
+    OCRB_CUDA(cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
+    attr_set[ctx->device & 15] = true;
+  }
+  const int Hp = H / 4, Wp = W / 4;
+  const int64_t units = cdiv(Wp, SK_PW) * cdiv(Hp, SK_PH) * B;
+  const int grid = (int)(units < 2 * ctx->sm_count ? units : 2 * ctx->sm_count);
+  if (is_u8)
+    stem_tc_kernel<uint8_t><<<grid, SK_THREADS, SK_SMEM, ctx->stream>>>((const uint8_t *)in, B, H, W, w, scale, shift, out, err);
+  else
+    stem_tc_kernel<float><<<grid, SK_THREADS, SK_SMEM, ctx->stream>>>((const float *)in, B, H, W, w, scale, shift, out, err);
+  return check_launch(ctx, "tc:stem");
+}
+
+}  // namespace ocrb
