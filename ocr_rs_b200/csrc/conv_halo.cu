@@ -24,12 +24,13 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "tc_epilogue.cuh"
 #include "tc_ptx.cuh"
 
 namespace ocrb {
 
-constexpr int HL_THREADS = 320;
 constexpr int HL_EPI_WARPS = 8;
+constexpr int HL_STG_BYTES = HL_EPI_WARPS * 2048;  // per-warp epilogue staging (tc_epilogue.cuh)
 
 struct HaloGeom {
   int PW, TH, TW;      // padded pitch, tile rows, valid tile columns (TW = PW - 2)
@@ -39,20 +40,25 @@ struct HaloGeom {
 };
 
 template <int N_TILE, int G>
-__global__ void __launch_bounds__(HL_THREADS, 1)
+__global__ void __launch_bounds__((1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS) * 32, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p, const HaloGeom g) {
+  // N = 64 MMAs last only 32 tensor-pipe cycles: two issuing warps (sub-tiles split between
+  // them) keep the pipe fed; N = 128 needs one
+  constexpr int MW = G >= 4 ? 2 : 1;
+  constexpr int GW = G / MW;  // sub-tiles per MMA warp
+  constexpr int THREADS = (1 + MW + HL_EPI_WARPS) * 32;
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_scale[512], s_shift[512];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int B_BYTES = N_TILE * 128;
   uint8_t *sA = smem;
   uint8_t *sB = smem + g.a_stages * g.a_stage_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + g.b_stages * B_BYTES);
+  uint8_t *sStg = sB + g.b_stages * B_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sStg + HL_STG_BYTES);
   uint64_t *a_full = bars, *a_empty = a_full + g.a_stages;
   uint64_t *b_full = a_empty + g.a_stages, *b_empty = b_full + g.b_stages;
   uint64_t *tfull = b_empty + g.b_stages, *tempty = tfull + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
-  float *s_scale = reinterpret_cast<float *>(tmem_slot + 4);
-  float *s_shift = s_scale + 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = 2 * G * N_TILE <= 256 ? 256 : 512;
@@ -62,16 +68,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_units = num_m_tiles * p.num_n_tiles;
   const int chunks = p.cin_chunks;
 
-  for (int i = threadIdx.x; i < p.Cout && i < 512; i += HL_THREADS) {
+  for (int i = threadIdx.x; i < p.Cout && i < 512; i += THREADS) {
     s_scale[i] = p.scale ? p.scale[i] : 1.0f;
     s_shift[i] = p.shift ? p.shift[i] : 0.0f;
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < g.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < g.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], HL_EPI_WARPS); }
+    for (int s = 0; s < g.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], MW); }
+    for (int s = 0; s < g.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], MW); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], MW); mbar_init(&tempty[a], HL_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -82,54 +88,59 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        const int n_tile = unit / num_m_tiles, m_tile = unit - n_tile * num_m_tiles;
-        const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
-        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-        for (int ck = 0; ck < chunks; ++ck) {
-          mbar_wait(&a_empty[as], aph ^ 1, p.err, 11);
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int n_tile = unit / num_m_tiles, m_tile = unit - n_tile * num_m_tiles;
+      const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
+      const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+      for (int ck = 0; ck < chunks; ++ck) {
+        mbar_wait(&a_empty[as], aph ^ 1, p.err, 11);
+        if (elect_one()) {
           mbar_expect_tx(&a_full[as], g.a_tx_bytes);
           tma_load_4d(sA + as * g.a_stage_bytes, &tmA, &a_full[as], ck * 64, tx * g.TW - 1, ty * g.TH - 1, b);
-          if (++as == g.a_stages) { as = 0; aph ^= 1; }
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&b_empty[bs], bph ^ 1, p.err, 12);
+        }
+        __syncwarp();
+        if (++as == g.a_stages) { as = 0; aph ^= 1; }
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_empty[bs], bph ^ 1, p.err, 12);
+          if (elect_one()) {
             mbar_expect_tx(&b_full[bs], B_BYTES);
             tma_load_2d(sB + bs * B_BYTES, &tmB, &b_full[bs], (tap * chunks + ck) * 64, n_tile * N_TILE);
-            if (++bs == g.b_stages) { bs = 0; bph ^= 1; }
           }
+          __syncwarp();
+          if (++bs == g.b_stages) { bs = 0; bph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (warp <= MW) {
+    // ================= MMA issuers =================
     constexpr uint32_t idesc = make_idesc(N_TILE);
+    const int g0 = (warp - 1) * GW;  // first sub-tile of this warp
     int as = 0, bs = 0, acc = 0;
     uint32_t aph = 0, bph = 0, acc_phase = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       mbar_wait(&tempty[acc], acc_phase ^ 1, p.err, 13);
       tc_fence_after();
-      const uint32_t d_base = tmem_base + (uint32_t)(acc * G * N_TILE);
+      const uint32_t d_base = tmem_base + (uint32_t)((acc * G + g0) * N_TILE);
       for (int ck = 0; ck < chunks; ++ck) {
         mbar_wait(&a_full[as], aph, p.err, 14);
-        const uint64_t a0 = make_smem_desc(sA + as * g.a_stage_bytes);
+        // start address advances by whole 128 B rows: (gi*128 + row_off) * 128 B >> 4
+        const uint64_t a0 = make_smem_desc(sA + as * g.a_stage_bytes) + (uint64_t)(g0 * 128 * 8);
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&b_full[bs], bph, p.err, 15);
           tc_fence_after();
-          if (lane == 0) {
-            const int r = tap / 3, s = tap - 3 * r;
-            const uint64_t bdesc = make_smem_desc(sB + bs * B_BYTES);
-            const uint32_t row_off = (uint32_t)(r * g.PW + s);
+          const int r = tap / 3, s = tap - 3 * r;
+          const uint64_t bdesc = make_smem_desc(sB + bs * B_BYTES);
+          const uint64_t at = a0 + (uint64_t)((r * g.PW + s) * 8);
+          const uint32_t first = (ck | tap) != 0 ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
-            for (int gi = 0; gi < G; ++gi) {
-              // start address advances by whole 128 B rows: (gi*128 + row_off) * 128 B >> 4
-              const uint64_t adesc = a0 + (uint64_t)((gi * 128 + row_off) * 8);
+            for (int gi = 0; gi < GW; ++gi) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(d_base + (uint32_t)(gi * N_TILE), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                          (ck | tap | k) != 0 ? 1u : 0u);
+                umma_bf16(d_base + (uint32_t)(gi * N_TILE), at + (uint64_t)(gi * 128 * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                          k != 0 ? 1u : first);
             }
             umma_commit(&b_empty[bs]);
             if (tap == 8) {
@@ -147,67 +158,62 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ================= epilogue =================
-    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;         // which half of the N_TILE columns
+    const int ew = warp - 1 - MW;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = ew >> 2;      // which half of the N_TILE columns
     constexpr int NH = N_TILE / 2;
+    constexpr int NBLK = NH / 32;  // 32-channel blocks per sub-tile for this warp
+    const uint32_t stg = smem_u32(sStg + ew * 2048);
+    EpiParams e;
+    e.s_scale = s_scale; e.s_shift = s_shift;
+    e.addend = p.residual; e.add_mode = p.residual ? EPI_ADD_RESIDUAL : EPI_ADD_NONE;
+    e.out = p.out; e.sum_out = nullptr;
+    e.Cout = p.Cout; e.out_ldc = p.out_ldc; e.out_coff = p.out_coff; e.rep = p.rep; e.Wo = p.Wo; e.relu = p.relu;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int n_tile = unit / num_m_tiles, m_tile = unit - n_tile * num_m_tiles;
       const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
       const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+      const int n0 = n_tile * N_TILE + half * NH;
+      // coalesced-view rows of sub-tile gi: row it*8 + (lane >> 2) of this warp's 32
+      auto rows_of = [&](int gi, EpiRows &rw) {
+        rw.valid = 0;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int m = gi * 128 + quarter * 32 + it * 8 + (lane >> 2);
+          const int yl = m / g.PW, xl = m - yl * g.PW;
+          const int y = ty * g.TH + yl, x = tx * g.TW + xl;
+          const bool ok = yl < g.TH && xl < g.TW && y < p.Ho && x < p.Wo;
+          rw.opix[it] = (b * p.Ho + y) * p.Wo + x;
+          rw.apix[it] = rw.opix[it];
+          if (ok) rw.valid |= 1u << it;
+        }
+      };
+      EpiRows rw, rw_next;
+      uint4 pre[4] = {};
+      rows_of(0, rw);
+      if (e.add_mode != EPI_ADD_NONE) epi_fetch_addend(pre, lane, rw, e.addend, e.Cout, n0);
       mbar_wait(&tfull[acc], acc_phase, p.err, 16);
       tc_fence_after();
 #pragma unroll 1
       for (int gi = 0; gi < G; ++gi) {
-        const int m = gi * 128 + quarter * 32 + lane;
-        const int yl = m / g.PW, xl = m - yl * g.PW;
-        const int y = ty * g.TH + yl, x = tx * g.TW + xl;
-        const bool valid = yl < g.TH && xl < g.TW && y < p.Ho && x < p.Wo;
-        const int64_t pix = ((int64_t)b * p.Ho + y) * p.Wo + x;
+        if (gi + 1 < G) rows_of(gi + 1, rw_next);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * G + gi) * N_TILE + half * NH);
-        const int n0 = n_tile * N_TILE + half * NH;
-#pragma unroll 1
-        for (int c0 = 0; c0 < NH; c0 += 32) {
-          // residual prefetch (issued before the TMEM load so its latency overlaps)
-          uint4 rr[4];
-          if (p.residual && valid) {
-            const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + pix * p.Cout + n0 + c0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rr[j] = rp[j];
-          }
+        for (int blk = 0; blk < NBLK; ++blk) {
           float v[32];
-          tmem_ld32(taddr + c0, v);
-          if (valid) {
-            const int n = n0 + c0;
+          tmem_ld32(taddr + blk * 32, v);
+          uint4 cur[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_scale[n + j], s_shift[n + j]);
-            if (p.residual) {
-              const uint32_t ru[16] = {rr[0].x, rr[0].y, rr[0].z, rr[0].w, rr[1].x, rr[1].y, rr[1].z, rr[1].w,
-                                       rr[2].x, rr[2].y, rr[2].z, rr[2].w, rr[3].x, rr[3].y, rr[3].z, rr[3].w};
-#pragma unroll
-              for (int j = 0; j < 16; ++j) { float2 f = unpack_bf16(ru[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-            }
-            uint4 o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-            const int rep = p.rep;
-            const int64_t Wr = (int64_t)p.Wo * rep;
-            for (int ry = 0; ry < rep; ++ry)
-              for (int rx = 0; rx < rep; ++rx) {
-                const int64_t opix = ((int64_t)b * p.Ho * rep + (int64_t)y * rep + ry) * Wr + (int64_t)x * rep + rx;
-                uint4 *op = reinterpret_cast<uint4 *>(p.out + opix * p.out_ldc + p.out_coff + n);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) op[j] = o[j];
-              }
+          for (int it = 0; it < 4; ++it) cur[it] = pre[it];
+          if (e.add_mode != EPI_ADD_NONE) {  // fetch the next block's addend now
+            if (blk + 1 < NBLK) epi_fetch_addend(pre, lane, rw, e.addend, e.Cout, n0 + (blk + 1) * 32);
+            else if (gi + 1 < G) epi_fetch_addend(pre, lane, rw_next, e.addend, e.Cout, n0);
           }
+          epi_block32(v, lane, stg, rw, e, n0 + blk * 32, cur);
         }
+        rw = rw_next;
       }
       tc_fence_before();
       __syncwarp();
@@ -256,7 +262,7 @@ int halo_geometry(int Ho, int Wo, int n_tile, int G, HaloGeom *out) {
   g.a_stage_bytes = ((rows * 128 + 1023) / 1024) * 1024;
   g.a_tx_bytes = halo_rows * 128;
   const int b_bytes = n_tile * 128;
-  const int budget = 227 * 1024 - 1024 /*align*/ - 4608 /*barriers + scale/shift*/;
+  const int budget = 227 * 1024 - 1024 /*align*/ - 4096 /*static scale/shift*/ - 512 /*barriers*/ - HL_STG_BYTES;
   g.a_stages = 2;
   g.b_stages = (budget - g.a_stages * g.a_stage_bytes) / b_bytes;
   if (g.b_stages > 8) {
@@ -283,12 +289,12 @@ static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensor
   static bool attr_set[16] = {false};
   auto kern = conv_halo_kernel<N_TILE, G>;
   if (!attr_set[ctx->device & 15]) {
-    OCRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OCRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
     attr_set[ctx->device & 15] = true;
   }
-  const int smem = 1024 + g.a_stages * g.a_stage_bytes + g.b_stages * N_TILE * 128 + 4608;
+  const int smem = 1024 + g.a_stages * g.a_stage_bytes + g.b_stages * N_TILE * 128 + HL_STG_BYTES + 512;
   const int grid = num_units < ctx->sm_count ? num_units : ctx->sm_count;
-  kern<<<grid, HL_THREADS, smem, ctx->stream>>>(tmA, tmB, p, g);
+  kern<<<grid, (1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS) * 32, smem, ctx->stream>>>(tmA, tmB, p, g);
   return check_launch(ctx, tag);
 }
 

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "tc_epilogue.cuh"
 #include "tc_ptx.cuh"
 
 namespace ocrb {
@@ -28,19 +29,21 @@ namespace ocrb {
 constexpr int TC_TW = 25, TC_TH = 5, TC_ROWS = TC_TW * TC_TH;  // 125 valid rows of 128
 constexpr int TC_A_BYTES = 128 * 128;                           // A stage: 128 rows x 64 bf16
 constexpr int TC_A_TX = TC_ROWS * 128;                          // bytes TMA actually writes
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;
+constexpr int TC_STG_BYTES = TC_EPI_WARPS * 2048;               // per-warp epilogue staging
 
 // ---------------------------------------------------------------------------------------
-// shared-memory carve-up
+// shared-memory carve-up (dynamic part; scale/shift/w2 are static __shared__)
 // ---------------------------------------------------------------------------------------
 template <int N_TILE, int STAGES>
 struct TcSmem {
   static constexpr int B_BYTES = N_TILE * 128;
   static constexpr int OFF_B = STAGES * TC_A_BYTES;
-  static constexpr int OFF_BAR = OFF_B + STAGES * B_BYTES;       // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  static constexpr int OFF_STG = OFF_B + STAGES * B_BYTES;
+  static constexpr int OFF_BAR = OFF_STG + TC_STG_BYTES;          // full[STAGES], empty[STAGES], tfull[2], tempty[2]
   static constexpr int OFF_TMEM = OFF_BAR + (2 * STAGES + 4) * 8;
-  static constexpr int OFF_SCALE = OFF_TMEM + 16;                // scale[512], shift[512], w2[256]
-  static constexpr int TOTAL = OFF_SCALE + (512 + 512 + 256) * 4;
+  static constexpr int TOTAL = OFF_TMEM + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;                 // slack for manual 1024 B alignment
 };
 
@@ -49,6 +52,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
   using L = TcSmem<N_TILE, STAGES>;
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_scale[512], s_shift[512], s_w2[256];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sA = smem;
   uint8_t *sB = smem + L::OFF_B;
@@ -57,9 +61,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t *tfull = empty + STAGES;
   uint64_t *tempty = tfull + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_TMEM);
-  float *s_scale = reinterpret_cast<float *>(smem + L::OFF_SCALE);
-  float *s_shift = s_scale + 512;
-  float *s_w2 = s_shift + 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64) ? 64 : (2 * N_TILE <= 128) ? 128 : (2 * N_TILE <= 256) ? 256 : 512;
@@ -86,7 +87,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -97,24 +98,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile / num_m_tiles, m_tile = tile - n_tile * num_m_tiles;
-        const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
-        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-        const int x_base = tx * TC_TW * p.stride - p.pad, y_base = ty * TC_TH * p.stride - p.pad;
-        for (int r = 0; r < p.R; ++r)
-          for (int s = 0; s < p.S; ++s)
-            for (int ck = 0; ck < p.cin_chunks; ++ck) {
-              mbar_wait(&empty[stage], phase ^ 1, p.err, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile / num_m_tiles, m_tile = tile - n_tile * num_m_tiles;
+      const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
+      const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+      const int x_base = tx * TC_TW * p.stride - p.pad, y_base = ty * TC_TH * p.stride - p.pad;
+      for (int r = 0; r < p.R; ++r)
+        for (int s = 0; s < p.S; ++s)
+          for (int ck = 0; ck < p.cin_chunks; ++ck) {
+            mbar_wait(&empty[stage], phase ^ 1, p.err, 1);
+            if (elect_one()) {
               mbar_expect_tx(&full[stage], TC_A_TX + L::B_BYTES);
               tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], ck * 64, x_base + s, y_base + r, b);
               tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full[stage], ((r * p.S + s) * p.cin_chunks + ck) * 64, n_tile * N_TILE);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-      }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
@@ -130,9 +132,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase, p.err, 3);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t adesc = make_smem_desc(sA + stage * TC_A_BYTES);
-          const uint64_t bdesc = make_smem_desc(sB + stage * L::B_BYTES);
+        const uint64_t adesc = make_smem_desc(sA + stage * TC_A_BYTES);
+        const uint64_t bdesc = make_smem_desc(sB + stage * L::B_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle atom
             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -146,97 +148,89 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ================= epilogue =================
+    // ================= epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
+    const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int m = quarter * 32 + lane;
-    const int yl = m / TC_TW, xl = m - yl * TC_TW;
+    const int half = ew >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    EpiParams e;
+    e.s_scale = s_scale; e.s_shift = s_shift;
+    e.addend = p.residual ? p.residual : p.up_src;
+    e.add_mode = p.residual ? EPI_ADD_RESIDUAL : (p.sum_out ? EPI_ADD_SUM : EPI_ADD_NONE);
+    e.out = p.out; e.sum_out = p.sum_out;
+    e.Cout = p.Cout; e.out_ldc = p.out_ldc; e.out_coff = p.out_coff; e.rep = p.rep; e.Wo = p.Wo; e.relu = p.relu;
+    const uint32_t stg = smem_u32(smem + L::OFF_STG + ew * 2048);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = tile / num_m_tiles, m_tile = tile - n_tile * num_m_tiles;
       const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
       const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-      const int y = ty * TC_TH + yl, x = tx * TC_TW + xl;
-      const bool valid = m < TC_ROWS && y < p.Ho && x < p.Wo;
-      mbar_wait(&tfull[acc], acc_phase, p.err, 4);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE);
       if (EPI == EPI_STD) {
-        const int64_t pix = ((int64_t)b * p.Ho + y) * p.Wo + x;
+        constexpr int NH = N_TILE / 2, NBLK = NH / 32;
+        const int n0 = n_tile * N_TILE + half * NH;
+        EpiRows rw;
+        rw.valid = 0;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int m = quarter * 32 + it * 8 + (lane >> 2);
+          const int yl = m / TC_TW, xl = m - yl * TC_TW;
+          const int y = ty * TC_TH + yl, x = tx * TC_TW + xl;
+          rw.opix[it] = (b * p.Ho + y) * p.Wo + x;
+          rw.apix[it] = p.sum_out ? (b * (p.Ho >> 1) + (y >> 1)) * (p.Wo >> 1) + (x >> 1) : rw.opix[it];
+          if (m < TC_ROWS && y < p.Ho && x < p.Wo) rw.valid |= 1u << it;
+        }
+        uint4 pre[4] = {};
+        if (e.add_mode != EPI_ADD_NONE) epi_fetch_addend(pre, lane, rw, e.addend, e.Cout, n0);
+        mbar_wait(&tfull[acc], acc_phase, p.err, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE + half * NH);
 #pragma unroll 1
-        for (int c0 = 0; c0 < N_TILE; c0 += 16) {
-          float v[16];
-          tmem_ld16(taddr + c0, v);
-          if (valid) {
-            const int n = n_tile * N_TILE + c0;
+        for (int blk = 0; blk < NBLK; ++blk) {
+          float v[32];
+          tmem_ld32(taddr + blk * 32, v);
+          uint4 cur[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], s_scale[n + j], s_shift[n + j]);
-            if (p.residual) {
-              const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + pix * p.Cout + n);
-              uint4 r0 = rp[0], r1 = rp[1];
-              const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { float2 f = unpack_bf16(ru[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
-            }
-            if (p.out) {
-              uint4 o0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-              uint4 o1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-              const int rep = p.rep;
-              const int64_t Wr = (int64_t)p.Wo * rep;
-              for (int ry = 0; ry < rep; ++ry)
-                for (int rx = 0; rx < rep; ++rx) {
-                  const int64_t opix = ((int64_t)b * p.Ho * rep + (int64_t)y * rep + ry) * Wr + (int64_t)x * rep + rx;
-                  uint4 *op = reinterpret_cast<uint4 *>(p.out + opix * p.out_ldc + p.out_coff + n);
-                  op[0] = o0;
-                  op[1] = o1;
-                }
-            }
-            if (p.sum_out) {
-              const int64_t upix = ((int64_t)b * (p.Ho / 2) + (y >> 1)) * (p.Wo / 2) + (x >> 1);
-              const uint4 *up = reinterpret_cast<const uint4 *>(p.up_src + upix * p.Cout + n);
-              uint4 u0 = up[0], u1 = up[1];
-              const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-              uint32_t so[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { float2 f = unpack_bf16(uu[j]); so[j] = pack_bf16(v[2 * j] + f.x, v[2 * j + 1] + f.y); }
-              uint4 *sp = reinterpret_cast<uint4 *>(p.sum_out + pix * p.Cout + n);
-              sp[0] = make_uint4(so[0], so[1], so[2], so[3]);
-              sp[1] = make_uint4(so[4], so[5], so[6], so[7]);
-            }
-          }
+          for (int it = 0; it < 4; ++it) cur[it] = pre[it];
+          if (e.add_mode != EPI_ADD_NONE && blk + 1 < NBLK) epi_fetch_addend(pre, lane, rw, e.addend, e.Cout, n0 + (blk + 1) * 32);
+          epi_block32(v, lane, stg, rw, e, n0 + blk * 32, cur);
         }
       } else {
         // DB head tail: columns n = tap(i,j)*64 + co of conv-transpose 1; per tap BN+ReLU then
-        // the 64 -> 4 dot products of conv-transpose 2, sigmoid, 4x4 block of the 4x map.
-        float o[4][4];
+        // the 64 -> 4 dot products of conv-transpose 2, sigmoid; each warp half takes two taps
+        // (= two rows of the pixel's 4x4 output block).
+        const int m = quarter * 32 + lane;
+        const int yl = m / TC_TW, xl = m - yl * TC_TW;
+        const int y = ty * TC_TH + yl, x = tx * TC_TW + xl;
+        const bool valid = m < TC_ROWS && y < p.Ho && x < p.Wo;
+        mbar_wait(&tfull[acc], acc_phase, p.err, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE);
+        float o[2][4];
 #pragma unroll
-        for (int tap = 0; tap < 4; ++tap) {
+        for (int tj = 0; tj < 2; ++tj) {
+          const int tap = half * 2 + tj;  // tap = i*2 + j with i = half
           float z[4] = {p.b2, p.b2, p.b2, p.b2};
-#pragma unroll 1
-          for (int c0 = 0; c0 < 64; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + tap * 64 + c0, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            float v[32];
+            tmem_ld32(taddr + tap * 64 + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
               const int co = c0 + j;
-              float h = fmaxf(fmaf(v[j], s_scale[co], s_shift[co]), 0.0f);
+              const float h = fmaxf(fmaf(v[j], s_scale[co], s_shift[co]), 0.0f);
 #pragma unroll
               for (int q = 0; q < 4; ++q) z[q] = fmaf(h, s_w2[q * 64 + co], z[q]);
             }
           }
-          // tap = i*2 + j of conv-transpose 1; q = i'*2 + j' of conv-transpose 2
+          // q = i'*2 + j' of conv-transpose 2: output (4y + 2i + i', 4x + 2j + j')
 #pragma unroll
-          for (int q = 0; q < 4; ++q) o[2 * (tap >> 1) + (q >> 1)][2 * (tap & 1) + (q & 1)] = 1.0f / (1.0f + expf(-z[q]));
+          for (int q = 0; q < 4; ++q) o[q >> 1][2 * tj + (q & 1)] = 1.0f / (1.0f + expf(-z[q]));
         }
         if (valid) {
           const int64_t Wp = (int64_t)p.Wo * 4;
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const int64_t off = ((int64_t)b * p.Ho * 4 + (int64_t)y * 4 + a) * Wp + (int64_t)x * 4;
+          for (int a = 0; a < 2; ++a) {
+            const int64_t off = ((int64_t)b * p.Ho * 4 + (int64_t)y * 4 + 2 * half + a) * Wp + (int64_t)x * 4;
             *reinterpret_cast<float4 *>(p.prob + off) = make_float4(o[a][0], o[a][1], o[a][2], o[a][3]);
             if (p.bitmap) {
               uint32_t bits = (o[a][0] > p.thresh ? 1u : 0u) | (o[a][1] > p.thresh ? 0x100u : 0u) |
