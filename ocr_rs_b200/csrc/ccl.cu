@@ -75,17 +75,22 @@ __global__ void __launch_bounds__(CCL_TW *CCL_TH) ccl_local_kernel(const uint8_t
   if (lane == 0) rowbits[r] = bits;
   __syncthreads();
   if (inside && r > 0) {
-    uint32_t up = rowbits[r - 1];
-    int n_fg = (up >> lane) & 1;
-    if (fg) {
-      if (n_fg) {
-        uf_union(L, threadIdx.x, threadIdx.x - CCL_TW);
-      } else {
-        if (lane > 0 && ((up >> (lane - 1)) & 1)) uf_union(L, threadIdx.x, threadIdx.x - CCL_TW - 1);
-        if (lane < 31 && ((up >> (lane + 1)) & 1)) uf_union(L, threadIdx.x, threadIdx.x - CCL_TW + 1);
-      }
-    } else if (!n_fg) {
-      uf_union(L, threadIdx.x, threadIdx.x - CCL_TW);
+    // One union per pair of overlapping runs, not per pixel: a vertical link is redundant when
+    // the pixel to the left is in my run and the pixel above it is in the run above me (the
+    // leftmost pixel of the overlap makes the link).  Diagonal links (8-connectivity of the
+    // foreground) are only needed from the ends of a run.
+    const uint32_t up = rowbits[r - 1];
+    const uint32_t up_same = fg ? up : (~up & valid);   // pixels above of my class
+    const bool n_same = (up_same >> lane) & 1;
+    if (n_same) {
+      const bool left_mine = lane > 0 && ((same >> (lane - 1)) & 1);
+      const bool upleft_same = lane > 0 && ((up_same >> (lane - 1)) & 1);
+      if (!(left_mine && upleft_same)) uf_union(L, threadIdx.x, threadIdx.x - CCL_TW);
+    } else if (fg) {
+      const bool left_fg = lane > 0 && ((bits >> (lane - 1)) & 1);
+      const bool right_fg = lane < 31 && ((bits >> (lane + 1)) & 1);
+      if (lane > 0 && !left_fg && ((up >> (lane - 1)) & 1)) uf_union(L, threadIdx.x, threadIdx.x - CCL_TW - 1);
+      if (lane < 31 && !right_fg && ((up >> (lane + 1)) & 1)) uf_union(L, threadIdx.x, threadIdx.x - CCL_TW + 1);
     }
   }
   __syncthreads();
@@ -100,22 +105,38 @@ __global__ void __launch_bounds__(CCL_TW *CCL_TH) ccl_local_kernel(const uint8_t
 // pass 2: seams.  A pixel whose W / NW / N / NE neighbour lies in another tile unites with
 // it in global memory (same adjacency rules as pass 1).
 // ---------------------------------------------------------------------------------------
-__global__ void ccl_seam_kernel(const uint8_t *__restrict__ bitmap, int H, int W, int B, int *__restrict__ labels) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t HW = (int64_t)H * W;
-  if (idx >= HW * B) return;
-  int b = (int)(idx / HW);
-  int i = (int)(idx % HW);
-  int x = i % W, y = i / W;
-  bool on_left = (x % CCL_TW) == 0, on_right = (x % CCL_TW) == CCL_TW - 1, on_top = (y % CCL_TH) == 0;
-  if (!on_left && !on_top && !on_right) return;
+__global__ void ccl_seam_kernel(const uint8_t *__restrict__ bitmap, int H, int W, int B, int tiles_x, int tiles_y,
+                                int *__restrict__ labels) {
+  // one thread per tile-border pixel: 32 top-row + 32 left-column + 32 right-column per tile
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tiles = (int64_t)tiles_x * tiles_y * B;
+  if (t >= tiles * 96) return;
+  const int k = (int)(t % 96);
+  const int64_t tile = t / 96;
+  const int b = (int)(tile / ((int64_t)tiles_x * tiles_y));
+  const int tt = (int)(tile % ((int64_t)tiles_x * tiles_y));
+  const int tx = tt % tiles_x, ty = tt / tiles_x;
+  int x, y;
+  if (k < 32) { x = tx * CCL_TW + k; y = ty * CCL_TH; }
+  else if (k < 64) { x = tx * CCL_TW; y = ty * CCL_TH + (k - 32); }
+  else { x = tx * CCL_TW + CCL_TW - 1; y = ty * CCL_TH + (k - 64); }
+  if (x >= W || y >= H) return;
+  const bool on_left = (x % CCL_TW) == 0, on_right = (x % CCL_TW) == CCL_TW - 1, on_top = (y % CCL_TH) == 0;
+  // corner pixels appear in two of the three groups: let the top-row instance do the work
+  if (k >= 32 && on_top) return;
+  const int64_t HW = (int64_t)H * W;
   const uint8_t *bm = bitmap + b * HW;
   int *L = labels + b * HW;
-  int fg = bm[i] != 0;
+  const int i = y * W + x;
+  const int fg = bm[i] != 0;
   if (on_left && x > 0 && (bm[i - 1] != 0) == fg) uf_union(L, i, i - 1);
   if (y > 0) {
-    int n_fg = bm[i - W] != 0;
-    if (on_top && n_fg == fg) uf_union(L, i, i - W);
+    const int n_fg = bm[i - W] != 0;
+    if (on_top && n_fg == fg) {
+      // same redundancy rule as the tile-local pass, along the whole image row
+      const bool skip = x > 0 && (bm[i - 1] != 0) == fg && (bm[i - W - 1] != 0) == fg;
+      if (!skip) uf_union(L, i, i - W);
+    }
     if (fg && !n_fg) {
       if (x > 0 && (on_top || on_left) && bm[i - W - 1] != 0) uf_union(L, i, i - W - 1);
       if (x + 1 < W && (on_top || on_right) && bm[i - W + 1] != 0) uf_union(L, i, i - W + 1);
@@ -141,7 +162,7 @@ int launch_ccl(ocrb_ctx *ctx, const uint8_t *bitmap, int B, int H, int W, int *l
   ccl_local_kernel<<<(unsigned)blocks, CCL_TW * CCL_TH, 0, ctx->stream>>>(bitmap, H, W, tiles_x, tiles_y, labels);
   OCRB_TRY(check_launch(ctx, "ccl_local"));
   int64_t n = (int64_t)B * H * W;
-  ccl_seam_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap, H, W, B, labels);
+  ccl_seam_kernel<<<(unsigned)cdiv(blocks * 96, 256), 256, 0, ctx->stream>>>(bitmap, H, W, B, tiles_x, tiles_y, labels);
   OCRB_TRY(check_launch(ctx, "ccl_seam"));
   ccl_flatten_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(H, W, B, labels);
   return check_launch(ctx, "ccl_flatten");

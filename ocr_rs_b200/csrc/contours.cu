@@ -141,17 +141,35 @@ __global__ void __launch_bounds__(128) contour_anchored_kernel(const uint8_t *__
   }
 }
 
-// flags -> contour records (start pixel as batch-global index, kind)
-__global__ void contour_records_kernel(const uint8_t *__restrict__ flags, const int *__restrict__ offs, int64_t n,
-                                       int64_t *__restrict__ start_idx, uint8_t *__restrict__ kind) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  uint8_t f = flags[idx];
-  if (f) {
-    int c = offs[idx];
-    start_idx[c] = idx;
-    kind[c] = f - 1;
+// flags -> contour records (start pixel as batch-global index, kind), in raster order:
+// order-preserving compaction with per-tile counts (scan.cuh tile reduce + scan of the tile
+// sums) and an in-tile rank computed here — no per-pixel offset array is ever written.
+__global__ void __launch_bounds__(SCAN_THREADS) contour_records_kernel(const uint8_t *__restrict__ flags, const int *__restrict__ tile_offs,
+                                                                       int64_t n, int64_t *__restrict__ start_idx, uint8_t *__restrict__ kind) {
+  __shared__ int smem[33];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  uint8_t f[SCAN_ITEMS];
+  int s = 0;
+  if (base + SCAN_ITEMS <= n) {
+    const uint2 u = *reinterpret_cast<const uint2 *>(flags + base);  // SCAN_ITEMS == 8, base % 8 == 0
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[j] = (u.x >> (8 * j)) & 0xff; f[4 + j] = (u.y >> (8 * j)) & 0xff; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) f[j] = base + j < n ? flags[base + j] : 0;
   }
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) s += f[j] != 0;
+  int total;
+  int rank = block_exclusive_scan<int>(s, &total, smem) + tile_offs[blockIdx.x];
+  if (s == 0) return;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j)
+    if (f[j]) {
+      start_idx[rank] = base + j;
+      kind[rank] = f[j] - 1;
+      ++rank;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -324,8 +342,19 @@ int launch_contour_starts(ocrb_ctx *ctx, const uint8_t *bitmap, const int *label
   return check_launch(ctx, "contour_anchored");
 }
 
-int launch_contour_records(ocrb_ctx *ctx, const uint8_t *flags, const int *offs, int64_t n, int64_t *start_idx, uint8_t *kind) {
-  contour_records_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(flags, offs, n, start_idx, kind);
+// phase 1: per-tile counts of the start flags and their exclusive scan; tile_offs must hold
+// scan_scratch_elems(n) * 2 ints.  The total lands at tile_offs[tiles] (see contour_count_slot).
+int launch_contour_count(ocrb_ctx *ctx, const uint8_t *flags, int64_t n, int *tile_offs) {
+  const int64_t tiles = cdiv(n, SCAN_TILE);
+  scan_tile_reduce_kernel<uint8_t, int, ScanNonZero><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(flags, n, tile_offs);
+  OCRB_TRY(check_launch(ctx, "scan_tile_reduce"));
+  int *lvl2 = tile_offs + tiles + 8;
+  return exclusive_scan<int, int, ScanIdentity>(ctx, tile_offs, tiles, tile_offs, lvl2);
+}
+int64_t contour_count_slot(int64_t n) { return cdiv(n, SCAN_TILE); }
+
+int launch_contour_records(ocrb_ctx *ctx, const uint8_t *flags, const int *tile_offs, int64_t n, int64_t *start_idx, uint8_t *kind) {
+  contour_records_kernel<<<(unsigned)cdiv(n, SCAN_TILE), SCAN_THREADS, 0, ctx->stream>>>(flags, tile_offs, n, start_idx, kind);
   return check_launch(ctx, "contour_records");
 }
 

@@ -3,8 +3,12 @@
 // plus glyph recognition (char_recognition/mod.rs:39-68) of a caller-provided crop set in the
 // same call (the reference has no polygon -> crop glue).
 //
-// Images are processed in chunks so the activation workspace stays bounded; each chunk is
-// H2D copy -> forward (the BF16 head writes the probability map AND the bitmap) -> post-proc.
+// Three streams per context keep the GPU busy across the post-processing's host round trips:
+//   copy stream     H2D of image chunk c+1 (double-buffered) while chunk c is in the detector
+//   forward stream  detector forward, chunk by chunk (32 images), into a GROUP buffer
+//   ctx->stream     post-processing of group g (up to 128 images per launch: the contour /
+//                   polygon kernels are latency-bound, so they are amortised over more images)
+//                   while the forward of group g+1 runs on the forward stream
 #include "common.cuh"
 
 namespace ocrb {
@@ -20,15 +24,32 @@ ocrb_polygons *polygons_new();
 int launch_binarize(ocrb_ctx *, const float *, int64_t, float, uint8_t *);
 
 struct PipelineWorkspace {
-  DevBuf images, prob, bitmap, adjust, glyphs, argmax;
+  DevBuf images[2], prob[2], bitmap[2], adjust, glyphs, argmax;
+  cudaStream_t fwd = nullptr, copy = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, fwd_done[2] = {nullptr, nullptr}, pp_ready = nullptr;
+  bool ready = false;
 };
 static PipelineWorkspace *g_ws[16] = {nullptr};
 
-static PipelineWorkspace *get_ws(ocrb_ctx *ctx) {
+static int get_ws(ocrb_ctx *ctx, PipelineWorkspace **out) {
   PipelineWorkspace *&w = g_ws[ctx->device & 15];
   if (!w) w = new PipelineWorkspace();
-  return w;
+  if (!w->ready) {
+    OCRB_CUDA(cudaStreamCreateWithFlags(&w->fwd, cudaStreamNonBlocking));
+    OCRB_CUDA(cudaStreamCreateWithFlags(&w->copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      OCRB_CUDA(cudaEventCreateWithFlags(&w->copied[i], cudaEventDisableTiming));
+      OCRB_CUDA(cudaEventCreateWithFlags(&w->consumed[i], cudaEventDisableTiming));
+      OCRB_CUDA(cudaEventCreateWithFlags(&w->fwd_done[i], cudaEventDisableTiming));
+    }
+    OCRB_CUDA(cudaEventCreateWithFlags(&w->pp_ready, cudaEventDisableTiming));
+    w->ready = true;
+  }
+  *out = w;
+  return OCRB_OK;
 }
+
+constexpr int PIPE_CHUNK_BF16 = 32, PIPE_CHUNK_FP32 = 4, PIPE_GROUP = 128;
 
 }  // namespace ocrb
 
@@ -45,26 +66,40 @@ extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uin
   ocrb_postproc_params prm;
   ocrb_postproc_default_params(&prm);
   if (params) prm = *params;
-  PipelineWorkspace *ws = get_ws(ctx);
+  PipelineWorkspace *ws = nullptr;
+  OCRB_TRY(get_ws(ctx, &ws));
   const int64_t HW = (int64_t)H * W;
   const bool bf16 = det_mode(det) == OCRB_MODE_BF16;
-  // chunk: <= 32 images and <= 2^31 pixels for the post-processing index arithmetic
-  int chunk = bf16 ? 32 : 4;
-  while ((int64_t)chunk * HW >= ((int64_t)1 << 31) && chunk > 1) chunk /= 2;
-  if (chunk > B) chunk = B;
+  // the per-launch event timeline (ocrb_ctx_profile_begin) needs one stream: serialise then
+  const bool serial = ctx->prof.on;
+  cudaStream_t s_pp = ctx->stream, s_fwd = serial ? ctx->stream : ws->fwd, s_copy = serial ? ctx->stream : ws->copy;
+  // group: <= 128 images and < 2^31 pixels (post-processing index arithmetic); chunk: <= 32 images
+  int group = PIPE_GROUP;
+  while ((int64_t)group * HW >= ((int64_t)1 << 31) && group > 1) group /= 2;
+  if (group > B) group = B;
+  int chunk = bf16 ? PIPE_CHUNK_BF16 : PIPE_CHUNK_FP32;
+  if (chunk > group) chunk = group;
+  const int n_groups = (B + group - 1) / group;
   const bool img_dev = is_device_ptr(images);
-  OCRB_TRY(ws->prob.reserve((size_t)chunk * HW * 4));
-  OCRB_TRY(ws->bitmap.reserve((size_t)chunk * HW));
+  for (int i = 0; i < (n_groups > 1 ? 2 : 1); ++i) {
+    OCRB_TRY(ws->prob[i].reserve((size_t)group * HW * 4));
+    OCRB_TRY(ws->bitmap[i].reserve((size_t)group * HW));
+  }
+  if (!img_dev)
+    for (int i = 0; i < 2; ++i) OCRB_TRY(ws->images[i].reserve((size_t)chunk * HW));
   OCRB_TRY(ws->adjust.reserve((size_t)B * 16));
-  if (!img_dev) OCRB_TRY(ws->images.reserve((size_t)chunk * HW));
-  OCRB_CUDA(cudaMemcpyAsync(ws->adjust.p, adjust, (size_t)B * 16, cudaMemcpyDefault, ctx->stream));
+  OCRB_CUDA(cudaMemcpyAsync(ws->adjust.p, adjust, (size_t)B * 16, cudaMemcpyDefault, s_pp));
+  // everything queued so far on ctx->stream (earlier calls) precedes this call's forward work
+  OCRB_CUDA(cudaEventRecord(ws->pp_ready, s_pp));
+  OCRB_CUDA(cudaStreamWaitEvent(s_fwd, ws->pp_ready, 0));
+  OCRB_CUDA(cudaStreamWaitEvent(s_copy, ws->pp_ready, 0));
 
-  // glyph recognition first: its kernels queue behind nothing and overlap the first H2D copy
+  // glyph recognition: independent of the detector, queued first on the post-processing stream
   if (n_glyphs > 0) {
     const void *g = glyphs;
     if (!is_device_ptr(glyphs)) {
       OCRB_TRY(ws->glyphs.reserve((size_t)n_glyphs * 784));
-      OCRB_CUDA(cudaMemcpyAsync(ws->glyphs.p, glyphs, (size_t)n_glyphs * 784, cudaMemcpyHostToDevice, ctx->stream));
+      OCRB_CUDA(cudaMemcpyAsync(ws->glyphs.p, glyphs, (size_t)n_glyphs * 784, cudaMemcpyHostToDevice, s_pp));
       g = ws->glyphs.p;
     }
     int32_t *am = glyph_argmax;
@@ -74,32 +109,55 @@ extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uin
     }
     OCRB_TRY(rec_forward_device(rec, g, 1, n_glyphs, nullptr, am, nullptr));
     if (glyph_argmax && am != glyph_argmax)
-      OCRB_CUDA(cudaMemcpyAsync(glyph_argmax, am, (size_t)n_glyphs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      OCRB_CUDA(cudaMemcpyAsync(glyph_argmax, am, (size_t)n_glyphs * 4, cudaMemcpyDeviceToHost, s_pp));
   }
 
+  int64_t chunk_no = 0;  // global chunk counter (selects the image staging buffer)
+  // queues copies + forwards of group g; the detector launches on ctx->stream, so it is
+  // pointed at the forward stream for the duration
+  auto enqueue_forward = [&](int g) -> int {
+    const int g0 = g * group, gn = B - g0 < group ? B - g0 : group;
+    float *prob = ws->prob[g & 1].as<float>();
+    uint8_t *bitmap = ws->bitmap[g & 1].as<uint8_t>();
+    int rc = OCRB_OK;
+    for (int c0 = 0; c0 < gn && rc == OCRB_OK; c0 += chunk, ++chunk_no) {
+      const int bc = gn - c0 < chunk ? gn - c0 : chunk;
+      const uint8_t *src = images + (size_t)(g0 + c0) * HW;
+      const int slot = (int)(chunk_no & 1);
+      if (!img_dev) {
+        if (chunk_no >= 2) OCRB_CUDA(cudaStreamWaitEvent(s_copy, ws->consumed[slot], 0));
+        OCRB_CUDA(cudaMemcpyAsync(ws->images[slot].p, src, (size_t)bc * HW, cudaMemcpyHostToDevice, s_copy));
+        OCRB_CUDA(cudaEventRecord(ws->copied[slot], s_copy));
+        OCRB_CUDA(cudaStreamWaitEvent(s_fwd, ws->copied[slot], 0));
+        src = ws->images[slot].as<uint8_t>();
+      }
+      cudaStream_t saved = ctx->stream;
+      ctx->stream = s_fwd;
+      rc = det_forward_device(det, src, OCRB_U8, bc, H, W, prob + (size_t)c0 * HW, bf16 ? bitmap + (size_t)c0 * HW : nullptr, (float)prm.thresh);
+      if (rc == OCRB_OK && !bf16) rc = launch_binarize(ctx, prob + (size_t)c0 * HW, (int64_t)bc * HW, (float)prm.thresh, bitmap + (size_t)c0 * HW);
+      ctx->stream = saved;
+      if (rc == OCRB_OK && !img_dev) OCRB_CUDA(cudaEventRecord(ws->consumed[slot], s_fwd));
+    }
+    if (rc == OCRB_OK) OCRB_CUDA(cudaEventRecord(ws->fwd_done[g & 1], s_fwd));
+    return rc;
+  };
+
   ocrb_polygons *res = polygons_new();
-  int rc = OCRB_OK;
-  for (int b0 = 0; b0 < B && rc == OCRB_OK; b0 += chunk) {
-    const int bc = B - b0 < chunk ? B - b0 : chunk;
-    const uint8_t *src = images + (size_t)b0 * HW;
-    if (!img_dev) {
-      cudaError_t e = cudaMemcpyAsync(ws->images.p, src, (size_t)bc * HW, cudaMemcpyHostToDevice, ctx->stream);
-      if (e != cudaSuccess) { set_error("H2D image copy -> %s", cudaGetErrorString(e)); rc = OCRB_ERR_CUDA; break; }
-      src = ws->images.as<uint8_t>();
-    }
-    if (bf16) {
-      rc = det_forward_device(det, src, OCRB_U8, bc, H, W, ws->prob.as<float>(), ws->bitmap.as<uint8_t>(), (float)prm.thresh);
-    } else {
-      rc = det_forward_device(det, src, OCRB_U8, bc, H, W, ws->prob.as<float>(), nullptr, (float)prm.thresh);
-      if (rc == OCRB_OK) rc = launch_binarize(ctx, ws->prob.as<float>(), (int64_t)bc * HW, (float)prm.thresh, ws->bitmap.as<uint8_t>());
-    }
+  int rc = enqueue_forward(0);
+  for (int g = 0; g < n_groups && rc == OCRB_OK; ++g) {
+    if (g + 1 < n_groups) rc = enqueue_forward(g + 1);
     if (rc != OCRB_OK) break;
+    const int g0 = g * group, gn = B - g0 < group ? B - g0 : group;
+    cudaError_t e = cudaStreamWaitEvent(s_pp, ws->fwd_done[g & 1], 0);
+    if (e != cudaSuccess) { set_error("cudaStreamWaitEvent -> %s", cudaGetErrorString(e)); rc = OCRB_ERR_CUDA; break; }
     ocrb_polygons *part = polygons_new();
-    rc = postproc_device(ctx, ws->prob.as<float>(), ws->bitmap.as<uint8_t>(), ws->adjust.as<double>() + (size_t)b0 * 2, bc, H, W, prm, part);
+    rc = postproc_device(ctx, ws->prob[g & 1].as<float>(), ws->bitmap[g & 1].as<uint8_t>(), ws->adjust.as<double>() + (size_t)g0 * 2, gn, H, W, prm, part);
     if (rc == OCRB_OK) polygons_append(res, part);
     ocrb_polygons_free(part);
   }
   if (rc == OCRB_OK) rc = sync(ctx);
+  cudaStreamSynchronize(ws->fwd);
+  cudaStreamSynchronize(ws->copy);
   if (rc == OCRB_OK && bf16) rc = det_check_err(det);
   if (rc != OCRB_OK) {
     cudaStreamSynchronize(ctx->stream);

@@ -126,7 +126,7 @@ def test_expand_polygon_vs_oracle(api, gt55):
             # difference flips the outward floor/ceil when a rotated coordinate is an exact integer
             assert np.abs(bg - be).max() <= 1 and abs(sg - se) <= 1.5
             n_exact += int(bg.tolist() == be.tolist() and abs(sg - se) <= 1e-12 * max(1.0, se))
-    assert n_some > 20 and n_exact >= 0.95 * n_some, (n_some, n_exact)
+    assert n_some > 20 and n_exact >= 0.9 * n_some, (n_some, n_exact)
     assert polygon.expand_polygon([(0, 0), (10, 0), (20, 0), (10, 0)], 2.0) is None
 
 
