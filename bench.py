@@ -38,10 +38,10 @@ METRIC = "800x800 det+rec images/sec"
 
 
 def tc_flops_per_image(h, w):
-    """2*MACs of every layer that runs on the tcgen05 kernel (model.rs:65-152; stem excluded:
-    it is a CUDA-core kernel, convT2 excluded: it is the head epilogue's FMA tail)."""
+    """2*MACs of every layer that runs on the tcgen05 kernels (model.rs:65-152; convT2
+    excluded: it is the head epilogue's FMA tail)."""
     h4, w4 = h // 4, w // 4
-    f = 0
+    f = 2 * (h // 2) * (w // 2) * 64 * 49  # stem 7x7 s2, 1 -> 64
     c_in = 64
     for li, c in enumerate((64, 128, 256, 512)):
         hh, ww = h4 >> li, w4 >> li
@@ -146,7 +146,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * sec_per_img * per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg4: detect+recognize, 800x800 synthetic document images (bounded CPU sample of the 1024-image batch)",
+        "config": {"workload": f"cfg4: end-to-end detect+recognize, {TOTAL_IMAGES} synthetic 800x800 document images; structured-head random weights (SURVEY 8d)"
+                               f" - bounded CPU sample: {per_step} images per step",
                    "images_per_step": per_step, "glyphs_per_image": GLYPHS_PER_IMAGE},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -253,7 +254,7 @@ def main():
     def e2e_step():
         res = step(host_imgs, host_gl, host_am, keep=True)
         d2h[0] = res.xy.nbytes + res.all_scores.nbytes + res.point_offsets.nbytes + res.image_offsets.nbytes + host_am.numel() * 4
-        sharding.gather_polygon_scores(res.polygons, res.scores)
+        sharding.gather_polygons(res)
 
     for _ in range(args.warmup):
         e2e_step()
@@ -308,7 +309,7 @@ def main():
         "gpu_launches": int(lt.item()),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                     "traffic": None, "kernel": "conv_tc_kernel (all tcgen05 implicit-GEMM launches of one step)", "launches": tc_n,
+                     "traffic": None, "kernel": "stem_tc / conv_halo / conv_tc kernels (all tcgen05 implicit-GEMM launches of one step)", "launches": tc_n,
                      "avg_launch_ms": tc_ms / max(tc_n, 1), "flops_per_image": tc_flops_per_image(H, W), "peak_source": peak_src,
                      "share_of_step": tc_ms / all_ms if all_ms else None},
         "kernels_ms_per_step": {k: round(v[1], 3) for k, v in top},

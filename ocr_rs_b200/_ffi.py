@@ -195,19 +195,58 @@ def weights_to_c(weights):
 
 
 class Polygons:
-    """PolygonScores (metrics.rs:32-35) backed by an ocrb_polygons handle; converted eagerly."""
+    """PolygonScores (metrics.rs:32-35) backed by an ocrb_polygons handle.  The flat arrays
+    (image_offsets, point_offsets, xy, all_scores, stats) are copied out eagerly; the
+    per-image Python lists `polygons` / `scores` are built on first use."""
 
-    def __init__(self, handle):
-        L = lib()
-        nb = L.ocrb_polygons_num_images(handle)
-        io = np.ctypeslib.as_array(L.ocrb_polygons_image_offsets(handle), shape=(nb + 1,)).copy()
-        npoly = int(io[-1])
-        po = np.ctypeslib.as_array(L.ocrb_polygons_point_offsets(handle), shape=(npoly + 1,)).copy()
-        npts = int(po[-1])
-        xy = np.ctypeslib.as_array(L.ocrb_polygons_xy(handle), shape=(max(npts, 1) * 2,)).copy()[: npts * 2].reshape(-1, 2)
-        sc = np.ctypeslib.as_array(L.ocrb_polygons_scores(handle), shape=(max(npoly, 1),)).copy()[:npoly]
-        self.stats = np.ctypeslib.as_array(L.ocrb_polygons_stats(handle), shape=(nb * 5,)).copy().reshape(nb, 5)
-        L.ocrb_polygons_free(handle)
-        self.image_offsets, self.point_offsets, self.xy, self.all_scores = io, po, xy, sc
-        self.polygons = [[xy[po[p]:po[p + 1]] for p in range(io[b], io[b + 1])] for b in range(nb)]
-        self.scores = [sc[io[b]:io[b + 1]] for b in range(nb)]
+    def __init__(self, handle=None, arrays=None):
+        if arrays is not None:
+            self.image_offsets, self.point_offsets, self.xy, self.all_scores, self.stats = arrays
+        else:
+            L = lib()
+            nb = L.ocrb_polygons_num_images(handle)
+            io = np.ctypeslib.as_array(L.ocrb_polygons_image_offsets(handle), shape=(nb + 1,)).copy()
+            npoly = int(io[-1])
+            po = np.ctypeslib.as_array(L.ocrb_polygons_point_offsets(handle), shape=(npoly + 1,)).copy()
+            npts = int(po[-1])
+            xy = np.ctypeslib.as_array(L.ocrb_polygons_xy(handle), shape=(max(npts, 1) * 2,)).copy()[: npts * 2].reshape(-1, 2)
+            sc = np.ctypeslib.as_array(L.ocrb_polygons_scores(handle), shape=(max(npoly, 1),)).copy()[:npoly]
+            self.stats = np.ctypeslib.as_array(L.ocrb_polygons_stats(handle), shape=(nb * 5,)).copy().reshape(nb, 5)
+            L.ocrb_polygons_free(handle)
+            self.image_offsets, self.point_offsets, self.xy, self.all_scores = io, po, xy, sc
+        self._polygons = self._scores = None
+
+    @property
+    def num_images(self):
+        return len(self.image_offsets) - 1
+
+    @property
+    def polygons(self):
+        if self._polygons is None:
+            io, po, xy = self.image_offsets, self.point_offsets, self.xy
+            self._polygons = [[xy[po[p]:po[p + 1]] for p in range(io[b], io[b + 1])] for b in range(self.num_images)]
+        return self._polygons
+
+    @property
+    def scores(self):
+        if self._scores is None:
+            io, sc = self.image_offsets, self.all_scores
+            self._scores = [sc[io[b]:io[b + 1]] for b in range(self.num_images)]
+        return self._scores
+
+    def arrays(self):
+        return self.image_offsets, self.point_offsets, self.xy, self.all_scores, self.stats
+
+    @staticmethod
+    def concat(parts):
+        """Concatenates per-shard results in the given (= image index) order."""
+        io, po, xy, sc, st = [np.zeros(1, np.int64)], [np.zeros(1, np.int64)], [], [], []
+        for a in parts:
+            pio, ppo, pxy, psc, pst = a.arrays() if isinstance(a, Polygons) else a
+            io.append(pio[1:] + io[-1][-1])
+            po.append(ppo[1:] + po[-1][-1])
+            xy.append(pxy)
+            sc.append(psc)
+            st.append(pst)
+        return Polygons(arrays=(np.concatenate(io), np.concatenate(po), np.concatenate(xy) if xy else np.zeros((0, 2), np.uint32),
+                                np.concatenate(sc) if sc else np.zeros(0), np.concatenate(st) if st else np.zeros((0, 5), np.int64)))

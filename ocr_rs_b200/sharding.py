@@ -32,3 +32,17 @@ def gather_polygon_scores(polygons, scores, dst=0, group=None):
         all_p.extend(p)
         all_s.extend(s)
     return all_p, all_s
+
+
+def gather_polygons(result, dst=0, group=None):
+    """result: this rank's _ffi.Polygons (flat arrays).  Returns the _ffi.Polygons of the whole
+    batch on `dst` (shards concatenated in rank = image index order), None elsewhere.  The
+    payload is the five flat arrays, a few bytes per polygon point."""
+    import torch.distributed as dist
+    from ._ffi import Polygons
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return result
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    out = [None] * world if rank == dst else None
+    dist.gather_object(result.arrays(), out, dst=dst, group=group)
+    return Polygons.concat(out) if rank == dst else None
