@@ -209,8 +209,10 @@ class Polygons:
             npoly = int(io[-1])
             po = np.ctypeslib.as_array(L.ocrb_polygons_point_offsets(handle), shape=(npoly + 1,)).copy()
             npts = int(po[-1])
-            xy = np.ctypeslib.as_array(L.ocrb_polygons_xy(handle), shape=(max(npts, 1) * 2,)).copy()[: npts * 2].reshape(-1, 2)
-            sc = np.ctypeslib.as_array(L.ocrb_polygons_scores(handle), shape=(max(npoly, 1),)).copy()[:npoly]
+            # an empty result has no backing storage (NULL data pointers)
+            xy = (np.ctypeslib.as_array(L.ocrb_polygons_xy(handle), shape=(npts * 2,)).copy().reshape(-1, 2)
+                  if npts > 0 else np.zeros((0, 2), np.uint32))
+            sc = np.ctypeslib.as_array(L.ocrb_polygons_scores(handle), shape=(npoly,)).copy() if npoly > 0 else np.zeros(0, np.float64)
             self.stats = np.ctypeslib.as_array(L.ocrb_polygons_stats(handle), shape=(nb * 5,)).copy().reshape(nb, 5)
             L.ocrb_polygons_free(handle)
             self.image_offsets, self.point_offsets, self.xy, self.all_scores = io, po, xy, sc

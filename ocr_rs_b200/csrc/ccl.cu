@@ -49,55 +49,77 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b) {
 }
 
 // ---------------------------------------------------------------------------------------
-// pass 1: tile-local.  1024 threads = 32 warps; warp r owns tile row r.
+// pass 1: tile-local.  256 threads = 8 warps; warp w owns tile rows 4w .. 4w+3.
 // Warp-level merge: every pixel starts labelled with the first pixel of its horizontal run
 // (ballot + bit scan, no atomics).  Vertical / diagonal links are then united in shared
-// memory.  Output: parent = image-local linear index of the tile-local root.
+// memory, one union per pair of overlapping runs.  Output: parent = image-local linear index
+// of the tile-local root.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CCL_TW *CCL_TH) ccl_local_kernel(const uint8_t *__restrict__ bitmap, int H, int W,
-                                                                  int tiles_x, int tiles_y, int *__restrict__ labels) {
+constexpr int CCL_THREADS = 256;
+constexpr int CCL_ROWS_PER_WARP = CCL_TH / (CCL_THREADS / 32);
+
+__global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *__restrict__ bitmap, int H, int W,
+                                                                 int tiles_x, int tiles_y, int *__restrict__ labels) {
   __shared__ int L[CCL_TW * CCL_TH];
-  __shared__ uint32_t rowbits[CCL_TH + 1];
-  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+  __shared__ uint32_t rowbits[CCL_TH], rowvalid[CCL_TH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile = blockIdx.x % (tiles_x * tiles_y), b = blockIdx.x / (tiles_x * tiles_y);
   const int tx = tile % tiles_x, ty = tile / tiles_x;
-  const int x = tx * CCL_TW + lane, y = ty * CCL_TH + r;
-  const bool inside = x < W && y < H;
+  const int x = tx * CCL_TW + lane;
   const uint8_t *bm = bitmap + (int64_t)b * H * W;
-  const int fg = inside ? (bm[(int64_t)y * W + x] != 0) : 0;
-  const uint32_t valid = __ballot_sync(0xffffffffu, inside);
-  const uint32_t bits = __ballot_sync(0xffffffffu, fg);
-  // run start of this lane within its row: pixels of the same class contiguous to the left
-  uint32_t same = fg ? bits : (~bits & valid);
-  uint32_t below = (~same) & ((1u << lane) - 1u);  // lanes to the left that break the run
-  int run_start = below ? (32 - __clz(below)) : 0;
-  L[threadIdx.x] = r * CCL_TW + run_start;
-  if (lane == 0) rowbits[r] = bits;
+  int fgv[CCL_ROWS_PER_WARP];
+#pragma unroll
+  for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) {  // all loads first
+    const int y = ty * CCL_TH + warp * CCL_ROWS_PER_WARP + k;
+    fgv[k] = (x < W && y < H) ? (bm[(int64_t)y * W + x] != 0) : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) {
+    const int r = warp * CCL_ROWS_PER_WARP + k, y = ty * CCL_TH + r;
+    const uint32_t valid = __ballot_sync(0xffffffffu, x < W && y < H);
+    const uint32_t bits = __ballot_sync(0xffffffffu, fgv[k]);
+    // run start of this lane within its row: pixels of the same class contiguous to the left
+    const uint32_t same = fgv[k] ? bits : (~bits & valid);
+    const uint32_t below = (~same) & ((1u << lane) - 1u);  // lanes to the left that break the run
+    const int run_start = below ? (32 - __clz(below)) : 0;
+    L[r * CCL_TW + lane] = r * CCL_TW + run_start;
+    if (lane == 0) { rowbits[r] = bits; rowvalid[r] = valid; }
+  }
   __syncthreads();
-  if (inside && r > 0) {
+#pragma unroll
+  for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) {
+    const int r = warp * CCL_ROWS_PER_WARP + k;
+    const uint32_t valid = rowvalid[r], bits = rowbits[r];
+    if (r == 0 || !((valid >> lane) & 1)) continue;
     // One union per pair of overlapping runs, not per pixel: a vertical link is redundant when
     // the pixel to the left is in my run and the pixel above it is in the run above me (the
     // leftmost pixel of the overlap makes the link).  Diagonal links (8-connectivity of the
     // foreground) are only needed from the ends of a run.
+    const int fg = (bits >> lane) & 1;
+    const int self = r * CCL_TW + lane;
+    const uint32_t same = fg ? bits : (~bits & valid);
     const uint32_t up = rowbits[r - 1];
-    const uint32_t up_same = fg ? up : (~up & valid);   // pixels above of my class
-    const bool n_same = (up_same >> lane) & 1;
-    if (n_same) {
+    const uint32_t up_same = fg ? up : (~up & valid);  // pixels above of my class
+    if ((up_same >> lane) & 1) {
       const bool left_mine = lane > 0 && ((same >> (lane - 1)) & 1);
       const bool upleft_same = lane > 0 && ((up_same >> (lane - 1)) & 1);
-      if (!(left_mine && upleft_same)) uf_union(L, threadIdx.x, threadIdx.x - CCL_TW);
+      if (!(left_mine && upleft_same)) uf_union(L, self, self - CCL_TW);
     } else if (fg) {
       const bool left_fg = lane > 0 && ((bits >> (lane - 1)) & 1);
       const bool right_fg = lane < 31 && ((bits >> (lane + 1)) & 1);
-      if (lane > 0 && !left_fg && ((up >> (lane - 1)) & 1)) uf_union(L, threadIdx.x, threadIdx.x - CCL_TW - 1);
-      if (lane < 31 && !right_fg && ((up >> (lane + 1)) & 1)) uf_union(L, threadIdx.x, threadIdx.x - CCL_TW + 1);
+      if (lane > 0 && !left_fg && ((up >> (lane - 1)) & 1)) uf_union(L, self, self - CCL_TW - 1);
+      if (lane < 31 && !right_fg && ((up >> (lane + 1)) & 1)) uf_union(L, self, self - CCL_TW + 1);
     }
   }
   __syncthreads();
-  if (inside) {
-    int root = uf_find(L, threadIdx.x);
-    int rx = tx * CCL_TW + (root & 31), ry = ty * CCL_TH + (root >> 5);
-    labels[(int64_t)b * H * W + (int64_t)y * W + x] = ry * W + rx;
+#pragma unroll
+  for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) {
+    const int r = warp * CCL_ROWS_PER_WARP + k, y = ty * CCL_TH + r;
+    if (x < W && y < H) {
+      const int root = uf_find(L, r * CCL_TW + lane);
+      const int rx = tx * CCL_TW + (root & 31), ry = ty * CCL_TH + (root >> 5);
+      labels[(int64_t)b * H * W + (int64_t)y * W + x] = ry * W + rx;
+    }
   }
 }
 
@@ -156,14 +178,17 @@ __global__ void ccl_flatten_kernel(int H, int W, int B, int *__restrict__ labels
   L[i] = root;
 }
 
-int launch_ccl(ocrb_ctx *ctx, const uint8_t *bitmap, int B, int H, int W, int *labels) {
+// flatten = false leaves a forest whose roots are final (label[i] == i  <=>  i is the raster-first
+// pixel of its component); consumers that need the root of an arbitrary pixel call ccl_find.
+int launch_ccl(ocrb_ctx *ctx, const uint8_t *bitmap, int B, int H, int W, int *labels, bool flatten) {
   int tiles_x = (int)cdiv(W, CCL_TW), tiles_y = (int)cdiv(H, CCL_TH);
   int64_t blocks = (int64_t)tiles_x * tiles_y * B;
-  ccl_local_kernel<<<(unsigned)blocks, CCL_TW * CCL_TH, 0, ctx->stream>>>(bitmap, H, W, tiles_x, tiles_y, labels);
+  ccl_local_kernel<<<(unsigned)blocks, CCL_THREADS, 0, ctx->stream>>>(bitmap, H, W, tiles_x, tiles_y, labels);
   OCRB_TRY(check_launch(ctx, "ccl_local"));
   int64_t n = (int64_t)B * H * W;
   ccl_seam_kernel<<<(unsigned)cdiv(blocks * 96, 256), 256, 0, ctx->stream>>>(bitmap, H, W, B, tiles_x, tiles_y, labels);
   OCRB_TRY(check_launch(ctx, "ccl_seam"));
+  if (!flatten) return OCRB_OK;
   ccl_flatten_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(H, W, B, labels);
   return check_launch(ctx, "ccl_flatten");
 }
@@ -202,7 +227,7 @@ int ccl_canonical_labels(ocrb_ctx *ctx, const uint8_t *bitmap_dev, int B, int H,
     if ((rc = lab.reserve(n * 4)) || (rc = flag.reserve(n)) || (rc = rank.reserve((n + 1) * 4)) ||
         (rc = scratch.reserve(scan_scratch_elems(n) * 4)))
       break;
-    if ((rc = launch_ccl(ctx, bitmap_dev, B, H, W, lab.as<int>()))) break;
+    if ((rc = launch_ccl(ctx, bitmap_dev, B, H, W, lab.as<int>(), true))) break;
     ccl_fg_root_flag_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap_dev, lab.as<int>(), HW, n, flag.as<uint8_t>());
     if ((rc = check_launch(ctx, "ccl_fg_root_flag"))) break;
     if ((rc = exclusive_scan<uint8_t, int>(ctx, flag.as<uint8_t>(), n, rank.as<int>(), scratch.as<int>()))) break;

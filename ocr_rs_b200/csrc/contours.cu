@@ -22,35 +22,66 @@ namespace ocrb {
 enum : uint8_t { START_NONE = 0, START_OUTER = 1, START_HOLE = 2 };
 
 // ---------------------------------------------------------------------------------------
-// per-component facts: background components reaching the frame; bounding boxes of
-// left-anchored foreground components (keyed by the row of their root, which is in col 0)
+// The labels arrive as an un-flattened union-find forest whose roots are final.
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int ccl_find(const int *__restrict__ L, int a) {
+  int p = L[a];
+  while (p != a) {
+    a = p;
+    p = L[a];
+  }
+  return a;
+}
+
+// frame pixels only: background components reaching the frame are "open" (no hole border);
+// a foreground root in column 0 means a left-anchored component exists (slow path needed)
+__global__ void contour_frame_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels, int H, int W, int B,
+                                     uint8_t *__restrict__ bg_open, int *__restrict__ need_anchored) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = 2 * W + 2 * H;
+  if (t >= (int64_t)per * B) return;
+  const int b = (int)(t / per), k = (int)(t % per);
+  int x, y;
+  if (k < W) { x = k; y = 0; }
+  else if (k < 2 * W) { x = k - W; y = H - 1; }
+  else if (k < 2 * W + H) { x = 0; y = k - 2 * W; }
+  else { x = W - 1; y = k - 2 * W - H; }
+  const int64_t HW = (int64_t)H * W;
+  const int i = y * W + x;
+  const int *L = labels + b * HW;
+  if (bitmap[b * HW + i] == 0) bg_open[b * HW + ccl_find(L, i)] = 1;
+  else if (x == 0 && L[i] == i) *need_anchored = 1;
+}
+
+// bounding boxes of left-anchored foreground components (keyed by the row of their root, which
+// is in column 0); does nothing unless such a component exists
 __global__ void contour_props_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels, int H, int W,
-                                     int B, uint8_t *__restrict__ bg_open, int4 *__restrict__ anchored_bbox) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t HW = (int64_t)H * W;
-  if (idx >= HW * B) return;
-  int64_t b = idx / HW;
-  int i = (int)(idx % HW);
-  int x = i % W, y = i / W;
-  int root = labels[idx];
-  if (bitmap[idx] == 0) {
-    if (x == 0 || y == 0 || x == W - 1 || y == H - 1) bg_open[b * HW + root] = 1;
-  } else if (root % W == 0) {
-    int4 *bb = anchored_bbox + b * H + root / W;
-    atomicMin(&bb->x, x);
-    atomicMax(&bb->y, x);
-    atomicMin(&bb->z, y);
-    atomicMax(&bb->w, y);
+                                     int B, const int *__restrict__ need_anchored, int4 *__restrict__ anchored_bbox) {
+  if (*need_anchored == 0) return;
+  const int64_t HW = (int64_t)H * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < HW * B; idx += (int64_t)gridDim.x * blockDim.x) {
+    if (bitmap[idx] == 0) continue;
+    const int64_t b = idx / HW;
+    const int i = (int)(idx % HW);
+    const int root = ccl_find(labels + b * HW, i);
+    if (root % W == 0) {
+      int4 *bb = anchored_bbox + b * H + root / W;
+      atomicMin(&bb->x, i % W);
+      atomicMax(&bb->y, i % W);
+      atomicMin(&bb->z, i / W);
+      atomicMax(&bb->w, i / W);
+    }
   }
 }
 
-__global__ void contour_bbox_init_kernel(int4 *bbox, int64_t n) {
+__global__ void contour_bbox_init_kernel(int4 *bbox, int64_t n, int *need_anchored) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) bbox[i] = make_int4(INT32_MAX, -1, INT32_MAX, -1);
+  if (i == 0) *need_anchored = 0;
 }
 
-// closed-form starts for ordinary components
+// closed-form starts for ordinary components: outer = a foreground root outside column 0;
+// hole = the pixel west of a closed background component's root
 __global__ void contour_start_flags_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels, int H, int W,
                                            int B, const uint8_t *__restrict__ bg_open, uint8_t *__restrict__ flags) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,13 +91,11 @@ __global__ void contour_start_flags_kernel(const uint8_t *__restrict__ bitmap, c
   int x = i % W;
   uint8_t f = START_NONE;
   if (bitmap[idx] != 0) {
-    int root = labels[idx];
-    if (root % W != 0) {  // not left-anchored
-      if (root == i) {
-        f = START_OUTER;  // x > 0 here because root % W != 0
-      } else if (x + 1 < W && bitmap[idx + 1] == 0 && labels[idx + 1] == i + 1 && !bg_open[idx + 1]) {
-        f = START_HOLE;
-      }
+    if (labels[idx] == i) {
+      if (x != 0) f = START_OUTER;  // a root in column 0 is left-anchored: replayed by contour_anchored_kernel
+    } else if (x + 1 < W && bitmap[idx + 1] == 0 && labels[idx + 1] == i + 1 && !bg_open[idx + 1]) {
+      const int root = ccl_find(labels + (idx - i), i);
+      if (root % W != 0) f = START_HOLE;
     }
   }
   flags[idx] = f;
@@ -76,8 +105,9 @@ __global__ void contour_start_flags_kernel(const uint8_t *__restrict__ bitmap, c
 // in column 0.  `hole_traced` is a zero-initialised byte per pixel (indexed by bg root).
 __global__ void __launch_bounds__(128) contour_anchored_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels,
                                                                int H, int W, int B, const uint8_t *__restrict__ bg_open,
-                                                               const int4 *__restrict__ anchored_bbox,
+                                                               const int4 *__restrict__ anchored_bbox, const int *__restrict__ need_anchored,
                                                                uint8_t *__restrict__ hole_traced, uint8_t *__restrict__ flags) {
+  if (*need_anchored == 0) return;
   const int lane = threadIdx.x & 31;
   int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wid >= (int64_t)B * H) return;
@@ -96,7 +126,7 @@ __global__ void __launch_bounds__(128) contour_anchored_kernel(const uint8_t *__
   for (int y = bb.z; y <= bb.w; ++y) {
     for (int xb = bb.x; xb <= bb.y; xb += 32) {
       int x = xb + lane;
-      bool in_f = x <= bb.y && bm[y * W + x] != 0 && L[y * W + x] == F;
+      bool in_f = x <= bb.y && bm[y * W + x] != 0 && ccl_find(L, y * W + x) == F;
       bool wcr = in_f && x > 0 && bm[y * W + x - 1] == 0;
       bool ecr = in_f && x + 1 < W && bm[y * W + x + 1] == 0;
       uint32_t cand = __ballot_sync(0xffffffffu, wcr || ecr);
@@ -116,7 +146,7 @@ __global__ void __launch_bounds__(128) contour_anchored_kernel(const uint8_t *__
           lab[k] = -2;  // not background
           if (nx < 0 || ny < 0 || nx >= W || ny >= H) lab[k] = -1;
           else if (bm[ny * W + nx] == 0) {
-            int r = L[ny * W + nx];
+            int r = ccl_find(L, ny * W + nx);
             lab[k] = open[r] ? -1 : r;
           }
           if (lab[k] == -1) visited |= traced_inf;
@@ -326,19 +356,21 @@ __global__ void approx_dp_kernel(const ushort2 *__restrict__ chain, const int64_
 // ---------------------------------------------------------------------------------------
 int launch_contour_starts(ocrb_ctx *ctx, const uint8_t *bitmap, const int *labels, int B, int H, int W,
                           uint8_t *bg_open /*B*HW, zeroed here*/, uint8_t *hole_traced /*B*HW, zeroed here*/,
-                          int4 *anchored_bbox /*B*H*/, uint8_t *flags /*B*HW*/) {
+                          int4 *anchored_bbox /*B*H*/, uint8_t *flags /*B*HW*/, int *need_anchored /*device int*/) {
   int64_t n = (int64_t)B * H * W;
   OCRB_CUDA(cudaMemsetAsync(bg_open, 0, n, ctx->stream));
   OCRB_CUDA(cudaMemsetAsync(hole_traced, 0, n, ctx->stream));
-  contour_bbox_init_kernel<<<(unsigned)cdiv((int64_t)B * H, 256), 256, 0, ctx->stream>>>(anchored_bbox, (int64_t)B * H);
+  contour_bbox_init_kernel<<<(unsigned)cdiv((int64_t)B * H, 256), 256, 0, ctx->stream>>>(anchored_bbox, (int64_t)B * H, need_anchored);
   OCRB_TRY(check_launch(ctx, "contour_bbox_init"));
-  contour_props_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, anchored_bbox);
+  contour_frame_kernel<<<(unsigned)cdiv((int64_t)B * (2 * W + 2 * H), 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, need_anchored);
+  OCRB_TRY(check_launch(ctx, "contour_frame"));
+  contour_props_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, need_anchored, anchored_bbox);
   OCRB_TRY(check_launch(ctx, "contour_props"));
   contour_start_flags_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, flags);
   OCRB_TRY(check_launch(ctx, "contour_start_flags"));
   int64_t warps = (int64_t)B * H;
   contour_anchored_kernel<<<(unsigned)cdiv(warps * 32, 128), 128, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open,
-                                                                                    anchored_bbox, hole_traced, flags);
+                                                                                    anchored_bbox, need_anchored, hole_traced, flags);
   return check_launch(ctx, "contour_anchored");
 }
 

@@ -48,7 +48,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int GW = G / MW;  // sub-tiles per MMA warp
   constexpr int THREADS = (1 + MW + HL_EPI_WARPS) * 32;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ float s_scale[512], s_shift[512];
+  __shared__ __align__(16) float s_scale[512], s_shift[512];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int B_BYTES = N_TILE * 128;
   uint8_t *sA = smem;
@@ -165,7 +165,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int NBLK = NH / 32;  // 32-channel blocks per sub-tile for this warp
     const uint32_t stg = smem_u32(sStg + ew * 2048);
     EpiParams e;
-    e.s_scale = s_scale; e.s_shift = s_shift;
+    e.s_scale = s_scale; e.s_shift = s_shift; e.has_affine = p.scale != nullptr;
     e.addend = p.residual; e.add_mode = p.residual ? EPI_ADD_RESIDUAL : EPI_ADD_NONE;
     e.out = p.out; e.sum_out = nullptr;
     e.Cout = p.Cout; e.out_ldc = p.out_ldc; e.out_coff = p.out_coff; e.rep = p.rep; e.Wo = p.Wo; e.relu = p.relu;

@@ -49,10 +49,11 @@ struct TcSmem {
 
 template <int N_TILE, int STAGES, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p,
+               const __grid_constant__ HeadConsts hc) {
   using L = TcSmem<N_TILE, STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ float s_scale[512], s_shift[512], s_w2[256];
+  __shared__ __align__(16) float s_scale[512], s_shift[512];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sA = smem;
   uint8_t *sB = smem + L::OFF_B;
@@ -70,7 +71,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_tiles = num_m_tiles * p.num_n_tiles;
 
   // ---- one-time setup ----
-  const int n_sc = (EPI == EPI_HEAD) ? 64 : (p.Cout < 512 ? p.Cout : 512);
+  const int n_sc = (EPI == EPI_HEAD) ? 0 : (p.Cout < 512 ? p.Cout : 512);
   for (int i = threadIdx.x; i < n_sc; i += TC_THREADS) {
     s_scale[i] = p.scale ? p.scale[i] : 1.0f;
     s_shift[i] = p.shift ? p.shift[i] : 0.0f;
@@ -81,8 +82,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     reinterpret_cast<uint32_t *>(sA + s * TC_A_BYTES + TC_ROWS * 128)[w] = 0u;
   }
   fence_proxy_async();
-  if (EPI == EPI_HEAD)
-    for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_w2[i] = p.w2[i];
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -155,7 +154,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     EpiParams e;
-    e.s_scale = s_scale; e.s_shift = s_shift;
+    e.s_scale = s_scale; e.s_shift = s_shift; e.has_affine = p.scale != nullptr;
     e.addend = p.residual ? p.residual : p.up_src;
     e.add_mode = p.residual ? EPI_ADD_RESIDUAL : (p.sum_out ? EPI_ADD_SUM : EPI_ADD_NONE);
     e.out = p.out; e.sum_out = p.sum_out;
@@ -216,10 +215,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32(taddr + tap * 64 + c0, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int co = c0 + j;
-              const float h = fmaxf(fmaf(v[j], s_scale[co], s_shift[co]), 0.0f);
+              const int co = c0 + j;  // compile-time after unrolling: hc.* are constant-bank operands
+              const float h = fmaxf(fmaf(v[j], hc.scale[co], hc.shift[co]), 0.0f);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) z[q] = fmaf(h, s_w2[q * 64 + co], z[q]);
+              for (int q = 0; q < 4; ++q) z[q] = fmaf(h, hc.w2[q * 64 + co], z[q]);
             }
           }
           // q = i'*2 + j' of conv-transpose 2: output (4y + 2i + i', 4x + 2j + j')
@@ -320,7 +319,8 @@ int make_weight_tensor_map(CUtensorMap *map, const void *base, int Cout, int Kto
 }
 
 template <int N_TILE, int STAGES, int EPI>
-static int launch_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvTcParams &p, int num_tiles, const char *tag) {
+static int launch_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvTcParams &p, int num_tiles, const char *tag,
+                      const HeadConsts &hc) {
   using L = TcSmem<N_TILE, STAGES>;
   static bool attr_set[16] = {false};
   auto kern = conv_tc_kernel<N_TILE, STAGES, EPI>;
@@ -329,11 +329,14 @@ static int launch_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &
     attr_set[ctx->device & 15] = true;
   }
   int grid = num_tiles < ctx->sm_count ? num_tiles : ctx->sm_count;
-  kern<<<grid, TC_THREADS, L::DYN_BYTES, ctx->stream>>>(tmA, tmB, p);
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, ctx->stream>>>(tmA, tmB, p, hc);
   return check_launch(ctx, tag);
 }
 
-int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, int epi, const char *tag) {
+int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, int epi, const char *tag,
+                   const HeadConsts *hcp) {
+  static const HeadConsts hc_zero = {};
+  const HeadConsts &hc = hcp ? *hcp : hc_zero;
   p.tiles_x = (int)cdiv(p.Wo, TC_TW);
   p.tiles_y = (int)cdiv(p.Ho, TC_TH);
   p.num_n_tiles = p.Cout / n_tile;
@@ -341,12 +344,12 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
   const int num_tiles = p.tiles_x * p.tiles_y * p.B * p.num_n_tiles;
   if (epi == EPI_HEAD) {
     if (n_tile != 256) { set_error("conv_tc head needs N tile 256"); return OCRB_ERR_INVALID; }
-    return launch_one<256, 4, EPI_HEAD>(ctx, tmA, tmB, p, num_tiles, tag);
+    return launch_one<256, 4, EPI_HEAD>(ctx, tmA, tmB, p, num_tiles, tag, hc);
   }
   switch (n_tile) {
-    case 64: return launch_one<64, 6, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag);
-    case 128: return launch_one<128, 5, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag);
-    case 256: return launch_one<256, 4, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag);
+    case 64: return launch_one<64, 6, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+    case 128: return launch_one<128, 5, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+    case 256: return launch_one<256, 4, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag, hc);
   }
   set_error("conv_tc: unsupported N tile %d", n_tile);
   return OCRB_ERR_INVALID;

@@ -30,9 +30,17 @@ struct ConvTcParams {
   int *err = nullptr;                       // device flag set before a pipeline-timeout trap
 };
 
+// DB head tail constants, passed by value (kernel parameter = constant bank: the fully unrolled
+// epilogue reads them as immediate constant operands, no shared-memory traffic)
+struct HeadConsts {
+  float scale[64], shift[64];  // bin_bn2 folded with the conv-transpose-1 bias
+  float w2[256];               // conv-transpose-2 weights [q][co]
+};
+
 int make_act_tensor_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int stride);
 int make_weight_tensor_map(CUtensorMap *map, const void *base, int Cout, int Ktot, int n_tile);
-int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, int epi, const char *tag = "tc:conv");
+int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, int epi, const char *tag = "tc:conv",
+                   const HeadConsts *hc = nullptr);
 
 // conv_halo.cu: 3x3 stride-1 convolutions with the halo'd input tile resident in shared memory
 int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G);

@@ -142,6 +142,7 @@ struct ConvSpec {
 
 struct DevConv {
   int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
+  bool has_bn = false;
   DevBuf w32;    // fp32 [k*k][cin][cout]
   DevBuf w16;    // bf16 [cout][k*k*cin]
   DevBuf scale, shift;
@@ -190,6 +191,7 @@ static int prep_conv(const HostWeights &hw, const ConvSpec &sp, bool want16, Dev
   OCRB_REQUIRE((int64_t)w->size() == (int64_t)sp.cout * sp.cin * kk, "tensor %s.weight has %zu elements, expected %lld",
                sp.name.c_str(), w->size(), (long long)sp.cout * sp.cin * kk);
   dc.cin = sp.cin; dc.cout = sp.cout; dc.k = sp.k; dc.stride = sp.stride; dc.pad = sp.pad;
+  dc.has_bn = !sp.bn.empty();
   std::vector<float> scale, shift;
   OCRB_TRY(fold_bn(hw, sp.bn, sp.cout, nullptr, scale, shift));
   OCRB_TRY(upload(dc.scale, scale));
@@ -227,6 +229,7 @@ struct ocrb_det {
   DevBuf head_w16;                       // bf16 path: [256][64]
   DevBuf tr2_w;                          // [4][64] fp32 (both paths)
   float tr2_bias = 0.f;
+  HeadConsts head_c;                     // bf16 path: head constants passed as a kernel parameter
   // activations (grow-only), keyed by name
   std::map<std::string, DevBuf> act;
   DevBuf staged_in, staged_out, err;
@@ -301,6 +304,8 @@ static int det_build(ocrb_det *d, const HostWeights &hw) {
       for (int tp = 0; tp < 4; ++tp) w2t[tp * 64 + ci] = (*w2)[ci * 4 + tp];
     OCRB_TRY(upload(d->tr2_w, w2t));
     d->tr2_bias = (*b2)[0];
+    for (int i = 0; i < 64; ++i) { d->head_c.scale[i] = sc[i]; d->head_c.shift[i] = sh[i]; }
+    for (int i = 0; i < 256; ++i) d->head_c.w2[i] = w2t[i];
   }
   OCRB_TRY(d->err.reserve(4));
   OCRB_CUDA(cudaMemset(d->err.p, 0, 4));
@@ -491,7 +496,8 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     p.Wo = (w + 2 * c.pad - c.k) / c.stride + 1;
     p.Cout = c.cout;
     p.R = c.k; p.S = c.k; p.cin_chunks = c.cin / 64; p.stride = c.stride; p.pad = c.pad;
-    p.scale = c.scale.as<float>(); p.shift = c.shift.as<float>();
+    p.scale = c.has_bn ? c.scale.as<float>() : nullptr;  // no batch-norm: identity epilogue
+    p.shift = c.has_bn ? c.shift.as<float>() : nullptr;
     if (p.out && p.out_ldc == 0) p.out_ldc = c.cout;
     p.err = d->err.as<int>();
     const std::string tag = "tc:" + name;
@@ -560,7 +566,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     q.scale = d->tr1_scale.as<float>(); q.shift = d->tr1_shift.as<float>();
     q.w2 = d->tr2_w.as<float>(); q.b2 = d->tr2_bias; q.thresh = thresh;
     q.prob = prob; q.bitmap = bitmap; q.err = d->err.as<int>();
-    OCRB_TRY(launch_conv_tc(ctx, *ma, *mb, q, 256, EPI_HEAD, "tc:head"));
+    OCRB_TRY(launch_conv_tc(ctx, *ma, *mb, q, 256, EPI_HEAD, "tc:head", &d->head_c));
   }
   return OCRB_OK;
 }

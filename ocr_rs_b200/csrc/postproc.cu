@@ -13,8 +13,8 @@ namespace ocrb {
 
 // kernels / launchers defined in the other translation units
 int launch_binarize(ocrb_ctx *, const float *, int64_t, float, uint8_t *);
-int launch_ccl(ocrb_ctx *, const uint8_t *, int, int, int, int *);
-int launch_contour_starts(ocrb_ctx *, const uint8_t *, const int *, int, int, int, uint8_t *, uint8_t *, int4 *, uint8_t *);
+int launch_ccl(ocrb_ctx *, const uint8_t *, int, int, int, int *, bool);
+int launch_contour_starts(ocrb_ctx *, const uint8_t *, const int *, int, int, int, uint8_t *, uint8_t *, int4 *, uint8_t *, int *);
 int launch_contour_records(ocrb_ctx *, const uint8_t *, const int *, int64_t, int64_t *, uint8_t *);
 int launch_contour_count(ocrb_ctx *, const uint8_t *, int64_t, int *);
 int64_t contour_count_slot(int64_t);
@@ -100,12 +100,13 @@ static int run_contour_stage(ocrb_ctx *ctx, PostprocWorkspace *ws, const uint8_t
   OCRB_TRY(ws->bg_open.reserve(n));
   OCRB_TRY(ws->hole_traced.reserve(n));
   OCRB_TRY(ws->flags.reserve(n));
-  OCRB_TRY(ws->bbox.reserve((size_t)B * H * sizeof(int4)));
+  OCRB_TRY(ws->bbox.reserve((size_t)B * H * sizeof(int4) + 16));
   OCRB_TRY(ws->offs.reserve(scan_scratch_elems(n) * 2 * 4 + 64));
   OCRB_TRY(ws->scan_scratch.reserve(scan_scratch_elems(n) * 8));
-  OCRB_TRY(launch_ccl(ctx, bitmap, B, H, W, ws->labels.as<int>()));
+  OCRB_TRY(launch_ccl(ctx, bitmap, B, H, W, ws->labels.as<int>(), false));
   OCRB_TRY(launch_contour_starts(ctx, bitmap, ws->labels.as<int>(), B, H, W, ws->bg_open.as<uint8_t>(),
-                                 ws->hole_traced.as<uint8_t>(), ws->bbox.as<int4>(), ws->flags.as<uint8_t>()));
+                                 ws->hole_traced.as<uint8_t>(), ws->bbox.as<int4>(), ws->flags.as<uint8_t>(),
+                                 reinterpret_cast<int *>(ws->bbox.as<int4>() + (size_t)B * H)));
   OCRB_TRY(launch_contour_count(ctx, ws->flags.as<uint8_t>(), n, ws->offs.as<int>()));
   int nc32 = 0;
   OCRB_TRY(read_scalar(ctx, ws->offs.as<int>() + contour_count_slot(n), &nc32));

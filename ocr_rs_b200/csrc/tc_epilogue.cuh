@@ -97,6 +97,7 @@ enum { EPI_ADD_NONE = 0, EPI_ADD_RESIDUAL = 1, EPI_ADD_SUM = 2 };
 
 struct EpiParams {
   const float *s_scale, *s_shift;  // shared-memory copies, indexed by absolute channel
+  int has_affine;                  // 0: scale = 1, shift = 0 (convolutions without batch-norm)
   // addend [..][Cout] bf16: RESIDUAL: y += addend[opix] before ReLU (model.rs:47-53);
   // SUM: second output sum_out = y + addend[apix] (FPN "up2 + lateral", model.rs:126-137)
   const __nv_bfloat16 *addend;
@@ -109,8 +110,17 @@ struct EpiParams {
 // pre: the addend block fetched by epi_fetch_addend (ignored when add_mode == NONE).
 __device__ __forceinline__ void epi_block32(float (&v)[32], int lane, uint32_t stg, const EpiRows &rw, const EpiParams &e, int n,
                                             const uint4 (&pre)[4]) {
+  if (e.has_affine) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], e.s_scale[n + j], e.s_shift[n + j]);
+    for (int j = 0; j < 8; ++j) {  // 128-bit broadcast loads: 16 shared-memory wavefronts instead of 64
+      const float4 sc = *reinterpret_cast<const float4 *>(e.s_scale + n + 4 * j);
+      const float4 sh = *reinterpret_cast<const float4 *>(e.s_shift + n + 4 * j);
+      v[4 * j + 0] = fmaf(v[4 * j + 0], sc.x, sh.x);
+      v[4 * j + 1] = fmaf(v[4 * j + 1], sc.y, sh.y);
+      v[4 * j + 2] = fmaf(v[4 * j + 2], sc.z, sh.z);
+      v[4 * j + 3] = fmaf(v[4 * j + 3], sc.w, sh.w);
+    }
+  }
   if (e.add_mode == EPI_ADD_RESIDUAL) {
     epi_stage_addend(stg, lane, pre);
     __syncwarp();
@@ -121,20 +131,33 @@ __device__ __forceinline__ void epi_block32(float (&v)[32], int lane, uint32_t s
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
+  if (e.add_mode == EPI_ADD_SUM) {
+    // lateral + FPN sum: y is staged once; the coalesced view stores y itself (if wanted) and
+    // y + addend, adding the prefetched addend registers in place (no second smem round trip;
+    // y is rounded to bf16 before the add, as the materialised lateral would be)
+    epi_put_own_row(stg, lane, v);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      if (!(rw.valid & (1u << it))) continue;
+      const uint4 u = lds_16(stg + epi_stg_off(it * 8 + (lane >> 2), lane & 3));
+      if (e.out) st_16(e.out + (int64_t)rw.opix[it] * e.out_ldc + e.out_coff + n + (lane & 3) * 8, u);
+      const uint32_t yw[4] = {u.x, u.y, u.z, u.w}, aw[4] = {pre[it].x, pre[it].y, pre[it].z, pre[it].w};
+      uint32_t sw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16(yw[j]), b = unpack_bf16(aw[j]);
+        sw[j] = pack_bf16(a.x + b.x, a.y + b.y);
+      }
+      st_16(e.sum_out + (int64_t)rw.opix[it] * e.Cout + n + (lane & 3) * 8, make_uint4(sw[0], sw[1], sw[2], sw[3]));
+    }
+    __syncwarp();
+    return;
+  }
   if (e.out) {
     epi_put_own_row(stg, lane, v);
     __syncwarp();
     epi_store(stg, lane, rw, e.out, e.out_ldc, e.out_coff + n, e.rep, e.Wo);
-    __syncwarp();
-  }
-  if (e.add_mode == EPI_ADD_SUM) {
-    epi_stage_addend(stg, lane, pre);
-    __syncwarp();
-    epi_add_own_row(stg, lane, v);
-    __syncwarp();
-    epi_put_own_row(stg, lane, v);
-    __syncwarp();
-    epi_store(stg, lane, rw, e.sum_out, e.Cout, n, 1, e.Wo);
     __syncwarp();
   }
 }

@@ -141,7 +141,7 @@ def _compare_maps(metrics, pp, prob, adjust):
         assert len(res.polygons[b]) == len(exp_p)
         for a, e in zip(res.polygons[b], exp_p):
             assert a.shape == e.shape and (a == e).all()
-        assert np.abs(res.scores[b] - exp_s).max(initial=0.0) <= 1e-12
+        assert np.allclose(res.scores[b], exp_s, rtol=0, atol=1e-12, equal_nan=True)  # NaN = empty mask (0/0) on both sides
         n += len(exp_p)
     return n
 
