@@ -194,4 +194,20 @@ inline int check_launch(ocrb_ctx *ctx, const char *what) {
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// One-item-per-thread kernels whose items follow wildly different control flow (border tracing,
+// Douglas-Peucker, polygon offsetting) run only SPARSE_LANES lanes per warp: a warp executes
+// its divergent lanes one after another, so fewer lanes per warp = shorter critical path, and
+// the extra warps spread over all SMs.  Index of this thread's item, or -1.
+constexpr int SPARSE_LANES = 4;
+#ifdef __CUDACC__
+__device__ __forceinline__ int64_t sparse_item_index() {
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  return lane < SPARSE_LANES ? gw * SPARSE_LANES + lane : -1;
+}
+#endif
+inline unsigned sparse_grid(int64_t n_items, int block_threads) {
+  return (unsigned)cdiv(cdiv(n_items, SPARSE_LANES) * 32, block_threads);
+}
+
 }  // namespace ocrb

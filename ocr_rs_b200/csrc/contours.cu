@@ -262,8 +262,8 @@ __device__ __forceinline__ int64_t trace_border(const Tracer &t, int sx, int sy,
 
 __global__ void trace_count_kernel(const uint8_t *__restrict__ bitmap, int H, int W, const int64_t *__restrict__ start_idx,
                                    const uint8_t *__restrict__ kind, int64_t n_contours, int *__restrict__ lengths) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_contours) return;
+  const int64_t c = sparse_item_index();
+  if (c < 0 || c >= n_contours) return;
   int64_t HW = (int64_t)H * W;
   int64_t g = start_idx[c];
   int64_t b = g / HW;
@@ -276,8 +276,8 @@ __global__ void trace_count_kernel(const uint8_t *__restrict__ bitmap, int H, in
 __global__ void trace_store_kernel(const uint8_t *__restrict__ bitmap, int H, int W, const int64_t *__restrict__ start_idx,
                                    const uint8_t *__restrict__ kind, int64_t n_contours,
                                    const int64_t *__restrict__ chain_off, ushort2 *__restrict__ chain) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_contours) return;
+  const int64_t c = sparse_item_index();
+  if (c < 0 || c >= n_contours) return;
   int64_t HW = (int64_t)H * W;
   int64_t g = start_idx[c];
   int64_t b = g / HW;
@@ -303,8 +303,8 @@ __device__ __forceinline__ double dist_d(double ax, double ay, double bx, double
 __global__ void approx_dp_kernel(const ushort2 *__restrict__ chain, const int64_t *__restrict__ chain_off,
                                  int64_t n_contours, int *__restrict__ stack, ushort2 *__restrict__ dp_out,
                                  int *__restrict__ dp_count) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_contours) return;
+  const int64_t c = sparse_item_index();
+  if (c < 0 || c >= n_contours) return;
   const int64_t off = chain_off[c];
   const int n = (int)(chain_off[c + 1] - off);
   const ushort2 *p = chain + off;
@@ -393,21 +393,21 @@ int launch_contour_records(ocrb_ctx *ctx, const uint8_t *flags, const int *tile_
 int launch_trace_count(ocrb_ctx *ctx, const uint8_t *bitmap, int H, int W, const int64_t *start_idx, const uint8_t *kind,
                        int64_t n_contours, int *lengths) {
   if (n_contours <= 0) return OCRB_OK;
-  trace_count_kernel<<<(unsigned)cdiv(n_contours, 128), 128, 0, ctx->stream>>>(bitmap, H, W, start_idx, kind, n_contours, lengths);
+  trace_count_kernel<<<sparse_grid(n_contours, 128), 128, 0, ctx->stream>>>(bitmap, H, W, start_idx, kind, n_contours, lengths);
   return check_launch(ctx, "trace_count");
 }
 
 int launch_trace_store(ocrb_ctx *ctx, const uint8_t *bitmap, int H, int W, const int64_t *start_idx, const uint8_t *kind,
                        int64_t n_contours, const int64_t *chain_off, ushort2 *chain) {
   if (n_contours <= 0) return OCRB_OK;
-  trace_store_kernel<<<(unsigned)cdiv(n_contours, 128), 128, 0, ctx->stream>>>(bitmap, H, W, start_idx, kind, n_contours, chain_off, chain);
+  trace_store_kernel<<<sparse_grid(n_contours, 128), 128, 0, ctx->stream>>>(bitmap, H, W, start_idx, kind, n_contours, chain_off, chain);
   return check_launch(ctx, "trace_store");
 }
 
 int launch_approx_dp(ocrb_ctx *ctx, const ushort2 *chain, const int64_t *chain_off, int64_t n_contours, int *stack,
                      ushort2 *dp_out, int *dp_count) {
   if (n_contours <= 0) return OCRB_OK;
-  approx_dp_kernel<<<(unsigned)cdiv(n_contours, 128), 128, 0, ctx->stream>>>(chain, chain_off, n_contours, stack, dp_out, dp_count);
+  approx_dp_kernel<<<sparse_grid(n_contours, 128), 128, 0, ctx->stream>>>(chain, chain_off, n_contours, stack, dp_out, dp_count);
   return check_launch(ctx, "approx_dp");
 }
 

@@ -570,13 +570,16 @@ __global__ void unclip_slab_size_kernel(const int *__restrict__ cand_contour, co
 
 // status: 0 dropped by score, 1 kept, 2 dropped (empty offset, reference panics, D11),
 //         3 dropped by min_size
-__global__ void unclip_kernel(const int *__restrict__ cand_contour, const int64_t *__restrict__ chain_off,
+constexpr int UNCLIP_THREADS = 64;
+
+__global__ void __launch_bounds__(UNCLIP_THREADS) unclip_kernel(const int *__restrict__ cand_contour, const int64_t *__restrict__ chain_off,
                               const ushort2 *__restrict__ dp_pts, const int *__restrict__ dp_count, int n_cand,
                               const double *__restrict__ scores, double box_thresh, double min_size, double factor,
                               const int64_t *__restrict__ slab_off, int2 *__restrict__ slabs, int *__restrict__ out_count,
                               uint8_t *__restrict__ status, double *__restrict__ sside_out, int2 *__restrict__ box_out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_cand) return;
+  const int64_t si = sparse_item_index();
+  if (si < 0 || si >= n_cand) return;
+  const int i = (int)si;
   out_count[i] = 0;
   double score = scores[i];
   if (score < 0.0 || box_thresh > score) {  // metrics.rs:100 (`score < 0` marks a rejected candidate)
@@ -626,7 +629,7 @@ int launch_unclip(ocrb_ctx *ctx, const int *cand_contour, const int64_t *chain_o
                   const int *dp_count, int n_cand, const double *scores, double box_thresh, double min_size, double factor,
                   const int64_t *slab_off, int2 *slabs, int *out_count, uint8_t *status, double *sside_out, int2 *box_out) {
   if (n_cand <= 0) return OCRB_OK;
-  unclip_kernel<<<(unsigned)cdiv(n_cand, 64), 64, 0, ctx->stream>>>(cand_contour, chain_off, dp_pts, dp_count, n_cand, scores,
+  unclip_kernel<<<sparse_grid(n_cand, UNCLIP_THREADS), UNCLIP_THREADS, 0, ctx->stream>>>(cand_contour, chain_off, dp_pts, dp_count, n_cand, scores,
                                                                     box_thresh, min_size, factor, slab_off, slabs, out_count,
                                                                     status, sside_out, box_out);
   return check_launch(ctx, "unclip");

@@ -5,7 +5,7 @@
 //
 // Three streams per context keep the GPU busy across the post-processing's host round trips:
 //   copy stream     H2D of image chunk c+1 (double-buffered) while chunk c is in the detector
-//   forward stream  detector forward, chunk by chunk (32 images), into a GROUP buffer
+//   forward stream  detector forward, chunk by chunk (64 images), into a GROUP buffer
 //   ctx->stream     post-processing of group g (up to 128 images per launch: the contour /
 //                   polygon kernels are latency-bound, so they are amortised over more images)
 //                   while the forward of group g+1 runs on the forward stream
@@ -49,7 +49,7 @@ static int get_ws(ocrb_ctx *ctx, PipelineWorkspace **out) {
   return OCRB_OK;
 }
 
-constexpr int PIPE_CHUNK_BF16 = 32, PIPE_CHUNK_FP32 = 4, PIPE_GROUP = 128;
+constexpr int PIPE_CHUNK_BF16 = 64, PIPE_CHUNK_FP32 = 4, PIPE_GROUP = 128;
 
 }  // namespace ocrb
 
@@ -73,11 +73,12 @@ extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uin
   // the per-launch event timeline (ocrb_ctx_profile_begin) needs one stream: serialise then
   const bool serial = ctx->prof.on;
   cudaStream_t s_pp = ctx->stream, s_fwd = serial ? ctx->stream : ws->fwd, s_copy = serial ? ctx->stream : ws->copy;
-  // group: <= 128 images and < 2^31 pixels (post-processing index arithmetic); chunk: <= 32 images
+  // group: <= 128 images and < 2^31 pixels (post-processing index arithmetic); chunk: <= 64 images
   int group = PIPE_GROUP;
   while ((int64_t)group * HW >= ((int64_t)1 << 31) && group > 1) group /= 2;
   if (group > B) group = B;
-  int chunk = bf16 ? PIPE_CHUNK_BF16 : PIPE_CHUNK_FP32;
+  static const int chunk_env = getenv("OCRB_CHUNK") ? atoi(getenv("OCRB_CHUNK")) : 0;  // tuning knob
+  int chunk = bf16 ? (chunk_env > 0 ? chunk_env : PIPE_CHUNK_BF16) : PIPE_CHUNK_FP32;
   if (chunk > group) chunk = group;
   const int n_groups = (B + group - 1) / group;
   const bool img_dev = is_device_ptr(images);

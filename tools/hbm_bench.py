@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Achieved GB/s of the HBM-bound kernels (binarize, u8<->f32 conversion, resize+luma+pad, CCL,
+full post-processing) against the measured copy bandwidth (MEASURED_PEAKS.json).  Device-resident
+inputs larger than L2, CUDA events on the ctx stream, 3 warm-ups + 10 timed calls each.
+Algorithmic bytes per unit are SURVEY.md §8(d)'s figures (binarize 5 B/px, CCL 5 B/px, ...)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ocr_rs_b200 import _ffi, synth  # noqa: E402
+
+
+def timed(ctx, fn, reps=10, warm=3):
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    for _ in range(warm):
+        fn()
+    ctx.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+    for _ in range(reps):
+        fn()
+    with torch.cuda.stream(stream):
+        e1.record()
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def main():
+    ctx = _ffi.Context(0)
+    L = _ffi.lib()
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    out = {}
+    n = 16 * 4096 * 4096  # 268M pixels: 1.07 GB f32 in, 268 MB u8 out
+    pred = torch.rand(n, device="cuda")
+    bits = torch.empty(n, dtype=torch.uint8, device="cuda")
+    t = timed(ctx, lambda: _ffi.check(L.ocrb_binarize(ctx.handle, pred.data_ptr(), n, 0.6, bits.data_ptr())))
+    out["binarize"] = {"bytes_per_px": 5, "GBps": 5 * n / t / 1e9}
+    img = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
+    f = torch.empty(n, dtype=torch.float32, device="cuda")
+    t = timed(ctx, lambda: _ffi.check(L.ocrb_convert_image_to_tensor(ctx.handle, img.data_ptr(), n, f.data_ptr())))
+    out["convert_image_to_tensor"] = {"bytes_per_px": 5, "GBps": 5 * n / t / 1e9}
+    t = timed(ctx, lambda: _ffi.check(L.ocrb_convert_tensor_to_image(ctx.handle, pred.data_ptr(), n, 255.0, bits.data_ptr())))
+    out["convert_tensor_to_image"] = {"bytes_per_px": 5, "GBps": 5 * n / t / 1e9}
+    del f, img
+    # resize + luma + pad: 4000x3000 RGBA -> 800x600 in an 800x800 frame
+    sw, sh = 4000, 3000
+    rgba = torch.randint(0, 256, (sh, sw, 4), dtype=torch.uint8, device="cuda")
+    gray = torch.empty((800, 800), dtype=torch.uint8, device="cuda")
+    import ctypes as C
+    ax, ay = C.c_double(), C.c_double()
+    t = timed(ctx, lambda: _ffi.check(L.ocrb_preprocess_rgba(ctx.handle, rgba.data_ptr(), sw, sh, 800, 800, gray.data_ptr(), C.byref(ax), C.byref(ay))))
+    out["preprocess_rgba_4000x3000"] = {"bytes": sw * sh * 4 + 800 * 800, "GBps": (sw * sh * 4 + 800 * 800) / t / 1e9, "ms": t * 1e3}
+    # CCL labels (test hook: includes flatten + canonical renumbering) and the full post-processing on cfg-5 maps
+    prob = torch.from_numpy(np.stack([synth.make_blob_prob_map(4096, 4096, 9000, seed=4 + i, near_thresh=4096, max_w=48, max_h=24) for i in range(2)])).cuda()
+    B, H, W = prob.shape
+    adj = np.ones((B, 2))
+    def pp():
+        h = _ffi.c_p()
+        _ffi.check(L.ocrb_get_boxes_and_box_scores(ctx.handle, prob.data_ptr(), _ffi.ptr(adj), B, H, W, None, C.byref(h)))
+        L.ocrb_polygons_free(h)
+    pp()  # warm-up: workspace allocation
+    pp()
+    ctx.profile_begin()
+    pp()
+    prof = ctx.profile_end()
+    t = timed(ctx, pp, reps=5)
+    px = B * H * W
+    out["postproc_cfg5_4096x4096"] = {"maps_per_s": B / t, "ms_per_map": t / B * 1e3,
+                                     "kernels_ms": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}}
+    ccl_ms = sum(v[1] for k, v in prof.items() if k.startswith("ccl_"))
+    out["ccl_cfg5"] = {"bytes_per_px": 5, "GBps": 5 * px / (ccl_ms * 1e-3) / 1e9, "ms": ccl_ms}
+    for k, v in out.items():
+        if "GBps" in v:
+            v["frac_of_measured_hbm_peak"] = v["GBps"] / peak
+    print(json.dumps({"hbm_peak_GBps": peak, "results": out}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
