@@ -39,18 +39,24 @@ struct HaloGeom {
   int a_stages, b_stages;
 };
 
-template <int N_TILE, int G>
+template <int N_TILE, int G, int CG>
 __global__ void __launch_bounds__((1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS) * 32, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p, const HaloGeom g) {
+  // CG = 2: a CTA PAIR works as one unit (tcgen05 cta_group::2).  Each CTA owns a spatial tile
+  // (its A operand, its accumulators) and HALF of every weight tile; the leader CTA issues
+  // UMMAs of M = 256 that read both halves.  Per CTA that halves the shared-memory reads and
+  // the L2 traffic of the B operand — the single-CTA kernel is bound by exactly those reads
+  // ((4 KB A + 32*N B) per N/2 tensor cycles: 192 B/cycle at N = 64, 128 B/cycle at N = 128).
   // N = 64 MMAs last only 32 tensor-pipe cycles: two issuing warps (sub-tiles split between
-  // them) keep the pipe fed; N = 128 needs one
+  // them) keep the pipe fed; N = 128 needs one.
   constexpr int MW = G >= 4 ? 2 : 1;
   constexpr int GW = G / MW;  // sub-tiles per MMA warp
   constexpr int THREADS = (1 + MW + HL_EPI_WARPS) * 32;
+  constexpr int NB = N_TILE / CG;  // weight rows held by this CTA
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(16) float s_scale[512], s_shift[512];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int B_BYTES = N_TILE * 128;
+  constexpr int B_BYTES = NB * 128;
   uint8_t *sA = smem;
   uint8_t *sB = smem + g.a_stages * g.a_stage_bytes;
   uint8_t *sStg = sB + g.b_stages * B_BYTES;
@@ -61,11 +67,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   constexpr uint32_t TMEM_COLS = 2 * G * N_TILE <= 256 ? 256 : 512;
   static_assert(2 * G * N_TILE <= 512, "accumulators do not fit TMEM");
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int num_m_tiles = tiles_per_img * p.B;
-  const int num_units = num_m_tiles * p.num_n_tiles;
+  const int pairs_per_n = (num_m_tiles + CG - 1) / CG;  // CG spatial tiles per work unit
+  const int num_units = pairs_per_n * p.num_n_tiles;
+  const int unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
   const int chunks = p.cin_chunks;
 
   for (int i = threadIdx.x; i < p.Cout && i < 512; i += THREADS) {
@@ -75,38 +84,56 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < g.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], MW); }
-    for (int s = 0; s < g.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], MW); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], MW); mbar_init(&tempty[a], HL_EPI_WARPS); }
+    // full barriers live in the leader: one producer arrival (+ its bytes) per CTA of the pair
+    for (int s = 0; s < g.a_stages; ++s) { mbar_init(&a_full[s], CG); mbar_init(&a_empty[s], MW); }
+    for (int s = 0; s < g.b_stages; ++s) { mbar_init(&b_full[s], CG); mbar_init(&b_empty[s], MW); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], MW); mbar_init(&tempty[a], CG * HL_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer (every CTA loads its own tile and its half of B) =================
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      const int n_tile = unit / num_m_tiles, m_tile = unit - n_tile * num_m_tiles;
+    for (int unit = unit0; unit < num_units; unit += unit_step) {
+      const int n_tile = unit / pairs_per_n, m_tile = (unit - n_tile * pairs_per_n) * CG + (int)rank;
+      // a tile index past the end (odd tile count) reads only out-of-bounds zeros
       const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
       const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
       for (int ck = 0; ck < chunks; ++ck) {
         mbar_wait(&a_empty[as], aph ^ 1, p.err, 11);
         if (elect_one()) {
-          mbar_expect_tx(&a_full[as], g.a_tx_bytes);
-          tma_load_4d(sA + as * g.a_stage_bytes, &tmA, &a_full[as], ck * 64, tx * g.TW - 1, ty * g.TH - 1, b);
+          if (CG == 2) {
+            const uint32_t bar = mapa_u32(&a_full[as], 0);
+            mbar_expect_tx_cluster(bar, g.a_tx_bytes);
+            tma_load_4d_2sm(sA + as * g.a_stage_bytes, &tmA, bar, ck * 64, tx * g.TW - 1, ty * g.TH - 1, b);
+          } else {
+            mbar_expect_tx(&a_full[as], g.a_tx_bytes);
+            tma_load_4d(sA + as * g.a_stage_bytes, &tmA, &a_full[as], ck * 64, tx * g.TW - 1, ty * g.TH - 1, b);
+          }
         }
         __syncwarp();
         if (++as == g.a_stages) { as = 0; aph ^= 1; }
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&b_empty[bs], bph ^ 1, p.err, 12);
           if (elect_one()) {
-            mbar_expect_tx(&b_full[bs], B_BYTES);
-            tma_load_2d(sB + bs * B_BYTES, &tmB, &b_full[bs], (tap * chunks + ck) * 64, n_tile * N_TILE);
+            if (CG == 2) {
+              const uint32_t bar = mapa_u32(&b_full[bs], 0);
+              mbar_expect_tx_cluster(bar, B_BYTES);
+              tma_load_2d_2sm(sB + bs * B_BYTES, &tmB, bar, (tap * chunks + ck) * 64, n_tile * N_TILE + (int)rank * NB);
+            } else {
+              mbar_expect_tx(&b_full[bs], B_BYTES);
+              tma_load_2d(sB + bs * B_BYTES, &tmB, &b_full[bs], (tap * chunks + ck) * 64, n_tile * N_TILE);
+            }
           }
           __syncwarp();
           if (++bs == g.b_stages) { bs = 0; bph ^= 1; }
@@ -114,47 +141,62 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp <= MW) {
-    // ================= MMA issuers =================
-    constexpr uint32_t idesc = make_idesc(N_TILE);
-    const int g0 = (warp - 1) * GW;  // first sub-tile of this warp
-    int as = 0, bs = 0, acc = 0;
-    uint32_t aph = 0, bph = 0, acc_phase = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      mbar_wait(&tempty[acc], acc_phase ^ 1, p.err, 13);
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + (uint32_t)((acc * G + g0) * N_TILE);
-      for (int ck = 0; ck < chunks; ++ck) {
-        mbar_wait(&a_full[as], aph, p.err, 14);
-        // start address advances by whole 128 B rows: (gi*128 + row_off) * 128 B >> 4
-        const uint64_t a0 = make_smem_desc(sA + as * g.a_stage_bytes) + (uint64_t)(g0 * 128 * 8);
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&b_full[bs], bph, p.err, 15);
-          tc_fence_after();
-          const int r = tap / 3, s = tap - 3 * r;
-          const uint64_t bdesc = make_smem_desc(sB + bs * B_BYTES);
-          const uint64_t at = a0 + (uint64_t)((r * g.PW + s) * 8);
-          const uint32_t first = (ck | tap) != 0 ? 1u : 0u;
-          if (elect_one()) {
+    // ================= MMA issuers (leader CTA only) =================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(N_TILE, 128 * CG);
+      const int g0 = (warp - 1) * GW;  // first sub-tile of this warp
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1, p.err, 13);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)((acc * G + g0) * N_TILE);
+        for (int ck = 0; ck < chunks; ++ck) {
+          mbar_wait(&a_full[as], aph, p.err, 14);
+          // start address advances by whole 128 B rows: (gi*128 + row_off) * 128 B >> 4
+          const uint64_t a0 = make_smem_desc(sA + as * g.a_stage_bytes) + (uint64_t)(g0 * 128 * 8);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[bs], bph, p.err, 15);
+            tc_fence_after();
+            const int r = tap / 3, s = tap - 3 * r;
+            const uint64_t bdesc = make_smem_desc(sB + bs * B_BYTES);
+            const uint64_t at = a0 + (uint64_t)((r * g.PW + s) * 8);
+            const uint32_t first = (ck | tap) != 0 ? 1u : 0u;
+            if (elect_one()) {
 #pragma unroll
-            for (int gi = 0; gi < GW; ++gi) {
+              for (int gi = 0; gi < GW; ++gi) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_base + (uint32_t)(gi * N_TILE), at + (uint64_t)(gi * 128 * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                          k != 0 ? 1u : first);
+                for (int k = 0; k < 4; ++k) {
+                  if (CG == 2)
+                    umma_bf16_2sm(d_base + (uint32_t)(gi * N_TILE), at + (uint64_t)(gi * 128 * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                  k != 0 ? 1u : first);
+                  else
+                    umma_bf16(d_base + (uint32_t)(gi * N_TILE), at + (uint64_t)(gi * 128 * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                              k != 0 ? 1u : first);
+                }
+              }
+              if (CG == 2) {
+                umma_commit_2sm(&b_empty[bs]);
+                if (tap == 8) {
+                  umma_commit_2sm(&a_empty[as]);
+                  if (ck == chunks - 1) umma_commit_2sm(&tfull[acc]);
+                }
+              } else {
+                umma_commit(&b_empty[bs]);
+                if (tap == 8) {
+                  umma_commit(&a_empty[as]);
+                  if (ck == chunks - 1) umma_commit(&tfull[acc]);
+                }
+              }
             }
-            umma_commit(&b_empty[bs]);
-            if (tap == 8) {
-              umma_commit(&a_empty[as]);
-              if (ck == chunks - 1) umma_commit(&tfull[acc]);
-            }
+            __syncwarp();
+            if (++bs == g.b_stages) { bs = 0; bph ^= 1; }
           }
-          __syncwarp();
-          if (++bs == g.b_stages) { bs = 0; bph ^= 1; }
+          if (++as == g.a_stages) { as = 0; aph ^= 1; }
         }
-        if (++as == g.a_stages) { as = 0; aph ^= 1; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ================= epilogue =================
@@ -171,8 +213,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     e.Cout = p.Cout; e.out_ldc = p.out_ldc; e.out_coff = p.out_coff; e.rep = p.rep; e.Wo = p.Wo; e.relu = p.relu;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      const int n_tile = unit / num_m_tiles, m_tile = unit - n_tile * num_m_tiles;
+    for (int unit = unit0; unit < num_units; unit += unit_step) {
+      const int n_tile = unit / pairs_per_n, m_tile = (unit - n_tile * pairs_per_n) * CG + (int)rank;
+      const bool real_tile = m_tile < num_m_tiles;
       const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
       const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
       const int n0 = n_tile * N_TILE + half * NH;
@@ -184,7 +227,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int m = gi * 128 + quarter * 32 + it * 8 + (lane >> 2);
           const int yl = m / g.PW, xl = m - yl * g.PW;
           const int y = ty * g.TH + yl, x = tx * g.TW + xl;
-          const bool ok = yl < g.TH && xl < g.TW && y < p.Ho && x < p.Wo;
+          const bool ok = real_tile && yl < g.TH && xl < g.TW && y < p.Ho && x < p.Wo;
           rw.opix[it] = (b * p.Ho + y) * p.Wo + x;
           rw.apix[it] = rw.opix[it];
           if (ok) rw.valid |= 1u << it;
@@ -217,16 +260,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));  // the issuer waits in the leader
+        else mbar_arrive(&tempty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -252,7 +300,7 @@ static void pick_geom(int Ho, int Wo, int G, int *PW, int *TH) {
   }
 }
 
-int halo_geometry(int Ho, int Wo, int n_tile, int G, HaloGeom *out) {
+int halo_geometry(int Ho, int Wo, int n_tile, int G, HaloGeom *out) {  // n_tile = weight rows per CTA
   HaloGeom g;
   pick_geom(Ho, Wo, G, &g.PW, &g.TH);
   g.TW = g.PW - 2;
@@ -277,40 +325,59 @@ int halo_geometry(int Ho, int Wo, int n_tile, int G, HaloGeom *out) {
 
 int make_act_tensor_map_box(CUtensorMap *map, const void *base, int B, int H, int W, int C, int box_w, int box_h);
 
-int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G) {
-  HaloGeom g;
-  OCRB_TRY(halo_geometry(H, W, n_tile, G, &g));
-  return make_act_tensor_map_box(map, base, B, H, W, C, g.PW, g.TH + 2);
-}
 
-template <int N_TILE, int G>
+template <int N_TILE, int G, int CG>
 static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvTcParams &p, const HaloGeom &g,
                            int num_units, const char *tag) {
   static bool attr_set[16] = {false};
-  auto kern = conv_halo_kernel<N_TILE, G>;
+  auto kern = conv_halo_kernel<N_TILE, G, CG>;
   if (!attr_set[ctx->device & 15]) {
     OCRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
     attr_set[ctx->device & 15] = true;
   }
-  const int smem = 1024 + g.a_stages * g.a_stage_bytes + g.b_stages * N_TILE * 128 + HL_STG_BYTES + 512;
-  const int grid = num_units < ctx->sm_count ? num_units : ctx->sm_count;
-  kern<<<grid, (1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS) * 32, smem, ctx->stream>>>(tmA, tmB, p, g);
+  const int smem = 1024 + g.a_stages * g.a_stage_bytes + g.b_stages * (N_TILE / CG) * 128 + HL_STG_BYTES + 512;
+  int grid = num_units * CG < ctx->sm_count ? num_units * CG : (ctx->sm_count / CG) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3((1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OCRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p, g));
   return check_launch(ctx, tag);
 }
+
+static int halo_cg() {  // CTA-pair mode unless OCRB_HALO_CG=1
+  static const int cg = (getenv("OCRB_HALO_CG") && atoi(getenv("OCRB_HALO_CG")) == 1) ? 1 : 2;
+  return cg;
+}
+
+int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G) {
+  HaloGeom g;
+  OCRB_TRY(halo_geometry(H, W, n_tile / halo_cg(), G, &g));
+  return make_act_tensor_map_box(map, base, B, H, W, C, g.PW, g.TH + 2);
+}
+int halo_weight_box_rows(int n_tile) { return n_tile / halo_cg(); }
 
 // 3x3 / stride 1 / pad 1 only; n_tile in {64 (G = 4), 128 (G = 2)}
 int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, const char *tag) {
   if (p.R != 3 || p.S != 3 || p.stride != 1 || p.pad != 1 || p.sum_out || !p.out) { set_error("conv_halo: unsupported convolution"); return OCRB_ERR_INVALID; }
   if (p.Cout % n_tile != 0 || p.Cout > 512) { set_error("conv_halo: Cout %d vs N tile %d", p.Cout, n_tile); return OCRB_ERR_INVALID; }
-  const int G = n_tile == 64 ? 4 : 2;
+  const int G = n_tile == 64 ? 4 : 2, CG = halo_cg();
   HaloGeom g;
-  OCRB_TRY(halo_geometry(p.Ho, p.Wo, n_tile, G, &g));
+  OCRB_TRY(halo_geometry(p.Ho, p.Wo, n_tile / CG, G, &g));
   p.tiles_x = (int)cdiv(p.Wo, g.TW);
   p.tiles_y = (int)cdiv(p.Ho, g.TH);
   p.num_n_tiles = p.Cout / n_tile;
-  const int num_units = p.tiles_x * p.tiles_y * p.B * p.num_n_tiles;
-  if (n_tile == 64) return launch_halo_one<64, 4>(ctx, tmA, tmB, p, g, num_units, tag);
-  if (n_tile == 128) return launch_halo_one<128, 2>(ctx, tmA, tmB, p, g, num_units, tag);
+  const int num_units = (int)cdiv((int64_t)p.tiles_x * p.tiles_y * p.B, CG) * p.num_n_tiles;
+  if (n_tile == 64) return CG == 2 ? launch_halo_one<64, 4, 2>(ctx, tmA, tmB, p, g, num_units, tag) : launch_halo_one<64, 4, 1>(ctx, tmA, tmB, p, g, num_units, tag);
+  if (n_tile == 128) return CG == 2 ? launch_halo_one<128, 2, 2>(ctx, tmA, tmB, p, g, num_units, tag) : launch_halo_one<128, 2, 1>(ctx, tmA, tmB, p, g, num_units, tag);
   set_error("conv_halo: unsupported N tile %d", n_tile);
   return OCRB_ERR_INVALID;
 }

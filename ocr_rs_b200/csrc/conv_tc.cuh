@@ -44,6 +44,7 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
 
 // conv_halo.cu: 3x3 stride-1 convolutions with the halo'd input tile resident in shared memory
 int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G);
+int halo_weight_box_rows(int n_tile);  // rows of the weight TMA box (half the N tile in CTA-pair mode)
 int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, const char *tag);
 
 }  // namespace ocrb

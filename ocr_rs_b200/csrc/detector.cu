@@ -490,7 +490,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     } else {
       OCRB_TRY(get_map(d, "a." + name, in, B, h, w, c.cin, c.stride, &ma));
     }
-    OCRB_TRY(get_wmap(d, (halo ? "wh." : "w.") + name, c.w16.p, c.cout, c.k * c.k * c.cin, nt, &mb));
+    OCRB_TRY(get_wmap(d, (halo ? "wh." : "w.") + name, c.w16.p, c.cout, c.k * c.k * c.cin, halo ? halo_weight_box_rows(nt) : nt, &mb));
     p.B = B;
     p.Ho = (h + 2 * c.pad - c.k) / c.stride + 1;
     p.Wo = (w + 2 * c.pad - c.k) / c.stride + 1;
