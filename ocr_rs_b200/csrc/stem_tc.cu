@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "tc_epilogue.cuh"
 #include "tc_ptx.cuh"
 
 namespace ocrb {
@@ -26,8 +27,18 @@ constexpr int SK_THREADS = 256;
 constexpr int SK_A_BYTES = 4 * 128 * 128;                  // 4 M tiles x 128 rows x 128 B
 constexpr int SK_OFF_B = SK_A_BYTES;                       // 64 x 128 B
 constexpr int SK_OFF_PATCH = SK_OFF_B + 64 * 128;          // bf16 [39][64]
-constexpr int SK_OFF_MISC = SK_OFF_PATCH + SK_IH * SK_IW * 2;
-constexpr int SK_SMEM = SK_OFF_MISC + 1024 + 1024;         // scale/shift/barrier + alignment slack
+constexpr int SK_RAW_WORDS = 17;                           // 68 raw bytes per patch row: 3 lead-in + 64 + 1
+constexpr int SK_RAW_BYTES = SK_IH * SK_RAW_WORDS * 4;     // one raw u8 patch (cp.async prefetch target)
+constexpr int SK_OFF_RAW = SK_OFF_PATCH + SK_IH * SK_IW * 2;
+constexpr int SK_OFF_MISC = SK_OFF_RAW + 2 * SK_RAW_BYTES;
+constexpr int SK_SMEM = SK_OFF_MISC + 64 + 1024;           // barrier + TMEM slot + alignment slack
+
+__device__ __forceinline__ void cp_async_4_zfill(uint32_t dst, const void *src, bool ok) {
+  const int n = ok ? 4 : 0;  // src-size 0: the 4 destination bytes are zero-filled (= conv / image padding)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <class TIn>
 __global__ void __launch_bounds__(SK_THREADS, 2)
@@ -38,10 +49,11 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
   uint8_t *sA = smem;
   uint8_t *sB = smem + SK_OFF_B;
   __nv_bfloat16 *s_patch = reinterpret_cast<__nv_bfloat16 *>(smem + SK_OFF_PATCH);
-  float *s_scale = reinterpret_cast<float *>(smem + SK_OFF_MISC);
-  float *s_shift = s_scale + 64;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(s_shift + 64);
+  uint8_t *s_raw = smem + SK_OFF_RAW;
+  __shared__ float s_scale[64], s_shift[64];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SK_OFF_MISC);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
+  const uint32_t sA_u32 = smem_u32(sA), patch_u32 = smem_u32(s_patch), raw_u32 = smem_u32(s_raw);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Hc = H / 2, Wc = W / 2, Hp = H / 4, Wp = W / 4;
@@ -75,30 +87,68 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
   constexpr uint32_t idesc = make_idesc(64);
   uint32_t parity = 0;
 
+  // u8 input: the raw patch of the NEXT unit is prefetched with cp.async while this one is
+  // computed.  Patch column j is raw byte 3 + j: ix0 = 4*px0 - 5 is always 3 (mod 4), so the
+  // 4-byte-aligned row start is ix0 - 3.
+  auto prefetch_raw = [&](int unit, int buf) {
+    const int b = unit / (tiles_x * tiles_y), t = unit - b * (tiles_x * tiles_y);
+    const int py0 = (t / tiles_x) * SK_PH, px0 = (t % tiles_x) * SK_PW;
+    const int iy0 = 4 * py0 - 5, xa = 4 * px0 - 8;
+    const uint8_t *img = reinterpret_cast<const uint8_t *>(in) + (int64_t)b * H * W;
+    for (int i = tid; i < SK_IH * SK_RAW_WORDS; i += SK_THREADS) {
+      const int row = i / SK_RAW_WORDS, w = i - row * SK_RAW_WORDS;
+      const int yy = iy0 + row, xx = xa + 4 * w;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      cp_async_4_zfill(raw_u32 + buf * SK_RAW_BYTES + i * 4, ok ? img + (int64_t)yy * W + xx : img, ok);
+    }
+    cp_async_commit();
+  };
+  int buf = 0;
+  if (sizeof(TIn) == 1 && (int)blockIdx.x < units) prefetch_raw(blockIdx.x, 0);
+
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int b = unit / (tiles_x * tiles_y), t = unit - b * (tiles_x * tiles_y);
     const int py0 = (t / tiles_x) * SK_PH, px0 = (t % tiles_x) * SK_PW;
     const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;  // conv-grid origin (pool pad 1)
     const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;  // input origin (conv pad 3)
-    const TIn *img = in + (int64_t)b * H * W;
     // ---- (a) input patch -> bf16 (u8 grey levels are exact in bf16)
-    for (int i = tid; i < SK_IH * SK_IW; i += SK_THREADS) {
-      const int yy = iy0 + (i >> 6), xx = ix0 + (i & 63);
-      const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (float)img[(int64_t)yy * W + xx] : 0.0f;
-      s_patch[i] = __float2bfloat16(v);
+    if (sizeof(TIn) == 1) {
+      cp_async_wait_all();
+      __syncthreads();
+      if (unit + (int)gridDim.x < units) prefetch_raw(unit + gridDim.x, buf ^ 1);
+      const uint32_t *raw = reinterpret_cast<const uint32_t *>(s_raw + buf * SK_RAW_BYTES);
+      for (int i = tid; i < SK_IH * SK_RAW_WORDS; i += SK_THREADS) {
+        const int row = i / SK_RAW_WORDS, w = i - row * SK_RAW_WORDS;
+        const uint32_t word = raw[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int col = 4 * w + k - 3;
+          if (col >= 0 && col < SK_IW) s_patch[row * SK_IW + col] = __float2bfloat16((float)((word >> (8 * k)) & 0xffu));
+        }
+      }
+      buf ^= 1;
+    } else {
+      const TIn *img = in + (int64_t)b * H * W;
+      for (int i = tid; i < SK_IH * SK_IW; i += SK_THREADS) {
+        const int yy = iy0 + (i >> 6), xx = ix0 + (i & 63);
+        const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (float)img[(int64_t)yy * W + xx] : 0.0f;
+        s_patch[i] = __float2bfloat16(v);
+      }
     }
     __syncthreads();
     // ---- (b) A rows: chunk j of row (cy, cx) = patch[2cy + j][2cx .. 2cx + 7]
     for (int m = tid; m < SK_ROWS; m += SK_THREADS) {
       const int cy = m / SK_CW, cx = m - cy * SK_CW;
-      uint8_t *row = sA + m * 128;
-      const uint32_t *src = reinterpret_cast<const uint32_t *>(s_patch + (2 * cy) * SK_IW + 2 * cx);
+      const uint32_t row = sA_u32 + m * 128;
+      const uint32_t src = patch_u32 + ((2 * cy) * SK_IW + 2 * cx) * 2;
 #pragma unroll
       for (int j = 0; j < 7; ++j) {
-        const uint32_t *s4 = src + j * (SK_IW / 2);
-        *reinterpret_cast<uint4 *>(row + ((j ^ (m & 7)) << 4)) = make_uint4(s4[0], s4[1], s4[2], s4[3]);
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.u32 %0, [%4];\n\tld.shared.u32 %1, [%4+4];\n\tld.shared.u32 %2, [%4+8];\n\tld.shared.u32 %3, [%4+12];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(src + j * SK_IW * 2));
+        sts_16(row + ((j ^ (m & 7)) << 4), make_uint4(w0, w1, w2, w3));
       }
-      *reinterpret_cast<uint4 *>(row + ((7 ^ (m & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+      sts_16(row + ((7 ^ (m & 7)) << 4), make_uint4(0, 0, 0, 0));
     }
     fence_proxy_async();
     __syncthreads();
@@ -144,7 +194,7 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
                 pk[h] = pack_bf16(y0, y1);
               }
               const int chunk = half * 4 + j4;
-              *reinterpret_cast<uint4 *>(sA + m * 128 + ((chunk ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              sts_16(sA_u32 + m * 128 + ((chunk ^ (m & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
             }
           }
         }
@@ -165,7 +215,7 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
             const int m = (2 * py + r) * SK_CW + 2 * px + s;
-            const uint4 u = *reinterpret_cast<const uint4 *>(sA + m * 128 + ((chunk ^ (m & 7)) << 4));
+            const uint4 u = lds_16(sA_u32 + m * 128 + ((chunk ^ (m & 7)) << 4));
             const __nv_bfloat162 *hv = reinterpret_cast<const __nv_bfloat162 *>(&u);
 #pragma unroll
             for (int h = 0; h < 4; ++h) mx[h] = __hmax2(mx[h], hv[h]);
