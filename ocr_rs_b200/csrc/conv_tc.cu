@@ -36,22 +36,23 @@ constexpr int TC_STG_BYTES = TC_EPI_WARPS * 2048;               // per-warp epil
 // ---------------------------------------------------------------------------------------
 // shared-memory carve-up (dynamic part; scale/shift/w2 are static __shared__)
 // ---------------------------------------------------------------------------------------
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, int RING>
 struct TcSmem {
   static constexpr int B_BYTES = N_TILE * 128;
   static constexpr int OFF_B = STAGES * TC_A_BYTES;
   static constexpr int OFF_STG = OFF_B + STAGES * B_BYTES;
-  static constexpr int OFF_BAR = OFF_STG + TC_STG_BYTES;          // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  static constexpr int OFF_RING = OFF_STG + TC_STG_BYTES;         // RING x 2 KB per epilogue warp (addend prefetch)
+  static constexpr int OFF_BAR = OFF_RING + TC_EPI_WARPS * RING * 2048;  // full[STAGES], empty[STAGES], tfull[2], tempty[2]
   static constexpr int OFF_TMEM = OFF_BAR + (2 * STAGES + 4) * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;                 // slack for manual 1024 B alignment
 };
 
-template <int N_TILE, int STAGES, int EPI>
+template <int N_TILE, int STAGES, int EPI, int RING>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p,
                const __grid_constant__ HeadConsts hc) {
-  using L = TcSmem<N_TILE, STAGES>;
+  using L = TcSmem<N_TILE, STAGES, RING>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(16) float s_scale[512], s_shift[512];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -167,19 +168,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (EPI == EPI_STD) {
         constexpr int NH = N_TILE / 2, NBLK = NH / 32;
         const int n0 = n_tile * N_TILE + half * NH;
-        EpiRows rw;
-        rw.valid = 0;
+        auto rows_of_tile = [&](int tl, EpiRows &rw) {
+          const int nt = tl / num_m_tiles, mt = tl - nt * num_m_tiles;
+          const int bb = mt / tiles_per_img, tt = mt - bb * tiles_per_img;
+          const int tyy = tt / p.tiles_x, txx = tt - tyy * p.tiles_x;
+          rw.valid = 0;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int m = quarter * 32 + it * 8 + (lane >> 2);
-          const int yl = m / TC_TW, xl = m - yl * TC_TW;
-          const int y = ty * TC_TH + yl, x = tx * TC_TW + xl;
-          rw.opix[it] = (b * p.Ho + y) * p.Wo + x;
-          rw.apix[it] = p.sum_out ? (b * (p.Ho >> 1) + (y >> 1)) * (p.Wo >> 1) + (x >> 1) : rw.opix[it];
-          if (m < TC_ROWS && y < p.Ho && x < p.Wo) rw.valid |= 1u << it;
-        }
+          for (int it = 0; it < 4; ++it) {
+            const int m = quarter * 32 + it * 8 + (lane >> 2);
+            const int yl = m / TC_TW, xl = m - yl * TC_TW;
+            const int y = tyy * TC_TH + yl, x = txx * TC_TW + xl;
+            rw.opix[it] = (bb * p.Ho + y) * p.Wo + x;
+            rw.apix[it] = p.sum_out ? (bb * (p.Ho >> 1) + (y >> 1)) * (p.Wo >> 1) + (x >> 1) : rw.opix[it];
+            if (m < TC_ROWS && y < p.Ho && x < p.Wo) rw.valid |= 1u << it;
+          }
+        };
+        EpiRows rw;
+        rows_of_tile(tile, rw);
+        constexpr bool USE_RING = RING >= NBLK && RING > 0;
+        const uint32_t ring = smem_u32(smem + L::OFF_RING + ew * (RING * 2048));
         uint4 pre[4] = {};
-        if (e.add_mode != EPI_ADD_NONE) epi_fetch_addend(pre, lane, rw, e.addend, e.Cout, n0);
+        if (e.add_mode != EPI_ADD_NONE) {
+          if (USE_RING) {
+            if (tile == (int)blockIdx.x) {  // first tile of this CTA: nothing was prefetched yet
+#pragma unroll
+              for (int blk = 0; blk < NBLK; ++blk) {
+                epi_prefetch_addend(ring + blk * 2048, lane, rw, e.addend, e.Cout, n0 + blk * 32);
+                cp_async_commit_group();
+              }
+            }
+          } else {
+            epi_fetch_addend(pre, lane, rw, e.addend, e.Cout, n0);
+          }
+        }
+        EpiRows rw_next;
+        const int next_tile = tile + gridDim.x;
+        if (USE_RING && e.add_mode != EPI_ADD_NONE && next_tile < num_tiles) rows_of_tile(next_tile, rw_next);
         mbar_wait(&tfull[acc], acc_phase, p.err, 4);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE + half * NH);
@@ -187,11 +211,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int blk = 0; blk < NBLK; ++blk) {
           float v[32];
           tmem_ld32(taddr + blk * 32, v);
-          uint4 cur[4];
+          if (USE_RING && e.add_mode != EPI_ADD_NONE) {
+            // this block's addend was prefetched a whole tile ago; NBLK - 1 younger groups may still fly
+            cp_async_wait_group<(NBLK > 0 ? NBLK - 1 : 0)>();
+            __syncwarp();
+            epi_block32(v, lane, stg, rw, e, n0 + blk * 32, pre, ring + blk * 2048);
+            // slot free again: prefetch the same block of the next tile (an empty group keeps the count uniform)
+            if (next_tile < num_tiles) {
+              const int nn0 = (next_tile / num_m_tiles) * N_TILE + half * NH;
+              epi_prefetch_addend(ring + blk * 2048, lane, rw_next, e.addend, e.Cout, nn0 + blk * 32);
+            }
+            cp_async_commit_group();
+          } else {
+            uint4 cur[4];
 #pragma unroll
-          for (int it = 0; it < 4; ++it) cur[it] = pre[it];
-          if (e.add_mode != EPI_ADD_NONE && blk + 1 < NBLK) epi_fetch_addend(pre, lane, rw, e.addend, e.Cout, n0 + (blk + 1) * 32);
-          epi_block32(v, lane, stg, rw, e, n0 + blk * 32, cur);
+            for (int it = 0; it < 4; ++it) cur[it] = pre[it];
+            if (e.add_mode != EPI_ADD_NONE && blk + 1 < NBLK) epi_fetch_addend(pre, lane, rw, e.addend, e.Cout, n0 + (blk + 1) * 32);
+            epi_block32(v, lane, stg, rw, e, n0 + blk * 32, cur);
+          }
         }
       } else {
         // DB head tail: columns n = tap(i,j)*64 + co of conv-transpose 1; per tap BN+ReLU then
@@ -318,12 +355,12 @@ int make_weight_tensor_map(CUtensorMap *map, const void *base, int Cout, int Kto
   return OCRB_OK;
 }
 
-template <int N_TILE, int STAGES, int EPI>
+template <int N_TILE, int STAGES, int EPI, int RING>
 static int launch_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvTcParams &p, int num_tiles, const char *tag,
                       const HeadConsts &hc) {
-  using L = TcSmem<N_TILE, STAGES>;
+  using L = TcSmem<N_TILE, STAGES, RING>;
   static bool attr_set[16] = {false};
-  auto kern = conv_tc_kernel<N_TILE, STAGES, EPI>;
+  auto kern = conv_tc_kernel<N_TILE, STAGES, EPI, RING>;
   if (!attr_set[ctx->device & 15]) {
     OCRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set[ctx->device & 15] = true;
@@ -344,12 +381,16 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
   const int num_tiles = p.tiles_x * p.tiles_y * p.B * p.num_n_tiles;
   if (epi == EPI_HEAD) {
     if (n_tile != 256) { set_error("conv_tc head needs N tile 256"); return OCRB_ERR_INVALID; }
-    return launch_one<256, 4, EPI_HEAD>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+    return launch_one<256, 4, EPI_HEAD, 0>(ctx, tmA, tmB, p, num_tiles, tag, hc);
   }
   switch (n_tile) {
-    case 64: return launch_one<64, 6, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag, hc);
-    case 128: return launch_one<128, 5, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag, hc);
-    case 256: return launch_one<256, 4, EPI_STD>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+    case 64: return launch_one<64, 6, EPI_STD, 0>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+    case 128: return launch_one<128, 5, EPI_STD, 0>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+    case 256:
+      // FPN laterals (second output = y + up2(addend)): 1x1 convs with few K blocks, so two
+      // operand stages suffice and the shared memory goes to the addend prefetch ring instead
+      if (p.sum_out) return launch_one<256, 2, EPI_STD, 4>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+      return launch_one<256, 4, EPI_STD, 0>(ctx, tmA, tmB, p, num_tiles, tag, hc);
   }
   set_error("conv_tc: unsupported N tile %d", n_tile);
   return OCRB_ERR_INVALID;

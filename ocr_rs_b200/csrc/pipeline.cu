@@ -75,6 +75,8 @@ extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uin
   cudaStream_t s_pp = ctx->stream, s_fwd = serial ? ctx->stream : ws->fwd, s_copy = serial ? ctx->stream : ws->copy;
   // group: <= 128 images and < 2^31 pixels (post-processing index arithmetic); chunk: <= 64 images
   int group = PIPE_GROUP;
+  // a small batch is still cut into two groups so that post-processing overlaps a forward
+  if (B < 2 * PIPE_GROUP && B >= 64) group = ((B + 1) / 2 + 31) / 32 * 32;
   while ((int64_t)group * HW >= ((int64_t)1 << 31) && group > 1) group /= 2;
   if (group > B) group = B;
   static const int chunk_env = getenv("OCRB_CHUNK") ? atoi(getenv("OCRB_CHUNK")) : 0;  // tuning knob

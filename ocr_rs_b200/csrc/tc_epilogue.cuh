@@ -93,6 +93,24 @@ __device__ __forceinline__ void epi_store(uint32_t stg, int lane, const EpiRows 
   }
 }
 
+// ---- addend prefetch ring (cp.async straight into shared memory, a whole tile ahead) -------
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void *src, bool ok) {
+  const int n = ok ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// one 32-row x 64-byte addend block -> ring slot (same swizzled layout as the staging block)
+__device__ __forceinline__ void epi_prefetch_addend(uint32_t slot, int lane, const EpiRows &rw, const __nv_bfloat16 *add, int add_ld, int n) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const bool ok = (rw.valid >> it) & 1u;
+    cp_async_16_zfill(slot + epi_stg_off(it * 8 + (lane >> 2), lane & 3), ok ? add + (int64_t)rw.apix[it] * add_ld + n + (lane & 3) * 8 : add, ok);
+  }
+}
+
 enum { EPI_ADD_NONE = 0, EPI_ADD_RESIDUAL = 1, EPI_ADD_SUM = 2 };
 
 struct EpiParams {
@@ -107,9 +125,10 @@ struct EpiParams {
 };
 
 // v: this thread's 32 accumulators for channels [n, n + 32); stg: this warp's 2 KB block;
-// pre: the addend block fetched by epi_fetch_addend (ignored when add_mode == NONE).
+// pre: the addend block fetched by epi_fetch_addend (ignored when add_mode == NONE), or, when
+// add_slot != 0, the addend block sits in that shared-memory ring slot (epi_prefetch_addend).
 __device__ __forceinline__ void epi_block32(float (&v)[32], int lane, uint32_t stg, const EpiRows &rw, const EpiParams &e, int n,
-                                            const uint4 (&pre)[4]) {
+                                            const uint4 (&pre)[4], uint32_t add_slot = 0) {
   if (e.has_affine) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {  // 128-bit broadcast loads: 16 shared-memory wavefronts instead of 64
@@ -142,7 +161,9 @@ __device__ __forceinline__ void epi_block32(float (&v)[32], int lane, uint32_t s
       if (!(rw.valid & (1u << it))) continue;
       const uint4 u = lds_16(stg + epi_stg_off(it * 8 + (lane >> 2), lane & 3));
       if (e.out) st_16(e.out + (int64_t)rw.opix[it] * e.out_ldc + e.out_coff + n + (lane & 3) * 8, u);
-      const uint32_t yw[4] = {u.x, u.y, u.z, u.w}, aw[4] = {pre[it].x, pre[it].y, pre[it].z, pre[it].w};
+      uint4 av = pre[it];
+      if (add_slot) av = lds_16(add_slot + epi_stg_off(it * 8 + (lane >> 2), lane & 3));
+      const uint32_t yw[4] = {u.x, u.y, u.z, u.w}, aw[4] = {av.x, av.y, av.z, av.w};
       uint32_t sw[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
