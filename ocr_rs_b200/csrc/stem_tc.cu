@@ -50,7 +50,7 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
   uint8_t *sB = smem + SK_OFF_B;
   __nv_bfloat16 *s_patch = reinterpret_cast<__nv_bfloat16 *>(smem + SK_OFF_PATCH);
   uint8_t *s_raw = smem + SK_OFF_RAW;
-  __shared__ float s_scale[64], s_shift[64];
+  __shared__ __align__(16) float s_scale[64], s_shift[64];
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SK_OFF_MISC);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
   const uint32_t sA_u32 = smem_u32(sA), patch_u32 = smem_u32(s_patch), raw_u32 = smem_u32(s_raw);
@@ -175,26 +175,31 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
         const int mt = (warp >> 2) + 2 * rep;
         const int m = mt * 128 + q * 32 + lane;
         const int cy = m / SK_CW, cx = m - cy * SK_CW;
-        const bool in_grid = m < SK_ROWS && (cy0 + cy) >= 0 && (cy0 + cy) < Hc && (cx0 + cx) >= 0 && (cx0 + cx) < Wc;
+        const bool in_grid = (cy0 + cy) >= 0 && (cy0 + cy) < Hc && (cx0 + cx) >= 0 && (cx0 + cx) < Wc;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64);
+        const uint32_t row = sA_u32 + m * 128;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float v[32];
           tmem_ld32(taddr + half * 32, v);
           if (m < SK_ROWS) {
+            if (in_grid) {
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                const int c = half * 32 + j4 * 8 + 2 * h;
-                // outside the conv grid = max-pool padding (-inf): a large negative finite value
-                const float y0 = in_grid ? fmaxf(fmaf(v[j4 * 8 + 2 * h], s_scale[c], s_shift[c]), 0.0f) : -3.0e38f;
-                const float y1 = in_grid ? fmaxf(fmaf(v[j4 * 8 + 2 * h + 1], s_scale[c + 1], s_shift[c + 1]), 0.0f) : -3.0e38f;
-                pk[h] = pack_bf16(y0, y1);
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const int c = half * 32 + j4 * 8;
+                const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + c), sc1 = *reinterpret_cast<const float4 *>(s_scale + c + 4);
+                const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + c), sh1 = *reinterpret_cast<const float4 *>(s_shift + c + 4);
+                const float *x = v + j4 * 8;
+                sts_16(row + (((half * 4 + j4) ^ (m & 7)) << 4),
+                       make_uint4(pack_bf16(fmaxf(fmaf(x[0], sc0.x, sh0.x), 0.f), fmaxf(fmaf(x[1], sc0.y, sh0.y), 0.f)),
+                                  pack_bf16(fmaxf(fmaf(x[2], sc0.z, sh0.z), 0.f), fmaxf(fmaf(x[3], sc0.w, sh0.w), 0.f)),
+                                  pack_bf16(fmaxf(fmaf(x[4], sc1.x, sh1.x), 0.f), fmaxf(fmaf(x[5], sc1.y, sh1.y), 0.f)),
+                                  pack_bf16(fmaxf(fmaf(x[6], sc1.z, sh1.z), 0.f), fmaxf(fmaf(x[7], sc1.w, sh1.w), 0.f))));
               }
-              const int chunk = half * 4 + j4;
-              sts_16(sA_u32 + m * 128 + ((chunk ^ (m & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            } else {
+              // outside the conv grid = max-pool padding (-inf): a large negative finite bf16 (0xFF7F)
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) sts_16(row + (((half * 4 + j4) ^ (m & 7)) << 4), make_uint4(0xFF7FFF7Fu, 0xFF7FFF7Fu, 0xFF7FFF7Fu, 0xFF7FFF7Fu));
             }
           }
         }
@@ -202,28 +207,44 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
     }
     tc_fence_before();
     __syncthreads();
-    // ---- (e) 3x3 / s2 max-pool from the conv tile -> global (16 B = 8 channels per thread)
-    for (int i = tid; i < SK_PH * SK_PW * 8; i += SK_THREADS) {
-      const int chunk = i & 7, pp = i >> 3;
-      const int py = pp / SK_PW, px = pp - py * SK_PW;
-      if (py0 + py < Hp && px0 + px < Wp) {
-        __nv_bfloat162 mx[4];
+    // ---- (e) 3x3 / s2 max-pool from the conv tile -> global.  One thread = one pooled column
+    // (px, 8-channel chunk) over 4 pooled rows: the horizontal 3-max of each of the 9 conv rows
+    // is computed once and shared by the two pooled rows that overlap it (27 loads / 4 outputs).
+    if (tid < SK_PW * 8 * 2) {
+      const int chunk = tid & 7, px = (tid >> 3) % SK_PW, hrow = tid / (8 * SK_PW);  // hrow: pooled rows 4*hrow .. 4*hrow+3
+      if (px0 + px < Wp) {
+        __nv_bfloat162 prev[4];  // horizontal max of the conv row shared with the previous pooled row
 #pragma unroll
-        for (int h = 0; h < 4; ++h) mx[h] = __floats2bfloat162_rn(-3.0e38f, -3.0e38f);
+        for (int k = 0; k < 9; ++k) {
+          const int cyr = 8 * hrow + k;  // conv row within the tile
+          __nv_bfloat162 hm[4];
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int m = (2 * py + r) * SK_CW + 2 * px + s;
+          for (int s3 = 0; s3 < 3; ++s3) {
+            const int m = cyr * SK_CW + 2 * px + s3;
             const uint4 u = lds_16(sA_u32 + m * 128 + ((chunk ^ (m & 7)) << 4));
             const __nv_bfloat162 *hv = reinterpret_cast<const __nv_bfloat162 *>(&u);
 #pragma unroll
-            for (int h = 0; h < 4; ++h) mx[h] = __hmax2(mx[h], hv[h]);
+            for (int h = 0; h < 4; ++h) hm[h] = s3 == 0 ? hv[h] : __hmax2(hm[h], hv[h]);
           }
-        uint4 o;
-        o.x = *reinterpret_cast<uint32_t *>(&mx[0]); o.y = *reinterpret_cast<uint32_t *>(&mx[1]);
-        o.z = *reinterpret_cast<uint32_t *>(&mx[2]); o.w = *reinterpret_cast<uint32_t *>(&mx[3]);
-        *reinterpret_cast<uint4 *>(out + (((int64_t)b * Hp + py0 + py) * Wp + px0 + px) * 64 + chunk * 8) = o;
+          if (k == 0) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) prev[h] = hm[h];
+          } else if (k & 1) {  // middle conv row of pooled row (k-1)/2: start accumulating
+#pragma unroll
+            for (int h = 0; h < 4; ++h) prev[h] = __hmax2(prev[h], hm[h]);
+          } else {             // last conv row of pooled row k/2 - 1 = first conv row of pooled row k/2
+            const int py = 4 * hrow + k / 2 - 1;
+            __nv_bfloat162 o2[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) { o2[h] = __hmax2(prev[h], hm[h]); prev[h] = hm[h]; }
+            if (py0 + py < Hp) {
+              uint4 o;
+              o.x = *reinterpret_cast<uint32_t *>(&o2[0]); o.y = *reinterpret_cast<uint32_t *>(&o2[1]);
+              o.z = *reinterpret_cast<uint32_t *>(&o2[2]); o.w = *reinterpret_cast<uint32_t *>(&o2[3]);
+              st_16(out + (((int64_t)b * Hp + py0 + py) * Wp + px0 + px) * 64 + chunk * 8, o);
+            }
+          }
+        }
       }
     }
     __syncthreads();  // the conv tile / patch are rewritten by the next unit

@@ -95,3 +95,31 @@ def test_bad_arguments(env):
     bad["in4.weight"] = bad["in4.weight"][:, :128]
     with pytest.raises(OcrbError):
         resnet18(bad, "fp32")
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 32), (3, 64, 32), (2, 32, 96), (1, 416, 96)])
+def test_tiny_and_odd_shapes(env, shape):
+    """Smallest legal maps (one 32x32 cell) and shapes whose feature maps are smaller than one MMA tile."""
+    synth, resnet18, mo = env
+    B, H, W = shape
+    w = synth.make_detector_weights(3, "hard_bn")
+    x = synth.make_noise_images(B, H, W, seed=B * H + W)
+    ref = mo.detector_forward(w, x.reshape(B, 1, H, W).astype(np.float32)).numpy()
+    for mode in ("fp32", "bf16"):
+        got = resnet18(w, mode).forward_t(x.reshape(B, 1, H, W))
+        err = np.abs(got - ref).max()
+        assert err <= TOL[mode], (mode, shape, err)
+
+
+def test_config3_batch16(env):
+    """BASELINE config 3: batch 16 of 800x800 (8 noise + 8 document images), BF16 mode, map tolerance."""
+    synth, resnet18, mo = env
+    w = synth.make_detector_weights(0, "structured1")
+    x = np.concatenate([synth.make_noise_images(8, 800, 800, seed=2), synth.document_image_shard(0, 8, 800, 800)])
+    got = resnet18(w, "bf16").forward_t(x.reshape(16, 1, 800, 800))
+    worst = 0.0
+    for b0 in range(0, 16, 4):  # oracle in slices to bound host memory
+        ref = mo.detector_forward(w, x[b0:b0 + 4].reshape(4, 1, 800, 800).astype(np.float32)).numpy()
+        worst = max(worst, float(np.abs(got[b0:b0 + 4] - ref).max()))
+    print(f"config3 bf16 batch 16: max|dp| = {worst:.3e}")
+    assert worst <= TOL["bf16"]

@@ -129,3 +129,29 @@ def test_pipeline_chunking_and_device_pointers(env):
     _ffi.check(_ffi.lib().ocrb_detect_and_recognize(det._h, None, _ffi.ptr(dimgs), _ffi.ptr(adj), B, H, W, None, None, 0, None, C.byref(h)))
     res2 = _ffi.Polygons(h)
     assert (res2.xy == res.xy).all() and (res2.image_offsets == res.image_offsets).all()
+
+
+def test_pipeline_sharding_invariance(env):
+    """BASELINE config 4 property at reduced size: the polygons of an image do not depend on
+    how the index range is cut (one call over 200 images == two shards == single-image calls),
+    across chunk (64) and group (128) boundaries."""
+    _ffi, synth, Net, resnet18, _, _ = env
+    B, H, W = 200, 160, 160
+    wd = synth.make_detector_weights(0, "structured")
+    imgs = synth.document_image_shard(0, B, H, W, unique=50)
+    # smaller boxes for the small frame
+    glyphs = synth.make_glyphs(4, 4, "strokes")
+    adj = np.ones((B, 2))
+    det, rec = resnet18(wd, "bf16"), Net(synth.make_rec_weights(1))
+    whole, _ = _run_pipeline(_ffi, det, rec, imgs, adj, glyphs)
+    a, _ = _run_pipeline(_ffi, det, rec, imgs[:77], adj[:77], glyphs)
+    b, _ = _run_pipeline(_ffi, det, rec, imgs[77:], adj[77:], glyphs)
+    both = _ffi.Polygons.concat([a, b])
+    for x, y in zip(whole.arrays(), both.arrays()):
+        assert x.shape == y.shape and (x == y).all()
+    for i in (0, 63, 64, 127, 128, 199):
+        one, _ = _run_pipeline(_ffi, det, rec, imgs[i:i + 1], adj[i:i + 1], glyphs)
+        assert len(one.polygons[0]) == len(whole.polygons[i])
+        for p, q in zip(one.polygons[0], whole.polygons[i]):
+            assert (p == q).all()
+    assert sum(len(p) for p in whole.polygons) > 0
