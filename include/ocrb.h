@@ -47,6 +47,7 @@ typedef struct ocrb_ctx ocrb_ctx;
 typedef struct ocrb_det ocrb_det;
 typedef struct ocrb_rec ocrb_rec;
 typedef struct ocrb_polygons ocrb_polygons;
+typedef struct ocrb_varstore ocrb_varstore;
 
 /* ---- context ------------------------------------------------------------------------
  * replaces the process-global `DEVICE` (main.rs:26-28) with an explicit handle */
@@ -170,6 +171,20 @@ int ocrb_rec_forward(ocrb_rec *rec, const float *glyphs, int B, float *logits, i
 int ocrb_rec_forward_u8(ocrb_rec *rec, const uint8_t *glyphs, int B, float *logits, int32_t *argmax, double *prob);
 /* utils::VALUES (utils.rs:7): class index -> character */
 char ocrb_class_to_char(int cls);
+
+/* ---- model files ---------------------------------------------------------------------
+ * vs.load(file) (text_detection/mod.rs:40-44, char_recognition/mod.rs:43-45): native reader of
+ * the libtorch archive tch's VarStore::save writes (utils.rs:55-63) — ZIP of STORED entries,
+ * `data.pkl` + raw storages.  Host-only; tensors are returned as float32 under their VarStore
+ * names (f64 / f16 / bf16 / integer storages are converted). */
+int ocrb_varstore_open(const char *path, ocrb_varstore **out);
+int ocrb_varstore_count(const ocrb_varstore *vs);
+const char *ocrb_varstore_name(const ocrb_varstore *vs, int i);
+int ocrb_varstore_tensor(const ocrb_varstore *vs, int i, const float **data, int64_t *numel, const int64_t **shape, int *ndim);
+void ocrb_varstore_close(ocrb_varstore *vs);
+/* resnet18(&vs.root()) + vs.load(path) / Net::new(&vs.root()) + vs.load(path) in one call */
+int ocrb_det_create_from_file(ocrb_ctx *ctx, const char *path, int mode, ocrb_det **out);
+int ocrb_rec_create_from_file(ocrb_ctx *ctx, const char *path, ocrb_rec **out);
 
 /* ---- pipeline -----------------------------------------------------------------------
  * run_text_detection's device part for a batch (text_detection/mod.rs:46-67, :188-204):

@@ -75,6 +75,13 @@ SIGNATURES = {
     "ocrb_rec_forward": (C.c_int, [c_p, c_p, C.c_int, c_p, c_p, c_p]),
     "ocrb_rec_forward_u8": (C.c_int, [c_p, c_p, C.c_int, c_p, c_p, c_p]),
     "ocrb_class_to_char": (C.c_char, [C.c_int]),
+    "ocrb_varstore_open": (C.c_int, [C.c_char_p, C.POINTER(c_p)]),
+    "ocrb_varstore_count": (C.c_int, [c_p]),
+    "ocrb_varstore_name": (C.c_char_p, [c_p, C.c_int]),
+    "ocrb_varstore_tensor": (C.c_int, [c_p, C.c_int, C.POINTER(C.POINTER(C.c_float)), C.POINTER(i64), C.POINTER(C.POINTER(i64)), C.POINTER(C.c_int)]),
+    "ocrb_varstore_close": (None, [c_p]),
+    "ocrb_det_create_from_file": (C.c_int, [c_p, C.c_char_p, C.c_int, C.POINTER(c_p)]),
+    "ocrb_rec_create_from_file": (C.c_int, [c_p, C.c_char_p, C.POINTER(c_p)]),
     "ocrb_detect_and_recognize": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.POINTER(PostprocParams),
                                             c_p, C.c_int, c_p, C.POINTER(c_p)]),
 }

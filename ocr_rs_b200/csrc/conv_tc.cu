@@ -245,19 +245,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int tj = 0; tj < 2; ++tj) {
           const int tap = half * 2 + tj;  // tap = i*2 + j with i = half
-          float z[4] = {p.b2, p.b2, p.b2, p.b2};
+          // packed fp32x2 FMAs (FFMA2): two channels at a time through BN, two outputs at a time
+          // through the 64 -> 4 contraction; hc.* are constant-bank operands after unrolling
+          float2 z01 = make_float2(p.b2, p.b2), z23 = make_float2(p.b2, p.b2);
 #pragma unroll
           for (int c0 = 0; c0 < 64; c0 += 32) {
             float v[32];
             tmem_ld32(taddr + tap * 64 + c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int co = c0 + j;  // compile-time after unrolling: hc.* are constant-bank operands
-              const float h = fmaxf(fmaf(v[j], hc.scale[co], hc.shift[co]), 0.0f);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) z[q] = fmaf(h, hc.w2[q * 64 + co], z[q]);
+            for (int j = 0; j < 32; j += 2) {
+              const int co = c0 + j;
+              const float2 h = ffma2(make_float2(v[j], v[j + 1]), make_float2(hc.scale[co], hc.scale[co + 1]),
+                                     make_float2(hc.shift[co], hc.shift[co + 1]));
+              const float h0 = fmaxf(h.x, 0.0f), h1 = fmaxf(h.y, 0.0f);
+              z01 = ffma2(make_float2(h0, h0), make_float2(hc.w2[co * 4 + 0], hc.w2[co * 4 + 1]), z01);
+              z23 = ffma2(make_float2(h0, h0), make_float2(hc.w2[co * 4 + 2], hc.w2[co * 4 + 3]), z23);
+              z01 = ffma2(make_float2(h1, h1), make_float2(hc.w2[co * 4 + 4], hc.w2[co * 4 + 5]), z01);
+              z23 = ffma2(make_float2(h1, h1), make_float2(hc.w2[co * 4 + 6], hc.w2[co * 4 + 7]), z23);
             }
           }
+          const float z[4] = {z01.x, z01.y, z23.x, z23.y};
           // q = i'*2 + j' of conv-transpose 2: output (4y + 2i + i', 4x + 2j + j')
 #pragma unroll
           for (int q = 0; q < 4; ++q) o[q >> 1][2 * tj + (q & 1)] = 1.0f / (1.0f + expf(-z[q]));

@@ -34,7 +34,7 @@ struct ConvTcParams {
 // epilogue reads them as immediate constant operands, no shared-memory traffic)
 struct HeadConsts {
   float scale[64], shift[64];  // bin_bn2 folded with the conv-transpose-1 bias
-  float w2[256];               // conv-transpose-2 weights [q][co]
+  float w2[256];               // conv-transpose-2 weights [co][q] (q = 2*i' + j' fastest)
 };
 
 int make_act_tensor_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int stride);

@@ -305,7 +305,8 @@ static int det_build(ocrb_det *d, const HostWeights &hw) {
     OCRB_TRY(upload(d->tr2_w, w2t));
     d->tr2_bias = (*b2)[0];
     for (int i = 0; i < 64; ++i) { d->head_c.scale[i] = sc[i]; d->head_c.shift[i] = sh[i]; }
-    for (int i = 0; i < 256; ++i) d->head_c.w2[i] = w2t[i];
+    for (int q = 0; q < 4; ++q)
+      for (int co = 0; co < 64; ++co) d->head_c.w2[co * 4 + q] = w2t[q * 64 + co];
   }
   OCRB_TRY(d->err.reserve(4));
   OCRB_CUDA(cudaMemset(d->err.p, 0, 4));
