@@ -222,6 +222,7 @@ struct ocrb_det {
   int mode = OCRB_MODE_BF16;
   // stem
   DevBuf stem_w, stem_scale, stem_shift;
+  float stem_scale_h[64], stem_shift_h[64];  // host copies (kernel-parameter constants of stem_tc)
   // body: index by name
   std::map<std::string, DevConv> conv;
   // head
@@ -254,6 +255,8 @@ static int det_build(ocrb_det *d, const HostWeights &hw) {
     for (int co = 0; co < 64; ++co)
       for (int tp = 0; tp < 49; ++tp) wt[tp * 64 + co] = (*w)[co * 49 + tp];
     OCRB_TRY(fold_bn(hw, "bn1", 64, nullptr, sc, sh));
+    memcpy(d->stem_scale_h, sc.data(), sizeof(d->stem_scale_h));
+    memcpy(d->stem_shift_h, sh.data(), sizeof(d->stem_shift_h));
     OCRB_TRY(upload(d->stem_w, wt));
     OCRB_TRY(upload(d->stem_scale, sc));
     OCRB_TRY(upload(d->stem_shift, sh));
@@ -466,8 +469,8 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
   // stem
   static const bool stem_cuda_cores = getenv("OCRB_STEM") && strcmp(getenv("OCRB_STEM"), "cuda") == 0;
   if (!stem_cuda_cores) {
-    OCRB_TRY(launch_stem_tc(ctx, img, sizeof(TIn) == 1, B, H, W, d->stem_w.as<float>(), d->stem_scale.as<float>(),
-                            d->stem_shift.as<float>(), x0, d->err.as<int>()));
+    OCRB_TRY(launch_stem_tc(ctx, img, sizeof(TIn) == 1, B, H, W, d->stem_w.as<float>(), d->stem_scale_h, d->stem_shift_h, x0,
+                            d->err.as<int>()));
   } else {
     const int tiles = (int)(cdiv(W4, ST_PW) * cdiv(H4, ST_PH)) * B;
     stem_fused_bf16_kernel<TIn><<<tiles, ST_THREADS, 0, ctx->stream>>>(img, B, H, W, d->stem_w.as<float>(), d->stem_scale.as<float>(),

@@ -40,17 +40,19 @@ __device__ __forceinline__ void cp_async_4_zfill(uint32_t dst, const void *src, 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// folded bn1 scale / shift, passed by value: after unrolling they are constant-bank operands
+struct StemConsts { float scale[64], shift[64]; };
+
 template <class TIn>
 __global__ void __launch_bounds__(SK_THREADS, 2)
 stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__restrict__ w /*[49][64]*/,
-               const float *__restrict__ scale, const float *__restrict__ shift, __nv_bfloat16 *__restrict__ out, int *err) {
+               const __grid_constant__ StemConsts sc, __nv_bfloat16 *__restrict__ out, int *err) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sA = smem;
   uint8_t *sB = smem + SK_OFF_B;
   __nv_bfloat16 *s_patch = reinterpret_cast<__nv_bfloat16 *>(smem + SK_OFF_PATCH);
   uint8_t *s_raw = smem + SK_OFF_RAW;
-  __shared__ __align__(16) float s_scale[64], s_shift[64];
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SK_OFF_MISC);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
   const uint32_t sA_u32 = smem_u32(sA), patch_u32 = smem_u32(s_patch), raw_u32 = smem_u32(s_raw);
@@ -76,7 +78,6 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
     }
     *reinterpret_cast<uint4 *>(sB + co * 128 + ((j ^ (co & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
-  if (tid < 64) { s_scale[tid] = scale[tid]; s_shift[tid] = shift[tid]; }
   if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(tmem_slot, 256);
   fence_proxy_async();
@@ -187,14 +188,14 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 const int c = half * 32 + j4 * 8;
-                const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + c), sc1 = *reinterpret_cast<const float4 *>(s_scale + c + 4);
-                const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + c), sh1 = *reinterpret_cast<const float4 *>(s_shift + c + 4);
-                const float *x = v + j4 * 8;
-                sts_16(row + (((half * 4 + j4) ^ (m & 7)) << 4),
-                       make_uint4(pack_bf16(fmaxf(fmaf(x[0], sc0.x, sh0.x), 0.f), fmaxf(fmaf(x[1], sc0.y, sh0.y), 0.f)),
-                                  pack_bf16(fmaxf(fmaf(x[2], sc0.z, sh0.z), 0.f), fmaxf(fmaf(x[3], sc0.w, sh0.w), 0.f)),
-                                  pack_bf16(fmaxf(fmaf(x[4], sc1.x, sh1.x), 0.f), fmaxf(fmaf(x[5], sc1.y, sh1.y), 0.f)),
-                                  pack_bf16(fmaxf(fmaf(x[6], sc1.z, sh1.z), 0.f), fmaxf(fmaf(x[7], sc1.w, sh1.w), 0.f))));
+                uint32_t pk[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  const float2 y = ffma2(make_float2(v[j4 * 8 + 2 * h], v[j4 * 8 + 2 * h + 1]), make_float2(sc.scale[c + 2 * h], sc.scale[c + 2 * h + 1]),
+                                         make_float2(sc.shift[c + 2 * h], sc.shift[c + 2 * h + 1]));
+                  pk[h] = pack_bf16(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f));
+                }
+                sts_16(row + (((half * 4 + j4) ^ (m & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
               }
             } else {
               // outside the conv grid = max-pool padding (-inf): a large negative finite bf16 (0xFF7F)
@@ -257,8 +258,11 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
   }
 }
 
-int launch_stem_tc(ocrb_ctx *ctx, const void *in, int is_u8, int B, int H, int W, const float *w, const float *scale,
-                   const float *shift, __nv_bfloat16 *out, int *err) {
+int launch_stem_tc(ocrb_ctx *ctx, const void *in, int is_u8, int B, int H, int W, const float *w, const float *scale_host,
+                   const float *shift_host, __nv_bfloat16 *out, int *err) {
+  StemConsts sc;
+  memcpy(sc.scale, scale_host, sizeof(sc.scale));
+  memcpy(sc.shift, shift_host, sizeof(sc.shift));
   static bool attr_set[16] = {false};
   if (!attr_set[ctx->device & 15]) {
     OCRB_CUDA(cudaFuncSetAttribute(stem_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
@@ -269,9 +273,9 @@ int launch_stem_tc(ocrb_ctx *ctx, const void *in, int is_u8, int B, int H, int W
   const int64_t units = cdiv(Wp, SK_PW) * cdiv(Hp, SK_PH) * B;
   const int grid = (int)(units < 2 * ctx->sm_count ? units : 2 * ctx->sm_count);
   if (is_u8)
-    stem_tc_kernel<uint8_t><<<grid, SK_THREADS, SK_SMEM, ctx->stream>>>((const uint8_t *)in, B, H, W, w, scale, shift, out, err);
+    stem_tc_kernel<uint8_t><<<grid, SK_THREADS, SK_SMEM, ctx->stream>>>((const uint8_t *)in, B, H, W, w, sc, out, err);
   else
-    stem_tc_kernel<float><<<grid, SK_THREADS, SK_SMEM, ctx->stream>>>((const float *)in, B, H, W, w, scale, shift, out, err);
+    stem_tc_kernel<float><<<grid, SK_THREADS, SK_SMEM, ctx->stream>>>((const float *)in, B, H, W, w, sc, out, err);
   return check_launch(ctx, "tc:stem");
 }
 
