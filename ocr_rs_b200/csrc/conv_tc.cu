@@ -29,30 +29,30 @@ namespace ocrb {
 constexpr int TC_TW = 25, TC_TH = 5, TC_ROWS = TC_TW * TC_TH;  // 125 valid rows of 128
 constexpr int TC_A_BYTES = 128 * 128;                           // A stage: 128 rows x 64 bf16
 constexpr int TC_A_TX = TC_ROWS * 128;                          // bytes TMA actually writes
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;
-constexpr int TC_STG_BYTES = TC_EPI_WARPS * 2048;               // per-warp epilogue staging
+// EW epilogue warps (8, or 16 for the store-bound FPN laterals): 4 TMEM lane quarters x EW/4 column parts
 
 // ---------------------------------------------------------------------------------------
 // shared-memory carve-up (dynamic part; scale/shift/w2 are static __shared__)
 // ---------------------------------------------------------------------------------------
-template <int N_TILE, int STAGES, int RING>
+template <int N_TILE, int STAGES, int RING, int EW>
 struct TcSmem {
   static constexpr int B_BYTES = N_TILE * 128;
   static constexpr int OFF_B = STAGES * TC_A_BYTES;
   static constexpr int OFF_STG = OFF_B + STAGES * B_BYTES;
-  static constexpr int OFF_RING = OFF_STG + TC_STG_BYTES;         // RING x 2 KB per epilogue warp (addend prefetch)
-  static constexpr int OFF_BAR = OFF_RING + TC_EPI_WARPS * RING * 2048;  // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  static constexpr int OFF_RING = OFF_STG + EW * 2048;            // per-warp 2 KB staging, then RING x 2 KB per warp (addend prefetch)
+  static constexpr int OFF_BAR = OFF_RING + EW * RING * 2048;  // full[STAGES], empty[STAGES], tfull[2], tempty[2]
   static constexpr int OFF_TMEM = OFF_BAR + (2 * STAGES + 4) * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;                 // slack for manual 1024 B alignment
 };
 
-template <int N_TILE, int STAGES, int EPI, int RING>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int N_TILE, int STAGES, int EPI, int RING, int EW>
+__global__ void __launch_bounds__((2 + EW) * 32, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p,
                const __grid_constant__ HeadConsts hc) {
-  using L = TcSmem<N_TILE, STAGES, RING>;
+  using L = TcSmem<N_TILE, STAGES, RING, EW>;
+  constexpr int TC_THREADS = (2 + EW) * 32;
+  constexpr int PARTS = EW / 4;  // column parts
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(16) float s_scale[512], s_shift[512];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -87,7 +87,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EW); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -151,7 +151,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================= epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = ew >> 2;
+    const int half = ew >> 2;  // column part of this warp (0 .. PARTS-1)
     int acc = 0;
     uint32_t acc_phase = 0;
     EpiParams e;
@@ -166,7 +166,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
       const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
       if (EPI == EPI_STD) {
-        constexpr int NH = N_TILE / 2, NBLK = NH / 32;
+        constexpr int NH = N_TILE / PARTS, NBLK = NH / 32;
         const int n0 = n_tile * N_TILE + half * NH;
         auto rows_of_tile = [&](int tl, EpiRows &rw) {
           const int nt = tl / num_m_tiles, mt = tl - nt * num_m_tiles;
@@ -231,6 +231,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else {
+        static_assert(EPI != EPI_HEAD || PARTS == 2, "head epilogue splits the four taps over two warp halves");
         // DB head tail: columns n = tap(i,j)*64 + co of conv-transpose 1; per tap BN+ReLU then
         // the 64 -> 4 dot products of conv-transpose 2, sigmoid; each warp half takes two taps
         // (= two rows of the pixel's 4x4 output block).
@@ -362,18 +363,18 @@ int make_weight_tensor_map(CUtensorMap *map, const void *base, int Cout, int Kto
   return OCRB_OK;
 }
 
-template <int N_TILE, int STAGES, int EPI, int RING>
+template <int N_TILE, int STAGES, int EPI, int RING, int EW>
 static int launch_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvTcParams &p, int num_tiles, const char *tag,
                       const HeadConsts &hc) {
-  using L = TcSmem<N_TILE, STAGES, RING>;
+  using L = TcSmem<N_TILE, STAGES, RING, EW>;
   static bool attr_set[16] = {false};
-  auto kern = conv_tc_kernel<N_TILE, STAGES, EPI, RING>;
+  auto kern = conv_tc_kernel<N_TILE, STAGES, EPI, RING, EW>;
   if (!attr_set[ctx->device & 15]) {
     OCRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set[ctx->device & 15] = true;
   }
   int grid = num_tiles < ctx->sm_count ? num_tiles : ctx->sm_count;
-  kern<<<grid, TC_THREADS, L::DYN_BYTES, ctx->stream>>>(tmA, tmB, p, hc);
+  kern<<<grid, (2 + EW) * 32, L::DYN_BYTES, ctx->stream>>>(tmA, tmB, p, hc);
   return check_launch(ctx, tag);
 }
 
@@ -388,16 +389,20 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
   const int num_tiles = p.tiles_x * p.tiles_y * p.B * p.num_n_tiles;
   if (epi == EPI_HEAD) {
     if (n_tile != 256) { set_error("conv_tc head needs N tile 256"); return OCRB_ERR_INVALID; }
-    return launch_one<256, 4, EPI_HEAD, 0>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+    return launch_one<256, 4, EPI_HEAD, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc);
   }
   switch (n_tile) {
-    case 64: return launch_one<64, 6, EPI_STD, 0>(ctx, tmA, tmB, p, num_tiles, tag, hc);
-    case 128: return launch_one<128, 5, EPI_STD, 0>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+    case 64: return launch_one<64, 6, EPI_STD, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+    case 128: return launch_one<128, 5, EPI_STD, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc);
     case 256:
       // FPN laterals (second output = y + up2(addend)): 1x1 convs with few K blocks, so two
       // operand stages suffice and the shared memory goes to the addend prefetch ring instead
-      if (p.sum_out) return launch_one<256, 2, EPI_STD, 4>(ctx, tmA, tmB, p, num_tiles, tag, hc);
-      return launch_one<256, 4, EPI_STD, 0>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+      if (p.sum_out) {
+        static const bool ew16 = getenv("OCRB_LATERAL_EW") && atoi(getenv("OCRB_LATERAL_EW")) == 16;  // tuning knob: measured slower (in2 11.4 vs 10.0 ms / 1024 images)
+        return ew16 ? launch_one<256, 2, EPI_STD, 2, 16>(ctx, tmA, tmB, p, num_tiles, tag, hc)
+                    : launch_one<256, 2, EPI_STD, 4, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+      }
+      return launch_one<256, 4, EPI_STD, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc);
   }
   set_error("conv_tc: unsupported N tile %d", n_tile);
   return OCRB_ERR_INVALID;
