@@ -372,8 +372,17 @@ __device__ int union_outer(const ipt *Qin, int m_in, ipt *Q, ipt *out, int cap) 
   for (;;) {
     if (++guard > max_iter) return 0;
     rat t_best = {1, 1};
+    // bounding box of the current segment: a segment whose (closed) box misses it cannot hit it
+    // in any of the three ways seg_hit distinguishes — an exact, cheap reject of most pairs
+    const ipt cb0 = Q[cur], cb1 = Q[cur + 1 == m ? 0 : cur + 1];
+    const int cminx = cb0.x < cb1.x ? cb0.x : cb1.x, cmaxx = cb0.x < cb1.x ? cb1.x : cb0.x;
+    const int cminy = cb0.y < cb1.y ? cb0.y : cb1.y, cmaxy = cb0.y < cb1.y ? cb1.y : cb0.y;
+    auto box_miss = [&](int j) {
+      const ipt b0 = Q[j], b1 = Q[j + 1 == m ? 0 : j + 1];
+      return (b0.x < cminx && b1.x < cminx) || (b0.x > cmaxx && b1.x > cmaxx) || (b0.y < cminy && b1.y < cminy) || (b0.y > cmaxy && b1.y > cmaxy);
+    };
     for (int j = 0; j < m; ++j) {
-      if (j == cur) continue;
+      if (j == cur || box_miss(j)) continue;
       for (int which = 0; which < 3; ++which) {
         rat t, s;
         if (!seg_hit(Q, m, cur, j, which, &t, &s)) continue;
@@ -392,7 +401,7 @@ __device__ int union_outer(const ipt *Qin, int m_in, ipt *Q, ipt *out, int cap) 
     if (t_best.num == t_best.den) { node_is_vertex = true; node_v = c1; }
     else { nxt = cur; nxt_s = t_best; bdx = ux; bdy = uy; }
     for (int j = 0; j < m; ++j) {
-      if (j == cur) continue;
+      if (j == cur || box_miss(j)) continue;
       for (int which = 0; which < 3; ++which) {
         rat t, s;
         if (!seg_hit(Q, m, cur, j, which, &t, &s)) continue;
