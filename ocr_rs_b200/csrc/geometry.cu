@@ -344,12 +344,19 @@ __device__ __forceinline__ bool ccw_before(long long rx, long long ry, long long
 
 // outer boundary of {winding > 0} of the closed path Qin (see oracle/postproc_oracle.c for the
 // derivation of this restatement of Clipper's union).  Q: scratch for the de-duplicated path.
-__device__ int union_outer(const ipt *Qin, int m_in, ipt *Q, ipt *out, int cap) {
+__device__ int union_outer(const ipt *Qin, int m_in, ipt *Q, ipt *out, int cap, ipt *fast, int fast_cap) {
   int m = 0;
   for (int i = 0; i < m_in; ++i)
     if (m == 0 || Q[m - 1].x != Qin[i].x || Q[m - 1].y != Qin[i].y) Q[m++] = Qin[i];
   while (m > 1 && Q[0].x == Q[m - 1].x && Q[0].y == Q[m - 1].y) m--;
   if (m < 3) return 0;
+  // the walk below reads the vertex list thousands of times: keep it in the caller's fast
+  // (shared-memory) scratch when it fits
+  ipt *Qg = Q;
+  if (fast && m <= fast_cap) {
+    for (int i = 0; i < m; ++i) fast[i] = Q[i];
+    Q = fast;
+  }
   int sv = 0;
   for (int i = 1; i < m; ++i)
     if (Q[i].y < Q[sv].y || (Q[i].y == Q[sv].y && Q[i].x < Q[sv].x)) sv = i;
@@ -443,8 +450,8 @@ __device__ int union_outer(const ipt *Qin, int m_in, ipt *Q, ipt *out, int cap) 
   for (int i = 1; i < n_out; ++i)
     if (out[i].y < out[top].y || (out[i].y == out[top].y && out[i].x > out[top].x)) top = i;
   int st = (top + 1) % n_out;
-  for (int i = 0; i < n_out; ++i) Q[i] = out[(st + i) % n_out];  // n_out <= cap <= capacity of Q region? see slab layout
-  for (int i = 0; i < n_out; ++i) out[i] = Q[i];
+  for (int i = 0; i < n_out; ++i) Qg[i] = out[(st + i) % n_out];  // n_out <= cap = capacity of the Q slab region
+  for (int i = 0; i < n_out; ++i) out[i] = Qg[i];
   return n_out;
 }
 
@@ -580,6 +587,7 @@ __global__ void unclip_slab_size_kernel(const int *__restrict__ cand_contour, co
 // status: 0 dropped by score, 1 kept, 2 dropped (empty offset, reference panics, D11),
 //         3 dropped by min_size
 constexpr int UNCLIP_THREADS = 64;
+constexpr int UNCLIP_FAST_PTS = 256;  // 2 KB of shared memory per active lane
 
 __global__ void __launch_bounds__(UNCLIP_THREADS) unclip_kernel(const int *__restrict__ cand_contour, const int64_t *__restrict__ chain_off,
                               const ushort2 *__restrict__ dp_pts, const int *__restrict__ dp_count, int n_cand,
@@ -617,7 +625,8 @@ __global__ void __launch_bounds__(UNCLIP_THREADS) unclip_kernel(const int *__res
   double area = fabs(twice / 2.0);
   double distance = area * factor / perim;
   int m = clipper_offset_raw(src, n, distance, raw);
-  int ne = m >= 3 ? union_outer(raw, m, Q, out, cap) : 0;
+  __shared__ ipt s_fast[(UNCLIP_THREADS / 32) * SPARSE_LANES][UNCLIP_FAST_PTS];
+  int ne = m >= 3 ? union_outer(raw, m, Q, out, cap, s_fast[(threadIdx.x >> 5) * SPARSE_LANES + (threadIdx.x & 31)], UNCLIP_FAST_PTS) : 0;
   if (ne == 0) { status[i] = 2; return; }
   ipt box[4];
   double sside = min_area_bounding_box(out, ne, work, hull, box);
