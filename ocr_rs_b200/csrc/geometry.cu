@@ -6,6 +6,7 @@
 // Compiled with -fmad=false: every f32/f64 expression must round like the reference's
 // scalar code.  Integer predicates are exact (int64 / __int128).
 #include "common.cuh"
+#include "dd_math.cuh"
 
 namespace ocrb {
 
@@ -517,8 +518,12 @@ __device__ double min_area_bounding_box(const ipt *pts, int n, dpt *work, dpt *h
     dpt res[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     for (int e = 0; e + 1 < h; ++e) {
       double ex = hull[e + 1].x - hull[e].x, ey = hull[e + 1].y - hull[e].y;
-      double angle = fabs(fmod(atan2(ey, ex) + PI, PI / 2.));
-      double sn = sin(angle), cs = cos(angle);
+      // correctly rounded atan2 / sin / cos (dd_math.cuh): the reference's libm (glibc) rounds
+      // correctly in ~99.9 % of calls, CUDA's libm is 1-2 ulp off far more often, and one ulp
+      // flips the outward floor/ceil below whenever a rotated coordinate is an exact integer
+      double angle = fabs(fmod(ddm::cr_atan2(ey, ex) + PI, PI / 2.));
+      double sn, cs;
+      ddm::cr_sincos(angle, &sn, &cs);
       double min_x = 1.7976931348623157e308, max_x = -1.7976931348623157e308;
       double min_y = 1.7976931348623157e308, max_y = -1.7976931348623157e308;
       for (int i = 0; i < h; ++i) {

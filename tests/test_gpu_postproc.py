@@ -122,11 +122,13 @@ def test_expand_polygon_vs_oracle(api, gt55):
             n_some += 1
             be, se = pp.min_area_bounding_box(exp)
             bg, sg = metrics.get_min_area_bounding_box(exp)
-            # f64 trig (atan2/sin/cos) comes from CUDA's libm here and glibc in the oracle: an ulp of
-            # difference flips the outward floor/ceil when a rotated coordinate is an exact integer
+            # f64 trig: the device evaluates atan2/sin/cos correctly rounded (csrc/dd_math.cuh), glibc
+            # (the oracle, like the reference's libm) misrounds ~0.1 % of calls by one ulp, which can
+            # flip the outward floor/ceil when a rotated coordinate is an exact integer
             assert np.abs(bg - be).max() <= 1 and abs(sg - se) <= 1.5
             n_exact += int(bg.tolist() == be.tolist() and abs(sg - se) <= 1e-12 * max(1.0, se))
-    assert n_some > 20 and n_exact >= 0.9 * n_some, (n_some, n_exact)
+    assert n_some > 20 and n_exact >= 0.98 * n_some, (n_some, n_exact)
+    print(f"min-area-rect hook: {n_exact}/{n_some} boxes bit-identical to the oracle")
     assert polygon.expand_polygon([(0, 0), (10, 0), (20, 0), (10, 0)], 2.0) is None
 
 
