@@ -123,8 +123,12 @@ extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uin
     float *prob = ws->prob[g & 1].as<float>();
     uint8_t *bitmap = ws->bitmap[g & 1].as<uint8_t>();
     int rc = OCRB_OK;
-    for (int c0 = 0; c0 < gn && rc == OCRB_OK; c0 += chunk, ++chunk_no) {
-      const int bc = gn - c0 < chunk ? gn - c0 : chunk;
+    for (int c0 = 0, bc = 0; c0 < gn && rc == OCRB_OK; c0 += bc, ++chunk_no) {
+      bc = gn - c0 < chunk ? gn - c0 : chunk;
+      // host images: the very first copy of a call is exposed (nothing to overlap it with), so
+      // ramp up — 16 images first, the rest of the chunk while those are in the detector
+      if (!img_dev && chunk_no == 0 && bc > 32) bc = 16;
+      else if (!img_dev && chunk_no == 1 && c0 == 16 && chunk > 16 && gn - c0 > chunk - 16) bc = chunk - 16;
       const uint8_t *src = images + (size_t)(g0 + c0) * HW;
       const int slot = (int)(chunk_no & 1);
       if (!img_dev) {

@@ -123,3 +123,16 @@ def test_config3_batch16(env):
         worst = max(worst, float(np.abs(got[b0:b0 + 4] - ref).max()))
     print(f"config3 bf16 batch 16: max|dp| = {worst:.3e}")
     assert worst <= TOL["bf16"]
+
+
+def test_large_non_square_map(env):
+    """A map larger than the benchmark's (1216 x 1600, batch 2): tile / tensor-map arithmetic beyond 800x800."""
+    synth, resnet18, mo = env
+    B, H, W = 2, 1216, 1600
+    w = synth.make_detector_weights(4, "tch")
+    x = synth.make_noise_images(B, H, W, seed=9)
+    got = resnet18(w, "bf16").forward_t(x.reshape(B, 1, H, W))
+    ref = mo.detector_forward(w, x.reshape(B, 1, H, W).astype(np.float32)).numpy()
+    err = np.abs(got - ref).max()
+    print(f"1216x1600 bf16: max|dp| = {err:.3e}")
+    assert err <= TOL["bf16"]
