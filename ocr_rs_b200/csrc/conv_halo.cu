@@ -41,7 +41,8 @@ struct HaloGeom {
 
 template <int N_TILE, int G, int CG>
 __global__ void __launch_bounds__((1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS) * 32, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p, const HaloGeom g) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                 const ConvTcParams p, const HaloGeom g) {
   // CG = 2: a CTA PAIR works as one unit (tcgen05 cta_group::2).  Each CTA owns a spatial tile
   // (its A operand, its accumulators) and HALF of every weight tile; the leader CTA issues
   // UMMAs of M = 256 that read both halves.  Per CTA that halves the shared-memory reads and
@@ -84,6 +85,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.ds_chunks) tma_prefetch_desc(&tmD);
     // full barriers live in the leader: one producer arrival (+ its bytes) per CTA of the pair
     for (int s = 0; s < g.a_stages; ++s) { mbar_init(&a_full[s], CG); mbar_init(&a_empty[s], MW); }
     for (int s = 0; s < g.b_stages; ++s) { mbar_init(&b_full[s], CG); mbar_init(&b_empty[s], MW); }
@@ -139,6 +141,36 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (++bs == g.b_stages) { bs = 0; bph ^= 1; }
         }
       }
+      // fused downsample input: TH x PW positions of the stride-2 sampled block input, 1 "tap"
+      for (int dk = 0; dk < p.ds_chunks; ++dk) {
+        mbar_wait(&a_empty[as], aph ^ 1, p.err, 17);
+        if (elect_one()) {
+          const int ds_bytes = g.TH * g.PW * 128;
+          if (CG == 2) {
+            const uint32_t bar = mapa_u32(&a_full[as], 0);
+            mbar_expect_tx_cluster(bar, ds_bytes);
+            tma_load_4d_2sm(sA + as * g.a_stage_bytes, &tmD, bar, dk * 64, 2 * tx * g.TW, 2 * ty * g.TH, b);
+          } else {
+            mbar_expect_tx(&a_full[as], ds_bytes);
+            tma_load_4d(sA + as * g.a_stage_bytes, &tmD, &a_full[as], dk * 64, 2 * tx * g.TW, 2 * ty * g.TH, b);
+          }
+        }
+        __syncwarp();
+        if (++as == g.a_stages) { as = 0; aph ^= 1; }
+        mbar_wait(&b_empty[bs], bph ^ 1, p.err, 18);
+        if (elect_one()) {
+          if (CG == 2) {
+            const uint32_t bar = mapa_u32(&b_full[bs], 0);
+            mbar_expect_tx_cluster(bar, B_BYTES);
+            tma_load_2d_2sm(sB + bs * B_BYTES, &tmB, bar, (9 * chunks + dk) * 64, n_tile * N_TILE + (int)rank * NB);
+          } else {
+            mbar_expect_tx(&b_full[bs], B_BYTES);
+            tma_load_2d(sB + bs * B_BYTES, &tmB, &b_full[bs], (9 * chunks + dk) * 64, n_tile * N_TILE);
+          }
+        }
+        __syncwarp();
+        if (++bs == g.b_stages) { bs = 0; bph ^= 1; }
+      }
     }
   } else if (warp <= MW) {
     // ================= MMA issuers (leader CTA only) =================
@@ -179,19 +211,48 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_commit_2sm(&b_empty[bs]);
                 if (tap == 8) {
                   umma_commit_2sm(&a_empty[as]);
-                  if (ck == chunks - 1) umma_commit_2sm(&tfull[acc]);
+                  if (ck == chunks - 1 && p.ds_chunks == 0) umma_commit_2sm(&tfull[acc]);
                 }
               } else {
                 umma_commit(&b_empty[bs]);
                 if (tap == 8) {
                   umma_commit(&a_empty[as]);
-                  if (ck == chunks - 1) umma_commit(&tfull[acc]);
+                  if (ck == chunks - 1 && p.ds_chunks == 0) umma_commit(&tfull[acc]);
                 }
               }
             }
             __syncwarp();
             if (++bs == g.b_stages) { bs = 0; bph ^= 1; }
           }
+          if (++as == g.a_stages) { as = 0; aph ^= 1; }
+        }
+        for (int dk = 0; dk < p.ds_chunks; ++dk) {  // fused 1x1 stride-2 downsample: no tap offset
+          mbar_wait(&a_full[as], aph, p.err, 19);
+          mbar_wait(&b_full[bs], bph, p.err, 20);
+          tc_fence_after();
+          const uint64_t a0 = make_smem_desc(sA + as * g.a_stage_bytes) + (uint64_t)(g0 * 128 * 8);
+          const uint64_t bdesc = make_smem_desc(sB + bs * B_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int gi = 0; gi < GW; ++gi) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (CG == 2) umma_bf16_2sm(d_base + (uint32_t)(gi * N_TILE), a0 + (uint64_t)(gi * 128 * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                else umma_bf16(d_base + (uint32_t)(gi * N_TILE), a0 + (uint64_t)(gi * 128 * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+              }
+            }
+            if (CG == 2) {
+              umma_commit_2sm(&b_empty[bs]);
+              umma_commit_2sm(&a_empty[as]);
+              if (dk == p.ds_chunks - 1) umma_commit_2sm(&tfull[acc]);
+            } else {
+              umma_commit(&b_empty[bs]);
+              umma_commit(&a_empty[as]);
+              if (dk == p.ds_chunks - 1) umma_commit(&tfull[acc]);
+            }
+          }
+          __syncwarp();
+          if (++bs == g.b_stages) { bs = 0; bph ^= 1; }
           if (++as == g.a_stages) { as = 0; aph ^= 1; }
         }
         acc ^= 1;
@@ -327,8 +388,8 @@ int make_act_tensor_map_box(CUtensorMap *map, const void *base, int B, int H, in
 
 
 template <int N_TILE, int G, int CG>
-static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvTcParams &p, const HaloGeom &g,
-                           int num_units, const char *tag) {
+static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmD, const ConvTcParams &p,
+                           const HaloGeom &g, int num_units, const char *tag) {
   static bool attr_set[16] = {false};
   auto kern = conv_halo_kernel<N_TILE, G, CG>;
   if (!attr_set[ctx->device & 15]) {
@@ -349,7 +410,7 @@ static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensor
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  OCRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p, g));
+  OCRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, p, g));
   return check_launch(ctx, tag);
 }
 
@@ -366,7 +427,18 @@ int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, i
 int halo_weight_box_rows(int n_tile) { return n_tile / halo_cg(); }
 
 // 3x3 / stride 1 / pad 1 only; n_tile in {64 (G = 4), 128 (G = 2)}
-int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, const char *tag) {
+// the fused downsample input [B][H][W][C] sampled at stride 2: box of PW x TH positions (pitch PW like the main tile)
+int make_act_tensor_map_strided_box(CUtensorMap *map, const void *base, int B, int H, int W, int C, int box_w, int box_h, int stride);
+int make_halo_ds_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int Ho, int Wo, int n_tile, int G) {
+  HaloGeom g;
+  OCRB_TRY(halo_geometry(Ho, Wo, n_tile / halo_cg(), G, &g));
+  return make_act_tensor_map_strided_box(map, base, B, H, W, C, g.PW, g.TH, 2);
+}
+
+int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, const char *tag,
+                     const CUtensorMap *tmDp) {
+  const CUtensorMap &tmD = tmDp ? *tmDp : tmA;
+  if ((p.ds_chunks != 0) != (tmDp != nullptr)) { set_error("conv_halo: downsample chunks without a tensor map (or vice versa)"); return OCRB_ERR_INVALID; }
   if (p.R != 3 || p.S != 3 || p.stride != 1 || p.pad != 1 || p.sum_out || !p.out) { set_error("conv_halo: unsupported convolution"); return OCRB_ERR_INVALID; }
   if (p.Cout % n_tile != 0 || p.Cout > 512) { set_error("conv_halo: Cout %d vs N tile %d", p.Cout, n_tile); return OCRB_ERR_INVALID; }
   const int G = n_tile == 64 ? 4 : 2, CG = halo_cg();
@@ -376,8 +448,8 @@ int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &t
   p.tiles_y = (int)cdiv(p.Ho, g.TH);
   p.num_n_tiles = p.Cout / n_tile;
   const int num_units = (int)cdiv((int64_t)p.tiles_x * p.tiles_y * p.B, CG) * p.num_n_tiles;
-  if (n_tile == 64) return CG == 2 ? launch_halo_one<64, 4, 2>(ctx, tmA, tmB, p, g, num_units, tag) : launch_halo_one<64, 4, 1>(ctx, tmA, tmB, p, g, num_units, tag);
-  if (n_tile == 128) return CG == 2 ? launch_halo_one<128, 2, 2>(ctx, tmA, tmB, p, g, num_units, tag) : launch_halo_one<128, 2, 1>(ctx, tmA, tmB, p, g, num_units, tag);
+  if (n_tile == 64) return CG == 2 ? launch_halo_one<64, 4, 2>(ctx, tmA, tmB, tmD, p, g, num_units, tag) : launch_halo_one<64, 4, 1>(ctx, tmA, tmB, tmD, p, g, num_units, tag);
+  if (n_tile == 128) return CG == 2 ? launch_halo_one<128, 2, 2>(ctx, tmA, tmB, tmD, p, g, num_units, tag) : launch_halo_one<128, 2, 1>(ctx, tmA, tmB, tmD, p, g, num_units, tag);
   set_error("conv_halo: unsupported N tile %d", n_tile);
   return OCRB_ERR_INVALID;
 }

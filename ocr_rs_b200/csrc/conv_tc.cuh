@@ -13,6 +13,10 @@ struct ConvTcParams {
   // problem geometry (output side); tiles_x/tiles_y/num_n_tiles are filled by the launcher
   int B = 0, Ho = 0, Wo = 0, Cout = 0;
   int R = 1, S = 1, cin_chunks = 1, stride = 1, pad = 0;
+  // conv_halo only: a fused 1x1 stride-2 side input (ResNet downsample, model.rs:30-38): ds_chunks extra
+  // K blocks of 64 channels read from a second tensor map, weights appended after the 9 taps
+  int ds_chunks = 0;
+  const __nv_bfloat16 *ds_src = nullptr;    // host-side only: base of that side input
   int tiles_x = 0, tiles_y = 0, num_n_tiles = 0;
   // standard epilogue: y = acc * scale[c] + shift[c] (+ residual) (ReLU)
   const float *scale = nullptr, *shift = nullptr;
@@ -45,6 +49,8 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
 // conv_halo.cu: 3x3 stride-1 convolutions with the halo'd input tile resident in shared memory
 int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G);
 int halo_weight_box_rows(int n_tile);  // rows of the weight TMA box (half the N tile in CTA-pair mode)
-int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, const char *tag);
+int make_halo_ds_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int Ho, int Wo, int n_tile, int G);
+int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, const char *tag,
+                     const CUtensorMap *tmD = nullptr);
 
 }  // namespace ocrb

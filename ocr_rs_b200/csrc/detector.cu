@@ -143,6 +143,7 @@ struct ConvSpec {
 struct DevConv {
   int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
   bool has_bn = false;
+  int ds_cin = 0;  // > 0: w16 carries a fused 1x1 stride-2 downsample of ds_cin channels after the 9 taps
   DevBuf w32;    // fp32 [k*k][cin][cout]
   DevBuf w16;    // bf16 [cout][k*k*cin]
   DevBuf scale, shift;
@@ -213,6 +214,33 @@ static int prep_conv(const HostWeights &hw, const ConvSpec &sp, bool want16, Dev
   return OCRB_OK;
 }
 
+// ResNet downsample (model.rs:30-38) folded into the block's conv2:
+//   relu(bn2(conv2(t)) + bn_ds(conv_ds(x))) = relu(s2 * (W2*t + (s_ds/s2) W_ds*x) + t2 + t_ds)
+// so the 1x1 stride-2 convolution becomes cin_ds extra K columns of conv2's weight matrix
+// (pre-scaled per output channel in fp32, then rounded to bf16) and its shift joins conv2's.
+static int prep_fused_downsample(const HostWeights &hw, const std::string &p, int cin_ds, int c, DevConv &dc) {
+  const auto *w2 = hw.get(p + ".conv2.weight"), *wd = hw.get(p + ".downsample.0.weight");
+  OCRB_REQUIRE(w2 && wd, "missing conv2 / downsample weights of %s", p.c_str());
+  std::vector<float> s2, t2, sd, td;
+  OCRB_TRY(fold_bn(hw, p + ".bn2", c, nullptr, s2, t2));
+  OCRB_TRY(fold_bn(hw, p + ".downsample.1", c, nullptr, sd, td));
+  for (int co = 0; co < c; ++co)
+    if (!(fabsf(s2[co]) > 1e-20f)) return OCRB_OK;  // bn2 scale of 0: keep the separate downsample launch
+  const int ktot = 9 * c + cin_ds;
+  std::vector<uint16_t> w16((size_t)c * ktot);
+  for (int co = 0; co < c; ++co) {
+    for (int tp = 0; tp < 9; ++tp)
+      for (int ci = 0; ci < c; ++ci) w16[(size_t)co * ktot + tp * c + ci] = f2bf((*w2)[((size_t)co * c + ci) * 9 + tp]);
+    const float ratio = sd[co] / s2[co];
+    for (int ci = 0; ci < cin_ds; ++ci) w16[(size_t)co * ktot + 9 * c + ci] = f2bf((*wd)[(size_t)co * cin_ds + ci] * ratio);
+    t2[co] += td[co];
+  }
+  OCRB_TRY(upload(dc.w16, w16));
+  OCRB_TRY(upload(dc.shift, t2));
+  dc.ds_cin = cin_ds;
+  return OCRB_OK;
+}
+
 }  // namespace ocrb
 
 using namespace ocrb;
@@ -270,8 +298,14 @@ static int det_build(ocrb_det *d, const HostWeights &hw) {
       const int stride = (blk == 0 && li > 0) ? 2 : 1;
       OCRB_TRY(prep_conv(hw, {p + ".conv1", p + ".bn1", bc_in, c, 3, stride, 1}, bf, d->conv[p + ".conv1"]));
       OCRB_TRY(prep_conv(hw, {p + ".conv2", p + ".bn2", c, c, 3, 1, 1}, bf, d->conv[p + ".conv2"]));
-      if (blk == 0 && li > 0)
+      if (blk == 0 && li > 0) {
         OCRB_TRY(prep_conv(hw, {p + ".downsample.0", p + ".downsample.1", bc_in, c, 1, stride, 0}, bf, d->conv[p + ".downsample"]));
+        static const bool fuse_ds = !(getenv("OCRB_FUSE_DS") && atoi(getenv("OCRB_FUSE_DS")) == 0);
+        if (bf && fuse_ds) {
+          // keep an unfused copy of conv2 for callers that cannot use the fused form (none today), fuse into conv2
+          OCRB_TRY(prep_fused_downsample(hw, p, bc_in, c, d->conv[p + ".conv2"]));
+        }
+      }
     }
     cin = c;
   }
@@ -494,7 +528,19 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     } else {
       OCRB_TRY(get_map(d, "a." + name, in, B, h, w, c.cin, c.stride, &ma));
     }
-    OCRB_TRY(get_wmap(d, (halo ? "wh." : "w.") + name, c.w16.p, c.cout, c.k * c.k * c.cin, halo ? halo_weight_box_rows(nt) : nt, &mb));
+    OCRB_TRY(get_wmap(d, (halo ? "wh." : "w.") + name, c.w16.p, c.cout, c.k * c.k * c.cin + c.ds_cin, halo ? halo_weight_box_rows(nt) : nt, &mb));
+    CUtensorMap *md = nullptr;
+    if (c.ds_cin > 0) {  // fused downsample: second input = the block input sampled at stride 2
+      OCRB_REQUIRE(halo && p.ds_src, "fused downsample needs the halo kernel and a source");
+      auto it = d->maps.m.find("d." + name);
+      if (it == d->maps.m.end()) {
+        CUtensorMap m;
+        OCRB_TRY(make_halo_ds_map(&m, p.ds_src, B, 2 * h, 2 * w, c.ds_cin, h, w, nt, nt == 64 ? 4 : 2));
+        it = d->maps.m.emplace("d." + name, m).first;
+      }
+      md = &it->second;
+      p.ds_chunks = c.ds_cin / 64;
+    }
     p.B = B;
     p.Ho = (h + 2 * c.pad - c.k) / c.stride + 1;
     p.Wo = (w + 2 * c.pad - c.k) / c.stride + 1;
@@ -505,7 +551,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     if (p.out && p.out_ldc == 0) p.out_ldc = c.cout;
     p.err = d->err.as<int>();
     const std::string tag = "tc:" + name;
-    if (halo) return launch_conv_halo(ctx, *ma, *mb, p, nt, tag.c_str());
+    if (halo) return launch_conv_halo(ctx, *ma, *mb, p, nt, tag.c_str(), md);
     return launch_conv_tc(ctx, *ma, *mb, p, nt, EPI_STD, tag.c_str());
   };
   const bf *x = x0;
@@ -520,14 +566,16 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
       q1.relu = 1; q1.out = bk.t;
       OCRB_TRY(conv(p + ".conv1", x, hin, win, q1));
       const bf *res = x;
-      if (bk.ds) {
+      const bool ds_fused = bk.ds && d->conv[p + ".conv2"].ds_cin > 0;
+      if (bk.ds && !ds_fused) {
         ConvTcParams qd;
         qd.relu = 0; qd.out = bk.ds;
         OCRB_TRY(conv(p + ".downsample", x, hin, win, qd));
         res = bk.ds;
       }
       ConvTcParams q2;
-      q2.relu = 1; q2.out = bk.y; q2.residual = res;
+      q2.relu = 1; q2.out = bk.y; q2.residual = ds_fused ? nullptr : res;
+      q2.ds_src = ds_fused ? x : nullptr;
       OCRB_TRY(conv(p + ".conv2", bk.t, fh[li], fw[li], q2));
       x = bk.y;
     }
