@@ -37,12 +37,23 @@ struct HaloGeom {
   int a_stage_bytes;   // bytes of one A stage (multiple of 1024)
   int a_tx_bytes;      // bytes one halo TMA box writes = (TH + 2) * PW * 128
   int a_stages, b_stages;
+  // M rows between consecutive sub-tiles: 128 (sub-tiles tile the padded pitch linearly) or, for the
+  // TMA-store epilogue, sub_rows * PW <= 128 so that every sub-tile covers WHOLE tile rows
+  int sub_rows, sub_stride;
+  int obufs, obuf_bytes;  // TMA-store epilogue: ring of output / residual staging tiles [sub_rows * TW][128 B]
 };
+constexpr int HL_MAX_OBUFS = 4;
 
-template <int N_TILE, int G, int CG>
-__global__ void __launch_bounds__((1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS) * 32, 1)
+// TS = 1 (N_TILE = 64 only): the epilogue leaves through TMA.  Sub-tiles are row-aligned, so a
+// sub-tile's valid outputs are one box {64 ch, TW, sub_rows}; the epilogue threads write their own
+// pixel row (bf16, 128B-swizzled) into a staging tile and one extra warp turns full tiles into
+// cp.async.bulk.tensor stores (image borders clipped by the hardware) and TMA-loads the residual
+// tile of a later sub-tile INTO the freed staging tile (read-modify-write in place).  No
+// per-thread global loads/stores, no transposing round trip through shared memory.
+template <int N_TILE, int G, int CG, int TS>
+__global__ void __launch_bounds__((1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS + TS) * 32, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
-                 const ConvTcParams p, const HaloGeom g) {
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const ConvTcParams p, const HaloGeom g) {
   // CG = 2: a CTA PAIR works as one unit (tcgen05 cta_group::2).  Each CTA owns a spatial tile
   // (its A operand, its accumulators) and HALF of every weight tile; the leader CTA issues
   // UMMAs of M = 256 that read both halves.  Per CTA that halves the shared-memory reads and
@@ -52,7 +63,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // them) keep the pipe fed; N = 128 needs one.
   constexpr int MW = G >= 4 ? 2 : 1;
   constexpr int GW = G / MW;  // sub-tiles per MMA warp
-  constexpr int THREADS = (1 + MW + HL_EPI_WARPS) * 32;
+  constexpr int THREADS = (1 + MW + HL_EPI_WARPS + TS) * 32;
+  static_assert(!TS || N_TILE == 64, "TMA-store epilogue: one 128-byte row per pixel");
   constexpr int NB = N_TILE / CG;  // weight rows held by this CTA
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(16) float s_scale[512], s_shift[512];
@@ -61,11 +73,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t *sA = smem;
   uint8_t *sB = smem + g.a_stages * g.a_stage_bytes;
   uint8_t *sStg = sB + g.b_stages * B_BYTES;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sStg + HL_STG_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sStg + (TS ? g.obufs * g.obuf_bytes : HL_STG_BYTES));
   uint64_t *a_full = bars, *a_empty = a_full + g.a_stages;
   uint64_t *b_full = a_empty + g.a_stages, *b_empty = b_full + g.b_stages;
   uint64_t *tfull = b_empty + g.b_stages, *tempty = tfull + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  uint64_t *o_ready = tempty + 2, *o_done = o_ready + HL_MAX_OBUFS;  // TS only
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_done + HL_MAX_OBUFS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -90,6 +103,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < g.a_stages; ++s) { mbar_init(&a_full[s], CG); mbar_init(&a_empty[s], MW); }
     for (int s = 0; s < g.b_stages; ++s) { mbar_init(&b_full[s], CG); mbar_init(&b_empty[s], MW); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], MW); mbar_init(&tempty[a], CG * HL_EPI_WARPS); }
+    if (TS) {
+      tma_prefetch_desc(&tmO);
+      if (p.residual) tma_prefetch_desc(&tmR);
+      for (int s = 0; s < g.obufs; ++s) { mbar_init(&o_ready[s], 1); mbar_init(&o_done[s], HL_EPI_WARPS); }
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -186,7 +204,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int ck = 0; ck < chunks; ++ck) {
           mbar_wait(&a_full[as], aph, p.err, 14);
           // start address advances by whole 128 B rows: (gi*128 + row_off) * 128 B >> 4
-          const uint64_t a0 = make_smem_desc(sA + as * g.a_stage_bytes) + (uint64_t)(g0 * 128 * 8);
+          const uint64_t a0 = make_smem_desc(sA + as * g.a_stage_bytes) + (uint64_t)(g0 * g.sub_stride * 8);
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_full[bs], bph, p.err, 15);
             tc_fence_after();
@@ -200,10 +218,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   if (CG == 2)
-                    umma_bf16_2sm(d_base + (uint32_t)(gi * N_TILE), at + (uint64_t)(gi * 128 * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                    umma_bf16_2sm(d_base + (uint32_t)(gi * N_TILE), at + (uint64_t)(gi * g.sub_stride * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                   k != 0 ? 1u : first);
                   else
-                    umma_bf16(d_base + (uint32_t)(gi * N_TILE), at + (uint64_t)(gi * 128 * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                    umma_bf16(d_base + (uint32_t)(gi * N_TILE), at + (uint64_t)(gi * g.sub_stride * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
                               k != 0 ? 1u : first);
                 }
               }
@@ -230,15 +248,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&a_full[as], aph, p.err, 19);
           mbar_wait(&b_full[bs], bph, p.err, 20);
           tc_fence_after();
-          const uint64_t a0 = make_smem_desc(sA + as * g.a_stage_bytes) + (uint64_t)(g0 * 128 * 8);
+          const uint64_t a0 = make_smem_desc(sA + as * g.a_stage_bytes) + (uint64_t)(g0 * g.sub_stride * 8);
           const uint64_t bdesc = make_smem_desc(sB + bs * B_BYTES);
           if (elect_one()) {
 #pragma unroll
             for (int gi = 0; gi < GW; ++gi) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                if (CG == 2) umma_bf16_2sm(d_base + (uint32_t)(gi * N_TILE), a0 + (uint64_t)(gi * 128 * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
-                else umma_bf16(d_base + (uint32_t)(gi * N_TILE), a0 + (uint64_t)(gi * 128 * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                if (CG == 2) umma_bf16_2sm(d_base + (uint32_t)(gi * N_TILE), a0 + (uint64_t)(gi * g.sub_stride * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                else umma_bf16(d_base + (uint32_t)(gi * N_TILE), a0 + (uint64_t)(gi * g.sub_stride * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
               }
             }
             if (CG == 2) {
@@ -258,6 +276,122 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+    }
+  } else if (TS && warp == 1 + MW + HL_EPI_WARPS) {
+    // ================= TMA store / residual-load warp (one thread: bulk groups are per thread) =================
+    if (lane == 0) {
+      const int obuf_tx = g.sub_rows * g.TW * 128;
+      auto coords = [&](int unit, int gi, int &c0, int &c1, int &c2, int &c3) -> bool {
+        const int n_tile = unit / pairs_per_n, m_tile = (unit - n_tile * pairs_per_n) * CG + (int)rank;
+        const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
+        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        c0 = n_tile * N_TILE; c1 = tx * g.TW; c2 = ty * g.TH + gi * g.sub_rows; c3 = b;
+        return m_tile < num_m_tiles;
+      };
+      // hand staging tile `buf` to the epilogue for sub-tile (unit, gi): with its residual tile in it, or just free
+      auto prepare = [&](int buf, int unit, int gi) {
+        if (unit >= num_units) return;
+        if (p.residual) {
+          int c0, c1, c2, c3;
+          coords(unit, gi, c0, c1, c2, c3);  // past-the-end tiles read zeros (batch index out of bounds)
+          mbar_expect_tx(&o_ready[buf], obuf_tx);
+          tma_load_4d(sStg + buf * g.obuf_bytes, &tmR, &o_ready[buf], c0, c1, c2, c3);
+        } else {
+          mbar_arrive(&o_ready[buf]);
+        }
+      };
+      int pu = unit0, pg = 0;  // next sub-tile to prepare
+      for (int j = 0; j < g.obufs; ++j) {
+        prepare(j, pu, pg);
+        if (++pg == G) { pg = 0; pu += unit_step; }
+      }
+      int buf = 0, prev = -1;
+      uint32_t dph = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        for (int gi = 0; gi < G; ++gi) {
+          mbar_wait(&o_done[buf], dph, p.err, 21);
+          int c0, c1, c2, c3;
+          if (coords(unit, gi, c0, c1, c2, c3)) tma_store_4d(&tmO, sStg + buf * g.obuf_bytes, c0, c1, c2, c3);
+          bulk_commit_group();
+          if (prev >= 0) {
+            bulk_wait_group_read<1>();  // the previous sub-tile's store has left its staging tile
+            prepare(prev, pu, pg);
+            if (++pg == G) { pg = 0; pu += unit_step; }
+          }
+          prev = buf;
+          if (++buf == g.obufs) { buf = 0; dph ^= 1; }
+        }
+      }
+      bulk_wait_group<0>();
+    }
+  } else if (TS) {
+    // ================= epilogue through TMA =================
+    const int ew = warp - 1 - MW;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = ew >> 2;      // which 32 of the 64 channels
+    const int m_local = quarter * 32 + lane;
+    const int ysub = m_local / g.PW, xl = m_local - ysub * g.PW;
+    const bool row_ok = m_local < g.sub_stride && xl < g.TW;  // else a junk row: pitch padding / overlap with the next sub-tile
+    const int r = ysub * g.TW + xl;                           // row of the staging tile = box-linear pixel index
+    uint32_t own[4];                                          // this thread's four 16-byte chunks (128B swizzle, like TMA's)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) own[c] = (uint32_t)(r * 128 + (((4 * half + c) ^ (r & 7)) << 4));
+    const bool affine = p.scale != nullptr, has_res = p.residual != nullptr;
+    int acc = 0, buf = 0;
+    uint32_t acc_phase = 0, rph = 0;
+    for (int unit = unit0; unit < num_units; unit += unit_step) {
+      const int n0 = (unit / pairs_per_n) * N_TILE + half * 32;
+      mbar_wait(&tfull[acc], acc_phase, p.err, 16);
+      tc_fence_after();
+#pragma unroll 1
+      for (int gi = 0; gi < G; ++gi) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * G + gi) * N_TILE + half * 32), v);
+        if (affine) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + n0 + 4 * j);
+            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + n0 + 4 * j);
+            v[4 * j + 0] = fmaf(v[4 * j + 0], sc.x, sh.x);
+            v[4 * j + 1] = fmaf(v[4 * j + 1], sc.y, sh.y);
+            v[4 * j + 2] = fmaf(v[4 * j + 2], sc.z, sh.z);
+            v[4 * j + 3] = fmaf(v[4 * j + 3], sc.w, sh.w);
+          }
+        }
+        mbar_wait(&o_ready[buf], rph, p.err, 22);
+        const uint32_t tile = smem_u32(sStg + buf * g.obuf_bytes);
+        if (row_ok) {
+          if (has_res) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 u = lds_16(tile + own[c]);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(w[j]); v[c * 8 + 2 * j] += f.x; v[c * 8 + 2 * j + 1] += f.y; }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            sts_16(tile + own[c], make_uint4(pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]),
+                                             pack_bf16(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16(v[c * 8 + 6], v[c * 8 + 7])));
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_done[buf]);
+        if (++buf == g.obufs) { buf = 0; rph ^= 1; }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
+        else mbar_arrive(&tempty[acc]);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ================= epilogue =================
@@ -361,17 +495,50 @@ static void pick_geom(int Ho, int Wo, int G, int *PW, int *TH) {
   }
 }
 
-int halo_geometry(int Ho, int Wo, int n_tile, int G, HaloGeom *out) {  // n_tile = weight rows per CTA
+// Row-aligned variant (TMA-store epilogue): each sub-tile = sub_rows whole rows of pitch PW.
+static void pick_geom_rows(int Ho, int Wo, int G, int *PW, int *sub_rows) {
+  double best = -1.0;
+  for (int tw = 8; tw <= 126 && tw <= Wo + 7; ++tw) {
+    const int pw = tw + 2;
+    int rps = 128 / pw;
+    const int need = (Ho + G - 1) / G;
+    if (rps > need) rps = need;
+    const int th = G * rps;
+    const int tx = (Wo + tw - 1) / tw, ty = (Ho + th - 1) / th;
+    const double eff = (double)Ho * Wo / ((double)tx * ty * G * 128);
+    static const double halo_w = getenv("OCRB_HALO_W") ? atof(getenv("OCRB_HALO_W")) : 0.3;
+    const double score = eff - halo_w * ((double)(th + 2) * pw / ((double)th * tw) - 1.0);
+    if (score > best) { best = score; *PW = pw; *sub_rows = rps; }
+  }
+}
+
+// TMA-store epilogue for 64-channel convolutions without replication (OCRB_HALO_TS=0 turns it off)
+bool halo_use_ts(int n_tile, int rep) {
+  static const bool on = !(getenv("OCRB_HALO_TS") && atoi(getenv("OCRB_HALO_TS")) == 0);
+  return on && n_tile == 64 && rep == 1;
+}
+
+int halo_geometry(int Ho, int Wo, int n_tile, int G, int ts, HaloGeom *out) {  // n_tile = weight rows per CTA
   HaloGeom g;
-  pick_geom(Ho, Wo, G, &g.PW, &g.TH);
+  if (ts) {
+    pick_geom_rows(Ho, Wo, G, &g.PW, &g.sub_rows);
+    g.TH = G * g.sub_rows;
+    g.sub_stride = g.sub_rows * g.PW;
+  } else {
+    pick_geom(Ho, Wo, G, &g.PW, &g.TH);
+    g.sub_rows = 0;
+    g.sub_stride = 128;
+  }
   g.TW = g.PW - 2;
+  g.obuf_bytes = ts ? ((g.sub_rows * g.TW * 128 + 1023) / 1024) * 1024 : 0;
+  g.obufs = ts ? 3 : 0;
   const int halo_rows = (g.TH + 2) * g.PW;
-  const int read_rows = G * 128 + 2 * g.PW + 2;  // last sub-tile, tap (2,2)
+  const int read_rows = (G - 1) * g.sub_stride + 128 + 2 * g.PW + 2;  // last sub-tile, tap (2,2)
   int rows = halo_rows > read_rows ? halo_rows : read_rows;
   g.a_stage_bytes = ((rows * 128 + 1023) / 1024) * 1024;
   g.a_tx_bytes = halo_rows * 128;
   const int b_bytes = n_tile * 128;
-  const int budget = 227 * 1024 - 1024 /*align*/ - 4096 /*static scale/shift*/ - 512 /*barriers*/ - HL_STG_BYTES;
+  const int budget = 227 * 1024 - 1024 /*align*/ - 4096 /*static scale/shift*/ - 512 /*barriers*/ - (ts ? g.obufs * g.obuf_bytes : HL_STG_BYTES);
   g.a_stages = 2;
   g.b_stages = (budget - g.a_stages * g.a_stage_bytes) / b_bytes;
   if (g.b_stages > 8) {
@@ -385,22 +552,23 @@ int halo_geometry(int Ho, int Wo, int n_tile, int G, HaloGeom *out) {  // n_tile
 }
 
 int make_act_tensor_map_box(CUtensorMap *map, const void *base, int B, int H, int W, int C, int box_w, int box_h);
+int make_act_tensor_map_pitched(CUtensorMap *map, const void *base, int B, int H, int W, int C, int ldc, int box_w, int box_h);
 
 
-template <int N_TILE, int G, int CG>
-static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmD, const ConvTcParams &p,
-                           const HaloGeom &g, int num_units, const char *tag) {
+template <int N_TILE, int G, int CG, int TS>
+static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmD, const CUtensorMap &tmO,
+                           const CUtensorMap &tmR, const ConvTcParams &p, const HaloGeom &g, int num_units, const char *tag) {
   static bool attr_set[16] = {false};
-  auto kern = conv_halo_kernel<N_TILE, G, CG>;
+  auto kern = conv_halo_kernel<N_TILE, G, CG, TS>;
   if (!attr_set[ctx->device & 15]) {
     OCRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
     attr_set[ctx->device & 15] = true;
   }
-  const int smem = 1024 + g.a_stages * g.a_stage_bytes + g.b_stages * (N_TILE / CG) * 128 + HL_STG_BYTES + 512;
+  const int smem = 1024 + g.a_stages * g.a_stage_bytes + g.b_stages * (N_TILE / CG) * 128 + (TS ? g.obufs * g.obuf_bytes : HL_STG_BYTES) + 512;
   int grid = num_units * CG < ctx->sm_count ? num_units * CG : (ctx->sm_count / CG) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3((1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS) * 32);
+  cfg.blockDim = dim3((1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS + TS) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
@@ -410,7 +578,7 @@ static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensor
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  OCRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, p, g));
+  OCRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmO, tmR, p, g));
   return check_launch(ctx, tag);
 }
 
@@ -419,9 +587,9 @@ static int halo_cg() {  // CTA-pair mode unless OCRB_HALO_CG=1
   return cg;
 }
 
-int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G) {
+int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G, int rep) {
   HaloGeom g;
-  OCRB_TRY(halo_geometry(H, W, n_tile / halo_cg(), G, &g));
+  OCRB_TRY(halo_geometry(H, W, n_tile / halo_cg(), G, halo_use_ts(n_tile, rep), &g));
   return make_act_tensor_map_box(map, base, B, H, W, C, g.PW, g.TH + 2);
 }
 int halo_weight_box_rows(int n_tile) { return n_tile / halo_cg(); }
@@ -431,7 +599,7 @@ int halo_weight_box_rows(int n_tile) { return n_tile / halo_cg(); }
 int make_act_tensor_map_strided_box(CUtensorMap *map, const void *base, int B, int H, int W, int C, int box_w, int box_h, int stride);
 int make_halo_ds_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int Ho, int Wo, int n_tile, int G) {
   HaloGeom g;
-  OCRB_TRY(halo_geometry(Ho, Wo, n_tile / halo_cg(), G, &g));
+  OCRB_TRY(halo_geometry(Ho, Wo, n_tile / halo_cg(), G, 0, &g));  // fused downsample: 128-channel tiles only
   return make_act_tensor_map_strided_box(map, base, B, H, W, C, g.PW, g.TH, 2);
 }
 
@@ -442,14 +610,25 @@ int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &t
   if (p.R != 3 || p.S != 3 || p.stride != 1 || p.pad != 1 || p.sum_out || !p.out) { set_error("conv_halo: unsupported convolution"); return OCRB_ERR_INVALID; }
   if (p.Cout % n_tile != 0 || p.Cout > 512) { set_error("conv_halo: Cout %d vs N tile %d", p.Cout, n_tile); return OCRB_ERR_INVALID; }
   const int G = n_tile == 64 ? 4 : 2, CG = halo_cg();
+  const int ts = halo_use_ts(n_tile, p.rep);
+  if (ts && p.ds_chunks) { set_error("conv_halo: fused downsample with 64-channel tiles"); return OCRB_ERR_INVALID; }
   HaloGeom g;
-  OCRB_TRY(halo_geometry(p.Ho, p.Wo, n_tile / CG, G, &g));
+  OCRB_TRY(halo_geometry(p.Ho, p.Wo, n_tile / CG, G, ts, &g));
   p.tiles_x = (int)cdiv(p.Wo, g.TW);
   p.tiles_y = (int)cdiv(p.Ho, g.TH);
   p.num_n_tiles = p.Cout / n_tile;
   const int num_units = (int)cdiv((int64_t)p.tiles_x * p.tiles_y * p.B, CG) * p.num_n_tiles;
-  if (n_tile == 64) return CG == 2 ? launch_halo_one<64, 4, 2>(ctx, tmA, tmB, tmD, p, g, num_units, tag) : launch_halo_one<64, 4, 1>(ctx, tmA, tmB, tmD, p, g, num_units, tag);
-  if (n_tile == 128) return CG == 2 ? launch_halo_one<128, 2, 2>(ctx, tmA, tmB, tmD, p, g, num_units, tag) : launch_halo_one<128, 2, 1>(ctx, tmA, tmB, tmD, p, g, num_units, tag);
+  if (ts) {
+    // output slice [B][Ho][Wo][Cout] at channel offset out_coff of an out_ldc-wide buffer; residual [B][Ho][Wo][Cout]
+    CUtensorMap tmO, tmR;
+    OCRB_TRY(make_act_tensor_map_pitched(&tmO, p.out + p.out_coff, p.B, p.Ho, p.Wo, p.Cout, p.out_ldc, g.TW, g.sub_rows));
+    if (p.residual) OCRB_TRY(make_act_tensor_map_pitched(&tmR, p.residual, p.B, p.Ho, p.Wo, p.Cout, p.Cout, g.TW, g.sub_rows));
+    else tmR = tmO;
+    return CG == 2 ? launch_halo_one<64, 4, 2, 1>(ctx, tmA, tmB, tmD, tmO, tmR, p, g, num_units, tag)
+                   : launch_halo_one<64, 4, 1, 1>(ctx, tmA, tmB, tmD, tmO, tmR, p, g, num_units, tag);
+  }
+  if (n_tile == 64) return CG == 2 ? launch_halo_one<64, 4, 2, 0>(ctx, tmA, tmB, tmD, tmA, tmA, p, g, num_units, tag) : launch_halo_one<64, 4, 1, 0>(ctx, tmA, tmB, tmD, tmA, tmA, p, g, num_units, tag);
+  if (n_tile == 128) return CG == 2 ? launch_halo_one<128, 2, 2, 0>(ctx, tmA, tmB, tmD, tmA, tmA, p, g, num_units, tag) : launch_halo_one<128, 2, 1, 0>(ctx, tmA, tmB, tmD, tmA, tmA, p, g, num_units, tag);
   set_error("conv_halo: unsupported N tile %d", n_tile);
   return OCRB_ERR_INVALID;
 }

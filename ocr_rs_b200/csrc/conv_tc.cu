@@ -348,6 +348,21 @@ int make_act_tensor_map_box(CUtensorMap *map, const void *base, int B, int H, in
   return OCRB_OK;
 }
 
+// a C-channel slice of pixels that are ldc channels apart ([B][H][W][ldc], base already at the slice): TMA store / residual load box
+int make_act_tensor_map_pitched(CUtensorMap *map, const void *base, int B, int H, int W, int C, int ldc, int box_w, int box_h) {
+  auto fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return OCRB_ERR_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ldc * 2, (cuuint64_t)W * ldc * 2, (cuuint64_t)H * W * ldc * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(pitched box %dx%d, ldc %d) -> %d", box_w, box_h, ldc, (int)r); return OCRB_ERR_CUDA; }
+  return OCRB_OK;
+}
+
 // activations NHWC bf16 sampled every `stride` pixels: box of box_w x box_h SAMPLED positions
 int make_act_tensor_map_strided_box(CUtensorMap *map, const void *base, int B, int H, int W, int C, int box_w, int box_h, int stride) {
   auto fn = get_encode_fn();

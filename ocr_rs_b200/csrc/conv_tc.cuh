@@ -47,10 +47,15 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
                    const HeadConsts *hc = nullptr);
 
 // conv_halo.cu: 3x3 stride-1 convolutions with the halo'd input tile resident in shared memory
-int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G);
+int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G, int rep);
 int halo_weight_box_rows(int n_tile);  // rows of the weight TMA box (half the N tile in CTA-pair mode)
 int make_halo_ds_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int Ho, int Wo, int n_tile, int G);
 int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, const char *tag,
                      const CUtensorMap *tmD = nullptr);
+
+// conv_lateral.cu: FPN lateral 1x1 conv + "up2 + lateral" sum, TMA in / TMA out
+bool lateral_ts_supported(int Cin, int Cout, int Ho, int Wo);
+int launch_conv_lateral(ocrb_ctx *ctx, const __nv_bfloat16 *in, const __nv_bfloat16 *w, const __nv_bfloat16 *upper, __nv_bfloat16 *out,
+                        __nv_bfloat16 *sum, int B, int Ho, int Wo, int Cin, int *err, const char *tag);
 
 }  // namespace ocrb

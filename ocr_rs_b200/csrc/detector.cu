@@ -515,13 +515,15 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
   auto conv = [&](const std::string &name, const bf *in, int h, int w, ConvTcParams p) -> int {
     DevConv &c = d->conv[name];
     CUtensorMap *ma, *mb;
+    if (c.k == 1 && c.stride == 1 && p.sum_out && p.up_src && !c.has_bn && !p.relu && lateral_ts_supported(c.cin, c.cout, h, w))
+      return launch_conv_lateral(ctx, in, c.w16.as<bf>(), p.up_src, p.out, p.sum_out, B, h, w, c.cin, d->err.as<int>(), ("tc:" + name).c_str());
     const bool halo = use_halo && c.k == 3 && c.stride == 1 && !p.sum_out && p.out;
     const int nt = halo ? (c.cout == 64 ? 64 : 128) : n_tile_for(c.cout);
     if (halo) {
       auto it = d->maps.m.find("h." + name);
       if (it == d->maps.m.end()) {
         CUtensorMap m;
-        OCRB_TRY(make_halo_act_map(&m, in, B, h, w, c.cin, nt, nt == 64 ? 4 : 2));
+        OCRB_TRY(make_halo_act_map(&m, in, B, h, w, c.cin, nt, nt == 64 ? 4 : 2, p.rep));
         it = d->maps.m.emplace("h." + name, m).first;
       }
       ma = &it->second;
