@@ -284,7 +284,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r1_ncu_forward_traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read+write of the same launches from one `ncu --set full` capture
         tj = json.load(open(tpath))
-        traffic = tj["dram_bytes_per_launch"] * min(count, 64) / 64.0  # one launch covers one chunk of <= 64 images
+        # per launch like `achieved`: the pipeline forwards chunks of <= 128 images, the capture holds tj["images"] per launch
+        traffic = tj["dram_bytes_per_launch"] * min(count, 128) / float(tj["images"])
     flops_step = tc_flops_per_image(H, W) * count
     achieved = flops_step / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     groups = {}
@@ -314,7 +315,7 @@ def main():
         "gpu_launches": int(lt.item()),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                     "traffic": traffic, "traffic_note": "avg DRAM bytes per tcgen05 launch (64-image chunk), profiles/r1_ncu_forward_traffic.json; algorithmic unfused bf16 activation traffic is 285.8 MB/image", "kernel": "stem_tc / conv_halo / conv_tc kernels (all tcgen05 implicit-GEMM launches of one step)", "launches": tc_n,
+                     "traffic": traffic, "traffic_note": "avg DRAM bytes per tcgen05 launch scaled to this run's chunk of <= 128 images (profiles/r1_ncu_forward_traffic.json: 227 MB/image measured); algorithmic unfused bf16 activation traffic is 285.8 MB/image", "kernel": "stem_tc / conv_halo / conv_lateral / conv_tc kernels (all tcgen05 implicit-GEMM launches of one step)", "launches": tc_n,
                      "avg_launch_ms": tc_ms / max(tc_n, 1), "flops_per_image": tc_flops_per_image(H, W), "peak_source": peak_src,
                      "share_of_step": tc_ms / all_ms if all_ms else None},
         "kernels_ms_per_step": {k: round(v[1], 3) for k, v in top},
