@@ -52,7 +52,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ HeadConsts hc) {
   using L = TcSmem<N_TILE, STAGES, RING, EW>;
   constexpr int TC_THREADS = (2 + EW) * 32;
-  constexpr int PARTS = EW / 4;  // column parts
+  // DB head tail with 16 epilogue warps: TWO groups of 8, group g owns accumulator stage g and takes every
+  // second tile of this CTA — the tail is FP32-issue/latency bound, so two tiles in flight fill the schedulers
+  constexpr int GROUPS = (EPI == EPI_HEAD && EW == 16) ? 2 : 1;
+  constexpr int PARTS = EW / 4 / GROUPS;  // column parts
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(16) float s_scale[512], s_shift[512];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -87,7 +90,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EW); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EW / GROUPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -151,9 +154,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================= epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = ew >> 2;  // column part of this warp (0 .. PARTS-1)
-    int acc = 0;
+    const int half = (ew >> 2) % PARTS;  // column part of this warp (0 .. PARTS-1)
+    const int group = ew / (EW / GROUPS);
+    int acc = GROUPS == 2 ? group : 0;
     uint32_t acc_phase = 0;
+    int tile_it = 0;
     EpiParams e;
     e.s_scale = s_scale; e.s_shift = s_shift; e.has_affine = p.scale != nullptr;
     e.addend = p.residual ? p.residual : p.up_src;
@@ -161,7 +166,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     e.out = p.out; e.sum_out = p.sum_out;
     e.Cout = p.Cout; e.out_ldc = p.out_ldc; e.out_coff = p.out_coff; e.rep = p.rep; e.Wo = p.Wo; e.relu = p.relu;
     const uint32_t stg = smem_u32(smem + L::OFF_STG + ew * 2048);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+      if (GROUPS == 2 && (tile_it & 1) != group) continue;
       const int n_tile = tile / num_m_tiles, m_tile = tile - n_tile * num_m_tiles;
       const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
       const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
@@ -287,8 +293,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (GROUPS == 2) {
+        acc_phase ^= 1;  // this group's stage is used by every second tile
+      } else {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
   }
   // ---- teardown ----
@@ -420,7 +430,9 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
   const int num_tiles = p.tiles_x * p.tiles_y * p.B * p.num_n_tiles;
   if (epi == EPI_HEAD) {
     if (n_tile != 256) { set_error("conv_tc head needs N tile 256"); return OCRB_ERR_INVALID; }
-    return launch_one<256, 4, EPI_HEAD, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+    static const bool ew8 = getenv("OCRB_HEAD_EW") && atoi(getenv("OCRB_HEAD_EW")) == 8;  // tuning knob
+    return ew8 ? launch_one<256, 4, EPI_HEAD, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc)
+               : launch_one<256, 4, EPI_HEAD, 0, 16>(ctx, tmA, tmB, p, num_tiles, tag, hc);
   }
   switch (n_tile) {
     case 64: return launch_one<64, 6, EPI_STD, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc);
