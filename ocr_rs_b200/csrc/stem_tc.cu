@@ -19,15 +19,23 @@
 
 namespace ocrb {
 
-constexpr int SK_PH = 8, SK_PW = 14;                       // pooled tile
+#ifndef OCRB_STEM_PW
+#define OCRB_STEM_PW 14
+#endif
+constexpr int SK_PH = 8, SK_PW = OCRB_STEM_PW;             // pooled tile: 14 wide = 4 M tiles, 2 CTAs per SM (7 wide / 4 CTAs measured 17% slower: the kernel is bound by shared-memory wavefronts, not latency)
 constexpr int SK_CH = 2 * SK_PH + 1, SK_CW = 2 * SK_PW + 1;  // conv tile 17 x 29
 constexpr int SK_ROWS = SK_CH * SK_CW;                     // 493 valid GEMM rows
-constexpr int SK_IH = 2 * SK_CH + 5, SK_IW = 64;           // input patch 39 x 64 (63 used + the zero-weight column)
+constexpr int SK_MT = (SK_ROWS + 127) / 128;               // M tiles of 128 rows
+#ifndef OCRB_STEM_OCC
+#define OCRB_STEM_OCC (SK_MT <= 2 ? 4 : 2)
+#endif
+constexpr int SK_OCC = OCRB_STEM_OCC;                      // CTAs per SM (shared memory and 512 TMEM columns)
+constexpr int SK_IH = 2 * SK_CH + 5, SK_IW = 2 * SK_CW + 6;  // input patch 39 x 64 (63 used + the zero-weight column)
 constexpr int SK_THREADS = 256;
-constexpr int SK_A_BYTES = 4 * 128 * 128;                  // 4 M tiles x 128 rows x 128 B
+constexpr int SK_A_BYTES = SK_MT * 128 * 128;              // M tiles x 128 rows x 128 B
 constexpr int SK_OFF_B = SK_A_BYTES;                       // 64 x 128 B
-constexpr int SK_OFF_PATCH = SK_OFF_B + 64 * 128;          // bf16 [39][64]
-constexpr int SK_RAW_WORDS = 17;                           // 68 raw bytes per patch row: 3 lead-in + 64 + 1
+constexpr int SK_OFF_PATCH = SK_OFF_B + 64 * 128;          // bf16 [39][SK_IW]
+constexpr int SK_RAW_WORDS = (SK_IW + 6) / 4;              // raw bytes per patch row: 3 lead-in + SK_IW (+ pad to a word)
 constexpr int SK_RAW_BYTES = SK_IH * SK_RAW_WORDS * 4;     // one raw u8 patch (cp.async prefetch target)
 constexpr int SK_OFF_RAW = SK_OFF_PATCH + SK_IH * SK_IW * 2;
 constexpr int SK_OFF_MISC = SK_OFF_RAW + 2 * SK_RAW_BYTES;
@@ -44,7 +52,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 struct StemConsts { float scale[64], shift[64]; };
 
 template <class TIn>
-__global__ void __launch_bounds__(SK_THREADS, 2)
+__global__ void __launch_bounds__(SK_THREADS, SK_OCC)
 stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__restrict__ w /*[49][64]*/,
                const __grid_constant__ StemConsts sc, __nv_bfloat16 *__restrict__ out, int *err) {
   extern __shared__ uint8_t smem_raw[];
@@ -79,7 +87,7 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
     *reinterpret_cast<uint4 *>(sB + co * 128 + ((j ^ (co & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
   if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tmem_alloc(tmem_slot, SK_MT * 64);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -131,7 +139,7 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
     } else {
       const TIn *img = in + (int64_t)b * H * W;
       for (int i = tid; i < SK_IH * SK_IW; i += SK_THREADS) {
-        const int yy = iy0 + (i >> 6), xx = ix0 + (i & 63);
+        const int yy = iy0 + i / SK_IW, xx = ix0 + i % SK_IW;
         const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (float)img[(int64_t)yy * W + xx] : 0.0f;
         s_patch[i] = __float2bfloat16(v);
       }
@@ -158,7 +166,7 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
       tc_fence_after();
       const uint64_t bdesc = make_smem_desc(sB);
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
+      for (int mt = 0; mt < SK_MT; ++mt) {
         const uint64_t adesc = make_smem_desc(sA + mt * 16384);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + mt * 64, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
@@ -172,8 +180,7 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
     {
       const int q = warp & 3;
 #pragma unroll 1
-      for (int rep = 0; rep < 2; ++rep) {
-        const int mt = (warp >> 2) + 2 * rep;
+      for (int mt = warp >> 2; mt < SK_MT; mt += 2) {
         const int m = mt * 128 + q * 32 + lane;
         const int cy = m / SK_CW, cx = m - cy * SK_CW;
         const bool in_grid = (cy0 + cy) >= 0 && (cy0 + cy) < Hc && (cx0 + cx) >= 0 && (cx0 + cx) < Wc;
@@ -254,7 +261,7 @@ stem_tc_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__r
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, SK_MT * 64);
   }
 }
 
@@ -271,7 +278,7 @@ int launch_stem_tc(ocrb_ctx *ctx, const void *in, int is_u8, int B, int H, int W
   }
   const int Hp = H / 4, Wp = W / 4;
   const int64_t units = cdiv(Wp, SK_PW) * cdiv(Hp, SK_PH) * B;
-  const int grid = (int)(units < 2 * ctx->sm_count ? units : 2 * ctx->sm_count);
+  const int grid = (int)(units < SK_OCC * ctx->sm_count ? units : SK_OCC * ctx->sm_count);
   if (is_u8)
     stem_tc_kernel<uint8_t><<<grid, SK_THREADS, SK_SMEM, ctx->stream>>>((const uint8_t *)in, B, H, W, w, sc, out, err);
   else
