@@ -73,6 +73,20 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *_
     const int y = ty * CCL_TH + warp * CCL_ROWS_PER_WARP + k;
     fgv[k] = (x < W && y < H) ? (bm[(int64_t)y * W + x] != 0) : 0;
   }
+  // Tiles without a foreground pixel (most of a document page) are one 4-connected background
+  // rectangle: every pixel points at the tile origin, no union-find needed.
+  int any_fg = 0;
+#pragma unroll
+  for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) any_fg |= fgv[k];
+  if (!__syncthreads_or(any_fg)) {
+    const int origin = ty * CCL_TH * W + tx * CCL_TW;
+#pragma unroll
+    for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) {
+      const int y = ty * CCL_TH + warp * CCL_ROWS_PER_WARP + k;
+      if (x < W && y < H) labels[(int64_t)b * H * W + (int64_t)y * W + x] = origin;
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) {
     const int r = warp * CCL_ROWS_PER_WARP + k, y = ty * CCL_TH + r;
