@@ -35,6 +35,7 @@ TOTAL_IMAGES = 1024
 H = W = 800
 GLYPHS_PER_IMAGE = 4
 METRIC = "800x800 det+rec images/sec"
+CPU_BATCH = 4
 
 
 def tc_flops_per_image(h, w):
@@ -118,12 +119,14 @@ def time_cpu_sample(n_images, budget_s, threads, seed_first=0):
     wr = synth.make_rec_weights(1)
     imgs = synth.document_image_shard(seed_first, n_images, H, W)
     glyphs = synth.make_glyphs(n_images * GLYPHS_PER_IMAGE, 1, "strokes")
-    adj = np.ones((1, 2))
-    cpu_path(wd, wr, imgs[:1], glyphs[:GLYPHS_PER_IMAGE], adj, threads)  # warm-up
+    nb = CPU_BATCH  # the reference batches its evaluation loop (text_detection/mod.rs:188-204); 4 measured best for torch-CPU
+    adj = np.ones((nb, 2))
+    cpu_path(wd, wr, imgs[:1], glyphs[:GLYPHS_PER_IMAGE], adj[:1], threads)  # warm-up
     done, t0 = 0, time.time()
     while done < n_images and (time.time() - t0 < budget_s or done == 0):
-        cpu_path(wd, wr, imgs[done:done + 1], glyphs[done * GLYPHS_PER_IMAGE:(done + 1) * GLYPHS_PER_IMAGE], adj, threads)
-        done += 1
+        k = min(nb, n_images - done)
+        cpu_path(wd, wr, imgs[done:done + k], glyphs[done * GLYPHS_PER_IMAGE:(done + k) * GLYPHS_PER_IMAGE], adj[:k], threads)
+        done += k
     dt = time.time() - t0
     return done / dt, done, dt
 
@@ -132,7 +135,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_step = 4
+    per_step = 8
     times = []
     total = args.warmup + args.steps
     for s in range(total):
@@ -141,7 +144,7 @@ def run_reference(args, rank):
             times.append(dt / done)
     sec_per_img = statistics.mean(times)
     value = 1.0 / sec_per_img
-    sample = f"{per_step} images 800x800 (+{GLYPHS_PER_IMAGE} glyphs each) per step, batch 1, torch {threads} threads + single-thread C post-proc"
+    sample = f"{per_step} images 800x800 (+{GLYPHS_PER_IMAGE} glyphs each) per step, batch {CPU_BATCH}, torch {threads} threads + single-thread C post-proc"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * sec_per_img * per_step, "higher_is_better": True, "scaling": "strong",
@@ -187,6 +190,10 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # any NCCL_DEBUG level prints a version banner on stdout: keep stdout to the single JSON line (BENCH_NCCL_DEBUG overrides)
+        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("BENCH_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = _ffi.Context(local)
     det = resnet18(synth.make_detector_weights(0, "structured"), args.mode, ctx)
@@ -298,9 +305,9 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, done, dt = time_cpu_sample(48, 12.0, threads)
+        v, done, dt = time_cpu_sample(192, 15.0, threads)
         cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"{done} of the {args.images} images (+{GLYPHS_PER_IMAGE} glyphs each), batch 1, {dt:.1f} s: torch-CPU restatement ({threads} threads) + single-thread C post-proc"}
+               "sample": f"{done} of the {args.images} images (+{GLYPHS_PER_IMAGE} glyphs each), batch {CPU_BATCH}, {dt:.1f} s: torch-CPU restatement ({threads} threads) + single-thread C post-proc"}
 
     out = {
         "metric": METRIC, "value": args.images * args.steps / (ms_dev * 1e-3), "unit": "images/s", "n_gpus": world,
