@@ -43,6 +43,9 @@ struct HaloGeom {
   int obufs, obuf_bytes;  // TMA-store epilogue: ring of output / residual staging tiles [sub_rows * TW][128 B]
 };
 constexpr int HL_MAX_OBUFS = 4;
+// folded batch-norm of a 64-channel convolution, passed by value: the TMA-store epilogue reads it from the constant
+// bank (shared memory is the bottleneck of the N = 64 kernels — operand reads alone exceed its bandwidth)
+struct HaloAffine { float scale[64], shift[64]; };
 
 // TS = 1 (N_TILE = 64 only): the epilogue leaves through TMA.  Sub-tiles are row-aligned, so a
 // sub-tile's valid outputs are one box {64 ch, TW, sub_rows}; the epilogue threads write their own
@@ -53,7 +56,8 @@ constexpr int HL_MAX_OBUFS = 4;
 template <int N_TILE, int G, int CG, int TS>
 __global__ void __launch_bounds__((1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS + TS) * 32, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
-                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const ConvTcParams p, const HaloGeom g) {
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const ConvTcParams p, const HaloGeom g,
+                 const __grid_constant__ HaloAffine ha) {
   // CG = 2: a CTA PAIR works as one unit (tcgen05 cta_group::2).  Each CTA owns a spatial tile
   // (its A operand, its accumulators) and HALF of every weight tile; the leader CTA issues
   // UMMAs of M = 256 that read both halves.  Per CTA that halves the shared-memory reads and
@@ -337,6 +341,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
     for (int c = 0; c < 4; ++c) own[c] = (uint32_t)(r * 128 + (((4 * half + c) ^ (r & 7)) << 4));
     const bool affine = p.scale != nullptr, has_res = p.residual != nullptr;
+    const bool affine_c = affine && p.scale_host != nullptr && p.num_n_tiles == 1;  // constants valid (Cout = 64)
     int acc = 0, buf = 0;
     uint32_t acc_phase = 0, rph = 0;
     for (int unit = unit0; unit < num_units; unit += unit_step) {
@@ -347,7 +352,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int gi = 0; gi < G; ++gi) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * G + gi) * N_TILE + half * 32), v);
-        if (affine) {
+        if (affine_c) {
+          if (half == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], ha.scale[j], ha.shift[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], ha.scale[32 + j], ha.shift[32 + j]);
+          }
+        } else if (affine) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 sc = *reinterpret_cast<const float4 *>(s_scale + n0 + 4 * j);
@@ -558,6 +571,14 @@ int make_act_tensor_map_pitched(CUtensorMap *map, const void *base, int B, int H
 template <int N_TILE, int G, int CG, int TS>
 static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmD, const CUtensorMap &tmO,
                            const CUtensorMap &tmR, const ConvTcParams &p, const HaloGeom &g, int num_units, const char *tag) {
+  HaloAffine ha = {};
+  ConvTcParams pk = p;
+  if (TS && p.scale_host && p.shift_host && p.Cout == 64) {
+    memcpy(ha.scale, p.scale_host, sizeof(ha.scale));
+    memcpy(ha.shift, p.shift_host, sizeof(ha.shift));
+  } else {
+    pk.scale_host = pk.shift_host = nullptr;
+  }
   static bool attr_set[16] = {false};
   auto kern = conv_halo_kernel<N_TILE, G, CG, TS>;
   if (!attr_set[ctx->device & 15]) {
@@ -578,7 +599,7 @@ static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensor
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  OCRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmO, tmR, p, g));
+  OCRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmO, tmR, pk, g, ha));
   return check_launch(ctx, tag);
 }
 

@@ -20,6 +20,7 @@ struct ConvTcParams {
   int tiles_x = 0, tiles_y = 0, num_n_tiles = 0;
   // standard epilogue: y = acc * scale[c] + shift[c] (+ residual) (ReLU)
   const float *scale = nullptr, *shift = nullptr;
+  const float *scale_host = nullptr, *shift_host = nullptr;  // host copies of the same (optional; launcher-side only)
   const __nv_bfloat16 *residual = nullptr;  // [B][Ho][Wo][Cout]
   int relu = 0;
   __nv_bfloat16 *out = nullptr;             // [B][Ho*rep][Wo*rep][out_ldc], channel offset out_coff

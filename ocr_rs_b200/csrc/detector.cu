@@ -147,6 +147,7 @@ struct DevConv {
   DevBuf w32;    // fp32 [k*k][cin][cout]
   DevBuf w16;    // bf16 [cout][k*k*cin]
   DevBuf scale, shift;
+  std::vector<float> scale_h, shift_h;  // host copies: kernel-parameter constants of the TMA-store epilogue
 };
 
 static uint16_t f2bf(float f) {
@@ -197,6 +198,7 @@ static int prep_conv(const HostWeights &hw, const ConvSpec &sp, bool want16, Dev
   OCRB_TRY(fold_bn(hw, sp.bn, sp.cout, nullptr, scale, shift));
   OCRB_TRY(upload(dc.scale, scale));
   OCRB_TRY(upload(dc.shift, shift));
+  dc.scale_h = scale; dc.shift_h = shift;
   // OIHW -> [tap][ci][co] fp32
   std::vector<float> w32((size_t)kk * sp.cin * sp.cout);
   for (int co = 0; co < sp.cout; ++co)
@@ -550,6 +552,8 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     p.R = c.k; p.S = c.k; p.cin_chunks = c.cin / 64; p.stride = c.stride; p.pad = c.pad;
     p.scale = c.has_bn ? c.scale.as<float>() : nullptr;  // no batch-norm: identity epilogue
     p.shift = c.has_bn ? c.shift.as<float>() : nullptr;
+    p.scale_host = c.has_bn && !c.scale_h.empty() ? c.scale_h.data() : nullptr;
+    p.shift_host = c.has_bn && !c.shift_h.empty() ? c.shift_h.data() : nullptr;
     if (p.out && p.out_ldc == 0) p.out_ldc = c.cout;
     p.err = d->err.as<int>();
     const std::string tag = "tc:" + name;
