@@ -139,12 +139,75 @@ __global__ void contour_start_flags_vec4_kernel(const uint8_t *__restrict__ bitm
   *reinterpret_cast<uint32_t *>(flags + idx0) = out;
 }
 
+// same, 16 pixels per thread (W % 16 == 0) and one scan tile (SCAN_TILE pixels) per block: most 16-pixel groups of a
+// page are empty (one 16-byte load, one 16-byte store), and the block's count of starts goes straight into the
+// per-tile counts of the order-preserving compaction — the flags are not re-read to be counted.
+constexpr int FLAGS16_THREADS = SCAN_TILE / 16;
+__global__ void __launch_bounds__(FLAGS16_THREADS) contour_start_flags_vec16_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels,
+                                                                                    int H, int W, int B, const uint8_t *__restrict__ bg_open,
+                                                                                    uint8_t *__restrict__ flags, int *__restrict__ tile_counts) {
+  __shared__ int s_cnt[FLAGS16_THREADS / 32];
+  const int64_t idx0 = ((int64_t)blockIdx.x * FLAGS16_THREADS + threadIdx.x) * 16;
+  const int64_t HW = (int64_t)H * W;
+  int cnt = 0;
+  if (idx0 < HW * B) {
+    const uint4 bm4 = *reinterpret_cast<const uint4 *>(bitmap + idx0);
+    const uint32_t bmw[4] = {bm4.x, bm4.y, bm4.z, bm4.w};
+    uint32_t outw[4] = {0u, 0u, 0u, 0u};
+    if ((bm4.x | bm4.y | bm4.z | bm4.w) != 0) {
+      const int i0 = (int)(idx0 % HW);
+      const int x0 = i0 % W;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t bm = bmw[w];
+        if (bm == 0) continue;
+        const int4 lab = *reinterpret_cast<const int4 *>(labels + idx0 + 4 * w);
+        const int labs[4] = {lab.x, lab.y, lab.z, lab.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (((bm >> (8 * k)) & 0xffu) == 0) continue;
+          const int i = i0 + 4 * w + k, x = x0 + 4 * w + k;
+          uint32_t f = START_NONE;
+          if (labs[k] == i) {
+            if (x != 0) f = START_OUTER;
+          } else if (x + 1 < W) {
+            const int64_t e = idx0 + 4 * w + k + 1;  // east neighbour
+            const bool east_bg = k < 3 ? ((bm >> (8 * (k + 1))) & 0xffu) == 0 : (w < 3 ? (bmw[(w + 1) & 3] & 0xffu) == 0 : bitmap[e] == 0);
+            if (east_bg) {
+              const int east_lab = k < 3 ? labs[k + 1] : labels[e];
+              if (east_lab == i + 1 && !bg_open[e]) {
+                const int root = ccl_find(labels + (idx0 - i0), i);
+                if (root % W != 0) f = START_HOLE;
+              }
+            }
+          }
+          outw[w] |= f << (8 * k);
+        }
+      }
+    }
+    *reinterpret_cast<uint4 *>(flags + idx0) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) cnt += __popc((outw[w] | (outw[w] >> 1)) & 0x01010101u);  // flag values are 0, 1, 2
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < FLAGS16_THREADS / 32; ++k) t += s_cnt[k];
+    tile_counts[blockIdx.x] = t;
+  }
+}
+
 // sequential replay for left-anchored components; one warp per image row that holds a root
 // in column 0.  `hole_traced` is a zero-initialised byte per pixel (indexed by bg root).
 __global__ void __launch_bounds__(128) contour_anchored_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels,
                                                                int H, int W, int B, const uint8_t *__restrict__ bg_open,
                                                                const int4 *__restrict__ anchored_bbox, const int *__restrict__ need_anchored,
-                                                               uint8_t *__restrict__ hole_traced, uint8_t *__restrict__ flags) {
+                                                               uint8_t *__restrict__ hole_traced, uint8_t *__restrict__ flags,
+                                                               int *__restrict__ tile_counts /* per-SCAN_TILE start counts to keep current, or null */) {
   if (*need_anchored == 0) return;
   const int lane = threadIdx.x & 31;
   int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -194,13 +257,19 @@ __global__ void __launch_bounds__(128) contour_anchored_kernel(const uint8_t *__
         if (has_w && !visited) {
           if (lab[0] == -1) traced_inf = true;
           else if (lane == 0) traced[lab[0]] = 1;
-          if (lane == 0) fl[q] = START_OUTER;
+          if (lane == 0) {
+            fl[q] = START_OUTER;  // anchored starts only ever land on pixels the closed-form pass left at NONE
+            if (tile_counts) atomicAdd(&tile_counts[(b * HW + q) / SCAN_TILE], 1);
+          }
         } else if (has_e) {
           bool e_traced = lab[1] == -1 ? traced_inf : (traced[lab[1]] != 0);
           if (!e_traced) {
             if (lab[1] == -1) traced_inf = true;
             else if (lane == 0) traced[lab[1]] = 1;
-            if (lane == 0) fl[q] = START_HOLE;
+            if (lane == 0) {
+              fl[q] = START_HOLE;
+              if (tile_counts) atomicAdd(&tile_counts[(b * HW + q) / SCAN_TILE], 1);
+            }
           }
         }
         __syncwarp();
@@ -215,6 +284,8 @@ __global__ void __launch_bounds__(128) contour_anchored_kernel(const uint8_t *__
 __global__ void __launch_bounds__(SCAN_THREADS) contour_records_kernel(const uint8_t *__restrict__ flags, const int *__restrict__ tile_offs,
                                                                        int64_t n, int64_t *__restrict__ start_idx, uint8_t *__restrict__ kind) {
   __shared__ int smem[33];
+  // exclusive tile offsets with the grand total in the slot after the last tile: an empty tile (most of a page) is skipped unread
+  if (tile_offs[blockIdx.x + 1] == tile_offs[blockIdx.x]) return;
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   uint8_t f[SCAN_ITEMS];
   int s = 0;
@@ -394,7 +465,8 @@ __global__ void approx_dp_kernel(const ushort2 *__restrict__ chain, const int64_
 // ---------------------------------------------------------------------------------------
 int launch_contour_starts(ocrb_ctx *ctx, const uint8_t *bitmap, const int *labels, int B, int H, int W,
                           uint8_t *bg_open /*B*HW, zeroed here*/, uint8_t *hole_traced /*B*HW, zeroed here*/,
-                          int4 *anchored_bbox /*B*H*/, uint8_t *flags /*B*HW*/, int *need_anchored /*device int*/) {
+                          int4 *anchored_bbox /*B*H*/, uint8_t *flags /*B*HW*/, int *need_anchored /*device int*/,
+                          int *tile_counts /* cdiv(B*HW, SCAN_TILE) ints: start flags per scan tile */) {
   int64_t n = (int64_t)B * H * W;
   OCRB_CUDA(cudaMemsetAsync(bg_open, 0, n, ctx->stream));
   OCRB_CUDA(cudaMemsetAsync(hole_traced, 0, n, ctx->stream));
@@ -404,23 +476,31 @@ int launch_contour_starts(ocrb_ctx *ctx, const uint8_t *bitmap, const int *label
   OCRB_TRY(check_launch(ctx, "contour_frame"));
   contour_props_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, need_anchored, anchored_bbox);
   OCRB_TRY(check_launch(ctx, "contour_props"));
-  if (W % 4 == 0)
+  const bool counted = W % 16 == 0;  // the flags kernel counts per tile itself
+  if (counted)
+    contour_start_flags_vec16_kernel<<<(unsigned)cdiv(n, SCAN_TILE), FLAGS16_THREADS, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, flags,
+                                                                                                       tile_counts);
+  else if (W % 4 == 0)
     contour_start_flags_vec4_kernel<<<(unsigned)cdiv(n / 4, 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, flags);
   else
     contour_start_flags_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, flags);
   OCRB_TRY(check_launch(ctx, "contour_start_flags"));
   int64_t warps = (int64_t)B * H;
   contour_anchored_kernel<<<(unsigned)cdiv(warps * 32, 128), 128, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open,
-                                                                                    anchored_bbox, need_anchored, hole_traced, flags);
-  return check_launch(ctx, "contour_anchored");
+                                                                                    anchored_bbox, need_anchored, hole_traced, flags,
+                                                                                    counted ? tile_counts : nullptr);
+  OCRB_TRY(check_launch(ctx, "contour_anchored"));
+  if (!counted) {
+    scan_tile_reduce_kernel<uint8_t, int, ScanNonZero><<<(unsigned)cdiv(n, SCAN_TILE), SCAN_THREADS, 0, ctx->stream>>>(flags, n, tile_counts);
+    OCRB_TRY(check_launch(ctx, "scan_tile_reduce"));
+  }
+  return OCRB_OK;
 }
 
-// phase 1: per-tile counts of the start flags and their exclusive scan; tile_offs must hold
+// phase 1: exclusive scan of the per-tile start counts left by launch_contour_starts; tile_offs must hold
 // scan_scratch_elems(n) * 2 ints.  The total lands at tile_offs[tiles] (see contour_count_slot).
-int launch_contour_count(ocrb_ctx *ctx, const uint8_t *flags, int64_t n, int *tile_offs) {
+int launch_contour_count(ocrb_ctx *ctx, int64_t n, int *tile_offs) {
   const int64_t tiles = cdiv(n, SCAN_TILE);
-  scan_tile_reduce_kernel<uint8_t, int, ScanNonZero><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(flags, n, tile_offs);
-  OCRB_TRY(check_launch(ctx, "scan_tile_reduce"));
   int *lvl2 = tile_offs + tiles + 8;
   return exclusive_scan<int, int, ScanIdentity>(ctx, tile_offs, tiles, tile_offs, lvl2);
 }

@@ -14,9 +14,9 @@ namespace ocrb {
 // kernels / launchers defined in the other translation units
 int launch_binarize(ocrb_ctx *, const float *, int64_t, float, uint8_t *);
 int launch_ccl(ocrb_ctx *, const uint8_t *, int, int, int, int *, bool);
-int launch_contour_starts(ocrb_ctx *, const uint8_t *, const int *, int, int, int, uint8_t *, uint8_t *, int4 *, uint8_t *, int *);
+int launch_contour_starts(ocrb_ctx *, const uint8_t *, const int *, int, int, int, uint8_t *, uint8_t *, int4 *, uint8_t *, int *, int *);
 int launch_contour_records(ocrb_ctx *, const uint8_t *, const int *, int64_t, int64_t *, uint8_t *);
-int launch_contour_count(ocrb_ctx *, const uint8_t *, int64_t, int *);
+int launch_contour_count(ocrb_ctx *, int64_t, int *);
 int64_t contour_count_slot(int64_t);
 int launch_trace_count(ocrb_ctx *, const uint8_t *, int, int, const int64_t *, const uint8_t *, int64_t, int *);
 int launch_trace_store(ocrb_ctx *, const uint8_t *, int, int, const int64_t *, const uint8_t *, int64_t, const int64_t *, ushort2 *);
@@ -106,8 +106,8 @@ static int run_contour_stage(ocrb_ctx *ctx, PostprocWorkspace *ws, const uint8_t
   OCRB_TRY(launch_ccl(ctx, bitmap, B, H, W, ws->labels.as<int>(), false));
   OCRB_TRY(launch_contour_starts(ctx, bitmap, ws->labels.as<int>(), B, H, W, ws->bg_open.as<uint8_t>(),
                                  ws->hole_traced.as<uint8_t>(), ws->bbox.as<int4>(), ws->flags.as<uint8_t>(),
-                                 reinterpret_cast<int *>(ws->bbox.as<int4>() + (size_t)B * H)));
-  OCRB_TRY(launch_contour_count(ctx, ws->flags.as<uint8_t>(), n, ws->offs.as<int>()));
+                                 reinterpret_cast<int *>(ws->bbox.as<int4>() + (size_t)B * H), ws->offs.as<int>()));
+  OCRB_TRY(launch_contour_count(ctx, n, ws->offs.as<int>()));
   int nc32 = 0;
   OCRB_TRY(read_scalar(ctx, ws->offs.as<int>() + contour_count_slot(n), &nc32));
   const int64_t nc = nc32;
