@@ -249,32 +249,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE);
         float o[2][4];
+        {
+          // both taps of this warp half go through the channel loop together: every BN / conv-transpose-2 constant
+          // (a uniform-register load per use) serves two taps, and eight independent accumulator chains hide the FMA latency.
+          // packed fp32x2 FMAs (FFMA2): two channels at a time through BN, two outputs at a time through the 64 -> 4 contraction
+          float2 z01[2], z23[2];
 #pragma unroll
-        for (int tj = 0; tj < 2; ++tj) {
-          const int tap = half * 2 + tj;  // tap = i*2 + j with i = half
-          // packed fp32x2 FMAs (FFMA2): two channels at a time through BN, two outputs at a time
-          // through the 64 -> 4 contraction; hc.* are constant-bank operands after unrolling
-          float2 z01 = make_float2(p.b2, p.b2), z23 = make_float2(p.b2, p.b2);
+          for (int tj = 0; tj < 2; ++tj) { z01[tj] = make_float2(p.b2, p.b2); z23[tj] = make_float2(p.b2, p.b2); }
 #pragma unroll
           for (int c0 = 0; c0 < 64; c0 += 32) {
-            float v[32];
-            tmem_ld32(taddr + tap * 64 + c0, v);
+            float v[2][32];
+            tmem_ld32(taddr + (half * 2 + 0) * 64 + c0, v[0]);  // tap = i*2 + j with i = half
+            tmem_ld32(taddr + (half * 2 + 1) * 64 + c0, v[1]);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const int co = c0 + j;
-              const float2 h = ffma2(make_float2(v[j], v[j + 1]), make_float2(hc.scale[co], hc.scale[co + 1]),
-                                     make_float2(hc.shift[co], hc.shift[co + 1]));
-              const float h0 = fmaxf(h.x, 0.0f), h1 = fmaxf(h.y, 0.0f);
-              z01 = ffma2(make_float2(h0, h0), make_float2(hc.w2[co * 4 + 0], hc.w2[co * 4 + 1]), z01);
-              z23 = ffma2(make_float2(h0, h0), make_float2(hc.w2[co * 4 + 2], hc.w2[co * 4 + 3]), z23);
-              z01 = ffma2(make_float2(h1, h1), make_float2(hc.w2[co * 4 + 4], hc.w2[co * 4 + 5]), z01);
-              z23 = ffma2(make_float2(h1, h1), make_float2(hc.w2[co * 4 + 6], hc.w2[co * 4 + 7]), z23);
+              const float2 sc = make_float2(hc.scale[co], hc.scale[co + 1]), sh = make_float2(hc.shift[co], hc.shift[co + 1]);
+              const float2 wa01 = make_float2(hc.w2[co * 4 + 0], hc.w2[co * 4 + 1]), wa23 = make_float2(hc.w2[co * 4 + 2], hc.w2[co * 4 + 3]);
+              const float2 wb01 = make_float2(hc.w2[co * 4 + 4], hc.w2[co * 4 + 5]), wb23 = make_float2(hc.w2[co * 4 + 6], hc.w2[co * 4 + 7]);
+#pragma unroll
+              for (int tj = 0; tj < 2; ++tj) {
+                const float2 h = ffma2(make_float2(v[tj][j], v[tj][j + 1]), sc, sh);
+                const float h0 = fmaxf(h.x, 0.0f), h1 = fmaxf(h.y, 0.0f);
+                z01[tj] = ffma2(make_float2(h0, h0), wa01, z01[tj]);
+                z23[tj] = ffma2(make_float2(h0, h0), wa23, z23[tj]);
+                z01[tj] = ffma2(make_float2(h1, h1), wb01, z01[tj]);
+                z23[tj] = ffma2(make_float2(h1, h1), wb23, z23[tj]);
+              }
             }
           }
-          const float z[4] = {z01.x, z01.y, z23.x, z23.y};
-          // q = i'*2 + j' of conv-transpose 2: output (4y + 2i + i', 4x + 2j + j')
 #pragma unroll
-          for (int q = 0; q < 4; ++q) o[q >> 1][2 * tj + (q & 1)] = 1.0f / (1.0f + expf(-z[q]));
+          for (int tj = 0; tj < 2; ++tj) {
+            const float z[4] = {z01[tj].x, z01[tj].y, z23[tj].x, z23[tj].y};
+            // q = i'*2 + j' of conv-transpose 2: output (4y + 2i + i', 4x + 2j + j')
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q >> 1][2 * tj + (q & 1)] = 1.0f / (1.0f + expf(-z[q]));
+          }
         }
         if (valid) {
           const int64_t Wp = (int64_t)p.Wo * 4;

@@ -155,3 +155,33 @@ def test_pipeline_sharding_invariance(env):
         for p, q in zip(one.polygons[0], whole.polygons[i]):
             assert (p == q).all()
     assert sum(len(p) for p in whole.polygons) > 0
+
+
+def test_config4_full_size_shard_invariance(env):
+    """BASELINE config 4 at full size (1024 images 800x800, the bench workload): one call over the whole
+    range == the concatenation of 8 contiguous shards of 128 (what 8 ranks compute) == single-image calls
+    at sampled indices; recognised glyph classes do not depend on the call either."""
+    _ffi, synth, Net, resnet18, _, _ = env
+    B, H, W = 1024, 800, 800
+    wd = synth.make_detector_weights(0, "structured")
+    imgs = synth.document_image_shard(0, B, H, W)
+    glyphs = synth.make_glyphs(64, 1, "strokes")
+    adj = np.ones((B, 2))
+    det, rec = resnet18(wd, "bf16"), Net(synth.make_rec_weights(1))
+    whole, am = _run_pipeline(_ffi, det, rec, imgs, adj, glyphs)
+    parts = []
+    for r in range(8):
+        p, am_r = _run_pipeline(_ffi, det, rec, imgs[r * 128:(r + 1) * 128], adj[r * 128:(r + 1) * 128], glyphs)
+        parts.append(p)
+        assert (am_r == am).all()
+    both = _ffi.Polygons.concat(parts)
+    for x, y in zip(whole.arrays(), both.arrays()):
+        assert x.shape == y.shape and (x == y).all()
+    for i in (0, 127, 128, 500, 1023):
+        one, _ = _run_pipeline(_ffi, det, rec, imgs[i:i + 1], adj[i:i + 1], glyphs)
+        assert len(one.polygons[0]) == len(whole.polygons[i])
+        for p, q in zip(one.polygons[0], whole.polygons[i]):
+            assert (p == q).all()
+    n = sum(len(p) for p in whole.polygons)
+    print(f"config 4 full size: {n} polygons over {B} images")
+    assert n > 10000
