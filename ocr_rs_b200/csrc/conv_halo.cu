@@ -148,6 +148,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
         if (++as == g.a_stages) { as = 0; aph ^= 1; }
         for (int tap = 0; tap < 9; ++tap) {
+          if (!((p.tap_mask >> tap) & 1)) continue;
           mbar_wait(&b_empty[bs], bph ^ 1, p.err, 12);
           if (elect_one()) {
             if (CG == 2) {
@@ -201,6 +202,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int g0 = (warp - 1) * GW;  // first sub-tile of this warp
       int as = 0, bs = 0, acc = 0;
       uint32_t aph = 0, bph = 0, acc_phase = 0;
+      const int first_tap = __ffs(p.tap_mask) - 1, last_tap = 31 - __clz(p.tap_mask);
       for (int unit = unit0; unit < num_units; unit += unit_step) {
         mbar_wait(&tempty[acc], acc_phase ^ 1, p.err, 13);
         tc_fence_after();
@@ -210,12 +212,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // start address advances by whole 128 B rows: (gi*128 + row_off) * 128 B >> 4
           const uint64_t a0 = make_smem_desc(sA + as * g.a_stage_bytes) + (uint64_t)(g0 * g.sub_stride * 8);
           for (int tap = 0; tap < 9; ++tap) {
+            if (!((p.tap_mask >> tap) & 1)) continue;
             mbar_wait(&b_full[bs], bph, p.err, 15);
             tc_fence_after();
             const int r = tap / 3, s = tap - 3 * r;
             const uint64_t bdesc = make_smem_desc(sB + bs * B_BYTES);
             const uint64_t at = a0 + (uint64_t)((r * g.PW + s) * 8);
-            const uint32_t first = (ck | tap) != 0 ? 1u : 0u;
+            const uint32_t first = (ck != 0 || tap != first_tap) ? 1u : 0u;
             if (elect_one()) {
 #pragma unroll
               for (int gi = 0; gi < GW; ++gi) {
@@ -231,13 +234,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               if (CG == 2) {
                 umma_commit_2sm(&b_empty[bs]);
-                if (tap == 8) {
+                if (tap == last_tap) {
                   umma_commit_2sm(&a_empty[as]);
                   if (ck == chunks - 1 && p.ds_chunks == 0) umma_commit_2sm(&tfull[acc]);
                 }
               } else {
                 umma_commit(&b_empty[bs]);
-                if (tap == 8) {
+                if (tap == last_tap) {
                   umma_commit(&a_empty[as]);
                   if (ck == chunks - 1 && p.ds_chunks == 0) umma_commit(&tfull[acc]);
                 }
@@ -565,7 +568,7 @@ int halo_geometry(int Ho, int Wo, int n_tile, int G, int ts, HaloGeom *out) {  /
 }
 
 int make_act_tensor_map_box(CUtensorMap *map, const void *base, int B, int H, int W, int C, int box_w, int box_h);
-int make_act_tensor_map_pitched(CUtensorMap *map, const void *base, int B, int H, int W, int C, int ldc, int box_w, int box_h);
+int make_act_tensor_map_pitched(CUtensorMap *map, const void *base, int B, int H, int W, int C, int ldc, int box_w, int box_h, int step = 1);
 
 
 template <int N_TILE, int G, int CG, int TS>
@@ -632,6 +635,9 @@ int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &t
   if (p.Cout % n_tile != 0 || p.Cout > 512) { set_error("conv_halo: Cout %d vs N tile %d", p.Cout, n_tile); return OCRB_ERR_INVALID; }
   const int G = n_tile == 64 ? 4 : 2, CG = halo_cg();
   const int ts = halo_use_ts(n_tile, p.rep);
+  if (!ts && (p.out_step != 1 || (p.tap_mask & 0x1ff) != 0x1ff)) { set_error("conv_halo: tap mask / output step need the TMA-store path"); return OCRB_ERR_INVALID; }
+  if ((p.tap_mask & 0x1ff) == 0) { set_error("conv_halo: empty tap mask"); return OCRB_ERR_INVALID; }
+  p.tap_mask &= 0x1ff;
   if (ts && p.ds_chunks) { set_error("conv_halo: fused downsample with 64-channel tiles"); return OCRB_ERR_INVALID; }
   HaloGeom g;
   OCRB_TRY(halo_geometry(p.Ho, p.Wo, n_tile / CG, G, ts, &g));
@@ -642,7 +648,7 @@ int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &t
   if (ts) {
     // output slice [B][Ho][Wo][Cout] at channel offset out_coff of an out_ldc-wide buffer; residual [B][Ho][Wo][Cout]
     CUtensorMap tmO, tmR;
-    OCRB_TRY(make_act_tensor_map_pitched(&tmO, p.out + p.out_coff, p.B, p.Ho, p.Wo, p.Cout, p.out_ldc, g.TW, g.sub_rows));
+    OCRB_TRY(make_act_tensor_map_pitched(&tmO, p.out + p.out_coff, p.B, p.Ho, p.Wo, p.Cout, p.out_ldc, g.TW, g.sub_rows, p.out_step));
     if (p.residual) OCRB_TRY(make_act_tensor_map_pitched(&tmR, p.residual, p.B, p.Ho, p.Wo, p.Cout, p.Cout, g.TW, g.sub_rows));
     else tmR = tmO;
     return CG == 2 ? launch_halo_one<64, 4, 2, 1>(ctx, tmA, tmB, tmD, tmO, tmR, p, g, num_units, tag)

@@ -25,6 +25,10 @@ struct ConvTcParams {
   int relu = 0;
   __nv_bfloat16 *out = nullptr;             // [B][Ho*rep][Wo*rep][out_ldc], channel offset out_coff
   int out_ldc = 0, out_coff = 0, rep = 1;
+  // conv_halo TMA-store path only: 3x3 taps actually present (bit r*3+s; absent taps are skipped, their weights
+  // never read) and the pixel step of the output (2: results land on every second pixel / row of a map twice
+  // as large — `out` then points at the first of them)
+  int tap_mask = 0x1ff, out_step = 1;
   const __nv_bfloat16 *up_src = nullptr;    // [B][Ho/2][Wo/2][Cout]
   __nv_bfloat16 *sum_out = nullptr;         // [B][Ho][Wo][Cout] = y + up2(up_src)
   // DB head tail
@@ -49,6 +53,7 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
 
 // conv_halo.cu: 3x3 stride-1 convolutions with the halo'd input tile resident in shared memory
 int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G, int rep);
+bool halo_use_ts(int n_tile, int rep);  // TMA-store epilogue in use for this tile shape
 int halo_weight_box_rows(int n_tile);  // rows of the weight TMA box (half the N tile in CTA-pair mode)
 int make_halo_ds_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int Ho, int Wo, int n_tile, int G);
 int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, ConvTcParams p, int n_tile, const char *tag,

@@ -144,6 +144,7 @@ struct DevConv {
   int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
   bool has_bn = false;
   int ds_cin = 0;  // > 0: w16 carries a fused 1x1 stride-2 downsample of ds_cin channels after the 9 taps
+  int tap_mask = 0x1ff;  // 3x3 taps with non-zero weights (class kernels of the fused FPN level use 4 of 9)
   DevBuf w32;    // fp32 [k*k][cin][cout]
   DevBuf w16;    // bf16 [cout][k*k*cin]
   DevBuf scale, shift;
@@ -243,6 +244,65 @@ static int prep_fused_downsample(const HostWeights &hw, const std::string &p, in
   return OCRB_OK;
 }
 
+// FPN level 2 without its 256-channel intermediate (model.rs:126-129, BF16 mode):
+//   p2 = out2(up2(in3) + in2(x1)),  in2 = 1x1 conv without bias, out2 = 3x3 conv without bias, zero padding
+//      = conv3x3(W_out2 o W_in2)(x1)  +  conv3x3(W_out2)(up2(in3))
+// * the first term is a 64 -> 64 3x3 convolution of x1 with the composed weights (K = 576 instead of 2304);
+// * the second, a 3x3 convolution of a nearest-upsampled map, is for each output parity class (a, b) = (y & 1, x & 1)
+//   a 2x2 convolution of the half-resolution lateral itself: row offsets {-1, 0} carry W[-1], W[0]+W[1] for even y and
+//   {0, +1} carry W[-1]+W[0], W[1] for odd y (same for columns) — four 4-tap convolutions at 100 x 100 whose results are
+//   stored pixel-shuffled (class (a,b) of low-res pixel (Y,X) at (2Y+a, 2X+b)) into one 64-channel map that the first
+//   convolution adds as a residual.  Zero padding maps to zero padding, so borders are exact.
+// 13.1 -> 8.2 GFLOP per image for this level and s2 (20 MB per image written and re-read) never exists.
+static void compose_weights(const std::vector<float> &w_out /*[co][m][3][3]*/, const std::vector<float> &w_in /*[m][ci]*/, int co_n, int m_n,
+                            int ci_n, std::vector<float> &wc /*[co][ci][3][3]*/) {
+  wc.assign((size_t)co_n * ci_n * 9, 0.0f);
+  std::vector<double> acc((size_t)ci_n);
+  for (int co = 0; co < co_n; ++co)
+    for (int tp = 0; tp < 9; ++tp) {
+      std::fill(acc.begin(), acc.end(), 0.0);
+      for (int m = 0; m < m_n; ++m) {
+        const double wo = w_out[((size_t)co * m_n + m) * 9 + tp];
+        const float *wi = &w_in[(size_t)m * ci_n];
+        for (int ci = 0; ci < ci_n; ++ci) acc[ci] += wo * wi[ci];
+      }
+      for (int ci = 0; ci < ci_n; ++ci) wc[((size_t)co * ci_n + ci) * 9 + tp] = (float)acc[ci];
+    }
+}
+
+// OIHW fp32 -> DevConv (bf16 K-major rows [co][tap][ci]) for a bias-free, BN-free 3x3 convolution
+static int upload_plain_conv3(const std::vector<float> &w, int cin, int cout, int tap_mask, DevConv &dc) {
+  dc.cin = cin; dc.cout = cout; dc.k = 3; dc.stride = 1; dc.pad = 1; dc.has_bn = false; dc.tap_mask = tap_mask;
+  std::vector<uint16_t> w16((size_t)cout * 9 * cin);
+  for (int co = 0; co < cout; ++co)
+    for (int tp = 0; tp < 9; ++tp)
+      for (int ci = 0; ci < cin; ++ci) w16[((size_t)co * 9 + tp) * cin + ci] = f2bf(w[((size_t)co * cin + ci) * 9 + tp]);
+  return upload(dc.w16, w16);
+}
+
+static int prep_fused_fpn2(const HostWeights &hw, std::map<std::string, DevConv> &conv) {
+  const auto *wo = hw.get("out2.weight"), *wi = hw.get("in2.weight");
+  OCRB_REQUIRE(wo && wi && wo->size() == (size_t)64 * 256 * 9 && wi->size() == (size_t)256 * 64, "missing / mis-shaped in2 / out2 weights");
+  std::vector<float> wc;
+  compose_weights(*wo, *wi, 64, 256, 64, wc);
+  OCRB_TRY(upload_plain_conv3(wc, 64, 64, 0x1ff, conv["out2.x1"]));
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      // low-res tap r' (row offset r' - 1) collects the full-res taps dy whose source row (2Y + a + dy) >> 1 is Y + r' - 1
+      std::vector<float> wk((size_t)64 * 256 * 9, 0.0f);
+      int mask = 0;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int rr = ((a + dy) >> 1) + 1, ss = ((b + dx) >> 1) + 1;  // arithmetic shift = floor
+          mask |= 1 << (rr * 3 + ss);
+          for (int co = 0; co < 64; ++co)
+            for (int m = 0; m < 256; ++m) wk[((size_t)co * 256 + m) * 9 + rr * 3 + ss] += (*wo)[((size_t)co * 256 + m) * 9 + (dy + 1) * 3 + dx + 1];
+        }
+      OCRB_TRY(upload_plain_conv3(wk, 256, 64, mask, conv["out2.up" + std::to_string(a) + std::to_string(b)]));
+    }
+  return OCRB_OK;
+}
+
 }  // namespace ocrb
 
 using namespace ocrb;
@@ -266,6 +326,7 @@ struct ocrb_det {
   DevBuf staged_in, staged_out, err;
   // last forward (for taps)
   int last_B = 0, last_H = 0, last_W = 0;
+  bool fpn2_fused = false;  // BF16 mode: level 2 of the FPN computed from x1 and in3 directly (prep_fused_fpn2)
   // tensor-map cache
   struct Maps { int B = 0, H = 0, W = 0; std::map<std::string, CUtensorMap> m; } maps;
 };
@@ -317,6 +378,14 @@ static int det_build(ocrb_det *d, const HostWeights &hw) {
   OCRB_TRY(prep_conv(hw, {"in2", "", 64, 256, 1, 1, 0}, bf, d->conv["in2"]));
   for (const char *n : {"out5", "out4", "out3", "out2"}) OCRB_TRY(prep_conv(hw, {n, "", 256, 64, 3, 1, 1}, bf, d->conv[n]));
   OCRB_TRY(prep_conv(hw, {"bin_conv1", "bin_bn1", 256, 64, 3, 1, 1}, bf, d->conv["bin_conv1"]));
+  {
+    static const bool fuse_fpn2 = !(getenv("OCRB_FUSE_FPN2") && atoi(getenv("OCRB_FUSE_FPN2")) == 0);  // tuning / bisecting knob
+    static const bool halo_on = !(getenv("OCRB_CONV") && strcmp(getenv("OCRB_CONV"), "tc") == 0);
+    if (bf && fuse_fpn2 && halo_on && halo_use_ts(64, 1)) {
+      OCRB_TRY(prep_fused_fpn2(hw, d->conv));
+      d->fpn2_fused = true;
+    }
+  }
   // head: conv-transpose weights are [in][out][kh][kw]
   {
     const auto *w1 = hw.get("bin_conv_tr1.weight"), *b1 = hw.get("bin_conv_tr1.bias");
@@ -496,6 +565,8 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
   OCRB_TRY(act(d, "b.s2", (int64_t)B * fh[0] * fw[0] * 256, &s2));
   OCRB_TRY(act(d, "b.fuse", (int64_t)B * H4 * W4 * 256, &fuse));
   OCRB_TRY(act(d, "b.bin1", (int64_t)B * H4 * W4 * 64, &b1));
+  bf *up2 = nullptr;  // fused FPN level 2: out2's share of up2(in3), pixel-shuffled, [B][H4][W4][64]
+  if (d->fpn2_fused) OCRB_TRY(act(d, "b.up2", (int64_t)B * H4 * W4 * 64, &up2));
   for (auto &kv : d->act) after += kv.second.cap;
   if (after != before || d->maps.B != B || d->maps.H != H || d->maps.W != W) {
     d->maps.m.clear();  // some buffer moved or the shape changed: rebuild the descriptors
@@ -552,6 +623,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     p.R = c.k; p.S = c.k; p.cin_chunks = c.cin / 64; p.stride = c.stride; p.pad = c.pad;
     p.scale = c.has_bn ? c.scale.as<float>() : nullptr;  // no batch-norm: identity epilogue
     p.shift = c.has_bn ? c.shift.as<float>() : nullptr;
+    p.tap_mask = c.tap_mask;
     p.scale_host = c.has_bn && !c.scale_h.empty() ? c.scale_h.data() : nullptr;
     p.shift_host = c.has_bn && !c.shift_h.empty() ? c.shift_h.data() : nullptr;
     if (p.out && p.out_ldc == 0) p.out_ldc = c.cout;
@@ -596,8 +668,10 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     OCRB_TRY(conv("in4", feat[2], fh[2], fw[2], q));
     q = ConvTcParams(); q.out = in3; q.up_src = in4; q.sum_out = s3;
     OCRB_TRY(conv("in3", feat[1], fh[1], fw[1], q));
-    q = ConvTcParams(); q.out = nullptr; q.up_src = in3; q.sum_out = s2;
-    OCRB_TRY(conv("in2", feat[0], fh[0], fw[0], q));
+    if (!d->fpn2_fused) {
+      q = ConvTcParams(); q.out = nullptr; q.up_src = in3; q.sum_out = s2;
+      OCRB_TRY(conv("in2", feat[0], fh[0], fw[0], q));
+    }
   }
   {  // out convs write their (replicated) result into the concat buffer: cat([p5,p4,p3,p2], 1)
     ConvTcParams q;
@@ -608,7 +682,19 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     q.out_coff = 128; q.rep = 2;
     OCRB_TRY(conv("out3", s3, fh[1], fw[1], q));
     q.out_coff = 192; q.rep = 1;
-    OCRB_TRY(conv("out2", s2, fh[0], fw[0], q));
+    if (!d->fpn2_fused) {
+      OCRB_TRY(conv("out2", s2, fh[0], fw[0], q));
+    } else {
+      // p2 = conv3x3(W_out2 o W_in2)(x1) + [four 2x2 class convolutions of in3, pixel-shuffled into up2] (see prep_fused_fpn2)
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          ConvTcParams k;
+          k.out = up2 + ((int64_t)a * fw[0] + b) * 64; k.out_ldc = 64; k.out_step = 2;
+          OCRB_TRY(conv("out2.up" + std::to_string(a) + std::to_string(b), in3, fh[1], fw[1], k));
+        }
+      q.residual = up2;
+      OCRB_TRY(conv("out2.x1", feat[0], fh[0], fw[0], q));
+    }
   }
   {
     ConvTcParams q;
