@@ -114,6 +114,19 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_bf16_kernel(const TIn *
   }
 }
 
+// test tap "fuse" when p3 lives outside the concat buffer: rebuild cat[p5^8, p4^4, p3^2, p2] as NCHW fp32
+__global__ void fuse_tap_kernel(const __nv_bfloat16 *__restrict__ fuse192, const __nv_bfloat16 *__restrict__ p3, int B, int H, int W,
+                                float *__restrict__ out) {
+  const int64_t n = (int64_t)B * 256 * H * W;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((int64_t)W * H)) % 256), b = (int)(i / ((int64_t)W * H * 256));
+  float v;
+  if (c >= 128 && c < 192) v = __bfloat162float(p3[(((int64_t)b * (H / 2) + y / 2) * (W / 2) + x / 2) * 64 + (c - 128)]);
+  else v = __bfloat162float(fuse192[(((int64_t)b * H + y) * W + x) * 192 + (c < 128 ? c : c - 64)]);
+  out[i] = v;
+}
+
 __global__ void bf16_nhwc_to_nchw_f32_kernel(const __nv_bfloat16 *__restrict__ in, int B, int H, int W, int C, int ldc,
                                              float *__restrict__ out) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -303,6 +316,46 @@ static int prep_fused_fpn2(const HostWeights &hw, std::map<std::string, DevConv>
   return OCRB_OK;
 }
 
+// The same parity-class identity takes p3 out of the concat buffer (model.rs:140-143): bin_conv1(cat[p5^8, p4^4, p3^2, p2])
+//   = conv3x3(W_bin[:, p5|p4|p2 channels])(cat[p5^8, p4^4, p2])  +  conv3x3(W_bin[:, p3 channels])(up2(p3)),
+// the second term again four 4-tap class convolutions at 100 x 100 (K = 256), stored pixel-shuffled and added as a
+// residual.  bin_bn1 multiplies the whole sum, so its scale is folded into the class weights (the residual joins after
+// the main convolution's scale / shift).  out3 then writes p3 once at its own resolution instead of 2 x 2 replicated.
+static int prep_fused_bin_p3(const HostWeights &hw, std::map<std::string, DevConv> &conv) {
+  const auto *wb = hw.get("bin_conv1.weight");
+  OCRB_REQUIRE(wb && wb->size() == (size_t)64 * 256 * 9, "missing / mis-shaped bin_conv1 weights");
+  std::vector<float> sc, sh;
+  OCRB_TRY(fold_bn(hw, "bin_bn1", 64, nullptr, sc, sh));
+  // main part: input channels [p5 | p4 | p2] = reference channels 0..127 and 192..255
+  std::vector<float> wm((size_t)64 * 192 * 9);
+  for (int co = 0; co < 64; ++co)
+    for (int ci = 0; ci < 192; ++ci) {
+      const int src = ci < 128 ? ci : ci + 64;
+      for (int tp = 0; tp < 9; ++tp) wm[((size_t)co * 192 + ci) * 9 + tp] = (*wb)[((size_t)co * 256 + src) * 9 + tp];
+    }
+  DevConv &m = conv["bin_conv1.main"];
+  OCRB_TRY(upload_plain_conv3(wm, 192, 64, 0x1ff, m));
+  m.has_bn = true;
+  OCRB_TRY(upload(m.scale, sc));
+  OCRB_TRY(upload(m.shift, sh));
+  m.scale_h = sc; m.shift_h = sh;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      std::vector<float> wk((size_t)64 * 64 * 9, 0.0f);
+      int mask = 0;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int rr = ((a + dy) >> 1) + 1, ss = ((b + dx) >> 1) + 1;
+          mask |= 1 << (rr * 3 + ss);
+          for (int co = 0; co < 64; ++co)
+            for (int ci = 0; ci < 64; ++ci)
+              wk[((size_t)co * 64 + ci) * 9 + rr * 3 + ss] += sc[co] * (*wb)[((size_t)co * 256 + 128 + ci) * 9 + (dy + 1) * 3 + dx + 1];
+        }
+      OCRB_TRY(upload_plain_conv3(wk, 64, 64, mask, conv["bin_conv1.up" + std::to_string(a) + std::to_string(b)]));
+    }
+  return OCRB_OK;
+}
+
 }  // namespace ocrb
 
 using namespace ocrb;
@@ -326,7 +379,9 @@ struct ocrb_det {
   DevBuf staged_in, staged_out, err;
   // last forward (for taps)
   int last_B = 0, last_H = 0, last_W = 0;
-  bool fpn2_fused = false;  // BF16 mode: level 2 of the FPN computed from x1 and in3 directly (prep_fused_fpn2)
+  // BF16 mode: level 2 of the FPN computed from x1 and in3 directly (prep_fused_fpn2) and p3 kept out of the concat
+  // buffer (prep_fused_bin_p3): "b.fuse" is then [B][H/4][W/4][192] = [p5^8 | p4^4 | p2], "b.p3" [B][H/8][W/8][64]
+  bool fpn2_fused = false;
   // tensor-map cache
   struct Maps { int B = 0, H = 0, W = 0; std::map<std::string, CUtensorMap> m; } maps;
 };
@@ -383,6 +438,7 @@ static int det_build(ocrb_det *d, const HostWeights &hw) {
     static const bool halo_on = !(getenv("OCRB_CONV") && strcmp(getenv("OCRB_CONV"), "tc") == 0);
     if (bf && fuse_fpn2 && halo_on && halo_use_ts(64, 1)) {
       OCRB_TRY(prep_fused_fpn2(hw, d->conv));
+      OCRB_TRY(prep_fused_bin_p3(hw, d->conv));
       d->fpn2_fused = true;
     }
   }
@@ -563,10 +619,15 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
   OCRB_TRY(act(d, "b.s4", (int64_t)B * fh[2] * fw[2] * 256, &s4));
   OCRB_TRY(act(d, "b.s3", (int64_t)B * fh[1] * fw[1] * 256, &s3));
   OCRB_TRY(act(d, "b.s2", (int64_t)B * fh[0] * fw[0] * 256, &s2));
-  OCRB_TRY(act(d, "b.fuse", (int64_t)B * H4 * W4 * 256, &fuse));
+  const int fuse_c = d->fpn2_fused ? 192 : 256;
+  OCRB_TRY(act(d, "b.fuse", (int64_t)B * H4 * W4 * fuse_c, &fuse));
   OCRB_TRY(act(d, "b.bin1", (int64_t)B * H4 * W4 * 64, &b1));
   bf *up2 = nullptr;  // fused FPN level 2: out2's share of up2(in3), pixel-shuffled, [B][H4][W4][64]
-  if (d->fpn2_fused) OCRB_TRY(act(d, "b.up2", (int64_t)B * H4 * W4 * 64, &up2));
+  bf *p3 = nullptr;
+  if (d->fpn2_fused) {
+    OCRB_TRY(act(d, "b.up2", (int64_t)B * H4 * W4 * 64, &up2));
+    OCRB_TRY(act(d, "b.p3", (int64_t)B * fh[1] * fw[1] * 64, &p3));
+  }
   for (auto &kv : d->act) after += kv.second.cap;
   if (after != before || d->maps.B != B || d->maps.H != H || d->maps.W != W) {
     d->maps.m.clear();  // some buffer moved or the shape changed: rebuild the descriptors
@@ -675,13 +736,19 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
   }
   {  // out convs write their (replicated) result into the concat buffer: cat([p5,p4,p3,p2], 1)
     ConvTcParams q;
-    q.out = fuse; q.out_ldc = 256; q.out_coff = 0; q.rep = 8;
+    q.out = fuse; q.out_ldc = fuse_c; q.out_coff = 0; q.rep = 8;
     OCRB_TRY(conv("out5", in5, fh[3], fw[3], q));
     q.out_coff = 64; q.rep = 4;
     OCRB_TRY(conv("out4", s4, fh[2], fw[2], q));
-    q.out_coff = 128; q.rep = 2;
-    OCRB_TRY(conv("out3", s3, fh[1], fw[1], q));
-    q.out_coff = 192; q.rep = 1;
+    if (!d->fpn2_fused) {
+      q.out_coff = 128; q.rep = 2;
+      OCRB_TRY(conv("out3", s3, fh[1], fw[1], q));
+    } else {
+      ConvTcParams k;
+      k.out = p3;  // at its own resolution; bin_conv1 takes it through the class convolutions below
+      OCRB_TRY(conv("out3", s3, fh[1], fw[1], k));
+    }
+    q.out_coff = d->fpn2_fused ? 128 : 192; q.rep = 1;
     if (!d->fpn2_fused) {
       OCRB_TRY(conv("out2", s2, fh[0], fw[0], q));
     } else {
@@ -696,10 +763,21 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
       OCRB_TRY(conv("out2.x1", feat[0], fh[0], fw[0], q));
     }
   }
-  {
+  if (!d->fpn2_fused) {
     ConvTcParams q;
     q.relu = 1; q.out = b1;
     OCRB_TRY(conv("bin_conv1", fuse, H4, W4, q));
+  } else {
+    // up2 is free again (out2.x1 consumed it, same stream): it now collects p3's share of bin_conv1
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        ConvTcParams k;
+        k.out = up2 + ((int64_t)a * fw[0] + b) * 64; k.out_ldc = 64; k.out_step = 2;
+        OCRB_TRY(conv("bin_conv1.up" + std::to_string(a) + std::to_string(b), p3, fh[1], fw[1], k));
+      }
+    ConvTcParams q;
+    q.relu = 1; q.out = b1; q.residual = up2;
+    OCRB_TRY(conv("bin_conv1.main", fuse, H4, W4, q));
   }
   {  // head tail
     CUtensorMap *ma, *mb;
@@ -838,7 +916,12 @@ int ocrb_det_tap(ocrb_det *det, const char *name, float *out, int64_t numel) {
     OCRB_REQUIRE(it != det->act.end(), "tap %s not available", name);
     DevBuf tmp;
     OCRB_TRY(tmp.reserve((size_t)n * 4));
-    if (det->mode == OCRB_MODE_BF16) {
+    if (det->mode == OCRB_MODE_BF16 && det->fpn2_fused && strcmp(name, "fuse") == 0) {
+      auto ip = det->act.find("b.p3");
+      OCRB_REQUIRE(ip != det->act.end(), "tap fuse not available");
+      fuse_tap_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(it->second.as<__nv_bfloat16>(), ip->second.as<__nv_bfloat16>(), B, h, w, tmp.as<float>());
+      OCRB_TRY(check_launch(ctx, "fuse_tap"));
+    } else if (det->mode == OCRB_MODE_BF16) {
       bf16_nhwc_to_nchw_f32_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(it->second.as<__nv_bfloat16>(), B, h, w, t.c, t.c, tmp.as<float>());
       OCRB_TRY(check_launch(ctx, "bf16_nhwc_to_nchw_f32"));
     } else {
