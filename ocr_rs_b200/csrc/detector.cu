@@ -114,16 +114,16 @@ __global__ void __launch_bounds__(ST_THREADS) stem_fused_bf16_kernel(const TIn *
   }
 }
 
-// test tap "fuse" when p3 lives outside the concat buffer: rebuild cat[p5^8, p4^4, p3^2, p2] as NCHW fp32
-__global__ void fuse_tap_kernel(const __nv_bfloat16 *__restrict__ fuse192, const __nv_bfloat16 *__restrict__ p3, int B, int H, int W,
+// test tap "fuse" in the fused layout: rebuild cat[p5^8, p4^4, p3^2, p2] as NCHW fp32 from p2 and cat3 = [p5^4 | p4^2 | p3]
+__global__ void fuse_tap_kernel(const __nv_bfloat16 *__restrict__ p2, const __nv_bfloat16 *__restrict__ cat3, int B, int H, int W,
                                 float *__restrict__ out) {
   const int64_t n = (int64_t)B * 256 * H * W;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((int64_t)W * H)) % 256), b = (int)(i / ((int64_t)W * H * 256));
   float v;
-  if (c >= 128 && c < 192) v = __bfloat162float(p3[(((int64_t)b * (H / 2) + y / 2) * (W / 2) + x / 2) * 64 + (c - 128)]);
-  else v = __bfloat162float(fuse192[(((int64_t)b * H + y) * W + x) * 192 + (c < 128 ? c : c - 64)]);
+  if (c < 192) v = __bfloat162float(cat3[(((int64_t)b * (H / 2) + y / 2) * (W / 2) + x / 2) * 192 + c]);
+  else v = __bfloat162float(p2[(((int64_t)b * H + y) * W + x) * 64 + (c - 192)]);
   out[i] = v;
 }
 
@@ -316,42 +316,42 @@ static int prep_fused_fpn2(const HostWeights &hw, std::map<std::string, DevConv>
   return OCRB_OK;
 }
 
-// The same parity-class identity takes p3 out of the concat buffer (model.rs:140-143): bin_conv1(cat[p5^8, p4^4, p3^2, p2])
-//   = conv3x3(W_bin[:, p5|p4|p2 channels])(cat[p5^8, p4^4, p2])  +  conv3x3(W_bin[:, p3 channels])(up2(p3)),
-// the second term again four 4-tap class convolutions at 100 x 100 (K = 256), stored pixel-shuffled and added as a
-// residual.  bin_bn1 multiplies the whole sum, so its scale is folded into the class weights (the residual joins after
-// the main convolution's scale / shift).  out3 then writes p3 once at its own resolution instead of 2 x 2 replicated.
+// The same parity-class identity shrinks the concat buffer (model.rs:140-143).  Nearest upsampling composes
+// (up8 = up2 o up4, up4 = up2 o up2), so cat[p5^8, p4^4, p3^2] = up2(cat3) with cat3 = cat[p5^4, p4^2, p3] at 100 x 100 and
+//   bin_conv1(cat[p5^8, p4^4, p3^2, p2]) = conv3x3(W_bin[:, p2 channels])(p2)  +  conv3x3(W_bin[:, 0..191])(up2(cat3)),
+// the second term again four 4-tap class convolutions at 100 x 100 (K = 4 x 192), stored pixel-shuffled and added as a
+// residual: 768 instead of 1728 MACs per output pixel and channel, and the 256-channel 200 x 200 buffer is never built.
+// bin_bn1 multiplies the whole sum, so its scale is folded into the class weights (the residual joins after the main
+// convolution's scale / shift).
 static int prep_fused_bin_p3(const HostWeights &hw, std::map<std::string, DevConv> &conv) {
   const auto *wb = hw.get("bin_conv1.weight");
   OCRB_REQUIRE(wb && wb->size() == (size_t)64 * 256 * 9, "missing / mis-shaped bin_conv1 weights");
   std::vector<float> sc, sh;
   OCRB_TRY(fold_bn(hw, "bin_bn1", 64, nullptr, sc, sh));
-  // main part: input channels [p5 | p4 | p2] = reference channels 0..127 and 192..255
-  std::vector<float> wm((size_t)64 * 192 * 9);
+  // main part: p2 = reference channels 192..255
+  std::vector<float> wm((size_t)64 * 64 * 9);
   for (int co = 0; co < 64; ++co)
-    for (int ci = 0; ci < 192; ++ci) {
-      const int src = ci < 128 ? ci : ci + 64;
-      for (int tp = 0; tp < 9; ++tp) wm[((size_t)co * 192 + ci) * 9 + tp] = (*wb)[((size_t)co * 256 + src) * 9 + tp];
-    }
+    for (int ci = 0; ci < 64; ++ci)
+      for (int tp = 0; tp < 9; ++tp) wm[((size_t)co * 64 + ci) * 9 + tp] = (*wb)[((size_t)co * 256 + 192 + ci) * 9 + tp];
   DevConv &m = conv["bin_conv1.main"];
-  OCRB_TRY(upload_plain_conv3(wm, 192, 64, 0x1ff, m));
+  OCRB_TRY(upload_plain_conv3(wm, 64, 64, 0x1ff, m));
   m.has_bn = true;
   OCRB_TRY(upload(m.scale, sc));
   OCRB_TRY(upload(m.shift, sh));
   m.scale_h = sc; m.shift_h = sh;
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
-      std::vector<float> wk((size_t)64 * 64 * 9, 0.0f);
+      std::vector<float> wk((size_t)64 * 192 * 9, 0.0f);
       int mask = 0;
       for (int dy = -1; dy <= 1; ++dy)
         for (int dx = -1; dx <= 1; ++dx) {
           const int rr = ((a + dy) >> 1) + 1, ss = ((b + dx) >> 1) + 1;
           mask |= 1 << (rr * 3 + ss);
           for (int co = 0; co < 64; ++co)
-            for (int ci = 0; ci < 64; ++ci)
-              wk[((size_t)co * 64 + ci) * 9 + rr * 3 + ss] += sc[co] * (*wb)[((size_t)co * 256 + 128 + ci) * 9 + (dy + 1) * 3 + dx + 1];
+            for (int ci = 0; ci < 192; ++ci)  // cat3 keeps the reference channel order [p5 | p4 | p3]
+              wk[((size_t)co * 192 + ci) * 9 + rr * 3 + ss] += sc[co] * (*wb)[((size_t)co * 256 + ci) * 9 + (dy + 1) * 3 + dx + 1];
         }
-      OCRB_TRY(upload_plain_conv3(wk, 64, 64, mask, conv["bin_conv1.up" + std::to_string(a) + std::to_string(b)]));
+      OCRB_TRY(upload_plain_conv3(wk, 192, 64, mask, conv["bin_conv1.up" + std::to_string(a) + std::to_string(b)]));
     }
   return OCRB_OK;
 }
@@ -380,7 +380,7 @@ struct ocrb_det {
   // last forward (for taps)
   int last_B = 0, last_H = 0, last_W = 0;
   // BF16 mode: level 2 of the FPN computed from x1 and in3 directly (prep_fused_fpn2) and p3 kept out of the concat
-  // buffer (prep_fused_bin_p3): "b.fuse" is then [B][H/4][W/4][192] = [p5^8 | p4^4 | p2], "b.p3" [B][H/8][W/8][64]
+  // buffer (prep_fused_bin_p3): "b.fuse" is then just p2 [B][H/4][W/4][64], "b.cat3" [B][H/8][W/8][192] = [p5^4 | p4^2 | p3]
   bool fpn2_fused = false;
   // tensor-map cache
   struct Maps { int B = 0, H = 0, W = 0; std::map<std::string, CUtensorMap> m; } maps;
@@ -619,14 +619,14 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
   OCRB_TRY(act(d, "b.s4", (int64_t)B * fh[2] * fw[2] * 256, &s4));
   OCRB_TRY(act(d, "b.s3", (int64_t)B * fh[1] * fw[1] * 256, &s3));
   OCRB_TRY(act(d, "b.s2", (int64_t)B * fh[0] * fw[0] * 256, &s2));
-  const int fuse_c = d->fpn2_fused ? 192 : 256;
+  const int fuse_c = d->fpn2_fused ? 64 : 256;
   OCRB_TRY(act(d, "b.fuse", (int64_t)B * H4 * W4 * fuse_c, &fuse));
   OCRB_TRY(act(d, "b.bin1", (int64_t)B * H4 * W4 * 64, &b1));
   bf *up2 = nullptr;  // fused FPN level 2: out2's share of up2(in3), pixel-shuffled, [B][H4][W4][64]
   bf *p3 = nullptr;
   if (d->fpn2_fused) {
     OCRB_TRY(act(d, "b.up2", (int64_t)B * H4 * W4 * 64, &up2));
-    OCRB_TRY(act(d, "b.p3", (int64_t)B * fh[1] * fw[1] * 64, &p3));
+    OCRB_TRY(act(d, "b.cat3", (int64_t)B * fh[1] * fw[1] * 192, &p3));
   }
   for (auto &kv : d->act) after += kv.second.cap;
   if (after != before || d->maps.B != B || d->maps.H != H || d->maps.W != W) {
@@ -736,19 +736,18 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
   }
   {  // out convs write their (replicated) result into the concat buffer: cat([p5,p4,p3,p2], 1)
     ConvTcParams q;
-    q.out = fuse; q.out_ldc = fuse_c; q.out_coff = 0; q.rep = 8;
+    // cat[p5, p4, p3] at 200 x 200 (x8, x4, x2), or — fused — at 100 x 100 (x4, x2, x1): bin_conv1 takes that one through its
+    // class convolutions
+    const int rdiv = d->fpn2_fused ? 2 : 1;
+    q.out = d->fpn2_fused ? p3 : fuse; q.out_ldc = d->fpn2_fused ? 192 : 256;
+    q.out_coff = 0; q.rep = 8 / rdiv;
     OCRB_TRY(conv("out5", in5, fh[3], fw[3], q));
-    q.out_coff = 64; q.rep = 4;
+    q.out_coff = 64; q.rep = 4 / rdiv;
     OCRB_TRY(conv("out4", s4, fh[2], fw[2], q));
-    if (!d->fpn2_fused) {
-      q.out_coff = 128; q.rep = 2;
-      OCRB_TRY(conv("out3", s3, fh[1], fw[1], q));
-    } else {
-      ConvTcParams k;
-      k.out = p3;  // at its own resolution; bin_conv1 takes it through the class convolutions below
-      OCRB_TRY(conv("out3", s3, fh[1], fw[1], k));
-    }
-    q.out_coff = d->fpn2_fused ? 128 : 192; q.rep = 1;
+    q.out_coff = 128; q.rep = 2 / rdiv;
+    OCRB_TRY(conv("out3", s3, fh[1], fw[1], q));
+    q.out = fuse; q.out_ldc = fuse_c;
+    q.out_coff = d->fpn2_fused ? 0 : 192; q.rep = 1;
     if (!d->fpn2_fused) {
       OCRB_TRY(conv("out2", s2, fh[0], fw[0], q));
     } else {
@@ -768,7 +767,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     q.relu = 1; q.out = b1;
     OCRB_TRY(conv("bin_conv1", fuse, H4, W4, q));
   } else {
-    // up2 is free again (out2.x1 consumed it, same stream): it now collects p3's share of bin_conv1
+    // up2 is free again (out2.x1 consumed it, same stream): it now collects the share of cat3 = [p5 | p4 | p3] in bin_conv1
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {
         ConvTcParams k;
@@ -917,7 +916,7 @@ int ocrb_det_tap(ocrb_det *det, const char *name, float *out, int64_t numel) {
     DevBuf tmp;
     OCRB_TRY(tmp.reserve((size_t)n * 4));
     if (det->mode == OCRB_MODE_BF16 && det->fpn2_fused && strcmp(name, "fuse") == 0) {
-      auto ip = det->act.find("b.p3");
+      auto ip = det->act.find("b.cat3");
       OCRB_REQUIRE(ip != det->act.end(), "tap fuse not available");
       fuse_tap_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(it->second.as<__nv_bfloat16>(), ip->second.as<__nv_bfloat16>(), B, h, w, tmp.as<float>());
       OCRB_TRY(check_launch(ctx, "fuse_tap"));
