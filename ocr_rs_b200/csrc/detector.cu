@@ -262,7 +262,8 @@ static int prep_fused_downsample(const HostWeights &hw, const std::string &p, in
 //      = conv3x3(W_out2 o W_in2)(x1)  +  conv3x3(W_out2)(up2(in3))
 // * the first term is a 64 -> 64 3x3 convolution of x1 with the composed weights (K = 576 instead of 2304);
 // * the second, a 3x3 convolution of a nearest-upsampled map, is for each output parity class (a, b) = (y & 1, x & 1)
-//   a 2x2 convolution of the half-resolution lateral itself: row offsets {-1, 0} carry W[-1], W[0]+W[1] for even y and
+//   a 2x2 convolution of the half-resolution lateral itself (and, in3 being a 1x1 convolution of x2, of x2 with weights
+//   composed once more): row offsets {-1, 0} carry W[-1], W[0]+W[1] for even y and
 //   {0, +1} carry W[-1]+W[0], W[1] for odd y (same for columns) — four 4-tap convolutions at 100 x 100 whose results are
 //   stored pixel-shuffled (class (a,b) of low-res pixel (Y,X) at (2Y+a, 2X+b)) into one 64-channel map that the first
 //   convolution adds as a residual.  Zero padding maps to zero padding, so borders are exact.
@@ -294,8 +295,9 @@ static int upload_plain_conv3(const std::vector<float> &w, int cin, int cout, in
 }
 
 static int prep_fused_fpn2(const HostWeights &hw, std::map<std::string, DevConv> &conv) {
-  const auto *wo = hw.get("out2.weight"), *wi = hw.get("in2.weight");
+  const auto *wo = hw.get("out2.weight"), *wi = hw.get("in2.weight"), *wi3 = hw.get("in3.weight");
   OCRB_REQUIRE(wo && wi && wo->size() == (size_t)64 * 256 * 9 && wi->size() == (size_t)256 * 64, "missing / mis-shaped in2 / out2 weights");
+  OCRB_REQUIRE(wi3 && wi3->size() == (size_t)256 * 128, "missing / mis-shaped in3 weights");
   std::vector<float> wc;
   compose_weights(*wo, *wi, 64, 256, 64, wc);
   OCRB_TRY(upload_plain_conv3(wc, 64, 64, 0x1ff, conv["out2.x1"]));
@@ -311,7 +313,11 @@ static int prep_fused_fpn2(const HostWeights &hw, std::map<std::string, DevConv>
           for (int co = 0; co < 64; ++co)
             for (int m = 0; m < 256; ++m) wk[((size_t)co * 256 + m) * 9 + rr * 3 + ss] += (*wo)[((size_t)co * 256 + m) * 9 + (dy + 1) * 3 + dx + 1];
         }
-      OCRB_TRY(upload_plain_conv3(wk, 256, 64, mask, conv["out2.up" + std::to_string(a) + std::to_string(b)]));
+      // in3 is itself a bias-free 1x1 convolution of x2 (128 channels): compose once more, K = 4 x 128 instead of 4 x 256,
+      // and the raw lateral in3 is never materialised
+      std::vector<float> wkc;
+      compose_weights(wk, *wi3, 64, 256, 128, wkc);
+      OCRB_TRY(upload_plain_conv3(wkc, 128, 64, mask, conv["out2.up" + std::to_string(a) + std::to_string(b)]));
     }
   return OCRB_OK;
 }
@@ -727,7 +733,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     OCRB_TRY(conv("in5", feat[3], fh[3], fw[3], q));
     q = ConvTcParams(); q.out = in4; q.up_src = in5; q.sum_out = s4;
     OCRB_TRY(conv("in4", feat[2], fh[2], fw[2], q));
-    q = ConvTcParams(); q.out = in3; q.up_src = in4; q.sum_out = s3;
+    q = ConvTcParams(); q.out = d->fpn2_fused ? nullptr : in3; q.up_src = in4; q.sum_out = s3;  // fused level 2 reads x2, not in3
     OCRB_TRY(conv("in3", feat[1], fh[1], fw[1], q));
     if (!d->fpn2_fused) {
       q = ConvTcParams(); q.out = nullptr; q.up_src = in3; q.sum_out = s2;
@@ -756,7 +762,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
         for (int b = 0; b < 2; ++b) {
           ConvTcParams k;
           k.out = up2 + ((int64_t)a * fw[0] + b) * 64; k.out_ldc = 64; k.out_step = 2;
-          OCRB_TRY(conv("out2.up" + std::to_string(a) + std::to_string(b), in3, fh[1], fw[1], k));
+          OCRB_TRY(conv("out2.up" + std::to_string(a) + std::to_string(b), feat[1], fh[1], fw[1], k));
         }
       q.residual = up2;
       OCRB_TRY(conv("out2.x1", feat[0], fh[0], fw[0], q));
