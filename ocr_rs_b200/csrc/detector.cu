@@ -294,13 +294,15 @@ static int upload_plain_conv3(const std::vector<float> &w, int cin, int cout, in
   return upload(dc.w16, w16);
 }
 
-static int prep_fused_fpn2(const HostWeights &hw, std::map<std::string, DevConv> &conv) {
-  const auto *wo = hw.get("out2.weight"), *wi = hw.get("in2.weight"), *wi3 = hw.get("in3.weight");
-  OCRB_REQUIRE(wo && wi && wo->size() == (size_t)64 * 256 * 9 && wi->size() == (size_t)256 * 64, "missing / mis-shaped in2 / out2 weights");
-  OCRB_REQUIRE(wi3 && wi3->size() == (size_t)256 * 128, "missing / mis-shaped in3 weights");
+// one FPN level: out_l(in_l(x_l) + up2(in_u(x_u))) -> "<out>.x" (3x3 on x_l, composed) + "<out>.up{a}{b}" (4-tap classes on x_u)
+static int prep_fused_fpn_level(const HostWeights &hw, const std::string &out, const std::string &in_l, const std::string &in_u, int c_l, int c_u,
+                                std::map<std::string, DevConv> &conv) {
+  const auto *wo = hw.get(out + ".weight"), *wi = hw.get(in_l + ".weight"), *wu = hw.get(in_u + ".weight");
+  OCRB_REQUIRE(wo && wi && wu && wo->size() == (size_t)64 * 256 * 9 && wi->size() == (size_t)256 * c_l && wu->size() == (size_t)256 * c_u,
+               "missing / mis-shaped %s / %s / %s weights", out.c_str(), in_l.c_str(), in_u.c_str());
   std::vector<float> wc;
-  compose_weights(*wo, *wi, 64, 256, 64, wc);
-  OCRB_TRY(upload_plain_conv3(wc, 64, 64, 0x1ff, conv["out2.x1"]));
+  compose_weights(*wo, *wi, 64, 256, c_l, wc);
+  OCRB_TRY(upload_plain_conv3(wc, c_l, 64, 0x1ff, conv[out + ".x"]));
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       // low-res tap r' (row offset r' - 1) collects the full-res taps dy whose source row (2Y + a + dy) >> 1 is Y + r' - 1
@@ -313,13 +315,18 @@ static int prep_fused_fpn2(const HostWeights &hw, std::map<std::string, DevConv>
           for (int co = 0; co < 64; ++co)
             for (int m = 0; m < 256; ++m) wk[((size_t)co * 256 + m) * 9 + rr * 3 + ss] += (*wo)[((size_t)co * 256 + m) * 9 + (dy + 1) * 3 + dx + 1];
         }
-      // in3 is itself a bias-free 1x1 convolution of x2 (128 channels): compose once more, K = 4 x 128 instead of 4 x 256,
-      // and the raw lateral in3 is never materialised
+      // the upper lateral is itself a bias-free 1x1 convolution of x_u: compose once more (K = 4 x c_u), and the raw
+      // lateral is never materialised for this level
       std::vector<float> wkc;
-      compose_weights(wk, *wi3, 64, 256, 128, wkc);
-      OCRB_TRY(upload_plain_conv3(wkc, 128, 64, mask, conv["out2.up" + std::to_string(a) + std::to_string(b)]));
+      compose_weights(wk, *wu, 64, 256, c_u, wkc);
+      OCRB_TRY(upload_plain_conv3(wkc, c_u, 64, mask, conv[out + ".up" + std::to_string(a) + std::to_string(b)]));
     }
   return OCRB_OK;
+}
+
+static int prep_fused_fpn2(const HostWeights &hw, std::map<std::string, DevConv> &conv) {
+  OCRB_TRY(prep_fused_fpn_level(hw, "out2", "in2", "in3", 64, 128, conv));   // p2 from x1 (200^2) and x2
+  return prep_fused_fpn_level(hw, "out3", "in3", "in4", 128, 256, conv);     // p3 from x2 (100^2) and x3
 }
 
 // The same parity-class identity shrinks the concat buffer (model.rs:140-143).  Nearest upsampling composes
@@ -731,10 +738,12 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     ConvTcParams q;
     q.out = in5;
     OCRB_TRY(conv("in5", feat[3], fh[3], fw[3], q));
-    q = ConvTcParams(); q.out = in4; q.up_src = in5; q.sum_out = s4;
+    q = ConvTcParams(); q.out = d->fpn2_fused ? nullptr : in4; q.up_src = in5; q.sum_out = s4;  // raw in4 only feeds the unfused in3
     OCRB_TRY(conv("in4", feat[2], fh[2], fw[2], q));
-    q = ConvTcParams(); q.out = d->fpn2_fused ? nullptr : in3; q.up_src = in4; q.sum_out = s3;  // fused level 2 reads x2, not in3
-    OCRB_TRY(conv("in3", feat[1], fh[1], fw[1], q));
+    if (!d->fpn2_fused) {  // fused levels 2 and 3 read x2 / x3 directly: neither in3 nor s3 exists
+      q = ConvTcParams(); q.out = in3; q.up_src = in4; q.sum_out = s3;
+      OCRB_TRY(conv("in3", feat[1], fh[1], fw[1], q));
+    }
     if (!d->fpn2_fused) {
       q = ConvTcParams(); q.out = nullptr; q.up_src = in3; q.sum_out = s2;
       OCRB_TRY(conv("in2", feat[0], fh[0], fw[0], q));
@@ -751,7 +760,20 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     q.out_coff = 64; q.rep = 4 / rdiv;
     OCRB_TRY(conv("out4", s4, fh[2], fw[2], q));
     q.out_coff = 128; q.rep = 2 / rdiv;
-    OCRB_TRY(conv("out3", s3, fh[1], fw[1], q));
+    if (!d->fpn2_fused) {
+      OCRB_TRY(conv("out3", s3, fh[1], fw[1], q));
+    } else {
+      // p3 = conv3x3(W_out3 o W_in3)(x2) + [class convolutions of x3, pixel-shuffled into the first quarter of up2]
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          ConvTcParams k;
+          k.out = up2 + ((int64_t)a * fw[1] + b) * 64; k.out_ldc = 64; k.out_step = 2;
+          OCRB_TRY(conv("out3.up" + std::to_string(a) + std::to_string(b), feat[2], fh[2], fw[2], k));
+        }
+      q.residual = up2;
+      OCRB_TRY(conv("out3.x", feat[1], fh[1], fw[1], q));
+      q.residual = nullptr;
+    }
     q.out = fuse; q.out_ldc = fuse_c;
     q.out_coff = d->fpn2_fused ? 0 : 192; q.rep = 1;
     if (!d->fpn2_fused) {
@@ -765,7 +787,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
           OCRB_TRY(conv("out2.up" + std::to_string(a) + std::to_string(b), feat[1], fh[1], fw[1], k));
         }
       q.residual = up2;
-      OCRB_TRY(conv("out2.x1", feat[0], fh[0], fw[0], q));
+      OCRB_TRY(conv("out2.x", feat[0], fh[0], fw[0], q));
     }
   }
   if (!d->fpn2_fused) {

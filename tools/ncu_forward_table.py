@@ -16,11 +16,12 @@ for li, (hw, c) in enumerate(((100, 128), (50, 256), (25, 512)), start=2):
     k = 9 * c
     L += [(f"l{li}.0.c1(s2)", hw * hw * c * (k // 2)), (f"l{li}.0.c2(+ds)", hw * hw * c * (k + c // 2)),
           (f"l{li}.1.c1", hw * hw * c * k), (f"l{li}.1.c2", hw * hw * c * k)]
-L += [("in5", 25 * 25 * 256 * 512), ("in4(+sum)", 50 * 50 * 256 * 256), ("in3(+sum)", 100 * 100 * 256 * 128)]
-L += [("out5(x4)", 25 * 25 * 64 * 2304), ("out4(x2)", 50 * 50 * 64 * 2304), ("out3", 100 * 100 * 64 * 2304)]
-# FPN level 2 without s2: four 4-tap class convolutions of in3 + the composed 3x3 on x1 (detector.cu prep_fused_fpn2);
-# MACs actually executed (the reference's in2 + out2 are 200*200*(256*64 + 64*2304))
-L += [(f"out2.up{a}{b}", 100 * 100 * 64 * 1024) for a in (0, 1) for b in (0, 1)] + [("out2.x1(+res)", 200 * 200 * 64 * 576)]
+L += [("in5", 25 * 25 * 256 * 512), ("in4(+sum)", 50 * 50 * 256 * 256)]
+L += [("out5(x4)", 25 * 25 * 64 * 2304), ("out4(x2)", 50 * 50 * 64 * 2304)]
+# FPN levels 3 and 2 without their 256-channel intermediates (detector.cu prep_fused_fpn_level): four 4-tap class
+# convolutions of the level above's backbone feature + the composed 3x3 on the level's own; MACs actually executed
+L += [(f"out3.up{a}{b}", 50 * 50 * 64 * 1024) for a in (0, 1) for b in (0, 1)] + [("out3.x(+res)", 100 * 100 * 64 * 1152)]
+L += [(f"out2.up{a}{b}", 100 * 100 * 64 * 512) for a in (0, 1) for b in (0, 1)] + [("out2.x(+res)", 200 * 200 * 64 * 576)]
 # cat3 = [p5^4 | p4^2 | p3] reaches bin_conv1 through four 4-tap class convolutions (prep_fused_bin_p3); the main part reads p2
 L += [(f"bin_conv1.up{a}{b}", 100 * 100 * 64 * 768) for a in (0, 1) for b in (0, 1)] + [("bin_conv1.main(+res)", 200 * 200 * 64 * 576)]
 L += [("head", 200 * 200 * 256 * 64 + 400 * 400 * 4 * 64)]
