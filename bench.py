@@ -57,6 +57,17 @@ def tc_flops_per_image(h, w):
     return f
 
 
+def tc_flops_executed_per_image(h, w):
+    """2*MACs the BF16 graph actually executes: FPN levels 2 / 3 and bin_conv1 run in their algebraically fused form
+    (detector.cu prep_fused_fpn_level / prep_fused_bin_p3) — fewer MACs for the same function."""
+    h4, w4, h8, w8, h16, w16 = h // 4, w // 4, h // 8, w // 8, h // 16, w // 16
+    ref = 2 * (h4 * w4 * (256 * 64 + 64 * 2304) + h8 * w8 * (256 * 128 + 64 * 2304) + h4 * w4 * 64 * 2304)  # in2+out2, in3+out3, bin_conv1
+    fused = 2 * (h4 * w4 * 64 * 576 + 4 * h8 * w8 * 64 * 512        # out2.x + out2.up{ab}
+                 + h8 * w8 * 64 * 1152 + 4 * h16 * w16 * 64 * 1024  # out3.x + out3.up{ab}
+                 + h4 * w4 * 64 * 576 + 4 * h8 * w8 * 64 * 768)     # bin_conv1.main + bin_conv1.up{ab}
+    return tc_flops_per_image(h, w) - ref + fused
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -323,7 +334,10 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                      "traffic": traffic, "traffic_note": "avg DRAM bytes per tcgen05 launch scaled to this run's chunk of <= 128 images (profiles/r1_ncu_forward_traffic.json: 227 MB/image measured); algorithmic unfused bf16 activation traffic is 285.8 MB/image", "kernel": "stem_tc / conv_halo / conv_lateral / conv_tc kernels (all tcgen05 implicit-GEMM launches of one step)", "launches": tc_n,
-                     "avg_launch_ms": tc_ms / max(tc_n, 1), "flops_per_image": tc_flops_per_image(H, W), "peak_source": peak_src,
+                     "avg_launch_ms": tc_ms / max(tc_n, 1), "flops_per_image": tc_flops_per_image(H, W), "flops_executed_per_image": tc_flops_executed_per_image(H, W) if args.mode == "bf16" else tc_flops_per_image(H, W),
+                     "achieved_executed": (achieved * tc_flops_executed_per_image(H, W) / tc_flops_per_image(H, W)) if args.mode == "bf16" else achieved,
+                     "flops_note": "achieved/frac count the reference network's algorithmic FLOPs (SURVEY 8d); the fused FPN / bin_conv1 form executes fewer (flops_executed_per_image, achieved_executed)",
+                     "peak_source": peak_src,
                      "share_of_step": tc_ms / all_ms if all_ms else None},
         "kernels_ms_per_step": {k: round(v[1], 3) for k, v in top},
         "cpu_baseline": cpu,
