@@ -26,7 +26,8 @@ L += [(f"out2.up{a}{b}", 100 * 100 * 64 * 512) for a in (0, 1) for b in (0, 1)] 
 L += [(f"bin_conv1.up{a}{b}", 100 * 100 * 64 * 768) for a in (0, 1) for b in (0, 1)] + [("bin_conv1.main(+res)", 200 * 200 * 64 * 576)]
 L += [("head", 200 * 200 * 256 * 64 + 400 * 400 * 4 * 64)]
 
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# REPORT may also be the `ncu -i REPORT.ncu-rep --page raw --csv` export (reports over 64 MiB do not travel back from the GPU box)
+out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 col = {h: i for i, h in enumerate(hdr)}
