@@ -554,9 +554,14 @@ int halo_geometry(int Ho, int Wo, int n_tile, int G, int ts, HaloGeom *out) {  /
   g.a_stage_bytes = ((rows * 128 + 1023) / 1024) * 1024;
   g.a_tx_bytes = halo_rows * 128;
   const int b_bytes = n_tile * 128;
-  const int budget = 227 * 1024 - 1024 /*align*/ - 4096 /*static scale/shift*/ - 512 /*barriers*/ - (ts ? g.obufs * g.obuf_bytes : HL_STG_BYTES);
+  int budget = 227 * 1024 - 1024 /*align*/ - 4096 /*static scale/shift*/ - 512 /*barriers*/ - (ts ? g.obufs * g.obuf_bytes : HL_STG_BYTES);
   g.a_stages = 2;
   g.b_stages = (budget - g.a_stages * g.a_stage_bytes) / b_bytes;
+  if (ts && g.b_stages < 4) {  // wide tiles with whole weight tiles per CTA (single-CTA mode): two staging tiles instead of three
+    budget += g.obuf_bytes;
+    g.obufs = 2;
+    g.b_stages = (budget - g.a_stages * g.a_stage_bytes) / b_bytes;
+  }
   if (g.b_stages > 8) {
     // room to spare: a third A stage helps layers with many input chunks
     if (budget - 3 * g.a_stage_bytes >= 6 * b_bytes) { g.a_stages = 3; g.b_stages = (budget - 3 * g.a_stage_bytes) / b_bytes; }

@@ -136,3 +136,36 @@ def test_large_non_square_map(env):
     err = np.abs(got - ref).max()
     print(f"1216x1600 bf16: max|dp| = {err:.3e}")
     assert err <= TOL["bf16"]
+
+
+@pytest.mark.parametrize("knobs", [{"OCRB_FUSE_FPN2": "0"}, {"OCRB_FUSE_FPN2": "0", "OCRB_HALO_TS": "0", "OCRB_LATERAL_TS": "0"},
+                                   {"OCRB_HALO_CG": "1"}, {"OCRB_CONV": "tc", "OCRB_FUSE_DS": "0"}])
+def test_alternate_kernel_paths(knobs):
+    """The library's tuning knobs select older / more literal code paths (the reference's literal FPN graph with the
+    lateral kernel, per-thread-store epilogues, single-CTA tiles, the one-box-per-tap engine with separate downsample
+    launches).  They are read once per process, so each combination runs in its own interpreter; same tolerance."""
+    import os
+    import subprocess
+    import sys
+    script = r"""
+import numpy as np
+from ocr_rs_b200 import synth
+from ocr_rs_b200.text_detection.model import resnet18
+from oracle import model_oracle as mo
+worst = 0.0
+for (B, H, W), variant in (((2, 160, 224), "hard_bn"), ((1, 416, 96), "tch")):
+    w = synth.make_detector_weights(3, variant)
+    x = synth.make_noise_images(B, H, W, seed=H + W)
+    got = resnet18(w, "bf16").forward_t(x.reshape(B, 1, H, W))
+    ref = mo.detector_forward(w, x.reshape(B, 1, H, W).astype(np.float32)).numpy()
+    worst = max(worst, float(np.abs(got - ref).max()))
+print("WORST", worst)
+"""
+    env = dict(os.environ, **knobs)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    out = subprocess.run([sys.executable, "-c", script], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    worst = float([l for l in out.stdout.splitlines() if l.startswith("WORST")][-1].split()[1])
+    print(knobs, f"max|dp| = {worst:.3e}")
+    assert worst <= TOL["bf16"]
