@@ -302,8 +302,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r1_ncu_forward_traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read+write of the same launches from one `ncu --set full` capture
         tj = json.load(open(tpath))
-        # per launch like `achieved`: the pipeline forwards chunks of <= 128 images, the capture holds tj["images"] per launch
-        traffic = tj["dram_bytes_per_launch"] * min(count, 128) / float(tj["images"])
+        # per launch like `achieved`: the pipeline forwards chunks of <= 256 images, the capture holds tj["images"] per launch
+        traffic = tj["dram_bytes_per_launch"] * min(count, 256) / float(tj["images"])
     flops_step = tc_flops_per_image(H, W) * count
     achieved = flops_step / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     groups = {}
@@ -333,7 +333,7 @@ def main():
         "gpu_launches": int(lt.item()),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                     "traffic": traffic, "traffic_note": "avg DRAM bytes per tcgen05 launch scaled to this run's chunk of <= 128 images (profiles/r1_ncu_forward_traffic.json: 227 MB/image measured); algorithmic unfused bf16 activation traffic is 285.8 MB/image", "kernel": "stem_tc / conv_halo / conv_lateral / conv_tc kernels (all tcgen05 implicit-GEMM launches of one step)", "launches": tc_n,
+                     "traffic": traffic, "traffic_note": "avg DRAM bytes per tcgen05 launch scaled to this run's chunk of <= 256 images (profiles/r1_ncu_forward_traffic.json: 227 MB/image measured); algorithmic unfused bf16 activation traffic is 285.8 MB/image", "kernel": "stem_tc / conv_halo / conv_lateral / conv_tc kernels (all tcgen05 implicit-GEMM launches of one step)", "launches": tc_n,
                      "avg_launch_ms": tc_ms / max(tc_n, 1), "flops_per_image": tc_flops_per_image(H, W), "flops_executed_per_image": tc_flops_executed_per_image(H, W) if args.mode == "bf16" else tc_flops_per_image(H, W),
                      "achieved_executed": (achieved * tc_flops_executed_per_image(H, W) / tc_flops_per_image(H, W)) if args.mode == "bf16" else achieved,
                      "flops_note": "achieved/frac count the reference network's algorithmic FLOPs (SURVEY 8d); the fused FPN / bin_conv1 form executes fewer (flops_executed_per_image, achieved_executed)",
