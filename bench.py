@@ -35,7 +35,7 @@ TOTAL_IMAGES = 1024
 H = W = 800
 GLYPHS_PER_IMAGE = 4
 METRIC = "800x800 det+rec images/sec"
-CPU_BATCH = 4
+CPU_BATCH = 0  # 0 = calibrate (1 or 4) on first use
 
 
 def tc_flops_per_image(h, w):
@@ -130,9 +130,21 @@ def time_cpu_sample(n_images, budget_s, threads, seed_first=0):
     wr = synth.make_rec_weights(1)
     imgs = synth.document_image_shard(seed_first, n_images, H, W)
     glyphs = synth.make_glyphs(n_images * GLYPHS_PER_IMAGE, 1, "strokes")
-    nb = CPU_BATCH  # the reference batches its evaluation loop (text_detection/mod.rs:188-204); 4 measured best for torch-CPU
-    adj = np.ones((nb, 2))
+    # the reference batches its evaluation loop (text_detection/mod.rs:188-204); which of batch 1 / 4 is faster for
+    # torch-CPU depends on the host: calibrate on a few images and give the CPU its better setting
+    global CPU_BATCH
+    adj = np.ones((4, 2))
     cpu_path(wd, wr, imgs[:1], glyphs[:GLYPHS_PER_IMAGE], adj[:1], threads)  # warm-up
+    if CPU_BATCH == 0:
+        rate = {}
+        for nb in (1, 4):
+            k = min(4, n_images)
+            t0 = time.time()
+            for i in range(0, k, nb):
+                cpu_path(wd, wr, imgs[i:i + nb], glyphs[i * GLYPHS_PER_IMAGE:(i + nb) * GLYPHS_PER_IMAGE], adj[:min(nb, k - i)], threads)
+            rate[nb] = k / (time.time() - t0)
+        CPU_BATCH = max(rate, key=rate.get)
+    nb = CPU_BATCH
     done, t0 = 0, time.time()
     while done < n_images and (time.time() - t0 < budget_s or done == 0):
         k = min(nb, n_images - done)
