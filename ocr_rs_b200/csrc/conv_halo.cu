@@ -68,7 +68,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int MW = G >= 4 ? 2 : 1;
   constexpr int GW = G / MW;  // sub-tiles per MMA warp
   constexpr int THREADS = (1 + MW + HL_EPI_WARPS + TS) * 32;
-  static_assert(!TS || N_TILE == 64, "TMA-store epilogue: one 128-byte row per pixel");
+  static_assert(!TS || N_TILE == 64 || (N_TILE == 128 && G == 2), "TMA-store epilogue: one 128-byte row per pixel (N = 128: pair mode, two rows)");
   constexpr int NB = N_TILE / CG;  // weight rows held by this CTA
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(16) float s_scale[512], s_shift[512];
@@ -139,10 +139,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (CG == 2) {
             const uint32_t bar = mapa_u32(&a_full[as], 0);
             mbar_expect_tx_cluster(bar, g.a_tx_bytes);
-            tma_load_4d_2sm(sA + as * g.a_stage_bytes, &tmA, bar, ck * 64, tx * g.TW - 1, ty * g.TH - 1, b);
+            tma_load_4d_2sm(sA + as * g.a_stage_bytes, &tmA, bar, ck * 64, tx * g.TW - 1 + p.in_x_off, ty * g.TH - 1, b);
           } else {
             mbar_expect_tx(&a_full[as], g.a_tx_bytes);
-            tma_load_4d(sA + as * g.a_stage_bytes, &tmA, &a_full[as], ck * 64, tx * g.TW - 1, ty * g.TH - 1, b);
+            tma_load_4d(sA + as * g.a_stage_bytes, &tmA, &a_full[as], ck * 64, tx * g.TW - 1 + p.in_x_off, ty * g.TH - 1, b);
           }
         }
         __syncwarp();
@@ -318,7 +318,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int gi = 0; gi < G; ++gi) {
           mbar_wait(&o_done[buf], dph, p.err, 21);
           int c0, c1, c2, c3;
-          if (coords(unit, gi, c0, c1, c2, c3)) tma_store_4d(&tmO, sStg + buf * g.obuf_bytes, c0, c1, c2, c3);
+          if (coords(unit, gi, c0, c1, c2, c3)) {
+            if (N_TILE == 128) {  // pair mode: half 0 -> `out` (tmO), half 1 -> `out2` (tmR's slot); the one-column shift between them is in the maps' base pointers
+              tma_store_4d(&tmO, sStg + buf * g.obuf_bytes, 0, c1, c2, c3);
+              tma_store_4d(&tmR, sStg + buf * g.obuf_bytes + g.obuf_bytes / 2, 0, c1, c2, c3);
+            } else {
+              tma_store_4d(&tmO, sStg + buf * g.obuf_bytes, c0, c1, c2, c3);
+            }
+          }
           bulk_commit_group();
           if (prev >= 0) {
             bulk_wait_group_read<1>();  // the previous sub-tile's store has left its staging tile
@@ -330,6 +337,50 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       bulk_wait_group<0>();
+    }
+  } else if (TS && N_TILE == 128) {
+    // ================= pair-mode epilogue: plain bf16 conversion, one staging tile per 64-channel half =================
+    const int ew = warp - 1 - MW;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = ew >> 2;      // which of the two convolutions
+    const int m_local = quarter * 32 + lane;
+    const int ysub = m_local / g.PW, xl = m_local - ysub * g.PW;
+    const bool row_ok = m_local < g.sub_stride && xl < g.TW;
+    const int r = ysub * g.TW + xl;
+    int acc = 0, buf = 0;
+    uint32_t acc_phase = 0, rph = 0;
+    for (int unit = unit0; unit < num_units; unit += unit_step) {
+      mbar_wait(&tfull[acc], acc_phase, p.err, 16);
+      tc_fence_after();
+#pragma unroll 1
+      for (int gi = 0; gi < G; ++gi) {
+        mbar_wait(&o_ready[buf], rph, p.err, 22);
+        const uint32_t tile = smem_u32(sStg + buf * g.obuf_bytes + half * (g.obuf_bytes / 2));
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * G + gi) * N_TILE + half * 64 + blk * 32), v);
+          if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              sts_16(tile + (uint32_t)(r * 128 + (((4 * blk + c) ^ (r & 7)) << 4)),
+                     make_uint4(pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]), pack_bf16(v[c * 8 + 4], v[c * 8 + 5]),
+                                pack_bf16(v[c * 8 + 6], v[c * 8 + 7])));
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_done[buf]);
+        if (++buf == g.obufs) { buf = 0; rph ^= 1; }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
+        else mbar_arrive(&tempty[acc]);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (TS) {
     // ================= epilogue through TMA =================
@@ -546,7 +597,7 @@ int halo_geometry(int Ho, int Wo, int n_tile, int G, int ts, HaloGeom *out) {  /
     g.sub_stride = 128;
   }
   g.TW = g.PW - 2;
-  g.obuf_bytes = ts ? ((g.sub_rows * g.TW * 128 + 1023) / 1024) * 1024 : 0;
+  g.obuf_bytes = ts ? ((g.sub_rows * g.TW * 128 + 1023) / 1024) * 1024 * (ts == 2 ? 2 : 1) : 0;  // ts = 2: pair mode, one tile per half
   g.obufs = ts ? 3 : 0;
   const int halo_rows = (g.TH + 2) * g.PW;
   const int read_rows = (G - 1) * g.sub_stride + 128 + 2 * g.PW + 2;  // last sub-tile, tap (2,2)
@@ -573,7 +624,7 @@ int halo_geometry(int Ho, int Wo, int n_tile, int G, int ts, HaloGeom *out) {  /
 }
 
 int make_act_tensor_map_box(CUtensorMap *map, const void *base, int B, int H, int W, int C, int box_w, int box_h);
-int make_act_tensor_map_pitched(CUtensorMap *map, const void *base, int B, int H, int W, int C, int ldc, int box_w, int box_h, int step = 1);
+int make_act_tensor_map_pitched(CUtensorMap *map, const void *base, int B, int H, int W, int C, int ldc, int box_w, int box_h, int step = 1, int row_px = 0);
 
 
 template <int N_TILE, int G, int CG, int TS>
@@ -616,9 +667,10 @@ static int halo_cg() {  // CTA-pair mode unless OCRB_HALO_CG=1
   return cg;
 }
 
-int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G, int rep) {
+int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G, int rep, int pair) {
   HaloGeom g;
-  OCRB_TRY(halo_geometry(H, W, n_tile / halo_cg(), G, halo_use_ts(n_tile, rep), &g));
+  // pair mode: one output column more than input columns, geometry of the launch (launch_conv_halo) must match
+  OCRB_TRY(halo_geometry(H, W + (pair ? 1 : 0), n_tile / halo_cg(), G, pair ? 2 : (int)halo_use_ts(n_tile, rep), &g));
   return make_act_tensor_map_box(map, base, B, H, W, C, g.PW, g.TH + 2);
 }
 int halo_weight_box_rows(int n_tile) { return n_tile / halo_cg(); }
@@ -639,7 +691,11 @@ int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &t
   if (p.R != 3 || p.S != 3 || p.stride != 1 || p.pad != 1 || p.sum_out || !p.out) { set_error("conv_halo: unsupported convolution"); return OCRB_ERR_INVALID; }
   if (p.Cout % n_tile != 0 || p.Cout > 512) { set_error("conv_halo: Cout %d vs N tile %d", p.Cout, n_tile); return OCRB_ERR_INVALID; }
   const int G = n_tile == 64 ? 4 : 2, CG = halo_cg();
-  const int ts = halo_use_ts(n_tile, p.rep);
+  const int ts = p.pair_mode ? 2 : (int)halo_use_ts(n_tile, p.rep);
+  if (p.pair_mode && (n_tile != 128 || p.Cout != 128 || p.rep != 1 || p.residual || p.scale || p.relu || !p.out2 || p.ds_chunks || !halo_use_ts(64, 1))) {
+    set_error("conv_halo: bad pair-mode arguments");
+    return OCRB_ERR_INVALID;
+  }
   if (!ts && (p.out_step != 1 || (p.tap_mask & 0x1ff) != 0x1ff)) { set_error("conv_halo: tap mask / output step need the TMA-store path"); return OCRB_ERR_INVALID; }
   if ((p.tap_mask & 0x1ff) == 0) { set_error("conv_halo: empty tap mask"); return OCRB_ERR_INVALID; }
   p.tap_mask &= 0x1ff;
@@ -650,11 +706,20 @@ int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &t
   p.tiles_y = (int)cdiv(p.Ho, g.TH);
   p.num_n_tiles = p.Cout / n_tile;
   const int num_units = (int)cdiv((int64_t)p.tiles_x * p.tiles_y * p.B, CG) * p.num_n_tiles;
+  if (ts == 2) {
+    // two 64-channel outputs, Wo columns each (the caller's buffers have the padding for the surplus end columns)
+    if (p.out_row_px <= 0) { set_error("conv_halo: pair mode needs padded output rows"); return OCRB_ERR_INVALID; }
+    CUtensorMap tmO, tmO2;
+    OCRB_TRY(make_act_tensor_map_pitched(&tmO, p.out + p.out_coff, p.B, p.Ho, p.Wo, 64, p.out_ldc, g.TW, g.sub_rows, p.out_step, p.out_row_px));
+    OCRB_TRY(make_act_tensor_map_pitched(&tmO2, p.out2 + p.out_coff, p.B, p.Ho, p.Wo, 64, p.out_ldc, g.TW, g.sub_rows, p.out_step, p.out_row_px));
+    return CG == 2 ? launch_halo_one<128, 2, 2, 1>(ctx, tmA, tmB, tmD, tmO, tmO2, p, g, num_units, tag)
+                   : launch_halo_one<128, 2, 1, 1>(ctx, tmA, tmB, tmD, tmO, tmO2, p, g, num_units, tag);
+  }
   if (ts) {
     // output slice [B][Ho][Wo][Cout] at channel offset out_coff of an out_ldc-wide buffer; residual [B][Ho][Wo][Cout]
     CUtensorMap tmO, tmR;
-    OCRB_TRY(make_act_tensor_map_pitched(&tmO, p.out + p.out_coff, p.B, p.Ho, p.Wo, p.Cout, p.out_ldc, g.TW, g.sub_rows, p.out_step));
-    if (p.residual) OCRB_TRY(make_act_tensor_map_pitched(&tmR, p.residual, p.B, p.Ho, p.Wo, p.Cout, p.Cout, g.TW, g.sub_rows));
+    OCRB_TRY(make_act_tensor_map_pitched(&tmO, p.out + p.out_coff, p.B, p.Ho, p.Wo, p.Cout, p.out_ldc, g.TW, g.sub_rows, p.out_step, p.out_row_px));
+    if (p.residual) OCRB_TRY(make_act_tensor_map_pitched(&tmR, p.residual, p.B, p.Ho, p.Wo, p.Cout, p.Cout, g.TW, g.sub_rows, 1, p.res_row_px));
     else tmR = tmO;
     return CG == 2 ? launch_halo_one<64, 4, 2, 1>(ctx, tmA, tmB, tmD, tmO, tmR, p, g, num_units, tag)
                    : launch_halo_one<64, 4, 1, 1>(ctx, tmA, tmB, tmD, tmO, tmR, p, g, num_units, tag);

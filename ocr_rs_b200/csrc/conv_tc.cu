@@ -369,12 +369,13 @@ int make_act_tensor_map_box(CUtensorMap *map, const void *base, int B, int H, in
 }
 
 // a C-channel slice of pixels that are ldc channels apart ([B][H][W][ldc], base already at the slice): TMA store / residual load box
-// step > 1: the H x W positions sit on every step-th pixel and row of a (H*step) x (W*step) map
-int make_act_tensor_map_pitched(CUtensorMap *map, const void *base, int B, int H, int W, int C, int ldc, int box_w, int box_h, int step) {
+// step > 1: the H x W positions sit on every step-th pixel and row of a (H*step) x (W*step) map; row_px > 0: pixels per
+// (full-resolution) row of the buffer when its rows are padded
+int make_act_tensor_map_pitched(CUtensorMap *map, const void *base, int B, int H, int W, int C, int ldc, int box_w, int box_h, int step, int row_px) {
   auto fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return OCRB_ERR_CUDA; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  const cuuint64_t row = (cuuint64_t)W * step * ldc * 2;  // bytes of one full-resolution row
+  const cuuint64_t row = (cuuint64_t)(row_px > 0 ? row_px : W * step) * ldc * 2;  // bytes of one full-resolution row
   cuuint64_t strides[3] = {(cuuint64_t)ldc * 2 * step, row * step, row * (cuuint64_t)H * step};
   cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};

@@ -29,6 +29,16 @@ struct ConvTcParams {
   // never read) and the pixel step of the output (2: results land on every second pixel / row of a map twice
   // as large — `out` then points at the first of them)
   int tap_mask = 0x1ff, out_step = 1;
+  // conv_halo "pair" mode (N tile 128 through the TMA-store epilogue): the two 64-channel halves are two different
+  // convolutions of the same input patch whose results belong to neighbouring output columns — half 0 goes to `out` at
+  // column X - 1, half 1 to `out2` at column X (X = output column of the tile, Wo = input width + 1, the input tile
+  // starts one column further left: in_x_off = -1).  Used for the parity-class convolutions of the fused neck.
+  int pair_mode = 0, in_x_off = 0;
+  __nv_bfloat16 *out2 = nullptr;
+  // TMA-store path: pixels per full-resolution row of the out / residual buffers when their rows are padded (0 = dense).
+  // TMA stores take no negative coordinates, so pair mode writes its column -1 (and Wo - 1 of `out2`) into padding:
+  // both outputs are Wo columns wide.
+  int out_row_px = 0, res_row_px = 0;
   const __nv_bfloat16 *up_src = nullptr;    // [B][Ho/2][Wo/2][Cout]
   __nv_bfloat16 *sum_out = nullptr;         // [B][Ho][Wo][Cout] = y + up2(up_src)
   // DB head tail
@@ -52,7 +62,7 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
                    const HeadConsts *hc = nullptr);
 
 // conv_halo.cu: 3x3 stride-1 convolutions with the halo'd input tile resident in shared memory
-int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G, int rep);
+int make_halo_act_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int n_tile, int G, int rep, int pair = 0);
 bool halo_use_ts(int n_tile, int rep);  // TMA-store epilogue in use for this tile shape
 int halo_weight_box_rows(int n_tile);  // rows of the weight TMA box (half the N tile in CTA-pair mode)
 int make_halo_ds_map(CUtensorMap *map, const void *base, int B, int H, int W, int C, int Ho, int Wo, int n_tile, int G);

@@ -158,6 +158,7 @@ struct DevConv {
   bool has_bn = false;
   int ds_cin = 0;  // > 0: w16 carries a fused 1x1 stride-2 downsample of ds_cin channels after the 9 taps
   int tap_mask = 0x1ff;  // 3x3 taps with non-zero weights (class kernels of the fused FPN level use 4 of 9)
+  bool pair = false;     // conv_halo pair mode: 128 rows = two parity-class kernels sharing one input patch
   DevBuf w32;    // fp32 [k*k][cin][cout]
   DevBuf w16;    // bf16 [cout][k*k*cin]
   DevBuf scale, shift;
@@ -294,6 +295,27 @@ static int upload_plain_conv3(const std::vector<float> &w, int cin, int cout, in
   return upload(dc.w16, w16);
 }
 
+// Classes (a, 1) at low-res column X and (a, 0) at column X + 1 read the SAME 2x2 input patch (columns X, X + 1): one
+// 128-row weight matrix = [class (a,1) | class (a,0) shifted one tap to the right], taps rows(a) x {1, 2}, feeds both from
+// one operand tile (N = 128: the tensor pipe is no longer starved by shared-memory operand reads as with N = 64).
+// conv_halo's pair mode stores half 0 at column X and half 1 at column X + 1 of their pixel-shuffled positions.
+static int upload_pair_conv3(const std::vector<float> &w_b1, const std::vector<float> &w_b0, int cin, int a, DevConv &dc) {
+  std::vector<float> wp((size_t)128 * cin * 9, 0.0f);
+  int mask = 0;
+  for (int rr = a; rr <= a + 1; ++rr)  // rows(a): {0, 1} for a = 0, {1, 2} for a = 1
+    for (int ss = 1; ss <= 2; ++ss) {
+      mask |= 1 << (rr * 3 + ss);
+      for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < cin; ++ci) {
+          wp[((size_t)co * cin + ci) * 9 + rr * 3 + ss] = w_b1[((size_t)co * cin + ci) * 9 + rr * 3 + ss];
+          wp[((size_t)(64 + co) * cin + ci) * 9 + rr * 3 + ss] = w_b0[((size_t)co * cin + ci) * 9 + rr * 3 + ss - 1];
+        }
+    }
+  OCRB_TRY(upload_plain_conv3(wp, cin, 128, mask, dc));
+  dc.pair = true;
+  return OCRB_OK;
+}
+
 // one FPN level: out_l(in_l(x_l) + up2(in_u(x_u))) -> "<out>.x" (3x3 on x_l, composed) + "<out>.up{a}{b}" (4-tap classes on x_u)
 static int prep_fused_fpn_level(const HostWeights &hw, const std::string &out, const std::string &in_l, const std::string &in_u, int c_l, int c_u,
                                 std::map<std::string, DevConv> &conv) {
@@ -303,6 +325,7 @@ static int prep_fused_fpn_level(const HostWeights &hw, const std::string &out, c
   std::vector<float> wc;
   compose_weights(*wo, *wi, 64, 256, c_l, wc);
   OCRB_TRY(upload_plain_conv3(wc, c_l, 64, 0x1ff, conv[out + ".x"]));
+  std::vector<float> cls[2][2];
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       // low-res tap r' (row offset r' - 1) collects the full-res taps dy whose source row (2Y + a + dy) >> 1 is Y + r' - 1
@@ -320,7 +343,9 @@ static int prep_fused_fpn_level(const HostWeights &hw, const std::string &out, c
       std::vector<float> wkc;
       compose_weights(wk, *wu, 64, 256, c_u, wkc);
       OCRB_TRY(upload_plain_conv3(wkc, c_u, 64, mask, conv[out + ".up" + std::to_string(a) + std::to_string(b)]));
+      cls[a][b].swap(wkc);
     }
+  for (int a = 0; a < 2; ++a) OCRB_TRY(upload_pair_conv3(cls[a][1], cls[a][0], c_u, a, conv[out + ".pair" + std::to_string(a)]));
   return OCRB_OK;
 }
 
@@ -352,6 +377,7 @@ static int prep_fused_bin_p3(const HostWeights &hw, std::map<std::string, DevCon
   OCRB_TRY(upload(m.scale, sc));
   OCRB_TRY(upload(m.shift, sh));
   m.scale_h = sc; m.shift_h = sh;
+  std::vector<float> cls[2][2];
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       std::vector<float> wk((size_t)64 * 192 * 9, 0.0f);
@@ -365,7 +391,9 @@ static int prep_fused_bin_p3(const HostWeights &hw, std::map<std::string, DevCon
               wk[((size_t)co * 192 + ci) * 9 + rr * 3 + ss] += sc[co] * (*wb)[((size_t)co * 256 + ci) * 9 + (dy + 1) * 3 + dx + 1];
         }
       OCRB_TRY(upload_plain_conv3(wk, 192, 64, mask, conv["bin_conv1.up" + std::to_string(a) + std::to_string(b)]));
+      cls[a][b].swap(wk);
     }
+  for (int a = 0; a < 2; ++a) OCRB_TRY(upload_pair_conv3(cls[a][1], cls[a][0], 192, a, conv["bin_conv1.pair" + std::to_string(a)]));
   return OCRB_OK;
 }
 
@@ -389,7 +417,8 @@ struct ocrb_det {
   HeadConsts head_c;                     // bf16 path: head constants passed as a kernel parameter
   // activations (grow-only), keyed by name
   std::map<std::string, DevBuf> act;
-  DevBuf staged_in, staged_out, err;
+  DevBuf staged_in, staged_out;
+  PinBuf err;  // pipeline-timeout code: pinned host memory written by the kernels, readable even after a trap killed the context
   // last forward (for taps)
   int last_B = 0, last_H = 0, last_W = 0;
   // BF16 mode: level 2 of the FPN computed from x1 and in3 directly (prep_fused_fpn2) and p3 kept out of the concat
@@ -486,7 +515,7 @@ static int det_build(ocrb_det *d, const HostWeights &hw) {
       for (int co = 0; co < 64; ++co) d->head_c.w2[co * 4 + q] = w2t[q * 64 + co];
   }
   OCRB_TRY(d->err.reserve(4));
-  OCRB_CUDA(cudaMemset(d->err.p, 0, 4));
+  *d->err.as<int>() = 0;
   return OCRB_OK;
 }
 
@@ -638,7 +667,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
   bf *up2 = nullptr;  // fused FPN level 2: out2's share of up2(in3), pixel-shuffled, [B][H4][W4][64]
   bf *p3 = nullptr;
   if (d->fpn2_fused) {
-    OCRB_TRY(act(d, "b.up2", (int64_t)B * H4 * W4 * 64, &up2));
+    OCRB_TRY(act(d, "b.up2", (int64_t)B * H4 * (W4 + 2) * 64, &up2));  // rows padded by one pixel at either end (class_convs)
     OCRB_TRY(act(d, "b.cat3", (int64_t)B * fh[1] * fw[1] * 192, &p3));
   }
   for (auto &kv : d->act) after += kv.second.cap;
@@ -666,11 +695,15 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
       return launch_conv_lateral(ctx, in, c.w16.as<bf>(), p.up_src, p.out, p.sum_out, B, h, w, c.cin, d->err.as<int>(), ("tc:" + name).c_str());
     const bool halo = use_halo && c.k == 3 && c.stride == 1 && !p.sum_out && p.out;
     const int nt = halo ? (c.cout == 64 ? 64 : 128) : n_tile_for(c.cout);
+    if (c.pair) {
+      OCRB_REQUIRE(halo && p.out2, "pair convolution needs the halo kernel and two outputs");
+      p.pair_mode = 1; p.in_x_off = -1;
+    }
     if (halo) {
       auto it = d->maps.m.find("h." + name);
       if (it == d->maps.m.end()) {
         CUtensorMap m;
-        OCRB_TRY(make_halo_act_map(&m, in, B, h, w, c.cin, nt, nt == 64 ? 4 : 2, p.rep));
+        OCRB_TRY(make_halo_act_map(&m, in, B, h, w, c.cin, nt, nt == 64 ? 4 : 2, p.rep, c.pair ? 1 : 0));
         it = d->maps.m.emplace("h." + name, m).first;
       }
       ma = &it->second;
@@ -692,7 +725,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     }
     p.B = B;
     p.Ho = (h + 2 * c.pad - c.k) / c.stride + 1;
-    p.Wo = (w + 2 * c.pad - c.k) / c.stride + 1;
+    p.Wo = (w + 2 * c.pad - c.k) / c.stride + 1 + (c.pair ? 1 : 0);  // pair mode: output columns -1 .. w - 1
     p.Cout = c.cout;
     p.R = c.k; p.S = c.k; p.cin_chunks = c.cin / 64; p.stride = c.stride; p.pad = c.pad;
     p.scale = c.has_bn ? c.scale.as<float>() : nullptr;  // no batch-norm: identity epilogue
@@ -705,6 +738,30 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     const std::string tag = "tc:" + name;
     if (halo) return launch_conv_halo(ctx, *ma, *mb, p, nt, tag.c_str(), md);
     return launch_conv_tc(ctx, *ma, *mb, p, nt, EPI_STD, tag.c_str());
+  };
+  // the four parity-class convolutions of `in` (hl x wl), pixel-shuffled into dst [B][2 hl][2 wl][64]: two pair launches
+  // (N = 128, classes (a,1) | (a,0) from one operand tile), or four single-class launches with OCRB_PAIR=0
+  static const bool use_pairs = !(getenv("OCRB_PAIR") && atoi(getenv("OCRB_PAIR")) == 0);
+  auto class_convs = [&](const std::string &prefix, const bf *in, int hl, int wl, bf *dst) -> int {
+    // dst rows are padded: pixel x of a row sits at column x + 1 of 2 wl + 2 (TMA stores take no negative coordinates, and
+    // a pair launch produces one surplus column at either end)
+    const int64_t wp = 2 * (int64_t)wl + 2;
+    for (int a = 0; a < 2; ++a) {
+      if (use_pairs) {
+        // output index i = low-res column + 1: class (a,1) of column i - 1 -> pixel 2i - 1 -> padded column 2i;
+        // class (a,0) of column i -> pixel 2i -> padded column 2i + 1
+        ConvTcParams k;
+        k.out = dst + (a * wp) * 64; k.out2 = dst + (a * wp + 1) * 64; k.out_ldc = 64; k.out_step = 2; k.out_row_px = (int)wp;
+        OCRB_TRY(conv(prefix + ".pair" + std::to_string(a), in, hl, wl, k));
+      } else {
+        for (int b = 0; b < 2; ++b) {
+          ConvTcParams k;
+          k.out = dst + (a * wp + b + 1) * 64; k.out_ldc = 64; k.out_step = 2; k.out_row_px = (int)wp;
+          OCRB_TRY(conv(prefix + ".up" + std::to_string(a) + std::to_string(b), in, hl, wl, k));
+        }
+      }
+    }
+    return OCRB_OK;
   };
   const bf *x = x0;
   int h = H4, w = W4;
@@ -764,15 +821,10 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
       OCRB_TRY(conv("out3", s3, fh[1], fw[1], q));
     } else {
       // p3 = conv3x3(W_out3 o W_in3)(x2) + [class convolutions of x3, pixel-shuffled into the first quarter of up2]
-      for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b) {
-          ConvTcParams k;
-          k.out = up2 + ((int64_t)a * fw[1] + b) * 64; k.out_ldc = 64; k.out_step = 2;
-          OCRB_TRY(conv("out3.up" + std::to_string(a) + std::to_string(b), feat[2], fh[2], fw[2], k));
-        }
-      q.residual = up2;
+      OCRB_TRY(class_convs("out3", feat[2], fh[2], fw[2], up2));
+      q.residual = up2 + 64; q.res_row_px = fw[1] + 2;
       OCRB_TRY(conv("out3.x", feat[1], fh[1], fw[1], q));
-      q.residual = nullptr;
+      q.residual = nullptr; q.res_row_px = 0;
     }
     q.out = fuse; q.out_ldc = fuse_c;
     q.out_coff = d->fpn2_fused ? 0 : 192; q.rep = 1;
@@ -780,13 +832,8 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
       OCRB_TRY(conv("out2", s2, fh[0], fw[0], q));
     } else {
       // p2 = conv3x3(W_out2 o W_in2)(x1) + [four 2x2 class convolutions of in3, pixel-shuffled into up2] (see prep_fused_fpn2)
-      for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b) {
-          ConvTcParams k;
-          k.out = up2 + ((int64_t)a * fw[0] + b) * 64; k.out_ldc = 64; k.out_step = 2;
-          OCRB_TRY(conv("out2.up" + std::to_string(a) + std::to_string(b), feat[1], fh[1], fw[1], k));
-        }
-      q.residual = up2;
+      OCRB_TRY(class_convs("out2", feat[1], fh[1], fw[1], up2));
+      q.residual = up2 + 64; q.res_row_px = fw[0] + 2;
       OCRB_TRY(conv("out2.x", feat[0], fh[0], fw[0], q));
     }
   }
@@ -796,14 +843,9 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
     OCRB_TRY(conv("bin_conv1", fuse, H4, W4, q));
   } else {
     // up2 is free again (out2.x1 consumed it, same stream): it now collects the share of cat3 = [p5 | p4 | p3] in bin_conv1
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b) {
-        ConvTcParams k;
-        k.out = up2 + ((int64_t)a * fw[0] + b) * 64; k.out_ldc = 64; k.out_step = 2;
-        OCRB_TRY(conv("bin_conv1.up" + std::to_string(a) + std::to_string(b), p3, fh[1], fw[1], k));
-      }
+    OCRB_TRY(class_convs("bin_conv1", p3, fh[1], fw[1], up2));
     ConvTcParams q;
-    q.relu = 1; q.out = b1; q.residual = up2;
+    q.relu = 1; q.out = b1; q.residual = up2 + 64; q.res_row_px = fw[0] + 2;
     OCRB_TRY(conv("bin_conv1.main", fuse, H4, W4, q));
   }
   {  // head tail
@@ -841,9 +883,8 @@ int det_forward_device(ocrb_det *det, const void *img_dev, int dtype, int B, int
 ocrb_ctx *det_ctx(ocrb_det *det) { return det->ctx; }
 int det_mode(ocrb_det *det) { return det->mode; }
 int det_check_err(ocrb_det *det) {
-  int err = 0;
-  OCRB_CUDA(cudaMemcpy(&err, det->err.p, 4, cudaMemcpyDeviceToHost));
-  if (err) { set_error("conv_tc pipeline timeout (code %d)", err); return OCRB_ERR_INTERNAL; }
+  const int err = *reinterpret_cast<volatile int *>(det->err.p);
+  if (err) { set_error("tcgen05 pipeline timeout (wait site %d)", err); return OCRB_ERR_INTERNAL; }
   return OCRB_OK;
 }
 
@@ -886,12 +927,8 @@ int ocrb_det_destroy(ocrb_det *d) {
   return OCRB_OK;
 }
 
-int ocrb_det_forward(ocrb_det *det, const void *images, int dtype, int B, int H, int W, float *prob) {
-  OCRB_REQUIRE(det && images && prob, "null argument");
-  OCRB_REQUIRE(dtype == OCRB_U8 || dtype == OCRB_F32, "unknown dtype %d", dtype);
-  OCRB_REQUIRE(B > 0 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "H and W must be positive multiples of 32 (got %dx%d, B=%d)", H, W, B);
+static int det_forward_chunks(ocrb_det *det, const void *images, int dtype, int B, int H, int W, float *prob) {
   ocrb_ctx *ctx = det->ctx;
-  OCRB_CUDA(cudaSetDevice(ctx->device));
   const size_t esz = dtype == OCRB_U8 ? 1 : 4;
   const int64_t HW = (int64_t)H * W;
   const int chunk = det->mode == OCRB_MODE_BF16 ? 64 : 4;
@@ -916,11 +953,18 @@ int ocrb_det_forward(ocrb_det *det, const void *images, int dtype, int B, int H,
     // host staging buffers are reused by the next chunk
     if (!in_dev || !out_dev) OCRB_TRY(sync(ctx));
   }
-  OCRB_TRY(sync(ctx));
-  int err = 0;
-  OCRB_CUDA(cudaMemcpy(&err, det->err.p, 4, cudaMemcpyDeviceToHost));
-  if (err) { set_error("conv_tc pipeline timeout (code %d)", err); return OCRB_ERR_INTERNAL; }
-  return OCRB_OK;
+  return sync(ctx);
+}
+
+int ocrb_det_forward(ocrb_det *det, const void *images, int dtype, int B, int H, int W, float *prob) {
+  OCRB_REQUIRE(det && images && prob, "null argument");
+  OCRB_REQUIRE(dtype == OCRB_U8 || dtype == OCRB_F32, "unknown dtype %d", dtype);
+  OCRB_REQUIRE(B > 0 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "H and W must be positive multiples of 32 (got %dx%d, B=%d)", H, W, B);
+  OCRB_CUDA(cudaSetDevice(det->ctx->device));
+  const int rc = det_forward_chunks(det, images, dtype, B, H, W, prob);
+  // a bounded pipeline wait that expired traps the kernel: name the wait site instead of the generic CUDA error
+  if (det_check_err(det) != OCRB_OK) return OCRB_ERR_INTERNAL;
+  return rc;
 }
 
 int ocrb_det_tap(ocrb_det *det, const char *name, float *out, int64_t numel) {

@@ -39,8 +39,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) {
-      if (err) atomicExch(err, code);
-      __threadfence_system();
+      if (err) {
+        // pinned host memory: let the write land before the trap takes the context down
+        *reinterpret_cast<volatile int *>(err) = code;
+        __threadfence_system();
+        const long long t1 = clock64();
+        while (clock64() - t1 < 2000000ll) {}
+      }
       __trap();
     }
   }

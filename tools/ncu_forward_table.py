@@ -20,10 +20,11 @@ L += [("in5", 25 * 25 * 256 * 512), ("in4(+sum)", 50 * 50 * 256 * 256)]
 L += [("out5(x4)", 25 * 25 * 64 * 2304), ("out4(x2)", 50 * 50 * 64 * 2304)]
 # FPN levels 3 and 2 without their 256-channel intermediates (detector.cu prep_fused_fpn_level): four 4-tap class
 # convolutions of the level above's backbone feature + the composed 3x3 on the level's own; MACs actually executed
-L += [(f"out3.up{a}{b}", 50 * 50 * 64 * 1024) for a in (0, 1) for b in (0, 1)] + [("out3.x(+res)", 100 * 100 * 64 * 1152)]
-L += [(f"out2.up{a}{b}", 100 * 100 * 64 * 512) for a in (0, 1) for b in (0, 1)] + [("out2.x(+res)", 200 * 200 * 64 * 576)]
-# cat3 = [p5^4 | p4^2 | p3] reaches bin_conv1 through four 4-tap class convolutions (prep_fused_bin_p3); the main part reads p2
-L += [(f"bin_conv1.up{a}{b}", 100 * 100 * 64 * 768) for a in (0, 1) for b in (0, 1)] + [("bin_conv1.main(+res)", 200 * 200 * 64 * 576)]
+# parity classes run as pairs: classes (a,1) | (a,0) of neighbouring columns share one operand tile (N = 128, conv_halo pair mode)
+L += [(f"out3.pair{a}", 50 * 50 * 128 * 1024) for a in (0, 1)] + [("out3.x(+res)", 100 * 100 * 64 * 1152)]
+L += [(f"out2.pair{a}", 100 * 100 * 128 * 512) for a in (0, 1)] + [("out2.x(+res)", 200 * 200 * 64 * 576)]
+# cat3 = [p5^4 | p4^2 | p3] reaches bin_conv1 through its class pairs (prep_fused_bin_p3); the main part reads p2
+L += [(f"bin_conv1.pair{a}", 100 * 100 * 128 * 768) for a in (0, 1)] + [("bin_conv1.main(+res)", 200 * 200 * 64 * 576)]
 L += [("head", 200 * 200 * 256 * 64 + 400 * 400 * 4 * 64)]
 
 # REPORT may also be the `ncu -i REPORT.ncu-rep --page raw --csv` export (reports over 64 MiB do not travel back from the GPU box)
