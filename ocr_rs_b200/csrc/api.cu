@@ -80,6 +80,7 @@ int ocrb_ctx_destroy(ocrb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   free_pp(ctx);
   for (auto &b : ctx->stage) b.release();
+  ctx->ccl_tile_empty.release();
   for (auto &b : ctx->pin) b.release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -59,7 +59,8 @@ constexpr int CCL_THREADS = 256;
 constexpr int CCL_ROWS_PER_WARP = CCL_TH / (CCL_THREADS / 32);
 
 __global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *__restrict__ bitmap, int H, int W,
-                                                                 int tiles_x, int tiles_y, int *__restrict__ labels) {
+                                                                 int tiles_x, int tiles_y, int *__restrict__ labels,
+                                                                 uint8_t *__restrict__ tile_empty) {
   __shared__ int L[CCL_TW * CCL_TH];
   __shared__ uint32_t rowbits[CCL_TH], rowvalid[CCL_TH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -78,7 +79,9 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *_
   int any_fg = 0;
 #pragma unroll
   for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) any_fg |= fgv[k];
-  if (!__syncthreads_or(any_fg)) {
+  const int none = !__syncthreads_or(any_fg);
+  if (threadIdx.x == 0) tile_empty[blockIdx.x] = (uint8_t)none;  // lets the seam pass skip this tile's border without reading it
+  if (none) {
     const int origin = ty * CCL_TH * W + tx * CCL_TW;
 #pragma unroll
     for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) {
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *_
 // it in global memory (same adjacency rules as pass 1).
 // ---------------------------------------------------------------------------------------
 __global__ void ccl_seam_kernel(const uint8_t *__restrict__ bitmap, int H, int W, int B, int tiles_x, int tiles_y,
-                                int *__restrict__ labels) {
+                                int *__restrict__ labels, const uint8_t *__restrict__ tile_empty) {
   // one thread per tile-border pixel: top row + left column + right column of every tile
   constexpr int PER_TILE = CCL_TW + 2 * CCL_TH;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,6 +164,17 @@ __global__ void ccl_seam_kernel(const uint8_t *__restrict__ bitmap, int H, int W
   const bool on_left = (x % CCL_TW) == 0, on_right = (x % CCL_TW) == CCL_TW - 1, on_top = (y % CCL_TH) == 0;
   // corner pixels appear in two of the three groups: let the top-row instance do the work
   if (k >= CCL_TW && on_top) return;
+  // Tiles without foreground are single background rectangles already pointing at their origin.  Between two such
+  // tiles the corner thread (k = 0, which always runs the full rules) makes the one link that is needed:
+  //   * right column: only foreground pixels link diagonally from there;
+  //   * left column below the corner: the link to the left tile is redundant;
+  //   * top row right of the corner: the link upwards is skipped by the run rule anyway (left and up-left are
+  //     background of the same two tiles).
+  if (tile_empty[tile]) {
+    if (k >= CCL_TW + CCL_TH) return;
+    if (k >= CCL_TW && tx > 0 && tile_empty[tile - 1]) return;
+    if (k > 0 && k < CCL_TW && ty > 0 && tile_empty[tile - tiles_x]) return;
+  }
   const int64_t HW = (int64_t)H * W;
   const uint8_t *bm = bitmap + b * HW;
   int *L = labels + b * HW;
@@ -198,10 +212,12 @@ __global__ void ccl_flatten_kernel(int H, int W, int B, int *__restrict__ labels
 int launch_ccl(ocrb_ctx *ctx, const uint8_t *bitmap, int B, int H, int W, int *labels, bool flatten) {
   int tiles_x = (int)cdiv(W, CCL_TW), tiles_y = (int)cdiv(H, CCL_TH);
   int64_t blocks = (int64_t)tiles_x * tiles_y * B;
-  ccl_local_kernel<<<(unsigned)blocks, CCL_THREADS, 0, ctx->stream>>>(bitmap, H, W, tiles_x, tiles_y, labels);
+  OCRB_TRY(ctx->ccl_tile_empty.reserve((size_t)blocks));
+  uint8_t *tile_empty = ctx->ccl_tile_empty.as<uint8_t>();
+  ccl_local_kernel<<<(unsigned)blocks, CCL_THREADS, 0, ctx->stream>>>(bitmap, H, W, tiles_x, tiles_y, labels, tile_empty);
   OCRB_TRY(check_launch(ctx, "ccl_local"));
   int64_t n = (int64_t)B * H * W;
-  ccl_seam_kernel<<<(unsigned)cdiv(blocks * (CCL_TW + 2 * CCL_TH), 256), 256, 0, ctx->stream>>>(bitmap, H, W, B, tiles_x, tiles_y, labels);
+  ccl_seam_kernel<<<(unsigned)cdiv(blocks * (CCL_TW + 2 * CCL_TH), 256), 256, 0, ctx->stream>>>(bitmap, H, W, B, tiles_x, tiles_y, labels, tile_empty);
   OCRB_TRY(check_launch(ctx, "ccl_seam"));
   if (!flatten) return OCRB_OK;
   ccl_flatten_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(H, W, B, labels);
