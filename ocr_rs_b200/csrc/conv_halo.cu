@@ -47,7 +47,8 @@ constexpr int HL_MAX_OBUFS = 4;
 // bank (shared memory is the bottleneck of the N = 64 kernels — operand reads alone exceed its bandwidth)
 struct HaloAffine { float scale[64], shift[64]; };
 
-// TS = 1 (N_TILE = 64 only): the epilogue leaves through TMA.  Sub-tiles are row-aligned, so a
+// TS = 1: the epilogue leaves through TMA (N_TILE = 64; N_TILE = 128 is the "pair" mode of the fused neck: two
+// 64-channel convolutions of one operand tile, one staging tile and one destination map per half — conv_tc.cuh).  Sub-tiles are row-aligned, so a
 // sub-tile's valid outputs are one box {64 ch, TW, sub_rows}; the epilogue threads write their own
 // pixel row (bf16, 128B-swizzled) into a staging tile and one extra warp turns full tiles into
 // cp.async.bulk.tensor stores (image borders clipped by the hardware) and TMA-loads the residual
