@@ -157,6 +157,11 @@ int ocrb_find_contours(ocrb_ctx *ctx, const uint8_t *bitmap, int H, int W,
 int ocrb_approx_polygon(ocrb_ctx *ctx, const int32_t *chain_xy, int64_t n_pts,
                         int32_t *out_xy, int64_t out_cap_pts, int64_t *n_out);
 
+/* host-only test hook (no device needed): the tiling the 3x3 convolution kernel (csrc/conv_halo.cu) would choose for an
+ * Ho x Wo map.  mode 0 = N tile 128 (linear sub-tiles), 1 = N tile 64 with the TMA-store epilogue, 2 = pair mode.
+ * out[10] = {PW, TH, TW, sub_rows, sub_stride, a_stage_bytes, a_stages, b_stages, obufs * obuf_bytes, dynamic smem bytes} */
+int ocrb_debug_conv_geometry(int Ho, int Wo, int mode, int *out);
+
 /* ---- char_recognition ---------------------------------------------------------------
  * Net::new + vs.load (char_recognition/model.rs:12-25, mod.rs:43-45).  Names: canonical
  * "conv1.weight" ... "fc2.bias" or the de-duplicated VarStore names. */

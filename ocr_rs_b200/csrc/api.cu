@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 namespace ocrb {
+int debug_conv_geometry(int Ho, int Wo, int mode, int *out);
 
 static thread_local std::string g_last_error;
 
@@ -232,6 +233,11 @@ int ocrb_ccl_labels(ocrb_ctx *ctx, const uint8_t *bitmap, int B, int H, int W, i
 char ocrb_class_to_char(int cls) {
   static const char *VALUES = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789";  // utils.rs:7
   return (cls >= 0 && cls < 62) ? VALUES[cls] : '?';
+}
+
+int ocrb_debug_conv_geometry(int Ho, int Wo, int mode, int *out) {
+  OCRB_REQUIRE(out && Ho > 0 && Wo > 0 && mode >= 0 && mode <= 2, "bad argument");
+  return ocrb::debug_conv_geometry(Ho, Wo, mode, out);
 }
 
 }  // extern "C"

@@ -546,9 +546,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ---------------------------------------------------------------------------------------
 // Picks the padded pitch / tile height for a Wo-wide map: TH * PW <= G * 128, valid fraction
 // (TW / PW) * (TH * PW / (G*128)) * (coverage of Wo and Ho by whole tiles) maximised.
-static void pick_geom(int Ho, int Wo, int G, int *PW, int *TH) {
+static void pick_geom(int Ho, int Wo, int G, int max_tw, int *PW, int *TH) {
   double best = -1.0;
-  for (int tw = 8; tw <= 254 && tw <= Wo + 7; ++tw) {
+  for (int tw = 8; tw <= max_tw && tw <= Wo + 7; ++tw) {
     const int pw = tw + 2;
     int th = G * 128 / pw;
     if (th > 254) th = 254;
@@ -564,9 +564,9 @@ static void pick_geom(int Ho, int Wo, int G, int *PW, int *TH) {
 }
 
 // Row-aligned variant (TMA-store epilogue): each sub-tile = sub_rows whole rows of pitch PW.
-static void pick_geom_rows(int Ho, int Wo, int G, int *PW, int *sub_rows) {
+static void pick_geom_rows(int Ho, int Wo, int G, int max_tw, int *PW, int *sub_rows) {
   double best = -1.0;
-  for (int tw = 8; tw <= 126 && tw <= Wo + 7; ++tw) {
+  for (int tw = 8; tw <= max_tw && tw <= 126 && tw <= Wo + 7; ++tw) {
     const int pw = tw + 2;
     int rps = 128 / pw;
     const int need = (Ho + G - 1) / G;
@@ -586,14 +586,26 @@ bool halo_use_ts(int n_tile, int rep) {
   return on && n_tile == 64 && rep == 1;
 }
 
+static int halo_geometry_try(int Ho, int Wo, int n_tile, int G, int ts, int max_tw, HaloGeom *out);
+
+// A very wide, very flat map (one row of 240 pixels, say) would pick a tile whose halo'd operand stage leaves no room
+// for the weight ring: retry with narrower tiles until everything fits.
 int halo_geometry(int Ho, int Wo, int n_tile, int G, int ts, HaloGeom *out) {  // n_tile = weight rows per CTA
+  for (int max_tw = 254; max_tw >= 8; max_tw /= 2)
+    if (halo_geometry_try(Ho, Wo, n_tile, G, ts, max_tw, out) == OCRB_OK) return OCRB_OK;
+  set_error("conv_halo: no tiling of a %dx%d map fits shared memory", Wo, Ho);
+  return OCRB_ERR_INTERNAL;
+}
+
+static int halo_geometry_try(int Ho, int Wo, int n_tile, int G, int ts, int max_tw, HaloGeom *out) {
   HaloGeom g;
   if (ts) {
-    pick_geom_rows(Ho, Wo, G, &g.PW, &g.sub_rows);
+    pick_geom_rows(Ho, Wo, G, max_tw, &g.PW, &g.sub_rows);
     g.TH = G * g.sub_rows;
     g.sub_stride = g.sub_rows * g.PW;
   } else {
-    pick_geom(Ho, Wo, G, &g.PW, &g.TH);
+    // PW <= 128: the fused-downsample input is a stride-2 TMA box of 2 * PW pixels (box dimensions are limited to 256)
+    pick_geom(Ho, Wo, G, max_tw < 126 ? max_tw : 126, &g.PW, &g.TH);
     g.sub_rows = 0;
     g.sub_stride = 128;
   }
@@ -619,7 +631,7 @@ int halo_geometry(int Ho, int Wo, int n_tile, int G, int ts, HaloGeom *out) {  /
     if (budget - 3 * g.a_stage_bytes >= 6 * b_bytes) { g.a_stages = 3; g.b_stages = (budget - 3 * g.a_stage_bytes) / b_bytes; }
     if (g.b_stages > 8) g.b_stages = 8;
   }
-  if (g.b_stages < 2) { set_error("conv_halo: tile %dx%d does not fit shared memory", g.PW, g.TH); return OCRB_ERR_INTERNAL; }
+  if (g.b_stages < 2) return OCRB_ERR_INTERNAL;  // the caller retries with narrower tiles
   *out = g;
   return OCRB_OK;
 }
@@ -729,6 +741,19 @@ int launch_conv_halo(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &t
   if (n_tile == 128) return CG == 2 ? launch_halo_one<128, 2, 2, 0>(ctx, tmA, tmB, tmD, tmA, tmA, p, g, num_units, tag) : launch_halo_one<128, 2, 1, 0>(ctx, tmA, tmB, tmD, tmA, tmA, p, g, num_units, tag);
   set_error("conv_halo: unsupported N tile %d", n_tile);
   return OCRB_ERR_INVALID;
+}
+
+// host-side view of the tiling for tests (include/ocrb.h)
+int debug_conv_geometry(int Ho, int Wo, int mode, int *out) {
+  const int cg = halo_cg();
+  const int n_tile = mode == 1 ? 64 : 128, G = mode == 1 ? 4 : 2;
+  HaloGeom g;
+  OCRB_TRY(halo_geometry(Ho, Wo + (mode == 2 ? 1 : 0), n_tile / cg, G, mode, &g));
+  const int stg = mode ? g.obufs * g.obuf_bytes : HL_STG_BYTES;
+  const int smem = 1024 + g.a_stages * g.a_stage_bytes + g.b_stages * (n_tile / cg) * 128 + stg + 512;
+  const int v[10] = {g.PW, g.TH, g.TW, g.sub_rows, g.sub_stride, g.a_stage_bytes, g.a_stages, g.b_stages, stg, smem};
+  for (int i = 0; i < 10; ++i) out[i] = v[i];
+  return OCRB_OK;
 }
 
 }  // namespace ocrb

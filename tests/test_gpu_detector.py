@@ -97,9 +97,10 @@ def test_bad_arguments(env):
         resnet18(bad, "fp32")
 
 
-@pytest.mark.parametrize("shape", [(1, 32, 32), (3, 64, 32), (2, 32, 96), (1, 416, 96)])
+@pytest.mark.parametrize("shape", [(1, 32, 32), (3, 64, 32), (2, 32, 96), (1, 416, 96), (1, 32, 7680)])
 def test_tiny_and_odd_shapes(env, shape):
-    """Smallest legal maps (one 32x32 cell) and shapes whose feature maps are smaller than one MMA tile."""
+    """Smallest legal maps (one 32x32 cell), shapes whose feature maps are smaller than one MMA tile, and a one-cell-high
+    strip whose deepest map is 1 x 240 (the widest tile would not leave room for the weight ring: tests/test_conv_geometry.py)."""
     synth, resnet18, mo = env
     B, H, W = shape
     w = synth.make_detector_weights(3, "hard_bn")
