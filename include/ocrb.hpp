@@ -1,0 +1,244 @@
+// ocrb.hpp — C++ host side above the C ABI (include/ocrb.h), mirroring the module layout of lazareviczoran/ocr-rs.
+//
+// ocr-rs is compiled code (Rust) and no Rust toolchain exists in the build image, so the host-side mirror of its
+// public functions is C++ (header-only, C++17): same module names, argument meaning and error behaviour
+// (`anyhow::Result` -> exception ocr_rs::Error carrying the C error code and message; `Option::None` -> std::nullopt).
+// Each function cites the reference function it stands for; INTEGRATION.md shows the equivalent Rust `ocrb-sys` shim.
+// Pointers handed to these functions may be host or device memory (the library inspects them).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "ocrb.h"
+
+namespace ocr_rs {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) {
+  if (rc != OCRB_OK) throw Error(rc, std::string("libocrb error ") + std::to_string(rc) + ": " + ocrb_last_error());
+}
+
+// replaces the process-global `DEVICE` (main.rs:26-28): one context per (device, host thread)
+class Context {
+ public:
+  explicit Context(int device = 0) { check(ocrb_ctx_create(device, &p_)); }
+  ~Context() { if (p_) ocrb_ctx_destroy(p_); }
+  Context(const Context &) = delete;
+  Context &operator=(const Context &) = delete;
+  Context(Context &&o) noexcept : p_(std::exchange(o.p_, nullptr)) {}
+  ocrb_ctx *raw() const { return p_; }
+  void synchronize() { check(ocrb_ctx_synchronize(p_)); }
+  int64_t launch_count() const { return ocrb_ctx_launch_count(p_); }
+
+ private:
+  ocrb_ctx *p_ = nullptr;
+};
+
+struct Point { int32_t x, y; };
+using Polygon = std::vector<std::array<uint32_t, 2>>;  // geo::Polygon<u32> exterior, no closing point
+
+// metrics.rs:32-35
+struct PolygonScores {
+  std::vector<std::vector<Polygon>> polygons;  // Vec<MultiPolygon<u32>>: per image
+  std::vector<std::vector<double>> scores;     // Vec<Vec<f64>>
+};
+
+namespace detail {
+inline PolygonScores take(ocrb_polygons *h) {
+  PolygonScores r;
+  const int n = ocrb_polygons_num_images(h);
+  const int64_t *io = ocrb_polygons_image_offsets(h), *po = ocrb_polygons_point_offsets(h);
+  const uint32_t *xy = ocrb_polygons_xy(h);
+  const double *sc = ocrb_polygons_scores(h);
+  r.polygons.resize(n);
+  r.scores.resize(n);
+  for (int b = 0; b < n; ++b)
+    for (int64_t p = io[b]; p < io[b + 1]; ++p) {
+      Polygon poly;
+      for (int64_t k = po[p]; k < po[p + 1]; ++k) poly.push_back({xy[2 * k], xy[2 * k + 1]});
+      r.polygons[b].push_back(std::move(poly));
+      r.scores[b].push_back(sc[p]);
+    }
+  ocrb_polygons_free(h);
+  return r;
+}
+inline std::vector<int32_t> flat(const std::vector<Point> &pts) {
+  std::vector<int32_t> v;
+  v.reserve(pts.size() * 2);
+  for (const Point &p : pts) { v.push_back(p.x); v.push_back(p.y); }
+  return v;
+}
+}  // namespace detail
+
+namespace image_ops {
+struct Preprocessed {
+  std::vector<uint8_t> image;  // GrayImage, [h][w]
+  double adjust_x, adjust_y;
+};
+// image_ops::preprocess_image (image_ops.rs:188-220) after the file decode: RGBA8 [src_h][src_w][4]
+inline Preprocessed preprocess_image(Context &ctx, const uint8_t *rgba, int src_w, int src_h, std::pair<uint32_t, uint32_t> dims) {
+  Preprocessed r;
+  r.image.resize((size_t)dims.first * dims.second);
+  check(ocrb_preprocess_rgba(ctx.raw(), rgba, src_w, src_h, (int)dims.first, (int)dims.second, r.image.data(), &r.adjust_x, &r.adjust_y));
+  return r;
+}
+// image_ops::convert_image_to_tensor + to_kind(Float) (image_ops.rs:350-364)
+inline std::vector<float> convert_image_to_tensor(Context &ctx, const uint8_t *image, int64_t n) {
+  std::vector<float> t((size_t)n);
+  check(ocrb_convert_image_to_tensor(ctx.raw(), image, n, t.data()));
+  return t;
+}
+// image_ops::convert_tensor_to_image (image_ops.rs:367-381); `scale` as in text_detection/mod.rs:57
+inline std::vector<uint8_t> convert_tensor_to_image(Context &ctx, const float *tensor, int64_t n, float scale = 1.0f) {
+  std::vector<uint8_t> img((size_t)n);
+  check(ocrb_convert_tensor_to_image(ctx.raw(), tensor, n, scale, img.data()));
+  return img;
+}
+// image_ops::load_image_as_tensor (image_ops.rs:73-85) after the decode
+inline std::vector<float> load_image_as_tensor(Context &ctx, const uint8_t *luma, int64_t n) {
+  std::vector<float> t((size_t)n);
+  check(ocrb_load_image_as_tensor(ctx.raw(), luma, n, t.data()));
+  return t;
+}
+}  // namespace image_ops
+
+namespace text_detection {
+namespace model {
+// resnet18(&vs.root()) + vs.load(model_file_path) (model.rs:154, text_detection/mod.rs:35-44)
+class Resnet18 {
+ public:
+  Resnet18(Context &ctx, const std::string &model_file_path, int mode = OCRB_MODE_BF16) { check(ocrb_det_create_from_file(ctx.raw(), model_file_path.c_str(), mode, &p_)); }
+  // from named OIHW float32 tensors (vs.variables())
+  Resnet18(Context &ctx, const std::vector<std::string> &names, const std::vector<const float *> &data, const std::vector<int64_t> &numel,
+           int mode = OCRB_MODE_BF16) {
+    std::vector<const char *> cn;
+    for (const auto &s : names) cn.push_back(s.c_str());
+    check(ocrb_det_create(ctx.raw(), (int)cn.size(), cn.data(), data.data(), numel.data(), mode, &p_));
+  }
+  ~Resnet18() { if (p_) ocrb_det_destroy(p_); }
+  Resnet18(const Resnet18 &) = delete;
+  Resnet18 &operator=(const Resnet18 &) = delete;
+  // net.forward_t(&images.view((b, 1, h, w)), false) (text_detection/mod.rs:52, :196): u8 grey levels in, f32 map out
+  std::vector<float> forward_t(const uint8_t *images, int b, int h, int w) {
+    std::vector<float> prob((size_t)b * h * w);
+    check(ocrb_det_forward(p_, images, OCRB_U8, b, h, w, prob.data()));
+    return prob;
+  }
+  void forward_t(const void *images, int dtype, int b, int h, int w, float *prob) { check(ocrb_det_forward(p_, images, dtype, b, h, w, prob)); }
+  ocrb_det *raw() const { return p_; }
+
+ private:
+  ocrb_det *p_ = nullptr;
+};
+}  // namespace model
+
+namespace metrics {
+// metrics::binarize (metrics.rs:129-131)
+inline std::vector<uint8_t> binarize(Context &ctx, const float *pred, int64_t n, double thresh) {
+  std::vector<uint8_t> out((size_t)n);
+  check(ocrb_binarize(ctx.raw(), pred, n, thresh, out.data()));
+  return out;
+}
+// metrics::box_score_fast (metrics.rs:150-184): pred [dim_m2][dim_m1]
+inline double box_score_fast(Context &ctx, const float *pred, int dim_m2, int dim_m1, const std::vector<Point> &points) {
+  const std::vector<int32_t> xy = detail::flat(points);
+  double s = 0.0;
+  check(ocrb_box_score_fast(ctx.raw(), pred, dim_m2, dim_m1, xy.data(), (int)points.size(), &s));
+  return s;
+}
+// metrics::get_min_area_bounding_box (metrics.rs:133-148) -> (4 corners, short side)
+inline std::pair<std::vector<Point>, double> get_min_area_bounding_box(Context &ctx, const std::vector<Point> &points) {
+  const std::vector<int32_t> xy = detail::flat(points);
+  int32_t box[8];
+  double sside = 0.0;
+  check(ocrb_min_area_bounding_box(ctx.raw(), xy.data(), (int)points.size(), box, &sside));
+  std::vector<Point> corners;
+  for (int i = 0; i < 4; ++i) corners.push_back({box[2 * i], box[2 * i + 1]});
+  return {corners, sside};
+}
+// metrics::get_polygons_from_bitmap (metrics.rs:58-127): one image; adjust = {adjust_x, adjust_y}
+inline std::pair<std::vector<Polygon>, std::vector<double>> get_polygons_from_bitmap(Context &ctx, const float *pred, const uint8_t *bitmap,
+                                                                                        const double adjust[2], int h, int w) {
+  ocrb_polygons *out = nullptr;
+  check(ocrb_get_polygons_from_bitmap(ctx.raw(), pred, bitmap, adjust, h, w, nullptr, &out));
+  PolygonScores r = detail::take(out);
+  return {std::move(r.polygons.at(0)), std::move(r.scores.at(0))};
+}
+// metrics::get_boxes_and_box_scores (metrics.rs:37-56): pred [b][h][w] (the reference's [b,1,h,w]), adjust [b][2]
+inline PolygonScores get_boxes_and_box_scores(Context &ctx, const float *pred, const double *adjust_values, int b, int h, int w) {
+  ocrb_polygons *out = nullptr;
+  check(ocrb_get_boxes_and_box_scores(ctx.raw(), pred, adjust_values, b, h, w, nullptr, &out));
+  return detail::take(out);
+}
+}  // namespace metrics
+}  // namespace text_detection
+
+namespace polygon {
+// polygon::expand_polygon (polygon.rs:51-56): None when the offset is empty
+inline std::optional<std::vector<Point>> expand_polygon(Context &ctx, const std::vector<Point> &points, double factor) {
+  const std::vector<int32_t> xy = detail::flat(points);
+  std::vector<int32_t> out(2 * (4 * points.size() + 16));
+  int n = 0;
+  check(ocrb_expand_polygon(ctx.raw(), xy.data(), (int)points.size(), factor, out.data(), (int)(out.size() / 2), &n));
+  if (n == 0) return std::nullopt;
+  std::vector<Point> r;
+  for (int i = 0; i < n; ++i) r.push_back({out[2 * i], out[2 * i + 1]});
+  return r;
+}
+}  // namespace polygon
+
+namespace utils {
+// utils::VALUES (utils.rs:7)
+inline char class_to_char(int cls) { return ocrb_class_to_char(cls); }
+}  // namespace utils
+
+namespace char_recognition {
+namespace model {
+// Net::new(&vs.root()) + vs.load(model_file_path) (char_recognition/model.rs:12-25, mod.rs:43-45)
+class Net {
+ public:
+  Net(Context &ctx, const std::string &model_file_path) { check(ocrb_rec_create_from_file(ctx.raw(), model_file_path.c_str(), &p_)); }
+  ~Net() { if (p_) ocrb_rec_destroy(p_); }
+  Net(const Net &) = delete;
+  Net &operator=(const Net &) = delete;
+  // forward_t(xs, false): glyphs [b][784] f32 in [0, 1] -> logits [b][62]
+  std::vector<float> forward_t(const float *glyphs, int b) {
+    std::vector<float> logits((size_t)b * 62);
+    check(ocrb_rec_forward(p_, glyphs, b, logits.data(), nullptr, nullptr));
+    return logits;
+  }
+  // run_prediction's tail (mod.rs:53-56): softmax(-1, Double) + topk(1) -> (character, probability) per glyph
+  std::vector<std::pair<char, double>> predict(const uint8_t *glyphs_u8, int b) {
+    std::vector<int32_t> am((size_t)b);
+    std::vector<double> pr((size_t)b);
+    check(ocrb_rec_forward_u8(p_, glyphs_u8, b, nullptr, am.data(), pr.data()));
+    std::vector<std::pair<char, double>> r;
+    for (int i = 0; i < b; ++i) r.emplace_back(ocrb_class_to_char(am[i]), pr[i]);
+    return r;
+  }
+  ocrb_rec *raw() const { return p_; }
+
+ private:
+  ocrb_rec *p_ = nullptr;
+};
+}  // namespace model
+}  // namespace char_recognition
+
+// run_text_detection's device part for a batch (text_detection/mod.rs:46-67, :188-204) + glyph classes in one call
+inline PolygonScores detect_and_recognize(text_detection::model::Resnet18 &det, char_recognition::model::Net *rec, const uint8_t *images,
+                                          const double *adjust_values, int b, int h, int w, const uint8_t *glyphs = nullptr, int n_glyphs = 0,
+                                          int32_t *glyph_classes = nullptr) {
+  ocrb_polygons *out = nullptr;
+  check(ocrb_detect_and_recognize(det.raw(), rec ? rec->raw() : nullptr, images, adjust_values, b, h, w, nullptr, glyphs, n_glyphs, glyph_classes, &out));
+  return detail::take(out);
+}
+
+}  // namespace ocr_rs

@@ -1,0 +1,65 @@
+// Host-side C++ mirror of ocr-rs's modules (include/ocrb.hpp) exercised from compiled code: compiled and run by
+// tests/test_cpp_host.py.  Without a CUDA device it checks the host-only helpers and the error behaviour (no CPU
+// fallback); with one it runs the known-answer tests of the reference (metrics.rs:406-508) through the mirror.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "ocrb.hpp"
+
+#define REQUIRE(c)                                                          \
+  do {                                                                      \
+    if (!(c)) { std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } \
+  } while (0)
+
+int main() {
+  using namespace ocr_rs;
+  REQUIRE(ocrb_version() == OCRB_VERSION);
+  // utils::VALUES (utils.rs:7)
+  REQUIRE(utils::class_to_char(0) == 'A' && utils::class_to_char(26) == 'a' && utils::class_to_char(52) == '0' && utils::class_to_char(62) == '?');
+  int rw = 0, rh = 0;
+  REQUIRE(ocrb_resize_dims(300, 200, 800, 800, &rw, &rh) == OCRB_OK && rw == 800 && rh == 533);  // image_ops.rs fixtures
+  int n_dev = 0;
+  if (ocrb_device_count(&n_dev) != OCRB_OK || n_dev == 0) {
+    bool threw = false;
+    try {
+      Context ctx(0);
+    } catch (const Error &e) {
+      threw = e.code == OCRB_ERR_CUDA;  // anyhow::Error in the reference; here the C code + message
+    }
+    REQUIRE(threw);
+    std::puts("host-only checks ok (no CUDA device: Context refuses, no CPU fallback)");
+    return 0;
+  }
+  Context ctx(0);
+  // metrics.rs:486-508 binarize: strict > in f32 (0.6f > 0.6 is false)
+  const float pred[6] = {0.1f, 0.6f, 0.6000001f, 0.7f, 0.59f, 1.0f};  // 0.6000001f is the next float above (float)0.6
+  const std::vector<uint8_t> bm = text_detection::metrics::binarize(ctx, pred, 6, 0.6);
+  REQUIRE(bm[0] == 0 && bm[1] == 0 && bm[2] == 1 && bm[3] == 1 && bm[4] == 0 && bm[5] == 1);
+  // metrics.rs:406-424 get_min_area_bounding_box: axis-aligned rectangle, short side 5
+  const std::vector<Point> rect = {{10, 10}, {30, 10}, {30, 15}, {10, 15}};
+  auto [corners, sside] = text_detection::metrics::get_min_area_bounding_box(ctx, rect);
+  REQUIRE(corners.size() == 4 && std::fabs(sside - 5.0) < 1e-9);
+  // metrics.rs:150-184 box_score_fast: constant map -> its value
+  std::vector<float> map(40 * 40, 0.25f);
+  const double s = text_detection::metrics::box_score_fast(ctx, map.data(), 40, 40, rect);
+  REQUIRE(std::fabs(s - 0.25) < 1e-12);
+  // polygon.rs:51-56 expand_polygon: grows the rectangle; a degenerate polygon gives None
+  auto grown = polygon::expand_polygon(ctx, rect, 2.0);
+  REQUIRE(grown.has_value() && grown->size() >= 4);
+  int minx = 1 << 30, maxx = -(1 << 30);
+  for (const Point &p : *grown) { minx = p.x < minx ? p.x : minx; maxx = p.x > maxx ? p.x : maxx; }
+  REQUIRE(minx < 10 && maxx > 30);
+  // metrics.rs:37-56 on an empty map: no polygons, one (empty) entry per image
+  std::vector<float> zeros(2 * 64 * 64, 0.0f);
+  const double adj[4] = {1.0, 1.0, 1.0, 1.0};
+  const PolygonScores ps = text_detection::metrics::get_boxes_and_box_scores(ctx, zeros.data(), adj, 2, 64, 64);
+  REQUIRE(ps.polygons.size() == 2 && ps.polygons[0].empty() && ps.scores[1].empty());
+  // a bright block is found again, scaled by adjust
+  for (int y = 20; y < 40; ++y)
+    for (int x = 8; x < 56; ++x) zeros[y * 64 + x] = 0.9f;
+  const PolygonScores one = text_detection::metrics::get_boxes_and_box_scores(ctx, zeros.data(), adj, 2, 64, 64);
+  REQUIRE(one.polygons[0].size() == 1 && one.polygons[1].empty() && one.scores[0][0] > 0.7);
+  std::printf("device checks ok (%lld kernel launches)\n", (long long)ctx.launch_count());
+  return 0;
+}
