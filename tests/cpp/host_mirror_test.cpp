@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "ocrb.hpp"
 
@@ -12,9 +13,28 @@
     if (!(c)) { std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } \
   } while (0)
 
-int main() {
+int main(int argc, char **argv) {
   using namespace ocr_rs;
   REQUIRE(ocrb_version() == OCRB_VERSION);
+  if (argc > 1) {
+    // vs.load(file) (text_detection/mod.rs:40-44): the native reader of tch's VarStore archives, on the fixture written
+    // by libtorch's own serializer (tests/golden/varstore_libtorch.ot: 18 tensors, conv1.weight is [4][1][7][7])
+    ocrb_varstore *vs = nullptr;
+    REQUIRE(ocrb_varstore_open(argv[1], &vs) == OCRB_OK && ocrb_varstore_count(vs) == 18);
+    bool found = false;
+    for (int i = 0; i < ocrb_varstore_count(vs); ++i) {
+      if (std::string(ocrb_varstore_name(vs, i)) != "conv1.weight") continue;
+      const float *data = nullptr;
+      const int64_t *shape = nullptr;
+      int64_t numel = 0;
+      int ndim = 0;
+      REQUIRE(ocrb_varstore_tensor(vs, i, &data, &numel, &shape, &ndim) == OCRB_OK);
+      found = data && numel == 4 * 49 && ndim == 4 && shape[0] == 4 && shape[1] == 1 && shape[2] == 7 && shape[3] == 7;
+    }
+    ocrb_varstore_close(vs);
+    REQUIRE(found);
+    REQUIRE(ocrb_varstore_open("/nonexistent/model.ot", &vs) != OCRB_OK);  // vs.load errors on a missing file
+  }
   // utils::VALUES (utils.rs:7)
   REQUIRE(utils::class_to_char(0) == 'A' && utils::class_to_char(26) == 'a' && utils::class_to_char(52) == '0' && utils::class_to_char(62) == '?');
   int rw = 0, rh = 0;

@@ -26,7 +26,7 @@ def _build(tmp_path):
 def test_cpp_mirror_compiles_and_runs_host_only(tmp_path):
     import torch
     exe = _build(tmp_path)
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    out = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "varstore_libtorch.ot")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     if not torch.cuda.is_available():
         assert "no CUDA device" in out.stdout
@@ -35,6 +35,6 @@ def test_cpp_mirror_compiles_and_runs_host_only(tmp_path):
 @pytest.mark.gpu
 def test_cpp_mirror_on_device(tmp_path):
     exe = _build(tmp_path)
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    out = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "varstore_libtorch.ot")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "device checks ok" in out.stdout
