@@ -106,15 +106,74 @@ def offset_raw(points, delta):
     return out[:m].copy()
 
 
-def expand_polygon(points, factor=2.0, return_distance=False):
-    """polygon.rs:51-56 -> [m,2] int32 or None."""
+def clip_polygon(points, factor, shrink, return_distance=False):
+    """polygon.rs:13-42 -> [m,2] int32 or None."""
     p = _pts(points)
     cap = 6 * len(p) + 32
     out = np.empty((cap, 2), np.int32)
     d = C.c_double(0)
-    m = lib().orc_expand_polygon(_p(p, C.c_int32), len(p), C.c_double(factor), _p(out, C.c_int32), cap, C.byref(d))
+    m = lib().orc_clip_polygon(_p(p, C.c_int32), len(p), C.c_double(factor), int(bool(shrink)), _p(out, C.c_int32), cap, C.byref(d))
     res = out[:m].copy() if m > 0 else None
     return (res, d.value) if return_distance else res
+
+
+def expand_polygon(points, factor=2.0, return_distance=False):
+    """polygon.rs:51-56 -> [m,2] int32 or None."""
+    return clip_polygon(points, factor, False, return_distance)
+
+
+def shrink_polygon(points, factor):
+    """polygon.rs:44-49 (training-side caller image_ops.rs:265; used here to pin the Clipper restatement)."""
+    return clip_polygon(points, factor, True)
+
+
+def union_of_path(raw):
+    """Clipper's clean-up of one closed (offset) path -> [m,2] int32 or None."""
+    p = _pts(raw)
+    cap = 4 * len(p) + 16
+    out = np.empty((cap, 2), np.int32)
+    m = lib().orc_union_of_path(_p(p, C.c_int32), len(p), _p(out, C.c_int32), cap)
+    return out[:m].copy() if m > 0 else None
+
+
+def draw_polygon(canvas, points, value):
+    """imageproc draw_polygon_mut on a [H,W] u8 canvas, in place."""
+    assert canvas.dtype == np.uint8 and canvas.flags.c_contiguous
+    p = _pts(points)
+    lib().orc_draw_polygon(_p(canvas, C.c_uint8), canvas.shape[1], canvas.shape[0], _p(p, C.c_int32), len(p), int(value))
+    return canvas
+
+
+MIN_TEXT_SIZE = 8  # image_ops.rs:42
+
+
+def generate_gt_and_mask_images(polygons, adjust_x, adjust_y, target_dim):
+    """image_ops.rs:222-277 (dataset preparation; not on the hot path): the ground-truth map is every
+    polygon shrunk by 1 - 0.5^2 and filled, the mask blanks ignored polygons.  -> (gt, mask, ignore_flags)"""
+    width, height = target_dim
+    gt = np.zeros((height, width), np.uint8)
+    mask = np.full((height, width), 255, np.uint8)
+    flags = []
+    for poly in polygons:
+        pts = np.asarray(poly, np.int64)
+        pw, ph = pts[:, 0].max() - pts[:, 0].min(), pts[:, 1].max() - pts[:, 1].min()
+        vals = np.stack([(pts[:, 0].astype(np.float64) * adjust_x).astype(np.int32),
+                         (pts[:, 1].astype(np.float64) * adjust_y).astype(np.int32)], 1)
+        if len(vals) < 4:
+            flags.append(True)
+            continue
+        if min(pw, ph) < MIN_TEXT_SIZE:
+            draw_polygon(mask, vals, 0)
+            flags.append(True)
+            continue
+        sh = shrink_polygon(vals, 1.0 - 0.5 ** 2)
+        if sh is None:
+            draw_polygon(mask, vals, 0)
+            flags.append(True)
+        else:
+            draw_polygon(gt, sh, 255)
+            flags.append(False)
+    return gt, mask, flags
 
 
 def min_area_bounding_box(points):

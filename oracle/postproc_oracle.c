@@ -17,9 +17,13 @@
  *  and PINNED by the reference's own golden tests
  * (metrics.rs:406-646), reproduced by tests/test_oracle_goldens.py.
  *
- * Parity status: post-processing pinned (goldens); Clipper's general polygon union is
- * restated as "outer boundary of the positive-winding region" (see orc_union_outer) and is
- * pinned only through the 4+4 golden polygons — stated in DESIGN.md.
+ * Parity status: post-processing pinned (goldens).  Clipper's clean-up union is restated as
+ * "boundary of the positive-winding region" (orc_union_positive) and pinned three ways: the
+ * 4+4 golden polygons of metrics.rs:510-646; the reference's gt_shrinked_img{55,224,494,545}.png
+ * and mask_img*.png regenerated bit-exactly from its ground-truth polygon files through
+ * clip_polygon(Shrink) + draw_polygon_mut (image_ops.rs:222-277, tests/test_oracle_goldens.py);
+ * and an independent winding-number rasteriser that shares no code with the walk
+ * (oracle/region_check.c, tests/test_union_region.py).
  *
  * Build: oracle/Makefile (gcc -O2 -ffp-contract=off -shared -fPIC).
  */
@@ -181,7 +185,7 @@ static int cmp_i32(const void *a, const void *b) {
 }
 
 /* draws mask (mw x mh, row-major bytes 0/1) */
-static void draw_polygon_mask(uint8_t *mask, int mw, int mh, const ipt *poly, int n) {
+static void draw_polygon_mask(uint8_t *mask, int mw, int mh, const ipt *poly, int n, uint8_t value) {
   if (n == 0) return;
   int32_t y_min = INT32_MAX, y_max = INT32_MIN;
   for (int i = 0; i < n; ++i) {
@@ -214,7 +218,7 @@ static void draw_polygon_mask(uint8_t *mask, int mw, int mh, const ipt *poly, in
       if (from < mw && to >= 0) {
         if (from < 0) from = 0;
         if (to < 0) to = 0;
-        for (int32_t x = from; x <= to; ++x) mask[(int64_t)y * mw + x] = 1;
+        for (int32_t x = from; x <= to; ++x) mask[(int64_t)y * mw + x] = value;
       }
     }
   }
@@ -230,12 +234,17 @@ static void draw_polygon_mask(uint8_t *mask, int mw, int mh, const ipt *poly, in
     int32_t x = (int32_t)x0, y = (int32_t)y0, end_x = (int32_t)x1, y_step = y0 < y1 ? 1 : -1;
     while (x <= end_x) {
       int32_t px = steep ? y : x, py = steep ? x : y;
-      if (px >= 0 && px < mw && py >= 0 && py < mh) mask[(int64_t)py * mw + px] = 1;
+      if (px >= 0 && px < mw && py >= 0 && py < mh) mask[(int64_t)py * mw + px] = value;
       x += 1;
       error -= dy;
       if (error < 0.0f) { y += y_step; error += dx; }
     }
   }
+}
+
+/* imageproc 0.22.0 draw_polygon_mut on a W x H Luma8 canvas (image_ops.rs:265-270) */
+void orc_draw_polygon(uint8_t *canvas, int W, int H, const ipt *poly, int n, int value) {
+  draw_polygon_mask(canvas, W, H, poly, n, (uint8_t)value);
 }
 
 double orc_box_score(const float *pred, int dim_m2, int dim_m1, const ipt *pts, int n,
@@ -254,7 +263,7 @@ double orc_box_score(const float *pred, int dim_m2, int dim_m1, const ipt *pts, 
   uint8_t *mask = (uint8_t *)calloc((size_t)mw * mh, 1);
   ipt *moved = (ipt *)malloc(sizeof(ipt) * (size_t)n);
   for (int i = 0; i < n; ++i) { moved[i].x = pts[i].x - (int32_t)min_x; moved[i].y = pts[i].y - (int32_t)min_y; }
-  draw_polygon_mask(mask, mw, mh, moved, n);
+  draw_polygon_mask(mask, mw, mh, moved, n, 1);
   double s = 0.0, cnt = 0.0;
   for (int y = 0; y < mh; ++y)
     for (int x = 0; x < mw; ++x)
@@ -419,8 +428,8 @@ static int seg_hit(const ipt *Q, int m, int i, int j, int which, rat *t, rat *s)
   return 1;
 }
 
-/* rotation rank of direction d relative to the back direction r = -u, counter-clockwise,
- * in (0, 2pi]: compares two candidate directions exactly.  returns 1 if a comes before b */
+/* rotation rank of direction d relative to a reference direction r, counter-clockwise, in
+ * (0, 2pi]: compares two candidate directions exactly.  returns 1 if a comes before b */
 static int half_of(int64_t rx, int64_t ry, int64_t dx, int64_t dy) {
   /* 0: angle in (0,pi) ccw from r, 1: angle == pi, 2: (pi,2pi), 3: angle == 2pi (same as r) */
   int64_t c = crossi(rx, ry, dx, dy), d = doti(rx, ry, dx, dy);
@@ -434,50 +443,142 @@ static int ccw_before(int64_t rx, int64_t ry, int64_t ax, int64_t ay, int64_t bx
   if (ha == 1 || ha == 3) return 0;
   return crossi(ax, ay, bx, by) > 0; /* a before b when b is further ccw */
 }
+static int same_dir(int64_t ax, int64_t ay, int64_t bx, int64_t by) {
+  return crossi(ax, ay, bx, by) == 0 && doti(ax, ay, bx, by) > 0;
+}
+
+/* One ray of the arrangement at a node: the part of path segment `seg` leaving the node
+ * (sign +1, direction = the segment's) or arriving at it (sign -1, direction reversed).
+ * Crossing a ray while turning counter-clockwise about the node changes the winding number
+ * by its sign. */
+typedef struct { int64_t dx, dy; int sign, seg; rat s; } ray_t;
+#define ORC_MAX_RAYS 64
+
+/* All rays at the point P = (pxn, pyn) / pden (pden > 0).  *is_vertex / *vtx: P coincides with
+ * a path vertex.  Returns the ray count, -1 when more than ORC_MAX_RAYS meet in one point. */
+static int rays_at(const ipt *Q, int m, __int128 pxn, __int128 pyn, __int128 pden, ray_t *rays,
+                   int *is_vertex, ipt *vtx) {
+  int k = 0;
+  *is_vertex = 0;
+  for (int j = 0; j < m; ++j) {
+    ipt b0 = Q[j], b1 = Q[(j + 1) % m];
+    int64_t dx = (int64_t)b1.x - b0.x, dy = (int64_t)b1.y - b0.y;
+    __int128 qx = pxn - (__int128)b0.x * pden, qy = pyn - (__int128)b0.y * pden; /* (P - b0) * pden */
+    if (qx * dy - qy * dx != 0) continue;                                        /* not on the line */
+    __int128 sn = qx * dx + qy * dy, sd = pden * ((__int128)dx * dx + (__int128)dy * dy);
+    if (sn < 0 || sn > sd) continue;
+    if (sn == 0) { *is_vertex = 1; *vtx = b0; }
+    if (sn == sd) { *is_vertex = 1; *vtx = b1; }
+    /* reduce s to 64-bit: s = sn / sd with sd <= 2^62 for coordinates below 2^15 */
+    rat s = {(int64_t)sn, (int64_t)sd};
+    if (sn < sd) { if (k >= ORC_MAX_RAYS) return -1; rays[k].dx = dx; rays[k].dy = dy; rays[k].sign = 1; rays[k].seg = j; rays[k].s = s; k++; }
+    if (sn > 0) { if (k >= ORC_MAX_RAYS) return -1; rays[k].dx = -dx; rays[k].dy = -dy; rays[k].sign = -1; rays[k].seg = j; rays[k].s = s; k++; }
+  }
+  return k;
+}
+
+/* Turn counter-clockwise about a node, starting just after direction (rx, ry) where the
+ * winding number is w0, and stop at the first group of coincident rays across which it
+ * becomes positive: that group carries the boundary of {winding > 0} away from the node,
+ * region on its left.  The group in direction r itself is met last.  Returns the index of an
+ * outgoing ray of that group (-1: none) and the winding number on its right in *w_right. */
+static int next_boundary_ray(ray_t *rays, int k, int64_t rx, int64_t ry, int w0, int prefer_seg, int *w_right) {
+  for (int i = 1; i < k; ++i) { /* insertion sort, counter-clockwise from r */
+    ray_t key = rays[i];
+    int j = i - 1;
+    while (j >= 0 && ccw_before(rx, ry, key.dx, key.dy, rays[j].dx, rays[j].dy)) { rays[j + 1] = rays[j]; j--; }
+    rays[j + 1] = key;
+  }
+  int w = w0;
+  for (int i = 0; i < k;) {
+    int e = i, net = 0, pick = -1;
+    while (e < k && same_dir(rays[i].dx, rays[i].dy, rays[e].dx, rays[e].dy)) {
+      net += rays[e].sign;
+      if (rays[e].sign > 0 && (pick < 0 || rays[e].seg == prefer_seg)) pick = e;
+      e++;
+    }
+    if (w <= 0 && w + net > 0) { *w_right = w; return pick; }
+    w += net;
+    i = e;
+  }
+  return -1;
+}
+
+/* winding number of the closed path at (P.x - eps, P.y + delta), 0 < eps << delta << 1, for the
+ * rational point P = (pxn, pyn) / pden: crossings of the upward vertical ray; segments through P
+ * itself pass below that point */
+static int winding_above_left(const ipt *Q, int m, __int128 pxn, __int128 pyn, __int128 pden) {
+  int w = 0;
+  for (int j = 0; j < m; ++j) {
+    ipt a = Q[j], b = Q[(j + 1) % m];
+    __int128 ax = (__int128)a.x * pden, bx = (__int128)b.x * pden;
+    int dir;
+    if (ax < pxn && pxn <= bx) dir = -1;      /* heading +x */
+    else if (bx < pxn && pxn <= ax) dir = 1;  /* heading -x */
+    else continue;
+    /* y on the segment at x = P.x, compared with P.y: (P.x-a.x)*(b.y-a.y)/(b.x-a.x) > P.y-a.y */
+    __int128 lhs = (pxn - ax) * ((int64_t)b.y - a.y), rhs = (pyn - (__int128)a.y * pden) * ((int64_t)b.x - a.x);
+    int above = (b.x > a.x) ? (lhs > rhs) : (lhs < rhs);
+    if (above) w += dir;
+  }
+  return w;
+}
+
+/* Is the node P on the boundary of {winding > 0}?  If so: the boundary ray leaving it. */
+static int boundary_start_at(const ipt *Q, int m, __int128 pxn, __int128 pyn, __int128 pden, ray_t *rays,
+                             int *seg, rat *s, int *w_right) {
+  int isv; ipt vt;
+  int k = rays_at(Q, m, pxn, pyn, pden, rays, &isv, &vt);
+  if (k <= 0) return k;
+  int w0 = winding_above_left(Q, m, pxn, pyn, pden);
+  int pick = next_boundary_ray(rays, k, 0, 1, w0, -1, w_right); /* any w0: a rise is only seen after the winding was <= 0 */
+  if (pick < 0) return 0;
+  *seg = rays[pick].seg; *s = rays[pick].s;
+  return 1;
+}
+
+/* node ordering of the start search: y descending, then x ascending; rational points */
+typedef struct { __int128 xn, yn, den; } rpt;
+static int node_after(rpt a, rpt b) { /* 1 if a comes strictly after b */
+  __int128 ya = a.yn * b.den, yb = b.yn * a.den;
+  if (ya != yb) return ya < yb;
+  return a.xn * b.den > b.xn * a.den;
+}
 
 /*
- * Union with positive fill of ONE closed path = outer boundary of {winding > 0}.
- * Path Q is counter-clockwise in the raw (x,y) plane (Clipper Area >= 0), so the interior
- * lies to the LEFT of every forward edge and the unbounded face to the right of the
- * boundary.  Walk: start at the lowest-y (then lowest-x) vertex along its forward edge of
- * smallest polar angle; at every arrangement node take the first forward edge met when
- * rotating counter-clockwise from the direction we came from (right-most turn).
- * Node coordinates: integer path vertices as they are; proper crossings through Clipper's
- * IntersectPoint (double arithmetic, half-away-from-zero rounding).  Afterwards duplicate
- * and collinear vertices are dropped (Clipper FixupOutPolygon) and the ring is rotated so
- * that it starts right after the last top-most (min y, then max x) vertex — Clipper's
- * BuildResult order as observed on all golden polygons.
+ * Clipper's clean-up of ONE closed offset path = boundary of the region {winding > 0}
+ * (ctUnion with pftPositive for delta > 0; for delta < 0 ClipperOffset adds a reversed outer
+ * rectangle, fills pftNegative and returns the HOLES of that, which is the same region).
+ * Winding numbers are taken in the raw (x, y) plane, counter-clockwise positive, so a path
+ * with Clipper Area >= 0 has winding +1 inside.
+ *
+ * The region's boundary is walked with the region on the left.  At every node of the
+ * arrangement (path vertices as they are, crossings as exact rationals) all rays through the
+ * node are ordered by angle and the winding numbers of the sectors between them follow from
+ * the one on the right of the arriving edge; the walk leaves along the first ray across which
+ * the winding turns positive (next_boundary_ray).  Emitted vertices: path vertices as they
+ * are, crossings through Clipper's IntersectPoint (double arithmetic, half-away-from-zero
+ * rounding).  Afterwards duplicate and collinear vertices are dropped (FixupOutPolygon) and
+ * the ring is rotated so that it starts right after the last top-most (min y, then max x)
+ * vertex — Clipper's BuildResult order as observed on all golden polygons.
+ *
+ * Several polygons: Clipper sweeps from the largest y downwards and numbers output polygons
+ * in the order their first (largest-y) vertex is met, merged pieces keeping the lower index;
+ * the reference takes polygon 0 (polygon.rs:35), i.e. the one that owns the largest-y
+ * boundary vertex (ties: smallest x).  The walk therefore starts at the first path vertex in
+ * that order that lies on the region's boundary.  Holes are never visited (the reference
+ * reads the exterior only).
  * Returns vertex count (0 = empty result).  out capacity >= 4*m+16.
  */
-static int orc_union_outer(const ipt *Qin, int m_in, ipt *out, int cap) {
-  ipt *Q = (ipt *)malloc(sizeof(ipt) * (size_t)(m_in > 0 ? m_in : 1));
-  int m = 0;
-  for (int i = 0; i < m_in; ++i)
-    if (m == 0 || Q[m - 1].x != Qin[i].x || Q[m - 1].y != Qin[i].y) Q[m++] = Qin[i];
-  while (m > 1 && Q[0].x == Q[m - 1].x && Q[0].y == Q[m - 1].y) m--;
-  if (m < 3) { free(Q); return 0; }
-  /* start vertex: min y, then min x; among coincident copies the forward edge of smallest
-   * polar angle in [0, pi] (ties: lowest index) */
-  int sv = 0;
-  for (int i = 1; i < m; ++i)
-    if (Q[i].y < Q[sv].y || (Q[i].y == Q[sv].y && Q[i].x < Q[sv].x)) sv = i;
-  int best = -1;
-  for (int i = 0; i < m; ++i) {
-    if (Q[i].x != Q[sv].x || Q[i].y != Q[sv].y) continue;
-    int64_t dx = Q[(i + 1) % m].x - Q[i].x, dy = Q[(i + 1) % m].y - Q[i].y;
-    if (best < 0) { best = i; continue; }
-    int64_t bx = Q[(best + 1) % m].x - Q[best].x, by = Q[(best + 1) % m].y - Q[best].y;
-    /* all directions have dy >= 0 (and dx > 0 when dy == 0): smaller angle = cross(b,d) < 0 */
-    if (crossi(bx, by, dx, dy) < 0) best = i;
-  }
-  int cur = best;
-  rat cur_t = {0, 1};
-  int start_seg = cur;
-  int n_out = 0;
-  out[n_out++] = Q[cur];
-  int guard = 0, max_iter = 8 * m + 64, ok = 1;
+/* Walks one ring of the boundary from (start_seg, start_t) with w_right on its right, then applies
+ * FixupOutPolygon.  Returns the vertex count (< 3: the ring collapsed on the integer grid), -1 on failure. */
+static int walk_ring(const ipt *Q, int m, int start_seg, rat start_t, int w_right, ipt *out, int cap) {
+  ray_t rays[ORC_MAX_RAYS];
+  int cur = start_seg, n_out = 0;
+  rat cur_t = start_t;
+  int guard = 0, max_iter = 8 * m + 64;
   for (;;) {
-    if (++guard > max_iter) { ok = 0; break; }
+    if (++guard > max_iter) return -1;
     /* next event on cur after cur_t */
     rat t_best = {1, 1};
     for (int j = 0; j < m; ++j) {
@@ -489,38 +590,29 @@ static int orc_union_outer(const ipt *Qin, int m_in, ipt *out, int cap) {
         if (rat_lt(t, t_best)) t_best = t;
       }
     }
-    /* gather forward rays at the node */
     ipt c0 = Q[cur], c1 = Q[(cur + 1) % m];
-    int64_t ux = c1.x - c0.x, uy = c1.y - c0.y;
-    int64_t rx = -ux, ry = -uy;
-    int nxt = -1; rat nxt_s = {0, 1};
-    int64_t bdx = 0, bdy = 0;
-    int node_is_vertex = 0; ipt node_v = {0, 0};
-    if (t_best.num == t_best.den) { node_is_vertex = 1; node_v = c1; }
-    else { nxt = cur; nxt_s = t_best; bdx = ux; bdy = uy; } /* continuing straight is a candidate */
-    for (int j = 0; j < m; ++j) {
-      if (j == cur) continue;
-      for (int which = 0; which < 3; ++which) {
-        rat t, s;
-        if (!seg_hit(Q, m, cur, j, which, &t, &s)) continue;
-        if (!rat_eq(t, t_best)) continue;
-        if (s.num == 0) { node_is_vertex = 1; node_v = Q[j]; }
-        if (s.num == s.den) { node_is_vertex = 1; node_v = Q[(j + 1) % m]; continue; } /* j ends here */
-        int64_t dx = Q[(j + 1) % m].x - Q[j].x, dy = Q[(j + 1) % m].y - Q[j].y;
-        if (nxt < 0 || ccw_before(rx, ry, dx, dy, bdx, bdy)) { nxt = j; nxt_s = s; bdx = dx; bdy = dy; }
-      }
+    int64_t ux = (int64_t)c1.x - c0.x, uy = (int64_t)c1.y - c0.y;
+    /* node P = c0 + t_best * u */
+    __int128 pden = t_best.den;
+    __int128 pxn = (__int128)c0.x * pden + (__int128)t_best.num * ux, pyn = (__int128)c0.y * pden + (__int128)t_best.num * uy;
+    int node_is_vertex; ipt node_v = {0, 0};
+    int k = rays_at(Q, m, pxn, pyn, pden, rays, &node_is_vertex, &node_v);
+    if (k < 0) return -1;
+    int wr;
+    int pick = next_boundary_ray(rays, k, -ux, -uy, w_right, cur, &wr);
+    if (pick < 0) return -1;
+    int nxt = rays[pick].seg;
+    rat nxt_s = rays[pick].s;
+    if (node_is_vertex || nxt != cur) {
+      ipt node;
+      if (node_is_vertex) node = node_v;
+      else clipper_intersect_point(c0, c1, Q[nxt], Q[(nxt + 1) % m], &node);
+      if (n_out >= cap) return -1;
+      out[n_out++] = node;
     }
-    if (nxt < 0) { ok = 0; break; }
-    if (nxt == start_seg && nxt_s.num == 0) break; /* closed the ring */
-    ipt node;
-    if (node_is_vertex) node = node_v;
-    else clipper_intersect_point(c0, c1, Q[nxt], Q[(nxt + 1) % m], &node);
-    if (n_out >= cap) { ok = 0; break; }
-    out[n_out++] = node;
-    cur = nxt; cur_t = nxt_s;
+    if (nxt == start_seg && rat_eq(nxt_s, start_t)) break; /* closed the ring (the start node was emitted last) */
+    cur = nxt; cur_t = nxt_s; w_right = wr;
   }
-  free(Q);
-  if (!ok) return 0;
   /* FixupOutPolygon: drop duplicates and collinear middles until stable */
   int changed = 1;
   while (changed && n_out >= 3) {
@@ -528,13 +620,62 @@ static int orc_union_outer(const ipt *Qin, int m_in, ipt *out, int cap) {
     for (int i = 0; i < n_out && n_out >= 3; ++i) {
       ipt p = out[(i + n_out - 1) % n_out], c = out[i], n = out[(i + 1) % n_out];
       int dup = (c.x == n.x && c.y == n.y) || (c.x == p.x && c.y == p.y);
-      int col = crossi(c.x - p.x, c.y - p.y, n.x - c.x, n.y - c.y) == 0;
+      int col = crossi((int64_t)c.x - p.x, (int64_t)c.y - p.y, (int64_t)n.x - c.x, (int64_t)n.y - c.y) == 0;
       if (dup || col) {
         memmove(out + i, out + i + 1, sizeof(ipt) * (size_t)(n_out - i - 1));
         n_out--; changed = 1; i--;
       }
     }
   }
+  return n_out;
+}
+
+static int orc_union_positive(const ipt *Qin, int m_in, ipt *out, int cap) {
+  ipt *Q = (ipt *)malloc(sizeof(ipt) * (size_t)(m_in > 0 ? m_in : 1));
+  int m = 0;
+  for (int i = 0; i < m_in; ++i)
+    if (m == 0 || Q[m - 1].x != Qin[i].x || Q[m - 1].y != Qin[i].y) Q[m++] = Qin[i];
+  while (m > 1 && Q[0].x == Q[m - 1].x && Q[0].y == Q[m - 1].y) m--;
+  if (m < 3) { free(Q); return 0; }
+  ray_t rays[ORC_MAX_RAYS];
+  /* start search: nodes in (y descending, x ascending) order.  The first one is always a path
+   * vertex (a crossing lies inside both segments' extents); the general search over vertices
+   * and crossings runs only when that vertex is not on the region's boundary, or when the ring
+   * through it collapses on the integer grid (Clipper disposes of output rings with fewer than
+   * three distinct vertices, so "polygon 0" is the first SURVIVING one). */
+  rpt last = {0, 0, 1};
+  int n_out = 0;
+  for (int tries = 0; tries < 4 * m + 16; ++tries) {
+    rpt best = {0, 0, 0}; /* den == 0: none yet */
+    for (int i = 0; i < m; ++i) {
+      rpt c = {Q[i].x, Q[i].y, 1};
+      if (tries > 0 && !node_after(c, last)) continue;
+      if (best.den == 0 || node_after(best, c)) best = c;
+    }
+    if (tries > 0) {
+      for (int i = 0; i < m; ++i)
+        for (int j = i + 1; j < m; ++j) {
+          rat t, sj;
+          if (!seg_hit(Q, m, i, j, 0, &t, &sj)) continue;
+          int64_t ux = (int64_t)Q[(i + 1) % m].x - Q[i].x, uy = (int64_t)Q[(i + 1) % m].y - Q[i].y;
+          rpt c = {(__int128)Q[i].x * t.den + (__int128)t.num * ux, (__int128)Q[i].y * t.den + (__int128)t.num * uy, t.den};
+          if (!node_after(c, last)) continue;
+          if (best.den == 0 || node_after(best, c)) best = c;
+        }
+    }
+    if (best.den == 0) break;
+    last = best;
+    int seg, w_right;
+    rat st;
+    int rc = boundary_start_at(Q, m, best.xn, best.yn, best.den, rays, &seg, &st, &w_right);
+    if (rc < 0) break;
+    if (rc == 0) continue;
+    n_out = walk_ring(Q, m, seg, st, w_right, out, cap);
+    if (n_out < 0) { n_out = 0; break; }
+    if (n_out >= 3) break;
+    n_out = 0;
+  }
+  free(Q);
   if (n_out < 3) return 0;
   /* BuildResult order: start right after the last top-most vertex */
   int top = 0;
@@ -548,8 +689,11 @@ static int orc_union_outer(const ipt *Qin, int m_in, ipt *out, int cap) {
   return n_out;
 }
 
-/* expand_polygon(points, factor) — polygon.rs:13-56.  Returns vertex count, 0 = None. */
-int orc_expand_polygon(const ipt *pts, int n, double factor, ipt *out, int cap, double *distance_out) {
+/* raw offset path -> cleaned polygon (test hook for the independent region check) */
+int orc_union_of_path(const ipt *raw, int m, ipt *out, int cap) { return m >= 3 ? orc_union_positive(raw, m, out, cap) : 0; }
+
+/* clip_polygon(points, factor, Shrink | Expand) — polygon.rs:13-49.  Returns vertex count, 0 = None. */
+int orc_clip_polygon(const ipt *pts, int n, double factor, int shrink, ipt *out, int cap, double *distance_out) {
   /* geo 0.15: unsigned_area (shoelace, closed ring) and euclidean_length of the closed ring */
   double twice = 0.0, perim = 0.0;
   for (int i = 0; i < n; ++i) {
@@ -559,12 +703,18 @@ int orc_expand_polygon(const ipt *pts, int n, double factor, ipt *out, int cap, 
   }
   double area = fabs(twice / 2.0);
   double distance = area * factor / perim;
+  if (shrink) distance *= -1.;
   if (distance_out) *distance_out = distance;
   ipt *raw = (ipt *)malloc(sizeof(ipt) * (size_t)(3 * n + 3));
   int m = clipper_offset_raw(pts, n, distance, raw);
-  int r = m >= 3 ? orc_union_outer(raw, m, out, cap) : 0;
+  int r = m >= 3 ? orc_union_positive(raw, m, out, cap) : 0;
   free(raw);
   return r;
+}
+
+/* expand_polygon(points, factor) — polygon.rs:51-56 */
+int orc_expand_polygon(const ipt *pts, int n, double factor, ipt *out, int cap, double *distance_out) {
+  return orc_clip_polygon(pts, n, factor, 0, out, cap, distance_out);
 }
 
 int orc_offset_raw(const ipt *pts, int n, double delta, ipt *out) { return clipper_offset_raw(pts, n, delta, out); }
