@@ -342,10 +342,161 @@ __device__ __forceinline__ bool ccw_before(long long rx, long long ry, long long
   if (ha == 1 || ha == 3) return false;
   return crossi(ax, ay, bx, by) > 0;
 }
+__device__ __forceinline__ bool same_dir(long long ax, long long ay, long long bx, long long by) {
+  return crossi(ax, ay, bx, by) == 0 && doti(ax, ay, bx, by) > 0;
+}
 
-// outer boundary of {winding > 0} of the closed path Qin (see oracle/postproc_oracle.c for the
-// derivation of this restatement of Clipper's union).  Q: scratch for the de-duplicated path.
-__device__ int union_outer(const ipt *Qin, int m_in, ipt *Q, ipt *out, int cap, ipt *fast, int fast_cap) {
+// Clipper's clean-up of one closed offset path = the boundary of {winding > 0}, walked with the region on
+// the left; the derivation, the node rule and the "first surviving polygon" rule are spelled out at
+// orc_union_positive in oracle/postproc_oracle.c, which this code must match vertex for vertex.  The
+// restatement is pinned by the reference's golden polygons and ground-truth maps (tests/test_oracle_goldens.py)
+// and, independently of both implementations, by a winding-number rasteriser (oracle/region_check.c).
+struct ray_t { int dx, dy, sign, seg; rat s; };  // part of path segment `seg` leaving (+1) / reaching (-1) a node
+constexpr int MAX_RAYS = 32;                    // more segments through one point: the candidate is dropped
+
+// all rays at P = (pxn, pyn) / pden; returns the count, -1 on overflow
+__device__ int rays_at(const ipt *Q, int m, __int128 pxn, __int128 pyn, long long pden, ray_t *rays, bool *is_vertex, ipt *vtx) {
+  int k = 0;
+  *is_vertex = false;
+  // P in floating point with a one-pixel margin rejects almost every segment before the exact test
+  const double fx = (double)pxn / (double)pden, fy = (double)pyn / (double)pden;
+  for (int j = 0; j < m; ++j) {
+    const ipt b0 = Q[j], b1 = Q[j + 1 == m ? 0 : j + 1];
+    if ((b0.x < fx - 1 && b1.x < fx - 1) || (b0.x > fx + 1 && b1.x > fx + 1) || (b0.y < fy - 1 && b1.y < fy - 1) || (b0.y > fy + 1 && b1.y > fy + 1)) continue;
+    const long long dx = (long long)b1.x - b0.x, dy = (long long)b1.y - b0.y;
+    const __int128 qx = pxn - (__int128)b0.x * pden, qy = pyn - (__int128)b0.y * pden;  // (P - b0) * pden
+    if (qx * dy - qy * dx != 0) continue;
+    // parameter of P along the segment from its dominant coordinate (64-bit safe for 16-bit coordinates)
+    const bool use_x = (dx < 0 ? -dx : dx) >= (dy < 0 ? -dy : dy);
+    const long long dd = use_x ? dx : dy;
+    __int128 sn = use_x ? qx : qy;
+    if (dd < 0) sn = -sn;
+    const __int128 sd = (__int128)pden * (dd < 0 ? -dd : dd);
+    if (sn < 0 || sn > sd) continue;
+    if (sn == 0) { *is_vertex = true; *vtx = b0; }
+    if (sn == sd) { *is_vertex = true; *vtx = b1; }
+    const rat s = {(long long)sn, (long long)sd};
+    if (sn < sd) { if (k >= MAX_RAYS) return -1; rays[k].dx = (int)dx; rays[k].dy = (int)dy; rays[k].sign = 1; rays[k].seg = j; rays[k].s = s; k++; }
+    if (sn > 0) { if (k >= MAX_RAYS) return -1; rays[k].dx = (int)-dx; rays[k].dy = (int)-dy; rays[k].sign = -1; rays[k].seg = j; rays[k].s = s; k++; }
+  }
+  return k;
+}
+
+// turn counter-clockwise about the node from just after direction r (winding w0 there); the first group of
+// coincident rays across which the winding becomes positive carries the boundary on.  Returns an outgoing ray
+// of that group (-1: none) and the winding on its right.
+__device__ int next_boundary_ray(ray_t *rays, int k, long long rx, long long ry, int w0, int prefer_seg, int *w_right) {
+  for (int i = 1; i < k; ++i) {
+    ray_t key = rays[i];
+    int j = i - 1;
+    while (j >= 0 && ccw_before(rx, ry, key.dx, key.dy, rays[j].dx, rays[j].dy)) { rays[j + 1] = rays[j]; j--; }
+    rays[j + 1] = key;
+  }
+  int w = w0;
+  for (int i = 0; i < k;) {
+    int e = i, net = 0, pick = -1;
+    while (e < k && same_dir(rays[i].dx, rays[i].dy, rays[e].dx, rays[e].dy)) {
+      net += rays[e].sign;
+      if (rays[e].sign > 0 && (pick < 0 || rays[e].seg == prefer_seg)) pick = e;
+      e++;
+    }
+    if (w <= 0 && w + net > 0) { *w_right = w; return pick; }
+    w += net;
+    i = e;
+  }
+  return -1;
+}
+
+// winding number at (P.x - eps, P.y + delta), 0 < eps << delta << 1
+__device__ int winding_above_left(const ipt *Q, int m, __int128 pxn, __int128 pyn, long long pden) {
+  int w = 0;
+  for (int j = 0; j < m; ++j) {
+    const ipt a = Q[j], b = Q[j + 1 == m ? 0 : j + 1];
+    const __int128 ax = (__int128)a.x * pden, bx = (__int128)b.x * pden;
+    int dir;
+    if (ax < pxn && pxn <= bx) dir = -1;
+    else if (bx < pxn && pxn <= ax) dir = 1;
+    else continue;
+    const __int128 lhs = (pxn - ax) * ((long long)b.y - a.y), rhs = (pyn - (__int128)a.y * pden) * ((long long)b.x - a.x);
+    const bool above = (b.x > a.x) ? (lhs > rhs) : (lhs < rhs);
+    if (above) w += dir;
+  }
+  return w;
+}
+
+struct rpt { __int128 xn, yn; long long den; };
+__device__ __forceinline__ bool node_after(const rpt &a, const rpt &b) {  // a strictly after b in (y descending, x ascending)
+  const __int128 ya = a.yn * b.den, yb = b.yn * a.den;
+  if (ya != yb) return ya < yb;
+  return a.xn * b.den > b.xn * a.den;
+}
+
+// one ring from (start_seg, start_t), then FixupOutPolygon; < 3: collapsed, -1: failure
+__device__ int walk_ring(const ipt *Q, int m, int start_seg, rat start_t, int w_right, ipt *out, int cap, ray_t *rays) {
+  int cur = start_seg, n_out = 0;
+  rat cur_t = start_t;
+  int guard = 0;
+  const int max_iter = 8 * m + 64;
+  for (;;) {
+    if (++guard > max_iter) return -1;
+    rat t_best = {1, 1};
+    // bounding box of the current segment: a segment whose (closed) box misses it cannot hit it
+    // in any of the three ways seg_hit distinguishes — an exact, cheap reject of most pairs
+    const ipt c0 = Q[cur], c1 = Q[cur + 1 == m ? 0 : cur + 1];
+    const int cminx = c0.x < c1.x ? c0.x : c1.x, cmaxx = c0.x < c1.x ? c1.x : c0.x;
+    const int cminy = c0.y < c1.y ? c0.y : c1.y, cmaxy = c0.y < c1.y ? c1.y : c0.y;
+    for (int j = 0; j < m; ++j) {
+      if (j == cur) continue;
+      const ipt b0 = Q[j], b1 = Q[j + 1 == m ? 0 : j + 1];
+      if ((b0.x < cminx && b1.x < cminx) || (b0.x > cmaxx && b1.x > cmaxx) || (b0.y < cminy && b1.y < cminy) || (b0.y > cmaxy && b1.y > cmaxy)) continue;
+      for (int which = 0; which < 3; ++which) {
+        rat t, s;
+        if (!seg_hit(Q, m, cur, j, which, &t, &s)) continue;
+        if (!rat_lt(cur_t, t)) continue;
+        if (rat_lt(t, t_best)) t_best = t;
+      }
+    }
+    const long long ux = (long long)c1.x - c0.x, uy = (long long)c1.y - c0.y;
+    const long long pden = t_best.den;
+    const __int128 pxn = (__int128)c0.x * pden + (__int128)t_best.num * ux, pyn = (__int128)c0.y * pden + (__int128)t_best.num * uy;
+    bool node_is_vertex;
+    ipt node_v = {0, 0};
+    const int k = rays_at(Q, m, pxn, pyn, pden, rays, &node_is_vertex, &node_v);
+    if (k < 0) return -1;
+    int wr;
+    const int pick = next_boundary_ray(rays, k, -ux, -uy, w_right, cur, &wr);
+    if (pick < 0) return -1;
+    const int nxt = rays[pick].seg;
+    const rat nxt_s = rays[pick].s;
+    if (node_is_vertex || nxt != cur) {
+      ipt node;
+      if (node_is_vertex) node = node_v;
+      else clipper_intersect_point(c0, c1, Q[nxt], Q[nxt + 1 == m ? 0 : nxt + 1], &node);
+      if (n_out >= cap) return -1;
+      out[n_out++] = node;
+    }
+    if (nxt == start_seg && rat_eq(nxt_s, start_t)) break;  // closed the ring (the start node was emitted last)
+    cur = nxt; cur_t = nxt_s; w_right = wr;
+  }
+  // FixupOutPolygon: drop duplicates and collinear middles until stable
+  bool changed = true;
+  while (changed && n_out >= 3) {
+    changed = false;
+    for (int i = 0; i < n_out && n_out >= 3; ++i) {
+      ipt p = out[(i + n_out - 1) % n_out], c = out[i], nn = out[(i + 1) % n_out];
+      bool dup = (c.x == nn.x && c.y == nn.y) || (c.x == p.x && c.y == p.y);
+      bool col = crossi((long long)c.x - p.x, (long long)c.y - p.y, (long long)nn.x - c.x, (long long)nn.y - c.y) == 0;
+      if (dup || col) {
+        for (int k2 = i; k2 + 1 < n_out; ++k2) out[k2] = out[k2 + 1];
+        n_out--; changed = true; i--;
+      }
+    }
+  }
+  return n_out;
+}
+
+// Q: scratch for the de-duplicated path (also the rotation scratch).
+__device__ int union_positive(const ipt *Qin, int m_in, ipt *Q, ipt *out, int cap, ipt *fast, int fast_cap) {
   int m = 0;
   for (int i = 0; i < m_in; ++i)
     if (m == 0 || Q[m - 1].x != Qin[i].x || Q[m - 1].y != Qin[i].y) Q[m++] = Qin[i];
@@ -358,92 +509,45 @@ __device__ int union_outer(const ipt *Qin, int m_in, ipt *Q, ipt *out, int cap, 
     for (int i = 0; i < m; ++i) fast[i] = Q[i];
     Q = fast;
   }
-  int sv = 0;
-  for (int i = 1; i < m; ++i)
-    if (Q[i].y < Q[sv].y || (Q[i].y == Q[sv].y && Q[i].x < Q[sv].x)) sv = i;
-  int best = -1;
-  for (int i = 0; i < m; ++i) {
-    if (Q[i].x != Q[sv].x || Q[i].y != Q[sv].y) continue;
-    if (best < 0) { best = i; continue; }
-    int i1 = i + 1 == m ? 0 : i + 1, b1 = best + 1 == m ? 0 : best + 1;
-    long long dx = Q[i1].x - Q[i].x, dy = Q[i1].y - Q[i].y;
-    long long bx = Q[b1].x - Q[best].x, by = Q[b1].y - Q[best].y;
-    if (crossi(bx, by, dx, dy) < 0) best = i;
-  }
-  int cur = best;
-  rat cur_t = {0, 1};
-  const int start_seg = cur;
+  ray_t rays[MAX_RAYS];
+  // start search in (y descending, x ascending) order: the largest-y vertex first (nearly always on the
+  // boundary), then all vertices and crossings
+  rpt last = {0, 0, 1};
   int n_out = 0;
-  out[n_out++] = Q[cur];
-  int guard = 0;
-  const int max_iter = 8 * m + 64;
-  for (;;) {
-    if (++guard > max_iter) return 0;
-    rat t_best = {1, 1};
-    // bounding box of the current segment: a segment whose (closed) box misses it cannot hit it
-    // in any of the three ways seg_hit distinguishes — an exact, cheap reject of most pairs
-    const ipt cb0 = Q[cur], cb1 = Q[cur + 1 == m ? 0 : cur + 1];
-    const int cminx = cb0.x < cb1.x ? cb0.x : cb1.x, cmaxx = cb0.x < cb1.x ? cb1.x : cb0.x;
-    const int cminy = cb0.y < cb1.y ? cb0.y : cb1.y, cmaxy = cb0.y < cb1.y ? cb1.y : cb0.y;
-    auto box_miss = [&](int j) {
-      const ipt b0 = Q[j], b1 = Q[j + 1 == m ? 0 : j + 1];
-      return (b0.x < cminx && b1.x < cminx) || (b0.x > cmaxx && b1.x > cmaxx) || (b0.y < cminy && b1.y < cminy) || (b0.y > cmaxy && b1.y > cmaxy);
-    };
-    for (int j = 0; j < m; ++j) {
-      if (j == cur || box_miss(j)) continue;
-      for (int which = 0; which < 3; ++which) {
-        rat t, s;
-        if (!seg_hit(Q, m, cur, j, which, &t, &s)) continue;
-        if (!rat_lt(cur_t, t)) continue;
-        if (rat_lt(t, t_best)) t_best = t;
-      }
+  for (int tries = 0; tries < 4 * m + 16; ++tries) {
+    rpt best = {0, 0, 0};
+    for (int i = 0; i < m; ++i) {
+      rpt c = {Q[i].x, Q[i].y, 1};
+      if (tries > 0 && !node_after(c, last)) continue;
+      if (best.den == 0 || node_after(best, c)) best = c;
     }
-    ipt c0 = Q[cur], c1 = Q[cur + 1 == m ? 0 : cur + 1];
-    long long ux = c1.x - c0.x, uy = c1.y - c0.y;
-    long long rx = -ux, ry = -uy;
-    int nxt = -1;
-    rat nxt_s = {0, 1};
-    long long bdx = 0, bdy = 0;
-    bool node_is_vertex = false;
-    ipt node_v = {0, 0};
-    if (t_best.num == t_best.den) { node_is_vertex = true; node_v = c1; }
-    else { nxt = cur; nxt_s = t_best; bdx = ux; bdy = uy; }
-    for (int j = 0; j < m; ++j) {
-      if (j == cur || box_miss(j)) continue;
-      for (int which = 0; which < 3; ++which) {
-        rat t, s;
-        if (!seg_hit(Q, m, cur, j, which, &t, &s)) continue;
-        if (!rat_eq(t, t_best)) continue;
-        int j1 = j + 1 == m ? 0 : j + 1;
-        if (s.num == 0) { node_is_vertex = true; node_v = Q[j]; }
-        if (s.num == s.den) { node_is_vertex = true; node_v = Q[j1]; continue; }
-        long long dx = Q[j1].x - Q[j].x, dy = Q[j1].y - Q[j].y;
-        if (nxt < 0 || ccw_before(rx, ry, dx, dy, bdx, bdy)) { nxt = j; nxt_s = s; bdx = dx; bdy = dy; }
-      }
+    if (tries > 0) {
+      for (int i = 0; i < m; ++i)
+        for (int j = i + 1; j < m; ++j) {
+          rat t, sj;
+          if (!seg_hit(Q, m, i, j, 0, &t, &sj)) continue;
+          const int i1 = i + 1 == m ? 0 : i + 1;
+          const long long ux = (long long)Q[i1].x - Q[i].x, uy = (long long)Q[i1].y - Q[i].y;
+          rpt c = {(__int128)Q[i].x * t.den + (__int128)t.num * ux, (__int128)Q[i].y * t.den + (__int128)t.num * uy, t.den};
+          if (!node_after(c, last)) continue;
+          if (best.den == 0 || node_after(best, c)) best = c;
+        }
     }
-    if (nxt < 0) return 0;
-    if (nxt == start_seg && nxt_s.num == 0) break;
-    ipt node;
-    if (node_is_vertex) node = node_v;
-    else clipper_intersect_point(c0, c1, Q[nxt], Q[nxt + 1 == m ? 0 : nxt + 1], &node);
-    if (n_out >= cap) return 0;
-    out[n_out++] = node;
-    cur = nxt;
-    cur_t = nxt_s;
-  }
-  // FixupOutPolygon: drop duplicates and collinear middles until stable
-  bool changed = true;
-  while (changed && n_out >= 3) {
-    changed = false;
-    for (int i = 0; i < n_out && n_out >= 3; ++i) {
-      ipt p = out[(i + n_out - 1) % n_out], c = out[i], nn = out[(i + 1) % n_out];
-      bool dup = (c.x == nn.x && c.y == nn.y) || (c.x == p.x && c.y == p.y);
-      bool col = crossi(c.x - p.x, c.y - p.y, nn.x - c.x, nn.y - c.y) == 0;
-      if (dup || col) {
-        for (int k = i; k + 1 < n_out; ++k) out[k] = out[k + 1];
-        n_out--; changed = true; i--;
-      }
-    }
+    if (best.den == 0) break;
+    last = best;
+    bool isv;
+    ipt vt;
+    const int k = rays_at(Q, m, best.xn, best.yn, best.den, rays, &isv, &vt);
+    if (k < 0) break;
+    if (k == 0) continue;
+    const int w0 = winding_above_left(Q, m, best.xn, best.yn, best.den);
+    int w_right;
+    const int pick = next_boundary_ray(rays, k, 0, 1, w0, -1, &w_right);
+    if (pick < 0) continue;
+    n_out = walk_ring(Q, m, rays[pick].seg, rays[pick].s, w_right, out, cap, rays);
+    if (n_out < 0) { n_out = 0; break; }
+    if (n_out >= 3) break;
+    n_out = 0;
   }
   if (n_out < 3) return 0;
   // BuildResult order: start right after the last top-most vertex (rotate in place via Q)
@@ -631,7 +735,7 @@ __global__ void __launch_bounds__(UNCLIP_THREADS) unclip_kernel(const int *__res
   double distance = area * factor / perim;
   int m = clipper_offset_raw(src, n, distance, raw);
   __shared__ ipt s_fast[(UNCLIP_THREADS / 32) * SPARSE_LANES][UNCLIP_FAST_PTS];
-  int ne = m >= 3 ? union_outer(raw, m, Q, out, cap, s_fast[(threadIdx.x >> 5) * SPARSE_LANES + (threadIdx.x & 31)], UNCLIP_FAST_PTS) : 0;
+  int ne = m >= 3 ? union_positive(raw, m, Q, out, cap, s_fast[(threadIdx.x >> 5) * SPARSE_LANES + (threadIdx.x & 31)], UNCLIP_FAST_PTS) : 0;
   if (ne == 0) { status[i] = 2; return; }
   ipt box[4];
   double sside = min_area_bounding_box(out, ne, work, hull, box);

@@ -452,7 +452,7 @@ static int same_dir(int64_t ax, int64_t ay, int64_t bx, int64_t by) {
  * Crossing a ray while turning counter-clockwise about the node changes the winding number
  * by its sign. */
 typedef struct { int64_t dx, dy; int sign, seg; rat s; } ray_t;
-#define ORC_MAX_RAYS 64
+#define ORC_MAX_RAYS 32
 
 /* All rays at the point P = (pxn, pyn) / pden (pden > 0).  *is_vertex / *vtx: P coincides with
  * a path vertex.  Returns the ray count, -1 when more than ORC_MAX_RAYS meet in one point. */
@@ -465,11 +465,15 @@ static int rays_at(const ipt *Q, int m, __int128 pxn, __int128 pyn, __int128 pde
     int64_t dx = (int64_t)b1.x - b0.x, dy = (int64_t)b1.y - b0.y;
     __int128 qx = pxn - (__int128)b0.x * pden, qy = pyn - (__int128)b0.y * pden; /* (P - b0) * pden */
     if (qx * dy - qy * dx != 0) continue;                                        /* not on the line */
-    __int128 sn = qx * dx + qy * dy, sd = pden * ((__int128)dx * dx + (__int128)dy * dy);
+    /* parameter of P along the segment, from its dominant coordinate (fits 64 bits for 16-bit coordinates) */
+    int use_x = (dx < 0 ? -dx : dx) >= (dy < 0 ? -dy : dy);
+    int64_t dd = use_x ? dx : dy;
+    __int128 sn = use_x ? qx : qy;
+    if (dd < 0) sn = -sn;
+    __int128 sd = pden * (dd < 0 ? -dd : dd);
     if (sn < 0 || sn > sd) continue;
     if (sn == 0) { *is_vertex = 1; *vtx = b0; }
     if (sn == sd) { *is_vertex = 1; *vtx = b1; }
-    /* reduce s to 64-bit: s = sn / sd with sd <= 2^62 for coordinates below 2^15 */
     rat s = {(int64_t)sn, (int64_t)sd};
     if (sn < sd) { if (k >= ORC_MAX_RAYS) return -1; rays[k].dx = dx; rays[k].dy = dy; rays[k].sign = 1; rays[k].seg = j; rays[k].s = s; k++; }
     if (sn > 0) { if (k >= ORC_MAX_RAYS) return -1; rays[k].dx = -dx; rays[k].dy = -dy; rays[k].sign = -1; rays[k].seg = j; rays[k].s = s; k++; }
