@@ -213,10 +213,10 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # any NCCL_DEBUG level prints a version banner on stdout: keep stdout to the single JSON line (BENCH_NCCL_DEBUG overrides)
-        os.environ.pop("NCCL_DEBUG", None)
-        if os.environ.get("BENCH_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
+        # NCCL_DEBUG output (the driver reads the rank count from it) is kept, but on stderr: stdout must hold the
+        # single JSON line, and NCCL writes its log to stdout unless NCCL_DEBUG_FILE names another file
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = _ffi.Context(local)
     det = resnet18(synth.make_detector_weights(0, "structured"), args.mode, ctx)
@@ -311,11 +311,16 @@ def main():
 
     peak_tf, peak_hbm, peak_src = peaks()
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_ncu_forward_traffic.json")
-    if os.path.exists(tpath):  # dram__bytes_read+write of the same launches from one `ncu --set full` capture
+    traffic_note = "no ncu --set full capture committed"
+    tpath = next((os.path.join(ROOT, "profiles", f) for f in ("r2_ncu_forward_traffic.json", "r1_ncu_forward_traffic.json")
+                  if os.path.exists(os.path.join(ROOT, "profiles", f))), "")
+    if tpath:  # dram__bytes_read+write of the same launches from one `ncu --set full` capture
         tj = json.load(open(tpath))
         # per launch like `achieved`: the pipeline forwards chunks of <= 256 images, the capture holds tj["images"] per launch
         traffic = tj["dram_bytes_per_launch"] * min(count, 256) / float(tj["images"])
+        per_image = tj.get("dram_bytes_per_image") or tj["dram_bytes_per_launch"] * tj.get("launches", 0) / float(tj["images"])
+        traffic_note = (f"avg DRAM bytes per tcgen05 launch from {os.path.basename(tpath)} ({per_image / 1e6:.0f} MB/image over {tj.get('launches', '?')} launches), "
+                        "scaled to this run's chunk of <= 256 images; algorithmic unfused bf16 activation traffic is 285.8 MB/image")
     flops_step = tc_flops_per_image(H, W) * count
     achieved = flops_step / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     groups = {}
@@ -345,7 +350,7 @@ def main():
         "gpu_launches": int(lt.item()),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                     "traffic": traffic, "traffic_note": "avg DRAM bytes per tcgen05 launch scaled to this run's chunk of <= 256 images (profiles/r1_ncu_forward_traffic.json: 227 MB/image measured); algorithmic unfused bf16 activation traffic is 285.8 MB/image", "kernel": "stem_tc / conv_halo / conv_lateral / conv_tc kernels (all tcgen05 implicit-GEMM launches of one step)", "launches": tc_n,
+                     "traffic": traffic, "traffic_note": traffic_note, "kernel": "stem_tc / conv_halo / conv_lateral / conv_tc kernels (all tcgen05 implicit-GEMM launches of one step)", "launches": tc_n,
                      "avg_launch_ms": tc_ms / max(tc_n, 1), "flops_per_image": tc_flops_per_image(H, W), "flops_executed_per_image": tc_flops_executed_per_image(H, W) if args.mode == "bf16" else tc_flops_per_image(H, W),
                      "achieved_executed": (achieved * tc_flops_executed_per_image(H, W) / tc_flops_per_image(H, W)) if args.mode == "bf16" else achieved,
                      "flops_note": "achieved/frac count the reference network's algorithmic FLOPs (SURVEY 8d); the fused FPN / bin_conv1 form executes fewer (flops_executed_per_image, achieved_executed)",

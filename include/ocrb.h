@@ -11,7 +11,12 @@
  *   - one ocrb_ctx per (device, stream); one ctx per host thread; no hidden global state.
  *   - every data pointer may be HOST memory (pageable or pinned) or DEVICE memory on the
  *     ctx's device; the library inspects the pointer (cudaPointerGetAttributes) and stages
- *     host buffers itself.  Calls are synchronous with respect to host-visible results.
+ *     host buffers itself.
+ *   - stream ordering: all work is launched on the ctx's own non-blocking stream(s) and every
+ *     entry point returns only after that work has completed, so OUTPUTS (host or device) are
+ *     complete on return.  A device INPUT must be complete before the call — synchronise its
+ *     producer, or call ocrb_ctx_wait_stream(ctx, producer_stream) first, which orders everything
+ *     queued on that stream so far before the ctx's later work without blocking the host.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     OCRB_ERR_CUDA.
  *   - layouts follow the reference: images / maps are row-major [B][H][W]; points are
@@ -58,6 +63,9 @@ int ocrb_ctx_create(int device, ocrb_ctx **out);
 int ocrb_ctx_destroy(ocrb_ctx *ctx);
 int ocrb_ctx_synchronize(ocrb_ctx *ctx);
 void *ocrb_ctx_stream(ocrb_ctx *ctx); /* cudaStream_t the ctx launches on */
+/* orders the work queued so far on `producer_stream` (a cudaStream_t; NULL = the legacy default
+ * stream) before everything this ctx launches afterwards.  Does not block the host. */
+int ocrb_ctx_wait_stream(ocrb_ctx *ctx, void *producer_stream);
 int ocrb_ctx_device(ocrb_ctx *ctx);
 /* number of kernels this ctx has launched since creation (bench.py "gpu_launches") */
 int64_t ocrb_ctx_launch_count(ocrb_ctx *ctx);

@@ -35,6 +35,7 @@ SIGNATURES = {
     "ocrb_ctx_destroy": (C.c_int, [c_p]),
     "ocrb_ctx_synchronize": (C.c_int, [c_p]),
     "ocrb_ctx_stream": (c_p, [c_p]),
+    "ocrb_ctx_wait_stream": (C.c_int, [c_p, c_p]),
     "ocrb_ctx_device": (C.c_int, [c_p]),
     "ocrb_ctx_launch_count": (i64, [c_p]),
     "ocrb_ctx_profile_begin": (C.c_int, [c_p]),
@@ -128,6 +129,12 @@ def ptr(x):
         return x
     if hasattr(x, "data_ptr"):
         assert x.is_contiguous(), "tensor must be contiguous"
+        if x.is_cuda:
+            # ocrb.h stream-ordering contract: a device input must be complete before the call.  The tensor may
+            # still be in flight on torch's current stream (and libocrb launches on its own stream), so its
+            # producer is synchronised here; outputs are complete when the call returns.
+            import torch
+            torch.cuda.current_stream(x.device).synchronize()
         return x.data_ptr()
     raise TypeError(type(x))
 

@@ -22,6 +22,7 @@ int launch_f32_to_u8(ocrb_ctx *, const float *, int64_t, float, uint8_t *);
 int launch_preprocess(ocrb_ctx *, const uint8_t *, int, int, int, int, int, int, uint8_t *, uint8_t *);
 int ccl_canonical_labels(ocrb_ctx *, const uint8_t *, int, int, int, int *, int *);
 void free_pp(ocrb_ctx *);
+void free_pipe(ocrb_ctx *);
 
 }  // namespace ocrb
 
@@ -80,6 +81,7 @@ int ocrb_ctx_destroy(ocrb_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   free_pp(ctx);
+  free_pipe(ctx);
   for (auto &b : ctx->stage) b.release();
   ctx->ccl_tile_empty.release();
   for (auto &b : ctx->pin) b.release();
@@ -93,6 +95,21 @@ int ocrb_ctx_synchronize(ocrb_ctx *ctx) {
   return sync(ctx);
 }
 void *ocrb_ctx_stream(ocrb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int ocrb_ctx_wait_stream(ocrb_ctx *ctx, void *producer_stream) {
+  OCRB_REQUIRE(ctx, "null ctx");
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  cudaEvent_t ev;
+  OCRB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, (cudaStream_t)producer_stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+  cudaEventDestroy(ev);  // released once the wait has been satisfied
+  if (e != cudaSuccess) {
+    set_error("ocrb_ctx_wait_stream -> %s", cudaGetErrorString(e));
+    return OCRB_ERR_CUDA;
+  }
+  return OCRB_OK;
+}
 int ocrb_ctx_device(ocrb_ctx *ctx) { return ctx ? ctx->device : -1; }
 int64_t ocrb_ctx_launch_count(ocrb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

@@ -94,6 +94,7 @@ struct PinBuf {
 };
 
 struct PostprocWorkspace;  // postproc.cu
+struct PipelineWorkspace;  // pipeline.cu
 
 // per-launch CUDA-event timeline of one ctx (the B200 counterpart of the reference's
 // measure_time! macro, macros.rs:46-71): when enabled, check_launch()/prof_mark() record an
@@ -118,6 +119,9 @@ struct ocrb_ctx {
   ocrb::PinBuf pin[3];
   ocrb::DevBuf ccl_tile_empty;  // one byte per CCL tile of the last labelling: 1 = no foreground pixel (ccl.cu)
   ocrb::PostprocWorkspace *pp = nullptr;
+  ocrb::PipelineWorkspace *pipe = nullptr;  // streams / events / buffers of ocrb_detect_and_recognize, created on first use
+  std::vector<const void *> smem_attr_done;  // kernels whose dynamic shared-memory limit this ctx has raised
+  int sm_limit = 0;                          // > 0: persistent convolution kernels use at most this many SMs (pipeline.cu)
   ocrb::Profiler prof;
 };
 
@@ -194,6 +198,18 @@ inline int check_launch(ocrb_ctx *ctx, const char *what) {
 }
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (device, function); remembered per ctx, so that two contexts
+// (devices, host threads) never share state
+template <class K>
+inline int ensure_dyn_smem(ocrb_ctx *ctx, K kern, int bytes) {
+  const void *key = reinterpret_cast<const void *>(kern);
+  for (const void *k : ctx->smem_attr_done)
+    if (k == key) return OCRB_OK;
+  OCRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  ctx->smem_attr_done.push_back(key);
+  return OCRB_OK;
+}
 
 // One-item-per-thread kernels whose items follow wildly different control flow (border tracing,
 // Douglas-Peucker, polygon offsetting) run only SPARSE_LANES lanes per warp: a warp executes

@@ -651,12 +651,8 @@ static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensor
   } else {
     pk.scale_host = pk.shift_host = nullptr;
   }
-  static bool attr_set[16] = {false};
   auto kern = conv_halo_kernel<N_TILE, G, CG, TS>;
-  if (!attr_set[ctx->device & 15]) {
-    OCRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
-    attr_set[ctx->device & 15] = true;
-  }
+  OCRB_TRY(ensure_dyn_smem(ctx, kern, 227 * 1024 - 4096));
   const int smem = 1024 + g.a_stages * g.a_stage_bytes + g.b_stages * (N_TILE / CG) * 128 + (TS ? g.obufs * g.obuf_bytes : HL_STG_BYTES) + 512;
   int grid = num_units * CG < ctx->sm_count ? num_units * CG : (ctx->sm_count / CG) * CG;
   cudaLaunchConfig_t cfg = {};

@@ -421,12 +421,8 @@ template <int N_TILE, int STAGES, int EPI, int RING, int EW>
 static int launch_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvTcParams &p, int num_tiles, const char *tag,
                       const HeadConsts &hc) {
   using L = TcSmem<N_TILE, STAGES, RING, EW>;
-  static bool attr_set[16] = {false};
   auto kern = conv_tc_kernel<N_TILE, STAGES, EPI, RING, EW>;
-  if (!attr_set[ctx->device & 15]) {
-    OCRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-    attr_set[ctx->device & 15] = true;
-  }
+  OCRB_TRY(ensure_dyn_smem(ctx, kern, L::DYN_BYTES));
   int grid = num_tiles < ctx->sm_count ? num_tiles : ctx->sm_count;
   kern<<<grid, (2 + EW) * 32, L::DYN_BYTES, ctx->stream>>>(tmA, tmB, p, hc);
   return check_launch(ctx, tag);

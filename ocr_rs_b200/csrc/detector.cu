@@ -254,6 +254,8 @@ static int prep_fused_downsample(const HostWeights &hw, const std::string &p, in
   }
   OCRB_TRY(upload(dc.w16, w16));
   OCRB_TRY(upload(dc.shift, t2));
+  dc.shift_h = t2;  // the host copy feeds the TMA-store epilogue's kernel-parameter constants: keep it in step
+  dc.scale_h = s2;
   dc.ds_cin = cin_ds;
   return OCRB_OK;
 }
@@ -643,7 +645,7 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
   for (auto &kv : d->act) before += kv.second.cap;
   bf *x0;
   OCRB_TRY(act(d, "b.stem", (int64_t)B * H4 * W4 * 64, &x0));
-  struct Blk { bf *t, *y, *ds; };
+  struct Blk { bf *t, *y, *ds; bool has_ds; };
   Blk blks[4][2];
   for (int li = 0; li < 4; ++li)
     for (int blk = 0; blk < 2; ++blk) {
@@ -652,15 +654,19 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
       OCRB_TRY(act(d, "b." + p + ".t", n, &blks[li][blk].t));
       OCRB_TRY(act(d, "b." + p + ".y", n, &blks[li][blk].y));
       blks[li][blk].ds = nullptr;
-      if (blk == 0 && li > 0) OCRB_TRY(act(d, "b." + p + ".ds", n, &blks[li][blk].ds));
+      blks[li][blk].has_ds = blk == 0 && li > 0;
+      // the downsample output exists only when the 1x1 stride-2 convolution is NOT folded into conv2
+      if (blks[li][blk].has_ds && d->conv[p + ".conv2"].ds_cin == 0) OCRB_TRY(act(d, "b." + p + ".ds", n, &blks[li][blk].ds));
     }
-  bf *in5, *in4, *in3, *s4, *s3, *s2, *fuse, *b1;
+  bf *in5, *in4 = nullptr, *in3 = nullptr, *s4, *s3 = nullptr, *s2 = nullptr, *fuse, *b1;
   OCRB_TRY(act(d, "b.in5", (int64_t)B * fh[3] * fw[3] * 256, &in5));
-  OCRB_TRY(act(d, "b.in4", (int64_t)B * fh[2] * fw[2] * 256, &in4));
-  OCRB_TRY(act(d, "b.in3", (int64_t)B * fh[1] * fw[1] * 256, &in3));
   OCRB_TRY(act(d, "b.s4", (int64_t)B * fh[2] * fw[2] * 256, &s4));
-  OCRB_TRY(act(d, "b.s3", (int64_t)B * fh[1] * fw[1] * 256, &s3));
-  OCRB_TRY(act(d, "b.s2", (int64_t)B * fh[0] * fw[0] * 256, &s2));
+  if (!d->fpn2_fused) {  // the fused neck reads x2 / x3 directly: raw in4, in3 and the sums s3 / s2 are never built
+    OCRB_TRY(act(d, "b.in4", (int64_t)B * fh[2] * fw[2] * 256, &in4));
+    OCRB_TRY(act(d, "b.in3", (int64_t)B * fh[1] * fw[1] * 256, &in3));
+    OCRB_TRY(act(d, "b.s3", (int64_t)B * fh[1] * fw[1] * 256, &s3));
+    OCRB_TRY(act(d, "b.s2", (int64_t)B * fh[0] * fw[0] * 256, &s2));
+  }
   const int fuse_c = d->fpn2_fused ? 64 : 256;
   OCRB_TRY(act(d, "b.fuse", (int64_t)B * H4 * W4 * fuse_c, &fuse));
   OCRB_TRY(act(d, "b.bin1", (int64_t)B * H4 * W4 * 64, &b1));
@@ -775,8 +781,8 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
       q1.relu = 1; q1.out = bk.t;
       OCRB_TRY(conv(p + ".conv1", x, hin, win, q1));
       const bf *res = x;
-      const bool ds_fused = bk.ds && d->conv[p + ".conv2"].ds_cin > 0;
-      if (bk.ds && !ds_fused) {
+      const bool ds_fused = bk.has_ds && d->conv[p + ".conv2"].ds_cin > 0;
+      if (bk.has_ds && !ds_fused) {
         ConvTcParams qd;
         qd.relu = 0; qd.out = bk.ds;
         OCRB_TRY(conv(p + ".downsample", x, hin, win, qd));

@@ -21,7 +21,7 @@ struct dpt { double x, y; };
 // HBM traffic: bbox_area * 4 B of the probability map, read once.
 // =======================================================================================
 constexpr int BS_THREADS = 256;
-constexpr int BS_MAX_PTS = 256;           // DP polygons with more vertices are rejected (flagged)
+constexpr int BS_MAX_PTS = 256;           // DP polygons with more vertices are read from global memory
 constexpr int BS_MASK_WORDS = 8192;       // 32 KB of mask bits per band
 
 __device__ __forceinline__ int clampi(long long v, long long lo, long long hi) { return (int)(v < lo ? lo : (v > hi ? hi : v)); }
@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(BS_THREADS) box_score_kernel(const float *__re
   if (cand >= n_cand) return;
   const int c = cand_contour ? cand_contour[cand] : cand;
   const int n = dp_count[c];
-  if (n > BS_MAX_PTS || n < 1) {
-    if (threadIdx.x == 0) { scores[cand] = -1.0; if (n > BS_MAX_PTS) atomicOr(err_flags, 1); }
+  if (n < 1) {
+    if (threadIdx.x == 0) scores[cand] = -1.0;
     return;
   }
   const ushort2 *pts = dp_pts + chain_off[c];
@@ -57,11 +57,17 @@ __global__ void __launch_bounds__(BS_THREADS) box_score_kernel(const float *__re
   const int min_x = clampi(mnx, 0, dim_m2 - 1), max_x = clampi(mxx, 0, dim_m2 - 1);
   const int min_y = clampi(mny, 0, dim_m1 - 1), max_y = clampi(mxy, 0, dim_m1 - 1);
   const int mw = max_x - min_x + 1, mh = max_y - min_y + 1;
-  for (int i = threadIdx.x; i < n; i += BS_THREADS) { px[i] = (int)pts[i].x - min_x; py[i] = (int)pts[i].y - min_y; }
+  // vertices relative to the box: in shared memory when they fit, straight from the DP arena otherwise (the
+  // reference has no vertex limit; a polygon with more than BS_MAX_PTS vertices is just slower here)
+  const bool in_smem = n <= BS_MAX_PTS;
+  if (in_smem)
+    for (int i = threadIdx.x; i < n; i += BS_THREADS) { px[i] = (int)pts[i].x - min_x; py[i] = (int)pts[i].y - min_y; }
   __syncthreads();
+  auto PX = [&](int i) { return in_smem ? px[i] : (int)pts[i].x - min_x; };
+  auto PY = [&](int i) { return in_smem ? py[i] : (int)pts[i].y - min_y; };
   // polygon vertical range clipped to the canvas (draw_polygon_mut)
   int y_min = INT32_MAX, y_max = INT32_MIN;
-  for (int i = 0; i < n; ++i) { y_min = min(y_min, py[i]); y_max = max(y_max, py[i]); }
+  for (int i = 0; i < n; ++i) { y_min = min(y_min, PY(i)); y_max = max(y_max, PY(i)); }
   y_min = max(0, min(y_min, mh - 1));
   y_max = max(0, min(y_max, mh - 1));
 
@@ -91,7 +97,8 @@ __global__ void __launch_bounds__(BS_THREADS) box_score_kernel(const float *__re
         // find the next crossing value >= last_v (respecting multiplicities)
         int best = INT32_MAX, best_mult = 0, cur_mult = 0;
         for (int e = 0; e < n; ++e) {
-          int x0 = px[e], y0 = py[e], x1 = px[e + 1 == n ? 0 : e + 1], y1 = py[e + 1 == n ? 0 : e + 1];
+          const int e1 = e + 1 == n ? 0 : e + 1;
+          int x0 = PX(e), y0 = PY(e), x1 = PX(e1), y1 = PY(e1);
           if (!((y0 <= y && y1 >= y) || (y1 <= y && y0 >= y))) continue;
           int v[2], nv = 0;
           if (y0 == y1) { v[nv++] = x0; v[nv++] = x1; }
@@ -133,8 +140,9 @@ __global__ void __launch_bounds__(BS_THREADS) box_score_kernel(const float *__re
     __syncthreads();
     // ---- outline: one thread per edge, Bresenham exactly as imageproc (f32 state) ----
     for (int e = threadIdx.x; e < n; e += BS_THREADS) {
-      float x0 = (float)px[e], y0 = (float)py[e];
-      float x1 = (float)px[e + 1 == n ? 0 : e + 1], y1 = (float)py[e + 1 == n ? 0 : e + 1];
+      const int e1 = e + 1 == n ? 0 : e + 1;
+      float x0 = (float)PX(e), y0 = (float)PY(e);
+      float x1 = (float)PX(e1), y1 = (float)PY(e1);
       bool steep = fabsf(y1 - y0) > fabsf(x1 - x0);
       if (steep) { float t = x0; x0 = y0; y0 = t; t = x1; x1 = y1; y1 = t; }
       if (x0 > x1) { float t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }

@@ -29,11 +29,10 @@ struct PipelineWorkspace {
   cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, fwd_done[2] = {nullptr, nullptr}, pp_ready = nullptr;
   bool ready = false;
 };
-static PipelineWorkspace *g_ws[16] = {nullptr};
-
+// the workspace belongs to the ctx (one ctx per host thread: no state is shared between contexts)
 static int get_ws(ocrb_ctx *ctx, PipelineWorkspace **out) {
-  PipelineWorkspace *&w = g_ws[ctx->device & 15];
-  if (!w) w = new PipelineWorkspace();
+  if (!ctx->pipe) ctx->pipe = new PipelineWorkspace();
+  PipelineWorkspace *w = ctx->pipe;
   if (!w->ready) {
     OCRB_CUDA(cudaStreamCreateWithFlags(&w->fwd, cudaStreamNonBlocking));
     OCRB_CUDA(cudaStreamCreateWithFlags(&w->copy, cudaStreamNonBlocking));
@@ -47,6 +46,23 @@ static int get_ws(ocrb_ctx *ctx, PipelineWorkspace **out) {
   }
   *out = w;
   return OCRB_OK;
+}
+
+void free_pipe(ocrb_ctx *ctx) {
+  PipelineWorkspace *w = ctx->pipe;
+  if (!w) return;
+  DevBuf *bufs[] = {&w->images[0], &w->images[1], &w->prob[0], &w->prob[1], &w->bitmap[0], &w->bitmap[1], &w->adjust, &w->glyphs, &w->argmax};
+  for (DevBuf *b : bufs) b->release();
+  for (int i = 0; i < 2; ++i) {
+    if (w->copied[i]) cudaEventDestroy(w->copied[i]);
+    if (w->consumed[i]) cudaEventDestroy(w->consumed[i]);
+    if (w->fwd_done[i]) cudaEventDestroy(w->fwd_done[i]);
+  }
+  if (w->pp_ready) cudaEventDestroy(w->pp_ready);
+  if (w->fwd) cudaStreamDestroy(w->fwd);
+  if (w->copy) cudaStreamDestroy(w->copy);
+  delete w;
+  ctx->pipe = nullptr;
 }
 
 constexpr int PIPE_CHUNK_BF16 = 256, PIPE_CHUNK_FP32 = 4, PIPE_GROUP = 256;  // 256 / 256 measured +3 % over 128 / 128 (fewer, longer launches)

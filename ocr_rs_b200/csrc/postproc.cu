@@ -227,10 +227,9 @@ static int run_postproc(ocrb_ctx *ctx, const float *pred, const uint8_t *bitmap,
   OCRB_CUDA(cudaMemcpyAsync(st.data(), ws->stats.p, (size_t)5 * B * 8, cudaMemcpyDeviceToHost, ctx->stream));
   OCRB_CUDA(cudaMemcpyAsync(&err, ws->err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   OCRB_TRY(sync(ctx));
-  if (err) {
-    set_error("post-processing capacity: a Douglas-Peucker polygon has more than 256 vertices or a box is wider than "
-              "262144 px (flags %d)", err);
-    return OCRB_ERR_CAPACITY;
+  if (err) {  // cannot happen for maps up to 65535 px wide (run_contour_stage checks that); kept as an internal check
+    set_error("post-processing: a candidate's bounding box does not fit the mask band (flags %d)", err);
+    return OCRB_ERR_INTERNAL;
   }
   for (size_t i = 0; i < st.size(); ++i) res->stats[i] = (int64_t)st[i];
   res->point_offsets[n_kept] = n_kept_pts;
@@ -418,7 +417,6 @@ static int upload_polygon(ocrb_ctx *ctx, PostprocWorkspace *ws, const int32_t *x
 
 int ocrb_box_score_fast(ocrb_ctx *ctx, const float *pred, int dim_m2, int dim_m1, const int32_t *xy, int n_pts, double *score) {
   OCRB_REQUIRE(ctx && pred && xy && score && n_pts > 0 && dim_m1 > 0 && dim_m2 > 0, "bad argument");
-  OCRB_REQUIRE(n_pts <= 256, "box_score_fast supports up to 256 polygon points");
   OCRB_CUDA(cudaSetDevice(ctx->device));
   PostprocWorkspace *ws = get_pp(ctx);
   const void *pred_dev = nullptr;

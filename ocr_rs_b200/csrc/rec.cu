@@ -191,21 +191,36 @@ extern "C" {
 int ocrb_rec_create(ocrb_ctx *ctx, int n, const char *const *names, const float *const *data, const int64_t *numel, ocrb_rec **out) {
   OCRB_REQUIRE(ctx && names && data && numel && out && n > 0, "bad argument");
   OCRB_CUDA(cudaSetDevice(ctx->device));
-  // canonical names, or the de-duplicated VarStore names tch produces when all four layers
-  // are created on one path (char_recognition/model.rs:14-17)
+  // Canonical names ("conv1.weight" ...), or the VarStore names of the reference's model file.  There all four
+  // layers are created on ONE path (char_recognition/model.rs:14-17), so the names collide and tch de-duplicates
+  // them with a "__<n>" suffix whose numbering depends on the creation order inside nn::conv / nn::linear
+  // (bias-first for conv; linear differs between tch versions).  The suffix is therefore NOT
+  // interpreted: a tensor called weight* / bias* is placed by its element count, and the eight counts are distinct.
   static const char *canon[8] = {"conv1.bias", "conv1.weight", "conv2.bias", "conv2.weight", "fc1.bias", "fc1.weight", "fc2.bias", "fc2.weight"};
-  static const char *alias[8] = {"bias", "weight", "bias__2", "weight__3", "bias__4", "weight__5", "bias__6", "weight__7"};
   static const int64_t sizes[8] = {32, 32 * 25, 64, 64 * 32 * 25, 512, 512 * 1024, 62, 62 * 512};
   const float *t[8] = {nullptr};
   for (int i = 0; i < n; ++i) {
     OCRB_REQUIRE(names[i] && data[i], "bad tensor %d", i);
+    int slot = -1;
     for (int k = 0; k < 8; ++k)
-      if (strcmp(names[i], canon[k]) == 0 || strcmp(names[i], alias[k]) == 0) {
-        OCRB_REQUIRE(numel[i] == sizes[k], "tensor %s has %lld elements, expected %lld", names[i], (long long)numel[i], (long long)sizes[k]);
-        t[k] = data[i];
-      }
+      if (strcmp(names[i], canon[k]) == 0) slot = k;
+    if (slot < 0) {
+      std::string base(names[i]);
+      const size_t us = base.find("__");
+      if (us != std::string::npos) base.resize(us);
+      const size_t dot = base.rfind('.');
+      if (dot != std::string::npos) base = base.substr(dot + 1);
+      const int kind = base == "bias" ? 0 : (base == "weight" ? 1 : -1);
+      if (kind < 0) continue;  // not a tensor of this net
+      for (int k = kind; k < 8; k += 2)
+        if (numel[i] == sizes[k]) slot = k;
+      OCRB_REQUIRE(slot >= 0, "tensor %s has %lld elements: no %s of the glyph net has that size", names[i], (long long)numel[i], base.c_str());
+    }
+    OCRB_REQUIRE(numel[i] == sizes[slot], "tensor %s has %lld elements, expected %lld", names[i], (long long)numel[i], (long long)sizes[slot]);
+    OCRB_REQUIRE(!t[slot], "tensor %s: %s given twice", names[i], canon[slot]);
+    t[slot] = data[i];
   }
-  for (int k = 0; k < 8; ++k) OCRB_REQUIRE(t[k], "missing tensor %s (alias %s)", canon[k], alias[k]);
+  for (int k = 0; k < 8; ++k) OCRB_REQUIRE(t[k], "missing tensor %s", canon[k]);
   ocrb_rec *r = new ocrb_rec();
   r->ctx = ctx;
   auto fail = [&](int rc) { ocrb_rec_destroy(r); return rc; };

@@ -270,12 +270,8 @@ int launch_stem_tc(ocrb_ctx *ctx, const void *in, int is_u8, int B, int H, int W
   StemConsts sc;
   memcpy(sc.scale, scale_host, sizeof(sc.scale));
   memcpy(sc.shift, shift_host, sizeof(sc.shift));
-  static bool attr_set[16] = {false};
-  if (!attr_set[ctx->device & 15]) {
-    OCRB_CUDA(cudaFuncSetAttribute(stem_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
-    OCRB_CUDA(cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
-    attr_set[ctx->device & 15] = true;
-  }
+  OCRB_TRY(ensure_dyn_smem(ctx, stem_tc_kernel<uint8_t>, SK_SMEM));
+  OCRB_TRY(ensure_dyn_smem(ctx, stem_tc_kernel<float>, SK_SMEM));
   const int Hp = H / 4, Wp = W / 4;
   const int64_t units = cdiv(Wp, SK_PW) * cdiv(Hp, SK_PH) * B;
   const int grid = (int)(units < SK_OCC * ctx->sm_count ? units : SK_OCC * ctx->sm_count);

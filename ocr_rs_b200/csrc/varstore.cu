@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <exception>
 #include <memory>
 #include <string>
 #include <vector>
@@ -43,15 +44,15 @@ int zip_index(const std::vector<uint8_t> &f, std::vector<ZipEntry> &out) {
   if (cd_off == 0xffffffffu || count == 0xffff) {  // ZIP64: locator just before the EOCD
     if (eocd < 20 || rd32(&f[eocd - 20]) != 0x07064b50u) { set_error("ZIP64 locator missing"); return OCRB_ERR_INVALID; }
     const uint64_t e64 = rd64(&f[eocd - 20 + 8]);
-    if (e64 + 56 > n || rd32(&f[e64]) != 0x06064b50u) { set_error("bad ZIP64 end-of-central-directory record"); return OCRB_ERR_INVALID; }
+    if (e64 > n || n - e64 < 56 || rd32(&f[e64]) != 0x06064b50u) { set_error("bad ZIP64 end-of-central-directory record"); return OCRB_ERR_INVALID; }
     count = rd64(&f[e64 + 32]);
     cd_size = rd64(&f[e64 + 40]);
     cd_off = rd64(&f[e64 + 48]);
   }
-  if (cd_off + cd_size > n) { set_error("ZIP central directory out of range"); return OCRB_ERR_INVALID; }
+  if (cd_off > n || cd_size > n - cd_off) { set_error("ZIP central directory out of range"); return OCRB_ERR_INVALID; }
   uint64_t p = cd_off;
   for (uint64_t i = 0; i < count; ++i) {
-    if (p + 46 > n || rd32(&f[p]) != 0x02014b50u) { set_error("bad ZIP central-directory entry %llu", (unsigned long long)i); return OCRB_ERR_INVALID; }
+    if (p > n || n - p < 46 || rd32(&f[p]) != 0x02014b50u) { set_error("bad ZIP central-directory entry %llu", (unsigned long long)i); return OCRB_ERR_INVALID; }
     ZipEntry e;
     e.method = rd16(&f[p + 10]);
     uint64_t csize = rd32(&f[p + 20]), usize = rd32(&f[p + 24]), lho = rd32(&f[p + 42]);
@@ -70,10 +71,10 @@ int zip_index(const std::vector<uint8_t> &f, std::vector<ZipEntry> &out) {
       }
       x += 4 + len;
     }
-    if (lho + 30 > n || rd32(&f[lho]) != 0x04034b50u) { set_error("bad ZIP local header for %s", e.name.c_str()); return OCRB_ERR_INVALID; }
+    if (lho > n || n - lho < 30 || rd32(&f[lho]) != 0x04034b50u) { set_error("bad ZIP local header for %s", e.name.c_str()); return OCRB_ERR_INVALID; }
     e.data_off = lho + 30 + rd16(&f[lho + 26]) + rd16(&f[lho + 28]);
     e.size = usize;
-    if (e.method == 0 && e.data_off + e.size > n) { set_error("ZIP entry %s out of range", e.name.c_str()); return OCRB_ERR_INVALID; }
+    if (e.method == 0 && (e.data_off > n || e.size > n - e.data_off)) { set_error("ZIP entry %s out of range", e.name.c_str()); return OCRB_ERR_INVALID; }
     (void)csize;
     out.push_back(e);
     p += 46 + nl + xl + cl;
@@ -256,9 +257,7 @@ struct ocrb_varstore {
 
 using namespace ocrb;
 
-extern "C" {
-
-int ocrb_varstore_open(const char *path, ocrb_varstore **out) {
+static int varstore_open_impl(const char *path, ocrb_varstore **out) {
   OCRB_REQUIRE(path && out, "null argument");
   FILE *fp = fopen(path, "rb");
   if (!fp) { set_error("cannot open model file %s", path); return OCRB_ERR_INVALID; }
@@ -304,9 +303,16 @@ int ocrb_varstore_open(const char *path, ocrb_varstore **out) {
     for (auto &e : entries)
       if (e.name == want) blob = &e;
     OCRB_REQUIRE(blob && blob->method == 0, "storage %s of variable %s is missing from the archive", want.c_str(), k->s.c_str());
+    // sizes come from the pickle: bound the element count before allocating.  A tensor may be a broadcast view
+    // (stride 0) of a smaller storage, so the bound is generous but finite: 2^31 elements.
     int64_t numel = 1;
-    for (int64_t d : v->sizes) numel *= d;
-    OCRB_REQUIRE(v->sizes.size() == v->strides.size() && numel >= 0, "variable %s has inconsistent sizes/strides", k->s.c_str());
+    bool sane = v->sizes.size() == v->strides.size() && v->sizes.size() <= 8;
+    for (int64_t d : v->sizes) {
+      if (d < 0 || (d > 0 && numel > ((int64_t)1 << 31) / d)) { sane = false; break; }
+      numel *= d;
+    }
+    OCRB_REQUIRE(sane, "variable %s has inconsistent or oversized sizes/strides", k->s.c_str());
+    const uint64_t storage_elems = blob->size / (uint64_t)esz;
     std::vector<float> vals((size_t)numel);
     const uint8_t *base = f.data() + blob->data_off;
     const int nd = (int)v->sizes.size();
@@ -314,7 +320,7 @@ int ocrb_varstore_open(const char *path, ocrb_varstore **out) {
     for (int64_t n = 0; n < numel; ++n) {  // general strided gather (tch writes contiguous tensors; views are legal)
       int64_t off = v->offset;
       for (int d = 0; d < nd; ++d) off += idx[d] * v->strides[d];
-      OCRB_REQUIRE(off >= 0 && (uint64_t)(off + 1) * esz <= blob->size, "variable %s reads outside its storage", k->s.c_str());
+      OCRB_REQUIRE(off >= 0 && (uint64_t)off < storage_elems, "variable %s reads outside its storage", k->s.c_str());
       const uint8_t *q = base + off * esz;
       float x;
       switch (kind) {
@@ -336,6 +342,21 @@ int ocrb_varstore_open(const char *path, ocrb_varstore **out) {
   OCRB_REQUIRE(!vs->names.empty(), "%s holds no tensors", path);
   *out = vs.release();
   return OCRB_OK;
+}
+
+extern "C" {
+
+// nothing throws across the ABI: a corrupt archive can still make a container throw (bad_alloc, length_error)
+int ocrb_varstore_open(const char *path, ocrb_varstore **out) {
+  try {
+    return varstore_open_impl(path, out);
+  } catch (const std::exception &e) {
+    set_error("model file %s: %s", path ? path : "(null)", e.what());
+    return OCRB_ERR_INVALID;
+  } catch (...) {
+    set_error("model file %s: unknown failure", path ? path : "(null)");
+    return OCRB_ERR_INVALID;
+  }
 }
 
 int ocrb_varstore_count(const ocrb_varstore *vs) { return vs ? (int)vs->names.size() : 0; }

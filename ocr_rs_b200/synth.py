@@ -131,9 +131,14 @@ REC_CANONICAL = [
     ("fc2.weight", (62, 512)),
 ]
 # tch de-duplicated names when all four layers share one path (SURVEY.md Appendix B,
-# char_recognition/model.rs:14-17); accepted as aliases by ocrb_rec_create.
-REC_VARSTORE_ALIASES = [
+# char_recognition/model.rs:14-17).  The "__<n>" numbering depends on the creation order inside nn::conv /
+# nn::linear, which differs between tch versions: ocrb_rec_create ignores the suffix and places weight* / bias*
+# tensors by element count, so both orders (and any other numbering) load.
+REC_VARSTORE_ALIASES = [  # bias before weight in every layer
     "bias", "weight", "bias__2", "weight__3", "bias__4", "weight__5", "bias__6", "weight__7",
+]
+REC_VARSTORE_ALIASES_WEIGHT_FIRST_LINEAR = [  # nn::conv bias-first, nn::linear weight-first (tch 0.3.0 as read by the advisor)
+    "bias", "weight", "bias__2", "weight__3", "bias__5", "weight__4", "bias__7", "weight__6",
 ]
 
 

@@ -35,6 +35,18 @@ def test_box_score_kats(api, pts, expected):
     assert metrics.box_score_fast(cf.KAT_MAP_5x5, pts) == expected
 
 
+def test_box_score_many_vertices(api):
+    """No vertex limit (the reference has none): 300- and 1000-vertex polygons take the global-memory path."""
+    metrics, _, synth, pp = api
+    rng = np.random.default_rng(5)
+    pred = rng.random((400, 500), dtype=np.float32)
+    for n in (256, 257, 300, 1000):
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+        r = rng.uniform(60, 190, n)
+        pts = np.stack([250 + r * np.cos(ang), 200 + r * np.sin(ang)], 1).round().astype(np.int32)
+        assert abs(metrics.box_score_fast(pred, pts) - pp.box_score(pred, pts)) <= 1e-12
+
+
 def test_min_area_bounding_box_kat(api):
     metrics = api[0]
     box, sside = metrics.get_min_area_bounding_box(cf.KAT_MINRECT_IN)

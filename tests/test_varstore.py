@@ -80,3 +80,39 @@ def test_create_from_file_matches_create_from_arrays(tmp_path):
     rec.ctx, rec._h = ctx, _ffi.c_p()
     _ffi.check(_ffi.lib().ocrb_rec_create_from_file(ctx.handle, pr.encode(), C.byref(rec._h)))
     assert (rec.predict(g)[0] == Net(wr).predict(g)[0]).all()
+
+
+def test_corrupt_archives_are_rejected_not_fatal(tmp_path):
+    """ocrb.h: nothing throws across the ABI.  Truncated files, absurd sizes in the pickle and wrapped ZIP
+    offsets must come back as OCRB_ERR_INVALID (host-only: no device needed)."""
+    import ctypes as C
+    import os
+
+    from ocr_rs_b200 import _ffi
+    src = open(os.path.join(os.path.dirname(__file__), "golden", "varstore_libtorch.ot"), "rb").read()
+    L = _ffi.lib()
+
+    def opens(blob):
+        p = tmp_path / "m.ot"
+        p.write_bytes(blob)
+        h = _ffi.c_p()
+        rc = L.ocrb_varstore_open(str(p).encode(), C.byref(h))
+        if rc == 0:
+            L.ocrb_varstore_close(h)
+        return rc
+
+    assert opens(src) == 0
+    assert opens(src[:10]) == -1 and opens(b"") == -1 and opens(src[: len(src) // 2]) == -1
+    rng = np.random.default_rng(0)
+    for _ in range(300):  # random byte corruption anywhere (directory, pickle, sizes): never a crash
+        b = bytearray(src)
+        for _ in range(int(rng.integers(1, 8))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        assert opens(bytes(b)) in (0, -1)
+    # a huge dimension written into the pickle's size tuple (BININT 'J' + 4 bytes little endian)
+    b = bytearray(src)
+    pk = src.find(b"data.pkl")
+    for i in range(pk, len(b) - 5):
+        if b[i] == ord("J"):
+            b[i + 1:i + 5] = (0x7fffffff).to_bytes(4, "little")
+    assert opens(bytes(b)) in (0, -1)
