@@ -278,17 +278,31 @@ def main():
     launches = ctx.launch_count - l0
     clocks = sampler.stop(t0, t1) if sampler else None
 
-    # ---- e2e: pinned host inputs, results to the host, host gather of the polygons
+    # ---- e2e: pinned host inputs, results to the host, host gather of the polygons (every step: rank 0 ends the
+    # step holding the whole batch's polygon list).  One process per GPU on one box: the gather goes through POSIX
+    # shared memory (sharding.ShmGather) — no pickling, no collective, no GPU synchronisation.
     d2h = [0]
+    gather = sharding.ShmGather(rank, world, os.environ.get("MASTER_PORT", "0") + "_" + str(os.getppid())) if world > 1 else None
+    e2e_no = [0]
+    e2e_polys = [0]
 
     def e2e_step():
         res = step(host_imgs, host_gl, host_am, keep=True)
         d2h[0] = res.xy.nbytes + res.all_scores.nbytes + res.point_offsets.nbytes + res.image_offsets.nbytes + host_am.numel() * 4
-        sharding.gather_polygons(res)
+        if gather:
+            gather.publish(res, e2e_no[0])
+            if rank == 0:
+                res = gather.collect(e2e_no[0])
+            e2e_no[0] += 1
+        if rank == 0:
+            e2e_polys[0] = len(res.all_scores)
 
     for _ in range(args.warmup):
         e2e_step()
     ms_e2e, _, _ = timed(e2e_step, args.steps)
+    if gather:
+        barrier()
+        gather.close()
 
     # ---- per-kernel timeline of one more device-resident step (CUDA events on the ctx stream)
     ctx.profile_begin()
@@ -344,7 +358,8 @@ def main():
         "config": {"workload": f"cfg4: end-to-end detect+recognize, {args.images} synthetic 800x800 document images sharded by index over {world} GPU(s); "
                                "structured-head random weights (SURVEY 8d)", "images_per_step": args.images, "images_per_gpu": count,
                    "glyphs_per_image": GLYPHS_PER_IMAGE, "l2": "inputs (0.64 MB/image) larger than L2; no flush needed",
-                   "polygons_per_step_rank0": n_poly},
+                   "polygons_per_step_rank0": n_poly, "polygons_per_step_gathered": e2e_polys[0],
+                   "gather": "POSIX shared memory, rank order (sharding.ShmGather)" if world > 1 else "single rank"},
         "e2e": {"value": args.images * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": int(host_imgs.numel() + host_gl.numel() + adj.nbytes) * world, "d2h_bytes_per_step": int(d2h[0]) * world},
         "gpu_launches": int(lt.item()),

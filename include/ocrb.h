@@ -209,6 +209,32 @@ int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uint8_t *image
                               const uint8_t *glyphs, int n_glyphs, int32_t *glyph_argmax,
                               ocrb_polygons **out);
 
+/* ---- several GPUs of one box, one process -----------------------------------------------------
+ * The batch contract of the reference's evaluation loop (text_detection/mod.rs:188-204: images [n][H][W] +
+ * adjust [n][2] -> one PolygonScores) across devices: contiguous index shards (the first n % G shards hold one
+ * image more), one host thread per device inside the library, each with its own ctx + detector + recognition
+ * net (weights replicated), results appended into ONE host CSR in image order.  No collective.
+ * All buffers are HOST memory; allocate them with ocrb_host_alloc (page-locked) for full copy / compute overlap. */
+typedef struct ocrb_shards ocrb_shards;
+int ocrb_shards_create(const int *devices, int n_devices,
+                       int n_det, const char *const *det_names, const float *const *det_data, const int64_t *det_numel, int mode,
+                       int n_rec, const char *const *rec_names, const float *const *rec_data, const int64_t *rec_numel, /* n_rec = 0: no recognition net */
+                       ocrb_shards **out);
+int ocrb_shards_create_from_files(const int *devices, int n_devices, const char *det_path, const char *rec_path /* may be NULL */,
+                                  int mode, ocrb_shards **out);
+int ocrb_shards_destroy(ocrb_shards *s);
+int ocrb_shards_count(const ocrb_shards *s);
+int ocrb_shards_device(const ocrb_shards *s, int i);
+int64_t ocrb_shards_launch_count(const ocrb_shards *s); /* kernels launched by all shards since creation */
+/* [first, first + count) of shard `shard` out of `n_shards` */
+int ocrb_shard_range(int64_t n_items, int shard, int n_shards, int64_t *first, int64_t *count);
+/* ocrb_detect_and_recognize over all devices of `s`; glyphs are split the same way as the images */
+int ocrb_detect_and_recognize_sharded(ocrb_shards *s, const uint8_t *images, const double *adjust, int B, int H, int W,
+                                      const ocrb_postproc_params *params, const uint8_t *glyphs, int n_glyphs,
+                                      int32_t *glyph_argmax, ocrb_polygons **out);
+int ocrb_host_alloc(size_t bytes, void **out);
+int ocrb_host_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,18 @@ SIGNATURES = {
     "ocrb_rec_create_from_file": (C.c_int, [c_p, C.c_char_p, C.POINTER(c_p)]),
     "ocrb_detect_and_recognize": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.POINTER(PostprocParams),
                                             c_p, C.c_int, c_p, C.POINTER(c_p)]),
+    "ocrb_shards_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_p), C.POINTER(i64), C.c_int,
+                                     C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_p), C.POINTER(i64), C.POINTER(c_p)]),
+    "ocrb_shards_create_from_files": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(c_p)]),
+    "ocrb_shards_destroy": (C.c_int, [c_p]),
+    "ocrb_shards_count": (C.c_int, [c_p]),
+    "ocrb_shards_device": (C.c_int, [c_p, C.c_int]),
+    "ocrb_shards_launch_count": (i64, [c_p]),
+    "ocrb_shard_range": (C.c_int, [i64, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)]),
+    "ocrb_detect_and_recognize_sharded": (C.c_int, [c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.POINTER(PostprocParams),
+                                                    c_p, C.c_int, c_p, C.POINTER(c_p)]),
+    "ocrb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(c_p)]),
+    "ocrb_host_free": (C.c_int, [c_p]),
 }
 
 _lib = None

@@ -205,3 +205,38 @@ def test_config4_full_size_shard_invariance(env):
         undecidable += r["undecidable"]
     print(f"config 4 bench images vs oracle end-to-end: {matched} polygons matched at IoU>=0.99, {undecidable} undecidable, 0 failures")
     assert matched >= 500 and undecidable <= matched // 4, (matched, undecidable)
+
+
+def test_sharded_entry_point(env):
+    """ocrb_detect_and_recognize_sharded (one host thread per device inside the library): the whole
+    batch's polygons and glyph classes are those of the single-device call, on one device and — when the box has
+    them — on two and on all devices; more devices than images is legal."""
+    torch = pytest.importorskip("torch")
+    _ffi, synth, Net, resnet18, _, _ = env
+    from ocr_rs_b200 import OcrbError, sharding
+    B, H, W = 45, 160, 160
+    wd = synth.make_detector_weights(0, "structured")
+    wr = synth.make_rec_weights(1)
+    imgs = synth.document_image_shard(0, B, H, W, unique=50)
+    glyphs = synth.make_glyphs(4 * B + 3, 4, "strokes")
+    adj = np.ones((B, 2))
+    adj[::3] = (2.0, 0.5)
+    det, rec = resnet18(wd, "bf16"), Net(wr)
+    want, want_am = _run_pipeline(_ffi, det, rec, imgs, adj, glyphs)
+    n_dev = torch.cuda.device_count()
+    for devices in ([0], list(range(min(2, n_dev))), list(range(n_dev))):
+        sh = sharding.Shards(devices, wd, wr, "bf16")
+        got, am = sh.detect_and_recognize(imgs, adj, glyphs)
+        for x, y in zip(want.arrays(), got.arrays()):
+            assert x.shape == y.shape and (x == y).all(), devices
+        assert (am == want_am).all()
+        # a batch smaller than the device list
+        got1, am1 = sh.detect_and_recognize(imgs[:1], adj[:1], glyphs[:2])
+        assert (got1.xy == _run_pipeline(_ffi, det, rec, imgs[:1], adj[:1], glyphs[:2])[0].xy).all() and (am1 == want_am[:2]).all()
+        assert sh.launch_count > 0
+        sh.close()
+    with pytest.raises(OcrbError):
+        sharding.Shards([0, 0], wd, wr)
+    with pytest.raises(OcrbError):
+        sh = sharding.Shards([0], wd, None)
+        sh.detect_and_recognize(torch.from_numpy(imgs).cuda(), adj)  # device pointers cannot feed several devices

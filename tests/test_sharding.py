@@ -81,3 +81,60 @@ def test_gather_world_size_2_gloo():
     for a, b in zip(arrays, whole.arrays()):
         assert a.shape == b.shape and (a == b).all()
     assert lists == [[p.tolist() for p in img] for img in whole.polygons]
+
+
+def test_c_shard_range_matches_python():
+    """ocrb_shard_range (the split ocrb_detect_and_recognize_sharded uses inside the library) == sharding.shard_range."""
+    import ctypes as C
+
+    from ocr_rs_b200 import _ffi
+    from ocr_rs_b200.sharding import shard_range
+    L = _ffi.lib()
+    for n in (0, 1, 7, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                f, c = C.c_int64(), C.c_int64()
+                assert L.ocrb_shard_range(n, r, world, C.byref(f), C.byref(c)) == 0
+                assert (f.value, c.value) == shard_range(n, r, world)
+    assert L.ocrb_shard_range(5, 3, 3, C.byref(f), C.byref(c)) != 0
+
+
+def _shm_worker(rank, world, key, n, steps, q):
+    sys.path.insert(0, ROOT)
+    from ocr_rs_b200 import sharding
+    g = sharding.ShmGather(rank, world, key, cap_bytes=1 << 20)
+    first, count = sharding.shard_range(n, rank, world)
+    out = []
+    for step in range(steps):
+        mine = _fake_result(first + step, count)  # a different payload every step
+        g.publish(mine, step)
+        if rank == 0:
+            out.append(g.collect(step).arrays())
+    if rank == 0:
+        q.put(out)
+    else:
+        import time
+        time.sleep(0.5)  # keep the segment alive until rank 0 has read the last step
+    g.close()
+
+
+def test_shm_gather_world_size_3():
+    """The shared-memory gather the bench's e2e leg uses at N > 1: three ranks, five steps (slots are reused:
+    the writer must wait for the reader's acknowledgement), results in rank order."""
+    import multiprocessing as mp
+    n, world, steps, key = 11, 3, 5, f"test{os.getpid()}"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shm_worker, args=(r, world, key, n, steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    from ocr_rs_b200.sharding import shard_range
+    from ocr_rs_b200._ffi import Polygons
+    for step in range(steps):
+        want = Polygons.concat([_fake_result(shard_range(n, r, world)[0] + step, shard_range(n, r, world)[1]) for r in range(world)])
+        for a, b in zip(out[step], want.arrays()):
+            assert a.shape == b.shape and (a == b).all()
