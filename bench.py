@@ -5,7 +5,7 @@
   python bench.py --impl reference ...                   (the CPU path: oracle port on the host cores)
 
 A "step" is one pass of the hot path (u8 images -> detector -> binarize -> contours -> box score
--> unclip -> polygons, plus the glyph CNN on 4 crops per image) over BASELINE config 4's batch:
+-> unclip -> polygons -> crop glue: 4 glyph tiles cut from every kept polygon -> glyph CNN) over BASELINE config 4's batch:
 1024 synthetic 800x800 images, sharded by contiguous index range over the N ranks (strong
 scaling, no data-path collective; host-side gather of the polygons only).
 
@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 TOTAL_IMAGES = 1024
 H = W = 800
-GLYPHS_PER_IMAGE = 4
+GLYPHS_PER_POLYGON = 4  # crop glue: tiles cut from every kept polygon (ocrb_detect_and_read)
 METRIC = "800x800 det+rec images/sec"
 CPU_BATCH = 0  # 0 = calibrate (1 or 4) on first use
 
@@ -110,18 +110,25 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_path(wd, wr, imgs, glyphs, adj, threads):
-    """The reference's CPU implementation of the path, restated (oracle/): returns #polygons."""
+def cpu_path(wd, wr, imgs, adj, threads):
+    """The reference's CPU implementation of the path, restated (oracle/): detector -> post-processing -> crop glue ->
+    glyph net on the crops.  Returns #polygons."""
     import torch
     from oracle import model_oracle as mo
     from oracle import postproc as pp
     torch.set_num_threads(threads)
     x = torch.from_numpy(imgs.reshape(-1, 1, imgs.shape[-2], imgs.shape[-1])).to(torch.float32)  # convert_image_to_tensor + to_kind(Float)
     pred = mo.detector_forward(wd, x).numpy()
-    polys, _ = pp.boxes_and_box_scores(pred, adj)
-    g = torch.from_numpy(glyphs).to(torch.float32) / 255.0
-    mo.rec_top1(mo.rec_forward(wr, g))
-    return sum(len(p) for p in polys)
+    seg = pp.binarize(pred, 0.6)
+    n, tiles = 0, []
+    for b in range(len(imgs)):
+        polys, _, boxes = pp.polygons_from_bitmap(pred[b, 0], seg[b, 0], tuple(adj[b]), return_boxes=True)
+        n += len(polys)
+        tiles += [pp.crop_glyphs(imgs[b], box, GLYPHS_PER_POLYGON) for box in boxes]
+    if tiles:
+        g = torch.from_numpy(np.concatenate(tiles)).to(torch.float32) / 255.0
+        mo.rec_top1(mo.rec_forward(wr, g))
+    return n
 
 
 def time_cpu_sample(n_images, budget_s, threads, seed_first=0):
@@ -129,26 +136,25 @@ def time_cpu_sample(n_images, budget_s, threads, seed_first=0):
     wd = synth.make_detector_weights(0, "structured")
     wr = synth.make_rec_weights(1)
     imgs = synth.document_image_shard(seed_first, n_images, H, W)
-    glyphs = synth.make_glyphs(n_images * GLYPHS_PER_IMAGE, 1, "strokes")
     # the reference batches its evaluation loop (text_detection/mod.rs:188-204); which of batch 1 / 4 is faster for
     # torch-CPU depends on the host: calibrate on a few images and give the CPU its better setting
     global CPU_BATCH
     adj = np.ones((4, 2))
-    cpu_path(wd, wr, imgs[:1], glyphs[:GLYPHS_PER_IMAGE], adj[:1], threads)  # warm-up
+    cpu_path(wd, wr, imgs[:1], adj[:1], threads)  # warm-up
     if CPU_BATCH == 0:
         rate = {}
         for nb in (1, 4):
             k = min(4, n_images)
             t0 = time.time()
             for i in range(0, k, nb):
-                cpu_path(wd, wr, imgs[i:i + nb], glyphs[i * GLYPHS_PER_IMAGE:(i + nb) * GLYPHS_PER_IMAGE], adj[:min(nb, k - i)], threads)
+                cpu_path(wd, wr, imgs[i:i + nb], adj[:min(nb, k - i)], threads)
             rate[nb] = k / (time.time() - t0)
         CPU_BATCH = max(rate, key=rate.get)
     nb = CPU_BATCH
     done, t0 = 0, time.time()
     while done < n_images and (time.time() - t0 < budget_s or done == 0):
         k = min(nb, n_images - done)
-        cpu_path(wd, wr, imgs[done:done + k], glyphs[done * GLYPHS_PER_IMAGE:(done + k) * GLYPHS_PER_IMAGE], adj[:k], threads)
+        cpu_path(wd, wr, imgs[done:done + k], adj[:k], threads)
         done += k
     dt = time.time() - t0
     return done / dt, done, dt
@@ -167,14 +173,15 @@ def run_reference(args, rank):
             times.append(dt / done)
     sec_per_img = statistics.mean(times)
     value = 1.0 / sec_per_img
-    sample = f"{per_step} images 800x800 (+{GLYPHS_PER_IMAGE} glyphs each) per step, batch {CPU_BATCH}, torch {threads} threads + single-thread C post-proc"
+    sample = f"{per_step} images 800x800 ({GLYPHS_PER_POLYGON} glyph crops per kept polygon) per step, batch {CPU_BATCH}, torch {threads} threads + single-thread C post-proc / crop"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * sec_per_img * per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg4: end-to-end detect+recognize, {TOTAL_IMAGES} synthetic 800x800 document images; structured-head random weights (SURVEY 8d)"
+        "config": {"workload": f"cfg4: end-to-end detect+recognize, {TOTAL_IMAGES} synthetic 800x800 document images; structured-head random weights (SURVEY 8d); "
+                               f"recognition fed by the crop glue ({GLYPHS_PER_POLYGON} glyph tiles per kept polygon)"
                                f" - bounded CPU sample: {per_step} images per step",
-                   "images_per_step": per_step, "glyphs_per_image": GLYPHS_PER_IMAGE},
+                   "images_per_step": per_step, "glyphs_per_polygon": GLYPHS_PER_POLYGON},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -223,23 +230,17 @@ def main():
     rec = Net(synth.make_rec_weights(1), ctx)
     first, count = sharding.shard_range(args.images, rank, world)
     imgs = synth.document_image_shard(first, count, H, W)
-    glyphs = synth.make_glyphs(args.images * GLYPHS_PER_IMAGE, 1, "strokes")[first * GLYPHS_PER_IMAGE:(first + count) * GLYPHS_PER_IMAGE]
     adj = np.ones((count, 2), np.float64)
-    n_gl = len(glyphs)
 
     host_imgs = torch.from_numpy(imgs).pin_memory()
-    host_gl = torch.from_numpy(glyphs).pin_memory()
-    host_am = torch.empty(n_gl, dtype=torch.int32).pin_memory()
     dev_imgs = host_imgs.cuda()
-    dev_gl = host_gl.cuda()
-    dev_am = torch.empty(n_gl, dtype=torch.int32, device="cuda")
     stream = torch.cuda.ExternalStream(ctx.stream)
     L = _ffi.lib()
 
-    def step(images, gl, am, keep=False):
+    def step(images, keep=False):
+        # the whole path in one call: detector -> post-processing -> crop glue -> glyph net on the crops
         h = _ffi.c_p()
-        _ffi.check(L.ocrb_detect_and_recognize(det._h, rec._h, _ffi.ptr(images), _ffi.ptr(adj), count, H, W, None,
-                                               _ffi.ptr(gl), n_gl, _ffi.ptr(am), C.byref(h)))
+        _ffi.check(L.ocrb_detect_and_read(det._h, rec._h, _ffi.ptr(images), _ffi.ptr(adj), count, H, W, None, GLYPHS_PER_POLYGON, C.byref(h)))
         if keep:
             return _ffi.Polygons(h)
         n = int(L.ocrb_polygons_image_offsets(h)[count])
@@ -271,10 +272,10 @@ def main():
 
     # ---- value: device-resident inputs
     for _ in range(args.warmup):
-        n_poly = step(dev_imgs, dev_gl, dev_am)
+        n_poly = step(dev_imgs)
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ctx.launch_count
-    ms_dev, t0, t1 = timed(lambda: step(dev_imgs, dev_gl, dev_am), args.steps)
+    ms_dev, t0, t1 = timed(lambda: step(dev_imgs), args.steps)
     launches = ctx.launch_count - l0
     clocks = sampler.stop(t0, t1) if sampler else None
 
@@ -287,8 +288,8 @@ def main():
     e2e_polys = [0]
 
     def e2e_step():
-        res = step(host_imgs, host_gl, host_am, keep=True)
-        d2h[0] = res.xy.nbytes + res.all_scores.nbytes + res.point_offsets.nbytes + res.image_offsets.nbytes + host_am.numel() * 4
+        res = step(host_imgs, keep=True)
+        d2h[0] = res.xy.nbytes + res.all_scores.nbytes + res.point_offsets.nbytes + res.image_offsets.nbytes + res.glyph_classes.nbytes
         if gather:
             gather.publish(res, e2e_no[0])
             if rank == 0:
@@ -306,7 +307,7 @@ def main():
 
     # ---- per-kernel timeline of one more device-resident step (CUDA events on the ctx stream)
     ctx.profile_begin()
-    step(dev_imgs, dev_gl, dev_am)
+    step(dev_imgs)
     prof = ctx.profile_end()
     tc_ms = sum(ms for k, (c, ms) in prof.items() if k.startswith("tc:"))
     tc_n = sum(c for k, (c, ms) in prof.items() if k.startswith("tc:"))
@@ -349,19 +350,20 @@ def main():
         threads = os.cpu_count() or 1
         v, done, dt = time_cpu_sample(192, 15.0, threads)
         cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"{done} of the {args.images} images (+{GLYPHS_PER_IMAGE} glyphs each), batch {CPU_BATCH}, {dt:.1f} s: torch-CPU restatement ({threads} threads) + single-thread C post-proc"}
+               "sample": f"{done} of the {args.images} images ({GLYPHS_PER_POLYGON} glyph crops per kept polygon), batch {CPU_BATCH}, {dt:.1f} s: torch-CPU restatement ({threads} threads) + single-thread C post-proc / crop"}
 
     out = {
         "metric": METRIC, "value": args.images * args.steps / (ms_dev * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": args.mode if args.mode == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": f"cfg4: end-to-end detect+recognize, {args.images} synthetic 800x800 document images sharded by index over {world} GPU(s); "
-                               "structured-head random weights (SURVEY 8d)", "images_per_step": args.images, "images_per_gpu": count,
-                   "glyphs_per_image": GLYPHS_PER_IMAGE, "l2": "inputs (0.64 MB/image) larger than L2; no flush needed",
+                               f"structured-head random weights (SURVEY 8d); recognition fed by the crop glue: {GLYPHS_PER_POLYGON} glyph tiles cut from "
+                               "every kept polygon (ocrb_detect_and_read)", "images_per_step": args.images, "images_per_gpu": count,
+                   "glyphs_per_polygon": GLYPHS_PER_POLYGON, "glyphs_per_step_rank0": n_poly * GLYPHS_PER_POLYGON, "l2": "inputs (0.64 MB/image) larger than L2; no flush needed",
                    "polygons_per_step_rank0": n_poly, "polygons_per_step_gathered": e2e_polys[0],
                    "gather": "POSIX shared memory, rank order (sharding.ShmGather)" if world > 1 else "single rank"},
         "e2e": {"value": args.images * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
-                "h2d_bytes_per_step": int(host_imgs.numel() + host_gl.numel() + adj.nbytes) * world, "d2h_bytes_per_step": int(d2h[0]) * world},
+                "h2d_bytes_per_step": int(host_imgs.numel() + adj.nbytes) * world, "d2h_bytes_per_step": int(d2h[0]) * world},
         "gpu_launches": int(lt.item()),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,

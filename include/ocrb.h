@@ -209,6 +209,22 @@ int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uint8_t *image
                               const uint8_t *glyphs, int n_glyphs, int32_t *glyph_argmax,
                               ocrb_polygons **out);
 
+/* detection + the polygon -> glyph crop glue + recognition in one call.  The reference stops at the polygons
+ * (character segmentation is an open item of its README.md:20-26) and feeds its recognition net ready-made
+ * 28x28 files (image_ops.rs:73-85); this entry point closes the gap on the device: every kept polygon's min-area
+ * rectangle (metrics.rs:133-148) is cut out of its source image into `glyphs_per_polygon` cells along the
+ * rectangle's longer side, each cell is resized to 28x28 with preprocess_image's Triangle filter (crop spec v1,
+ * oracle/postproc_oracle.c orc_crop_glyphs) and classified.  Result: the polygons as above plus
+ * glyph_classes [n_polygons][glyphs_per_polygon] (class index -> character: ocrb_class_to_char). */
+int ocrb_detect_and_read(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, const double *adjust, int B, int H, int W,
+                         const ocrb_postproc_params *params, int glyphs_per_polygon, ocrb_polygons **out);
+int ocrb_polygons_glyphs_per_polygon(const ocrb_polygons *p);
+const int32_t *ocrb_polygons_glyph_classes(const ocrb_polygons *p);
+/* test hook of the crop stage: image u8 [H][W], boxes [n][4] (x,y) corners TL,TR,BR,BL as ocrb_min_area_bounding_box
+ * returns them -> out_glyphs u8 [n * glyphs_per_box][784] */
+int ocrb_crop_glyphs(ocrb_ctx *ctx, const uint8_t *image, int H, int W, const int32_t *boxes_xy, int n_boxes, int glyphs_per_box,
+                     uint8_t *out_glyphs);
+
 /* ---- several GPUs of one box, one process -----------------------------------------------------
  * The batch contract of the reference's evaluation loop (text_detection/mod.rs:188-204: images [n][H][W] +
  * adjust [n][2] -> one PolygonScores) across devices: contiguous index shards (the first n % G shards hold one
@@ -232,6 +248,9 @@ int ocrb_shard_range(int64_t n_items, int shard, int n_shards, int64_t *first, i
 int ocrb_detect_and_recognize_sharded(ocrb_shards *s, const uint8_t *images, const double *adjust, int B, int H, int W,
                                       const ocrb_postproc_params *params, const uint8_t *glyphs, int n_glyphs,
                                       int32_t *glyph_argmax, ocrb_polygons **out);
+/* ocrb_detect_and_read over all devices of `s` */
+int ocrb_detect_and_read_sharded(ocrb_shards *s, const uint8_t *images, const double *adjust, int B, int H, int W,
+                                 const ocrb_postproc_params *params, int glyphs_per_polygon, ocrb_polygons **out);
 int ocrb_host_alloc(size_t bytes, void **out);
 int ocrb_host_free(void *p);
 

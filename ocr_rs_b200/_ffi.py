@@ -86,6 +86,11 @@ SIGNATURES = {
     "ocrb_rec_create_from_file": (C.c_int, [c_p, C.c_char_p, C.POINTER(c_p)]),
     "ocrb_detect_and_recognize": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.POINTER(PostprocParams),
                                             c_p, C.c_int, c_p, C.POINTER(c_p)]),
+    "ocrb_detect_and_read": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.POINTER(PostprocParams), C.c_int, C.POINTER(c_p)]),
+    "ocrb_polygons_glyphs_per_polygon": (C.c_int, [c_p]),
+    "ocrb_polygons_glyph_classes": (C.POINTER(C.c_int32), [c_p]),
+    "ocrb_crop_glyphs": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, C.c_int, C.c_int, c_p]),
+    "ocrb_detect_and_read_sharded": (C.c_int, [c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.POINTER(PostprocParams), C.c_int, C.POINTER(c_p)]),
     "ocrb_shards_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_p), C.POINTER(i64), C.c_int,
                                      C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_p), C.POINTER(i64), C.POINTER(c_p)]),
     "ocrb_shards_create_from_files": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(c_p)]),
@@ -241,9 +246,15 @@ class Polygons:
                   if npts > 0 else np.zeros((0, 2), np.uint32))
             sc = np.ctypeslib.as_array(L.ocrb_polygons_scores(handle), shape=(npoly,)).copy() if npoly > 0 else np.zeros(0, np.float64)
             self.stats = np.ctypeslib.as_array(L.ocrb_polygons_stats(handle), shape=(nb * 5,)).copy().reshape(nb, 5)
+            k = L.ocrb_polygons_glyphs_per_polygon(handle)
+            if k > 0:  # ocrb_detect_and_read: classes of the glyph tiles cut from every polygon
+                self.glyph_classes = (np.ctypeslib.as_array(L.ocrb_polygons_glyph_classes(handle), shape=(npoly * k,)).copy().reshape(npoly, k)
+                                      if npoly > 0 else np.zeros((0, k), np.int32))
             L.ocrb_polygons_free(handle)
             self.image_offsets, self.point_offsets, self.xy, self.all_scores = io, po, xy, sc
         self._polygons = self._scores = None
+        if not hasattr(self, "glyph_classes"):
+            self.glyph_classes = None
 
     @property
     def num_images(self):
@@ -270,12 +281,16 @@ class Polygons:
     def concat(parts):
         """Concatenates per-shard results in the given (= image index) order."""
         io, po, xy, sc, st = [np.zeros(1, np.int64)], [np.zeros(1, np.int64)], [], [], []
+        gc = [a.glyph_classes if isinstance(a, Polygons) else (a[5] if len(a) > 5 else None) for a in parts]
         for a in parts:
-            pio, ppo, pxy, psc, pst = a.arrays() if isinstance(a, Polygons) else a
+            pio, ppo, pxy, psc, pst = a.arrays() if isinstance(a, Polygons) else a[:5]
             io.append(pio[1:] + io[-1][-1])
             po.append(ppo[1:] + po[-1][-1])
             xy.append(pxy)
             sc.append(psc)
             st.append(pst)
-        return Polygons(arrays=(np.concatenate(io), np.concatenate(po), np.concatenate(xy) if xy else np.zeros((0, 2), np.uint32),
-                                np.concatenate(sc) if sc else np.zeros(0), np.concatenate(st) if st else np.zeros((0, 5), np.int64)))
+        out = Polygons(arrays=(np.concatenate(io), np.concatenate(po), np.concatenate(xy) if xy else np.zeros((0, 2), np.uint32),
+                               np.concatenate(sc) if sc else np.zeros(0), np.concatenate(st) if st else np.zeros((0, 5), np.int64)))
+        if gc and all(g is not None for g in gc):
+            out.glyph_classes = np.concatenate(gc)
+        return out

@@ -790,7 +790,8 @@ __global__ void emit_polygons_kernel(const int *__restrict__ cand_contour, const
                                      const int2 *__restrict__ slabs, const int *__restrict__ out_count,
                                      const double *__restrict__ scores, const double *__restrict__ adjust,
                                      uint32_t *__restrict__ xy, double *__restrict__ out_scores,
-                                     int64_t *__restrict__ out_pt_off, int *__restrict__ out_image) {
+                                     int64_t *__restrict__ out_pt_off, int *__restrict__ out_image,
+                                     const int2 *__restrict__ cand_box, int2 *__restrict__ out_box) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cand || status[i] != 1) return;
   const int c = cand_contour ? cand_contour[i] : i;
@@ -808,18 +809,20 @@ __global__ void emit_polygons_kernel(const int *__restrict__ cand_contour, const
   out_scores[r] = scores[i];
   out_pt_off[r] = po;
   out_image[r] = (int)b;
+  if (out_box)
+    for (int k = 0; k < 4; ++k) out_box[r * 4 + k] = cand_box[i * 4 + k];
 }
 
 int launch_emit_polygons(ocrb_ctx *ctx, const int *cand_contour, const int *dp_count, const int64_t *start_idx,
                          int64_t image_stride, int n_cand, const uint8_t *status, const int *kept_rank,
                          const int64_t *pt_off, const int64_t *slab_off, const int2 *slabs, const int *out_count,
                          const double *scores, const double *adjust, uint32_t *xy, double *out_scores,
-                         int64_t *out_pt_off, int *out_image) {
+                         int64_t *out_pt_off, int *out_image, const int2 *cand_box, int2 *out_box) {
   if (n_cand <= 0) return OCRB_OK;
   emit_polygons_kernel<<<(unsigned)cdiv(n_cand, 128), 128, 0, ctx->stream>>>(cand_contour, dp_count, start_idx, image_stride,
                                                                             n_cand, status, kept_rank, pt_off, slab_off, slabs,
                                                                             out_count, scores, adjust, xy, out_scores,
-                                                                            out_pt_off, out_image);
+                                                                            out_pt_off, out_image, cand_box, out_box);
   return check_launch(ctx, "emit_polygons");
 }
 

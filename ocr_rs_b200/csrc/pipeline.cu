@@ -22,11 +22,15 @@ int postproc_device(ocrb_ctx *, const float *, const uint8_t *, const double *, 
 void polygons_append(ocrb_polygons *, const ocrb_polygons *);
 ocrb_polygons *polygons_new();
 int launch_binarize(ocrb_ctx *, const float *, int64_t, float, uint8_t *);
+void postproc_kept_boxes(ocrb_ctx *, const int2 **, const int **);
+int launch_crop_glyphs(ocrb_ctx *, const uint8_t *, int, int, const int2 *, const int *, int, int, uint8_t *);
 
 struct PipelineWorkspace {
-  DevBuf images[2], prob[2], bitmap[2], adjust, glyphs, argmax;
+  DevBuf images[2], prob[2], bitmap[2], adjust, glyphs, argmax;  // images: one staging buffer per GROUP (kept until its crops are cut)
+  DevBuf crops[2], crop_cls[2];                                   // glyph tiles / classes of a group's kept polygons
+  std::vector<PinBuf> cls_host;                                   // per group: classes on the host, read after the final sync
   cudaStream_t fwd = nullptr, copy = nullptr;
-  cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, fwd_done[2] = {nullptr, nullptr}, pp_ready = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr}, img_free[2] = {nullptr, nullptr}, fwd_done[2] = {nullptr, nullptr}, pp_ready = nullptr;
   bool ready = false;
 };
 // the workspace belongs to the ctx (one ctx per host thread: no state is shared between contexts)
@@ -38,7 +42,7 @@ static int get_ws(ocrb_ctx *ctx, PipelineWorkspace **out) {
     OCRB_CUDA(cudaStreamCreateWithFlags(&w->copy, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
       OCRB_CUDA(cudaEventCreateWithFlags(&w->copied[i], cudaEventDisableTiming));
-      OCRB_CUDA(cudaEventCreateWithFlags(&w->consumed[i], cudaEventDisableTiming));
+      OCRB_CUDA(cudaEventCreateWithFlags(&w->img_free[i], cudaEventDisableTiming));
       OCRB_CUDA(cudaEventCreateWithFlags(&w->fwd_done[i], cudaEventDisableTiming));
     }
     OCRB_CUDA(cudaEventCreateWithFlags(&w->pp_ready, cudaEventDisableTiming));
@@ -51,11 +55,13 @@ static int get_ws(ocrb_ctx *ctx, PipelineWorkspace **out) {
 void free_pipe(ocrb_ctx *ctx) {
   PipelineWorkspace *w = ctx->pipe;
   if (!w) return;
-  DevBuf *bufs[] = {&w->images[0], &w->images[1], &w->prob[0], &w->prob[1], &w->bitmap[0], &w->bitmap[1], &w->adjust, &w->glyphs, &w->argmax};
+  DevBuf *bufs[] = {&w->images[0], &w->images[1], &w->prob[0], &w->prob[1], &w->bitmap[0], &w->bitmap[1], &w->adjust, &w->glyphs, &w->argmax,
+                    &w->crops[0], &w->crops[1], &w->crop_cls[0], &w->crop_cls[1]};
   for (DevBuf *b : bufs) b->release();
+  for (PinBuf &b : w->cls_host) b.release();
   for (int i = 0; i < 2; ++i) {
     if (w->copied[i]) cudaEventDestroy(w->copied[i]);
-    if (w->consumed[i]) cudaEventDestroy(w->consumed[i]);
+    if (w->img_free[i]) cudaEventDestroy(w->img_free[i]);
     if (w->fwd_done[i]) cudaEventDestroy(w->fwd_done[i]);
   }
   if (w->pp_ready) cudaEventDestroy(w->pp_ready);
@@ -65,18 +71,24 @@ void free_pipe(ocrb_ctx *ctx) {
   ctx->pipe = nullptr;
 }
 
+void polygons_set_glyph_classes(ocrb_polygons *, int, const std::vector<PinBuf> &, const std::vector<int64_t> &);
+
 constexpr int PIPE_CHUNK_BF16 = 256, PIPE_CHUNK_FP32 = 4, PIPE_GROUP = 256;  // 256 / 256 measured +3 % over 128 / 128 (fewer, longer launches)
 
 }  // namespace ocrb
 
 using namespace ocrb;
 
-extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, const double *adjust, int B, int H,
-                                         int W, const ocrb_postproc_params *params, const uint8_t *glyphs, int n_glyphs,
-                                         int32_t *glyph_argmax, ocrb_polygons **out) {
+// crop_k > 0: the polygon -> glyph crop glue (crop.cu) feeds the recognition net from the detector's own polygons;
+// crop_k == 0: the caller's glyph set is classified (ocrb_detect_and_recognize).
+static int run_pipeline(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, const double *adjust, int B, int H, int W,
+                        const ocrb_postproc_params *params, const uint8_t *glyphs, int n_glyphs, int32_t *glyph_argmax, int crop_k,
+                        ocrb_polygons **out) {
   OCRB_REQUIRE(det && images && adjust && out, "null argument");
   OCRB_REQUIRE(B > 0 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "H and W must be positive multiples of 32 (got %dx%d, B=%d)", H, W, B);
   OCRB_REQUIRE(n_glyphs == 0 || (rec && glyphs), "glyphs given without a recognition net");
+  OCRB_REQUIRE(crop_k == 0 || rec, "glyph crops asked for without a recognition net");
+  OCRB_REQUIRE(crop_k >= 0 && crop_k <= 64, "glyphs_per_polygon must be in 0..64 (got %d)", crop_k);
   ocrb_ctx *ctx = det_ctx(det);
   OCRB_CUDA(cudaSetDevice(ctx->device));
   ocrb_postproc_params prm;
@@ -104,9 +116,9 @@ extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uin
   for (int i = 0; i < (n_groups > 1 ? 2 : 1); ++i) {
     OCRB_TRY(ws->prob[i].reserve((size_t)group * HW * 4));
     OCRB_TRY(ws->bitmap[i].reserve((size_t)group * HW));
+    if (!img_dev) OCRB_TRY(ws->images[i].reserve((size_t)group * HW));
   }
-  if (!img_dev)
-    for (int i = 0; i < 2; ++i) OCRB_TRY(ws->images[i].reserve((size_t)chunk * HW));
+  if (crop_k > 0 && (int)ws->cls_host.size() < n_groups) ws->cls_host.resize(n_groups);
   OCRB_TRY(ws->adjust.reserve((size_t)B * 16));
   OCRB_CUDA(cudaMemcpyAsync(ws->adjust.p, adjust, (size_t)B * 16, cudaMemcpyDefault, s_pp));
   // everything queued so far on ctx->stream (earlier calls) precedes this call's forward work
@@ -114,7 +126,7 @@ extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uin
   OCRB_CUDA(cudaStreamWaitEvent(s_fwd, ws->pp_ready, 0));
   OCRB_CUDA(cudaStreamWaitEvent(s_copy, ws->pp_ready, 0));
 
-  // glyph recognition: independent of the detector, queued first on the post-processing stream
+  // caller-provided glyphs: independent of the detector, queued first on the post-processing stream
   if (n_glyphs > 0) {
     const void *g = glyphs;
     if (!is_device_ptr(glyphs)) {
@@ -132,7 +144,7 @@ extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uin
       OCRB_CUDA(cudaMemcpyAsync(glyph_argmax, am, (size_t)n_glyphs * 4, cudaMemcpyDeviceToHost, s_pp));
   }
 
-  int64_t chunk_no = 0;  // global chunk counter (selects the image staging buffer)
+  bool first_copy = true;
   // queues copies + forwards of group g; the detector launches on ctx->stream, so it is
   // pointed at the forward stream for the duration
   auto enqueue_forward = [&](int g) -> int {
@@ -140,33 +152,35 @@ extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uin
     float *prob = ws->prob[g & 1].as<float>();
     uint8_t *bitmap = ws->bitmap[g & 1].as<uint8_t>();
     int rc = OCRB_OK;
-    for (int c0 = 0, bc = 0; c0 < gn && rc == OCRB_OK; c0 += bc, ++chunk_no) {
+    // the group's staging buffer is free once group g - 2 has been forwarded and (with the crop glue) cropped
+    if (!img_dev && g >= 2) OCRB_CUDA(cudaStreamWaitEvent(s_copy, ws->img_free[g & 1], 0));
+    for (int c0 = 0, bc = 0; c0 < gn && rc == OCRB_OK; c0 += bc) {
       bc = gn - c0 < chunk ? gn - c0 : chunk;
       // host images: the very first copy of a call is exposed (nothing to overlap it with), so
-      // ramp up — 16 images first, the rest of the chunk while those are in the detector
-      if (!img_dev && chunk_no == 0 && bc > 32) bc = 16;
-      else if (!img_dev && chunk_no == 1 && c0 == 16 && chunk > 16 && gn - c0 > chunk - 16) bc = chunk - 16;
+      // ramp up — 16 images first, the rest while those are in the detector
+      if (!img_dev && first_copy && bc > 32) bc = 16;
+      first_copy = false;
       const uint8_t *src = images + (size_t)(g0 + c0) * HW;
-      const int slot = (int)(chunk_no & 1);
       if (!img_dev) {
-        if (chunk_no >= 2) OCRB_CUDA(cudaStreamWaitEvent(s_copy, ws->consumed[slot], 0));
-        OCRB_CUDA(cudaMemcpyAsync(ws->images[slot].p, src, (size_t)bc * HW, cudaMemcpyHostToDevice, s_copy));
-        OCRB_CUDA(cudaEventRecord(ws->copied[slot], s_copy));
-        OCRB_CUDA(cudaStreamWaitEvent(s_fwd, ws->copied[slot], 0));
-        src = ws->images[slot].as<uint8_t>();
+        uint8_t *dst = ws->images[g & 1].as<uint8_t>() + (size_t)c0 * HW;
+        OCRB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bc * HW, cudaMemcpyHostToDevice, s_copy));
+        OCRB_CUDA(cudaEventRecord(ws->copied[g & 1], s_copy));
+        OCRB_CUDA(cudaStreamWaitEvent(s_fwd, ws->copied[g & 1], 0));
+        src = dst;
       }
       cudaStream_t saved = ctx->stream;
       ctx->stream = s_fwd;
       rc = det_forward_device(det, src, OCRB_U8, bc, H, W, prob + (size_t)c0 * HW, bf16 ? bitmap + (size_t)c0 * HW : nullptr, (float)prm.thresh);
       if (rc == OCRB_OK && !bf16) rc = launch_binarize(ctx, prob + (size_t)c0 * HW, (int64_t)bc * HW, (float)prm.thresh, bitmap + (size_t)c0 * HW);
       ctx->stream = saved;
-      if (rc == OCRB_OK && !img_dev) OCRB_CUDA(cudaEventRecord(ws->consumed[slot], s_fwd));
     }
     if (rc == OCRB_OK) OCRB_CUDA(cudaEventRecord(ws->fwd_done[g & 1], s_fwd));
+    if (rc == OCRB_OK && !img_dev && crop_k == 0) OCRB_CUDA(cudaEventRecord(ws->img_free[g & 1], s_fwd));
     return rc;
   };
 
   ocrb_polygons *res = polygons_new();
+  std::vector<int64_t> group_kept(n_groups, 0);
   int rc = enqueue_forward(0);
   for (int g = 0; g < n_groups && rc == OCRB_OK; ++g) {
     if (g + 1 < n_groups) rc = enqueue_forward(g + 1);
@@ -176,8 +190,32 @@ extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uin
     if (e != cudaSuccess) { set_error("cudaStreamWaitEvent -> %s", cudaGetErrorString(e)); rc = OCRB_ERR_CUDA; break; }
     ocrb_polygons *part = polygons_new();
     rc = postproc_device(ctx, ws->prob[g & 1].as<float>(), ws->bitmap[g & 1].as<uint8_t>(), ws->adjust.as<double>() + (size_t)g0 * 2, gn, H, W, prm, part);
+    const int64_t n_kept = rc == OCRB_OK ? ocrb_polygons_image_offsets(part)[gn] : 0;
     if (rc == OCRB_OK) polygons_append(res, part);
     ocrb_polygons_free(part);
+    if (rc == OCRB_OK && crop_k > 0) {
+      // crop glue: kept boxes (device, result order) -> 28x28 tiles from the group's source images -> classes;
+      // queued behind the post-processing, read on the host after the final synchronisation
+      group_kept[g] = n_kept;
+      if (n_kept > 0) {
+        const int2 *boxes;
+        const int *box_image;
+        postproc_kept_boxes(ctx, &boxes, &box_image);
+        const int64_t n_tiles = n_kept * crop_k;
+        if ((rc = ws->crops[g & 1].reserve((size_t)n_tiles * 784)) != OCRB_OK) break;
+        if ((rc = ws->crop_cls[g & 1].reserve((size_t)n_tiles * 4)) != OCRB_OK) break;
+        if ((rc = ws->cls_host[g].reserve((size_t)n_tiles * 4)) != OCRB_OK) break;
+        const uint8_t *src = img_dev ? images + (size_t)g0 * HW : ws->images[g & 1].as<uint8_t>();
+        if ((rc = launch_crop_glyphs(ctx, src, H, W, boxes, box_image, (int)n_kept, crop_k, ws->crops[g & 1].as<uint8_t>())) != OCRB_OK) break;
+        if ((rc = rec_forward_device(rec, ws->crops[g & 1].p, 1, (int)n_tiles, nullptr, ws->crop_cls[g & 1].as<int32_t>(), nullptr)) != OCRB_OK) break;
+        e = cudaMemcpyAsync(ws->cls_host[g].p, ws->crop_cls[g & 1].p, (size_t)n_tiles * 4, cudaMemcpyDeviceToHost, s_pp);
+        if (e != cudaSuccess) { set_error("cudaMemcpyAsync -> %s", cudaGetErrorString(e)); rc = OCRB_ERR_CUDA; break; }
+      }
+      if (!img_dev) {
+        e = cudaEventRecord(ws->img_free[g & 1], s_pp);
+        if (e != cudaSuccess) { set_error("cudaEventRecord -> %s", cudaGetErrorString(e)); rc = OCRB_ERR_CUDA; break; }
+      }
+    }
   }
   if (rc == OCRB_OK) rc = sync(ctx);
   cudaStreamSynchronize(ws->fwd);
@@ -188,6 +226,19 @@ extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uin
     ocrb_polygons_free(res);
     return rc;
   }
+  if (crop_k > 0) polygons_set_glyph_classes(res, crop_k, ws->cls_host, group_kept);
   *out = res;
   return OCRB_OK;
+}
+
+extern "C" int ocrb_detect_and_recognize(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, const double *adjust, int B, int H,
+                                         int W, const ocrb_postproc_params *params, const uint8_t *glyphs, int n_glyphs,
+                                         int32_t *glyph_argmax, ocrb_polygons **out) {
+  return run_pipeline(det, rec, images, adjust, B, H, W, params, glyphs, n_glyphs, glyph_argmax, 0, out);
+}
+
+extern "C" int ocrb_detect_and_read(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, const double *adjust, int B, int H, int W,
+                                    const ocrb_postproc_params *params, int glyphs_per_polygon, ocrb_polygons **out) {
+  OCRB_REQUIRE(glyphs_per_polygon > 0, "glyphs_per_polygon must be positive");
+  return run_pipeline(det, rec, images, adjust, B, H, W, params, nullptr, 0, nullptr, glyphs_per_polygon, out);
 }

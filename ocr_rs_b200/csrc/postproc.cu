@@ -28,7 +28,7 @@ int launch_unclip(ocrb_ctx *, const int *, const int64_t *, const ushort2 *, con
                   double, double, const int64_t *, int2 *, int *, uint8_t *, double *, int2 *);
 int launch_emit_polygons(ocrb_ctx *, const int *, const int *, const int64_t *, int64_t, int, const uint8_t *, const int *,
                          const int64_t *, const int64_t *, const int2 *, const int *, const double *, const double *,
-                         uint32_t *, double *, int64_t *, int *);
+                         uint32_t *, double *, int64_t *, int *, const int2 *, int2 *);
 int launch_flag_ge4(ocrb_ctx *, const int *, int64_t, uint8_t *);
 int launch_compact_index(ocrb_ctx *, const uint8_t *, const int *, int64_t, int *);
 int launch_kept_sizes(ocrb_ctx *, const uint8_t *, const int *, int, uint8_t *, int *);
@@ -42,11 +42,12 @@ struct PostprocWorkspace {
   DevBuf chain, dp_out, stack;
   DevBuf cand_contour, scores, slab_units, slab_off, out_count, status, kept_flag, kept_pts, kept_rank, pt_off, slabs;
   DevBuf out_xy, out_scores, out_pt_off, out_image, stats, err, adjust;
+  DevBuf cand_box, out_box;  // min-area boxes of all candidates / of the kept polygons (TL, TR, BR, BL; map coordinates)
   void release() {
     DevBuf *all[] = {&bitmap, &labels, &bg_open, &hole_traced, &flags, &bbox, &offs, &scan_scratch, &start_idx, &kind,
                      &lengths, &chain_off, &dp_count, &cand_flag, &cand_rank, &chain, &dp_out, &stack, &cand_contour,
                      &scores, &slab_units, &slab_off, &out_count, &status, &kept_flag, &kept_pts, &kept_rank, &pt_off,
-                     &slabs, &out_xy, &out_scores, &out_pt_off, &out_image, &stats, &err, &adjust};
+                     &slabs, &out_xy, &out_scores, &out_pt_off, &out_image, &stats, &err, &adjust, &cand_box, &out_box};
     for (DevBuf *b : all) b->release();
   }
 };
@@ -78,6 +79,8 @@ struct ocrb_polygons {
   std::vector<uint32_t> xy;            // 2 * n_points
   std::vector<double> scores;          // n_polys
   std::vector<int64_t> stats;          // 5 * n_images
+  int glyphs_per_polygon = 0;          // > 0: filled by ocrb_detect_and_read
+  std::vector<int32_t> glyph_classes;  // n_polys * glyphs_per_polygon
   // contour-stage outputs kept for the test hooks
   std::vector<int64_t> chain_offsets;
   std::vector<uint8_t> chain_types;
@@ -189,10 +192,11 @@ static int run_postproc(ocrb_ctx *ctx, const float *pred, const uint8_t *bitmap,
     int64_t total_units = 0;
     OCRB_TRY(read_scalar(ctx, ws->slab_off.as<int64_t>() + n_cand, &total_units));
     OCRB_TRY(ws->slabs.reserve((size_t)total_units * 8));
+    OCRB_TRY(ws->cand_box.reserve((size_t)n_cand * 4 * sizeof(int2)));
     OCRB_TRY(launch_unclip(ctx, ws->cand_contour.as<int>(), ws->chain_off.as<int64_t>(), ws->dp_out.as<ushort2>(),
                            ws->dp_count.as<int>(), n_cand, ws->scores.as<double>(), prm.box_thresh, prm.min_size,
                            prm.unclip_factor, ws->slab_off.as<int64_t>(), ws->slabs.as<int2>(), ws->out_count.as<int>(),
-                           ws->status.as<uint8_t>(), nullptr, nullptr));
+                           ws->status.as<uint8_t>(), nullptr, ws->cand_box.as<int2>()));
     OCRB_TRY(launch_kept_sizes(ctx, ws->status.as<uint8_t>(), ws->out_count.as<int>(), n_cand, ws->kept_flag.as<uint8_t>(),
                                ws->kept_pts.as<int>()));
     OCRB_TRY((exclusive_scan<uint8_t, int>(ctx, ws->kept_flag.as<uint8_t>(), n_cand, ws->kept_rank.as<int>(), ws->scan_scratch.as<int>())));
@@ -208,11 +212,12 @@ static int run_postproc(ocrb_ctx *ctx, const float *pred, const uint8_t *bitmap,
     OCRB_TRY(ws->out_scores.reserve((size_t)n_kept * 8));
     OCRB_TRY(ws->out_pt_off.reserve((size_t)n_kept * 8));
     OCRB_TRY(ws->out_image.reserve((size_t)n_kept * 4));
+    OCRB_TRY(ws->out_box.reserve((size_t)n_kept * 4 * sizeof(int2)));
     OCRB_TRY(launch_emit_polygons(ctx, ws->cand_contour.as<int>(), ws->dp_count.as<int>(), ws->start_idx.as<int64_t>(), HW,
                                   n_cand, ws->status.as<uint8_t>(), ws->kept_rank.as<int>(), ws->pt_off.as<int64_t>(),
                                   ws->slab_off.as<int64_t>(), ws->slabs.as<int2>(), ws->out_count.as<int>(),
                                   ws->scores.as<double>(), adjust_dev, ws->out_xy.as<uint32_t>(), ws->out_scores.as<double>(),
-                                  ws->out_pt_off.as<int64_t>(), ws->out_image.as<int>()));
+                                  ws->out_pt_off.as<int64_t>(), ws->out_image.as<int>(), ws->cand_box.as<int2>(), ws->out_box.as<int2>()));
     res->xy.resize((size_t)n_kept_pts * 2);
     res->scores.resize(n_kept);
     res->point_offsets.resize(n_kept + 1);
@@ -238,6 +243,14 @@ static int run_postproc(ocrb_ctx *ctx, const float *pred, const uint8_t *bitmap,
   return OCRB_OK;
 }
 
+// pipeline.cu: the kept polygons' min-area boxes and image indices of the LAST post-processing call on this ctx
+// (device arrays, in result order; valid until the next call)
+void postproc_kept_boxes(ocrb_ctx *ctx, const int2 **boxes, const int **image) {
+  PostprocWorkspace *ws = get_pp(ctx);
+  *boxes = ws->out_box.as<int2>();
+  *image = ws->out_image.as<int>();
+}
+
 // pipeline.cu entry: pred / bitmap / adjust already on the device; appends nothing, fills `res`
 int postproc_device(ocrb_ctx *ctx, const float *pred_dev, const uint8_t *bitmap_dev, const double *adjust_dev, int B, int H,
                     int W, const ocrb_postproc_params &prm, ocrb_polygons *res) {
@@ -256,9 +269,21 @@ void polygons_append(ocrb_polygons *dst, const ocrb_polygons *src) {
   dst->xy.insert(dst->xy.end(), src->xy.begin(), src->xy.end());
   dst->scores.insert(dst->scores.end(), src->scores.begin(), src->scores.end());
   dst->stats.insert(dst->stats.end(), src->stats.begin(), src->stats.end());
+  dst->glyph_classes.insert(dst->glyph_classes.end(), src->glyph_classes.begin(), src->glyph_classes.end());
+  if (src->glyphs_per_polygon) dst->glyphs_per_polygon = src->glyphs_per_polygon;
   dst->n_images += src->n_images;
 }
 ocrb_polygons *polygons_new() { return new ocrb_polygons(); }
+
+// pipeline.cu: classes of the glyph tiles, group by group (host copies), in result order
+void polygons_set_glyph_classes(ocrb_polygons *p, int k, const std::vector<PinBuf> &cls, const std::vector<int64_t> &kept) {
+  p->glyphs_per_polygon = k;
+  p->glyph_classes.clear();
+  for (size_t g = 0; g < kept.size(); ++g) {
+    const int32_t *src = cls[g].as<int32_t>();
+    p->glyph_classes.insert(p->glyph_classes.end(), src, src + kept[g] * k);
+  }
+}
 
 }  // namespace ocrb
 
@@ -333,6 +358,8 @@ const int64_t *ocrb_polygons_point_offsets(const ocrb_polygons *p) { return p->p
 const uint32_t *ocrb_polygons_xy(const ocrb_polygons *p) { return p->xy.data(); }
 const double *ocrb_polygons_scores(const ocrb_polygons *p) { return p->scores.data(); }
 const int64_t *ocrb_polygons_stats(const ocrb_polygons *p) { return p->stats.data(); }
+int ocrb_polygons_glyphs_per_polygon(const ocrb_polygons *p) { return p ? p->glyphs_per_polygon : 0; }
+const int32_t *ocrb_polygons_glyph_classes(const ocrb_polygons *p) { return p->glyph_classes.data(); }
 void ocrb_polygons_free(ocrb_polygons *p) { delete p; }
 
 // ---- fine-grained hooks ------------------------------------------------------------------

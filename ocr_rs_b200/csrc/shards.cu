@@ -121,10 +121,11 @@ int ocrb_shard_range(int64_t n_items, int shard, int n_shards, int64_t *first, i
   return OCRB_OK;
 }
 
-int ocrb_detect_and_recognize_sharded(ocrb_shards *s, const uint8_t *images, const double *adjust, int B, int H, int W,
-                                      const ocrb_postproc_params *params, const uint8_t *glyphs, int n_glyphs,
-                                      int32_t *glyph_argmax, ocrb_polygons **out) {
+static int run_sharded(ocrb_shards *s, const uint8_t *images, const double *adjust, int B, int H, int W,
+                       const ocrb_postproc_params *params, const uint8_t *glyphs, int n_glyphs, int32_t *glyph_argmax, int crop_k,
+                       ocrb_polygons **out) {
   OCRB_REQUIRE(s && images && adjust && out, "null argument");
+  OCRB_REQUIRE(crop_k == 0 || !s->rec.empty(), "glyph crops asked for without a recognition net");
   OCRB_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape B=%d H=%d W=%d", B, H, W);
   OCRB_REQUIRE(n_glyphs == 0 || (glyphs && !s->rec.empty()), "glyphs given without a recognition net");
   OCRB_REQUIRE(!is_device_ptr(images) && !is_device_ptr(glyphs) && !is_device_ptr(glyph_argmax),
@@ -145,7 +146,9 @@ int ocrb_detect_and_recognize_sharded(ocrb_shards *s, const uint8_t *images, con
     if (count == 0 && gcount == 0) continue;
     threads.emplace_back([=, &parts]() {
       Part &p = parts[r];
-      if (count > 0) {
+      if (count > 0 && crop_k > 0) {
+        p.rc = ocrb_detect_and_read(s->det[r], s->rec[r], images + first * HW, adjust + first * 2, (int)count, H, W, params, crop_k, &p.res);
+      } else if (count > 0) {
         p.rc = ocrb_detect_and_recognize(s->det[r], gcount > 0 ? s->rec[r] : nullptr, images + first * HW, adjust + first * 2, (int)count, H, W,
                                          params, gcount > 0 ? glyphs + gfirst * 784 : nullptr, (int)gcount,
                                          glyph_argmax && gcount > 0 ? glyph_argmax + gfirst : nullptr, &p.res);
@@ -173,6 +176,18 @@ int ocrb_detect_and_recognize_sharded(ocrb_shards *s, const uint8_t *images, con
   if (rc != OCRB_OK) return rc;
   *out = res;
   return OCRB_OK;
+}
+
+int ocrb_detect_and_recognize_sharded(ocrb_shards *s, const uint8_t *images, const double *adjust, int B, int H, int W,
+                                      const ocrb_postproc_params *params, const uint8_t *glyphs, int n_glyphs,
+                                      int32_t *glyph_argmax, ocrb_polygons **out) {
+  return run_sharded(s, images, adjust, B, H, W, params, glyphs, n_glyphs, glyph_argmax, 0, out);
+}
+
+int ocrb_detect_and_read_sharded(ocrb_shards *s, const uint8_t *images, const double *adjust, int B, int H, int W,
+                                 const ocrb_postproc_params *params, int glyphs_per_polygon, ocrb_polygons **out) {
+  OCRB_REQUIRE(glyphs_per_polygon > 0, "glyphs_per_polygon must be positive");
+  return run_sharded(s, images, adjust, B, H, W, params, nullptr, 0, nullptr, glyphs_per_polygon, out);
 }
 
 // page-locked host memory for the image / glyph buffers (full-speed, asynchronous H2D copies)

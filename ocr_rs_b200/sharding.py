@@ -89,6 +89,19 @@ class Shards:
                                                                 _ffi.ptr(glyphs), n_gl, _ffi.ptr(am), C.byref(h)))
         return _ffi.Polygons(h), am
 
+    def detect_and_read(self, images, adjust, glyphs_per_polygon=4, params=None):
+        """ocrb_detect_and_read_sharded: polygons + glyph_classes [n_polygons, glyphs_per_polygon] of the whole batch"""
+        import ctypes as C
+
+        import numpy as np
+        _ffi = self._ffi
+        B, H, W = images.shape
+        adjust = np.ascontiguousarray(adjust, np.float64)
+        h = _ffi.c_p()
+        _ffi.check(_ffi.lib().ocrb_detect_and_read_sharded(self._h, _ffi.ptr(images), _ffi.ptr(adjust), B, H, W, params,
+                                                           int(glyphs_per_polygon), C.byref(h)))
+        return _ffi.Polygons(h)
+
     def close(self):
         if self._h:
             self._ffi.lib().ocrb_shards_destroy(self._h)
@@ -132,10 +145,11 @@ class ShmGather:
         import time
         np = self.np
         io, po, xy, sc, st = result.arrays()
+        gc = result.glyph_classes if result.glyph_classes is not None else np.zeros((0, 0), np.int32)
         while step >= 2 and self.mine[0] < step - 2:  # the reader still owns this slot
             time.sleep(20e-6)
         hdr, body = self._slot(self.mine, step)
-        need = len(io) + len(po) + (xy.size + 1) // 2 + len(sc) + st.size
+        need = len(io) + len(po) + (xy.size + 1) // 2 + len(sc) + st.size + (gc.size + 1) // 2
         if need > len(body):
             raise RuntimeError(f"ShmGather: shard needs {need * 8} bytes, capacity {self.cap}")
         o = 0
@@ -147,7 +161,9 @@ class ShmGather:
         body[o:o + len(sc)].view(np.float64)[:] = sc
         o += len(sc)
         body[o:o + st.size] = st.reshape(-1)
-        hdr[1], hdr[2], hdr[3] = len(io) - 1, len(sc), len(xy)
+        o += st.size
+        body[o:o + (gc.size + 1) // 2].view(np.int32)[:gc.size] = gc.reshape(-1)
+        hdr[1], hdr[2], hdr[3], hdr[4] = len(io) - 1, len(sc), len(xy), (gc.shape[1] if gc.size else 0)
         hdr[0] = step + 1  # published last: the slot is complete when the reader sees it
 
     def collect(self, step, timeout_s=60.0):
@@ -174,14 +190,15 @@ class ShmGather:
                 if time.time() - t0 > timeout_s:
                     raise TimeoutError(f"ShmGather: rank {r} did not publish step {step}")
                 time.sleep(20e-6)
-            ni, npoly, npts = int(hdr[1]), int(hdr[2]), int(hdr[3])
+            ni, npoly, npts, k = int(hdr[1]), int(hdr[2]), int(hdr[3]), int(hdr[4])
             o = 0
             io = np.array(body[o:o + ni + 1]); o += ni + 1
             po = np.array(body[o:o + npoly + 1]); o += npoly + 1
             xy = np.array(body[o:o + (2 * npts + 1) // 2].view(np.uint32)[:2 * npts]).reshape(-1, 2); o += (2 * npts + 1) // 2
             sc = np.array(body[o:o + npoly].view(np.float64)); o += npoly
-            st = np.array(body[o:o + 5 * ni]).reshape(ni, 5)
-            parts.append((io, po, xy, sc, st))
+            st = np.array(body[o:o + 5 * ni]).reshape(ni, 5); o += 5 * ni
+            gc = np.array(body[o:o + (npoly * k + 1) // 2].view(np.int32)[:npoly * k]).reshape(npoly, k) if k else None
+            parts.append((io, po, xy, sc, st, gc))
             seg[0] = step  # ack
         return Polygons.concat(parts)
 

@@ -185,7 +185,7 @@ def min_area_bounding_box(points):
 
 
 def polygons_from_bitmap(pred, bitmap, adjust=(1.0, 1.0), box_thresh=0.7, min_size=5.0,
-                         unclip=2.0, return_stats=False):
+                         unclip=2.0, return_stats=False, return_boxes=False):
     """metrics.rs:58-127 for one image -> (list of [m,2] uint32 arrays, scores f64[n])."""
     pred = np.ascontiguousarray(pred, np.float32)
     bm = np.ascontiguousarray(bitmap, np.uint8)
@@ -196,13 +196,17 @@ def polygons_from_bitmap(pred, bitmap, adjust=(1.0, 1.0), box_thresh=0.7, min_si
     xy = np.empty((max_pts, 2), np.uint32)
     scores = np.empty(max_polys, np.float64)
     stats = np.zeros(5, np.int64)
+    boxes = np.empty((max_polys if return_boxes else 0, 4, 2), np.int32)
     n = lib().orc_polygons_from_bitmap(
         _p(pred, C.c_float), _p(bm, C.c_uint8), H, W, C.c_double(adjust[0]), C.c_double(adjust[1]),
         C.c_double(box_thresh), C.c_double(min_size), C.c_double(unclip), max_polys, C.c_int64(max_pts),
-        _p(offs, C.c_int64), _p(xy, C.c_uint32), _p(scores, C.c_double), _p(stats, C.c_int64))
+        _p(offs, C.c_int64), _p(xy, C.c_uint32), _p(scores, C.c_double), _p(stats, C.c_int64),
+        _p(boxes, C.c_int32) if return_boxes else None)
     if n < 0:
         raise RuntimeError("oracle polygons_from_bitmap capacity")
     polys = [xy[offs[i]:offs[i + 1]].copy() for i in range(n)]
+    if return_boxes:
+        return polys, scores[:n].copy(), boxes[:n].copy()
     if return_stats:
         return polys, scores[:n].copy(), stats
     return polys, scores[:n].copy()
@@ -249,3 +253,34 @@ def polygon_iou(a, b):
     inter = np.logical_and(ma, mb).sum()
     union = np.logical_or(ma, mb).sum()
     return inter / union if union else 1.0
+
+
+def crop_glyphs(image, box, k):
+    """crop spec v1 (see orc_crop_glyphs): u8 [H,W] image, box [4,2] (TL,TR,BR,BL) -> u8 [k,784]."""
+    img = np.ascontiguousarray(image, np.uint8)
+    b = _pts(box)
+    out = np.empty((k, 784), np.uint8)
+    lib().orc_crop_glyphs(_p(img, C.c_uint8), img.shape[1], img.shape[0], _p(b, C.c_int32), int(k), _p(out, C.c_uint8))
+    return out
+
+
+def kept_boxes_from_bitmap(pred, bitmap, box_thresh=0.7, min_size=5.0, unclip=2.0):
+    """The min-area boxes (map coordinates, TL,TR,BR,BL) of the polygons get_polygons_from_bitmap keeps, in its
+    order: contours -> DP -> score filter -> unclip -> size filter (metrics.rs:78-108)."""
+    pred = np.ascontiguousarray(pred, np.float32)
+    cs, _ = find_contours(bitmap)
+    boxes = []
+    for c in cs:
+        dp = dp_polygon(c)
+        if len(dp) < 4:
+            continue
+        if box_thresh > box_score(pred, dp):
+            continue
+        ex = expand_polygon(dp, unclip)
+        if ex is None:
+            continue
+        box, sside = min_area_bounding_box(ex)
+        if sside < min_size:
+            continue
+        boxes.append(box)
+    return boxes

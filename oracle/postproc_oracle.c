@@ -870,7 +870,7 @@ static inline uint32_t sat_u32(double v) {
 int orc_polygons_from_bitmap(const float *pred, const uint8_t *bitmap, int H, int W,
                              double adj_x, double adj_y, double box_thresh, double min_size,
                              double unclip_factor, int max_polys, int64_t max_pts,
-                             int64_t *offsets, uint32_t *xy, double *scores, int64_t *stats) {
+                             int64_t *offsets, uint32_t *xy, double *scores, int64_t *stats, ipt *boxes_out) {
   int64_t cap_pts = (int64_t)W * H * 2 + 16;
   int cap_c = W * H / 2 + 16;
   ipt *cpts = (ipt *)malloc(sizeof(ipt) * (size_t)cap_pts);
@@ -902,7 +902,8 @@ int orc_polygons_from_bitmap(const float *pred, const uint8_t *bitmap, int H, in
     int ne = orc_expand_polygon(dp, (int)nd, unclip_factor, ex, cap, NULL);
     free(dp);
     if (ne == 0) { st[4]++; free(ex); continue; } /* reference: unwrap() panic (D11) */
-    double sside = orc_min_area_bounding_box(ex, ne, NULL);
+    ipt box[4];
+    double sside = orc_min_area_bounding_box(ex, ne, box);
     if (sside < min_size) { free(ex); continue; }
     if (n_out >= max_polys || np_out + ne > max_pts) { free(ex); rc = -1; goto done; }
     for (int i = 0; i < ne; ++i) {
@@ -911,6 +912,7 @@ int orc_polygons_from_bitmap(const float *pred, const uint8_t *bitmap, int H, in
     }
     np_out += ne;
     scores[n_out] = score;
+    if (boxes_out) memcpy(boxes_out + 4 * (size_t)n_out, box, sizeof(box)); /* map coordinates; input of the crop glue */
     n_out++;
     offsets[n_out] = np_out;
     st[3]++;
@@ -1000,4 +1002,66 @@ void orc_preprocess(const uint8_t *rgba, int sw, int sh, int W, int H, uint8_t *
       dst[(int64_t)y * W + x] = (uint8_t)l;
     }
   free(res);
+}
+
+/* ------------------------------------------------------------------------------------
+ * Polygon -> glyph crop glue ("crop spec v1").  The reference has NO counterpart: character
+ * segmentation is an open item of its README (README.md:20-26), and its recognition net is
+ * only ever fed ready-made 28x28 files (image_ops.rs:73-85).  This is the definition the
+ * CUDA path (csrc/crop.cu) is held to, built from the reference's own pieces: the box is
+ * get_min_area_bounding_box's (metrics.rs:133-148; TL, TR, BR, BL), the resampling is
+ * preprocess_image's Triangle filter (image 0.23.11).
+ *
+ *   1. reading axis = the longer side of the box (u = TR - TL, v = BL - TL; swapped when |v| > |u|,
+ *      so vertical text reads top to bottom); pw = max(1, round(|u|)), ph = max(1, round(|v|)), f32
+ *   2. the box is rectified to a pw x ph patch by nearest sampling:
+ *      patch(x, y) = img[clamp(floor(o.y + s uy + t vy))][clamp(floor(o.x + s ux + t vx))],
+ *      s = (x + 0.5) / pw, t = (y + 0.5) / ph, every operation a separately rounded f32 one
+ *   3. the patch is cut into K cells along x: cell g = columns [min(g pw / K, pw - 1), max(x0 + 1, min(pw, (g + 1) pw / K)))
+ *   4. each cell is resized to 28 x 28 with the Triangle filter, vertical pass first, u8 truncation
+ *      after either pass (exactly resample_1d above)
+ * out: [K][784] u8.
+ * ---------------------------------------------------------------------------------- */
+void orc_crop_glyphs(const uint8_t *img, int W, int H, const ipt box[4], int K, uint8_t *out) {
+  ipt o = box[0];
+  float ux = (float)(box[1].x - box[0].x), uy = (float)(box[1].y - box[0].y);
+  float vx = (float)(box[3].x - box[0].x), vy = (float)(box[3].y - box[0].y);
+  float wlen = sqrtf(ux * ux + uy * uy), hlen = sqrtf(vx * vx + vy * vy);
+  if (hlen > wlen) {
+    float t;
+    t = ux; ux = vx; vx = t;
+    t = uy; uy = vy; vy = t;
+    t = wlen; wlen = hlen; hlen = t;
+  }
+  int pw = (int)roundf(wlen), ph = (int)roundf(hlen);
+  if (pw < 1) pw = 1;
+  if (ph < 1) ph = 1;
+  uint8_t *patch = (uint8_t *)malloc((size_t)pw * ph);
+  for (int y = 0; y < ph; ++y)
+    for (int x = 0; x < pw; ++x) {
+      float s = ((float)x + 0.5f) / (float)pw, t = ((float)y + 0.5f) / (float)ph;
+      float fx = ((float)o.x + s * ux) + t * vx, fy = ((float)o.y + s * uy) + t * vy;
+      int ix = (int)floorf(fx), iy = (int)floorf(fy);
+      ix = ix < 0 ? 0 : (ix > W - 1 ? W - 1 : ix);
+      iy = iy < 0 ? 0 : (iy > H - 1 ? H - 1 : iy);
+      patch[(size_t)y * pw + x] = img[(size_t)iy * W + ix];
+    }
+  int saved = g_resize_norm_first;
+  g_resize_norm_first = 0;
+  for (int g = 0; g < K; ++g) {
+    int x0 = (int)((int64_t)g * pw / K);
+    if (x0 > pw - 1) x0 = pw - 1;
+    int x1 = (int)((int64_t)(g + 1) * pw / K);
+    if (x1 > pw) x1 = pw;
+    if (x1 < x0 + 1) x1 = x0 + 1;
+    int sw = x1 - x0;
+    uint8_t *tmp = (uint8_t *)malloc((size_t)28 * sw);
+    /* vertical: [ph][sw] (row stride pw) -> [28][sw] */
+    resample_1d(patch + x0, ph, 28, pw, sw, sw, 1, 1, 1, tmp);
+    /* horizontal: [28][sw] -> [28][28] */
+    resample_1d(tmp, sw, 28, 1, 1, 28, sw, 28, 1, out + (size_t)g * 784);
+    free(tmp);
+  }
+  g_resize_norm_first = saved;
+  free(patch);
 }
