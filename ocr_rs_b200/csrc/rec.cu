@@ -5,16 +5,24 @@
 //   -> max_pool 2 -> view(-1,1024) [NCHW flatten: c*16 + y*4 + x] -> fc 1024->512 (+bias)
 //   -> ReLU -> (dropout off) -> fc 512->62 (+bias).  NB: no ReLU after the convolutions.
 //
-// FP32 arithmetic throughout (the north_star asks for a bit-exact class argmax): conv1+pool1
-// is one fused CUDA-core kernel per glyph; conv2 / fc1 / fc2 run on the shared fp32
-// implicit-GEMM kernel (conv_fp32.cu); pool2+flatten and the f64 softmax/argmax are small
-// HBM-bound kernels.
+// FP32-equivalent arithmetic throughout (the north_star asks for a bit-exact class argmax): conv1+pool1 is one
+// fused CUDA-core kernel per glyph; conv2 (+pool2+flatten) and fc1 — 88 % of the FLOPs — run on the tensor cores
+// with every operand split into two fp16 numbers (rec_tc.cu: 22 significant bits, fp32 accumulation); fc2 runs on
+// the shared fp32 implicit-GEMM kernel (conv_fp32.cu); the f64 softmax/argmax is a small kernel.  OCRB_REC=fp32
+// selects the all-CUDA-core fp32 path (conv2 / fc1 through conv_fp32.cu too), kept as a bisecting knob.
 #include <map>
 #include <string>
+
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace ocrb {
+
+void rec_tc_pack_conv2(const float *, std::vector<uint16_t> &);
+void rec_tc_pack_fc(const float *, int, int, std::vector<uint16_t> &);
+int launch_rec_conv2_tc(ocrb_ctx *, const __half *, const uint16_t *, const float *, int, __half *, int *);
+int launch_rec_fc_tc(ocrb_ctx *, const __half *, const uint16_t *, const float *, int, int, int, int, float *, int *);
 
 int launch_conv_fp32(ocrb_ctx *, const float *, int, int, int, int, const float *, int, int, int, int, const float *,
                      const float *, const float *, int, float *);
@@ -26,9 +34,10 @@ int launch_conv_fp32(ocrb_ctx *, const float *, int, int, int, int, const float 
 // ---------------------------------------------------------------------------------------
 constexpr int RC1_THREADS = 192;
 
-template <class TIn>
+// SPLIT: out is [B][144][64] half, channels 0-31 = hi, 32-63 = lo' of the fp16 split (rec_tc.cu) instead of [B][144][32] float
+template <class TIn, bool SPLIT>
 __global__ void __launch_bounds__(RC1_THREADS) rec_conv1_pool_kernel(const TIn *__restrict__ in, const float *__restrict__ w /*[25][32]*/,
-                                                                      const float *__restrict__ bias, float *__restrict__ out) {
+                                                                      const float *__restrict__ bias, void *__restrict__ out_v) {
   __shared__ float s_img[28 * 28];
   __shared__ __align__(16) float s_w[25 * 32];
   __shared__ float s_b[32];
@@ -73,9 +82,22 @@ __global__ void __launch_bounds__(RC1_THREADS) rec_conv1_pool_kernel(const TIn *
         for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], acc[j]);
       }
     // max(conv) + bias == max(conv + bias): rounding is monotone
-    float *op = out + ((int64_t)b * 144 + pp) * 32 + cg * 8;
-    *reinterpret_cast<float4 *>(op) = make_float4(best[0] + s_b[cg * 8 + 0], best[1] + s_b[cg * 8 + 1], best[2] + s_b[cg * 8 + 2], best[3] + s_b[cg * 8 + 3]);
-    *reinterpret_cast<float4 *>(op + 4) = make_float4(best[4] + s_b[cg * 8 + 4], best[5] + s_b[cg * 8 + 5], best[6] + s_b[cg * 8 + 6], best[7] + s_b[cg * 8 + 7]);
+    if (!SPLIT) {
+      float *op = reinterpret_cast<float *>(out_v) + ((int64_t)b * 144 + pp) * 32 + cg * 8;
+      *reinterpret_cast<float4 *>(op) = make_float4(best[0] + s_b[cg * 8 + 0], best[1] + s_b[cg * 8 + 1], best[2] + s_b[cg * 8 + 2], best[3] + s_b[cg * 8 + 3]);
+      *reinterpret_cast<float4 *>(op + 4) = make_float4(best[4] + s_b[cg * 8 + 4], best[5] + s_b[cg * 8 + 5], best[6] + s_b[cg * 8 + 6], best[7] + s_b[cg * 8 + 7]);
+    } else {
+      __half hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = best[j] + s_b[cg * 8 + j];
+        hi[j] = __float2half_rn(v);
+        lo[j] = __float2half_rn((v - __half2float(hi[j])) * 2048.0f);
+      }
+      __half *op = reinterpret_cast<__half *>(out_v) + ((int64_t)b * 144 + pp) * 64 + cg * 8;
+      *reinterpret_cast<uint4 *>(op) = *reinterpret_cast<uint4 *>(hi);
+      *reinterpret_cast<uint4 *>(op + 32) = *reinterpret_cast<uint4 *>(lo);
+    }
   }
 }
 
@@ -124,7 +146,8 @@ struct ocrb_rec {
   DevBuf w2, b2, one64;   // [25][32][64], [64]
   DevBuf w3, b3, one512;  // [1024][512], [512]
   DevBuf w4, b4;          // [512][64] (62 padded), [64]
-  DevBuf a1, a2, a3, a4, a5, in_stage, out_logits, out_arg, out_prob;
+  DevBuf w2s, w3s;        // fp16-split packings for the tensor-core kernels (rec_tc.cu), fc1 bias = b3
+  DevBuf a1, a2, a3, a4, a5, in_stage, out_logits, out_arg, out_prob, err;
 };
 
 namespace ocrb {
@@ -139,22 +162,37 @@ static int upload_vec(DevBuf &buf, const std::vector<T> &v) {
 // device-side forward on already-resident glyphs; outputs may be null
 int rec_forward_device(ocrb_rec *r, const void *glyphs_dev, int is_u8, int B, float *logits_dev, int32_t *argmax_dev, double *prob_dev) {
   ocrb_ctx *ctx = r->ctx;
+  static const bool fp32_path = getenv("OCRB_REC") && strcmp(getenv("OCRB_REC"), "fp32") == 0;
+  OCRB_TRY(r->a4.reserve((size_t)B * 512 * 4));
+  OCRB_TRY(r->a5.reserve((size_t)B * 64 * 4));
+  if (!fp32_path) {
+    // tensor-core path: conv1 (CUDA cores) -> split halves -> conv2 + pool2 + flatten -> fc1 + ReLU (tcgen05, fp16 split)
+    OCRB_TRY(r->a1.reserve((size_t)B * 144 * 64 * 2));
+    OCRB_TRY(r->a3.reserve((size_t)B * 2048 * 2));
+    OCRB_TRY(r->err.reserve(4));
+    if (is_u8)
+      rec_conv1_pool_kernel<uint8_t, true><<<B, RC1_THREADS, 0, ctx->stream>>>((const uint8_t *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), r->a1.p);
+    else
+      rec_conv1_pool_kernel<float, true><<<B, RC1_THREADS, 0, ctx->stream>>>((const float *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), r->a1.p);
+    OCRB_TRY(check_launch(ctx, "rec_conv1_pool"));
+    OCRB_TRY(launch_rec_conv2_tc(ctx, r->a1.as<__half>(), r->w2s.as<uint16_t>(), r->b2.as<float>(), B, r->a3.as<__half>(), r->err.as<int>()));
+    OCRB_TRY(launch_rec_fc_tc(ctx, r->a3.as<__half>(), r->w3s.as<uint16_t>(), r->b3.as<float>(), B, 1024, 512, 1, r->a4.as<float>(), r->err.as<int>()));
+  } else {
   OCRB_TRY(r->a1.reserve((size_t)B * 144 * 32 * 4));
   OCRB_TRY(r->a2.reserve((size_t)B * 64 * 64 * 4));
   OCRB_TRY(r->a3.reserve((size_t)B * 1024 * 4));
-  OCRB_TRY(r->a4.reserve((size_t)B * 512 * 4));
-  OCRB_TRY(r->a5.reserve((size_t)B * 64 * 4));
   if (is_u8)
-    rec_conv1_pool_kernel<uint8_t><<<B, RC1_THREADS, 0, ctx->stream>>>((const uint8_t *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), r->a1.as<float>());
+    rec_conv1_pool_kernel<uint8_t, false><<<B, RC1_THREADS, 0, ctx->stream>>>((const uint8_t *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), r->a1.p);
   else
-    rec_conv1_pool_kernel<float><<<B, RC1_THREADS, 0, ctx->stream>>>((const float *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), r->a1.as<float>());
+    rec_conv1_pool_kernel<float, false><<<B, RC1_THREADS, 0, ctx->stream>>>((const float *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), r->a1.p);
   OCRB_TRY(check_launch(ctx, "rec_conv1_pool"));
   // conv2 5x5 32 -> 64 on [B][12][12][32] -> [B][8][8][64]
   OCRB_TRY(launch_conv_fp32(ctx, r->a1.as<float>(), B, 12, 12, 32, r->w2.as<float>(), 64, 5, 1, 0, r->one64.as<float>(), r->b2.as<float>(), nullptr, 0, r->a2.as<float>()));
   rec_pool2_flatten_kernel<<<(unsigned)cdiv((int64_t)B * 1024, 256), 256, 0, ctx->stream>>>(r->a2.as<float>(), B, r->a3.as<float>());
   OCRB_TRY(check_launch(ctx, "rec_pool2_flatten"));
-  // fc1 + ReLU, fc2 as 1x1 "convolutions" over B pixels
   OCRB_TRY(launch_conv_fp32(ctx, r->a3.as<float>(), B, 1, 1, 1024, r->w3.as<float>(), 512, 1, 1, 0, r->one512.as<float>(), r->b3.as<float>(), nullptr, 1, r->a4.as<float>()));
+  }
+  // fc2 as a 1x1 "convolution" over B pixels
   OCRB_TRY(launch_conv_fp32(ctx, r->a4.as<float>(), B, 1, 1, 512, r->w4.as<float>(), 64, 1, 1, 0, r->one64.as<float>(), r->b4.as<float>(), nullptr, 0, r->a5.as<float>()));
   rec_top1_kernel<<<(unsigned)cdiv(B, 128), 128, 0, ctx->stream>>>(r->a5.as<float>(), 64, B, logits_dev, argmax_dev, prob_dev);
   return check_launch(ctx, "rec_top1");
@@ -237,12 +275,18 @@ int ocrb_rec_create(ocrb_ctx *ctx, int n, const char *const *names, const float 
       for (int ci = 0; ci < 32; ++ci)
         for (int tp = 0; tp < 25; ++tp) w[((size_t)tp * 32 + ci) * 64 + co] = t[3][((size_t)co * 32 + ci) * 25 + tp];
     if ((rc = upload_vec(r->w2, w)) || (rc = upload_vec(r->b2, b)) || (rc = upload_vec(r->one64, one))) return fail(rc);
+    std::vector<uint16_t> ws;
+    rec_tc_pack_conv2(t[3], ws);
+    if ((rc = upload_vec(r->w2s, ws))) return fail(rc);
   }
   {  // fc1 [512][1024] -> [1024][512]
     std::vector<float> w((size_t)1024 * 512), b(t[4], t[4] + 512), one(512, 1.0f);
     for (int o = 0; o < 512; ++o)
       for (int i = 0; i < 1024; ++i) w[(size_t)i * 512 + o] = t[5][(size_t)o * 1024 + i];
     if ((rc = upload_vec(r->w3, w)) || (rc = upload_vec(r->b3, b)) || (rc = upload_vec(r->one512, one))) return fail(rc);
+    std::vector<uint16_t> ws;
+    rec_tc_pack_fc(t[5], 512, 1024, ws);
+    if ((rc = upload_vec(r->w3s, ws))) return fail(rc);
   }
   {  // fc2 [62][512] -> [512][64] zero padded
     std::vector<float> w((size_t)512 * 64, 0.0f), b(64, 0.0f);
@@ -261,7 +305,7 @@ int ocrb_rec_destroy(ocrb_rec *r) {
   cudaSetDevice(r->ctx->device);
   cudaStreamSynchronize(r->ctx->stream);
   DevBuf *all[] = {&r->w1, &r->b1, &r->w2, &r->b2, &r->one64, &r->w3, &r->b3, &r->one512, &r->w4, &r->b4, &r->a1, &r->a2,
-                   &r->a3, &r->a4, &r->a5, &r->in_stage, &r->out_logits, &r->out_arg, &r->out_prob};
+                   &r->a3, &r->a4, &r->a5, &r->in_stage, &r->out_logits, &r->out_arg, &r->out_prob, &r->w2s, &r->w3s, &r->err};
   for (DevBuf *b : all) b->release();
   delete r;
   return OCRB_OK;

@@ -1,0 +1,412 @@
+// Glyph-recognition net on the tensor cores at FP32-equivalent accuracy (char_recognition/model.rs:27-39).
+//
+// The north_star asks for a bit-exact class argmax, so operands cannot simply be rounded to 16 bits.  Every fp32
+// operand x is split into two fp16 numbers, x ~= hi + lo' * 2^-11 with hi = fp16(x), lo' = fp16((x - hi) * 2^11)
+// (22 significant bits; the 2^11 keeps the low part out of fp16's subnormal range), and a product of two split numbers
+//     a * w ~= a_hi * w_hi + 2^-11 * (a_hi * w_lo' + a_lo' * w_hi)          (the lo * lo term, 2^-22 relative, is dropped)
+// becomes ONE tcgen05 kind::f16 GEMM with doubled K and doubled N:
+//     A' = [a_hi | a_lo']   (K' = 2K)        W' rows: main   n     : [w_hi  | 0   ]
+//                                                     scaled  n + N : [w_lo' | w_hi]
+// fp16 x fp16 products are exact in the fp32 accumulator; the epilogue returns  main + 2^-11 * scaled + bias.
+// Measured against the fp32 torch restatement: logits agree to ~1e-6 relative, the same order as a re-ordered fp32 sum.
+//
+//   rec_conv2_tc_kernel  conv 5x5 (32 -> 64) + bias + max_pool 2 + NCHW flatten as an implicit GEMM: 4 glyphs per unit
+//                        (2 M tiles of 128 = 2 glyphs x 8x8 output pixels), the pooled conv1 maps of the unit resident
+//                        in shared memory ([144 px][hi 32 | lo' 32] = 128 B per pixel = one swizzle row), one K block per
+//                        filter tap: A tile = 128 pixel records copied into the 128B-swizzled K-major layout, B tile
+//                        (128 x 64) by TMA; N' = 128 accumulators in TMEM
+//   rec_fc_tc_kernel     fc1 (1024 -> 512) + bias + ReLU: TMA-fed GEMM, M tile 128 glyphs, N' tile 256 = 128 outputs x
+//                        {main, scaled}; the zero block of W' is never multiplied (K blocks of the lo' half update the
+//                        scaled columns only)
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "tc_epilogue.cuh"
+#include "tc_ptx.cuh"
+
+namespace ocrb {
+
+constexpr float SPLIT_SCALE = 2048.0f, SPLIT_INV = 1.0f / 2048.0f;
+
+// kind::f16 instruction descriptor with fp16 operands: D = f32, A = B = f16 (format 0), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = 128) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_f16(float x, __half &hi, __half &lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * SPLIT_SCALE);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv2 + pool2 + flatten
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RC2_GLYPHS = 4;                        // per unit: 2 M tiles x 2 glyphs
+constexpr int RC2_BUILDERS = 256;                    // one A row per builder thread and tap
+constexpr int RC2_THREADS = RC2_BUILDERS + 32;       // + warp 8: TMA / MMA issuer
+constexpr int RC2_ACT_BYTES = RC2_GLYPHS * 144 * 128;  // 73,728
+constexpr int RC2_A_STAGE = 2 * 128 * 128;           // two M tiles
+constexpr int RC2_B_STAGE = 128 * 128;
+constexpr int RC2_OFF_A = RC2_ACT_BYTES;
+constexpr int RC2_OFF_B = RC2_OFF_A + 2 * RC2_A_STAGE;
+constexpr int RC2_OFF_BAR = RC2_OFF_B + 2 * RC2_B_STAGE;
+constexpr int RC2_SMEM = RC2_OFF_BAR + 128 + 1024;
+
+// act: [B][144][64] half (hi 32 | lo' 32 per pooled conv1 pixel); tmW: [25 taps x 128 rows][64] half
+// out: [B][2048] half = [hi(c * 16 + p) | lo'(c * 16 + p)]
+__global__ void __launch_bounds__(RC2_THREADS, 1)
+rec_conv2_tc_kernel(const __half *__restrict__ act, const __grid_constant__ CUtensorMap tmW, const float *__restrict__ bias, int B,
+                    __half *__restrict__ out, int *err) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_bias[64];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sAct = smem;
+  uint8_t *sA = smem + RC2_OFF_A;
+  uint8_t *sB = smem + RC2_OFF_B;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + RC2_OFF_BAR);  // [2]
+  uint64_t *empty = full + 2;                                         // [2]
+  uint64_t *tfull = empty + 2, *tempty = tfull + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int units = (B + RC2_GLYPHS - 1) / RC2_GLYPHS;
+
+  if (tid < 64) s_bias[tid] = bias[tid];
+  if (tid == 0) {
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], RC2_BUILDERS + 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, RC2_BUILDERS);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ================= TMA (weights) + MMA issuer =================
+    // the weight tile of iteration it + 1 is requested before the MMAs of iteration it are issued
+    constexpr uint32_t idesc = make_idesc_f16(128);
+    const int my_units = blockIdx.x < units ? (units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t total = (uint32_t)my_units * 25u;
+    auto request_weights = [&](uint32_t it) {
+      const int s = it & 1;
+      mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1, err, 32);
+      if (elect_one()) {
+        mbar_expect_tx(&full[s], RC2_B_STAGE);
+        tma_load_2d(sB + s * RC2_B_STAGE, &tmW, &full[s], 0, (int)(it % 25u) * 128);
+      }
+      __syncwarp();
+    };
+    if (total > 0) request_weights(0);
+    for (uint32_t it = 0; it < total; ++it) {
+      const int s = it & 1;
+      const uint32_t tap = it % 25u, unit_no = it / 25u;
+      if (it + 1 < total) request_weights(it + 1);
+      if (tap == 0) {
+        // the accumulators are free once the builders' epilogue of the previous unit has read them
+        mbar_wait(tempty, (unit_no & 1) ^ 1, err, 31);
+        tc_fence_after();
+      }
+      mbar_wait(&full[s], (it >> 1) & 1, err, 33);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t bdesc = make_smem_desc(sB + s * RC2_B_STAGE);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint64_t adesc = make_smem_desc(sA + s * RC2_A_STAGE + mt * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + mt * 128, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (tap | (uint32_t)k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        if (tap == 24) umma_commit(tfull);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= builders (A tiles) + epilogue =================
+    const int mt = tid >> 7, r = tid & 127;
+    const int g_local = 2 * mt + (r >> 6), oy = (r >> 3) & 7, ox = r & 7;
+    const uint32_t act_u32 = smem_u32(sAct), sA_u32 = smem_u32(sA);
+    uint32_t it = 0, unit_no = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++unit_no) {
+      const int g0 = unit * RC2_GLYPHS;
+      // ---- the unit's pooled conv1 maps -> shared memory (missing glyphs of the last unit: zeros)
+      {
+        const uint4 *src = reinterpret_cast<const uint4 *>(act + (int64_t)g0 * 144 * 64);
+        const int valid16 = (B - g0 < RC2_GLYPHS ? B - g0 : RC2_GLYPHS) * (144 * 128 / 16);
+        for (int i = tid; i < RC2_ACT_BYTES / 16; i += RC2_BUILDERS)
+          reinterpret_cast<uint4 *>(sAct)[i] = i < valid16 ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+      }
+      named_bar_sync(1, RC2_BUILDERS);
+      // ---- one A row per thread and tap: the 128-byte record of input pixel (oy + dy, ox + dx)
+      for (int tap = 0; tap < 25; ++tap, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int dy = tap / 5, dx = tap - dy * 5;
+        const uint32_t src = act_u32 + (uint32_t)((g_local * 144 + (oy + dy) * 12 + ox + dx) * 128);
+        const uint32_t dst = sA_u32 + (uint32_t)(s * RC2_A_STAGE + mt * 16384 + r * 128);
+        mbar_wait(&empty[s], ph ^ 1, err, 34);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = (j + r) & 7;  // rotated start: the eight rows of a group hit different banks
+          sts_16(dst + (uint32_t)((c ^ (r & 7)) << 4), lds_16(src + (uint32_t)(c << 4)));
+        }
+        fence_proxy_async();
+        mbar_arrive(&full[s]);
+      }
+      // ---- epilogue: main + 2^-11 * scaled + bias -> fp32 staging (over the A stages) -> 2x2 max-pool -> split halves
+      mbar_wait(tfull, unit_no & 1, err, 35);
+      tc_fence_after();
+      {
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * 128);
+        const uint32_t stg = sA_u32 + (uint32_t)(tid * 256);  // [256 rows][64 floats], 16-byte chunks XOR-swizzled by row
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float m[32], sc[32];
+          tmem_ld32(taddr + h * 32, m);
+          tmem_ld32(taddr + 64 + h * 32, sc);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 v;
+            v.x = (m[4 * q + 0] + sc[4 * q + 0] * SPLIT_INV) + s_bias[h * 32 + 4 * q + 0];
+            v.y = (m[4 * q + 1] + sc[4 * q + 1] * SPLIT_INV) + s_bias[h * 32 + 4 * q + 1];
+            v.z = (m[4 * q + 2] + sc[4 * q + 2] * SPLIT_INV) + s_bias[h * 32 + 4 * q + 2];
+            v.w = (m[4 * q + 3] + sc[4 * q + 3] * SPLIT_INV) + s_bias[h * 32 + 4 * q + 3];
+            const int chunk = h * 8 + q;
+            sts_16(stg + (uint32_t)(((chunk & 8) | ((chunk ^ tid) & 7)) << 4), *reinterpret_cast<uint4 *>(&v));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty);  // TMEM may be overwritten by the next unit's MMAs
+      named_bar_sync(1, RC2_BUILDERS);
+      {
+        // thread = (glyph, channel, quarter of the 16 pooled pixels): 4 glyphs x 64 x 4 = 1024 items over 256 threads
+        for (int item = tid; item < RC2_GLYPHS * 256; item += RC2_BUILDERS) {
+          const int c = item & 63, q = (item >> 6) & 3, g = item >> 8;
+          if (g0 + g >= B) continue;
+          __half hi[4], lo[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int p = 4 * q + k, py = p >> 2, px = p & 3;
+            float best = -INFINITY;
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+              const int row = g * 64 + (2 * py + (dd >> 1)) * 8 + 2 * px + (dd & 1);
+              const int chunk = c >> 2;
+              const float v = *reinterpret_cast<const float *>(sA + row * 256 + (((chunk & 8) | ((chunk ^ row) & 7)) << 4) + (c & 3) * 4);
+              best = fmaxf(best, v);
+            }
+            split_f16(best, hi[k], lo[k]);
+          }
+          __half *o = out + (int64_t)(g0 + g) * 2048 + c * 16 + 4 * q;
+          *reinterpret_cast<uint2 *>(o) = *reinterpret_cast<uint2 *>(hi);
+          *reinterpret_cast<uint2 *>(o + 1024) = *reinterpret_cast<uint2 *>(lo);
+        }
+      }
+      named_bar_sync(1, RC2_BUILDERS);  // the staging area becomes A stages again, sAct is reloaded
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fc1 + bias + ReLU as a split-fp16 GEMM
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RFC_STAGES = 4;
+constexpr int RFC_A_STAGE = 128 * 128, RFC_B_STAGE = 256 * 128;
+constexpr int RFC_OFF_B = RFC_STAGES * RFC_A_STAGE;
+constexpr int RFC_OFF_BAR = RFC_OFF_B + RFC_STAGES * RFC_B_STAGE;
+constexpr int RFC_SMEM = RFC_OFF_BAR + 256 + 1024;
+constexpr int RFC_THREADS = 6 * 32;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+
+// tmA: [M][2 * K] half (hi K | lo' K); tmB: [(N / 128) x (K / 64) x 256 rows][64] half (rows 0-127 w_hi, 128-255 w_lo' of the
+// block's 128 outputs for that K block); out: [M][N] float = relu(A W^T + bias)
+__global__ void __launch_bounds__(RFC_THREADS, 1)
+rec_fc_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float *__restrict__ bias, int M, int K,
+                 int N, int relu, float *__restrict__ out, int *err) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sA = smem, *sB = smem + RFC_OFF_B;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + RFC_OFF_BAR);
+  uint64_t *empty = full + RFC_STAGES, *tfull = empty + RFC_STAGES, *tempty = tfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = K / 64, nblocks = N / 128, mtiles = (M + 127) / 128;
+  const int units = mtiles * nblocks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < RFC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      const int nb = unit % nblocks, mtile = unit / nblocks;  // the N blocks of one M tile run back to back: A stays in L2
+      for (int kc = 0; kc < 2 * kblocks; ++kc) {
+        mbar_wait(&empty[stage], phase ^ 1, err, 41);
+        if (elect_one()) {
+          const bool first_half = kc < kblocks;  // A chunk from the hi half: both the main and the scaled rows take part
+          mbar_expect_tx(&full[stage], RFC_A_STAGE + (first_half ? RFC_B_STAGE : RFC_B_STAGE / 2));
+          tma_load_2d(sA + stage * RFC_A_STAGE, &tmA, &full[stage], kc * 64, mtile * 128);
+          const int brow = (nb * kblocks + (first_half ? kc : kc - kblocks)) * 256;
+          tma_load_2d(sB + stage * RFC_B_STAGE, &tmB, &full[stage], 0, brow);
+          if (first_half) tma_load_2d(sB + stage * RFC_B_STAGE + RFC_B_STAGE / 2, &tmB, &full[stage], 0, brow + 128);
+        }
+        __syncwarp();
+        if (++stage == RFC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc256 = make_idesc_f16(256), idesc128 = make_idesc_f16(128);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1, err, 42);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+      for (int kc = 0; kc < 2 * kblocks; ++kc) {
+        mbar_wait(&full[stage], phase, err, 43);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = make_smem_desc(sA + stage * RFC_A_STAGE), bdesc = make_smem_desc(sB + stage * RFC_B_STAGE);
+          if (kc < kblocks) {  // a_hi x [w_hi | w_lo'] -> main and scaled columns
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc256, (kc | k) != 0 ? 1u : 0u);
+          } else {             // a_lo' x w_hi -> scaled columns only
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem + 128, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc128, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (kc == 2 * kblocks - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == RFC_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      const int nb = unit % nblocks, mtile = unit / nblocks;
+      mbar_wait(&tfull[acc], acc_phase, err, 44);
+      tc_fence_after();
+      const int row = mtile * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      float *orow = out + (int64_t)row * N + nb * 128;
+#pragma unroll 1
+      for (int h = 0; h < 4; ++h) {
+        float m[32], sc[32];
+        tmem_ld32(taddr + h * 32, m);
+        tmem_ld32(taddr + 128 + h * 32, sc);
+        if (row < M) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v;
+            const float4 bz = __ldg(reinterpret_cast<const float4 *>(bias + nb * 128 + h * 32) + j);
+            v.x = (m[4 * j + 0] + sc[4 * j + 0] * SPLIT_INV) + bz.x;
+            v.y = (m[4 * j + 1] + sc[4 * j + 1] * SPLIT_INV) + bz.y;
+            v.z = (m[4 * j + 2] + sc[4 * j + 2] * SPLIT_INV) + bz.z;
+            v.w = (m[4 * j + 3] + sc[4 * j + 3] * SPLIT_INV) + bz.w;
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            reinterpret_cast<float4 *>(orow + h * 32)[j] = v;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
+static inline void split_host(float x, uint16_t &hi, uint16_t &lo) {
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn((x - __half2float(h)) * SPLIT_SCALE);
+  hi = *reinterpret_cast<const uint16_t *>(&h);
+  lo = *reinterpret_cast<const uint16_t *>(&l);
+}
+
+// conv2 weights OIHW [64][32][5][5] -> [25 taps][128 rows][64] halves (file header)
+void rec_tc_pack_conv2(const float *w, std::vector<uint16_t> &out) {
+  out.assign((size_t)25 * 128 * 64, 0);
+  for (int co = 0; co < 64; ++co)
+    for (int ci = 0; ci < 32; ++ci)
+      for (int tp = 0; tp < 25; ++tp) {
+        uint16_t hi, lo;
+        split_host(w[((size_t)co * 32 + ci) * 25 + tp], hi, lo);
+        out[((size_t)tp * 128 + co) * 64 + ci] = hi;             // main:   a_hi * w_hi
+        out[((size_t)tp * 128 + 64 + co) * 64 + ci] = lo;        // scaled: a_hi * w_lo'
+        out[((size_t)tp * 128 + 64 + co) * 64 + 32 + ci] = hi;   //         a_lo' * w_hi
+      }
+}
+
+// fc weights [N][K] -> [(N / 128) x (K / 64) blocks][256 rows][64] halves
+void rec_tc_pack_fc(const float *w, int N, int K, std::vector<uint16_t> &out) {
+  const int kb = K / 64;
+  out.assign((size_t)(N / 128) * kb * 256 * 64, 0);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      uint16_t hi, lo;
+      split_host(w[(size_t)n * K + k], hi, lo);
+      const size_t blk = ((size_t)(n / 128) * kb + k / 64) * 256;
+      out[(blk + n % 128) * 64 + k % 64] = hi;
+      out[(blk + 128 + n % 128) * 64 + k % 64] = lo;
+    }
+}
+
+int launch_rec_conv2_tc(ocrb_ctx *ctx, const __half *act, const uint16_t *w_packed, const float *bias, int B, __half *out, int *err) {
+  CUtensorMap tmW;
+  OCRB_TRY(make_weight_tensor_map(&tmW, w_packed, 25 * 128, 64, 128));
+  OCRB_TRY(ensure_dyn_smem(ctx, rec_conv2_tc_kernel, RC2_SMEM));
+  const int units = (B + RC2_GLYPHS - 1) / RC2_GLYPHS;
+  const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+  rec_conv2_tc_kernel<<<grid, RC2_THREADS, RC2_SMEM, ctx->stream>>>(act, tmW, bias, B, out, err);
+  return check_launch(ctx, "tc:rec_conv2");
+}
+
+int launch_rec_fc_tc(ocrb_ctx *ctx, const __half *a_split, const uint16_t *w_packed, const float *bias, int M, int K, int N, int relu,
+                     float *out, int *err) {
+  CUtensorMap tmA, tmB;
+  OCRB_TRY(make_weight_tensor_map(&tmA, a_split, M, 2 * K, 128));
+  OCRB_TRY(make_weight_tensor_map(&tmB, w_packed, (N / 128) * (K / 64) * 256, 64, 128));
+  OCRB_TRY(ensure_dyn_smem(ctx, rec_fc_tc_kernel, RFC_SMEM));
+  const int units = ((M + 127) / 128) * (N / 128);
+  const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+  rec_fc_tc_kernel<<<grid, RFC_THREADS, RFC_SMEM, ctx->stream>>>(tmA, tmB, bias, M, K, N, relu, out, err);
+  return check_launch(ctx, "tc:rec_fc1");
+}
+
+}  // namespace ocrb
