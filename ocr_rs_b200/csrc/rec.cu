@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace ocrb {
 
@@ -37,18 +38,20 @@ constexpr int RC1_THREADS = 192;
 // SPLIT: out is [B][144][64] half, channels 0-31 = hi, 32-63 = lo' of the fp16 split (rec_tc.cu) instead of [B][144][32] float
 template <class TIn, bool SPLIT>
 __global__ void __launch_bounds__(RC1_THREADS) rec_conv1_pool_kernel(const TIn *__restrict__ in, const float *__restrict__ w /*[25][32]*/,
-                                                                      const float *__restrict__ bias, void *__restrict__ out_v) {
+                                                                      const float *__restrict__ bias, int B, void *__restrict__ out_v) {
   __shared__ float s_img[28 * 28];
   __shared__ __align__(16) float s_w[25 * 32];
   __shared__ float s_b[32];
-  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < 800; i += RC1_THREADS) s_w[i] = w[i];
+  if (threadIdx.x < 32) s_b[threadIdx.x] = bias[threadIdx.x];
+  // persistent CTAs: the weights are staged once, glyphs are taken round robin
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  __syncthreads();  // the previous glyph's image has been consumed (and, first time, the weights are visible)
   const TIn *img = in + (int64_t)b * 784;
   for (int i = threadIdx.x; i < 784; i += RC1_THREADS) {
     if (sizeof(TIn) == 1) s_img[i] = (float)img[i] / 255.0f;
     else s_img[i] = (float)img[i];
   }
-  for (int i = threadIdx.x; i < 800; i += RC1_THREADS) s_w[i] = w[i];
-  if (threadIdx.x < 32) s_b[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   for (int item = threadIdx.x; item < 576; item += RC1_THREADS) {
     const int cg = item & 3, pp = item >> 2;
@@ -58,29 +61,34 @@ __global__ void __launch_bounds__(RC1_THREADS) rec_conv1_pool_kernel(const TIn *
     for (int r = 0; r < 6; ++r)
 #pragma unroll
       for (int s = 0; s < 6; ++s) patch[r * 6 + s] = s_img[(2 * py + r) * 28 + 2 * px + s];
+    // the four conv positions of the pool window share every weight load; channel pairs go through packed FFMA2
+    float2 acc[4][4];
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[pos][j] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        const float4 w0 = *reinterpret_cast<const float4 *>(&s_w[(r * 5 + s) * 32 + cg * 8]);
+        const float4 w1 = *reinterpret_cast<const float4 *>(&s_w[(r * 5 + s) * 32 + cg * 8 + 4]);
+#pragma unroll
+        for (int pos = 0; pos < 4; ++pos) {
+          const float v = patch[((pos >> 1) + r) * 6 + (pos & 1) + s];
+          const float2 vv = make_float2(v, v);
+          acc[pos][0] = ffma2(vv, make_float2(w0.x, w0.y), acc[pos][0]);
+          acc[pos][1] = ffma2(vv, make_float2(w0.z, w0.w), acc[pos][1]);
+          acc[pos][2] = ffma2(vv, make_float2(w1.x, w1.y), acc[pos][2]);
+          acc[pos][3] = ffma2(vv, make_float2(w1.z, w1.w), acc[pos][3]);
+        }
+      }
     float best[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-          for (int s = 0; s < 5; ++s) {
-            const float v = patch[(dy + r) * 6 + dx + s];
-            const float4 w0 = *reinterpret_cast<const float4 *>(&s_w[(r * 5 + s) * 32 + cg * 8]);
-            const float4 w1 = *reinterpret_cast<const float4 *>(&s_w[(r * 5 + s) * 32 + cg * 8 + 4]);
-            acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-            acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
-          }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], acc[j]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      best[2 * j] = fmaxf(fmaxf(acc[0][j].x, acc[1][j].x), fmaxf(acc[2][j].x, acc[3][j].x));
+      best[2 * j + 1] = fmaxf(fmaxf(acc[0][j].y, acc[1][j].y), fmaxf(acc[2][j].y, acc[3][j].y));
+    }
     // max(conv) + bias == max(conv + bias): rounding is monotone
     if (!SPLIT) {
       float *op = reinterpret_cast<float *>(out_v) + ((int64_t)b * 144 + pp) * 32 + cg * 8;
@@ -98,6 +106,7 @@ __global__ void __launch_bounds__(RC1_THREADS) rec_conv1_pool_kernel(const TIn *
       *reinterpret_cast<uint4 *>(op) = *reinterpret_cast<uint4 *>(hi);
       *reinterpret_cast<uint4 *>(op + 32) = *reinterpret_cast<uint4 *>(lo);
     }
+  }
   }
 }
 
@@ -163,6 +172,7 @@ static int upload_vec(DevBuf &buf, const std::vector<T> &v) {
 int rec_forward_device(ocrb_rec *r, const void *glyphs_dev, int is_u8, int B, float *logits_dev, int32_t *argmax_dev, double *prob_dev) {
   ocrb_ctx *ctx = r->ctx;
   static const bool fp32_path = getenv("OCRB_REC") && strcmp(getenv("OCRB_REC"), "fp32") == 0;
+  const int rc1_grid = B < 8 * ctx->sm_count ? B : 8 * ctx->sm_count;
   OCRB_TRY(r->a4.reserve((size_t)B * 512 * 4));
   OCRB_TRY(r->a5.reserve((size_t)B * 64 * 4));
   if (!fp32_path) {
@@ -171,9 +181,9 @@ int rec_forward_device(ocrb_rec *r, const void *glyphs_dev, int is_u8, int B, fl
     OCRB_TRY(r->a3.reserve((size_t)B * 2048 * 2));
     OCRB_TRY(r->err.reserve(4));
     if (is_u8)
-      rec_conv1_pool_kernel<uint8_t, true><<<B, RC1_THREADS, 0, ctx->stream>>>((const uint8_t *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), r->a1.p);
+      rec_conv1_pool_kernel<uint8_t, true><<<rc1_grid, RC1_THREADS, 0, ctx->stream>>>((const uint8_t *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), B, r->a1.p);
     else
-      rec_conv1_pool_kernel<float, true><<<B, RC1_THREADS, 0, ctx->stream>>>((const float *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), r->a1.p);
+      rec_conv1_pool_kernel<float, true><<<rc1_grid, RC1_THREADS, 0, ctx->stream>>>((const float *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), B, r->a1.p);
     OCRB_TRY(check_launch(ctx, "rec_conv1_pool"));
     OCRB_TRY(launch_rec_conv2_tc(ctx, r->a1.as<__half>(), r->w2s.as<uint16_t>(), r->b2.as<float>(), B, r->a3.as<__half>(), r->err.as<int>()));
     OCRB_TRY(launch_rec_fc_tc(ctx, r->a3.as<__half>(), r->w3s.as<uint16_t>(), r->b3.as<float>(), B, 1024, 512, 1, r->a4.as<float>(), r->err.as<int>()));
@@ -182,9 +192,9 @@ int rec_forward_device(ocrb_rec *r, const void *glyphs_dev, int is_u8, int B, fl
   OCRB_TRY(r->a2.reserve((size_t)B * 64 * 64 * 4));
   OCRB_TRY(r->a3.reserve((size_t)B * 1024 * 4));
   if (is_u8)
-    rec_conv1_pool_kernel<uint8_t, false><<<B, RC1_THREADS, 0, ctx->stream>>>((const uint8_t *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), r->a1.p);
+    rec_conv1_pool_kernel<uint8_t, false><<<rc1_grid, RC1_THREADS, 0, ctx->stream>>>((const uint8_t *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), B, r->a1.p);
   else
-    rec_conv1_pool_kernel<float, false><<<B, RC1_THREADS, 0, ctx->stream>>>((const float *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), r->a1.p);
+    rec_conv1_pool_kernel<float, false><<<rc1_grid, RC1_THREADS, 0, ctx->stream>>>((const float *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), B, r->a1.p);
   OCRB_TRY(check_launch(ctx, "rec_conv1_pool"));
   // conv2 5x5 32 -> 64 on [B][12][12][32] -> [B][8][8][64]
   OCRB_TRY(launch_conv_fp32(ctx, r->a1.as<float>(), B, 12, 12, 32, r->w2.as<float>(), 64, 5, 1, 0, r->one64.as<float>(), r->b2.as<float>(), nullptr, 0, r->a2.as<float>()));

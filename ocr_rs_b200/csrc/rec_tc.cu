@@ -46,15 +46,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volati
 // conv2 + pool2 + flatten
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int RC2_GLYPHS = 4;                        // per unit: 2 M tiles x 2 glyphs
-constexpr int RC2_BUILDERS = 256;                    // one A row per builder thread and tap
-constexpr int RC2_THREADS = RC2_BUILDERS + 32;       // + warp 8: TMA / MMA issuer
+constexpr int RC2_BUILDERS = 256;                    // warps 0-7: one A row per thread and tap
+constexpr int RC2_EPI = 128;                         // warps 9-12: epilogue (TMEM -> pool -> global)
+constexpr int RC2_THREADS = RC2_BUILDERS + 32 + RC2_EPI;  // warp 8: TMA / MMA issuer
 constexpr int RC2_ACT_BYTES = RC2_GLYPHS * 144 * 128;  // 73,728
 constexpr int RC2_A_STAGE = 2 * 128 * 128;           // two M tiles
+constexpr int RC2_A_STAGES = 3;
 constexpr int RC2_B_STAGE = 128 * 128;
+constexpr int RC2_B_STAGES = 3;                      // weight tiles are requested two taps ahead
 constexpr int RC2_OFF_A = RC2_ACT_BYTES;
-constexpr int RC2_OFF_B = RC2_OFF_A + 2 * RC2_A_STAGE;
-constexpr int RC2_OFF_BAR = RC2_OFF_B + 2 * RC2_B_STAGE;
-constexpr int RC2_SMEM = RC2_OFF_BAR + 128 + 1024;
+constexpr int RC2_OFF_B = RC2_OFF_A + RC2_A_STAGES * RC2_A_STAGE;
+constexpr int RC2_OFF_BAR = RC2_OFF_B + RC2_B_STAGES * RC2_B_STAGE;
+constexpr int RC2_SMEM = RC2_OFF_BAR + 256 + 1024;
 
 // act: [B][144][64] half (hi 32 | lo' 32 per pooled conv1 pixel); tmW: [25 taps x 128 rows][64] half
 // out: [B][2048] half = [hi(c * 16 + p) | lo'(c * 16 + p)]
@@ -67,22 +70,25 @@ rec_conv2_tc_kernel(const __half *__restrict__ act, const __grid_constant__ CUte
   uint8_t *sAct = smem;
   uint8_t *sA = smem + RC2_OFF_A;
   uint8_t *sB = smem + RC2_OFF_B;
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + RC2_OFF_BAR);  // [2]
-  uint64_t *empty = full + 2;                                         // [2]
-  uint64_t *tfull = empty + 2, *tempty = tfull + 1;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 1);
+  uint64_t *fullA = reinterpret_cast<uint64_t *>(smem + RC2_OFF_BAR);  // [2] builders -> MMA
+  uint64_t *emptyA = fullA + RC2_A_STAGES;                             // [2] MMA done with the A stage
+  uint64_t *fullB = emptyA + RC2_A_STAGES;                             // [4] TMA landed
+  uint64_t *emptyB = fullB + RC2_B_STAGES;                             // [4]
+  uint64_t *tfull = emptyB + RC2_B_STAGES, *tempty = tfull + 2;        // [2] accumulator sets
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int units = (B + RC2_GLYPHS - 1) / RC2_GLYPHS;
+  const int my_units = (int)blockIdx.x < units ? (units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (tid < 64) s_bias[tid] = bias[tid];
   if (tid == 0) {
     tma_prefetch_desc(&tmW);
-    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], RC2_BUILDERS + 1); mbar_init(&empty[s], 1); }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, RC2_BUILDERS);
+    for (int s = 0; s < RC2_A_STAGES; ++s) { mbar_init(&fullA[s], RC2_BUILDERS); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < RC2_B_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], RC2_EPI / 32); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -90,54 +96,55 @@ rec_conv2_tc_kernel(const __half *__restrict__ act, const __grid_constant__ CUte
 
   if (warp == 8) {
     // ================= TMA (weights) + MMA issuer =================
-    // the weight tile of iteration it + 1 is requested before the MMAs of iteration it are issued
     constexpr uint32_t idesc = make_idesc_f16(128);
-    const int my_units = blockIdx.x < units ? (units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const uint32_t total = (uint32_t)my_units * 25u;
     auto request_weights = [&](uint32_t it) {
-      const int s = it & 1;
-      mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1, err, 32);
+      const int s = it % RC2_B_STAGES;
+      mbar_wait(&emptyB[s], ((it / RC2_B_STAGES) & 1) ^ 1, err, 32);
       if (elect_one()) {
-        mbar_expect_tx(&full[s], RC2_B_STAGE);
-        tma_load_2d(sB + s * RC2_B_STAGE, &tmW, &full[s], 0, (int)(it % 25u) * 128);
+        mbar_expect_tx(&fullB[s], RC2_B_STAGE);
+        tma_load_2d(sB + s * RC2_B_STAGE, &tmW, &fullB[s], 0, (int)(it % 25u) * 128);
       }
       __syncwarp();
     };
-    if (total > 0) request_weights(0);
+    for (uint32_t it = 0; it < (uint32_t)(RC2_B_STAGES - 1) && it < total; ++it) request_weights(it);
     for (uint32_t it = 0; it < total; ++it) {
-      const int s = it & 1;
-      const uint32_t tap = it % 25u, unit_no = it / 25u;
-      if (it + 1 < total) request_weights(it + 1);
+      const int sa = it % RC2_A_STAGES, sb = it % RC2_B_STAGES;
+      const uint32_t tap = it % 25u, unit_no = it / 25u, acc = unit_no & 1;
+      if (it + RC2_B_STAGES - 1 < total) request_weights(it + RC2_B_STAGES - 1);
       if (tap == 0) {
-        // the accumulators are free once the builders' epilogue of the previous unit has read them
-        mbar_wait(tempty, (unit_no & 1) ^ 1, err, 31);
+        // this accumulator set is free once the epilogue of two units ago has read it
+        mbar_wait(&tempty[acc], ((unit_no >> 1) & 1) ^ 1, err, 31);
         tc_fence_after();
       }
-      mbar_wait(&full[s], (it >> 1) & 1, err, 33);
+      mbar_wait(&fullB[sb], (it / RC2_B_STAGES) & 1, err, 33);
+      mbar_wait(&fullA[sa], (it / RC2_A_STAGES) & 1, err, 36);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t bdesc = make_smem_desc(sB + s * RC2_B_STAGE);
+        const uint64_t bdesc = make_smem_desc(sB + sb * RC2_B_STAGE);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-          const uint64_t adesc = make_smem_desc(sA + s * RC2_A_STAGE + mt * 16384);
+          const uint64_t adesc = make_smem_desc(sA + sa * RC2_A_STAGE + mt * 16384);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + mt * 128, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (tap | (uint32_t)k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_base + acc * 256 + mt * 128, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (tap | (uint32_t)k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty[s]);
-        if (tap == 24) umma_commit(tfull);
+        umma_commit(&emptyA[sa]);
+        umma_commit(&emptyB[sb]);
+        if (tap == 24) umma_commit(&tfull[acc]);
       }
       __syncwarp();
     }
-  } else {
-    // ================= builders (A tiles) + epilogue =================
+  } else if (warp < 8) {
+    // ================= builders: the unit's activations -> shared memory, then one A row per thread and tap =================
     const int mt = tid >> 7, r = tid & 127;
     const int g_local = 2 * mt + (r >> 6), oy = (r >> 3) & 7, ox = r & 7;
     const uint32_t act_u32 = smem_u32(sAct), sA_u32 = smem_u32(sA);
-    uint32_t it = 0, unit_no = 0;
-    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++unit_no) {
+    uint32_t it = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
       const int g0 = unit * RC2_GLYPHS;
-      // ---- the unit's pooled conv1 maps -> shared memory (missing glyphs of the last unit: zeros)
+      // every builder has finished reading the previous unit's activations (its last A row is written)
+      named_bar_sync(1, RC2_BUILDERS);
       {
         const uint4 *src = reinterpret_cast<const uint4 *>(act + (int64_t)g0 * 144 * 64);
         const int valid16 = (B - g0 < RC2_GLYPHS ? B - g0 : RC2_GLYPHS) * (144 * 128 / 16);
@@ -145,80 +152,70 @@ rec_conv2_tc_kernel(const __half *__restrict__ act, const __grid_constant__ CUte
           reinterpret_cast<uint4 *>(sAct)[i] = i < valid16 ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
       }
       named_bar_sync(1, RC2_BUILDERS);
-      // ---- one A row per thread and tap: the 128-byte record of input pixel (oy + dy, ox + dx)
       for (int tap = 0; tap < 25; ++tap, ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
+        const int s = it % RC2_A_STAGES;
         const int dy = tap / 5, dx = tap - dy * 5;
         const uint32_t src = act_u32 + (uint32_t)((g_local * 144 + (oy + dy) * 12 + ox + dx) * 128);
         const uint32_t dst = sA_u32 + (uint32_t)(s * RC2_A_STAGE + mt * 16384 + r * 128);
-        mbar_wait(&empty[s], ph ^ 1, err, 34);
+        mbar_wait(&emptyA[s], ((it / RC2_A_STAGES) & 1) ^ 1, err, 34);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = (j + r) & 7;  // rotated start: the eight rows of a group hit different banks
           sts_16(dst + (uint32_t)((c ^ (r & 7)) << 4), lds_16(src + (uint32_t)(c << 4)));
         }
         fence_proxy_async();
-        mbar_arrive(&full[s]);
+        mbar_arrive(&fullA[s]);
       }
-      // ---- epilogue: main + 2^-11 * scaled + bias -> fp32 staging (over the A stages) -> 2x2 max-pool -> split halves
-      mbar_wait(tfull, unit_no & 1, err, 35);
+    }
+  } else {
+    // ================= epilogue: main + 2^-11 * scaled + bias -> 2x2 max-pool by warp shuffles -> split halves =================
+    // A warp reads TMEM lane quarter q = 32 GEMM rows = 4 output rows x 8 columns of one glyph: the pool partners of a
+    // pixel are lane ^ 1 (x) and lane ^ 8 (y), so no shared memory is needed.
+    const int q = warp & 3;
+    uint32_t unit_no = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++unit_no) {
+      const int g0 = unit * RC2_GLYPHS;
+      const uint32_t acc = unit_no & 1;
+      mbar_wait(&tfull[acc], (unit_no >> 1) & 1, err, 35);
       tc_fence_after();
-      {
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * 128);
-        const uint32_t stg = sA_u32 + (uint32_t)(tid * 256);  // [256 rows][64 floats], 16-byte chunks XOR-swizzled by row
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int row = q * 32 + lane;                 // GEMM row within the M tile
+        const int g = g0 + 2 * mt + (row >> 6);
+        const int oy = (row >> 3) & 7, ox = row & 7;
+        const bool writer = ((lane & 1) | (lane & 8)) == 0;  // even x, even y
+        const int p = (oy >> 1) * 4 + (ox >> 1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + (uint32_t)(mt * 128);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float m[32], sc[32];
           tmem_ld32(taddr + h * 32, m);
           tmem_ld32(taddr + 64 + h * 32, sc);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 v;
-            v.x = (m[4 * q + 0] + sc[4 * q + 0] * SPLIT_INV) + s_bias[h * 32 + 4 * q + 0];
-            v.y = (m[4 * q + 1] + sc[4 * q + 1] * SPLIT_INV) + s_bias[h * 32 + 4 * q + 1];
-            v.z = (m[4 * q + 2] + sc[4 * q + 2] * SPLIT_INV) + s_bias[h * 32 + 4 * q + 2];
-            v.w = (m[4 * q + 3] + sc[4 * q + 3] * SPLIT_INV) + s_bias[h * 32 + 4 * q + 3];
-            const int chunk = h * 8 + q;
-            sts_16(stg + (uint32_t)(((chunk & 8) | ((chunk ^ tid) & 7)) << 4), *reinterpret_cast<uint4 *>(&v));
+          for (int c = 0; c < 32; ++c) {
+            float v = (m[c] + sc[c] * SPLIT_INV) + s_bias[h * 32 + c];
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+            if (writer && g < B) {
+              __half hi, lo;
+              split_f16(v, hi, lo);
+              __half *o = out + (int64_t)g * 2048 + (h * 32 + c) * 16 + p;
+              o[0] = hi;
+              o[1024] = lo;
+            }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty);  // TMEM may be overwritten by the next unit's MMAs
-      named_bar_sync(1, RC2_BUILDERS);
-      {
-        // thread = (glyph, channel, quarter of the 16 pooled pixels): 4 glyphs x 64 x 4 = 1024 items over 256 threads
-        for (int item = tid; item < RC2_GLYPHS * 256; item += RC2_BUILDERS) {
-          const int c = item & 63, q = (item >> 6) & 3, g = item >> 8;
-          if (g0 + g >= B) continue;
-          __half hi[4], lo[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int p = 4 * q + k, py = p >> 2, px = p & 3;
-            float best = -INFINITY;
-#pragma unroll
-            for (int dd = 0; dd < 4; ++dd) {
-              const int row = g * 64 + (2 * py + (dd >> 1)) * 8 + 2 * px + (dd & 1);
-              const int chunk = c >> 2;
-              const float v = *reinterpret_cast<const float *>(sA + row * 256 + (((chunk & 8) | ((chunk ^ row) & 7)) << 4) + (c & 3) * 4);
-              best = fmaxf(best, v);
-            }
-            split_f16(best, hi[k], lo[k]);
-          }
-          __half *o = out + (int64_t)(g0 + g) * 2048 + c * 16 + 4 * q;
-          *reinterpret_cast<uint2 *>(o) = *reinterpret_cast<uint2 *>(hi);
-          *reinterpret_cast<uint2 *>(o + 1024) = *reinterpret_cast<uint2 *>(lo);
-        }
-      }
-      named_bar_sync(1, RC2_BUILDERS);  // the staging area becomes A stages again, sAct is reloaded
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
