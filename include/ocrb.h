@@ -151,6 +151,23 @@ const double *ocrb_polygons_scores(const ocrb_polygons *p);
 const int64_t *ocrb_polygons_stats(const ocrb_polygons *p);
 void ocrb_polygons_free(ocrb_polygons *p);
 
+/* ---- evaluation metrics (metrics.rs:191-394; host code, no device needed) -----------------------------
+ * MetricsItem (metrics.rs:22-30) */
+typedef struct ocrb_metrics_item {
+  double precision, recall, hmean;
+  int64_t gt_care, det_care, det_matched;
+} ocrb_metrics_item;
+/* get_intersection / get_union / get_intersection_over_union (metrics.rs:375-389): polygons as u32 (x,y) rings
+ * without the closing point; either output may be NULL */
+int ocrb_polygon_iou(const uint32_t *a_xy, int n_a, const uint32_t *b_xy, int n_b, double *intersection, double *iou);
+/* evaluate_image (metrics.rs:251-372): polygon g owns points [gt_offsets[g], gt_offsets[g+1]) of gt_xy (likewise the
+ * detections); ignore_flags[g] != 0 marks a don't-care ground-truth polygon.  validate_measure (metrics.rs:191-218) is
+ * this call per image on the detections with score >= 0.6. */
+int ocrb_evaluate_image(const int64_t *gt_offsets, const uint32_t *gt_xy, int n_gt, const uint8_t *ignore_flags,
+                        const int64_t *det_offsets, const uint32_t *det_xy, int n_det, ocrb_metrics_item *out);
+/* combine_results / gather_measure (metrics.rs:220-249) -> (precision, recall, hmean) */
+int ocrb_combine_results(const ocrb_metrics_item *items, int n, double *precision, double *recall, double *hmean);
+
 /* fine-grained test hooks of the contour stage (imageproc find_contours at
  * metrics.rs:78-81 and approximate_polygon_dp at :87-95) */
 /* 8-connected foreground labels, canonical raster-order numbering 1..n, 0 = background */

@@ -21,6 +21,11 @@ c_p = C.c_void_p
 i64 = C.c_int64
 
 
+class MetricsItem(C.Structure):
+    _fields_ = [("precision", C.c_double), ("recall", C.c_double), ("hmean", C.c_double),
+                ("gt_care", C.c_int64), ("det_care", C.c_int64), ("det_matched", C.c_int64)]
+
+
 class PostprocParams(C.Structure):
     _fields_ = [("thresh", C.c_double), ("box_thresh", C.c_double), ("min_size", C.c_double),
                 ("unclip_factor", C.c_double)]
@@ -91,6 +96,9 @@ SIGNATURES = {
     "ocrb_polygons_glyph_classes": (C.POINTER(C.c_int32), [c_p]),
     "ocrb_crop_glyphs": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, C.c_int, C.c_int, c_p]),
     "ocrb_detect_and_read_sharded": (C.c_int, [c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.POINTER(PostprocParams), C.c_int, C.POINTER(c_p)]),
+    "ocrb_polygon_iou": (C.c_int, [c_p, C.c_int, c_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ocrb_evaluate_image": (C.c_int, [c_p, c_p, C.c_int, c_p, c_p, c_p, C.c_int, C.POINTER(MetricsItem)]),
+    "ocrb_combine_results": (C.c_int, [C.POINTER(MetricsItem), C.c_int] + [C.POINTER(C.c_double)] * 3),
     "ocrb_shards_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_p), C.POINTER(i64), C.c_int,
                                      C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_p), C.POINTER(i64), C.POINTER(c_p)]),
     "ocrb_shards_create_from_files": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(c_p)]),

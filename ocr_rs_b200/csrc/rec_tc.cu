@@ -391,7 +391,7 @@ int launch_rec_conv2_tc(ocrb_ctx *ctx, const __half *act, const uint16_t *w_pack
   const int units = (B + RC2_GLYPHS - 1) / RC2_GLYPHS;
   const int grid = units < ctx->sm_count ? units : ctx->sm_count;
   rec_conv2_tc_kernel<<<grid, RC2_THREADS, RC2_SMEM, ctx->stream>>>(act, tmW, bias, B, out, err);
-  return check_launch(ctx, "tc:rec_conv2");
+  return check_launch(ctx, "rec_tc:conv2");
 }
 
 int launch_rec_fc_tc(ocrb_ctx *ctx, const __half *a_split, const uint16_t *w_packed, const float *bias, int M, int K, int N, int relu,
@@ -403,7 +403,7 @@ int launch_rec_fc_tc(ocrb_ctx *ctx, const __half *a_split, const uint16_t *w_pac
   const int units = ((M + 127) / 128) * (N / 128);
   const int grid = units < ctx->sm_count ? units : ctx->sm_count;
   rec_fc_tc_kernel<<<grid, RFC_THREADS, RFC_SMEM, ctx->stream>>>(tmA, tmB, bias, M, K, N, relu, out, err);
-  return check_launch(ctx, "tc:rec_fc1");
+  return check_launch(ctx, "rec_tc:fc1");
 }
 
 }  // namespace ocrb

@@ -140,3 +140,68 @@ def approx_polygon(chain, ctx=None):
     n = _ffi.i64(0)
     _ffi.check(_ffi.lib().ocrb_approx_polygon(ctx.handle, _ffi.ptr(c), len(c), _ffi.ptr(out), len(out), C.byref(n)))
     return out[: n.value].copy()
+
+
+# ---- evaluation metrics (metrics.rs:191-394; host code inside libocrb, no device needed) -----------------
+class MetricsItem:
+    """metrics.rs:22-30"""
+    __slots__ = ("precision", "recall", "hmean", "gt_care", "det_care", "det_matched")
+
+    def __init__(self, precision, recall, hmean, gt_care, det_care, det_matched):
+        self.precision, self.recall, self.hmean = precision, recall, hmean
+        self.gt_care, self.det_care, self.det_matched = gt_care, det_care, det_matched
+
+    def __repr__(self):
+        return (f"MetricsItem(precision={self.precision}, recall={self.recall}, hmean={self.hmean}, gt_care={self.gt_care}, "
+                f"det_care={self.det_care}, det_matched={self.det_matched})")
+
+
+def _csr(polys):
+    offs = np.zeros(len(polys) + 1, np.int64)
+    for i, p in enumerate(polys):
+        offs[i + 1] = offs[i] + len(p)
+    xy = (np.concatenate([np.asarray(p, np.uint32).reshape(-1, 2) for p in polys]) if len(polys) else np.zeros((0, 2), np.uint32))
+    return offs, np.ascontiguousarray(xy, np.uint32)
+
+
+def polygon_iou(a, b):
+    """get_intersection_over_union (metrics.rs:387-389) -> (intersection area, IoU)"""
+    a = np.ascontiguousarray(np.asarray(a, np.uint32).reshape(-1, 2))
+    b = np.ascontiguousarray(np.asarray(b, np.uint32).reshape(-1, 2))
+    inter, iou = C.c_double(), C.c_double()
+    _ffi.check(_ffi.lib().ocrb_polygon_iou(_ffi.ptr(a), len(a), _ffi.ptr(b), len(b), C.byref(inter), C.byref(iou)))
+    return inter.value, iou.value
+
+
+def evaluate_image(gt_points, ignore_flags, pred):
+    """metrics.rs:251-372: gt_points / pred = lists of polygons [(x, y)], ignore_flags = list of bool -> MetricsItem"""
+    go, gxy = _csr(gt_points)
+    do, dxy = _csr(pred)
+    ig = np.ascontiguousarray(np.asarray(ignore_flags, bool).astype(np.uint8))
+    item = _ffi.MetricsItem()
+    _ffi.check(_ffi.lib().ocrb_evaluate_image(_ffi.ptr(go), _ffi.ptr(gxy), len(gt_points), _ffi.ptr(ig) if len(ig) else None,
+                                              _ffi.ptr(do), _ffi.ptr(dxy), len(pred), C.byref(item)))
+    return MetricsItem(item.precision, item.recall, item.hmean, item.gt_care, item.det_care, item.det_matched)
+
+
+def validate_measure(polygons, ignore_tags, pred, scores):
+    """metrics.rs:191-218: per image, the predictions with score >= 0.6 against the ground truth"""
+    box_thresh = 0.6
+    out = []
+    for gt, ig, pr, sc in zip(polygons, ignore_tags, pred, scores):
+        kept = [p for s, p in zip(sc, pr) if s >= box_thresh]
+        out.append(evaluate_image(gt, ig, kept))
+    return out
+
+
+def combine_results(results):
+    """metrics.rs:229-249 -> (precision, recall, hmean)"""
+    arr = (_ffi.MetricsItem * len(results))(*[_ffi.MetricsItem(r.precision, r.recall, r.hmean, r.gt_care, r.det_care, r.det_matched) for r in results])
+    p, r, h = C.c_double(), C.c_double(), C.c_double()
+    _ffi.check(_ffi.lib().ocrb_combine_results(arr, len(results), C.byref(p), C.byref(r), C.byref(h)))
+    return p.value, r.value, h.value
+
+
+def gather_measure(metrics):
+    """metrics.rs:220-227: metrics = list (batches) of lists of MetricsItem"""
+    return combine_results([m for batch in metrics for m in batch])
