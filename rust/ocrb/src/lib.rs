@@ -1,0 +1,199 @@
+//! Drop-in replacements for the `pub fn`s ocr-rs's two drivers call, backed by libocrb.so.
+//! Names, argument meaning and error behaviour follow the reference; `tch::Tensor` arguments become slices /
+//! `GrayImage`s because the point of the exercise is to run WITHOUT libtorch.  Not compiled in the build image of this
+//! repository (it ships no Rust toolchain): the C ABI underneath is exercised by the Python and C++ mirrors, which are
+//! line-for-line the same calls.
+use anyhow::{anyhow, Result};
+use geo::{LineString, MultiPolygon, Polygon};
+use image::GrayImage;
+use ocrb_sys as sys;
+use std::ffi::{CStr, CString};
+use std::path::Path;
+use std::ptr;
+
+fn check(rc: i32) -> Result<()> {
+    if rc == sys::OCRB_OK {
+        return Ok(());
+    }
+    let msg = unsafe { CStr::from_ptr(sys::ocrb_last_error()) }.to_string_lossy().into_owned();
+    Err(anyhow!("libocrb error {}: {}", rc, msg))
+}
+
+/// Replaces the process-global `DEVICE` (main.rs:26-28): one context per (device, host thread).
+pub struct Ctx(*mut sys::ocrb_ctx);
+impl Ctx {
+    pub fn new(device: i32) -> Result<Self> {
+        let mut p = ptr::null_mut();
+        check(unsafe { sys::ocrb_ctx_create(device, &mut p) })?;
+        Ok(Ctx(p))
+    }
+    pub fn raw(&self) -> *mut sys::ocrb_ctx {
+        self.0
+    }
+}
+impl Drop for Ctx {
+    fn drop(&mut self) {
+        unsafe { sys::ocrb_ctx_destroy(self.0) };
+    }
+}
+
+/// `PolygonScores` (metrics.rs:32-35)
+pub struct PolygonScores {
+    pub polygons: Vec<MultiPolygon<u32>>,
+    pub scores: Vec<Vec<f64>>,
+    /// ocrb_detect_and_read only: classes of the glyph tiles cut from every polygon, `[polygon][tile]`
+    pub glyph_classes: Vec<Vec<Vec<i32>>>,
+}
+
+unsafe fn take_polygons(h: *mut sys::ocrb_polygons) -> PolygonScores {
+    let nb = sys::ocrb_polygons_num_images(h) as usize;
+    let io = std::slice::from_raw_parts(sys::ocrb_polygons_image_offsets(h), nb + 1);
+    let npoly = io[nb] as usize;
+    let po = std::slice::from_raw_parts(sys::ocrb_polygons_point_offsets(h), npoly + 1);
+    let (xy, sc): (&[u32], &[f64]) = if npoly > 0 {
+        (std::slice::from_raw_parts(sys::ocrb_polygons_xy(h), 2 * po[npoly] as usize),
+         std::slice::from_raw_parts(sys::ocrb_polygons_scores(h), npoly))
+    } else {
+        (&[], &[])
+    };
+    let k = sys::ocrb_polygons_glyphs_per_polygon(h) as usize;
+    let gc: &[i32] = if k > 0 && npoly > 0 { std::slice::from_raw_parts(sys::ocrb_polygons_glyph_classes(h), npoly * k) } else { &[] };
+    let mut out = PolygonScores { polygons: Vec::with_capacity(nb), scores: Vec::with_capacity(nb), glyph_classes: Vec::with_capacity(nb) };
+    for b in 0..nb {
+        let (mut polys, mut scores, mut classes) = (Vec::new(), Vec::new(), Vec::new());
+        for p in io[b] as usize..io[b + 1] as usize {
+            let pts: Vec<(u32, u32)> = (po[p] as usize..po[p + 1] as usize).map(|i| (xy[2 * i], xy[2 * i + 1])).collect();
+            polys.push(Polygon::new(LineString::from(pts), vec![])); // metrics.rs:111-121
+            scores.push(sc[p]);
+            if k > 0 {
+                classes.push(gc[p * k..(p + 1) * k].to_vec());
+            }
+        }
+        out.polygons.push(MultiPolygon::from(polys));
+        out.scores.push(scores);
+        out.glyph_classes.push(classes);
+    }
+    sys::ocrb_polygons_free(h);
+    out
+}
+
+pub mod image_ops {
+    use super::*;
+    /// image_ops::preprocess_image (image_ops.rs:188-220): the decode stays with the `image` crate, resize + luma + pad
+    /// run on the GPU.
+    pub fn preprocess_image<T: AsRef<Path>>(ctx: &Ctx, file_path: T, target_dim: (u32, u32)) -> Result<(GrayImage, f64, f64)> {
+        let rgba = image::open(file_path)?.into_rgba();
+        let (w, h) = target_dim;
+        let mut out = vec![0u8; (w * h) as usize];
+        let (mut ax, mut ay) = (0f64, 0f64);
+        check(unsafe {
+            sys::ocrb_preprocess_rgba(ctx.raw(), rgba.as_raw().as_ptr(), rgba.width() as i32, rgba.height() as i32, w as i32, h as i32,
+                                      out.as_mut_ptr(), &mut ax, &mut ay)
+        })?;
+        Ok((GrayImage::from_vec(w, h, out).unwrap(), ax, ay))
+    }
+}
+
+pub mod text_detection {
+    use super::*;
+
+    /// `resnet18(&vs.root())` + `vs.load(file)` (model.rs:154, text_detection/mod.rs:35-44): the VarStore archive is read
+    /// natively by the library.
+    pub struct Resnet18(*mut sys::ocrb_det);
+    impl Resnet18 {
+        pub fn load<T: AsRef<Path>>(ctx: &Ctx, model_file_path: T, bf16: bool) -> Result<Self> {
+            let path = CString::new(model_file_path.as_ref().to_string_lossy().as_bytes())?;
+            let mut p = ptr::null_mut();
+            check(unsafe { sys::ocrb_det_create_from_file(ctx.raw(), path.as_ptr(), if bf16 { sys::OCRB_MODE_BF16 } else { sys::OCRB_MODE_FP32 }, &mut p) })?;
+            Ok(Resnet18(p))
+        }
+        /// `net.forward_t(&images.view((b, 1, h, w)), false)` (text_detection/mod.rs:52-54): u8 grey levels in, f32 map out
+        pub fn forward_t(&self, images: &[u8], b: usize, h: usize, w: usize) -> Result<Vec<f32>> {
+            let mut prob = vec![0f32; b * h * w];
+            check(unsafe { sys::ocrb_det_forward(self.0, images.as_ptr() as *const _, sys::OCRB_U8, b as i32, h as i32, w as i32, prob.as_mut_ptr()) })?;
+            Ok(prob)
+        }
+        pub fn raw(&self) -> *mut sys::ocrb_det {
+            self.0
+        }
+    }
+    impl Drop for Resnet18 {
+        fn drop(&mut self) {
+            unsafe { sys::ocrb_det_destroy(self.0) };
+        }
+    }
+
+    pub mod metrics {
+        use super::super::*;
+        /// metrics.rs:37-56
+        pub fn get_boxes_and_box_scores(ctx: &Ctx, pred: &[f32], adjust_values: &[f64], b: usize, h: usize, w: usize) -> Result<PolygonScores> {
+            let mut out = ptr::null_mut();
+            check(unsafe { sys::ocrb_get_boxes_and_box_scores(ctx.raw(), pred.as_ptr(), adjust_values.as_ptr(), b as i32, h as i32, w as i32, ptr::null(), &mut out) })?;
+            Ok(unsafe { take_polygons(out) })
+        }
+        /// metrics.rs:150-184
+        pub fn box_score_fast(ctx: &Ctx, bitmap: &[f32], dim_m2: usize, dim_m1: usize, points: &[(i32, i32)]) -> Result<f64> {
+            let flat: Vec<i32> = points.iter().flat_map(|p| vec![p.0, p.1]).collect();
+            let mut s = 0f64;
+            check(unsafe { sys::ocrb_box_score_fast(ctx.raw(), bitmap.as_ptr(), dim_m2 as i32, dim_m1 as i32, flat.as_ptr(), points.len() as i32, &mut s) })?;
+            Ok(s)
+        }
+        /// metrics.rs:251-372
+        pub fn evaluate_image(gt: &MultiPolygon<u32>, ignore_flags: &[bool], pred: &MultiPolygon<u32>) -> Result<sys::ocrb_metrics_item> {
+            fn csr(mp: &MultiPolygon<u32>) -> (Vec<i64>, Vec<u32>) {
+                let (mut off, mut xy) = (vec![0i64], Vec::new());
+                for poly in &mp.0 {
+                    let ext = poly.exterior();
+                    for p in ext.points_iter().take(ext.num_coords() - 1) {
+                        xy.push(p.x());
+                        xy.push(p.y());
+                    }
+                    off.push((xy.len() / 2) as i64);
+                }
+                (off, xy)
+            }
+            let (go, gxy) = csr(gt);
+            let (do_, dxy) = csr(pred);
+            let ig: Vec<u8> = ignore_flags.iter().map(|&f| f as u8).collect();
+            let mut item = sys::ocrb_metrics_item::default();
+            check(unsafe { sys::ocrb_evaluate_image(go.as_ptr(), gxy.as_ptr(), gt.0.len() as i32, ig.as_ptr(), do_.as_ptr(), dxy.as_ptr(), pred.0.len() as i32, &mut item) })?;
+            Ok(item)
+        }
+    }
+}
+
+pub mod polygon {
+    use super::*;
+    /// polygon.rs:51-56 (`None` = the empty offset the reference `unwrap()`s)
+    pub fn expand_polygon(ctx: &Ctx, polygon: &[(i32, i32)], factor: f64) -> Result<Option<Vec<(i32, i32)>>> {
+        let flat: Vec<i32> = polygon.iter().flat_map(|p| vec![p.0, p.1]).collect();
+        let cap = 6 * polygon.len() + 32;
+        let mut out = vec![0i32; 2 * cap];
+        let mut n = 0i32;
+        check(unsafe { sys::ocrb_expand_polygon(ctx.raw(), flat.as_ptr(), polygon.len() as i32, factor, out.as_mut_ptr(), cap as i32, &mut n) })?;
+        Ok(if n == 0 { None } else { Some((0..n as usize).map(|i| (out[2 * i], out[2 * i + 1])).collect()) })
+    }
+}
+
+/// `run_text_detection` / the batched evaluation loop (text_detection/mod.rs:23, :188-204) plus recognition of the crops
+/// of every detected polygon, over all GPUs of the box: ocrb_detect_and_read_sharded.
+pub struct Shards(*mut sys::ocrb_shards);
+impl Shards {
+    pub fn load<T: AsRef<Path>>(devices: &[i32], det_model: T, rec_model: T, bf16: bool) -> Result<Self> {
+        let d = CString::new(det_model.as_ref().to_string_lossy().as_bytes())?;
+        let r = CString::new(rec_model.as_ref().to_string_lossy().as_bytes())?;
+        let mut p = ptr::null_mut();
+        check(unsafe { sys::ocrb_shards_create_from_files(devices.as_ptr(), devices.len() as i32, d.as_ptr(), r.as_ptr(), if bf16 { sys::OCRB_MODE_BF16 } else { sys::OCRB_MODE_FP32 }, &mut p) })?;
+        Ok(Shards(p))
+    }
+    pub fn detect_and_read(&self, images: &[u8], adjust: &[f64], b: usize, h: usize, w: usize, glyphs_per_polygon: i32) -> Result<PolygonScores> {
+        let mut out = ptr::null_mut();
+        check(unsafe { sys::ocrb_detect_and_read_sharded(self.0, images.as_ptr(), adjust.as_ptr(), b as i32, h as i32, w as i32, ptr::null(), glyphs_per_polygon, &mut out) })?;
+        Ok(unsafe { take_polygons(out) })
+    }
+}
+impl Drop for Shards {
+    fn drop(&mut self) {
+        unsafe { sys::ocrb_shards_destroy(self.0) };
+    }
+}

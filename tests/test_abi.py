@@ -58,3 +58,15 @@ def test_no_cpu_fallback(ffi):
     with pytest.raises(ffi.OcrbError) as e:
         ffi.Context(0)
     assert e.value.code == -2  # OCRB_ERR_CUDA
+
+
+def test_rust_sys_crate_is_in_sync_with_the_header():
+    """rust/ocrb-sys/src/lib.rs is generated from include/ocrb.h (tools/gen_rust_bindings.py): every declared symbol has an
+    `extern "C"` declaration and the committed file is what the generator emits today."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.call([sys.executable, os.path.join(root, "tools", "gen_rust_bindings.py"), "--check"]) == 0
+    rs = open(os.path.join(root, "rust", "ocrb-sys", "src", "lib.rs")).read()
+    assert sorted(re.findall(r"pub fn (ocrb_[a-z_0-9]+)\(", rs)) == _declared_symbols()
