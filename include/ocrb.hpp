@@ -49,6 +49,8 @@ using Polygon = std::vector<std::array<uint32_t, 2>>;  // geo::Polygon<u32> exte
 struct PolygonScores {
   std::vector<std::vector<Polygon>> polygons;  // Vec<MultiPolygon<u32>>: per image
   std::vector<std::vector<double>> scores;     // Vec<Vec<f64>>
+  // detect_and_read only: classes of the glyph tiles cut from every polygon, [image][polygon][tile]
+  std::vector<std::vector<std::vector<int32_t>>> glyph_classes;
 };
 
 namespace detail {
@@ -60,12 +62,16 @@ inline PolygonScores take(ocrb_polygons *h) {
   const double *sc = ocrb_polygons_scores(h);
   r.polygons.resize(n);
   r.scores.resize(n);
+  r.glyph_classes.resize(n);
+  const int gk = ocrb_polygons_glyphs_per_polygon(h);
+  const int32_t *gc = gk > 0 ? ocrb_polygons_glyph_classes(h) : nullptr;
   for (int b = 0; b < n; ++b)
     for (int64_t p = io[b]; p < io[b + 1]; ++p) {
       Polygon poly;
       for (int64_t k = po[p]; k < po[p + 1]; ++k) poly.push_back({xy[2 * k], xy[2 * k + 1]});
       r.polygons[b].push_back(std::move(poly));
       r.scores[b].push_back(sc[p]);
+      if (gc) r.glyph_classes[b].emplace_back(gc + p * gk, gc + (p + 1) * gk);
     }
   ocrb_polygons_free(h);
   return r;
@@ -240,5 +246,78 @@ inline PolygonScores detect_and_recognize(text_detection::model::Resnet18 &det, 
   check(ocrb_detect_and_recognize(det.raw(), rec ? rec->raw() : nullptr, images, adjust_values, b, h, w, nullptr, glyphs, n_glyphs, glyph_classes, &out));
   return detail::take(out);
 }
+
+// the same with the recognition net fed by the crop glue (README.md:20-26 "character segmentation"): glyphs_per_polygon
+// tiles cut from every kept polygon's min-area rectangle; PolygonScores::glyph_classes holds their classes
+inline PolygonScores detect_and_read(text_detection::model::Resnet18 &det, char_recognition::model::Net &rec, const uint8_t *images,
+                                     const double *adjust_values, int b, int h, int w, int glyphs_per_polygon = 4) {
+  ocrb_polygons *out = nullptr;
+  check(ocrb_detect_and_read(det.raw(), rec.raw(), images, adjust_values, b, h, w, nullptr, glyphs_per_polygon, &out));
+  return detail::take(out);
+}
+
+// evaluation metrics (metrics.rs:191-394); host code, no device needed
+namespace eval {
+using MetricsItem = ocrb_metrics_item;  // metrics.rs:22-30
+namespace detail {
+inline void csr(const std::vector<Polygon> &polys, std::vector<int64_t> &off, std::vector<uint32_t> &xy) {
+  off.assign(1, 0);
+  for (const Polygon &p : polys) {
+    for (const auto &q : p) { xy.push_back(q[0]); xy.push_back(q[1]); }
+    off.push_back((int64_t)xy.size() / 2);
+  }
+}
+}  // namespace detail
+// metrics.rs:251-372
+inline MetricsItem evaluate_image(const std::vector<Polygon> &gt_points, const std::vector<bool> &ignore_flags, const std::vector<Polygon> &pred) {
+  std::vector<int64_t> go, po;
+  std::vector<uint32_t> gxy, pxy;
+  detail::csr(gt_points, go, gxy);
+  detail::csr(pred, po, pxy);
+  std::vector<uint8_t> ig(ignore_flags.begin(), ignore_flags.end());
+  MetricsItem m{};
+  check(ocrb_evaluate_image(go.data(), gxy.data(), (int)gt_points.size(), ig.data(), po.data(), pxy.data(), (int)pred.size(), &m));
+  return m;
+}
+// metrics.rs:191-218
+inline std::vector<MetricsItem> validate_measure(const std::vector<std::vector<Polygon>> &polygons, const std::vector<std::vector<bool>> &ignore_tags,
+                                                 const std::vector<std::vector<Polygon>> &pred, const std::vector<std::vector<double>> &scores) {
+  std::vector<MetricsItem> out;
+  for (size_t i = 0; i < polygons.size(); ++i) {
+    std::vector<Polygon> kept;
+    for (size_t k = 0; k < pred[i].size(); ++k)
+      if (scores[i][k] >= 0.6) kept.push_back(pred[i][k]);
+    out.push_back(evaluate_image(polygons[i], ignore_tags[i], kept));
+  }
+  return out;
+}
+// metrics.rs:229-249 -> (precision, recall, hmean)
+inline std::array<double, 3> combine_results(const std::vector<MetricsItem> &results) {
+  std::array<double, 3> r{};
+  check(ocrb_combine_results(results.data(), (int)results.size(), &r[0], &r[1], &r[2]));
+  return r;
+}
+}  // namespace eval
+
+// several GPUs of one box from ONE process (text_detection/mod.rs:188-204 over ocrb_shards): model files are read natively
+class Shards {
+ public:
+  Shards(const std::vector<int> &devices, const std::string &det_model_file, const std::string &rec_model_file, bool bf16 = true) {
+    check(ocrb_shards_create_from_files(devices.data(), (int)devices.size(), det_model_file.c_str(), rec_model_file.empty() ? nullptr : rec_model_file.c_str(),
+                                        bf16 ? OCRB_MODE_BF16 : OCRB_MODE_FP32, &p_));
+  }
+  ~Shards() { if (p_) ocrb_shards_destroy(p_); }
+  Shards(const Shards &) = delete;
+  Shards &operator=(const Shards &) = delete;
+  int count() const { return ocrb_shards_count(p_); }
+  PolygonScores detect_and_read(const uint8_t *images, const double *adjust_values, int b, int h, int w, int glyphs_per_polygon = 4) {
+    ocrb_polygons *out = nullptr;
+    check(ocrb_detect_and_read_sharded(p_, images, adjust_values, b, h, w, nullptr, glyphs_per_polygon, &out));
+    return detail::take(out);
+  }
+
+ private:
+  ocrb_shards *p_ = nullptr;
+};
 
 }  // namespace ocr_rs

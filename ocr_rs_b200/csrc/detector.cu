@@ -30,6 +30,7 @@ int launch_nhwc_to_nchw_fp32(ocrb_ctx *, const float *, int, int, int, int, int,
 int launch_u8_to_f32(ocrb_ctx *, const uint8_t *, int64_t, float, float *);
 // stem_tc.cu
 int launch_stem_tc(ocrb_ctx *, const void *, int, int, int, int, const float *, const float *, const float *, __nv_bfloat16 *, int *);
+int launch_stem_tc2(ocrb_ctx *, const void *, int, int, int, int, const float *, const float *, const float *, __nv_bfloat16 *, int *);
 
 constexpr float BN_EPS = 1e-5f;  // tch nn::BatchNormConfig default
 
@@ -684,7 +685,13 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
 
   // stem
   static const bool stem_cuda_cores = getenv("OCRB_STEM") && strcmp(getenv("OCRB_STEM"), "cuda") == 0;
-  if (!stem_cuda_cores) {
+  // stem_tc2.cu (no im2col, register pooling) is correct but, at 13 k warp instructions per unit, issue-bound and no
+  // faster than stem_tc.cu (7.8 - 8.4 ms vs 7.2 ms per 1024 images): kept as the measured alternative, not the default
+  static const bool stem_v2 = getenv("OCRB_STEM") && strcmp(getenv("OCRB_STEM"), "v2") == 0;
+  if (!stem_cuda_cores && stem_v2) {
+    OCRB_TRY(launch_stem_tc2(ctx, img, sizeof(TIn) == 1, B, H, W, d->stem_w.as<float>(), d->stem_scale_h, d->stem_shift_h, x0,
+                             d->err.as<int>()));
+  } else if (!stem_cuda_cores) {
     OCRB_TRY(launch_stem_tc(ctx, img, sizeof(TIn) == 1, B, H, W, d->stem_w.as<float>(), d->stem_scale_h, d->stem_shift_h, x0,
                             d->err.as<int>()));
   } else {

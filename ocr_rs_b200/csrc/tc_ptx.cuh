@@ -50,6 +50,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
     }
   }
 }
+// the same for kernels whose waiting warps share the schedulers with instruction-bound working warps: a spinning waiter
+// takes issue slots from the warps it is waiting for, so it backs off between polls
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, int *err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  int polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if ((++polls & 1023) == 0 && clock64() - t0 > 4000000000ll) {
+      if (err) {
+        *reinterpret_cast<volatile int *>(err) = code;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
 // one lane of the (converged) warp; ptxas knows the predicate is warp-uniformly "exactly one",
 // which keeps the tcgen05 / TMA operands in uniform registers (no per-lane uniformisation loop)
 __device__ __forceinline__ bool elect_one() {
@@ -179,6 +196,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// asynchronous form: the registers are valid only after tmem_ld_wait16 on the SAME array (the "+r" operands make every
+// later use depend on the wait, so the compiler cannot hoist a use above it)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {

@@ -39,6 +39,20 @@ int main(int argc, char **argv) {
   REQUIRE(utils::class_to_char(0) == 'A' && utils::class_to_char(26) == 'a' && utils::class_to_char(52) == '0' && utils::class_to_char(62) == '?');
   int rw = 0, rh = 0;
   REQUIRE(ocrb_resize_dims(300, 200, 800, 800, &rw, &rh) == OCRB_OK && rw == 800 && rh == 533);  // image_ops.rs fixtures
+  {  // evaluation metrics are host code: the reference's KATs (metrics.rs:648-678, :814-856) through the mirror
+    const std::vector<Polygon> gt = {{{0, 0}, {10, 0}, {10, 10}, {0, 10}}, {{20, 20}, {30, 20}, {30, 30}, {20, 30}}};
+    const std::vector<Polygon> pred = {{{1, 1}, {10, 0}, {10, 10}, {0, 10}}};
+    const eval::MetricsItem m = eval::evaluate_image(gt, {false, false}, pred);
+    REQUIRE(m.gt_care == 2 && m.det_care == 1 && m.det_matched == 1);
+    REQUIRE(std::fabs(m.precision - 1.0) < 1e-15 && std::fabs(m.recall - 0.5) < 1e-15 && std::fabs(m.hmean - 0.6666666666666666) < 1e-15);
+    const eval::MetricsItem all_ignored = eval::evaluate_image(gt, {true, true}, pred);
+    REQUIRE(all_ignored.gt_care == 0 && all_ignored.det_care == 0 && all_ignored.precision == 1.0 && all_ignored.recall == 1.0);
+    const std::vector<eval::MetricsItem> items = {{1., 0.5, 0.6666666666666666, 2, 1, 1}, {1., 1., 1., 0, 0, 0}, {1., 1., 1., 2, 2, 2}, {0.3333333333333333, 0.2, 0.25, 5, 3, 1}};
+    const auto prh = eval::combine_results(items);
+    REQUIRE(prh[0] == 0.6666666666666666 && prh[1] == 0.4444444444444444 && prh[2] == 0.5333333333333333);
+    int64_t first = 0, count = 0;
+    REQUIRE(ocrb_shard_range(1024, 7, 8, &first, &count) == OCRB_OK && first == 896 && count == 128);
+  }
   int n_dev = 0;
   if (ocrb_device_count(&n_dev) != OCRB_OK || n_dev == 0) {
     bool threw = false;

@@ -42,6 +42,31 @@ def test_rec_logits_and_argmax(env, kind, n):
     assert (l2 == logits).all() and (a2 == argmax).all()
 
 
+def test_rec_fp32_cuda_core_path():
+    """OCRB_REC=fp32 (read once per process): the all-CUDA-core fp32 path of the glyph net gives the same classes and
+    logits within 1e-5 of the tensor-core fp16-split path's oracle."""
+    import os
+    import subprocess
+    import sys
+    script = r"""
+import numpy as np
+from ocr_rs_b200 import synth
+from ocr_rs_b200.char_recognition.model import Net
+from oracle import model_oracle as mo
+w = synth.make_rec_weights(1)
+g = synth.make_glyphs(777, 1, "strokes")
+logits, argmax, _ = Net(w).predict(g)
+ref = mo.rec_forward(w, g.astype(np.float32) / np.float32(255.0)).numpy()
+print("WORST", float(np.abs(logits - ref).max()), int((argmax != ref.argmax(-1)).sum()))
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OCRB_REC="fp32", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    out = subprocess.run([sys.executable, "-c", script], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    worst, mism = [l for l in out.stdout.splitlines() if l.startswith("WORST")][-1].split()[1:]
+    assert float(worst) <= 1e-5 and int(mism) == 0
+
+
 def test_rec_varstore_aliases_and_errors(env):
     _ffi, synth, Net, _, _, _ = env
     from ocr_rs_b200 import OcrbError, utils

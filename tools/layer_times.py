@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Per-kernel CUDA-event times of one detector forward (BF16 mode) of N device-resident 800x800 images, printed per
+1024 images.   python tools/layer_times.py [N] [name-filter]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ocr_rs_b200 import _ffi, synth  # noqa: E402
+from ocr_rs_b200.text_detection.model import resnet18  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+flt = sys.argv[2] if len(sys.argv) > 2 else ""
+ctx = _ffi.default_context(0)
+net = resnet18(synth.make_detector_weights(0, "structured"), "bf16", ctx)
+img = torch.from_numpy(synth.document_image_shard(0, n, 800, 800).reshape(n, 1, 800, 800)).cuda()
+out = torch.empty((n, 1, 800, 800), dtype=torch.float32, device="cuda")
+for _ in range(3):
+    net.forward_t(img, out=out)
+ctx.profile_begin()
+net.forward_t(img, out=out)
+prof = ctx.profile_end()
+tot = 0.0
+for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+    tot += ms
+    if flt in k:
+        print(f"{ms * 1024 / n:9.3f} ms/1024  x{c:3d}  {k}")
+print(f"{tot * 1024 / n:9.3f} ms/1024  total ({n} images)")
