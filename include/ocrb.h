@@ -84,6 +84,11 @@ int ocrb_ctx_profile_end(ocrb_ctx *ctx, char *buf, size_t cap, size_t *needed);
 int ocrb_resize_dims(int src_w, int src_h, int W, int H, int *resized_w, int *resized_h);
 int ocrb_preprocess_rgba(ocrb_ctx *ctx, const uint8_t *rgba, int src_w, int src_h, int W, int H,
                          uint8_t *out_gray, double *adjust_x, double *adjust_y);
+/* the same for a batch in ONE fused launch (the reference's u8 intermediate image lives in shared memory only):
+ * image i = RGBA8 [src_h[i]][src_w[i]][4] at byte offset src_offsets[i] (a multiple of 4) of `rgba`;
+ * out_gray [n][H][W], adjust [n][2] = (adjust_x, adjust_y) */
+int ocrb_preprocess_rgba_batch(ocrb_ctx *ctx, const uint8_t *rgba, const int64_t *src_offsets, const int *src_w, const int *src_h, int n,
+                               int W, int H, uint8_t *out_gray, double *adjust);
 /* image_ops::convert_image_to_tensor + to_kind(Float) (image_ops.rs:350-364,
  * text_detection/mod.rs:46-49): u8 -> f32, no scaling. */
 int ocrb_convert_image_to_tensor(ocrb_ctx *ctx, const uint8_t *image, int64_t n, float *out);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "ocrb_resize_dims": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int)] * 2),
     "ocrb_preprocess_rgba": (C.c_int, [c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p,
                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ocrb_preprocess_rgba_batch": (C.c_int, [c_p, c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p]),
     "ocrb_convert_image_to_tensor": (C.c_int, [c_p, c_p, i64, c_p]),
     "ocrb_convert_tensor_to_image": (C.c_int, [c_p, c_p, i64, C.c_float, c_p]),
     "ocrb_load_image_as_tensor": (C.c_int, [c_p, c_p, i64, c_p]),

@@ -1,5 +1,7 @@
 // C ABI: context, error reporting and the image_ops / binarize / CCL entry points.
 // (detector: detector.cu, recognition: rec.cu, post-processing: postproc.cu)
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ocrb {
@@ -20,6 +22,10 @@ int launch_binarize(ocrb_ctx *, const float *, int64_t, float, uint8_t *);
 int launch_u8_to_f32(ocrb_ctx *, const uint8_t *, int64_t, float, float *);
 int launch_f32_to_u8(ocrb_ctx *, const float *, int64_t, float, uint8_t *);
 int launch_preprocess(ocrb_ctx *, const uint8_t *, int, int, int, int, int, int, uint8_t *, uint8_t *);
+int launch_preprocess_batch(ocrb_ctx *, const uint8_t *, const void *, int, int, int, int, uint8_t *, int *);
+int launch_preprocess_batch_identity(ocrb_ctx *, const uint8_t *, const void *, int, int, int, uint8_t *);
+int preprocess_batch_span_limit();
+int preprocess_batch_tile_width();
 int ccl_canonical_labels(ocrb_ctx *, const uint8_t *, int, int, int, int *, int *);
 void free_pp(ocrb_ctx *);
 void free_pipe(ocrb_ctx *);
@@ -181,6 +187,59 @@ int ocrb_preprocess_rgba(ocrb_ctx *ctx, const uint8_t *rgba, int sw, int sh, int
   OCRB_TRY(ctx->stage[2].reserve((size_t)sw * rh * 4));
   OCRB_TRY(launch_preprocess(ctx, (const uint8_t *)src, sw, sh, rw, rh, W, H, ctx->stage[2].as<uint8_t>(), (uint8_t *)dst));
   OCRB_TRY(finish_output(ctx, out_gray, dst, (size_t)W * H));
+  return sync(ctx);
+}
+
+int ocrb_preprocess_rgba_batch(ocrb_ctx *ctx, const uint8_t *rgba, const int64_t *src_offsets, const int *src_w, const int *src_h, int n,
+                               int W, int H, uint8_t *out_gray, double *adjust) {
+  OCRB_REQUIRE(ctx && rgba && src_offsets && src_w && src_h && out_gray && adjust && n > 0 && W > 0 && H > 0, "bad argument");
+  OCRB_CUDA(cudaSetDevice(ctx->device));
+  struct PreImageH { int64_t src_off; int sw, sh, rw, rh; };
+  std::vector<PreImageH> im((size_t)n);
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    OCRB_REQUIRE(src_w[i] > 0 && src_h[i] > 0 && src_offsets[i] >= 0 && src_offsets[i] % 4 == 0, "image %d: bad size or offset", i);
+    im[i].src_off = src_offsets[i];
+    im[i].sw = src_w[i];
+    im[i].sh = src_h[i];
+    OCRB_TRY(ocrb_resize_dims(src_w[i], src_h[i], W, H, &im[i].rw, &im[i].rh));
+    adjust[2 * i] = (double)im[i].rw / (double)src_w[i];  // image_ops.rs:201-202
+    adjust[2 * i + 1] = (double)im[i].rh / (double)src_h[i];
+    const int64_t end = src_offsets[i] + (int64_t)src_w[i] * src_h[i] * 4;
+    total = end > total ? end : total;
+  }
+  const void *src = nullptr, *desc = nullptr;
+  void *dst = nullptr;
+  OCRB_TRY(to_device(ctx, 0, rgba, (size_t)total, &src));
+  OCRB_TRY(to_device(ctx, 3, im.data(), im.size() * sizeof(PreImageH), &desc));
+  OCRB_TRY(out_device(ctx, 1, out_gray, (size_t)n * W * H, &dst));
+  OCRB_TRY(ctx->stage[4].reserve(4));
+  OCRB_CUDA(cudaMemsetAsync(ctx->stage[4].p, 0, 4, ctx->stream));
+  // shared memory of the fused kernel = the source-column span of one output tile at the batch's largest horizontal
+  // down-scaling factor (+ the filter support on either side)
+  double worst = 1.0;
+  for (int i = 0; i < n; ++i) worst = std::max(worst, (double)im[i].sw / (double)im[i].rw);
+  const int span_cap = (int)(preprocess_batch_tile_width() * worst + 2.0 * worst + 8.0);
+  int overflow = span_cap > preprocess_batch_span_limit();
+  bool all_identity = W % 4 == 0;
+  for (int i = 0; i < n; ++i) all_identity = all_identity && im[i].rw == im[i].sw && im[i].rh == im[i].sh;
+  if (all_identity) {
+    OCRB_TRY(launch_preprocess_batch_identity(ctx, (const uint8_t *)src, desc, n, W, H, (uint8_t *)dst));
+    overflow = 0;
+  } else if (!overflow) {
+    OCRB_TRY(launch_preprocess_batch(ctx, (const uint8_t *)src, desc, n, W, H, span_cap, (uint8_t *)dst, ctx->stage[4].as<int>()));
+    OCRB_CUDA(cudaMemcpyAsync(&overflow, ctx->stage[4].p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    OCRB_TRY(sync(ctx));
+  }
+  if (overflow) {
+    // some image is scaled down by more than the fused kernel's tile span allows: the two-kernel path per image
+    for (int i = 0; i < n; ++i) {
+      OCRB_TRY(ctx->stage[2].reserve((size_t)im[i].sw * im[i].rh * 4));
+      OCRB_TRY(launch_preprocess(ctx, (const uint8_t *)src + im[i].src_off, im[i].sw, im[i].sh, im[i].rw, im[i].rh, W, H, ctx->stage[2].as<uint8_t>(),
+                                 (uint8_t *)dst + (size_t)i * W * H));
+    }
+  }
+  OCRB_TRY(finish_output(ctx, out_gray, dst, (size_t)n * W * H));
   return sync(ctx);
 }
 

@@ -8,14 +8,13 @@
 // (foreground) or — one pixel to the west — its hole border (background); SURVEY A.1.
 //
 // HBM traffic: reads the u8 bitmap (1 B/px) and writes i32 labels (4 B/px) in the local
-// pass; the seam and flatten passes touch labels again (documented in DESIGN.md).
+// pass — except for tiles without a foreground pixel, where only the tile origin's label is
+// written (ccl.cuh: ccl_parent answers for the rest); the seam pass touches border labels again.
+#include "ccl.cuh"
 #include "common.cuh"
 #include "scan.cuh"
 
 namespace ocrb {
-
-constexpr int CCL_TW = 32;  // tile width  (= warp size: one warp per tile row)
-constexpr int CCL_TH = 32;  // tile height (64 measured: local pass 4.1 -> 4.3 ms, seam 1.26 -> 1.15 ms per 1024 images: no gain)
 
 __device__ __forceinline__ int uf_find(const int *L, int a) {
   int p = L[a];
@@ -81,13 +80,9 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *_
   for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) any_fg |= fgv[k];
   const int none = !__syncthreads_or(any_fg);
   if (threadIdx.x == 0) tile_empty[blockIdx.x] = (uint8_t)none;  // lets the seam pass skip this tile's border without reading it
-  if (none) {
+  if (none) {  // only the origin's label exists in memory (ccl.cuh)
     const int origin = ty * CCL_TH * W + tx * CCL_TW;
-#pragma unroll
-    for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) {
-      const int y = ty * CCL_TH + warp * CCL_ROWS_PER_WARP + k;
-      if (x < W && y < H) labels[(int64_t)b * H * W + (int64_t)y * W + x] = origin;
-    }
+    if (threadIdx.x == 0) labels[(int64_t)b * H * W + origin] = origin;
     return;
   }
 #pragma unroll
@@ -180,15 +175,22 @@ __global__ void ccl_seam_kernel(const uint8_t *__restrict__ bitmap, int H, int W
   int *L = labels + b * HW;
   const int i = y * W + x;
   const int fg = bm[i] != 0;
-  if (on_left && x > 0 && (bm[i - 1] != 0) == fg) uf_union(L, i, i - 1);
+  // a pixel of a tile without foreground stands for its tile origin (the only label such a tile stores, ccl.cuh)
+  const uint8_t *te = tile_empty + (int64_t)b * tiles_x * tiles_y;
+  auto node = [&](int px, int py) {
+    const int ttx = px / CCL_TW, tty = py / CCL_TH;
+    return te[tty * tiles_x + ttx] ? tty * CCL_TH * W + ttx * CCL_TW : py * W + px;
+  };
+  const int self = node(x, y);
+  if (on_left && x > 0 && (bm[i - 1] != 0) == fg) uf_union(L, self, node(x - 1, y));
   if (y > 0) {
     const int n_fg = bm[i - W] != 0;
     if (on_top && n_fg == fg) {
       // same redundancy rule as the tile-local pass, along the whole image row
       const bool skip = x > 0 && (bm[i - 1] != 0) == fg && (bm[i - W - 1] != 0) == fg;
-      if (!skip) uf_union(L, i, i - W);
+      if (!skip) uf_union(L, self, node(x, y - 1));
     }
-    if (fg && !n_fg) {
+    if (fg && !n_fg) {  // foreground pixels are never in an "empty" tile
       if (x > 0 && (on_top || on_left) && bm[i - W - 1] != 0) uf_union(L, i, i - W - 1);
       if (x + 1 < W && (on_top || on_right) && bm[i - W + 1] != 0) uf_union(L, i, i - W + 1);
     }
@@ -196,14 +198,15 @@ __global__ void ccl_seam_kernel(const uint8_t *__restrict__ bitmap, int H, int W
 }
 
 // pass 3: flatten (every pixel points at its root = raster-first pixel of its component)
-__global__ void ccl_flatten_kernel(int H, int W, int B, int *__restrict__ labels) {
+__global__ void ccl_flatten_kernel(int H, int W, int B, int *__restrict__ labels, CclTiles tiles) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t HW = (int64_t)H * W;
   if (idx >= HW * B) return;
   int b = (int)(idx / HW);
   int i = (int)(idx % HW);
   int *L = labels + b * HW;
-  int root = uf_find_volatile(L, i);
+  // roots are final here and only non-root entries are rewritten, so concurrent walks see consistent chains
+  const int root = ccl_find_px(L, tiles, b, i, W);
   L[i] = root;
 }
 
@@ -220,7 +223,8 @@ int launch_ccl(ocrb_ctx *ctx, const uint8_t *bitmap, int B, int H, int W, int *l
   ccl_seam_kernel<<<(unsigned)cdiv(blocks * (CCL_TW + 2 * CCL_TH), 256), 256, 0, ctx->stream>>>(bitmap, H, W, B, tiles_x, tiles_y, labels, tile_empty);
   OCRB_TRY(check_launch(ctx, "ccl_seam"));
   if (!flatten) return OCRB_OK;
-  ccl_flatten_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(H, W, B, labels);
+  CclTiles tiles = {tile_empty, tiles_x, tiles_x * tiles_y};
+  ccl_flatten_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(H, W, B, labels, tiles);
   return check_launch(ctx, "ccl_flatten");
 }
 

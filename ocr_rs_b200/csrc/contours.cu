@@ -14,6 +14,7 @@
 //     borders of this component have been traced so far";
 //   * a chain is a pure function of (bitmap, start pixel, start direction).
 // Contours are emitted in raster order of their start pixel, like the reference.
+#include "ccl.cuh"
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -36,7 +37,7 @@ __device__ __forceinline__ int ccl_find(const int *__restrict__ L, int a) {
 // frame pixels only: background components reaching the frame are "open" (no hole border);
 // a foreground root in column 0 means a left-anchored component exists (slow path needed)
 __global__ void contour_frame_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels, int H, int W, int B,
-                                     uint8_t *__restrict__ bg_open, int *__restrict__ need_anchored) {
+                                     uint8_t *__restrict__ bg_open, int *__restrict__ need_anchored, CclTiles tiles) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int per = 2 * W + 2 * H;
   if (t >= (int64_t)per * B) return;
@@ -49,7 +50,7 @@ __global__ void contour_frame_kernel(const uint8_t *__restrict__ bitmap, const i
   const int64_t HW = (int64_t)H * W;
   const int i = y * W + x;
   const int *L = labels + b * HW;
-  if (bitmap[b * HW + i] == 0) bg_open[b * HW + ccl_find(L, i)] = 1;
+  if (bitmap[b * HW + i] == 0) bg_open[b * HW + ccl_find_px(L, tiles, b, i, W)] = 1;  // a background pixel may sit in a tile that stores no labels
   else if (x == 0 && L[i] == i) *need_anchored = 1;
 }
 
@@ -83,7 +84,7 @@ __global__ void contour_bbox_init_kernel(int4 *bbox, int64_t n, int *need_anchor
 // closed-form starts for ordinary components: outer = a foreground root outside column 0;
 // hole = the pixel west of a closed background component's root
 __global__ void contour_start_flags_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels, int H, int W,
-                                           int B, const uint8_t *__restrict__ bg_open, uint8_t *__restrict__ flags) {
+                                           int B, const uint8_t *__restrict__ bg_open, uint8_t *__restrict__ flags, CclTiles tiles) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t HW = (int64_t)H * W;
   if (idx >= HW * B) return;
@@ -93,7 +94,7 @@ __global__ void contour_start_flags_kernel(const uint8_t *__restrict__ bitmap, c
   if (bitmap[idx] != 0) {
     if (labels[idx] == i) {
       if (x != 0) f = START_OUTER;  // a root in column 0 is left-anchored: replayed by contour_anchored_kernel
-    } else if (x + 1 < W && bitmap[idx + 1] == 0 && labels[idx + 1] == i + 1 && !bg_open[idx + 1]) {
+    } else if (x + 1 < W && bitmap[idx + 1] == 0 && ccl_parent(labels + (idx - i), tiles, (int)(idx / HW), i + 1, W) == i + 1 && !bg_open[idx + 1]) {
       const int root = ccl_find(labels + (idx - i), i);
       if (root % W != 0) f = START_HOLE;
     }
@@ -104,7 +105,7 @@ __global__ void contour_start_flags_kernel(const uint8_t *__restrict__ bitmap, c
 // same, 4 pixels per thread (W % 4 == 0): one 32-bit bitmap load decides whether the labels are
 // needed at all, and the flags go out as one 32-bit store
 __global__ void contour_start_flags_vec4_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels, int H, int W,
-                                                int B, const uint8_t *__restrict__ bg_open, uint8_t *__restrict__ flags) {
+                                                int B, const uint8_t *__restrict__ bg_open, uint8_t *__restrict__ flags, CclTiles tiles) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t HW = (int64_t)H * W;
   if (q * 4 >= HW * B) return;
@@ -126,7 +127,8 @@ __global__ void contour_start_flags_vec4_kernel(const uint8_t *__restrict__ bitm
       } else if (x + 1 < W) {
         const bool east_bg = k < 3 ? ((bm >> (8 * (k + 1))) & 0xffu) == 0 : bitmap[idx0 + 4] == 0;
         if (east_bg) {
-          const int east_lab = k < 3 ? labs[k + 1] : labels[idx0 + 4];
+          // inside this 4-pixel group the east pixel shares the tile of a foreground pixel; across groups it may not
+          const int east_lab = k < 3 ? labs[k + 1] : ccl_parent(labels + (idx0 - i0), tiles, (int)(idx0 / HW), i + 1, W);
           if (east_lab == i + 1 && !bg_open[idx0 + k + 1]) {
             const int root = ccl_find(labels + (idx0 - i0), i);
             if (root % W != 0) f = START_HOLE;
@@ -145,7 +147,7 @@ __global__ void contour_start_flags_vec4_kernel(const uint8_t *__restrict__ bitm
 constexpr int FLAGS16_THREADS = SCAN_TILE / 16;
 __global__ void __launch_bounds__(FLAGS16_THREADS) contour_start_flags_vec16_kernel(const uint8_t *__restrict__ bitmap, const int *__restrict__ labels,
                                                                                     int H, int W, int B, const uint8_t *__restrict__ bg_open,
-                                                                                    uint8_t *__restrict__ flags, int *__restrict__ tile_counts) {
+                                                                                    uint8_t *__restrict__ flags, int *__restrict__ tile_counts, CclTiles tiles) {
   __shared__ int s_cnt[FLAGS16_THREADS / 32];
   const int64_t idx0 = ((int64_t)blockIdx.x * FLAGS16_THREADS + threadIdx.x) * 16;
   const int64_t HW = (int64_t)H * W;
@@ -174,7 +176,8 @@ __global__ void __launch_bounds__(FLAGS16_THREADS) contour_start_flags_vec16_ker
             const int64_t e = idx0 + 4 * w + k + 1;  // east neighbour
             const bool east_bg = k < 3 ? ((bm >> (8 * (k + 1))) & 0xffu) == 0 : (w < 3 ? (bmw[(w + 1) & 3] & 0xffu) == 0 : bitmap[e] == 0);
             if (east_bg) {
-              const int east_lab = k < 3 ? labs[k + 1] : labels[e];
+              // a 4-pixel group never straddles a tile, so labs[] are stored labels; the next group may lie in a tile that stores none
+              const int east_lab = k < 3 ? labs[k + 1] : ccl_parent(labels + (idx0 - i0), tiles, (int)(idx0 / HW), i + 1, W);
               if (east_lab == i + 1 && !bg_open[e]) {
                 const int root = ccl_find(labels + (idx0 - i0), i);
                 if (root % W != 0) f = START_HOLE;
@@ -207,7 +210,8 @@ __global__ void __launch_bounds__(128) contour_anchored_kernel(const uint8_t *__
                                                                int H, int W, int B, const uint8_t *__restrict__ bg_open,
                                                                const int4 *__restrict__ anchored_bbox, const int *__restrict__ need_anchored,
                                                                uint8_t *__restrict__ hole_traced, uint8_t *__restrict__ flags,
-                                                               int *__restrict__ tile_counts /* per-SCAN_TILE start counts to keep current, or null */) {
+                                                               int *__restrict__ tile_counts /* per-SCAN_TILE start counts to keep current, or null */,
+                                                               CclTiles tiles) {
   if (*need_anchored == 0) return;
   const int lane = threadIdx.x & 31;
   int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(128) contour_anchored_kernel(const uint8_t *__
           lab[k] = -2;  // not background
           if (nx < 0 || ny < 0 || nx >= W || ny >= H) lab[k] = -1;
           else if (bm[ny * W + nx] == 0) {
-            int r = ccl_find(L, ny * W + nx);
+            int r = ccl_find_px(L, tiles, (int)b, ny * W + nx, W);
             lab[k] = open[r] ? -1 : r;
           }
           if (lab[k] == -1) visited |= traced_inf;
@@ -468,27 +472,30 @@ int launch_contour_starts(ocrb_ctx *ctx, const uint8_t *bitmap, const int *label
                           int4 *anchored_bbox /*B*H*/, uint8_t *flags /*B*HW*/, int *need_anchored /*device int*/,
                           int *tile_counts /* cdiv(B*HW, SCAN_TILE) ints: start flags per scan tile */) {
   int64_t n = (int64_t)B * H * W;
+  // the labelling that produced `labels` left its per-tile "no foreground" flags in the ctx (launch_ccl)
+  const int tiles_x = (int)cdiv(W, CCL_TW), tiles_y = (int)cdiv(H, CCL_TH);
+  const CclTiles tiles = {ctx->ccl_tile_empty.as<uint8_t>(), tiles_x, tiles_x * tiles_y};
   OCRB_CUDA(cudaMemsetAsync(bg_open, 0, n, ctx->stream));
   OCRB_CUDA(cudaMemsetAsync(hole_traced, 0, n, ctx->stream));
   contour_bbox_init_kernel<<<(unsigned)cdiv((int64_t)B * H, 256), 256, 0, ctx->stream>>>(anchored_bbox, (int64_t)B * H, need_anchored);
   OCRB_TRY(check_launch(ctx, "contour_bbox_init"));
-  contour_frame_kernel<<<(unsigned)cdiv((int64_t)B * (2 * W + 2 * H), 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, need_anchored);
+  contour_frame_kernel<<<(unsigned)cdiv((int64_t)B * (2 * W + 2 * H), 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, need_anchored, tiles);
   OCRB_TRY(check_launch(ctx, "contour_frame"));
   contour_props_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, need_anchored, anchored_bbox);
   OCRB_TRY(check_launch(ctx, "contour_props"));
   const bool counted = W % 16 == 0;  // the flags kernel counts per tile itself
   if (counted)
     contour_start_flags_vec16_kernel<<<(unsigned)cdiv(n, SCAN_TILE), FLAGS16_THREADS, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, flags,
-                                                                                                       tile_counts);
+                                                                                                       tile_counts, tiles);
   else if (W % 4 == 0)
-    contour_start_flags_vec4_kernel<<<(unsigned)cdiv(n / 4, 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, flags);
+    contour_start_flags_vec4_kernel<<<(unsigned)cdiv(n / 4, 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, flags, tiles);
   else
-    contour_start_flags_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, flags);
+    contour_start_flags_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open, flags, tiles);
   OCRB_TRY(check_launch(ctx, "contour_start_flags"));
   int64_t warps = (int64_t)B * H;
   contour_anchored_kernel<<<(unsigned)cdiv(warps * 32, 128), 128, 0, ctx->stream>>>(bitmap, labels, H, W, B, bg_open,
                                                                                     anchored_bbox, need_anchored, hole_traced, flags,
-                                                                                    counted ? tile_counts : nullptr);
+                                                                                    counted ? tile_counts : nullptr, tiles);
   OCRB_TRY(check_launch(ctx, "contour_anchored"));
   if (!counted) {
     scan_tile_reduce_kernel<uint8_t, int, ScanNonZero><<<(unsigned)cdiv(n, SCAN_TILE), SCAN_THREADS, 0, ctx->stream>>>(flags, n, tile_counts);

@@ -34,6 +34,35 @@ def preprocess_image(rgba, target_dim, ctx=None):
     return out, ax.value, ay.value
 
 
+def preprocess_images(rgbas, target_dim, ctx=None, out=None):
+    """preprocess_image for a batch in one fused launch (ocrb_preprocess_rgba_batch).
+    rgbas: list of uint8 [h_i, w_i, 4] arrays, or a tuple (packed uint8 buffer (numpy / torch, host or cuda), offsets int64 [n],
+    widths int32 [n], heights int32 [n]).  -> (uint8 [n, height, width], adjust float64 [n, 2])"""
+    ctx = _ctx(ctx)
+    W, H = int(target_dim[0]), int(target_dim[1])
+    if isinstance(rgbas, tuple):
+        buf, offs, ws, hs = rgbas
+        offs = np.ascontiguousarray(offs, np.int64)
+        ws, hs = np.ascontiguousarray(ws, np.int32), np.ascontiguousarray(hs, np.int32)
+    else:
+        arrs = [np.ascontiguousarray(a, np.uint8) for a in rgbas]
+        for a in arrs:
+            if a.ndim != 3 or a.shape[2] != 4:
+                raise ValueError("expected RGBA8 images [h, w, 4]")
+        offs = np.zeros(len(arrs), np.int64)
+        offs[1:] = np.cumsum([a.size for a in arrs[:-1]])
+        buf = np.concatenate([a.reshape(-1) for a in arrs])
+        ws = np.array([a.shape[1] for a in arrs], np.int32)
+        hs = np.array([a.shape[0] for a in arrs], np.int32)
+    n = len(offs)
+    if out is None:
+        out = np.empty((n, H, W), np.uint8)
+    adj = np.empty((n, 2), np.float64)
+    _ffi.check(_ffi.lib().ocrb_preprocess_rgba_batch(ctx.handle, _ffi.ptr(buf), _ffi.ptr(offs), _ffi.ptr(ws), _ffi.ptr(hs), n, W, H,
+                                                     _ffi.ptr(out), _ffi.ptr(adj)))
+    return out, adj
+
+
 def convert_image_to_tensor(image, ctx=None, out=None):
     """GrayImage uint8 [H, W] -> float32 tensor [H, W] (the reference builds f64 then
     .to_kind(Float); values are 0..255, no scaling)."""

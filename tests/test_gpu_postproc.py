@@ -237,3 +237,27 @@ def test_image_ops_vs_oracle(api, preprocessed):
     t = rng.uniform(0, 1, size=(33, 47)).astype(np.float32)
     assert (image_ops.convert_tensor_to_image(t, 255.0) == (t * np.float32(255.0)).astype(np.uint8)).all()
     assert (image_ops.load_image_as_tensor(img) == (img.astype(np.float32) / np.float32(255.0)).reshape(1, -1)).all()
+
+
+def test_preprocess_batch_vs_oracle(api, preprocessed):
+    """ocrb_preprocess_rgba_batch (one fused launch, the u8 intermediate in shared memory only) is bit-identical to the
+    oracle's two-pass resize + luma + pad per image: the reference's JPEG sources, identity, up- and down-scaling,
+    portrait / landscape, and a down-scaling factor beyond the fused kernel's tile span (fallback path)."""
+    from ocr_rs_b200 import image_ops
+    _, _, synth, pp = api
+    rng = np.random.default_rng(3)
+    imgs = [preprocessed["src_img55"], preprocessed["src_img545"]]
+    for (h, w) in ((800, 800), (1600, 1600), (533, 800), (2400, 1100), (97, 1311), (64, 64), (3, 5)):
+        imgs.append(rng.integers(0, 256, (h, w, 4), dtype=np.uint8))
+    got, adj = image_ops.preprocess_images(imgs, (800, 800))
+    for i, im in enumerate(imgs):
+        want, ax, ay = pp.preprocess(im, 800, 800)
+        assert (got[i] == want).all(), (i, im.shape)
+        assert (adj[i] == (ax, ay)).all()
+        one, ax1, ay1 = image_ops.preprocess_image(im, (800, 800))
+        assert (one == want).all()
+    # beyond the tile span: 12 x down-scaling of a wide strip
+    wide = [rng.integers(0, 256, (80, 9600, 4), dtype=np.uint8), imgs[2]]
+    got, _ = image_ops.preprocess_images(wide, (800, 800))
+    for i, im in enumerate(wide):
+        assert (got[i] == pp.preprocess(im, 800, 800)[0]).all()
