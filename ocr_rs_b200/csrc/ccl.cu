@@ -56,34 +56,18 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b) {
 // ---------------------------------------------------------------------------------------
 constexpr int CCL_THREADS = 256;
 constexpr int CCL_ROWS_PER_WARP = CCL_TH / (CCL_THREADS / 32);
+constexpr int CCL_STRIP = 4;  // tiles per CTA: a 32-row x 128-column strip
 
-__global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *__restrict__ bitmap, int H, int W,
-                                                                 int tiles_x, int tiles_y, int *__restrict__ labels,
-                                                                 uint8_t *__restrict__ tile_empty) {
-  __shared__ int L[CCL_TW * CCL_TH];
-  __shared__ uint32_t rowbits[CCL_TH], rowvalid[CCL_TH];
+// one tile with foreground: union-find in shared memory (L: CCL_TW * CCL_TH ints)
+__device__ __forceinline__ void ccl_tile(const uint8_t *__restrict__ bm, int H, int W, int tx, int ty, int *__restrict__ labels_img, int *L,
+                                         uint32_t *rowbits, uint32_t *rowvalid) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tile = blockIdx.x % (tiles_x * tiles_y), b = blockIdx.x / (tiles_x * tiles_y);
-  const int tx = tile % tiles_x, ty = tile / tiles_x;
   const int x = tx * CCL_TW + lane;
-  const uint8_t *bm = bitmap + (int64_t)b * H * W;
   int fgv[CCL_ROWS_PER_WARP];
 #pragma unroll
-  for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) {  // all loads first
+  for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) {  // all loads first (the strip pass just touched these lines: L1 hits)
     const int y = ty * CCL_TH + warp * CCL_ROWS_PER_WARP + k;
     fgv[k] = (x < W && y < H) ? (bm[(int64_t)y * W + x] != 0) : 0;
-  }
-  // Tiles without a foreground pixel (most of a document page) are one 4-connected background
-  // rectangle: every pixel points at the tile origin, no union-find needed.
-  int any_fg = 0;
-#pragma unroll
-  for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) any_fg |= fgv[k];
-  const int none = !__syncthreads_or(any_fg);
-  if (threadIdx.x == 0) tile_empty[blockIdx.x] = (uint8_t)none;  // lets the seam pass skip this tile's border without reading it
-  if (none) {  // only the origin's label exists in memory (ccl.cuh)
-    const int origin = ty * CCL_TH * W + tx * CCL_TW;
-    if (threadIdx.x == 0) labels[(int64_t)b * H * W + origin] = origin;
-    return;
   }
 #pragma unroll
   for (int k = 0; k < CCL_ROWS_PER_WARP; ++k) {
@@ -130,8 +114,58 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *_
     if (x < W && y < H) {
       const int root = uf_find(L, r * CCL_TW + lane);
       const int rx = tx * CCL_TW + (root & 31), ry = ty * CCL_TH + (root >> 5);
-      labels[(int64_t)b * H * W + (int64_t)y * W + x] = ry * W + rx;
+      labels_img[(int64_t)y * W + x] = ry * W + rx;
     }
+  }
+  __syncthreads();  // L / rowbits are reused by the strip's next tile
+}
+
+// One CTA per strip of CCL_STRIP tiles.  The strip is read once with 16-byte loads (thread = row, 16-pixel chunk) to find
+// the tiles that hold foreground at all: on a document page most do not, and such a tile is one 4-connected background
+// rectangle — only its origin's label is stored (ccl.cuh).  Tiles with foreground run the union-find one after another.
+__global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *__restrict__ bitmap, int H, int W,
+                                                                 int tiles_x, int tiles_y, int strips_x, int *__restrict__ labels,
+                                                                 uint8_t *__restrict__ tile_empty) {
+  __shared__ int L[CCL_TW * CCL_TH];
+  __shared__ uint32_t rowbits[CCL_TH], rowvalid[CCL_TH];
+  __shared__ int s_any[CCL_STRIP];
+  const int strips = strips_x * tiles_y;
+  const int strip = blockIdx.x % strips, b = blockIdx.x / strips;
+  const int sx = strip % strips_x, ty = strip / strips_x;
+  const uint8_t *bm = bitmap + (int64_t)b * H * W;
+  int *labels_img = labels + (int64_t)b * H * W;
+  if (threadIdx.x < CCL_STRIP) s_any[threadIdx.x] = 0;
+  __syncthreads();
+  {
+    const int r = threadIdx.x >> 3, c = threadIdx.x & 7;  // 32 rows x 8 chunks of 16 pixels
+    const int y = ty * CCL_TH + r, x = sx * CCL_STRIP * CCL_TW + c * 16;
+    bool nz = false;
+    if (y < H && x < W) {
+      const uint8_t *p = bm + (int64_t)y * W + x;
+      if (x + 16 <= W && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p);
+        nz = (v.x | v.y | v.z | v.w) != 0;
+      } else {
+        for (int e = 0; e < 16 && x + e < W; ++e) nz |= p[e] != 0;
+      }
+    }
+    if (nz) s_any[c >> 1] = 1;  // benign race: every writer stores 1
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int t = 0; t < CCL_STRIP; ++t) {
+    const int tx = sx * CCL_STRIP + t;
+    if (tx >= tiles_x) break;
+    const int any_fg = s_any[t];
+    if (threadIdx.x == 0) tile_empty[(int64_t)b * tiles_x * tiles_y + ty * tiles_x + tx] = (uint8_t)!any_fg;  // the seam pass and the label consumers read this
+    if (!any_fg) {
+      if (threadIdx.x == 0) {
+        const int origin = ty * CCL_TH * W + tx * CCL_TW;
+        labels_img[origin] = origin;  // the only label an empty tile stores
+      }
+      continue;
+    }
+    ccl_tile(bm, H, W, tx, ty, labels_img, L, rowbits, rowvalid);
   }
 }
 
@@ -139,60 +173,62 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *_
 // pass 2: seams.  A pixel whose W / NW / N / NE neighbour lies in another tile unites with
 // it in global memory (same adjacency rules as pass 1).
 // ---------------------------------------------------------------------------------------
+// One warp per tile; its lanes walk the tile's border pixels (top row, left column, right column).  A tile without
+// foreground whose left and upper neighbours have none either needs exactly one link (its corner pixel): one lane works,
+// nothing else is even read — on a document page that is almost every tile.
 __global__ void ccl_seam_kernel(const uint8_t *__restrict__ bitmap, int H, int W, int B, int tiles_x, int tiles_y,
                                 int *__restrict__ labels, const uint8_t *__restrict__ tile_empty) {
-  // one thread per tile-border pixel: top row + left column + right column of every tile
   constexpr int PER_TILE = CCL_TW + 2 * CCL_TH;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t tiles = (int64_t)tiles_x * tiles_y * B;
-  if (t >= tiles * PER_TILE) return;
-  const int k = (int)(t % PER_TILE);
-  const int64_t tile = t / PER_TILE;
+  if (tile >= tiles) return;
   const int b = (int)(tile / ((int64_t)tiles_x * tiles_y));
   const int tt = (int)(tile % ((int64_t)tiles_x * tiles_y));
   const int tx = tt % tiles_x, ty = tt / tiles_x;
-  int x, y;
-  if (k < CCL_TW) { x = tx * CCL_TW + k; y = ty * CCL_TH; }
-  else if (k < CCL_TW + CCL_TH) { x = tx * CCL_TW; y = ty * CCL_TH + (k - CCL_TW); }
-  else { x = tx * CCL_TW + CCL_TW - 1; y = ty * CCL_TH + (k - CCL_TW - CCL_TH); }
-  if (x >= W || y >= H) return;
-  const bool on_left = (x % CCL_TW) == 0, on_right = (x % CCL_TW) == CCL_TW - 1, on_top = (y % CCL_TH) == 0;
-  // corner pixels appear in two of the three groups: let the top-row instance do the work
-  if (k >= CCL_TW && on_top) return;
-  // Tiles without foreground are single background rectangles already pointing at their origin.  Between two such
-  // tiles the corner thread (k = 0, which always runs the full rules) makes the one link that is needed:
+  const uint8_t *te = tile_empty + (int64_t)b * tiles_x * tiles_y;
+  const bool empty = te[tt] != 0;
+  const bool left_empty = tx > 0 && te[tt - 1], up_empty = ty > 0 && te[tt - tiles_x];
+  // between tiles without foreground the corner pixel (k = 0, which always runs the full rules) makes the one link needed:
   //   * right column: only foreground pixels link diagonally from there;
-  //   * left column below the corner: the link to the left tile is redundant;
-  //   * top row right of the corner: the link upwards is skipped by the run rule anyway (left and up-left are
-  //     background of the same two tiles).
-  if (tile_empty[tile]) {
-    if (k >= CCL_TW + CCL_TH) return;
-    if (k >= CCL_TW && tx > 0 && tile_empty[tile - 1]) return;
-    if (k > 0 && k < CCL_TW && ty > 0 && tile_empty[tile - tiles_x]) return;
-  }
+  //   * left column below the corner: the link to the left tile is redundant when that tile is empty too;
+  //   * top row right of the corner: the link upwards is skipped by the run rule when the upper tile is empty too.
+  const int k_end = !empty ? PER_TILE : (((tx > 0 && !left_empty) ? CCL_TW + CCL_TH : ((ty > 0 && !up_empty) ? CCL_TW : 1)));
   const int64_t HW = (int64_t)H * W;
   const uint8_t *bm = bitmap + b * HW;
   int *L = labels + b * HW;
-  const int i = y * W + x;
-  const int fg = bm[i] != 0;
-  // a pixel of a tile without foreground stands for its tile origin (the only label such a tile stores, ccl.cuh)
-  const uint8_t *te = tile_empty + (int64_t)b * tiles_x * tiles_y;
-  auto node = [&](int px, int py) {
+  auto node = [&](int px, int py) {  // a pixel of a tile without foreground stands for its tile origin (ccl.cuh)
     const int ttx = px / CCL_TW, tty = py / CCL_TH;
     return te[tty * tiles_x + ttx] ? tty * CCL_TH * W + ttx * CCL_TW : py * W + px;
   };
-  const int self = node(x, y);
-  if (on_left && x > 0 && (bm[i - 1] != 0) == fg) uf_union(L, self, node(x - 1, y));
-  if (y > 0) {
-    const int n_fg = bm[i - W] != 0;
-    if (on_top && n_fg == fg) {
-      // same redundancy rule as the tile-local pass, along the whole image row
-      const bool skip = x > 0 && (bm[i - 1] != 0) == fg && (bm[i - W - 1] != 0) == fg;
-      if (!skip) uf_union(L, self, node(x, y - 1));
+  for (int k = lane; k < k_end; k += 32) {
+    int x, y;
+    if (k < CCL_TW) { x = tx * CCL_TW + k; y = ty * CCL_TH; }
+    else if (k < CCL_TW + CCL_TH) { x = tx * CCL_TW; y = ty * CCL_TH + (k - CCL_TW); }
+    else { x = tx * CCL_TW + CCL_TW - 1; y = ty * CCL_TH + (k - CCL_TW - CCL_TH); }
+    if (x >= W || y >= H) continue;
+    const bool on_left = (x % CCL_TW) == 0, on_right = (x % CCL_TW) == CCL_TW - 1, on_top = (y % CCL_TH) == 0;
+    // corner pixels appear in two of the three groups: let the top-row instance do the work
+    if (k >= CCL_TW && on_top) continue;
+    if (empty) {
+      if (k >= CCL_TW && left_empty) continue;
+      if (k > 0 && k < CCL_TW && up_empty) continue;
     }
-    if (fg && !n_fg) {  // foreground pixels are never in an "empty" tile
-      if (x > 0 && (on_top || on_left) && bm[i - W - 1] != 0) uf_union(L, i, i - W - 1);
-      if (x + 1 < W && (on_top || on_right) && bm[i - W + 1] != 0) uf_union(L, i, i - W + 1);
+    const int i = y * W + x;
+    const int fg = bm[i] != 0;
+    const int self = node(x, y);
+    if (on_left && x > 0 && (bm[i - 1] != 0) == fg) uf_union(L, self, node(x - 1, y));
+    if (y > 0) {
+      const int n_fg = bm[i - W] != 0;
+      if (on_top && n_fg == fg) {
+        // same redundancy rule as the tile-local pass, along the whole image row
+        const bool skip = x > 0 && (bm[i - 1] != 0) == fg && (bm[i - W - 1] != 0) == fg;
+        if (!skip) uf_union(L, self, node(x, y - 1));
+      }
+      if (fg && !n_fg) {  // foreground pixels are never in an "empty" tile
+        if (x > 0 && (on_top || on_left) && bm[i - W - 1] != 0) uf_union(L, i, i - W - 1);
+        if (x + 1 < W && (on_top || on_right) && bm[i - W + 1] != 0) uf_union(L, i, i - W + 1);
+      }
     }
   }
 }
@@ -217,10 +253,11 @@ int launch_ccl(ocrb_ctx *ctx, const uint8_t *bitmap, int B, int H, int W, int *l
   int64_t blocks = (int64_t)tiles_x * tiles_y * B;
   OCRB_TRY(ctx->ccl_tile_empty.reserve((size_t)blocks));
   uint8_t *tile_empty = ctx->ccl_tile_empty.as<uint8_t>();
-  ccl_local_kernel<<<(unsigned)blocks, CCL_THREADS, 0, ctx->stream>>>(bitmap, H, W, tiles_x, tiles_y, labels, tile_empty);
+  const int strips_x = (int)cdiv(tiles_x, CCL_STRIP);
+  ccl_local_kernel<<<(unsigned)((int64_t)strips_x * tiles_y * B), CCL_THREADS, 0, ctx->stream>>>(bitmap, H, W, tiles_x, tiles_y, strips_x, labels, tile_empty);
   OCRB_TRY(check_launch(ctx, "ccl_local"));
   int64_t n = (int64_t)B * H * W;
-  ccl_seam_kernel<<<(unsigned)cdiv(blocks * (CCL_TW + 2 * CCL_TH), 256), 256, 0, ctx->stream>>>(bitmap, H, W, B, tiles_x, tiles_y, labels, tile_empty);
+  ccl_seam_kernel<<<(unsigned)cdiv(blocks * 32, 256), 256, 0, ctx->stream>>>(bitmap, H, W, B, tiles_x, tiles_y, labels, tile_empty);
   OCRB_TRY(check_launch(ctx, "ccl_seam"));
   if (!flatten) return OCRB_OK;
   CclTiles tiles = {tile_empty, tiles_x, tiles_x * tiles_y};
