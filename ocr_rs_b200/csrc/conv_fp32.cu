@@ -218,8 +218,9 @@ __global__ void __launch_bounds__(256) convt2x2_fp32_kernel(const float *__restr
 
 // final conv_transpose2d k2 s2 (Cin -> 1) + bias + sigmoid.  in [B][H][W][Cin], w [4][Cin],
 // out [B][2H][2W] f32
+// tap_major: `in` is [B][H / 2][W / 2][4 taps][Cin] (conv-transpose 1 computed as a 1x1 convolution 64 -> 4 * 64) instead of [B][H][W][Cin]
 __global__ void convt2x2_sigmoid_fp32_kernel(const float *__restrict__ in, int B, int H, int W, int Cin,
-                                             const float *__restrict__ w, float bias, float *__restrict__ out) {
+                                             const float *__restrict__ w, float bias, float *__restrict__ out, int tap_major) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int Ho = 2 * H, Wo = 2 * W;
   int64_t total = (int64_t)B * Ho * Wo;
@@ -227,7 +228,9 @@ __global__ void convt2x2_sigmoid_fp32_kernel(const float *__restrict__ in, int B
   int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho);
   int64_t b = idx / ((int64_t)Wo * Ho);
   int tap = (oy & 1) * 2 + (ox & 1);
-  const float *ip = in + ((b * H + oy / 2) * W + ox / 2) * Cin;
+  const int iy = oy / 2, ix = ox / 2;  // pixel of the H x W input map
+  const float *ip = tap_major ? in + ((((b * (H / 2) + iy / 2) * (W / 2) + ix / 2) * 4 + (iy & 1) * 2 + (ix & 1)) * (int64_t)Cin)
+                              : in + ((b * H + iy) * W + ix) * Cin;
   const float *wp = w + tap * Cin;
   float acc = 0.f;
   for (int ci = 0; ci < Cin; ci += 4) {
@@ -291,9 +294,9 @@ int launch_convt2x2_fp32(ocrb_ctx *ctx, const float *in, int B, int H, int W, in
   convt2x2_fp32_kernel<<<(unsigned)cdiv(total, 256), 256, 0, ctx->stream>>>(in, B, H, W, Cin, Cout, w, scale, shift, relu, out);
   return check_launch(ctx, "convt2x2_fp32");
 }
-int launch_convt2x2_sigmoid_fp32(ocrb_ctx *ctx, const float *in, int B, int H, int W, int Cin, const float *w, float bias, float *out) {
+int launch_convt2x2_sigmoid_fp32(ocrb_ctx *ctx, const float *in, int B, int H, int W, int Cin, const float *w, float bias, float *out, int tap_major) {
   int64_t total = (int64_t)B * 2 * H * 2 * W;
-  convt2x2_sigmoid_fp32_kernel<<<(unsigned)cdiv(total, 256), 256, 0, ctx->stream>>>(in, B, H, W, Cin, w, bias, out);
+  convt2x2_sigmoid_fp32_kernel<<<(unsigned)cdiv(total, 256), 256, 0, ctx->stream>>>(in, B, H, W, Cin, w, bias, out, tap_major);
   return check_launch(ctx, "convt2x2_sigmoid_fp32");
 }
 int launch_nhwc_to_nchw_fp32(ocrb_ctx *ctx, const float *in, int B, int H, int W, int C, int ldc, float *out) {

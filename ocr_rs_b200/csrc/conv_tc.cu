@@ -114,7 +114,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&empty[stage], phase ^ 1, p.err, 1);
             if (elect_one()) {
               mbar_expect_tx(&full[stage], TC_A_TX + L::B_BYTES);
-              tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], ck * 64, x_base + s, y_base + r, b);
+              int a_c = ck * 64;
+              if (p.split_nblk) {  // K block -> (term plane, 64-channel chunk) of the split activation tensor (conv_tc.cuh)
+                const int chunk = ck / p.split_nblk, j = ck - chunk * p.split_nblk;
+                const int plane = p.split_nblk == 3 ? (j == 2 ? 1 : 0) : (j < 3 ? 0 : (j < 5 ? 1 : 2));
+                a_c = plane * p.split_cin + chunk * 64;
+              }
+              tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], a_c, x_base + s, y_base + r, b);
               tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full[stage], ((r * p.S + s) * p.cin_chunks + ck) * 64, n_tile * N_TILE);
             }
             __syncwarp();
@@ -234,6 +240,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int it = 0; it < 4; ++it) cur[it] = pre[it];
             if (e.add_mode != EPI_ADD_NONE && blk + 1 < NBLK) epi_fetch_addend(pre, lane, rw, e.addend, e.Cout, n0 + (blk + 1) * 32);
             epi_block32(v, lane, stg, rw, e, n0 + blk * 32, cur);
+          }
+        }
+      } else if (EPI == EPI_F32) {
+        // fp32 in, fp32 out: a thread owns one pixel (TMEM lane) and this warp's share of the channels
+        constexpr int NH = N_TILE / PARTS;
+        const int n0 = n_tile * N_TILE + half * NH;
+        const int m = quarter * 32 + lane;
+        const int yl = m / TC_TW, xl = m - yl * TC_TW;
+        const int y = ty * TC_TH + yl, x = tx * TC_TW + xl;
+        const bool valid = m < TC_ROWS && y < p.Ho && x < p.Wo;
+        const int64_t pix = ((int64_t)b * p.Ho + y) * p.Wo + x;
+        mbar_wait(&tfull[acc], acc_phase, p.err, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE + half * NH);
+#pragma unroll 1
+        for (int blk = 0; blk < NH / 32; ++blk) {
+          float v[32];
+          tmem_ld32(taddr + blk * 32, v);
+          if (valid) {
+            const int n = n0 + blk * 32;
+            float *o = p.out32 + pix * p.Cout + n;
+            const float *rr = p.res32 ? p.res32 + pix * p.Cout + n : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 r4 = rr ? *reinterpret_cast<const float4 *>(rr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              float4 y4;
+              y4.x = v[j + 0] * s_scale[n + j + 0] + s_shift[n + j + 0] + r4.x;
+              y4.y = v[j + 1] * s_scale[n + j + 1] + s_shift[n + j + 1] + r4.y;
+              y4.z = v[j + 2] * s_scale[n + j + 2] + s_shift[n + j + 2] + r4.z;
+              y4.w = v[j + 3] * s_scale[n + j + 3] + s_shift[n + j + 3] + r4.w;
+              if (p.relu) { y4.x = fmaxf(y4.x, 0.f); y4.y = fmaxf(y4.y, 0.f); y4.z = fmaxf(y4.z, 0.f); y4.w = fmaxf(y4.w, 0.f); }
+              *reinterpret_cast<float4 *>(o + j) = y4;
+            }
           }
         }
       } else {
@@ -442,6 +481,15 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
     static const bool ew8 = getenv("OCRB_HEAD_EW") && atoi(getenv("OCRB_HEAD_EW")) == 8;  // tuning knob
     return ew8 ? launch_one<256, 4, EPI_HEAD, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc)
                : launch_one<256, 4, EPI_HEAD, 0, 16>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+  }
+  if (epi == EPI_F32) {
+    switch (n_tile) {
+      case 64: return launch_one<64, 6, EPI_F32, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+      case 128: return launch_one<128, 5, EPI_F32, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+      case 256: return launch_one<256, 4, EPI_F32, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+    }
+    set_error("conv_tc: unsupported N tile %d", n_tile);
+    return OCRB_ERR_INVALID;
   }
   switch (n_tile) {
     case 64: return launch_one<64, 6, EPI_STD, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc);

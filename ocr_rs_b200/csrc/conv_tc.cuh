@@ -7,7 +7,7 @@
 
 namespace ocrb {
 
-enum { EPI_STD = 0, EPI_HEAD = 1 };
+enum { EPI_STD = 0, EPI_HEAD = 1, EPI_F32 = 2 };
 
 struct ConvTcParams {
   // problem geometry (output side); tiles_x/tiles_y/num_n_tiles are filled by the launcher
@@ -47,6 +47,15 @@ struct ConvTcParams {
   float *prob = nullptr;                    // [B][4*Ho][4*Wo]
   uint8_t *bitmap = nullptr;                // optional
   int *err = nullptr;                       // device flag set before a pipeline-timeout trap
+  // FP32-accuracy mode on the tensor cores (EPI_F32): every fp32 operand is split into bf16 terms (x = hi + mid (+ lo)), the
+  // activation tensor holds the terms as channel planes [hi | mid (| lo)] of split_cin channels each, the weight rows hold the
+  // matching blocks, and a product of split numbers becomes split_nblk K blocks per (tap, 64-channel chunk):
+  //   2 terms, 3 blocks: (a_hi, w_hi) (a_hi, w_mid) (a_mid, w_hi)                          — 16 significant bits
+  //   3 terms, 6 blocks: (a_hi, w_hi) (a_hi, w_mid) (a_hi, w_lo) (a_mid, w_hi) (a_mid, w_mid) (a_lo, w_hi) — 24 bits
+  // cin_chunks counts ALL K blocks of a tap (split_nblk * split_cin / 64).  Accumulation, affine, residual and output are fp32.
+  int split_nblk = 0, split_cin = 0;
+  const float *res32 = nullptr;             // [B][Ho][Wo][Cout]
+  float *out32 = nullptr;                   // [B][Ho][Wo][Cout]
 };
 
 // DB head tail constants, passed by value (kernel parameter = constant bank: the fully unrolled

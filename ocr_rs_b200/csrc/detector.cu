@@ -20,12 +20,13 @@ namespace ocrb {
 // conv_fp32.cu
 int launch_stem_fp32(ocrb_ctx *, const float *, int, int, int, const float *, const float *, const float *, float *);
 int launch_maxpool_fp32(ocrb_ctx *, const float *, int, int, int, int, float *);
+int launch_split_terms(ocrb_ctx *, const float *, int64_t, int, int, void *);
 int launch_conv_fp32(ocrb_ctx *, const float *, int, int, int, int, const float *, int, int, int, int, const float *,
                      const float *, const float *, int, float *);
 int launch_upsample2_add_fp32(ocrb_ctx *, const float *, const float *, int, int, int, int, float *);
 int launch_upsample_concat_fp32(ocrb_ctx *, const float *, int, int, int, int, int, int, int, float *);
 int launch_convt2x2_fp32(ocrb_ctx *, const float *, int, int, int, int, int, const float *, const float *, const float *, int, float *);
-int launch_convt2x2_sigmoid_fp32(ocrb_ctx *, const float *, int, int, int, int, const float *, float, float *);
+int launch_convt2x2_sigmoid_fp32(ocrb_ctx *, const float *, int, int, int, int, const float *, float, float *, int);
 int launch_nhwc_to_nchw_fp32(ocrb_ctx *, const float *, int, int, int, int, int, float *);
 int launch_u8_to_f32(ocrb_ctx *, const uint8_t *, int64_t, float, float *);
 // stem_tc.cu
@@ -162,6 +163,8 @@ struct DevConv {
   bool pair = false;     // conv_halo pair mode: 128 rows = two parity-class kernels sharing one input patch
   DevBuf w32;    // fp32 [k*k][cin][cout]
   DevBuf w16;    // bf16 [cout][k*k*cin]
+  DevBuf wsplit;  // FP32-accuracy mode on the tensor cores: bf16 term blocks [cout][tap][cin / 64][split_nblk][64] (conv_tc.cuh)
+  int split_nblk = 0;
   DevBuf scale, shift;
   std::vector<float> scale_h, shift_h;  // host copies: kernel-parameter constants of the TMA-store epilogue
 };
@@ -202,16 +205,22 @@ static int fold_bn(const HostWeights &hw, const std::string &bn, int c, const st
   return OCRB_OK;
 }
 
+static int prep_conv_body(const HostWeights *hw, const std::vector<float> *w, const ConvSpec &sp, bool want16, DevConv &dc);
 static int prep_conv(const HostWeights &hw, const ConvSpec &sp, bool want16, DevConv &dc) {
   const auto *w = hw.get(sp.name + ".weight");
   OCRB_REQUIRE(w, "missing weight tensor %s.weight", sp.name.c_str());
+  return prep_conv_body(&hw, w, sp, want16, dc);
+}
+// the same from an OIHW weight vector that is not a VarStore tensor (no batch-norm lookup: identity affine)
+static int prep_conv_from(const std::vector<float> &w, const ConvSpec &sp, bool want16, DevConv &dc) { return prep_conv_body(nullptr, &w, sp, want16, dc); }
+static int prep_conv_body(const HostWeights *hwp, const std::vector<float> *w, const ConvSpec &sp, bool want16, DevConv &dc) {
   const int kk = sp.k * sp.k;
   OCRB_REQUIRE((int64_t)w->size() == (int64_t)sp.cout * sp.cin * kk, "tensor %s.weight has %zu elements, expected %lld",
                sp.name.c_str(), w->size(), (long long)sp.cout * sp.cin * kk);
   dc.cin = sp.cin; dc.cout = sp.cout; dc.k = sp.k; dc.stride = sp.stride; dc.pad = sp.pad;
   dc.has_bn = !sp.bn.empty();
-  std::vector<float> scale, shift;
-  OCRB_TRY(fold_bn(hw, sp.bn, sp.cout, nullptr, scale, shift));
+  std::vector<float> scale(sp.cout, 1.0f), shift(sp.cout, 0.0f);
+  if (hwp) OCRB_TRY(fold_bn(*hwp, sp.bn, sp.cout, nullptr, scale, shift));
   OCRB_TRY(upload(dc.scale, scale));
   OCRB_TRY(upload(dc.shift, shift));
   dc.scale_h = scale; dc.shift_h = shift;
@@ -221,6 +230,33 @@ static int prep_conv(const HostWeights &hw, const ConvSpec &sp, bool want16, Dev
     for (int ci = 0; ci < sp.cin; ++ci)
       for (int tp = 0; tp < kk; ++tp) w32[((size_t)tp * sp.cin + ci) * sp.cout + co] = (*w)[((size_t)co * sp.cin + ci) * kk + tp];
   OCRB_TRY(upload(dc.w32, w32));
+  // FP32 mode: the operands of every 64-channel-aligned convolution as bf16 terms for the tensor cores
+  // (OCRB_FP32=cuda keeps the CUDA-core kernels; OCRB_SPLIT_TERMS=3 selects the 24-bit form)
+  static const bool fp32_cuda = getenv("OCRB_FP32") && strcmp(getenv("OCRB_FP32"), "cuda") == 0;
+  static const int split_terms = getenv("OCRB_SPLIT_TERMS") && atoi(getenv("OCRB_SPLIT_TERMS")) == 3 ? 3 : 2;
+  if (!want16 && !fp32_cuda && sp.cin % 64 == 0) {
+    const int nblk = split_terms == 2 ? 3 : 6;
+    static const int wplane2[3] = {0, 1, 0}, wplane3[6] = {0, 1, 2, 0, 1, 0};  // weight term of each K block (conv_tc.cuh)
+    const int *wplane = split_terms == 2 ? wplane2 : wplane3;
+    std::vector<uint16_t> ws((size_t)sp.cout * kk * sp.cin * nblk);
+    for (int co = 0; co < sp.cout; ++co)
+      for (int tp = 0; tp < kk; ++tp)
+        for (int ci = 0; ci < sp.cin; ++ci) {
+          float r = (*w)[((size_t)co * sp.cin + ci) * kk + tp];
+          uint16_t term[3];
+          for (int t = 0; t < 3; ++t) {
+            term[t] = f2bf(r);
+            uint32_t u = (uint32_t)term[t] << 16;
+            float back;
+            memcpy(&back, &u, 4);
+            r -= back;
+          }
+          const size_t base = (((size_t)co * kk + tp) * (sp.cin / 64) + ci / 64) * nblk * 64 + ci % 64;
+          for (int b = 0; b < nblk; ++b) ws[base + (size_t)b * 64] = term[wplane[b]];
+        }
+    OCRB_TRY(upload(dc.wsplit, ws));
+    dc.split_nblk = nblk;
+  }
   if (want16 && sp.cin % 64 == 0) {
     // OIHW -> [co][tap][ci] bf16 (K-major rows)
     std::vector<uint16_t> w16((size_t)sp.cout * kk * sp.cin);
@@ -508,6 +544,21 @@ static int det_build(ocrb_det *d, const HostWeights &hw) {
         }
     OCRB_TRY(upload(d->tr1_w32, w32));
     if (bf) OCRB_TRY(upload(d->head_w16, w16));
+    if (!bf) {
+      // FP32 mode on the tensor cores: conv-transpose 1 as a 1x1 convolution 64 -> 4 * 64 (column = tap * 64 + co) through the
+      // split-operand engine; bin_bn2 (with the bias folded in) repeats per tap
+      DevConv &c = d->conv["tr1"];
+      std::vector<float> oihw((size_t)256 * 64), sc4(256), sh4(256);
+      for (int tp = 0; tp < 4; ++tp)
+        for (int co = 0; co < 64; ++co) {
+          sc4[tp * 64 + co] = sc[co];
+          sh4[tp * 64 + co] = sh[co];
+          for (int ci = 0; ci < 64; ++ci) oihw[((size_t)(tp * 64 + co)) * 64 + ci] = (*w1)[((size_t)ci * 64 + co) * 4 + tp];
+        }
+      OCRB_TRY(prep_conv_from(oihw, {"tr1", "", 64, 256, 1, 1, 0}, false, c));
+      OCRB_TRY(upload(c.scale, sc4));
+      OCRB_TRY(upload(c.shift, sh4));
+    }
     std::vector<float> w2t(4 * 64);  // [tap][ci]
     for (int ci = 0; ci < 64; ++ci)
       for (int tp = 0; tp < 4; ++tp) w2t[tp * 64 + ci] = (*w2)[ci * 4 + tp];
@@ -530,6 +581,8 @@ static int act(ocrb_det *d, const std::string &name, int64_t elems, T **out) {
   return OCRB_OK;
 }
 
+static int n_tile_for(int cout);
+
 // ------------------------------------------------------------------------------ FP32 graph
 static int forward_fp32(ocrb_det *d, const float *img /*[B][H][W] dev*/, int B, int H, int W, float *prob) {
   ocrb_ctx *ctx = d->ctx;
@@ -539,10 +592,32 @@ static int forward_fp32(ocrb_det *d, const float *img /*[B][H][W] dev*/, int B, 
   OCRB_TRY(act(d, "f.stem", (int64_t)B * H4 * W4 * 64, &x0));
   OCRB_TRY(launch_stem_fp32(ctx, img, B, H, W, d->stem_w.as<float>(), d->stem_scale.as<float>(), d->stem_shift.as<float>(), c1));
   OCRB_TRY(launch_maxpool_fp32(ctx, c1, B, H2, W2, 64, x0));
-  auto conv = [&](const std::string &name, const float *in, int h, int w, const float *res, int relu, float *out) {
+  auto conv = [&](const std::string &name, const float *in, int h, int w, const float *res, int relu, float *out) -> int {
     DevConv &c = d->conv[name];
-    return launch_conv_fp32(ctx, in, B, h, w, c.cin, c.w32.as<float>(), c.cout, c.k, c.stride, c.pad, c.scale.as<float>(),
-                            c.shift.as<float>(), res, relu, out);
+    if (c.split_nblk == 0)
+      return launch_conv_fp32(ctx, in, B, h, w, c.cin, c.w32.as<float>(), c.cout, c.k, c.stride, c.pad, c.scale.as<float>(),
+                              c.shift.as<float>(), res, relu, out);
+    // tensor-core path at fp32-class accuracy: the input is split into bf16 terms (channel planes), the convolution is a
+    // tcgen05 implicit GEMM over split_nblk K blocks per (tap, chunk), accumulation / affine / residual / output stay fp32
+    const int terms = c.split_nblk == 3 ? 2 : 3;
+    DevBuf &sb = d->act["f.split"];
+    OCRB_TRY(sb.reserve((size_t)B * h * w * c.cin * terms * 2));
+    OCRB_TRY(launch_split_terms(ctx, in, (int64_t)B * h * w, c.cin, terms, sb.p));
+    CUtensorMap tmA, tmB;
+    const int nt = n_tile_for(c.cout);
+    OCRB_TRY(make_act_tensor_map(&tmA, sb.p, B, h, w, terms * c.cin, c.stride));
+    OCRB_TRY(make_weight_tensor_map(&tmB, c.wsplit.p, c.cout, c.k * c.k * c.cin * c.split_nblk, nt));
+    ConvTcParams p;
+    p.B = B;
+    p.Ho = (h + 2 * c.pad - c.k) / c.stride + 1;
+    p.Wo = (w + 2 * c.pad - c.k) / c.stride + 1;
+    p.Cout = c.cout;
+    p.R = c.k; p.S = c.k; p.cin_chunks = c.split_nblk * (c.cin / 64); p.stride = c.stride; p.pad = c.pad;
+    p.scale = c.scale.as<float>(); p.shift = c.shift.as<float>();
+    p.res32 = res; p.relu = relu; p.out32 = out;
+    p.split_nblk = c.split_nblk; p.split_cin = c.cin;
+    p.err = d->err.as<int>();
+    return launch_conv_tc(ctx, tmA, tmB, p, nt, EPI_F32, ("tc:" + name).c_str());
   };
   const float *x = x0;
   int h = H4, w = W4;
@@ -603,9 +678,15 @@ static int forward_fp32(ocrb_det *d, const float *img /*[B][H][W] dev*/, int B, 
   OCRB_TRY(launch_upsample_concat_fp32(ctx, p3, B, H4, W4, 64, 2, 128, 256, fuse));
   OCRB_TRY(launch_upsample_concat_fp32(ctx, p2, B, H4, W4, 64, 1, 192, 256, fuse));
   OCRB_TRY(conv("bin_conv1", fuse, H4, W4, nullptr, 1, b1));
-  OCRB_TRY(launch_convt2x2_fp32(ctx, b1, B, H4, W4, 64, 64, d->tr1_w32.as<float>(), d->tr1_scale.as<float>(),
-                                d->tr1_shift.as<float>(), 1, t1));
-  OCRB_TRY(launch_convt2x2_sigmoid_fp32(ctx, t1, B, H2, W2, 64, d->tr2_w.as<float>(), d->tr2_bias, prob));
+  if (d->conv.count("tr1") && d->conv["tr1"].split_nblk) {
+    // t1 in tap-major form [B][H4][W4][4 taps][64]: pixel (2y + i, 2x + j) of the 400 x 400 map is tap 2i + j of pixel (y, x)
+    OCRB_TRY(conv("tr1", b1, H4, W4, nullptr, 1, t1));
+    OCRB_TRY(launch_convt2x2_sigmoid_fp32(ctx, t1, B, H2, W2, 64, d->tr2_w.as<float>(), d->tr2_bias, prob, 1));
+  } else {
+    OCRB_TRY(launch_convt2x2_fp32(ctx, b1, B, H4, W4, 64, 64, d->tr1_w32.as<float>(), d->tr1_scale.as<float>(),
+                                  d->tr1_shift.as<float>(), 1, t1));
+    OCRB_TRY(launch_convt2x2_sigmoid_fp32(ctx, t1, B, H2, W2, 64, d->tr2_w.as<float>(), d->tr2_bias, prob, 0));
+  }
   return OCRB_OK;
 }
 
@@ -944,7 +1025,7 @@ static int det_forward_chunks(ocrb_det *det, const void *images, int dtype, int 
   ocrb_ctx *ctx = det->ctx;
   const size_t esz = dtype == OCRB_U8 ? 1 : 4;
   const int64_t HW = (int64_t)H * W;
-  const int chunk = det->mode == OCRB_MODE_BF16 ? 64 : 4;
+  const int chunk = det->mode == OCRB_MODE_BF16 ? 64 : 16;  // FP32 mode keeps fp32 activations (~0.4 GB per image)
   const bool in_dev = is_device_ptr(images), out_dev = is_device_ptr(prob);
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int bc = B - b0 < chunk ? B - b0 : chunk;

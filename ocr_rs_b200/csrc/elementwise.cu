@@ -4,6 +4,8 @@
 //
 // reference: metrics.rs:129-131 (binarize), image_ops.rs:350-381 (conversions),
 //            image_ops.rs:73-85 (/255), image_ops.rs:188-220 (preprocess_image)
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ocrb {
@@ -119,6 +121,37 @@ int launch_f32_to_u8(ocrb_ctx *ctx, const float *in, int64_t n, float scale, uin
   if (blocks > cap) blocks = cap;
   f32_to_u8_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, n, scale);
   return check_launch(ctx, "f32_to_u8");
+}
+
+// fp32 [n][C] -> bf16 term planes [n][terms * C]: x = hi + mid (+ lo), each term the bf16 rounding of what is left
+// (conv_tc.cuh: operands of the FP32-accuracy mode on the tensor cores)
+__global__ void split_terms_kernel(const float *__restrict__ in, int64_t n, int C, int terms, __nv_bfloat16 *__restrict__ out) {
+  const int64_t total = n * (C / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / (C / 4);
+    const int c = (int)(i - row * (C / 4)) * 4;
+    const float4 v = *reinterpret_cast<const float4 *>(in + row * C + c);
+    float r[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 *o = out + row * (int64_t)(terms * C) + c;
+    for (int t = 0; t < terms; ++t) {
+      __nv_bfloat16 h[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h[e] = __float2bfloat16_rn(r[e]);
+        r[e] -= __bfloat162float(h[e]);
+      }
+      *reinterpret_cast<uint2 *>(o + (int64_t)t * C) = *reinterpret_cast<uint2 *>(h);
+    }
+  }
+}
+
+int launch_split_terms(ocrb_ctx *ctx, const float *in, int64_t n, int C, int terms, void *out) {
+  if (n <= 0) return OCRB_OK;
+  int64_t blocks = cdiv(n * (C / 4), 256);
+  const int64_t cap = (int64_t)ctx->sm_count * 32;
+  if (blocks > cap) blocks = cap;
+  split_terms_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, n, C, terms, reinterpret_cast<__nv_bfloat16 *>(out));
+  return check_launch(ctx, "split_terms");
 }
 
 // ---------------------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel CUDA-event times of one detector forward (BF16 mode) of N device-resident 800x800 images, printed per
-1024 images.   python tools/layer_times.py [N] [name-filter]"""
+1024 images.   python tools/layer_times.py [N] [name-filter] [bf16|fp32]"""
 import os
 import sys
 
@@ -13,8 +13,9 @@ from ocr_rs_b200.text_detection.model import resnet18  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 flt = sys.argv[2] if len(sys.argv) > 2 else ""
+mode = sys.argv[3] if len(sys.argv) > 3 else "bf16"
 ctx = _ffi.default_context(0)
-net = resnet18(synth.make_detector_weights(0, "structured"), "bf16", ctx)
+net = resnet18(synth.make_detector_weights(0, "structured"), mode, ctx)
 img = torch.from_numpy(synth.document_image_shard(0, n, 800, 800).reshape(n, 1, 800, 800)).cuda()
 out = torch.empty((n, 1, 800, 800), dtype=torch.float32, device="cuda")
 for _ in range(3):
