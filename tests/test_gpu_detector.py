@@ -171,3 +171,31 @@ print("WORST", worst)
     worst = float([l for l in out.stdout.splitlines() if l.startswith("WORST")][-1].split()[1])
     print(knobs, f"max|dp| = {worst:.3e}")
     assert worst <= TOL["bf16"]
+
+
+@pytest.mark.parametrize("knobs", [{"OCRB_FP32": "cuda"}, {"OCRB_SPLIT_TERMS": "3"}])
+def test_fp32_mode_alternate_paths(knobs):
+    """FP32 mode runs on the tensor cores by default (operands split into two bf16 terms, conv_tc.cuh); the knobs select the
+    CUDA-core fp32 kernels and the three-term (24-bit) split.  Same 1e-4 tolerance, each in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    script = r"""
+import numpy as np
+from ocr_rs_b200 import synth
+from ocr_rs_b200.text_detection.model import resnet18
+from oracle import model_oracle as mo
+w = synth.make_detector_weights(3, "hard_bn")
+x = synth.make_noise_images(2, 160, 224, seed=7)
+got = resnet18(w, "fp32").forward_t(x.reshape(2, 1, 160, 224))
+ref = mo.detector_forward(w, x.reshape(2, 1, 160, 224).astype(np.float32)).numpy()
+print("WORST", float(np.abs(got - ref).max()))
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **knobs)
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    out = subprocess.run([sys.executable, "-c", script], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    worst = float([l for l in out.stdout.splitlines() if l.startswith("WORST")][-1].split()[1])
+    print(knobs, f"max|dp| = {worst:.3e}")
+    assert worst <= TOL["fp32"]
