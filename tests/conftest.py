@@ -33,6 +33,17 @@ def gt_others():
 
 
 @pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def image_files():
+    z = np.load(os.path.join(GOLDEN, "image_files.npz"))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
 def preprocessed():
     z = np.load(os.path.join(GOLDEN, "preprocessed.npz"))
     return {k: z[k] for k in z.files}

@@ -75,9 +75,10 @@ def test_contours_match_opencv_on_framed_images():
 
 
 def test_preprocess_fixtures(preprocessed):
-    # image_ops.rs:805-1008: preprocess_image(img55.jpg) == preprocessed_img55.png.  The JPEG
+    # image_ops.rs:805-1008: preprocess_image(img55.jpg) == preprocessed_img55.png.  Here the JPEG
     # was decoded with libjpeg instead of jpeg-decoder 0.1.20, so equality holds to decoder
-    # noise: >= 95 % of pixels exact, max |diff| 2; dims and adjust exact.
+    # noise: >= 95 % of pixels exact, max |diff| 2; dims and adjust exact.  The BIT-EXACT form of
+    # this check, from the file bytes through the restated jpeg-decoder, is tests/test_decode_oracle.py.
     for name, adj, rows in (("img55", (800 / 300, 533 / 200), 533), ("img545", (537 / 184, 800 / 274), 800)):
         out, ax, ay = pp.preprocess(preprocessed["src_" + name], 800, 800)
         assert (ax, ay) == adj
