@@ -89,6 +89,27 @@ int ocrb_preprocess_rgba(ocrb_ctx *ctx, const uint8_t *rgba, int src_w, int src_
  * out_gray [n][H][W], adjust [n][2] = (adjust_x, adjust_y) */
 int ocrb_preprocess_rgba_batch(ocrb_ctx *ctx, const uint8_t *rgba, const int64_t *src_offsets, const int *src_w, const int *src_h, int n,
                                int W, int H, uint8_t *out_gray, double *adjust);
+/* ---- file decode: `image::open(file)?.into_rgba()` / `.into_luma()` (image_ops.rs:193, :78; image 0.23.11 ->
+ * jpeg-decoder 0.1.20 / png 0.16.7) ----------------------------------------------------------------------
+ * JPEG (baseline + progressive Huffman, 8 bit, grey or YCbCr with sampling ratios 1 and 2) and PNG (8-bit and
+ * sub-byte grey / palette / RGB / RGBA, tRNS, non-interlaced) are decoded; anything else returns OCRB_ERR_INVALID
+ * (the reference returns Err from image::open).  The serial entropy decode runs on host threads (one image
+ * each), the inverse DCT, chroma upsampling and colour conversion run on the device for the whole batch; results
+ * are bit-identical to the reference's decoder (pinned on its preprocessed_img*.png fixtures).
+ * ocrb_image_info needs no device. */
+enum { OCRB_PIXELS_RGBA = 0, OCRB_PIXELS_LUMA = 1 };
+int ocrb_image_info(const uint8_t *file, size_t size, int *width, int *height, int *channels);
+/* host-only test hook: what the host stage hands to the device for one file (JPEG: int16 DCT coefficients,
+ * components concatenated, natural order; PNG: pixels [h][w][channels]); out == NULL sizes the buffer */
+int ocrb_debug_decode_host(const uint8_t *file, size_t size, void *out, size_t cap, size_t *needed);
+/* files[i] (sizes[i] bytes) -> pixels at byte offset out_offsets[i] of `out` (host or device):
+ * RGBA8 [h][w][4] (offsets multiples of 4) or luma [h][w] */
+int ocrb_decode_images(ocrb_ctx *ctx, const uint8_t *const *files, const size_t *sizes, int n, int format,
+                       const int64_t *out_offsets, uint8_t *out);
+/* image_ops::preprocess_image(file, (W, H)) (image_ops.rs:188-220) for a batch of encoded files: decode ->
+ * resize -> luma -> pad with the decoded pixels kept in HBM; out_gray [n][H][W], adjust [n][2] */
+int ocrb_preprocess_files(ocrb_ctx *ctx, const uint8_t *const *files, const size_t *sizes, int n, int W, int H,
+                          uint8_t *out_gray, double *adjust);
 /* image_ops::convert_image_to_tensor + to_kind(Float) (image_ops.rs:350-364,
  * text_detection/mod.rs:46-49): u8 -> f32, no scaling. */
 int ocrb_convert_image_to_tensor(ocrb_ctx *ctx, const uint8_t *image, int64_t n, float *out);

@@ -96,6 +96,30 @@ inline Preprocessed preprocess_image(Context &ctx, const uint8_t *rgba, int src_
   check(ocrb_preprocess_rgba(ctx.raw(), rgba, src_w, src_h, (int)dims.first, (int)dims.second, r.image.data(), &r.adjust_x, &r.adjust_y));
   return r;
 }
+// image_ops::preprocess_image(file_path, target_dim) (image_ops.rs:188-220) from the ENCODED file bytes (JPEG / PNG): decode
+// (image::open(..)?.into_rgba()) + resize + luma + pad in one library call; throws like the reference returns Err for a file
+// it cannot decode
+inline Preprocessed preprocess_image(Context &ctx, const std::vector<uint8_t> &file, std::pair<uint32_t, uint32_t> dims) {
+  Preprocessed r;
+  r.image.resize((size_t)dims.first * dims.second);
+  const uint8_t *files[1] = {file.data()};
+  const size_t sizes[1] = {file.size()};
+  double adjust[2] = {0, 0};
+  check(ocrb_preprocess_files(ctx.raw(), files, sizes, 1, (int)dims.first, (int)dims.second, r.image.data(), adjust));
+  r.adjust_x = adjust[0];
+  r.adjust_y = adjust[1];
+  return r;
+}
+// image::open(file)?.into_luma() (image_ops.rs:78): decoded grey pixels [h][w]
+inline std::vector<uint8_t> open_into_luma(Context &ctx, const std::vector<uint8_t> &file, int *w, int *h) {
+  check(ocrb_image_info(file.data(), file.size(), w, h, nullptr));
+  std::vector<uint8_t> luma((size_t)*w * *h);
+  const uint8_t *files[1] = {file.data()};
+  const size_t sizes[1] = {file.size()};
+  const int64_t offs[1] = {0};
+  check(ocrb_decode_images(ctx.raw(), files, sizes, 1, OCRB_PIXELS_LUMA, offs, luma.data()));
+  return luma;
+}
 // image_ops::convert_image_to_tensor + to_kind(Float) (image_ops.rs:350-364)
 inline std::vector<float> convert_image_to_tensor(Context &ctx, const uint8_t *image, int64_t n) {
   std::vector<float> t((size_t)n);

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libocrb.so")
 OK = 0
 MODE_FP32, MODE_BF16 = 0, 1
 U8, F32 = 0, 1
+PIXELS_RGBA, PIXELS_LUMA = 0, 1
 
 c_p = C.c_void_p
 i64 = C.c_int64
@@ -49,6 +50,10 @@ SIGNATURES = {
     "ocrb_preprocess_rgba": (C.c_int, [c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p,
                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ocrb_preprocess_rgba_batch": (C.c_int, [c_p, c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p]),
+    "ocrb_image_info": (C.c_int, [c_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ocrb_debug_decode_host": (C.c_int, [c_p, C.c_size_t, c_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ocrb_decode_images": (C.c_int, [c_p, C.POINTER(c_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, c_p, c_p]),
+    "ocrb_preprocess_files": (C.c_int, [c_p, C.POINTER(c_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, c_p, c_p]),
     "ocrb_convert_image_to_tensor": (C.c_int, [c_p, c_p, i64, c_p]),
     "ocrb_convert_tensor_to_image": (C.c_int, [c_p, c_p, i64, C.c_float, c_p]),
     "ocrb_load_image_as_tensor": (C.c_int, [c_p, c_p, i64, c_p]),

@@ -90,6 +90,7 @@ int ocrb_ctx_destroy(ocrb_ctx *ctx) {
   free_pipe(ctx);
   for (auto &b : ctx->stage) b.release();
   ctx->ccl_tile_empty.release();
+  ctx->decode_rgba.release();
   for (auto &b : ctx->pin) b.release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -117,6 +117,7 @@ struct ocrb_ctx {
   // staging for host-pointer arguments (indexed slots so one call can stage several)
   ocrb::DevBuf stage[6];
   ocrb::PinBuf pin[3];
+  ocrb::DevBuf decode_rgba;     // decoded RGBA arena of ocrb_preprocess_files (decode.cu)
   ocrb::DevBuf ccl_tile_empty;  // one byte per CCL tile of the last labelling: 1 = no foreground pixel (ccl.cu)
   ocrb::PostprocWorkspace *pp = nullptr;
   ocrb::PipelineWorkspace *pipe = nullptr;  // streams / events / buffers of ocrb_detect_and_recognize, created on first use

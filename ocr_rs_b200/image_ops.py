@@ -4,10 +4,12 @@ preprocess_image            image_ops.rs:188-220
 convert_image_to_tensor     image_ops.rs:350-364
 convert_tensor_to_image     image_ops.rs:367-381
 load_image_as_tensor        image_ops.rs:73-85
-File decoding (image::open) is out of the kernel path (SURVEY §8f rank 4): these take
-decoded pixel arrays.
+File decoding (image::open, SURVEY §8f rank 4): preprocess_image / load_image_as_tensor take a file path or the
+encoded bytes like the reference (JPEG / PNG, decoded by libocrb: entropy decode on host threads, IDCT + upsampling +
+colour conversion on the device) — or, as before, already decoded pixel arrays.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -18,10 +20,73 @@ def _ctx(ctx):
     return ctx if ctx is not None else _ffi.default_context()
 
 
-def preprocess_image(rgba, target_dim, ctx=None):
-    """rgba: uint8 [h, w, 4] (DynamicImage::into_rgba), target_dim = (width, height)
+def _file_bytes(src):
+    """path / bytes -> bytes; raises like image::open for a missing file (image_ops.rs:193)."""
+    if isinstance(src, (bytes, bytearray, memoryview)):
+        return bytes(src)
+    with open(os.fspath(src), "rb") as f:
+        return f.read()
+
+
+def _blobs(files):
+    blobs = [_file_bytes(f) for f in files]
+    n = len(blobs)
+    keep = [np.frombuffer(b, np.uint8) for b in blobs]
+    ptrs = (C.c_void_p * n)(*[k.ctypes.data for k in keep])
+    sizes = (C.c_size_t * n)(*[len(b) for b in blobs])
+    return keep, ptrs, sizes, n
+
+
+def image_info(file):
+    """(width, height, channels) of an encoded JPEG / PNG file (path or bytes) — host only."""
+    b = _file_bytes(file)
+    w, h, c = C.c_int(), C.c_int(), C.c_int()
+    buf = np.frombuffer(b, np.uint8)
+    _ffi.check(_ffi.lib().ocrb_image_info(buf.ctypes.data, len(b), C.byref(w), C.byref(h), C.byref(c)))
+    return w.value, h.value, c.value
+
+
+def decode_images(files, fmt="rgba", ctx=None):
+    """image::open(file)?.into_rgba() / .into_luma() for a list of files (paths or bytes)
+    -> list of uint8 arrays [h, w, 4] (fmt="rgba") or [h, w] (fmt="luma")."""
+    ctx = _ctx(ctx)
+    keep, ptrs, sizes, n = _blobs(files)
+    bpp = 4 if fmt == "rgba" else 1
+    dims = [image_info(k.tobytes())[:2] for k in keep]
+    offs = np.zeros(n, np.int64)
+    offs[1:] = np.cumsum([w * h * bpp for w, h in dims[:-1]])
+    out = np.empty(int(offs[-1]) + dims[-1][0] * dims[-1][1] * bpp, np.uint8)
+    _ffi.check(_ffi.lib().ocrb_decode_images(ctx.handle, ptrs, sizes, n, _ffi.PIXELS_RGBA if fmt == "rgba" else _ffi.PIXELS_LUMA,
+                                             _ffi.ptr(offs), _ffi.ptr(out)))
+    res = []
+    for (w, h), o in zip(dims, offs):
+        a = out[o:o + w * h * bpp]
+        res.append(a.reshape(h, w, 4) if fmt == "rgba" else a.reshape(h, w))
+    return res
+
+
+def preprocess_files(files, target_dim, ctx=None, out=None):
+    """preprocess_image(file, target_dim) for a batch of encoded files (paths or bytes) in one call
+    (ocrb_preprocess_files: the decoded pixels stay in HBM) -> (uint8 [n, height, width], adjust float64 [n, 2])."""
+    ctx = _ctx(ctx)
+    W, H = int(target_dim[0]), int(target_dim[1])
+    keep, ptrs, sizes, n = _blobs(files)
+    if out is None:
+        out = np.empty((n, H, W), np.uint8)
+    adj = np.empty((n, 2), np.float64)
+    _ffi.check(_ffi.lib().ocrb_preprocess_files(ctx.handle, ptrs, sizes, n, W, H, _ffi.ptr(out), _ffi.ptr(adj)))
+    return out, adj
+
+
+def preprocess_image(image, target_dim, ctx=None):
+    """image: a file path / encoded bytes (the reference's signature, image_ops.rs:188) or decoded
+    uint8 [h, w, 4] pixels (DynamicImage::into_rgba); target_dim = (width, height)
     -> (GrayImage uint8 [height, width], adjust_x, adjust_y)."""
     ctx = _ctx(ctx)
+    if not isinstance(image, np.ndarray):
+        out, adj = preprocess_files([image], target_dim, ctx)
+        return out[0], float(adj[0, 0]), float(adj[0, 1])
+    rgba = image
     rgba = np.ascontiguousarray(rgba, np.uint8)
     if rgba.ndim != 3 or rgba.shape[2] != 4:
         raise ValueError("expected an RGBA8 image [h, w, 4]")
@@ -86,8 +151,13 @@ def convert_tensor_to_image(tensor, scale=1.0, ctx=None):
 
 
 def load_image_as_tensor(luma, ctx=None):
-    """luma uint8 [h, w] -> float32 [1, w*h] = pixel / 255 (image_ops.rs:79-83)."""
+    """file path / encoded bytes (image_ops.rs:73: open(file)?.into_luma()) or luma uint8 [h, w]
+    -> float32 [1, w*h] = pixel / 255 (image_ops.rs:79-83)."""
     ctx = _ctx(ctx)
+    if not isinstance(luma, np.ndarray):
+        if isinstance(luma, (str, os.PathLike)) and not os.path.exists(luma):
+            raise FileNotFoundError(f"File {luma} doesn't exist")  # image_ops.rs:75-77
+        luma = decode_images([luma], "luma", ctx)[0]
     luma = np.ascontiguousarray(luma, np.uint8)
     out = np.empty((1, luma.size), np.float32)
     _ffi.check(_ffi.lib().ocrb_load_image_as_tensor(ctx.handle, _ffi.ptr(luma), luma.size, _ffi.ptr(out)))

@@ -47,6 +47,20 @@ def jpeg_decode(data: bytes, variant: int = JPEG_COLOR_F32) -> np.ndarray:
     return a
 
 
+def jpeg_coefficients(data: bytes) -> np.ndarray:
+    """The entropy-decoded DCT coefficients (int16, components concatenated, natural order, MCU-padded block grid)."""
+    data = bytes(data)
+    px, co = C.POINTER(C.c_uint8)(), C.POINTER(C.c_int16)()
+    w, h, nc, cnt = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+    rc = lib().orc_jpeg_decode_ex(data, C.c_size_t(len(data)), 0, C.byref(px), C.byref(w), C.byref(h), C.byref(nc), C.byref(co), C.byref(cnt))
+    if rc != 0:
+        raise ValueError("jpeg decode failed")
+    a = np.ctypeslib.as_array(co, shape=(cnt.value,)).copy()
+    lib().orc_decode_free(px)
+    lib().orc_decode_free(co)
+    return a
+
+
 def png_decode(data: bytes) -> np.ndarray:
     """-> uint8 [h, w, c], c = 1 (L), 2 (LA), 3 (RGB) or 4 (RGBA) after the expansions `png` 0.16 applies for the
     image crate (palette -> RGB, tRNS -> alpha, sub-byte grey -> 8 bits)."""

@@ -327,8 +327,10 @@ static int decode_block_progressive(Bits *b, Comp *c, const HuffTable *dc, const
 
 // Decodes a JFIF / JPEG file into interleaved pixels: n_comp = 1 (L8) or 3 (RGB8).  Returns 0, or a negative code
 // (-1 malformed, -2 unsupported: arithmetic coding, lossless, 12-bit, CMYK, sampling ratios other than 1 and 2).
-// `coef_out` (optional) receives nothing here; the coefficient planes stay internal.
-int orc_jpeg_decode(const uint8_t *data, size_t n, int variant, uint8_t **pixels, int *width, int *height, int *n_comp) {
+// `coef_out` (optional): the entropy-decoded coefficients of all components, [component][block row][block][64] in
+// natural order over the MCU-padded block grid (what the product's host stage hands to its device kernels).
+int orc_jpeg_decode_ex(const uint8_t *data, size_t n, int variant, uint8_t **pixels, int *width, int *height, int *n_comp,
+                       int16_t **coef_out, size_t *coef_count) {
   int rc = 0;
   uint16_t qt[4][64];
   int qt_present[4] = {0, 0, 0, 0};
@@ -526,6 +528,19 @@ int orc_jpeg_decode(const uint8_t *data, size_t n, int variant, uint8_t **pixels
       for (int x = 0; x < W; ++x) ycbcr_to_rgb(variant, line[0][x], line[1][x], line[2][x], out + ((size_t)y * W + x) * 3);
     }
   }
+  if (coef_out) {
+    size_t total = 0;
+    for (int c = 0; c < nc; ++c) total += (size_t)comp[c].bw * comp[c].bh * 64;
+    int16_t *all = (int16_t *)malloc(total * sizeof(int16_t));
+    if (!all) ERR(-1);
+    size_t o = 0;
+    for (int c = 0; c < nc; ++c) {
+      memcpy(all + o, comp[c].coef, (size_t)comp[c].bw * comp[c].bh * 64 * sizeof(int16_t));
+      o += (size_t)comp[c].bw * comp[c].bh * 64;
+    }
+    *coef_out = all;
+    *coef_count = total;
+  }
   *pixels = out;
   out = NULL;
   *width = W;
@@ -539,6 +554,10 @@ done:
   }
   free(out);
   return rc;
+}
+
+int orc_jpeg_decode(const uint8_t *data, size_t n, int variant, uint8_t **pixels, int *width, int *height, int *n_comp) {
+  return orc_jpeg_decode_ex(data, n, variant, pixels, width, height, n_comp, NULL, NULL);
 }
 
 void orc_decode_free(void *p) { free(p); }

@@ -79,18 +79,48 @@ unsafe fn take_polygons(h: *mut sys::ocrb_polygons) -> PolygonScores {
 
 pub mod image_ops {
     use super::*;
-    /// image_ops::preprocess_image (image_ops.rs:188-220): the decode stays with the `image` crate, resize + luma + pad
-    /// run on the GPU.
+    /// image_ops::preprocess_image (image_ops.rs:188-220), file to padded grey image in one library call: the file is
+    /// decoded by libocrb (entropy decode on the host, inverse DCT / upsampling / colour conversion on the GPU,
+    /// bit-identical to the `image` crate's decoders), resize + luma + pad run on the decoded pixels in HBM.
     pub fn preprocess_image<T: AsRef<Path>>(ctx: &Ctx, file_path: T, target_dim: (u32, u32)) -> Result<(GrayImage, f64, f64)> {
-        let rgba = image::open(file_path)?.into_rgba();
+        let bytes = std::fs::read(file_path.as_ref())?;
+        let mut batch = preprocess_images(ctx, &[&bytes[..]], target_dim)?;
+        Ok(batch.remove(0))
+    }
+
+    /// the same for a batch of encoded files (one decode + one fused resize launch for all of them)
+    pub fn preprocess_images(ctx: &Ctx, files: &[&[u8]], target_dim: (u32, u32)) -> Result<Vec<(GrayImage, f64, f64)>> {
         let (w, h) = target_dim;
-        let mut out = vec![0u8; (w * h) as usize];
-        let (mut ax, mut ay) = (0f64, 0f64);
+        let n = files.len();
+        let ptrs: Vec<*const u8> = files.iter().map(|f| f.as_ptr()).collect();
+        let sizes: Vec<usize> = files.iter().map(|f| f.len()).collect();
+        let mut out = vec![0u8; n * (w * h) as usize];
+        let mut adjust = vec![0f64; 2 * n];
         check(unsafe {
-            sys::ocrb_preprocess_rgba(ctx.raw(), rgba.as_raw().as_ptr(), rgba.width() as i32, rgba.height() as i32, w as i32, h as i32,
-                                      out.as_mut_ptr(), &mut ax, &mut ay)
+            sys::ocrb_preprocess_files(ctx.raw(), ptrs.as_ptr(), sizes.as_ptr(), n as i32, w as i32, h as i32, out.as_mut_ptr(), adjust.as_mut_ptr())
         })?;
-        Ok((GrayImage::from_vec(w, h, out).unwrap(), ax, ay))
+        Ok(out
+            .chunks((w * h) as usize)
+            .enumerate()
+            .map(|(i, px)| (GrayImage::from_vec(w, h, px.to_vec()).unwrap(), adjust[2 * i], adjust[2 * i + 1]))
+            .collect())
+    }
+
+    /// image_ops::load_image_as_tensor (image_ops.rs:73-85): open(file)?.into_luma() / 255 as f32 [1, w*h]
+    pub fn load_image_as_tensor<T: AsRef<Path>>(ctx: &Ctx, file_path: T) -> Result<Vec<f32>> {
+        let path = file_path.as_ref();
+        if !path.exists() {
+            return Err(anyhow!("File {} doesn't exist", path.display()));
+        }
+        let bytes = std::fs::read(path)?;
+        let (mut w, mut h, mut c) = (0i32, 0i32, 0i32);
+        check(unsafe { sys::ocrb_image_info(bytes.as_ptr(), bytes.len(), &mut w, &mut h, &mut c) })?;
+        let mut luma = vec![0u8; (w * h) as usize];
+        let (ptrs, sizes, offs) = ([bytes.as_ptr()], [bytes.len()], [0i64]);
+        check(unsafe { sys::ocrb_decode_images(ctx.raw(), ptrs.as_ptr(), sizes.as_ptr(), 1, sys::OCRB_PIXELS_LUMA, offs.as_ptr(), luma.as_mut_ptr()) })?;
+        let mut t = vec![0f32; luma.len()];
+        check(unsafe { sys::ocrb_load_image_as_tensor(ctx.raw(), luma.as_ptr(), luma.len() as i64, t.as_mut_ptr()) })?;
+        Ok(t)
     }
 }
 
