@@ -32,6 +32,7 @@ int launch_u8_to_f32(ocrb_ctx *, const uint8_t *, int64_t, float, float *);
 // stem_tc.cu
 int launch_stem_tc(ocrb_ctx *, const void *, int, int, int, int, const float *, const float *, const float *, __nv_bfloat16 *, int *);
 int launch_stem_tc2(ocrb_ctx *, const void *, int, int, int, int, const float *, const float *, const float *, __nv_bfloat16 *, int *);
+int launch_stem_tc3(ocrb_ctx *, const void *, int, int, int, int, const float *, const float *, const float *, __nv_bfloat16 *, int *);
 
 constexpr float BN_EPS = 1e-5f;  // tch nn::BatchNormConfig default
 
@@ -766,10 +767,16 @@ static int forward_bf16(ocrb_det *d, const TIn *img, int B, int H, int W, float 
 
   // stem
   static const bool stem_cuda_cores = getenv("OCRB_STEM") && strcmp(getenv("OCRB_STEM"), "cuda") == 0;
-  // stem_tc2.cu (no im2col, register pooling) is correct but, at 13 k warp instructions per unit, issue-bound and no
-  // faster than stem_tc.cu (7.8 - 8.4 ms vs 7.2 ms per 1024 images): kept as the measured alternative, not the default
+  // default: stem_tc3.cu (transposed implicit GEMM, pooling in registers).  OCRB_STEM=v1: the im2col stem of stem_tc.cu
+  // (round 1: 8.2 ms per 1024 images against 4.1); v2: stem_tc2.cu (pixels in the TMEM lanes: issue-bound, 7.8 - 8.4 ms).
+  // The u8 form of v3 fetches the image in aligned 16-byte chunks; other shapes take v1.
+  static const bool stem_v1 = getenv("OCRB_STEM") && strcmp(getenv("OCRB_STEM"), "v1") == 0;
   static const bool stem_v2 = getenv("OCRB_STEM") && strcmp(getenv("OCRB_STEM"), "v2") == 0;
-  if (!stem_cuda_cores && stem_v2) {
+  const bool stem_v3 = !stem_v1 && !stem_v2 && (sizeof(TIn) != 1 || (W % 16 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0));
+  if (!stem_cuda_cores && stem_v3) {
+    OCRB_TRY(launch_stem_tc3(ctx, img, sizeof(TIn) == 1, B, H, W, d->stem_w.as<float>(), d->stem_scale_h, d->stem_shift_h, x0,
+                             d->err.as<int>()));
+  } else if (!stem_cuda_cores && stem_v2) {
     OCRB_TRY(launch_stem_tc2(ctx, img, sizeof(TIn) == 1, B, H, W, d->stem_w.as<float>(), d->stem_scale_h, d->stem_shift_h, x0,
                              d->err.as<int>()));
   } else if (!stem_cuda_cores) {
