@@ -23,6 +23,7 @@ namespace ocrb {
 void rec_tc_pack_conv2(const float *, std::vector<uint16_t> &);
 void rec_tc_pack_fc(const float *, int, int, std::vector<uint16_t> &);
 int launch_rec_conv2_tc(ocrb_ctx *, const __half *, const uint16_t *, const float *, int, __half *, int *);
+int launch_rec_conv1_tc(ocrb_ctx *, const uint8_t *, const float *, const float *, int, __half *, int *);
 int launch_rec_fc_tc(ocrb_ctx *, const __half *, const uint16_t *, const float *, int, int, int, int, float *, int *);
 
 int launch_conv_fp32(ocrb_ctx *, const float *, int, int, int, int, const float *, int, int, int, int, const float *,
@@ -180,11 +181,17 @@ int rec_forward_device(ocrb_rec *r, const void *glyphs_dev, int is_u8, int B, fl
     OCRB_TRY(r->a1.reserve((size_t)B * 144 * 64 * 2));
     OCRB_TRY(r->a3.reserve((size_t)B * 2048 * 2));
     OCRB_TRY(r->err.reserve(4));
-    if (is_u8)
-      rec_conv1_pool_kernel<uint8_t, true><<<rc1_grid, RC1_THREADS, 0, ctx->stream>>>((const uint8_t *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), B, r->a1.p);
-    else
-      rec_conv1_pool_kernel<float, true><<<rc1_grid, RC1_THREADS, 0, ctx->stream>>>((const float *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), B, r->a1.p);
-    OCRB_TRY(check_launch(ctx, "rec_conv1_pool"));
+    // conv1: u8 glyphs (16-byte aligned) on the tensor cores (rec_tc.cu); f32 glyphs / OCRB_REC_CONV1=cuda on CUDA cores
+    static const bool conv1_cuda = getenv("OCRB_REC_CONV1") && strcmp(getenv("OCRB_REC_CONV1"), "cuda") == 0;
+    if (is_u8 && !conv1_cuda && (reinterpret_cast<uintptr_t>(glyphs_dev) & 15) == 0) {
+      OCRB_TRY(launch_rec_conv1_tc(ctx, (const uint8_t *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), B, r->a1.as<__half>(), r->err.as<int>()));
+    } else {
+      if (is_u8)
+        rec_conv1_pool_kernel<uint8_t, true><<<rc1_grid, RC1_THREADS, 0, ctx->stream>>>((const uint8_t *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), B, r->a1.p);
+      else
+        rec_conv1_pool_kernel<float, true><<<rc1_grid, RC1_THREADS, 0, ctx->stream>>>((const float *)glyphs_dev, r->w1.as<float>(), r->b1.as<float>(), B, r->a1.p);
+      OCRB_TRY(check_launch(ctx, "rec_conv1_pool"));
+    }
     OCRB_TRY(launch_rec_conv2_tc(ctx, r->a1.as<__half>(), r->w2s.as<uint16_t>(), r->b2.as<float>(), B, r->a3.as<__half>(), r->err.as<int>()));
     OCRB_TRY(launch_rec_fc_tc(ctx, r->a3.as<__half>(), r->w3s.as<uint16_t>(), r->b3.as<float>(), B, 1024, 512, 1, r->a4.as<float>(), r->err.as<int>()));
   } else {

@@ -384,6 +384,240 @@ void rec_tc_pack_fc(const float *w, int N, int K, std::vector<uint16_t> &out) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// conv1 + pool2 (u8 glyphs): conv 5x5 (1 -> 32) + bias + max_pool 2 (char_recognition/model.rs:30-32)
+// ---------------------------------------------------------------------------------------------------------------
+// Transposed implicit GEMM without im2col, D[channel][conv pixel] (the detector stem's scheme, stem_tc3.cu):
+//   * the grey levels are integers <= 255, exact in fp16, so only the WEIGHTS are split: w * 2^e = w_hi + w_lo (two fp16
+//     terms; the power of two puts max |w| near 2^14, which keeps w_lo of every weight that matters out of the subnormal
+//     range) and the two terms sit side by side in K: A = [w_hi (6 chunks of 8) | w_lo (6 chunks)], both multiplied with the
+//     same pixels.  u8 x fp16 products are exact in the fp32 accumulator;  conv = acc / (255 * 2^e);
+//   * B = the glyph itself through NO-SWIZZLE K-major descriptors: T[x][y] = the 16 bytes fp16(img[y][x .. x + 7]) (5 used,
+//     the weights of the other 3 are zero), x-columns of 32 rows (28 + 4 zero rows).  GEMM row n = x * 32 + y: the eight rows
+//     of a core matrix are 8 consecutive y (128 contiguous bytes), the K-adjacent core matrix (filter row r + 1) is the SAME
+//     array one row further (LBO = 16 bytes), the next row group is + 128 bytes (SBO, uniform across x-columns);
+//   * M = 128 rows = the 32 channels four times, so each TMEM lane quarter holds all channels and the four epilogue warps
+//     split the pixels: warp q pools the x-column pair q of an N tile (8 x-columns x 32 y = 256 TMEM columns, two
+//     accumulator stages) in registers and writes the fp16-split [hi 32 | lo' 32] record conv2 reads.
+constexpr int RC1T_T_BYTES = 24 * 512;                  // T of one glyph: [24 x][32 y][16 B]
+constexpr int RC1T_RAW_BYTES = 800;                     // 784 bytes + slack for the 8-byte reads at the end
+constexpr int RC1T_OFF_A = 2 * RC1T_T_BYTES;            // two A tiles [128][64] fp16, 128B-swizzled: w_hi, w_lo
+constexpr int RC1T_OFF_RAW = RC1T_OFF_A + 2 * 128 * 128;
+constexpr int RC1T_OFF_BAR = RC1T_OFF_RAW + 3 * RC1T_RAW_BYTES;
+constexpr int RC1T_SMEM = RC1T_OFF_BAR + 256 + 1024;
+constexpr int RC1T_THREADS = 9 * 32;                    // warps 0-3 epilogue, 4-7 producers, 8 MMA
+static_assert(RC1T_OFF_A % 1024 == 0 && RC1T_OFF_RAW % 16 == 0 && RC1T_OFF_BAR % 8 == 0, "rec conv1 shared-memory layout");
+
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // layout type 0 = SWIZZLE_NONE
+}
+__device__ __forceinline__ void u8x4_to_f16x4_r(uint32_t x, uint32_t &lo, uint32_t &hi) {
+  const uint32_t a = __byte_perm(x, 0x64646464u, 0x4140), b = __byte_perm(x, 0x64646464u, 0x4342);  // 1024 + byte
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(lo) : "r"(a), "r"(0x64006400u));
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(hi) : "r"(b), "r"(0x64006400u));
+}
+__device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait32_raw(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// in: [B][784] u8 (16-byte aligned), w: [25][32] fp32 (tap-major), out: [B][144][64] half (hi 32 | lo' 32)
+__global__ void __launch_bounds__(RC1T_THREADS, 1)
+rec_conv1_tc_kernel(const uint8_t *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias, int B,
+                    __half *__restrict__ out, int *err) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_red[RC1T_THREADS / 32];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sA = smem + RC1T_OFF_A;
+  uint64_t *tfullT = reinterpret_cast<uint64_t *>(smem + RC1T_OFF_BAR);  // [2] T built
+  uint64_t *temptyT = tfullT + 2;                                        // [2] MMAs done reading it
+  uint64_t *accfull = temptyT + 2, *accempty = accfull + 2;              // [2] accumulator stages
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accempty + 2);
+  const uint32_t t_u32 = smem_u32(smem), raw_u32 = smem_u32(smem + RC1T_OFF_RAW);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int step = gridDim.x;
+
+  // ---- one-time setup: weight scale 2^e, A tiles, zero rows of T, barriers, TMEM
+  float m = 0.f;
+  for (int i = tid; i < 800; i += RC1T_THREADS) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) s_red[warp] = m;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfullT[s], 128);
+      mbar_init(&temptyT[s], 1);
+      mbar_init(&accfull[s], 1);
+      mbar_init(&accempty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 2 * RC1T_T_BYTES / 16; i += RC1T_THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 3 * RC1T_RAW_BYTES / 16; i += RC1T_THREADS) reinterpret_cast<uint4 *>(smem + RC1T_OFF_RAW)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  m = 0.f;
+#pragma unroll
+  for (int i = 0; i < RC1T_THREADS / 32; ++i) m = fmaxf(m, s_red[i]);
+  int e2 = 0;
+  if (m > 0.f && m < 3.0e38f) frexpf(m, &e2);  // m = f * 2^e2, f in [0.5, 1)
+  int ex = 14 - e2;
+  ex = ex < -100 ? -100 : ex > 100 ? 100 : ex;
+  const float wscale = ldexpf(1.0f, ex), inv = ldexpf(1.0f, -ex) / 255.0f;
+  for (int i = tid; i < 2 * 128 * 8; i += RC1T_THREADS) {
+    const int part = i >> 10, row = (i >> 3) & 127, j = i & 7, co = row & 31;  // part 0: w_hi, 1: w_lo; chunk j = filter row
+    uint32_t pk[4] = {0u, 0u, 0u, 0u};
+    if (j < 5) {
+      __half h[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        float v = 0.f;
+        if (x < 5) {
+          const float ws = w[(j * 5 + x) * 32 + co] * wscale;
+          const __half hi = __float2half_rn(ws);
+          v = part == 0 ? __half2float(hi) : ws - __half2float(hi);
+        }
+        h[x] = __float2half_rn(v);
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x) pk[x] = (uint32_t)__half_as_ushort(h[2 * x]) | ((uint32_t)__half_as_ushort(h[2 * x + 1]) << 16);
+    }
+    *reinterpret_cast<uint4 *>(sA + part * 16384 + row * 128 + ((j ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ================= epilogue: lane = channel, warp q = pooled column q of the N tile; 2x2 max-pool on registers =================
+    const float bs = bias[lane];
+    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(warp * 64);
+    uint32_t it = 0;
+    for (int b = blockIdx.x; b < B; b += step) {
+      unsigned short *ob = reinterpret_cast<unsigned short *>(out) + (int64_t)b * 144 * 64 + lane;
+#pragma unroll 1
+      for (int t = 0; t < 3; ++t, ++it) {
+        const uint32_t st = it & 1;
+        mbar_wait(&accfull[st], (it >> 1) & 1, err, 41);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld32_raw(tlane + st * 256u, v0);
+        tmem_ld32_raw(tlane + st * 256u + 32u, v1);
+        tmem_ld_wait32_raw(v0);
+        tmem_ld_wait32_raw(v1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&accempty[st]);
+        const int px = t * 4 + warp;
+#pragma unroll
+        for (int py = 0; py < 12; ++py) {
+          const float mx = fmaxf(fmaxf(__uint_as_float(v0[2 * py]), __uint_as_float(v0[2 * py + 1])),
+                                 fmaxf(__uint_as_float(v1[2 * py]), __uint_as_float(v1[2 * py + 1])));
+          const float val = fmaf(mx, inv, bs);  // max(conv) + bias == max(conv + bias)
+          const __half hi = __float2half_rn(val);
+          const __half lo = __float2half_rn((val - __half2float(hi)) * SPLIT_SCALE);
+          unsigned short *op = ob + (py * 12 + px) * 64;
+          op[0] = __half_as_ushort(hi);
+          op[32] = __half_as_ushort(lo);
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ================= producers: glyph bytes (cp.async two glyphs ahead) -> T =================
+    const int pt = (warp - 4) * 32 + lane;  // 0..127
+    auto prefetch_raw = [&](int b, int rb) {
+      if (pt < 49) cp_async_16_zfill(raw_u32 + rb * RC1T_RAW_BYTES + pt * 16, in + (int64_t)b * 784 + pt * 16, true);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if ((int)blockIdx.x < B) prefetch_raw(blockIdx.x, 0); else asm volatile("cp.async.commit_group;" ::: "memory");
+    if ((int)blockIdx.x + step < B) prefetch_raw(blockIdx.x + step, 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+    uint32_t n = 0;
+    for (int b = blockIdx.x; b < B; b += step, ++n) {
+      const uint32_t tb = n & 1;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      named_bar_sync(9, 128);  // glyph n has landed for everyone; everyone is done with the raw buffer of glyph n - 1
+      if (b + 2 * step < B) prefetch_raw(b + 2 * step, (n + 2) % 3); else asm volatile("cp.async.commit_group;" ::: "memory");
+      mbar_wait(&temptyT[tb], ((n >> 1) & 1) ^ 1, err, 42);
+      const uint32_t rawb = raw_u32 + (n % 3) * RC1T_RAW_BYTES, dst = t_u32 + tb * RC1T_T_BYTES;
+      // item (x, y): the 8 bytes img[y][x .. x + 7] (runs past column 27 into the next row: those weights are zero)
+      for (int k = pt; k < 24 * 28; k += 128) {
+        const int y = k / 24, x = k - y * 24;
+        const uint32_t o = (uint32_t)(y * 28 + x);
+        const uint32_t wa = rawb + (o & ~3u);
+        uint32_t w0, w1, w2;
+        asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];" : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(wa));
+        const uint32_t sh = (o & 3u) * 8u;
+        uint4 v;
+        u8x4_to_f16x4_r(__funnelshift_r(w0, w1, sh), v.x, v.y);
+        u8x4_to_f16x4_r(__funnelshift_r(w1, w2, sh), v.z, v.w);
+        sts_16(dst + (uint32_t)(x * 512 + y * 16), v);
+      }
+      fence_proxy_async();
+      mbar_arrive(&tfullT[tb]);
+    }
+  } else {
+    // ================= MMA issuer: per glyph 3 N tiles x 6 K steps of UMMA 128 x 256 x 16 =================
+    constexpr uint32_t idesc = make_idesc_f16(256);
+    const uint64_t adesc = make_smem_desc(sA);
+    uint32_t n = 0, it = 0;
+    for (int b = blockIdx.x; b < B; b += step, ++n) {
+      const uint32_t tb = n & 1;
+      mbar_wait(&tfullT[tb], (n >> 1) & 1, err, 43);
+#pragma unroll 1
+      for (int t = 0; t < 3; ++t, ++it) {
+        const uint32_t st = it & 1;
+        mbar_wait(&accempty[st], ((it >> 1) & 1) ^ 1, err, 44);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+            umma_bf16(tmem_base + st * 256u, adesc + (uint64_t)((k / 3) * (16384 >> 4) + 2 * (k % 3)),
+                      make_smem_desc_nosw(t_u32 + tb * RC1T_T_BYTES + (uint32_t)(t * 8 * 512 + 2 * (k % 3) * 16), 16, 128), idesc, k != 0 ? 1u : 0u);
+          umma_commit(&accfull[st]);
+          if (t == 2) umma_commit(&temptyT[tb]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_rec_conv1_tc(ocrb_ctx *ctx, const uint8_t *glyphs, const float *w, const float *bias, int B, __half *out, int *err) {
+  OCRB_TRY(ensure_dyn_smem(ctx, rec_conv1_tc_kernel, RC1T_SMEM));
+  const int grid = B < ctx->sm_count ? B : ctx->sm_count;
+  rec_conv1_tc_kernel<<<grid, RC1T_THREADS, RC1T_SMEM, ctx->stream>>>(glyphs, w, bias, B, out, err);
+  return check_launch(ctx, "rec_tc:conv1");
+}
+
 int launch_rec_conv2_tc(ocrb_ctx *ctx, const __half *act, const uint16_t *w_packed, const float *bias, int B, __half *out, int *err) {
   CUtensorMap tmW;
   OCRB_TRY(make_weight_tensor_map(&tmW, w_packed, 25 * 128, 64, 128));

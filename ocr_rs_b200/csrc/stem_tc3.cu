@@ -21,12 +21,17 @@
 //     channel and reads whole conv rows: the 3x3 / s2 max-pool is 3-input max instructions on registers — no shuffles, no
 //     shared memory, no packing before the pool; scale-back + shift + ReLU + bf16 rounding are applied to the pooled values
 //     only (max commutes with the monotonic affine / ReLU / rounding).
-// Warp-specialised, one CTA per SM, 13 warps: 8 epilogue warps (two per scheduler), 4 producer warps (raw patch by cp.async
-// two units ahead -> the interleaved phase copies, double-buffered), 1 MMA warp.  A unit's 15 conv rows sit in FOUR
-// accumulator stages of 128 TMEM columns (4 conv rows each; the last one 3 rows, N = 96); epilogue warp pair W_q owns
-// stage q, i.e. pooled rows 2q, 2q + 1 (conv rows 4q .. 4q + 4: the fifth is the first row of stage q + 1, read by both
-// neighbours), so a stage is handed back to the MMA warp after ~4 row reads and the next unit's MMAs run under the current
-// unit's epilogue.  Unit = 7 x 15 pooled pixels <- 15 x 32 conv pixels <- 36 x 70 input pixels.
+// Warp-specialised, one CTA per SM, 21 warps: 12 epilogue warps (three per scheduler), 8 producer warps (raw patch by
+// cp.async in aligned 16-byte chunks two units ahead -> one 8-pixel group of all four phase copies per thread,
+// double-buffered), 1 MMA warp.  A unit's 13 conv rows sit in FOUR accumulator stages of TMEM columns (4 conv rows = 128
+// columns each; the last one a single row, N = 32); epilogue warp group W_q owns stage q = pooled rows 2q, 2q + 1 (conv rows
+// 4q .. 4q + 4: the fifth is the first row of stage q + 1, read by both neighbours) and is split once more into two column
+// halves (pooled columns 0..7 / 8..14) and two channel halves, so a stage is handed back to the MMA warp after a few row
+// reads and the next unit's MMAs run under the current unit's epilogue.  Vertical maximum first (17 three-input maxima per
+// pooled row and thread), then the horizontal one.  Unit = 6 x 15 pooled pixels <- 13 x 32 conv pixels <- 32 x 70 input
+// pixels.  Measured (profiles/r2_stem3_ncu.md): 3.6 ms per 1024 images of 800 x 800 against 8.2 ms for stem_tc.cu; issue
+// slots 62 % busy, ALU pipe 52 % — the kernel is bound by instruction issue (maxima, conversions, 2-byte stores), not by the
+// tensor pipe (41 % busy) or shared memory (46 %).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
