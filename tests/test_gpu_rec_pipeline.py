@@ -37,9 +37,11 @@ def test_rec_logits_and_argmax(env, kind, n):
     print(f"rec {kind} n={n}: max|dlogit| = {np.abs(logits - ref).max():.2e}, top-2 gap < 1e-4 on {ties} glyphs, {mism} argmax mismatches")
     assert mism == 0
     assert np.abs(prob - want_p).max() <= 1e-6
-    # f32 entry point gives the same numbers as the u8 one
+    # the f32 entry point (conv1 on CUDA cores: arbitrary floats cannot use the exact-u8 tensor-core form) agrees with the
+    # u8 one to fp32 summation-order noise and gives the same classes
     l2, a2, _ = net.predict(x)
-    assert (l2 == logits).all() and (a2 == argmax).all()
+    assert np.abs(l2 - logits).max() <= 2e-6 and (a2 == argmax).all()
+    assert np.abs(l2 - ref).max() <= 1e-4
 
 
 def test_rec_fp32_cuda_core_path():
