@@ -407,6 +407,21 @@ int make_act_tensor_map_box(CUtensorMap *map, const void *base, int B, int H, in
   return OCRB_OK;
 }
 
+// the same with box_b images per box (glyph batches of the recognition net: rec_tc.cu)
+int make_act_tensor_map_box_b(CUtensorMap *map, const void *base, int B, int H, int W, int C, int box_w, int box_h, int box_b) {
+  auto fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return OCRB_ERR_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_b};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(act box %dx%dx%d of %dx%dx%dx%d) -> %d", box_w, box_h, box_b, B, H, W, C, (int)r); return OCRB_ERR_CUDA; }
+  return OCRB_OK;
+}
+
 // a C-channel slice of pixels that are ldc channels apart ([B][H][W][ldc], base already at the slice): TMA store / residual load box
 // step > 1: the H x W positions sit on every step-th pixel and row of a (H*step) x (W*step) map; row_px > 0: pixels per
 // (full-resolution) row of the buffer when its rows are padded

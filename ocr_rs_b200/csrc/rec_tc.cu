@@ -220,6 +220,145 @@ rec_conv2_tc_kernel(const __half *__restrict__ act, const __grid_constant__ CUte
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// conv2, second form (default): the A tile of a tap is ONE tiled TMA box {64 halves, 8, 8, 4 glyphs} of the activation
+// tensor [B][12][12][64] at (x, y) = (dx, dy) — rows land in (glyph, oy, ox) order, 128B-swizzled, exactly the two M tiles
+// the builder warps of rec_conv2_tc_kernel used to copy out of a shared-memory image of the unit (those copies, 64 KB of
+// shared-memory traffic per tap, were what the first form waited for: ncu showed the builders stalled on the load-store
+// unit and the MMA warp on their barrier).  The 25-fold re-read of a unit's 72 KB comes out of L2.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RC2T_A_STAGES = 4, RC2T_B_STAGES = 4;
+constexpr int RC2T_OFF_B = RC2T_A_STAGES * RC2_A_STAGE;
+constexpr int RC2T_OFF_BAR = RC2T_OFF_B + RC2T_B_STAGES * RC2_B_STAGE;
+constexpr int RC2T_SMEM = RC2T_OFF_BAR + 256 + 1024;
+constexpr int RC2T_THREADS = 6 * 32;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+
+__global__ void __launch_bounds__(RC2T_THREADS, 1)
+rec_conv2_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const float *__restrict__ bias, int B,
+                     __half *__restrict__ out, int *err) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_bias[64];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sA = smem, *sB = smem + RC2T_OFF_B;
+  uint64_t *fullA = reinterpret_cast<uint64_t *>(smem + RC2T_OFF_BAR), *emptyA = fullA + RC2T_A_STAGES;
+  uint64_t *fullB = emptyA + RC2T_A_STAGES, *emptyB = fullB + RC2T_B_STAGES;
+  uint64_t *tfull = emptyB + RC2T_B_STAGES, *tempty = tfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int units = (B + RC2_GLYPHS - 1) / RC2_GLYPHS;
+  const int my_units = (int)blockIdx.x < units ? (units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const uint32_t total = (uint32_t)my_units * 25u;
+
+  if (tid < 64) s_bias[tid] = bias[tid];
+  if (tid == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < RC2T_A_STAGES; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < RC2T_B_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: per (unit, tap) one activation box and one weight tile =================
+    for (uint32_t it = 0; it < total; ++it) {
+      const int sa = it % RC2T_A_STAGES, sb = it % RC2T_B_STAGES;
+      const uint32_t tap = it % 25u, unit_no = it / 25u;
+      const int g0 = ((int)blockIdx.x + (int)unit_no * (int)gridDim.x) * RC2_GLYPHS;
+      const int dy = (int)tap / 5, dx = (int)tap - dy * 5;
+      mbar_wait(&emptyA[sa], ((it / RC2T_A_STAGES) & 1) ^ 1, err, 34);
+      mbar_wait(&emptyB[sb], ((it / RC2T_B_STAGES) & 1) ^ 1, err, 32);
+      if (elect_one()) {
+        mbar_expect_tx(&fullA[sa], RC2_A_STAGE);
+        tma_load_4d(sA + sa * RC2_A_STAGE, &tmA, &fullA[sa], 0, dx, dy, g0);  // glyphs past the end: zero fill
+        mbar_expect_tx(&fullB[sb], RC2_B_STAGE);
+        tma_load_2d(sB + sb * RC2_B_STAGE, &tmW, &fullB[sb], 0, (int)tap * 128);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc_f16(128);
+    for (uint32_t it = 0; it < total; ++it) {
+      const int sa = it % RC2T_A_STAGES, sb = it % RC2T_B_STAGES;
+      const uint32_t tap = it % 25u, unit_no = it / 25u, acc = unit_no & 1;
+      if (tap == 0) {
+        mbar_wait(&tempty[acc], ((unit_no >> 1) & 1) ^ 1, err, 31);
+        tc_fence_after();
+      }
+      mbar_wait(&fullB[sb], (it / RC2T_B_STAGES) & 1, err, 33);
+      mbar_wait(&fullA[sa], (it / RC2T_A_STAGES) & 1, err, 36);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t bdesc = make_smem_desc(sB + sb * RC2_B_STAGE);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint64_t adesc = make_smem_desc(sA + sa * RC2_A_STAGE + mt * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + acc * 256 + mt * 128, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (tap | (uint32_t)k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&emptyA[sa]);
+        umma_commit(&emptyB[sb]);
+        if (tap == 24) umma_commit(&tfull[acc]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue (as in rec_conv2_tc_kernel): main + 2^-11 * scaled + bias -> 2x2 max-pool -> split halves =================
+    const int q = warp & 3;
+    uint32_t unit_no = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++unit_no) {
+      const int g0 = unit * RC2_GLYPHS;
+      const uint32_t acc = unit_no & 1;
+      mbar_wait(&tfull[acc], (unit_no >> 1) & 1, err, 35);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int row = q * 32 + lane;
+        const int g = g0 + 2 * mt + (row >> 6);
+        const int oy = (row >> 3) & 7, ox = row & 7;
+        const bool writer = ((lane & 1) | (lane & 8)) == 0;
+        const int p = (oy >> 1) * 4 + (ox >> 1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + (uint32_t)(mt * 128);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float m[32], sc[32];
+          tmem_ld32(taddr + h * 32, m);
+          tmem_ld32(taddr + 64 + h * 32, sc);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float v = (m[c] + sc[c] * SPLIT_INV) + s_bias[h * 32 + c];
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+            if (writer && g < B) {
+              __half hi, lo;
+              split_f16(v, hi, lo);
+              __half *o = out + (int64_t)g * 2048 + (h * 32 + c) * 16 + p;
+              o[0] = hi;
+              o[1024] = lo;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // fc1 + bias + ReLU as a split-fp16 GEMM
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int RFC_STAGES = 4;
@@ -618,9 +757,21 @@ int launch_rec_conv1_tc(ocrb_ctx *ctx, const uint8_t *glyphs, const float *w, co
   return check_launch(ctx, "rec_tc:conv1");
 }
 
+int make_act_tensor_map_box_b(CUtensorMap *map, const void *base, int B, int H, int W, int C, int box_w, int box_h, int box_b);
+
 int launch_rec_conv2_tc(ocrb_ctx *ctx, const __half *act, const uint16_t *w_packed, const float *bias, int B, __half *out, int *err) {
   CUtensorMap tmW;
   OCRB_TRY(make_weight_tensor_map(&tmW, w_packed, 25 * 128, 64, 128));
+  static const bool builders = getenv("OCRB_REC_CONV2") && strcmp(getenv("OCRB_REC_CONV2"), "smem") == 0;  // first form (knob)
+  if (!builders && B >= RC2_GLYPHS) {  // (a box may not be larger than the tensor)
+    CUtensorMap tmA;
+    OCRB_TRY(make_act_tensor_map_box_b(&tmA, act, B, 12, 12, 64, 8, 8, RC2_GLYPHS));
+    OCRB_TRY(ensure_dyn_smem(ctx, rec_conv2_tma_kernel, RC2T_SMEM));
+    const int units_t = (B + RC2_GLYPHS - 1) / RC2_GLYPHS;
+    const int grid_t = units_t < ctx->sm_count ? units_t : ctx->sm_count;
+    rec_conv2_tma_kernel<<<grid_t, RC2T_THREADS, RC2T_SMEM, ctx->stream>>>(tmA, tmW, bias, B, out, err);
+    return check_launch(ctx, "rec_tc:conv2");
+  }
   OCRB_TRY(ensure_dyn_smem(ctx, rec_conv2_tc_kernel, RC2_SMEM));
   const int units = (B + RC2_GLYPHS - 1) / RC2_GLYPHS;
   const int grid = units < ctx->sm_count ? units : ctx->sm_count;
