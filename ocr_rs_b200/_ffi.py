@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libocrb.so")
+LIB_PATH = os.environ.get("OCRB_LIB_PATH") or os.path.join(_HERE, "libocrb.so")  # (override: A/B runs of two builds)
 
 OK = 0
 MODE_FP32, MODE_BF16 = 0, 1

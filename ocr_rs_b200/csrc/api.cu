@@ -72,7 +72,12 @@ int ocrb_ctx_create(int device, ocrb_ctx **out) {
   ocrb_ctx *ctx = new ocrb_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  // experiment knob OCRB_PP_HIGHPRIO=1: the context's own stream (post-processing in the pipeline) at the highest priority,
+  // so that its CTAs are placed before those of the forward stream's next persistent kernel
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  const bool pp_high = getenv("OCRB_PP_HIGHPRIO") && atoi(getenv("OCRB_PP_HIGHPRIO")) != 0;
+  cudaError_t e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, pp_high ? prio_hi : 0);
   if (e != cudaSuccess) {
     delete ctx;
     set_error("cudaStreamCreate -> %s", cudaGetErrorString(e));

@@ -124,6 +124,8 @@ struct ocrb_ctx {
   std::vector<const void *> smem_attr_done;  // kernels whose dynamic shared-memory limit this ctx has raised
   int sm_limit = 0;                          // > 0: persistent convolution kernels use at most this many SMs (pipeline.cu)
   ocrb::Profiler prof;
+  // SMs a persistent kernel of this context may occupy
+  int sm_budget() const { return sm_limit > 0 && sm_limit < sm_count ? sm_limit : sm_count; }
 };
 
 namespace ocrb {

@@ -654,7 +654,7 @@ static int launch_halo_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensor
   auto kern = conv_halo_kernel<N_TILE, G, CG, TS>;
   OCRB_TRY(ensure_dyn_smem(ctx, kern, 227 * 1024 - 4096));
   const int smem = 1024 + g.a_stages * g.a_stage_bytes + g.b_stages * (N_TILE / CG) * 128 + (TS ? g.obufs * g.obuf_bytes : HL_STG_BYTES) + 512;
-  int grid = num_units * CG < ctx->sm_count ? num_units * CG : (ctx->sm_count / CG) * CG;
+  int grid = num_units * CG < ctx->sm_budget() ? num_units * CG : (ctx->sm_budget() / CG) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3((1 + (G >= 4 ? 2 : 1) + HL_EPI_WARPS + TS) * 32);

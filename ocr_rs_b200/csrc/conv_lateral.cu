@@ -270,7 +270,7 @@ int launch_conv_lateral(ocrb_ctx *ctx, const __nv_bfloat16 *in, const __nv_bfloa
   const int smem = 1024 + p.chunks * LT_W_BYTES + p.a_stages * p.chunks * LT_A_BYTES + LT_ADD_STAGES * LT_ADD_BYTES + LT_NOB * LT_OB_BYTES + 512;
   OCRB_TRY(ensure_dyn_smem(ctx, conv_lateral_kernel, 227 * 1024));
   const int num_tiles = p.tiles_x * p.tiles_y * B;
-  const int grid = num_tiles < ctx->sm_count ? num_tiles : ctx->sm_count;
+  const int grid = num_tiles < ctx->sm_budget() ? num_tiles : ctx->sm_budget();
   conv_lateral_kernel<<<grid, LT_THREADS, smem, ctx->stream>>>(tmA, tmW, tmAdd, tmOut, tmSum, p);
   return check_launch(ctx, tag);
 }

@@ -477,7 +477,7 @@ static int launch_one(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &
   using L = TcSmem<N_TILE, STAGES, RING, EW>;
   auto kern = conv_tc_kernel<N_TILE, STAGES, EPI, RING, EW>;
   OCRB_TRY(ensure_dyn_smem(ctx, kern, L::DYN_BYTES));
-  int grid = num_tiles < ctx->sm_count ? num_tiles : ctx->sm_count;
+  int grid = num_tiles < ctx->sm_budget() ? num_tiles : ctx->sm_budget();
   kern<<<grid, (2 + EW) * 32, L::DYN_BYTES, ctx->stream>>>(tmA, tmB, p, hc);
   return check_launch(ctx, tag);
 }

@@ -170,9 +170,14 @@ static int run_pipeline(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, con
       }
       cudaStream_t saved = ctx->stream;
       ctx->stream = s_fwd;
+      // experiment knob: leave a few SMs to the post-processing stream while the persistent convolution kernels run
+      static const int sm_leave = getenv("OCRB_SM_LEAVE") ? atoi(getenv("OCRB_SM_LEAVE")) : 0;
+      const int saved_limit = ctx->sm_limit;
+      if (sm_leave > 0 && !serial) ctx->sm_limit = ctx->sm_count - sm_leave;
       rc = det_forward_device(det, src, OCRB_U8, bc, H, W, prob + (size_t)c0 * HW, bf16 ? bitmap + (size_t)c0 * HW : nullptr, (float)prm.thresh);
       if (rc == OCRB_OK && !bf16) rc = launch_binarize(ctx, prob + (size_t)c0 * HW, (int64_t)bc * HW, (float)prm.thresh, bitmap + (size_t)c0 * HW);
       ctx->stream = saved;
+      ctx->sm_limit = saved_limit;
     }
     if (rc == OCRB_OK) OCRB_CUDA(cudaEventRecord(ws->fwd_done[g & 1], s_fwd));
     if (rc == OCRB_OK && !img_dev && crop_k == 0) OCRB_CUDA(cudaEventRecord(ws->img_free[g & 1], s_fwd));

@@ -275,16 +275,23 @@ stem_tc3_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__
     // ================= producers: input patch -> four phase-shifted fp16 copies, interleaved per row pair =================
     const int pt = (warp - S3_EPI_WARPS) * 32 + lane;  // 0..127
     constexpr int PT = S3_PROD_WARPS * 32;
+    // per-thread constants: this thread's 16-byte chunk of the raw prefetch (row prow, chunk pc) and its build item (row by,
+    // 8-pixel group bu)
+    const int prow = pt / (S3_RAW_ROW / 16), pc = pt - prow * (S3_RAW_ROW / 16);
+    const bool pf = pt < S3_ROWS * (S3_RAW_ROW / 16);
+    const int bu = pt & 7, by = pt >> 3;
+    const uint32_t b_src = (uint32_t)(by * S3_RAW_ROW + 8 * bu), b_dst = (uint32_t)((by >> 1) * 1024 + (by & 1) * 128 + bu * 16);
+    uint32_t deltas = 0;  // byte offset (0, 4, 8, 12) of patch column -3 inside raw buffer rb: bits [4 rb, 4 rb + 4)
     auto prefetch_raw = [&](int unit, int rb) {  // u8 path: raw patch rows as 16-byte chunks, zero-filled outside the image
       int b, py0, px0;
       unit_origin(unit, b, py0, px0);
-      const int iy0 = 4 * py0 - 5, xa = (4 * px0 - 8) & ~15;
-      const uint8_t *img = reinterpret_cast<const uint8_t *>(in) + (int64_t)b * H * W;
-      for (int k = pt; k < S3_ROWS * (S3_RAW_ROW / 16); k += PT) {
-        const int row = k / (S3_RAW_ROW / 16), c = k - row * (S3_RAW_ROW / 16);
-        const int yy = iy0 + row, xx = xa + 16 * c;
+      const int x8 = 4 * px0 - 8;
+      deltas = (deltas & ~(0xFu << (4 * rb))) | ((uint32_t)(x8 & 15) << (4 * rb));
+      if (pf) {
+        const int yy = 4 * py0 - 5 + prow, xx = (x8 & ~15) + 16 * pc;
         const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;  // (W % 16 == 0: a chunk is inside or outside as a whole)
-        cp_async_16_zfill(raw_u32 + rb * S3_RAW_BYTES + k * 16, ok ? img + (int64_t)yy * W + xx : img, ok);
+        const uint8_t *img = reinterpret_cast<const uint8_t *>(in);
+        cp_async_16_zfill(raw_u32 + (uint32_t)(rb * S3_RAW_BYTES + pt * 16), ok ? img + ((int64_t)b * H + yy) * W + xx : img, ok);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -293,26 +300,24 @@ stem_tc3_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__
       if ((int)blockIdx.x + step < units) prefetch_raw(blockIdx.x + step, 1); else asm volatile("cp.async.commit_group;" ::: "memory");
     }
     uint32_t n = 0;
+    int rb_cur = 0;  // n % 3
     for (int unit = blockIdx.x; unit < units; unit += step, ++n) {
       const uint32_t pb = n & 1;
       const uint32_t dst0 = patch_u32 + pb * S3_PATCH_BYTES;
+      const int rb_next = rb_cur == 0 ? 2 : rb_cur - 1;  // (n + 2) % 3
       if (sizeof(TIn) == 1) {
         // raw buffer n % 3 holds this unit.  After the barrier every producer's share of it has landed AND every producer
         // has finished building unit n - 1, whose raw buffer the prefetch of unit n + 2 reuses.
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         asm volatile("bar.sync 8, %0;" ::"r"(PT) : "memory");
-        if (unit + 2 * step < units) prefetch_raw(unit + 2 * step, (n + 2) % 3); else asm volatile("cp.async.commit_group;" ::: "memory");
+        if (unit + 2 * step < units) prefetch_raw(unit + 2 * step, rb_next); else asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      mbar_wait_relaxed(&pempty[pb], ((n >> 1) & 1) ^ 1, err, 52);
+      mbar_wait(&pempty[pb], ((n >> 1) & 1) ^ 1, err, 52);
       if (sizeof(TIn) == 1) {
         // one item = 8 patch columns group u of patch row y, all four phases: raw bytes delta + 8u + 3 + 2 phase .. + 7
-        int ub, upy0, upx0;
-        unit_origin(unit, ub, upy0, upx0);
-        const uint32_t rawb = raw_u32 + (n % 3) * S3_RAW_BYTES + (uint32_t)((4 * upx0 - 8) & 15);
         {
           {
-            const int u = pt & 7, y = pt >> 3;
-            const uint32_t ra = rawb + (uint32_t)(y * S3_RAW_ROW + 8 * u);
+            const uint32_t ra = raw_u32 + (uint32_t)(rb_cur * S3_RAW_BYTES) + ((deltas >> (4 * rb_cur)) & 15u) + b_src;
             uint32_t w0, w1, w2, w3, w4;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ra));
             asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(ra));
@@ -327,7 +332,7 @@ stem_tc3_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__
             u8x4_to_f16x4(__funnelshift_r(w1, w2, 8), g[3][0], g[3][1]);
             u8x4_to_f16x4(__funnelshift_r(w2, w3, 8), g[4][0], g[4][1]);
             u8x4_to_f16x4(__funnelshift_r(w3, w4, 8), g[5][0], g[5][1]);
-            const uint32_t d = dst0 + (uint32_t)((y >> 1) * 1024 + (y & 1) * 128 + u * 16);
+            const uint32_t d = dst0 + b_dst;
             sts_16(d, make_uint4(g[0][0], g[0][1], g[1][0], g[1][1]));        // phase 0: bytes 3..10
             sts_16(d + 256, make_uint4(g[3][0], g[3][1], g[4][0], g[4][1]));  // phase 1: bytes 5..12
             sts_16(d + 512, make_uint4(g[1][0], g[1][1], g[2][0], g[2][1]));  // phase 2: bytes 7..14
@@ -351,6 +356,7 @@ stem_tc3_kernel(const TIn *__restrict__ in, int B, int H, int W, const float *__
       }
       fence_proxy_async();
       mbar_arrive(&pfull[pb]);
+      rb_cur = rb_cur == 2 ? 0 : rb_cur + 1;
     }
   } else {
     // ================= MMA issuer: per unit 3 stages x 4 K steps of UMMA 128 x 128 x 16 + 1 stage of 128 x 32 x 16 =================

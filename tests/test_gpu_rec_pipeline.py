@@ -44,9 +44,12 @@ def test_rec_logits_and_argmax(env, kind, n):
     assert np.abs(l2 - ref).max() <= 1e-4
 
 
-def test_rec_fp32_cuda_core_path():
-    """OCRB_REC=fp32 (read once per process): the all-CUDA-core fp32 path of the glyph net gives the same classes and
-    logits within 1e-5 of the tensor-core fp16-split path's oracle."""
+@pytest.mark.parametrize("knobs", [{"OCRB_REC": "fp32"}, {"OCRB_REC_CONV1": "cuda"}, {"OCRB_REC_CONV2": "smem"},
+                                   {"OCRB_REC_CONV1": "cuda", "OCRB_REC_CONV2": "smem"}])
+def test_rec_alternate_paths(knobs):
+    """Knobs of the glyph net (read once per process): OCRB_REC=fp32 the all-CUDA-core fp32 path, OCRB_REC_CONV1=cuda conv1
+    on CUDA cores, OCRB_REC_CONV2=smem conv2 with the shared-memory builder warps instead of TMA boxes.  Same classes,
+    logits within 1e-5 of the oracle."""
     import os
     import subprocess
     import sys
@@ -62,7 +65,7 @@ ref = mo.rec_forward(w, g.astype(np.float32) / np.float32(255.0)).numpy()
 print("WORST", float(np.abs(logits - ref).max()), int((argmax != ref.argmax(-1)).sum()))
 """
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, OCRB_REC="fp32", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), **knobs)
     out = subprocess.run([sys.executable, "-c", script], env=env, cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     worst, mism = [l for l in out.stdout.splitlines() if l.startswith("WORST")][-1].split()[1:]

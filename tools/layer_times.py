@@ -20,9 +20,13 @@ img = torch.from_numpy(synth.document_image_shard(0, n, 800, 800).reshape(n, 1, 
 out = torch.empty((n, 1, 800, 800), dtype=torch.float32, device="cuda")
 for _ in range(3):
     net.forward_t(img, out=out)
-ctx.profile_begin()
-net.forward_t(img, out=out)
-prof = ctx.profile_end()
+prof = {}
+for _ in range(5):  # per-name minimum over five profiled forwards (single serialised runs show one-off outliers)
+    ctx.profile_begin()
+    net.forward_t(img, out=out)
+    for k, (c, ms) in ctx.profile_end().items():
+        if k not in prof or ms < prof[k][1]:
+            prof[k] = (c, ms)
 tot = 0.0
 for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
     tot += ms
