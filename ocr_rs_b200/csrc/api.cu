@@ -95,6 +95,7 @@ int ocrb_ctx_destroy(ocrb_ctx *ctx) {
   free_pipe(ctx);
   for (auto &b : ctx->stage) b.release();
   ctx->ccl_tile_empty.release();
+  ctx->ccl_seam_list.release();
   ctx->decode_rgba.release();
   for (auto &b : ctx->pin) b.release();
   cudaStreamDestroy(ctx->stream);

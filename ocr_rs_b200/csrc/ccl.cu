@@ -56,7 +56,7 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b) {
 // ---------------------------------------------------------------------------------------
 constexpr int CCL_THREADS = 256;
 constexpr int CCL_ROWS_PER_WARP = CCL_TH / (CCL_THREADS / 32);
-constexpr int CCL_STRIP = 4;  // tiles per CTA: a 32-row x 128-column strip
+constexpr int CCL_STRIP = 16;  // tiles per CTA: a 32-row x 512-column strip (16 KB, four 16-byte loads per thread)
 
 // one tile with foreground: union-find in shared memory (L: CCL_TW * CCL_TH ints)
 __device__ __forceinline__ void ccl_tile(const uint8_t *__restrict__ bm, int H, int W, int tx, int ty, int *__restrict__ labels_img, int *L,
@@ -136,8 +136,10 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *_
   int *labels_img = labels + (int64_t)b * H * W;
   if (threadIdx.x < CCL_STRIP) s_any[threadIdx.x] = 0;
   __syncthreads();
-  {
-    const int r = threadIdx.x >> 3, c = threadIdx.x & 7;  // 32 rows x 8 chunks of 16 pixels
+#pragma unroll
+  for (int it = 0; it < CCL_TH * CCL_STRIP * 2 / CCL_THREADS; ++it) {
+    const int idx = threadIdx.x + it * CCL_THREADS;
+    const int r = idx / (CCL_STRIP * 2), c = idx - r * (CCL_STRIP * 2);  // 32 rows x (2 * CCL_STRIP) chunks of 16 pixels
     const int y = ty * CCL_TH + r, x = sx * CCL_STRIP * CCL_TW + c * 16;
     bool nz = false;
     if (y < H && x < W) {
@@ -152,20 +154,22 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *_
     if (nz) s_any[c >> 1] = 1;  // benign race: every writer stores 1
   }
   __syncthreads();
+  if (threadIdx.x < CCL_STRIP) {  // one thread per tile of the strip: the flag, and the only label a tile without foreground stores
+    const int tx = sx * CCL_STRIP + threadIdx.x;
+    if (tx < tiles_x) {
+      const int any_fg = s_any[threadIdx.x];
+      tile_empty[(int64_t)b * tiles_x * tiles_y + ty * tiles_x + tx] = (uint8_t)!any_fg;  // the seam pass and the label consumers read this
+      if (!any_fg) {
+        const int origin = ty * CCL_TH * W + tx * CCL_TW;
+        labels_img[origin] = origin;
+      }
+    }
+  }
 #pragma unroll 1
   for (int t = 0; t < CCL_STRIP; ++t) {
     const int tx = sx * CCL_STRIP + t;
     if (tx >= tiles_x) break;
-    const int any_fg = s_any[t];
-    if (threadIdx.x == 0) tile_empty[(int64_t)b * tiles_x * tiles_y + ty * tiles_x + tx] = (uint8_t)!any_fg;  // the seam pass and the label consumers read this
-    if (!any_fg) {
-      if (threadIdx.x == 0) {
-        const int origin = ty * CCL_TH * W + tx * CCL_TW;
-        labels_img[origin] = origin;  // the only label an empty tile stores
-      }
-      continue;
-    }
-    ccl_tile(bm, H, W, tx, ty, labels_img, L, rowbits, rowvalid);
+    if (s_any[t]) ccl_tile(bm, H, W, tx, ty, labels_img, L, rowbits, rowvalid);
   }
 }
 
@@ -173,63 +177,99 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_local_kernel(const uint8_t *_
 // pass 2: seams.  A pixel whose W / NW / N / NE neighbour lies in another tile unites with
 // it in global memory (same adjacency rules as pass 1).
 // ---------------------------------------------------------------------------------------
-// One warp per tile; its lanes walk the tile's border pixels (top row, left column, right column).  A tile without
-// foreground whose left and upper neighbours have none either needs exactly one link (its corner pixel): one lane works,
-// nothing else is even read — on a document page that is almost every tile.
-__global__ void ccl_seam_kernel(const uint8_t *__restrict__ bitmap, int H, int W, int B, int tiles_x, int tiles_y,
-                                int *__restrict__ labels, const uint8_t *__restrict__ tile_empty) {
+// The lanes of a warp walk a tile's border pixels (top row, left column, right column).  A tile without foreground whose
+// left and upper neighbours have none either needs exactly one link (its corner pixel) — on a document page that is almost
+// every tile — so a CTA first gives every one of its 256 tiles ONE thread, which does that single link itself, and only
+// the remaining tiles are walked by whole warps.
+// border pixels a tile has to look at (k < k_end of top row | left column | right column): between tiles without
+// foreground the corner pixel (k = 0, which always runs the full rules) makes the one link needed:
+//   * right column: only foreground pixels link diagonally from there;
+//   * left column below the corner: the link to the left tile is redundant when that tile is empty too;
+//   * top row right of the corner: the link upwards is skipped by the run rule when the upper tile is empty too.
+struct SeamTile { int b, tx, ty, k_end; bool empty, left_empty, up_empty; };
+__device__ __forceinline__ SeamTile seam_tile_of(int64_t tile, int tiles_x, int tiles_y, const uint8_t *__restrict__ tile_empty) {
   constexpr int PER_TILE = CCL_TW + 2 * CCL_TH;
-  const int lane = threadIdx.x & 31;
-  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t tiles = (int64_t)tiles_x * tiles_y * B;
-  if (tile >= tiles) return;
-  const int b = (int)(tile / ((int64_t)tiles_x * tiles_y));
+  SeamTile t;
+  t.b = (int)(tile / ((int64_t)tiles_x * tiles_y));
   const int tt = (int)(tile % ((int64_t)tiles_x * tiles_y));
-  const int tx = tt % tiles_x, ty = tt / tiles_x;
-  const uint8_t *te = tile_empty + (int64_t)b * tiles_x * tiles_y;
-  const bool empty = te[tt] != 0;
-  const bool left_empty = tx > 0 && te[tt - 1], up_empty = ty > 0 && te[tt - tiles_x];
-  // between tiles without foreground the corner pixel (k = 0, which always runs the full rules) makes the one link needed:
-  //   * right column: only foreground pixels link diagonally from there;
-  //   * left column below the corner: the link to the left tile is redundant when that tile is empty too;
-  //   * top row right of the corner: the link upwards is skipped by the run rule when the upper tile is empty too.
-  const int k_end = !empty ? PER_TILE : (((tx > 0 && !left_empty) ? CCL_TW + CCL_TH : ((ty > 0 && !up_empty) ? CCL_TW : 1)));
+  t.tx = tt % tiles_x; t.ty = tt / tiles_x;
+  const uint8_t *te = tile_empty + (int64_t)t.b * tiles_x * tiles_y;
+  t.empty = te[tt] != 0;
+  t.left_empty = t.tx > 0 && te[tt - 1]; t.up_empty = t.ty > 0 && te[tt - tiles_x];
+  t.k_end = !t.empty ? PER_TILE : (((t.tx > 0 && !t.left_empty) ? CCL_TW + CCL_TH : ((t.ty > 0 && !t.up_empty) ? CCL_TW : 1)));
+  return t;
+}
+__device__ __forceinline__ void seam_border_pixel(int k, const SeamTile &t, const uint8_t *__restrict__ bitmap, int H, int W, int tiles_x, int tiles_y,
+                                                  int *__restrict__ labels, const uint8_t *__restrict__ tile_empty) {
   const int64_t HW = (int64_t)H * W;
-  const uint8_t *bm = bitmap + b * HW;
-  int *L = labels + b * HW;
+  const uint8_t *te = tile_empty + (int64_t)t.b * tiles_x * tiles_y;
+  const uint8_t *bm = bitmap + t.b * HW;
+  int *L = labels + t.b * HW;
   auto node = [&](int px, int py) {  // a pixel of a tile without foreground stands for its tile origin (ccl.cuh)
     const int ttx = px / CCL_TW, tty = py / CCL_TH;
     return te[tty * tiles_x + ttx] ? tty * CCL_TH * W + ttx * CCL_TW : py * W + px;
   };
-  for (int k = lane; k < k_end; k += 32) {
-    int x, y;
-    if (k < CCL_TW) { x = tx * CCL_TW + k; y = ty * CCL_TH; }
-    else if (k < CCL_TW + CCL_TH) { x = tx * CCL_TW; y = ty * CCL_TH + (k - CCL_TW); }
-    else { x = tx * CCL_TW + CCL_TW - 1; y = ty * CCL_TH + (k - CCL_TW - CCL_TH); }
-    if (x >= W || y >= H) continue;
-    const bool on_left = (x % CCL_TW) == 0, on_right = (x % CCL_TW) == CCL_TW - 1, on_top = (y % CCL_TH) == 0;
-    // corner pixels appear in two of the three groups: let the top-row instance do the work
-    if (k >= CCL_TW && on_top) continue;
-    if (empty) {
-      if (k >= CCL_TW && left_empty) continue;
-      if (k > 0 && k < CCL_TW && up_empty) continue;
+  int x, y;
+  if (k < CCL_TW) { x = t.tx * CCL_TW + k; y = t.ty * CCL_TH; }
+  else if (k < CCL_TW + CCL_TH) { x = t.tx * CCL_TW; y = t.ty * CCL_TH + (k - CCL_TW); }
+  else { x = t.tx * CCL_TW + CCL_TW - 1; y = t.ty * CCL_TH + (k - CCL_TW - CCL_TH); }
+  if (x >= W || y >= H) return;
+  const bool on_left = (x % CCL_TW) == 0, on_right = (x % CCL_TW) == CCL_TW - 1, on_top = (y % CCL_TH) == 0;
+  // corner pixels appear in two of the three groups: let the top-row instance do the work
+  if (k >= CCL_TW && on_top) return;
+  if (t.empty) {
+    if (k >= CCL_TW && t.left_empty) return;
+    if (k > 0 && k < CCL_TW && t.up_empty) return;
+  }
+  const int i = y * W + x;
+  const int fg = bm[i] != 0;
+  const int self = node(x, y);
+  if (on_left && x > 0 && (bm[i - 1] != 0) == fg) uf_union(L, self, node(x - 1, y));
+  if (y > 0) {
+    const int n_fg = bm[i - W] != 0;
+    if (on_top && n_fg == fg) {
+      // same redundancy rule as the tile-local pass, along the whole image row
+      const bool skip = x > 0 && (bm[i - 1] != 0) == fg && (bm[i - W - 1] != 0) == fg;
+      if (!skip) uf_union(L, self, node(x, y - 1));
     }
-    const int i = y * W + x;
-    const int fg = bm[i] != 0;
-    const int self = node(x, y);
-    if (on_left && x > 0 && (bm[i - 1] != 0) == fg) uf_union(L, self, node(x - 1, y));
-    if (y > 0) {
-      const int n_fg = bm[i - W] != 0;
-      if (on_top && n_fg == fg) {
-        // same redundancy rule as the tile-local pass, along the whole image row
-        const bool skip = x > 0 && (bm[i - 1] != 0) == fg && (bm[i - W - 1] != 0) == fg;
-        if (!skip) uf_union(L, self, node(x, y - 1));
-      }
-      if (fg && !n_fg) {  // foreground pixels are never in an "empty" tile
-        if (x > 0 && (on_top || on_left) && bm[i - W - 1] != 0) uf_union(L, i, i - W - 1);
-        if (x + 1 < W && (on_top || on_right) && bm[i - W + 1] != 0) uf_union(L, i, i - W + 1);
-      }
+    if (fg && !n_fg) {  // foreground pixels are never in an "empty" tile
+      if (x > 0 && (on_top || on_left) && bm[i - W - 1] != 0) uf_union(L, i, i - W - 1);
+      if (x + 1 < W && (on_top || on_right) && bm[i - W + 1] != 0) uf_union(L, i, i - W + 1);
     }
+  }
+}
+
+// first kernel: one THREAD per tile.  A tile that only needs its corner pixel (on a document page almost every tile) is
+// finished by that thread; the others are appended to a list (warp-aggregated atomics) ...
+__global__ void __launch_bounds__(256) ccl_seam_kernel(const uint8_t *__restrict__ bitmap, int H, int W, int B, int tiles_x, int tiles_y,
+                                                       int *__restrict__ labels, const uint8_t *__restrict__ tile_empty, int *__restrict__ list) {
+  const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tiles = (int64_t)tiles_x * tiles_y * B;
+  bool heavy = false;
+  if (tile < tiles) {
+    const SeamTile t = seam_tile_of(tile, tiles_x, tiles_y, tile_empty);
+    if (t.k_end == 1) seam_border_pixel(0, t, bitmap, H, W, tiles_x, tiles_y, labels, tile_empty);
+    else heavy = true;
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, heavy);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(&list[0], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (heavy) list[1 + base + __popc(m & ((1u << lane) - 1))] = (int)tile;
+  }
+}
+// ... which the second kernel walks with one WARP per listed tile (grid-stride: the launch does not know the count)
+__global__ void __launch_bounds__(256) ccl_seam_heavy_kernel(const uint8_t *__restrict__ bitmap, int H, int W, int tiles_x, int tiles_y,
+                                                             int *__restrict__ labels, const uint8_t *__restrict__ tile_empty,
+                                                             const int *__restrict__ list) {
+  const int lane = threadIdx.x & 31;
+  const int n = list[0];
+  const int warps = (int)((gridDim.x * blockDim.x) >> 5);
+  for (int j = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); j < n; j += warps) {
+    const SeamTile t = seam_tile_of(list[1 + j], tiles_x, tiles_y, tile_empty);
+    for (int k = lane; k < t.k_end; k += 32) seam_border_pixel(k, t, bitmap, H, W, tiles_x, tiles_y, labels, tile_empty);
   }
 }
 
@@ -257,8 +297,17 @@ int launch_ccl(ocrb_ctx *ctx, const uint8_t *bitmap, int B, int H, int W, int *l
   ccl_local_kernel<<<(unsigned)((int64_t)strips_x * tiles_y * B), CCL_THREADS, 0, ctx->stream>>>(bitmap, H, W, tiles_x, tiles_y, strips_x, labels, tile_empty);
   OCRB_TRY(check_launch(ctx, "ccl_local"));
   int64_t n = (int64_t)B * H * W;
-  ccl_seam_kernel<<<(unsigned)cdiv(blocks * 32, 256), 256, 0, ctx->stream>>>(bitmap, H, W, B, tiles_x, tiles_y, labels, tile_empty);
+  OCRB_REQUIRE(blocks < ((int64_t)1 << 31), "ccl: too many tiles");
+  OCRB_TRY(ctx->ccl_seam_list.reserve((size_t)(blocks + 1) * 4));
+  int *seam_list = ctx->ccl_seam_list.as<int>();
+  OCRB_CUDA(cudaMemsetAsync(seam_list, 0, 4, ctx->stream));
+  ccl_seam_kernel<<<(unsigned)cdiv(blocks, 256), 256, 0, ctx->stream>>>(bitmap, H, W, B, tiles_x, tiles_y, labels, tile_empty, seam_list);
   OCRB_TRY(check_launch(ctx, "ccl_seam"));
+  {
+    const int64_t want = cdiv(blocks * 32, 256), cap = (int64_t)ctx->sm_count * 8;
+    ccl_seam_heavy_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(bitmap, H, W, tiles_x, tiles_y, labels, tile_empty, seam_list);
+    OCRB_TRY(check_launch(ctx, "ccl_seam_heavy"));
+  }
   if (!flatten) return OCRB_OK;
   CclTiles tiles = {tile_empty, tiles_x, tiles_x * tiles_y};
   ccl_flatten_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(H, W, B, labels, tiles);

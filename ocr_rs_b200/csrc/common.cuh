@@ -119,6 +119,7 @@ struct ocrb_ctx {
   ocrb::PinBuf pin[3];
   ocrb::DevBuf decode_rgba;     // decoded RGBA arena of ocrb_preprocess_files (decode.cu)
   ocrb::DevBuf ccl_tile_empty;  // one byte per CCL tile of the last labelling: 1 = no foreground pixel (ccl.cu)
+  ocrb::DevBuf ccl_seam_list;   // [0] = count, [1..] = tiles whose seams need a whole warp (ccl.cu)
   ocrb::PostprocWorkspace *pp = nullptr;
   ocrb::PipelineWorkspace *pipe = nullptr;  // streams / events / buffers of ocrb_detect_and_recognize, created on first use
   std::vector<const void *> smem_attr_done;  // kernels whose dynamic shared-memory limit this ctx has raised
