@@ -41,7 +41,7 @@ struct TcSmem {
   static constexpr int OFF_STG = OFF_B + STAGES * B_BYTES;
   static constexpr int OFF_RING = OFF_STG + EW * 2048;            // per-warp 2 KB staging, then RING x 2 KB per warp (addend prefetch)
   static constexpr int OFF_BAR = OFF_RING + EW * RING * 2048;  // full[STAGES], empty[STAGES], tfull[2], tempty[2]
-  static constexpr int OFF_TMEM = OFF_BAR + (2 * STAGES + 4) * 8;
+  static constexpr int OFF_TMEM = OFF_BAR + (2 * STAGES + 8) * 8;  // + hready[2], zfull[2] (EPI_HEAD2)
   static constexpr int TOTAL = OFF_TMEM + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;                 // slack for manual 1024 B alignment
 };
@@ -54,7 +54,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int TC_THREADS = (2 + EW) * 32;
   // DB head tail with 16 epilogue warps: TWO groups of 8, group g owns accumulator stage g and takes every
   // second tile of this CTA — the tail is FP32-issue/latency bound, so two tiles in flight fill the schedulers
-  constexpr int GROUPS = (EPI == EPI_HEAD && EW == 16) ? 2 : 1;
+  constexpr bool HEAD = EPI == EPI_HEAD || EPI == EPI_HEAD2;
+  constexpr int GROUPS = (HEAD && EW == 16) ? 2 : 1;
+  static_assert(EPI != EPI_HEAD2 || (EW == 16 && N_TILE == 256), "tensor-core head tail: two epilogue groups, four taps of 64 channels");
   constexpr int PARTS = EW / 4 / GROUPS;  // column parts
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(16) float s_scale[512], s_shift[512];
@@ -65,6 +67,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t *empty = full + STAGES;
   uint64_t *tfull = empty + STAGES;
   uint64_t *tempty = tfull + 2;
+  uint64_t *hready = tempty + 2, *zfull = hready + 2;  // EPI_HEAD2: A operand of the second GEMM written / its result complete
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,7 +78,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_tiles = num_m_tiles * p.num_n_tiles;
 
   // ---- one-time setup ----
-  const int n_sc = (EPI == EPI_HEAD) ? 0 : (p.Cout < 512 ? p.Cout : 512);
+  const int n_sc = HEAD ? 0 : (p.Cout < 512 ? p.Cout : 512);
   for (int i = threadIdx.x; i < n_sc; i += TC_THREADS) {
     s_scale[i] = p.scale ? p.scale[i] : 1.0f;
     s_shift[i] = p.shift ? p.shift[i] : 0.0f;
@@ -85,12 +88,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int s = i / 96, w = i % 96;
     reinterpret_cast<uint32_t *>(sA + s * TC_A_BYTES + TC_ROWS * 128)[w] = 0u;
   }
+  if (EPI == EPI_HEAD2 && threadIdx.x < 128) {
+    // B operand of the second GEMM: [16 rows n][64 channels] bf16, K-major, 128B swizzle.  Rows 0..3 = the conv-transpose-2
+    // weights of output q = n rounded to bf16, rows 4..7 = what the rounding dropped (the two partial sums are added in the
+    // epilogue, so the weights count with 16 significant bits), rows 8..15 = 0 (N = 16 is the narrowest M = 128 shape).
+    const int n = threadIdx.x >> 3, j = threadIdx.x & 7;
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float f[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float x = hc.w2[(8 * j + 2 * e + h) * 4 + (n & 3)];
+        const float hi = __bfloat162float(__float2bfloat16_rn(x));
+        f[h] = n < 4 ? hi : (n < 8 ? x - hi : 0.0f);
+      }
+      w[e] = pack_bf16(f[0], f[1]);
+    }
+    *reinterpret_cast<uint4 *>(smem + L::OFF_STG + n * 128 + ((j ^ (n & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EW / GROUPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&hready[a], EW / GROUPS); mbar_init(&zfull[a], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -112,8 +135,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < p.S; ++s)
           for (int ck = 0; ck < p.cin_chunks; ++ck) {
             mbar_wait(&empty[stage], phase ^ 1, p.err, 1);
+            // EPI_HEAD2 (one K block per tile): the weight tile is loaded once, into stage 0's slot, and stays there
+            const bool load_b = EPI != EPI_HEAD2 || tile == (int)blockIdx.x;
             if (elect_one()) {
-              mbar_expect_tx(&full[stage], TC_A_TX + L::B_BYTES);
+              mbar_expect_tx(&full[stage], TC_A_TX + (load_b ? L::B_BYTES : 0));
               int a_c = ck * 64;
               if (p.split_nblk) {  // K block -> (term plane, 64-channel chunk) of the split activation tensor (conv_tc.cuh)
                 const int chunk = ck / p.split_nblk, j = ck - chunk * p.split_nblk;
@@ -121,7 +146,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 a_c = plane * p.split_cin + chunk * 64;
               }
               tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], a_c, x_base + s, y_base + r, b);
-              tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full[stage], ((r * p.S + s) * p.cin_chunks + ck) * 64, n_tile * N_TILE);
+              if (load_b) tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full[stage], ((r * p.S + s) * p.cin_chunks + ck) * 64, n_tile * N_TILE);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -134,7 +159,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    if (EPI == EPI_HEAD2) {
+      // GEMM 1 of tile i (conv-transpose 1: [125 px][64] x [64][4 taps x 64]) is followed by GEMM 2 of tile i - 1 (per tap
+      // [125 px][64 bf16 in TMEM] x [64][16]) as soon as that tile's epilogue group has written its A operand
+      constexpr uint32_t idesc2 = make_idesc(16);
+      const uint64_t bdesc1 = make_smem_desc(sB);
+      const uint64_t bdesc2 = make_smem_desc(smem + L::OFF_STG);
+      auto gemm2 = [&](int j) {
+        const int a2 = j & 1;
+        mbar_wait(&hready[a2], (uint32_t)((j >> 1) & 1), p.err, 5);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t base = tmem_base + (uint32_t)(a2 * N_TILE);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(base + (uint32_t)(t * 64 + 32), base + (uint32_t)(t * 64 + 8 * k), bdesc2 + (uint64_t)(2 * k), idesc2, k != 0 ? 1u : 0u);
+          umma_commit(&zfull[a2]);
+        }
+        __syncwarp();
+      };
+      // Both GEMMs are issued as soon as their own condition holds (polling, no fixed order): GEMM 1 of tile g1 when its
+      // accumulator stage is free (the epilogue of tile g1 - 2 has READ its results — the sigmoid and the stores come after
+      // the release), GEMM 2 of tile g2 when that tile's operand is written.
+      const int n_local = (int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      int g1 = 0, g2 = 0;
+      long long t0 = clock64();
+      while (g2 < n_local) {
+        bool progress = false;
+        if (g2 < g1 && mbar_try_wait(&hready[g2 & 1], (uint32_t)((g2 >> 1) & 1))) {
+          gemm2(g2);
+          ++g2;
+          progress = true;
+        }
+        if (g1 < n_local && mbar_try_wait(&tempty[g1 & 1], (uint32_t)(((g1 >> 1) & 1) ^ 1))) {
+          mbar_wait(&full[stage], phase, p.err, 3);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(sA + stage * TC_A_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + (uint32_t)((g1 & 1) * N_TILE), adesc + (uint64_t)(2 * k), bdesc1 + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+            umma_commit(&empty[stage]);
+            umma_commit(&tfull[g1 & 1]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          ++g1;
+          progress = true;
+        }
+        if (progress) {
+          t0 = clock64();
+        } else if (clock64() - t0 > 4000000000ll) {
+          if (p.err) { *reinterpret_cast<volatile int *>(p.err) = 7; __threadfence_system(); }
+          __trap();
+        }
+      }
+    }
+    for (int tile = blockIdx.x; EPI != EPI_HEAD2 && tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[acc], acc_phase ^ 1, p.err, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
@@ -275,6 +358,69 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+      } else if (EPI == EPI_HEAD2) {
+        // DB head tail, contraction on the tensor cores: per tap, BN + ReLU of the 64 conv-transpose-1 channels -> bf16 pairs
+        // written back over the accumulator's first 32 columns (lane = pixel, column = channel pair: the TMEM form of an A
+        // operand); the issuer warp multiplies them with the [64][16] tile of conv-transpose-2 weights into columns 32..47 of
+        // the same tap; this thread then reads its 4 + 4 partial sums, adds the bias, sigmoid, binarize.  Per pixel and tap:
+        // 32 packed FMAs + 32 conversions instead of 160 packed FMAs + 64 maxima on a dependent chain.
+        const int m = quarter * 32 + lane;
+        const int yl = m / TC_TW, xl = m - yl * TC_TW;
+        const int y = ty * TC_TH + yl, x = tx * TC_TW + xl;
+        const bool valid = m < TC_ROWS && y < p.Ho && x < p.Wo;
+        mbar_wait(&tfull[acc], acc_phase, p.err, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE);
+#pragma unroll
+        for (int tj = 0; tj < 2; ++tj) {
+          const uint32_t tap = taddr + (uint32_t)((half * 2 + tj) * 64);  // tap = i*2 + j with i = half
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            float v[32];
+            tmem_ld32(tap + c0, v);
+            uint32_t h[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const int co = c0 + j;
+              const float2 f = ffma2(make_float2(v[j], v[j + 1]), make_float2(hc.scale[co], hc.scale[co + 1]), make_float2(hc.shift[co], hc.shift[co + 1]));
+              h[j >> 1] = pack_bf16_relu(f.x, f.y);
+            }
+            tmem_st16(tap + (c0 >> 1), h);  // columns already read: the 16 packed pairs land on fp32 columns c0/2 .. c0/2 + 15
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hready[acc]);
+        mbar_wait(&zfull[acc], acc_phase, p.err, 6);
+        tc_fence_after();
+        float z[2][8];
+#pragma unroll
+        for (int tj = 0; tj < 2; ++tj) tmem_ld8(taddr + (uint32_t)((half * 2 + tj) * 64 + 32), z[tj]);
+        // the accumulator stage is free once its results are in registers: release it before the sigmoid and the stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        float o[2][4];
+#pragma unroll
+        for (int tj = 0; tj < 2; ++tj) {
+          // q = i'*2 + j' of conv-transpose 2: output (4y + 2i + i', 4x + 2j + j')
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q >> 1][2 * tj + (q & 1)] = __fdividef(1.0f, 1.0f + __expf(-(z[tj][q] + z[tj][4 + q] + p.b2)));
+        }
+        if (valid) {
+          const int64_t Wp = (int64_t)p.Wo * 4;
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const int64_t off = ((int64_t)b * p.Ho * 4 + (int64_t)y * 4 + 2 * half + a) * Wp + (int64_t)x * 4;
+            *reinterpret_cast<float4 *>(p.prob + off) = make_float4(o[a][0], o[a][1], o[a][2], o[a][3]);
+            if (p.bitmap) {
+              uint32_t bits = (o[a][0] > p.thresh ? 1u : 0u) | (o[a][1] > p.thresh ? 0x100u : 0u) |
+                              (o[a][2] > p.thresh ? 0x10000u : 0u) | (o[a][3] > p.thresh ? 0x1000000u : 0u);
+              *reinterpret_cast<uint32_t *>(p.bitmap + off) = bits;
+            }
+          }
+        }
       } else {
         static_assert(EPI != EPI_HEAD || PARTS == 2, "head epilogue splits the four taps over two warp halves");
         // DB head tail: columns n = tap(i,j)*64 + co of conv-transpose 1; per tap BN+ReLU then
@@ -339,9 +485,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (EPI != EPI_HEAD2) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
       if (GROUPS == 2) {
         acc_phase ^= 1;  // this group's stage is used by every second tile
       } else {
@@ -493,6 +641,10 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
   const int num_tiles = p.tiles_x * p.tiles_y * p.B * p.num_n_tiles;
   if (epi == EPI_HEAD) {
     if (n_tile != 256) { set_error("conv_tc head needs N tile 256"); return OCRB_ERR_INVALID; }
+    // default: the 64 -> 4 contraction of the tail as a second GEMM (OCRB_HEAD=cuda: on the CUDA cores, round 1's form)
+    static const bool head_cuda = getenv("OCRB_HEAD") && !strcmp(getenv("OCRB_HEAD"), "cuda");
+    if (!head_cuda && p.R == 1 && p.S == 1 && p.cin_chunks == 1 && p.num_n_tiles == 1 && !p.split_nblk)
+      return launch_one<256, 4, EPI_HEAD2, 0, 16>(ctx, tmA, tmB, p, num_tiles, tag, hc);
     static const bool ew8 = getenv("OCRB_HEAD_EW") && atoi(getenv("OCRB_HEAD_EW")) == 8;  // tuning knob
     return ew8 ? launch_one<256, 4, EPI_HEAD, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc)
                : launch_one<256, 4, EPI_HEAD, 0, 16>(ctx, tmA, tmB, p, num_tiles, tag, hc);
