@@ -54,9 +54,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int TC_THREADS = (2 + EW) * 32;
   // DB head tail with 16 epilogue warps: TWO groups of 8, group g owns accumulator stage g and takes every
   // second tile of this CTA — the tail is FP32-issue/latency bound, so two tiles in flight fill the schedulers
-  constexpr bool HEAD = EPI == EPI_HEAD || EPI == EPI_HEAD2;
+  constexpr bool HEAD2 = EPI == EPI_HEAD2 || EPI == EPI_HEAD2_TS;  // tensor-core head tail, second operand in shared memory / in TMEM
+  constexpr bool HEAD = EPI == EPI_HEAD || HEAD2;
+  // EPI_HEAD2 carve-up: three A stages; the [16][64] weight tile of the second GEMM in the fourth A slot; the conv-transpose-1
+  // weights resident in B slot 0; B slots 1..3 + the staging area = eight 16 KB tiles [128 px][64 ch] bf16 (stage x tap) for
+  // the A operand of the second GEMM when it is read from shared memory
+  constexpr int AS = HEAD2 ? 3 : STAGES;
+  static_assert(!HEAD2 || (STAGES == 4 && RING == 0), "EPI_HEAD2 shared-memory carve-up");
   constexpr int GROUPS = (HEAD && EW == 16) ? 2 : 1;
-  static_assert(EPI != EPI_HEAD2 || (EW == 16 && N_TILE == 256), "tensor-core head tail: two epilogue groups, four taps of 64 channels");
+  static_assert(!HEAD2 || (EW == 16 && N_TILE == 256), "tensor-core head tail: two epilogue groups, four taps of 64 channels");
   constexpr int PARTS = EW / 4 / GROUPS;  // column parts
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(16) float s_scale[512], s_shift[512];
@@ -88,7 +94,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int s = i / 96, w = i % 96;
     reinterpret_cast<uint32_t *>(sA + s * TC_A_BYTES + TC_ROWS * 128)[w] = 0u;
   }
-  if (EPI == EPI_HEAD2 && threadIdx.x < 128) {
+  if (HEAD2 && threadIdx.x < 128) {
     // B operand of the second GEMM: [16 rows n][64 channels] bf16, K-major, 128B swizzle.  Rows 0..3 = the conv-transpose-2
     // weights of output q = n rounded to bf16, rows 4..7 = what the rounding dropped (the two partial sums are added in the
     // epilogue, so the weights count with 16 significant bits), rows 8..15 = 0 (N = 16 is the narrowest M = 128 shape).
@@ -105,7 +111,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       w[e] = pack_bf16(f[0], f[1]);
     }
-    *reinterpret_cast<uint4 *>(smem + L::OFF_STG + n * 128 + ((j ^ (n & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4 *>(smem + 3 * TC_A_BYTES + n * 128 + ((j ^ (n & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
@@ -136,7 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int ck = 0; ck < p.cin_chunks; ++ck) {
             mbar_wait(&empty[stage], phase ^ 1, p.err, 1);
             // EPI_HEAD2 (one K block per tile): the weight tile is loaded once, into stage 0's slot, and stays there
-            const bool load_b = EPI != EPI_HEAD2 || tile == (int)blockIdx.x;
+            const bool load_b = !HEAD2 || tile == (int)blockIdx.x;
             if (elect_one()) {
               mbar_expect_tx(&full[stage], TC_A_TX + (load_b ? L::B_BYTES : 0));
               int a_c = ck * 64;
@@ -149,7 +155,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (load_b) tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full[stage], ((r * p.S + s) * p.cin_chunks + ck) * 64, n_tile * N_TILE);
             }
             __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == AS) { stage = 0; phase ^= 1; }
           }
     }
   } else if (warp == 1) {
@@ -159,23 +165,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    if (EPI == EPI_HEAD2) {
+    if (HEAD2) {
       // GEMM 1 of tile i (conv-transpose 1: [125 px][64] x [64][4 taps x 64]) is followed by GEMM 2 of tile i - 1 (per tap
       // [125 px][64 bf16 in TMEM] x [64][16]) as soon as that tile's epilogue group has written its A operand
       constexpr uint32_t idesc2 = make_idesc(16);
       const uint64_t bdesc1 = make_smem_desc(sB);
-      const uint64_t bdesc2 = make_smem_desc(smem + L::OFF_STG);
+      const uint64_t bdesc2 = make_smem_desc(smem + 3 * TC_A_BYTES);
+      constexpr bool h_in_tmem = EPI == EPI_HEAD2_TS;  // OCRB_HEAD=ts: A operand of the second GEMM in TMEM (128 tensor cycles per MMA: TMEM-read bound)
       auto gemm2 = [&](int j) {
         const int a2 = j & 1;
         mbar_wait(&hready[a2], (uint32_t)((j >> 1) & 1), p.err, 5);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t base = tmem_base + (uint32_t)(a2 * N_TILE);
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
+          if (h_in_tmem) {
+            // K step outermost: consecutive MMAs accumulate into different taps' results
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16_ts(base + (uint32_t)(t * 64 + 32), base + (uint32_t)(t * 64 + 8 * k), bdesc2 + (uint64_t)(2 * k), idesc2, k != 0 ? 1u : 0u);
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                umma_bf16_ts(base + (uint32_t)(t * 64 + 32), base + (uint32_t)(t * 64 + 8 * k), bdesc2 + (uint64_t)(2 * k), idesc2, k != 0 ? 1u : 0u);
+          } else {
+            const uint64_t hdesc = make_smem_desc(sB + L::B_BYTES + a2 * 4 * TC_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                umma_bf16(base + (uint32_t)(t * 64 + 32), hdesc + (uint64_t)(t * (TC_A_BYTES >> 4) + 2 * k), bdesc2 + (uint64_t)(2 * k), idesc2, k != 0 ? 1u : 0u);
+          }
           umma_commit(&zfull[a2]);
         }
         __syncwarp();
@@ -188,12 +205,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       long long t0 = clock64();
       while (g2 < n_local) {
         bool progress = false;
-        if (g2 < g1 && mbar_try_wait(&hready[g2 & 1], (uint32_t)((g2 >> 1) & 1))) {
+        if (g2 < g1 && mbar_test_wait(&hready[g2 & 1], (uint32_t)((g2 >> 1) & 1))) {
           gemm2(g2);
           ++g2;
           progress = true;
         }
-        if (g1 < n_local && mbar_try_wait(&tempty[g1 & 1], (uint32_t)(((g1 >> 1) & 1) ^ 1))) {
+        if (g1 < n_local && mbar_test_wait(&tempty[g1 & 1], (uint32_t)(((g1 >> 1) & 1) ^ 1))) {
           mbar_wait(&full[stage], phase, p.err, 3);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(sA + stage * TC_A_BYTES);
@@ -205,7 +222,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(&tfull[g1 & 1]);
           }
           __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == AS) { stage = 0; phase ^= 1; }
           ++g1;
           progress = true;
         }
@@ -217,7 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    for (int tile = blockIdx.x; EPI != EPI_HEAD2 && tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; !HEAD2 && tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[acc], acc_phase ^ 1, p.err, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
@@ -255,7 +272,126 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     e.out = p.out; e.sum_out = p.sum_out;
     e.Cout = p.Cout; e.out_ldc = p.out_ldc; e.out_coff = p.out_coff; e.rep = p.rep; e.Wo = p.Wo; e.relu = p.relu;
     const uint32_t stg = smem_u32(smem + L::OFF_STG + ew * 2048);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+    if (HEAD2) {
+      // DB head tail, contraction on the tensor cores: per tap, BN + ReLU of the 64 conv-transpose-1 channels -> bf16 pairs
+      // written back over the accumulator's first 32 columns (lane = pixel, column = channel pair: the TMEM form of an A
+      // operand); the issuer warp multiplies them with the [64][16] tile of conv-transpose-2 weights into columns 32..47 of
+      // the same tap; this thread then reads its 4 + 4 partial sums, adds the bias, sigmoid, binarize.  Per pixel and tap:
+      // 32 packed FMAs + 32 conversions instead of 160 packed FMAs + 64 maxima on a dependent chain.
+      // Group g takes the tiles blockIdx.x + (2 i + g) gridDim.x; the tile coordinates advance incrementally (no divisions).
+      const int m = quarter * 32 + lane;
+      const int yl = m / TC_TW, xl = m - yl * TC_TW;
+      const int step = 2 * (int)gridDim.x;
+      const int step_b = step / tiles_per_img, step_r = step - step_b * tiles_per_img;
+      const int step_y = step_r / p.tiles_x, step_x = step_r - step_y * p.tiles_x;
+      int tile = (int)blockIdx.x + group * (int)gridDim.x;
+      int b = tile / tiles_per_img, ty, tx;
+      { const int t = tile - b * tiles_per_img; ty = t / p.tiles_x; tx = t - ty * p.tiles_x; }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE);
+      const uint32_t tap0 = taddr + (uint32_t)(half * 128);  // taps i*2 + j with i = half: two rows of the pixel's 4x4 output block
+      const int64_t Wp = (int64_t)p.Wo * 4;
+      constexpr bool h_in_tmem = EPI == EPI_HEAD2_TS;
+      const uint32_t hrow = smem_u32(sB + L::B_BYTES + (acc * 4 + half * 2) * TC_A_BYTES + m * 128);
+      // 16 channels of one tap: raw accumulator registers -> 8 packed bf16 pairs
+      auto bn_relu16 = [&](const uint32_t (&r)[16], int co0, uint32_t *h) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const int co = co0 + j;
+          const float2 f = ffma2(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), make_float2(hc.scale[co], hc.scale[co + 1]),
+                                 make_float2(hc.shift[co], hc.shift[co + 1]));
+          h[j >> 1] = pack_bf16_relu(f.x, f.y);
+        }
+      };
+      for (; tile < num_tiles; tile += step) {
+        const int y = ty * TC_TH + yl, x = tx * TC_TW + xl;
+        const bool valid = m < TC_ROWS && y < p.Ho && x < p.Wo;
+        mbar_wait(&tfull[acc], acc_phase, p.err, 4);
+        tc_fence_after();
+        // the loads of the second tap fly while the first is converted
+        uint32_t ra[4][16], rb[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(tap0 + (uint32_t)(c * 16), ra[c]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_wait16(ra[c]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(tap0 + (uint32_t)(64 + c * 16), rb[c]);
+        if (h_in_tmem) {
+          {
+            uint32_t h[32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bn_relu16(ra[c], c * 16, h + c * 8);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld_wait16(rb[c]);
+            tmem_st32(tap0, h);  // every column of this tap is in registers: the pairs land on its first 32 columns
+          }
+          {
+            uint32_t h[32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bn_relu16(rb[c], c * 16, h + c * 8);
+            tmem_st32(tap0 + 64, h);
+          }
+          tmem_st_wait();
+        } else {
+          // this pixel's row of the [128][64] bf16 tile of each tap: eight 16-byte chunks, 128B-swizzled like a TMA-written tile
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t h[8];
+            bn_relu16(ra[c], c * 16, h);
+            sts_16(hrow + (uint32_t)(((2 * c) ^ (m & 7)) << 4), make_uint4(h[0], h[1], h[2], h[3]));
+            sts_16(hrow + (uint32_t)(((2 * c + 1) ^ (m & 7)) << 4), make_uint4(h[4], h[5], h[6], h[7]));
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld_wait16(rb[c]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t h[8];
+            bn_relu16(rb[c], c * 16, h);
+            sts_16(hrow + TC_A_BYTES + (uint32_t)(((2 * c) ^ (m & 7)) << 4), make_uint4(h[0], h[1], h[2], h[3]));
+            sts_16(hrow + TC_A_BYTES + (uint32_t)(((2 * c + 1) ^ (m & 7)) << 4), make_uint4(h[4], h[5], h[6], h[7]));
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's operand reads
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hready[acc]);
+        mbar_wait(&zfull[acc], acc_phase, p.err, 6);
+        tc_fence_after();
+        float z[2][8];
+#pragma unroll
+        for (int tj = 0; tj < 2; ++tj) tmem_ld8(tap0 + (uint32_t)(tj * 64 + 32), z[tj]);
+        // the accumulator stage is free once its results are in registers: release it before the sigmoid and the stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        acc_phase ^= 1;
+        float o[2][4];
+#pragma unroll
+        for (int tj = 0; tj < 2; ++tj) {
+          // q = i'*2 + j' of conv-transpose 2: output (4y + 2i + i', 4x + 2j + j')
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q >> 1][2 * tj + (q & 1)] = __fdividef(1.0f, 1.0f + __expf(-(z[tj][q] + z[tj][4 + q] + p.b2)));
+        }
+        if (valid) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const int64_t off = ((int64_t)b * p.Ho * 4 + (int64_t)y * 4 + 2 * half + a) * Wp + (int64_t)x * 4;
+            *reinterpret_cast<float4 *>(p.prob + off) = make_float4(o[a][0], o[a][1], o[a][2], o[a][3]);
+            if (p.bitmap) {
+              uint32_t bits = (o[a][0] > p.thresh ? 1u : 0u) | (o[a][1] > p.thresh ? 0x100u : 0u) |
+                              (o[a][2] > p.thresh ? 0x10000u : 0u) | (o[a][3] > p.thresh ? 0x1000000u : 0u);
+              *reinterpret_cast<uint32_t *>(p.bitmap + off) = bits;
+            }
+          }
+        }
+        tx += step_x;
+        if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+        ty += step_y;
+        if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
+        b += step_b;
+      }
+    }
+    for (int tile = blockIdx.x; !HEAD2 && tile < num_tiles; tile += gridDim.x, ++tile_it) {
       if (GROUPS == 2 && (tile_it & 1) != group) continue;
       const int n_tile = tile / num_m_tiles, m_tile = tile - n_tile * num_m_tiles;
       const int b = m_tile / tiles_per_img, t = m_tile - b * tiles_per_img;
@@ -358,69 +494,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-      } else if (EPI == EPI_HEAD2) {
-        // DB head tail, contraction on the tensor cores: per tap, BN + ReLU of the 64 conv-transpose-1 channels -> bf16 pairs
-        // written back over the accumulator's first 32 columns (lane = pixel, column = channel pair: the TMEM form of an A
-        // operand); the issuer warp multiplies them with the [64][16] tile of conv-transpose-2 weights into columns 32..47 of
-        // the same tap; this thread then reads its 4 + 4 partial sums, adds the bias, sigmoid, binarize.  Per pixel and tap:
-        // 32 packed FMAs + 32 conversions instead of 160 packed FMAs + 64 maxima on a dependent chain.
-        const int m = quarter * 32 + lane;
-        const int yl = m / TC_TW, xl = m - yl * TC_TW;
-        const int y = ty * TC_TH + yl, x = tx * TC_TW + xl;
-        const bool valid = m < TC_ROWS && y < p.Ho && x < p.Wo;
-        mbar_wait(&tfull[acc], acc_phase, p.err, 4);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE);
-#pragma unroll
-        for (int tj = 0; tj < 2; ++tj) {
-          const uint32_t tap = taddr + (uint32_t)((half * 2 + tj) * 64);  // tap = i*2 + j with i = half
-#pragma unroll
-          for (int c0 = 0; c0 < 64; c0 += 32) {
-            float v[32];
-            tmem_ld32(tap + c0, v);
-            uint32_t h[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const int co = c0 + j;
-              const float2 f = ffma2(make_float2(v[j], v[j + 1]), make_float2(hc.scale[co], hc.scale[co + 1]), make_float2(hc.shift[co], hc.shift[co + 1]));
-              h[j >> 1] = pack_bf16_relu(f.x, f.y);
-            }
-            tmem_st16(tap + (c0 >> 1), h);  // columns already read: the 16 packed pairs land on fp32 columns c0/2 .. c0/2 + 15
-          }
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&hready[acc]);
-        mbar_wait(&zfull[acc], acc_phase, p.err, 6);
-        tc_fence_after();
-        float z[2][8];
-#pragma unroll
-        for (int tj = 0; tj < 2; ++tj) tmem_ld8(taddr + (uint32_t)((half * 2 + tj) * 64 + 32), z[tj]);
-        // the accumulator stage is free once its results are in registers: release it before the sigmoid and the stores
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-        float o[2][4];
-#pragma unroll
-        for (int tj = 0; tj < 2; ++tj) {
-          // q = i'*2 + j' of conv-transpose 2: output (4y + 2i + i', 4x + 2j + j')
-#pragma unroll
-          for (int q = 0; q < 4; ++q) o[q >> 1][2 * tj + (q & 1)] = __fdividef(1.0f, 1.0f + __expf(-(z[tj][q] + z[tj][4 + q] + p.b2)));
-        }
-        if (valid) {
-          const int64_t Wp = (int64_t)p.Wo * 4;
-#pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const int64_t off = ((int64_t)b * p.Ho * 4 + (int64_t)y * 4 + 2 * half + a) * Wp + (int64_t)x * 4;
-            *reinterpret_cast<float4 *>(p.prob + off) = make_float4(o[a][0], o[a][1], o[a][2], o[a][3]);
-            if (p.bitmap) {
-              uint32_t bits = (o[a][0] > p.thresh ? 1u : 0u) | (o[a][1] > p.thresh ? 0x100u : 0u) |
-                              (o[a][2] > p.thresh ? 0x10000u : 0u) | (o[a][3] > p.thresh ? 0x1000000u : 0u);
-              *reinterpret_cast<uint32_t *>(p.bitmap + off) = bits;
-            }
-          }
-        }
       } else {
         static_assert(EPI != EPI_HEAD || PARTS == 2, "head epilogue splits the four taps over two warp halves");
         // DB head tail: columns n = tap(i,j)*64 + co of conv-transpose 1; per tap BN+ReLU then
@@ -485,11 +558,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      if (EPI != EPI_HEAD2) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
       if (GROUPS == 2) {
         acc_phase ^= 1;  // this group's stage is used by every second tile
       } else {
@@ -643,8 +714,10 @@ int launch_conv_tc(ocrb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB
     if (n_tile != 256) { set_error("conv_tc head needs N tile 256"); return OCRB_ERR_INVALID; }
     // default: the 64 -> 4 contraction of the tail as a second GEMM (OCRB_HEAD=cuda: on the CUDA cores, round 1's form)
     static const bool head_cuda = getenv("OCRB_HEAD") && !strcmp(getenv("OCRB_HEAD"), "cuda");
+    static const bool head_ts = !(getenv("OCRB_HEAD") && !strcmp(getenv("OCRB_HEAD"), "ss"));  // measured: 3.6 ms per 1024 images (ss: 4.3, cuda: 5.0)
     if (!head_cuda && p.R == 1 && p.S == 1 && p.cin_chunks == 1 && p.num_n_tiles == 1 && !p.split_nblk)
-      return launch_one<256, 4, EPI_HEAD2, 0, 16>(ctx, tmA, tmB, p, num_tiles, tag, hc);
+      return head_ts ? launch_one<256, 4, EPI_HEAD2_TS, 0, 16>(ctx, tmA, tmB, p, num_tiles, tag, hc)
+                     : launch_one<256, 4, EPI_HEAD2, 0, 16>(ctx, tmA, tmB, p, num_tiles, tag, hc);
     static const bool ew8 = getenv("OCRB_HEAD_EW") && atoi(getenv("OCRB_HEAD_EW")) == 8;  // tuning knob
     return ew8 ? launch_one<256, 4, EPI_HEAD, 0, 8>(ctx, tmA, tmB, p, num_tiles, tag, hc)
                : launch_one<256, 4, EPI_HEAD, 0, 16>(ctx, tmA, tmB, p, num_tiles, tag, hc);

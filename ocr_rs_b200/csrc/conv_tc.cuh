@@ -9,7 +9,7 @@ namespace ocrb {
 
 // EPI_HEAD2: the head tail with its 64 -> 4 contraction as a second tcgen05 GEMM (A operand written back to TMEM); EPI_HEAD: the
 // same tail on the CUDA cores (OCRB_HEAD=cuda)
-enum { EPI_STD = 0, EPI_HEAD = 1, EPI_F32 = 2, EPI_HEAD2 = 3 };
+enum { EPI_STD = 0, EPI_HEAD = 1, EPI_F32 = 2, EPI_HEAD2 = 3, EPI_HEAD2_TS = 4 };
 
 struct ConvTcParams {
   // problem geometry (output side); tiles_x/tiles_y/num_n_tiles are filled by the launcher

@@ -13,8 +13,10 @@
 
 namespace ocrb {
 
-constexpr int CROP_THREADS = 128;
+constexpr int CROP_THREADS = 256;
 constexpr int CROP_STRIP_W = 1024;  // strip columns held in shared memory at a time (28 KB)
+constexpr int CROP_FAST_W = 512;    // common case: cell width / patch height bound
+constexpr int CROP_MAXT = 16;       // common case: filter taps per output sample
 
 __device__ __forceinline__ float tri_w(float x) {
   const float a = fabsf(x);
@@ -90,6 +92,88 @@ __global__ void __launch_bounds__(CROP_THREADS) crop_glyphs_kernel(const uint8_t
   if (x1 < x0 + 1) x1 = x0 + 1;
   const int sw = x1 - x0;
   uint8_t *tile = out + (int64_t)gi * 784;
+
+  // ---- common case (a cell of at most 14 KB of rectified pixels, filters of at most CROP_MAXT taps): every quantity that
+  // depends on one index only is computed once — the two halves of the sampling position per patch column / patch row, the
+  // filter weights and their sums per output row / column — and every rectified pixel is sampled once into shared memory.
+  // The operations and their order are those of the general path below (and of the oracle), so the results are the same bits.
+  if (sw <= CROP_FAST_W && g.ph <= CROP_FAST_W && g.ph * sw <= 14 * 1024) {
+    __shared__ float s_ax[CROP_FAST_W], s_ay[CROP_FAST_W], s_bx[CROP_FAST_W], s_by[CROP_FAST_W];
+    __shared__ float s_w[2][28][CROP_MAXT], s_sum[2][28];
+    __shared__ int s_left[2][28], s_n[2][28];
+    uint8_t *patch = strip + 14 * 1024;  // [ph][sw]; the strip itself is [28][sw] here
+    int overflow = 0;
+    for (int c = threadIdx.x; c < sw; c += CROP_THREADS) {
+      const float s = ((float)(x0 + c) + 0.5f) / (float)g.pw;
+      s_ax[c] = (float)g.ox + s * g.ux;
+      s_ay[c] = (float)g.oy + s * g.uy;
+    }
+    for (int i = threadIdx.x; i < g.ph; i += CROP_THREADS) {
+      const float t = ((float)i + 0.5f) / (float)g.ph;
+      s_bx[i] = t * g.vx;
+      s_by[i] = t * g.vy;
+    }
+    if ((threadIdx.x & 31) < 28 && threadIdx.x < 64) {
+      const int pass = threadIdx.x >> 5, o = threadIdx.x & 31;  // pass 0: vertical (rows), pass 1: horizontal (columns)
+      const Taps tp = taps_for(o, pass ? sw : g.ph, 28);
+      const int n = tp.right - tp.left;
+      s_left[pass][o] = tp.left;
+      s_n[pass][o] = n;
+      if (n > CROP_MAXT) {
+        overflow = 1;
+      } else {
+        float sum = 0.0f;
+        for (int k = 0; k < n; ++k) {
+          const float w = tri_w(((float)(tp.left + k) - tp.inputc2) / tp.sratio);
+          sum += w;
+          s_w[pass][o][k] = w;
+        }
+        s_sum[pass][o] = sum;
+      }
+    }
+    if (!__syncthreads_or(overflow)) {
+      // four independent image reads in flight per thread (the kernel is bound by their latency)
+      const int n_px = g.ph * sw;
+      for (int base = threadIdx.x; base < n_px; base += 4 * CROP_THREADS) {
+        uint8_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int item = base + u * CROP_THREADS;
+          v[u] = 0;
+          if (item < n_px) {
+            const int i = item / sw, c = item - i * sw;
+            const float fx = s_ax[c] + s_bx[i], fy = s_ay[c] + s_by[i];
+            int ix = (int)floorf(fx), iy = (int)floorf(fy);
+            ix = ix < 0 ? 0 : (ix > g.W - 1 ? g.W - 1 : ix);
+            iy = iy < 0 ? 0 : (iy > g.H - 1 ? g.H - 1 : iy);
+            v[u] = __ldg(img + (int64_t)iy * g.W + ix);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (base + u * CROP_THREADS < n_px) patch[base + u * CROP_THREADS] = v[u];
+      }
+      __syncthreads();
+      for (int item = threadIdx.x; item < 28 * sw; item += CROP_THREADS) {
+        const int r = item / sw, c = item - r * sw;
+        const uint8_t *col = patch + s_left[0][r] * sw + c;
+        const int n = s_n[0][r];
+        float t = 0.0f;
+        for (int k = 0; k < n; ++k) t += (float)col[k * sw] * s_w[0][r][k];
+        strip[item] = finish_u8(t, s_sum[0][r]);
+      }
+      __syncthreads();
+      for (int item = threadIdx.x; item < 784; item += CROP_THREADS) {
+        const int r = item / 28, o = item - r * 28;
+        const uint8_t *row = strip + r * sw + s_left[1][o];
+        const int n = s_n[1][o];
+        float t = 0.0f;
+        for (int k = 0; k < n; ++k) t += (float)row[k] * s_w[1][o][k];
+        tile[item] = finish_u8(t, s_sum[1][o]);
+      }
+      return;
+    }
+  }
 
   // vertical pass for strip columns [c0, c1) -> strip[r][c - c0]
   auto vertical = [&](int c0, int c1) {

@@ -33,6 +33,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking form (try_wait may suspend the thread for a system-dependent time): for loops that poll several barriers
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // bounded wait: a mis-programmed pipeline traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *err, int code) {
   if (mbar_try_wait(bar, parity)) return;

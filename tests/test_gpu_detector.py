@@ -141,12 +141,12 @@ def test_large_non_square_map(env):
 
 @pytest.mark.parametrize("knobs", [{"OCRB_FUSE_FPN2": "0"}, {"OCRB_FUSE_FPN2": "0", "OCRB_HALO_TS": "0", "OCRB_LATERAL_TS": "0"},
                                    {"OCRB_HALO_CG": "1"}, {"OCRB_CONV": "tc", "OCRB_FUSE_DS": "0"}, {"OCRB_PAIR": "0"},
-                                   {"OCRB_STEM": "v2"}, {"OCRB_STEM": "v1"}])
+                                   {"OCRB_STEM": "v2"}, {"OCRB_STEM": "v1"}, {"OCRB_HEAD": "cuda"}, {"OCRB_HEAD": "ss"}])
 def test_alternate_kernel_paths(knobs):
     """The library's tuning knobs select older / more literal code paths (the reference's literal FPN graph with the
     lateral kernel, per-thread-store epilogues, single-CTA tiles, the one-box-per-tap engine with separate downsample
     launches, one launch per parity class instead of class pairs, the two older stems: stem_tc2.cu with pixels in the TMEM lanes and the
-    im2col stem of stem_tc.cu).  They are read once per process, so each combination runs in its own interpreter; same tolerance."""
+    im2col stem of stem_tc.cu, the head tail on the CUDA cores / with its second GEMM's operand in shared memory).  They are read once per process, so each combination runs in its own interpreter; same tolerance."""
     import os
     import subprocess
     import sys
