@@ -287,20 +287,48 @@ def main():
     e2e_no = [0]
     e2e_polys = [0]
 
+    # host-clock breakdown of the e2e step (ms summed over the steps run so far; reset before the timed region):
+    # call = ocrb_detect_and_read with host buffers (H2D, forward, post-processing, crops, glyph net, results D2H),
+    # wrap = the result arrays as numpy views, publish / collect = the shared-memory gather
+    bd = {"call": 0.0, "wrap": 0.0, "publish": 0.0, "collect": 0.0, "steps": 0}
+
     def e2e_step():
-        res = step(host_imgs, keep=True)
+        c0 = time.perf_counter()
+        h = _ffi.c_p()
+        _ffi.check(L.ocrb_detect_and_read(det._h, rec._h, _ffi.ptr(host_imgs), _ffi.ptr(adj), count, H, W, None, GLYPHS_PER_POLYGON, C.byref(h)))
+        c1 = time.perf_counter()
+        res = _ffi.Polygons(h)
         d2h[0] = res.xy.nbytes + res.all_scores.nbytes + res.point_offsets.nbytes + res.image_offsets.nbytes + res.glyph_classes.nbytes
+        c2 = c3 = c4 = time.perf_counter()
         if gather:
             gather.publish(res, e2e_no[0])
+            c3 = c4 = time.perf_counter()
             if rank == 0:
                 res = gather.collect(e2e_no[0])
+                c4 = time.perf_counter()
             e2e_no[0] += 1
         if rank == 0:
             e2e_polys[0] = len(res.all_scores)
+        bd["call"] += (c1 - c0) * 1e3
+        bd["wrap"] += (c2 - c1) * 1e3
+        bd["publish"] += (c3 - c2) * 1e3
+        bd["collect"] += (c4 - c3) * 1e3
+        bd["steps"] += 1
 
     for _ in range(args.warmup):
         e2e_step()
+    for k in bd:
+        bd[k] = 0
     ms_e2e, _, _ = timed(e2e_step, args.steps)
+    # per-step means, maximum over the ranks (rank 0 alone collects)
+    bdt = torch.tensor([bd[k] / max(bd["steps"], 1) for k in ("call", "wrap", "publish", "collect")], device="cuda")
+    if world > 1:
+        dist.all_reduce(bdt, op=dist.ReduceOp.MAX)
+    e2e_breakdown = {k: round(float(v), 3) for k, v in zip(("call_ms", "wrap_ms", "publish_ms", "collect_ms"), bdt.tolist())}
+    e2e_breakdown["resident_step_ms"] = round(ms_dev / args.steps, 3)
+    e2e_breakdown["note"] = ("host clock, per step, max over ranks: call = ocrb_detect_and_read on pinned host images (H2D + forward + "
+                             "post-processing + crops + glyph net + results D2H); resident_step_ms = the same call on device-resident images "
+                             "(`value`); call - resident = what the host copies add; publish / collect = shared-memory gather")
     if gather:
         barrier()
         gather.close()
@@ -369,7 +397,8 @@ def main():
                    "polygons_per_step_rank0": n_poly, "polygons_per_step_gathered": e2e_polys[0],
                    "gather": "POSIX shared memory, rank order (sharding.ShmGather)" if world > 1 else "single rank"},
         "e2e": {"value": args.images * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
-                "h2d_bytes_per_step": int(host_imgs.numel() + adj.nbytes) * world, "d2h_bytes_per_step": int(d2h[0]) * world},
+                "h2d_bytes_per_step": int(host_imgs.numel() + adj.nbytes) * world, "d2h_bytes_per_step": int(d2h[0]) * world,
+                "breakdown": e2e_breakdown},
         "gpu_launches": int(lt.item()),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
