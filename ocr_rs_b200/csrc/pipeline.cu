@@ -9,6 +9,15 @@
 //   ctx->stream     post-processing of group g (up to 256 images per launch: the contour /
 //                   polygon kernels are latency-bound, so they are amortised over more images)
 //                   while the forward of group g+1 runs on the forward stream
+//
+// OCRB_PP_SMS=k (k a multiple of 8): the device's SMs are split into two green contexts (driver resource partition):
+// 148 - k SMs for the forward stream — every convolution kernel is persistent with one CTA per SM of ITS partition — and k
+// SMs on which the latency-bound post-processing kernels of a group run BESIDE the forward of the next group.  Without the
+// partition the two streams never overlap: a persistent convolution kernel fills every SM, so a post-processing kernel
+// only gets SMs at a kernel boundary and then holds the next convolution kernel's CTAs off them.  The glyph net of such a
+// group runs on the forward partition (tensor-core kernels), the last group's post-processing on the whole device.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace ocrb {
@@ -31,15 +40,71 @@ struct PipelineWorkspace {
   std::vector<PinBuf> cls_host;                                   // per group: classes on the host, read after the final sync
   cudaStream_t fwd = nullptr, copy = nullptr;
   cudaEvent_t copied[2] = {nullptr, nullptr}, img_free[2] = {nullptr, nullptr}, fwd_done[2] = {nullptr, nullptr}, pp_ready = nullptr;
+  // SM partition (OCRB_PP_SMS): green contexts, the post-processing stream of the small one, SMs of the large one
+  CUgreenCtx g_fwd = nullptr, g_pp = nullptr;
+  cudaStream_t pp_small = nullptr;
+  int fwd_sms = 0;
+  cudaEvent_t pp_chain = nullptr, crop_done = nullptr, rec_done[2] = {nullptr, nullptr};
   bool ready = false;
 };
+
+// driver entry points of the green-context API, resolved at run time (the library does not link libcuda)
+template <class F>
+static bool drv_fn(const char *name, F *fn) {
+  void *ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !ptr) {
+    cudaGetLastError();
+    return false;
+  }
+  *fn = reinterpret_cast<F>(ptr);
+  return true;
+}
+
+// splits the device into (sm_count - pp_sms) + pp_sms SMs; on any failure the pipeline keeps its plain streams
+static bool make_partition(ocrb_ctx *ctx, PipelineWorkspace *w, int pp_sms) {
+  CUresult (*getRes)(CUdevice, CUdevResource *, CUdevResourceType) = nullptr;
+  CUresult (*split)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int) = nullptr;
+  CUresult (*genDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int) = nullptr;
+  CUresult (*gcCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*gcStream)(CUstream *, CUgreenCtx, unsigned int, int) = nullptr;
+  if (!drv_fn("cuDeviceGetDevResource", &getRes) || !drv_fn("cuDevSmResourceSplitByCount", &split) || !drv_fn("cuDevResourceGenerateDesc", &genDesc) ||
+      !drv_fn("cuGreenCtxCreate", &gcCreate) || !drv_fn("cuGreenCtxStreamCreate", &gcStream))
+    return false;
+  CUdevResource all, small, rest;
+  unsigned int groups = 1;
+  if (getRes((CUdevice)ctx->device, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+  if (split(&small, &groups, &all, &rest, 0, (unsigned int)pp_sms) != CUDA_SUCCESS || groups != 1) return false;
+  if (small.sm.smCount < 1 || rest.sm.smCount < 64) return false;
+  CUdevResourceDesc d_small, d_rest;
+  if (genDesc(&d_small, &small, 1) != CUDA_SUCCESS || genDesc(&d_rest, &rest, 1) != CUDA_SUCCESS) return false;
+  if (gcCreate(&w->g_pp, d_small, (CUdevice)ctx->device, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+  if (gcCreate(&w->g_fwd, d_rest, (CUdevice)ctx->device, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+  CUstream s_small = nullptr, s_fwd = nullptr;
+  if (gcStream(&s_small, w->g_pp, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+  if (gcStream(&s_fwd, w->g_fwd, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+  w->pp_small = s_small;
+  w->fwd = s_fwd;
+  w->fwd_sms = (int)rest.sm.smCount;
+  return true;
+}
 // the workspace belongs to the ctx (one ctx per host thread: no state is shared between contexts)
 static int get_ws(ocrb_ctx *ctx, PipelineWorkspace **out) {
   if (!ctx->pipe) ctx->pipe = new PipelineWorkspace();
   PipelineWorkspace *w = ctx->pipe;
   if (!w->ready) {
-    OCRB_CUDA(cudaStreamCreateWithFlags(&w->fwd, cudaStreamNonBlocking));
+    static const int pp_sms = getenv("OCRB_PP_SMS") ? atoi(getenv("OCRB_PP_SMS")) : 0;
+    if (pp_sms > 0 && !make_partition(ctx, w, pp_sms)) {
+      fprintf(stderr, "libocrb: OCRB_PP_SMS=%d: no green-context partition on this driver / device, plain streams\n", pp_sms);
+      w->pp_small = nullptr;
+      w->fwd = nullptr;
+      w->fwd_sms = 0;
+    }
+    if (!w->fwd) OCRB_CUDA(cudaStreamCreateWithFlags(&w->fwd, cudaStreamNonBlocking));
     OCRB_CUDA(cudaStreamCreateWithFlags(&w->copy, cudaStreamNonBlocking));
+    OCRB_CUDA(cudaEventCreateWithFlags(&w->pp_chain, cudaEventDisableTiming));
+    OCRB_CUDA(cudaEventCreateWithFlags(&w->crop_done, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) OCRB_CUDA(cudaEventCreateWithFlags(&w->rec_done[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
       OCRB_CUDA(cudaEventCreateWithFlags(&w->copied[i], cudaEventDisableTiming));
       OCRB_CUDA(cudaEventCreateWithFlags(&w->img_free[i], cudaEventDisableTiming));
@@ -65,8 +130,20 @@ void free_pipe(ocrb_ctx *ctx) {
     if (w->fwd_done[i]) cudaEventDestroy(w->fwd_done[i]);
   }
   if (w->pp_ready) cudaEventDestroy(w->pp_ready);
+  if (w->pp_chain) cudaEventDestroy(w->pp_chain);
+  if (w->crop_done) cudaEventDestroy(w->crop_done);
+  for (int i = 0; i < 2; ++i)
+    if (w->rec_done[i]) cudaEventDestroy(w->rec_done[i]);
+  if (w->pp_small) cudaStreamDestroy(w->pp_small);
   if (w->fwd) cudaStreamDestroy(w->fwd);
   if (w->copy) cudaStreamDestroy(w->copy);
+  if (w->g_fwd || w->g_pp) {
+    CUresult (*gcDestroy)(CUgreenCtx) = nullptr;
+    if (drv_fn("cuGreenCtxDestroy", &gcDestroy)) {
+      if (w->g_fwd) gcDestroy(w->g_fwd);
+      if (w->g_pp) gcDestroy(w->g_pp);
+    }
+  }
   delete w;
   ctx->pipe = nullptr;
 }
@@ -101,6 +178,7 @@ static int run_pipeline(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, con
   // the per-launch event timeline (ocrb_ctx_profile_begin) needs one stream: serialise then
   const bool serial = ctx->prof.on;
   cudaStream_t s_pp = ctx->stream, s_fwd = serial ? ctx->stream : ws->fwd, s_copy = serial ? ctx->stream : ws->copy;
+  const bool split = ws->pp_small != nullptr && !serial;  // SM partition in use
   // group: <= 256 images and < 2^31 pixels (post-processing index arithmetic); chunk: <= 256 images
   static const int group_env = getenv("OCRB_GROUP") ? atoi(getenv("OCRB_GROUP")) : 0;  // tuning knob
   int group = group_env > 0 ? group_env : PIPE_GROUP;
@@ -174,6 +252,7 @@ static int run_pipeline(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, con
       static const int sm_leave = getenv("OCRB_SM_LEAVE") ? atoi(getenv("OCRB_SM_LEAVE")) : 0;
       const int saved_limit = ctx->sm_limit;
       if (sm_leave > 0 && !serial) ctx->sm_limit = ctx->sm_count - sm_leave;
+      if (split) ctx->sm_limit = ws->fwd_sms;
       rc = det_forward_device(det, src, OCRB_U8, bc, H, W, prob + (size_t)c0 * HW, bf16 ? bitmap + (size_t)c0 * HW : nullptr, (float)prm.thresh);
       if (rc == OCRB_OK && !bf16) rc = launch_binarize(ctx, prob + (size_t)c0 * HW, (int64_t)bc * HW, (float)prm.thresh, bitmap + (size_t)c0 * HW);
       ctx->stream = saved;
@@ -187,12 +266,23 @@ static int run_pipeline(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, con
   ocrb_polygons *res = polygons_new();
   std::vector<int64_t> group_kept(n_groups, 0);
   int rc = enqueue_forward(0);
+  auto cuda_ok = [&](cudaError_t err) {
+    if (err == cudaSuccess) return true;
+    set_error("pipeline stream ordering -> %s", cudaGetErrorString(err));
+    rc = OCRB_ERR_CUDA;
+    return false;
+  };
   for (int g = 0; g < n_groups && rc == OCRB_OK; ++g) {
     if (g + 1 < n_groups) rc = enqueue_forward(g + 1);
     if (rc != OCRB_OK) break;
     const int g0 = g * group, gn = B - g0 < group ? B - g0 : group;
-    cudaError_t e = cudaStreamWaitEvent(s_pp, ws->fwd_done[g & 1], 0);
+    // with the SM partition, a group that has a forward to run beside goes to the small partition's stream
+    const bool small = split && g + 1 < n_groups;
+    cudaStream_t s_ppg = small ? ws->pp_small : s_pp;
+    cudaError_t e = cudaStreamWaitEvent(s_ppg, ws->fwd_done[g & 1], 0);
+    if (e == cudaSuccess && split) e = cudaStreamWaitEvent(s_ppg, g == 0 ? ws->pp_ready : ws->pp_chain, 0);  // adjust copied / workspace free
     if (e != cudaSuccess) { set_error("cudaStreamWaitEvent -> %s", cudaGetErrorString(e)); rc = OCRB_ERR_CUDA; break; }
+    ctx->stream = s_ppg;
     ocrb_polygons *part = polygons_new();
     rc = postproc_device(ctx, ws->prob[g & 1].as<float>(), ws->bitmap[g & 1].as<uint8_t>(), ws->adjust.as<double>() + (size_t)g0 * 2, gn, H, W, prm, part);
     const int64_t n_kept = rc == OCRB_OK ? ocrb_polygons_image_offsets(part)[gn] : 0;
@@ -211,17 +301,37 @@ static int run_pipeline(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, con
         if ((rc = ws->crop_cls[g & 1].reserve((size_t)n_tiles * 4)) != OCRB_OK) break;
         if ((rc = ws->cls_host[g].reserve((size_t)n_tiles * 4)) != OCRB_OK) break;
         const uint8_t *src = img_dev ? images + (size_t)g0 * HW : ws->images[g & 1].as<uint8_t>();
+        // the tile / class buffers of this parity are free once group g - 2's glyph net has read them
+        if (split && g >= 2 && !cuda_ok(cudaStreamWaitEvent(s_ppg, ws->rec_done[g & 1], 0))) break;
         if ((rc = launch_crop_glyphs(ctx, src, H, W, boxes, box_image, (int)n_kept, crop_k, ws->crops[g & 1].as<uint8_t>())) != OCRB_OK) break;
-        if ((rc = rec_forward_device(rec, ws->crops[g & 1].p, 1, (int)n_tiles, nullptr, ws->crop_cls[g & 1].as<int32_t>(), nullptr)) != OCRB_OK) break;
-        e = cudaMemcpyAsync(ws->cls_host[g].p, ws->crop_cls[g & 1].p, (size_t)n_tiles * 4, cudaMemcpyDeviceToHost, s_pp);
+        // the glyph net is tensor-core work: with the partition it follows the next group's forward on the large one
+        cudaStream_t s_rec = small ? s_fwd : s_ppg;
+        if (small) {
+          if (!cuda_ok(cudaEventRecord(ws->crop_done, s_ppg)) || !cuda_ok(cudaStreamWaitEvent(s_rec, ws->crop_done, 0))) break;
+          ctx->stream = s_rec;
+          ctx->sm_limit = ws->fwd_sms;
+        }
+        // one glyph net, one set of activations: its runs are ordered across the two streams
+        if (split && g >= 1 && !cuda_ok(cudaStreamWaitEvent(s_rec, ws->rec_done[(g - 1) & 1], 0))) break;
+        rc = rec_forward_device(rec, ws->crops[g & 1].p, 1, (int)n_tiles, nullptr, ws->crop_cls[g & 1].as<int32_t>(), nullptr);
+        ctx->stream = s_ppg;
+        ctx->sm_limit = 0;
+        if (rc != OCRB_OK) break;
+        e = cudaMemcpyAsync(ws->cls_host[g].p, ws->crop_cls[g & 1].p, (size_t)n_tiles * 4, cudaMemcpyDeviceToHost, s_rec);
         if (e != cudaSuccess) { set_error("cudaMemcpyAsync -> %s", cudaGetErrorString(e)); rc = OCRB_ERR_CUDA; break; }
+        if (split && !cuda_ok(cudaEventRecord(ws->rec_done[g & 1], s_rec))) break;
       }
       if (!img_dev) {
-        e = cudaEventRecord(ws->img_free[g & 1], s_pp);
+        e = cudaEventRecord(ws->img_free[g & 1], s_ppg);
         if (e != cudaSuccess) { set_error("cudaEventRecord -> %s", cudaGetErrorString(e)); rc = OCRB_ERR_CUDA; break; }
       }
     }
+    if (split && !cuda_ok(cudaEventRecord(ws->pp_chain, s_ppg))) break;
+    ctx->stream = s_pp;
   }
+  ctx->stream = s_pp;
+  ctx->sm_limit = 0;
+  if (split) cudaStreamSynchronize(ws->pp_small);
   if (rc == OCRB_OK) rc = sync(ctx);
   cudaStreamSynchronize(ws->fwd);
   cudaStreamSynchronize(ws->copy);
