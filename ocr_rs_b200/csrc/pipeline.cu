@@ -222,7 +222,7 @@ static int run_pipeline(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, con
       OCRB_CUDA(cudaMemcpyAsync(glyph_argmax, am, (size_t)n_glyphs * 4, cudaMemcpyDeviceToHost, s_pp));
   }
 
-  bool first_copy = true;
+  int ramp = 16;  // images of the next ramp-up chunk (host images only)
   // queues copies + forwards of group g; the detector launches on ctx->stream, so it is
   // pointed at the forward stream for the duration
   auto enqueue_forward = [&](int g) -> int {
@@ -234,10 +234,13 @@ static int run_pipeline(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, con
     if (!img_dev && g >= 2) OCRB_CUDA(cudaStreamWaitEvent(s_copy, ws->img_free[g & 1], 0));
     for (int c0 = 0, bc = 0; c0 < gn && rc == OCRB_OK; c0 += bc) {
       bc = gn - c0 < chunk ? gn - c0 : chunk;
-      // host images: the very first copy of a call is exposed (nothing to overlap it with), so
-      // ramp up — 16 images first, the rest while those are in the detector
-      if (!img_dev && first_copy && bc > 32) bc = 16;
-      first_copy = false;
+      // host images: the very first copy of a call is exposed (nothing to overlap it with), so ramp up — 16 images
+      // first, then chunks three times the previous one (a chunk's copy takes about a third of its forward when several
+      // GPUs share the host's memory and PCIe switches, so every copy hides behind the forward before it)
+      if (!img_dev && ramp < chunk) {
+        if (bc > ramp) bc = ramp;
+        ramp *= 3;
+      }
       const uint8_t *src = images + (size_t)(g0 + c0) * HW;
       if (!img_dev) {
         uint8_t *dst = ws->images[g & 1].as<uint8_t>() + (size_t)c0 * HW;
