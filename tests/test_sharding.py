@@ -138,3 +138,46 @@ def test_shm_gather_world_size_3():
         want = Polygons.concat([_fake_result(shard_range(n, r, world)[0] + step, shard_range(n, r, world)[1]) for r in range(world)])
         for a, b in zip(out[step], want.arrays()):
             assert a.shape == b.shape and (a == b).all()
+
+
+def _shm_worker_deferred(rank, world, key, n, steps, q):
+    sys.path.insert(0, ROOT)
+    from ocr_rs_b200 import sharding
+    g = sharding.ShmGather(rank, world, key, cap_bytes=1 << 20)
+    first, count = sharding.shard_range(n, rank, world)
+    out = []
+    for step in range(steps):
+        g.publish(_fake_result(first + step, count), step)
+        if rank == 0 and step >= 1:
+            out.append(g.collect(step - 1).arrays())  # one step behind, as bench.py's e2e leg does
+    if rank == 0:
+        out.append(g.collect(steps - 1).arrays())  # the flush at the end of the timed region
+        q.put(out)
+    else:
+        import time
+        time.sleep(0.5)
+    g.close()
+
+
+def test_shm_gather_collect_one_step_behind():
+    """bench.py's e2e leg at N > 1: rank 0 collects step i - 1 after publishing step i (it never waits for the slowest
+    rank) and flushes the last step at the end.  Two slots per segment: a writer two steps ahead of the reader's
+    acknowledgement waits, so no shard is overwritten before it is read."""
+    import multiprocessing as mp
+    n, world, steps, key = 13, 3, 6, f"testd{os.getpid()}"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shm_worker_deferred, args=(r, world, key, n, steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    from ocr_rs_b200.sharding import shard_range
+    from ocr_rs_b200._ffi import Polygons
+    assert len(out) == steps
+    for step in range(steps):
+        want = Polygons.concat([_fake_result(shard_range(n, r, world)[0] + step, shard_range(n, r, world)[1]) for r in range(world)])
+        for a, b in zip(out[step], want.arrays()):
+            assert a.shape == b.shape and (a == b).all()
