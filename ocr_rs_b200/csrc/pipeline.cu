@@ -182,8 +182,11 @@ static int run_pipeline(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, con
   // group: <= 256 images and < 2^31 pixels (post-processing index arithmetic); chunk: <= 256 images
   static const int group_env = getenv("OCRB_GROUP") ? atoi(getenv("OCRB_GROUP")) : 0;  // tuning knob
   int group = group_env > 0 ? group_env : PIPE_GROUP;
-  // a small batch is still cut into two groups so that post-processing overlaps a forward
-  if (B < 2 * group && B >= 64) group = ((B + 1) / 2 + 31) / 32 * 32;
+  // OCRB_GROUP_SPLIT=1: a small batch is still cut into two groups (round 1's rule, "so that post-processing overlaps a
+  // forward").  Off by default: the streams hide host round trips, not SM time, and one longer forward is more efficient —
+  // measured 9.99 against 10.48 ms per 128 images, 19.4 against 20.0 per 256 (the per-rank batches at 8 and 4 GPUs)
+  static const bool split_small = getenv("OCRB_GROUP_SPLIT") && atoi(getenv("OCRB_GROUP_SPLIT")) == 1;  // tuning knob
+  if (split_small && B < 2 * group && B >= 64) group = ((B + 1) / 2 + 31) / 32 * 32;
   while ((int64_t)group * HW >= ((int64_t)1 << 31) && group > 1) group /= 2;
   if (group > B) group = B;
   static const int chunk_env = getenv("OCRB_CHUNK") ? atoi(getenv("OCRB_CHUNK")) : 0;  // tuning knob
