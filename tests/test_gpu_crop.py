@@ -61,7 +61,8 @@ def test_crop_very_wide_cell(env):
 def test_detect_and_read_end_to_end(env, device_images):
     """One call: detector -> post-processing -> crops of every kept polygon -> classes.  Checked stage by stage against the
     oracle run on the device's own map: same kept boxes -> same tiles (oracle crop) -> same classes (torch restatement),
-    across several post-processing groups and for host and device-resident images."""
+    for host and device-resident images (several chunks with ramped host copies; the multi-group plans are covered by
+    test_pipeline_group_and_chunk_knobs and the 1024-image test)."""
     torch = pytest.importorskip("torch")
     _ffi, pipeline, synth, Net, resnet18, mo, pp = env
     B, H, W, K = 70, 160, 160, 3

@@ -171,7 +171,7 @@ def test_pipeline_chunking_and_device_pointers(env):
 def test_pipeline_sharding_invariance(env):
     """BASELINE config 4 property at reduced size: the polygons of an image do not depend on
     how the index range is cut (one call over 200 images == two shards == single-image calls),
-    across chunk (64) and group (128) boundaries."""
+    (round 1 cut such a batch into two groups; see test_pipeline_group_and_chunk_knobs for the multi-group plans)."""
     _ffi, synth, Net, resnet18, _, _ = env
     B, H, W = 200, 160, 160
     wd = synth.make_detector_weights(0, "structured")
@@ -270,3 +270,43 @@ def test_sharded_entry_point(env):
     with pytest.raises(OcrbError):
         sh = sharding.Shards([0], wd, None)
         sh.detect_and_recognize(torch.from_numpy(imgs).cuda(), adj)  # device pointers cannot feed several devices
+
+
+@pytest.mark.gpu
+def test_pipeline_group_and_chunk_knobs():
+    """Batching must not change results: the default plan (one post-processing group for a batch of up to 256 images),
+    small groups / chunks (OCRB_GROUP=32, OCRB_CHUNK=16: three groups, ramped host copies) and round 1's two-group rule
+    (OCRB_GROUP_SPLIT=1) give the same polygons, scores and glyph classes.  The knobs are read once per process, so every
+    plan runs in its own interpreter and prints a digest of the result arrays."""
+    import os
+    import subprocess
+    import sys
+    script = r"""
+import hashlib
+import numpy as np
+from ocr_rs_b200 import pipeline, synth
+from ocr_rs_b200.char_recognition.model import Net
+from ocr_rs_b200.text_detection.model import resnet18
+B, H, W, K = 70, 160, 160, 3
+imgs = synth.document_image_shard(0, B, H, W, unique=50)
+adj = np.ones((B, 2))
+adj[1::2] = (1.5, 0.75)
+det, rec = resnet18(synth.make_detector_weights(0, "structured"), "bf16"), Net(synth.make_rec_weights(1))
+res = pipeline.detect_and_read(det, rec, imgs, adj, K)
+h = hashlib.sha1()
+for a in list(res.arrays()) + [res.glyph_classes]:
+    h.update(np.ascontiguousarray(a).tobytes())
+print("DIGEST", h.hexdigest(), len(res.all_scores))
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for knobs in ({}, {"OCRB_GROUP": "32", "OCRB_CHUNK": "16"}, {"OCRB_GROUP_SPLIT": "1"}):
+        env = dict(os.environ, **knobs)
+        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        out = subprocess.run([sys.executable, "-c", script], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][-1].split()
+        assert int(line[2]) > 30
+        digests.append(line[1])
+        print(knobs, line[1], line[2])
+    assert digests[0] == digests[1] == digests[2]
