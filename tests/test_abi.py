@@ -46,6 +46,22 @@ def test_host_only_helpers(ffi):
     assert "".join(utils.class_to_char(i) for i in range(62)) == utils.VALUES
     assert utils.class_to_char(62) == "?"
     assert utils.parse_dimensions("800x600") == (800, 600)
+    for bad in ("800", "800x600x3", "ax600", "800X600"):  # utils.rs:72-79: two 'x'-separated u32 values or an error
+        with pytest.raises(ValueError):
+            utils.parse_dimensions(bad)
+    # utils::topk (utils.rs:28-43): largest first, class -> char through POS_TO_CHAR, the three accepted shapes
+    import numpy as np
+    p = np.zeros(62)
+    p[[3, 30, 61]] = (0.2, 0.5, 0.3)
+    assert utils.topk(p, 1) == [("e", 0.5)]
+    assert utils.topk(p.reshape(1, 62), 3) == [("e", 0.5), ("9", 0.3), ("D", 0.2)]
+    assert utils.topk(p.reshape(1, 1, 62), 2) == [("e", 0.5), ("9", 0.3)]
+    with pytest.raises(ValueError):
+        utils.topk(np.zeros((2, 62)), 1)
+    assert utils.VALUES_MAP["A"] == 0 and utils.VALUES_MAP["9"] == 61 and utils.POS_TO_CHAR[26] == "a"
+    assert utils.parse_number("12", "width") == 12
+    with pytest.raises(ValueError):
+        utils.parse_number("twelve", "width")
     p = ffi.PostprocParams()
     L.ocrb_postproc_default_params(C.byref(p))
     assert (p.thresh, p.box_thresh, p.min_size, p.unclip_factor) == (0.6, 0.7, 5.0, 2.0)  # metrics.rs:38,64,66,103

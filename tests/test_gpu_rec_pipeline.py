@@ -310,3 +310,22 @@ print("DIGEST", h.hexdigest(), len(res.all_scores))
         digests.append(line[1])
         print(knobs, line[1], line[2])
     assert digests[0] == digests[1] == digests[2]
+
+
+def test_run_prediction_topk(env):
+    """run_prediction (char_recognition/mod.rs:39-68) through the module mirror: one 28x28 luma glyph -> load_image_as_tensor ->
+    Net -> softmax in f64 -> utils::topk.  k = 1 is the reference's call; k = 3 exercises the utils::topk mirror.  Checked
+    against the torch restatement of the same steps."""
+    import torch
+    from ocr_rs_b200 import char_recognition, utils
+    _ffi, synth, Net, resnet18, mo, _ = env
+    wr = synth.make_rec_weights(1)
+    for g in synth.make_glyphs(3, 5, "strokes").reshape(-1, 28, 28):
+        logits = mo.rec_forward(wr, g.reshape(1, 784).astype(np.float32) / np.float32(255.0))
+        p = torch.softmax(logits.to(torch.float64), -1)[0].numpy()
+        want = utils.topk(p, 3)
+        ch, prob = char_recognition.run_prediction(g, wr)
+        assert ch == want[0][0] and abs(prob - want[0][1]) <= 1e-6
+        got = char_recognition.run_prediction(g, wr, k=3)
+        assert [c for c, _ in got] == [c for c, _ in want]
+        assert all(abs(a - b) <= 1e-6 for (_, a), (_, b) in zip(got, want))
