@@ -6,6 +6,7 @@
 // Each function cites the reference function it stands for; INTEGRATION.md shows the equivalent Rust `ocrb-sys` shim.
 // Pointers handed to these functions may be host or device memory (the library inspects them).
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <optional>
@@ -227,7 +228,38 @@ inline std::optional<std::vector<Point>> expand_polygon(Context &ctx, const std:
 
 namespace utils {
 // utils::VALUES (utils.rs:7)
+inline const char *const VALUES = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789";
+constexpr int VALUES_COUNT = 62;
 inline char class_to_char(int cls) { return ocrb_class_to_char(cls); }
+// utils::topk (utils.rs:28-43): the k largest of 62 class scores (run_prediction hands it softmax(-1, Double) of the
+// logits) as (character, value), largest first; equal values keep the lower class first.  A vector of another length is
+// the reference's panic on an unexpected tensor shape.
+inline std::vector<std::pair<char, double>> topk(const std::vector<double> &scores, int k) {
+  if ((int)scores.size() != VALUES_COUNT) throw Error(OCRB_ERR_INVALID, "unexpected tensor shape [" + std::to_string(scores.size()) + "]");
+  if (k < 0 || k > VALUES_COUNT) throw Error(OCRB_ERR_INVALID, "k out of range");
+  std::vector<int> order(VALUES_COUNT);
+  for (int i = 0; i < VALUES_COUNT; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return scores[a] > scores[b]; });
+  std::vector<std::pair<char, double>> r;
+  for (int i = 0; i < k; ++i) r.emplace_back(VALUES[order[i]], scores[order[i]]);
+  return r;
+}
+// utils::parse_dimensions ("800x800", utils.rs:72-79): exactly two 'x'-separated unsigned integers
+inline std::pair<uint32_t, uint32_t> parse_dimensions(const std::string &dims) {
+  const auto bad = [&]() { return Error(OCRB_ERR_INVALID, "Could not parse dimensions value: " + dims); };
+  const size_t x = dims.find('x');
+  if (x == std::string::npos || x == 0) throw bad();
+  std::string a = dims.substr(0, x), b = dims.substr(x + 1);
+  if (!b.empty() && b.back() == 'x') b.pop_back();  // split_terminator drops one trailing separator
+  if (b.empty() || b.find('x') != std::string::npos) throw bad();
+  for (const std::string *s : {&a, &b})
+    for (char c : *s)
+      if (c < '0' || c > '9') throw bad();
+  if (a.size() > 10 || b.size() > 10) throw bad();
+  const unsigned long long w = std::stoull(a), h = std::stoull(b);
+  if (w > 0xFFFFFFFFull || h > 0xFFFFFFFFull) throw bad();
+  return {(uint32_t)w, (uint32_t)h};
+}
 }  // namespace utils
 
 namespace char_recognition {

@@ -192,6 +192,35 @@ pub mod text_detection {
     }
 }
 
+pub mod utils {
+    //! utils.rs:7-79 — the class table, top-k decoding and argument parsing (host code in the reference as well).
+    use super::*;
+
+    pub const VALUES: &str = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789";
+    pub const VALUES_COUNT: usize = VALUES.len();
+
+    /// `utils::topk` (utils.rs:28-43): the `k` largest of the 62 class scores as `(char, value)`, largest first; equal
+    /// values keep the lower class first.  The reference panics on a tensor of another shape; here that is an error.
+    pub fn topk(scores: &[f64], k: usize) -> Result<Vec<(char, f64)>> {
+        if scores.len() != VALUES_COUNT || k > VALUES_COUNT {
+            return Err(anyhow!("unexpected tensor shape [{}]", scores.len()));
+        }
+        let mut order: Vec<usize> = (0..VALUES_COUNT).collect();
+        order.sort_by(|&a, &b| scores[b].partial_cmp(&scores[a]).unwrap_or(std::cmp::Ordering::Equal)); // stable
+        Ok(order[..k].iter().map(|&i| (VALUES.as_bytes()[i] as char, scores[i])).collect())
+    }
+
+    /// `utils::parse_dimensions` ("800x800", utils.rs:72-79)
+    pub fn parse_dimensions(dims_str: &str) -> Result<(u32, u32)> {
+        let values: Vec<&str> = dims_str.split_terminator('x').collect();
+        let bad = || anyhow!("Could not parse dimensions value: {}", dims_str);
+        if values.len() != 2 {
+            return Err(bad());
+        }
+        Ok((values[0].parse().map_err(|_| bad())?, values[1].parse().map_err(|_| bad())?))
+    }
+}
+
 pub mod polygon {
     use super::*;
     /// polygon.rs:51-56 (`None` = the empty offset the reference `unwrap()`s)

@@ -37,6 +37,21 @@ int main(int argc, char **argv) {
   }
   // utils::VALUES (utils.rs:7)
   REQUIRE(utils::class_to_char(0) == 'A' && utils::class_to_char(26) == 'a' && utils::class_to_char(52) == '0' && utils::class_to_char(62) == '?');
+  {  // utils::topk (utils.rs:28-43) and utils::parse_dimensions (utils.rs:72-79)
+    std::vector<double> p(62, 0.0);
+    p[3] = 0.2; p[30] = 0.5; p[61] = 0.3;
+    const auto t = utils::topk(p, 3);
+    REQUIRE(t.size() == 3 && t[0].first == 'e' && t[0].second == 0.5 && t[1].first == '9' && t[2].first == 'D');
+    bool threw = false;
+    try { utils::topk(std::vector<double>(61, 0.0), 1); } catch (const Error &) { threw = true; }
+    REQUIRE(threw);
+    REQUIRE(utils::parse_dimensions("800x600") == (std::pair<uint32_t, uint32_t>(800, 600)));
+    for (const char *bad : {"800", "800x600x3", "ax600", "800X600", "x600"}) {
+      threw = false;
+      try { utils::parse_dimensions(bad); } catch (const Error &) { threw = true; }
+      REQUIRE(threw);
+    }
+  }
   int rw = 0, rh = 0;
   REQUIRE(ocrb_resize_dims(300, 200, 800, 800, &rw, &rh) == OCRB_OK && rw == 800 && rh == 533);  // image_ops.rs fixtures
   {  // evaluation metrics are host code: the reference's KATs (metrics.rs:648-678, :814-856) through the mirror
