@@ -213,6 +213,12 @@ int ocrb_approx_polygon(ocrb_ctx *ctx, const int32_t *chain_xy, int64_t n_pts,
  * out[10] = {PW, TH, TW, sub_rows, sub_stride, a_stage_bytes, a_stages, b_stages, obufs * obuf_bytes, dynamic smem bytes} */
 int ocrb_debug_conv_geometry(int Ho, int Wo, int mode, int *out);
 
+/* host-only test hook (no device needed): the batching plan ocrb_detect_and_read / ocrb_detect_and_recognize would follow
+ * for B images of H x W (the batched loop of text_detection/mod.rs:188-204): images per post-processing group, and the
+ * forward chunks in order (bf16: mode of the detector; host_images: the images come from host memory, so the first
+ * chunks ramp up 16, 48, 144 to hide all but the first copy).  chunks[cap]; OCRB_ERR_CAPACITY if the plan has more. */
+int ocrb_debug_pipeline_plan(int B, int H, int W, int bf16, int host_images, int *group, int *chunks, int cap, int *n_chunks);
+
 /* ---- char_recognition ---------------------------------------------------------------
  * Net::new + vs.load (char_recognition/model.rs:12-25, mod.rs:43-45).  Names: canonical
  * "conv1.weight" ... "fc2.bias" or the de-duplicated VarStore names. */

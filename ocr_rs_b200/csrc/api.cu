@@ -6,6 +6,7 @@
 
 namespace ocrb {
 int debug_conv_geometry(int Ho, int Wo, int mode, int *out);
+int debug_pipeline_plan(int B, int H, int W, int bf16, int host_images, int *group_out, int *chunks, int cap, int *n_chunks);
 
 static thread_local std::string g_last_error;
 
@@ -321,6 +322,11 @@ char ocrb_class_to_char(int cls) {
 int ocrb_debug_conv_geometry(int Ho, int Wo, int mode, int *out) {
   OCRB_REQUIRE(out && Ho > 0 && Wo > 0 && mode >= 0 && mode <= 2, "bad argument");
   return ocrb::debug_conv_geometry(Ho, Wo, mode, out);
+}
+
+int ocrb_debug_pipeline_plan(int B, int H, int W, int bf16, int host_images, int *group, int *chunks, int cap, int *n_chunks) {
+  OCRB_REQUIRE(group && chunks && n_chunks && B > 0 && H > 0 && W > 0 && cap > 0, "bad argument");
+  return ocrb::debug_pipeline_plan(B, H, W, bf16, host_images, group, chunks, cap, n_chunks);
 }
 
 }  // extern "C"

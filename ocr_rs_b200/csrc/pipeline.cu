@@ -152,6 +152,56 @@ void polygons_set_glyph_classes(ocrb_polygons *, int, const std::vector<PinBuf> 
 
 constexpr int PIPE_CHUNK_BF16 = 256, PIPE_CHUNK_FP32 = 16, PIPE_GROUP = 256;  // 256 / 256 measured +3 % over 128 / 128 (fewer, longer launches)
 
+// The batching plan of a call: images per post-processing group and per forward chunk.
+// group: <= 256 images and < 2^31 pixels (post-processing index arithmetic); chunk: <= 256 images, never across a group
+static void pipeline_plan(int B, int64_t HW, bool bf16, int *group_out, int *chunk_out) {
+  static const int group_env = getenv("OCRB_GROUP") ? atoi(getenv("OCRB_GROUP")) : 0;  // tuning knob
+  int group = group_env > 0 ? group_env : PIPE_GROUP;
+  // OCRB_GROUP_SPLIT=1: a small batch is still cut into two groups (round 1's rule, "so that post-processing overlaps a
+  // forward").  Off by default: the streams hide host round trips, not SM time, and one longer forward is more efficient —
+  // measured 9.99 against 10.48 ms per 128 images, 19.4 against 20.0 per 256 (the per-rank batches at 8 and 4 GPUs)
+  static const bool split_small = getenv("OCRB_GROUP_SPLIT") && atoi(getenv("OCRB_GROUP_SPLIT")) == 1;  // tuning knob
+  if (split_small && B < 2 * group && B >= 64) group = ((B + 1) / 2 + 31) / 32 * 32;
+  while ((int64_t)group * HW >= ((int64_t)1 << 31) && group > 1) group /= 2;
+  if (group > B) group = B;
+  static const int chunk_env = getenv("OCRB_CHUNK") ? atoi(getenv("OCRB_CHUNK")) : 0;  // tuning knob
+  int chunk = bf16 ? (chunk_env > 0 ? chunk_env : PIPE_CHUNK_BF16) : PIPE_CHUNK_FP32;
+  if (chunk > group) chunk = group;
+  *group_out = group;
+  *chunk_out = chunk;
+}
+
+// Images of the next forward chunk when `remaining` images of the group are left.  Host images: the very first copy of a
+// call is exposed (nothing to overlap it with), so ramp up — 16 images first, then chunks three times the previous one (a
+// chunk's copy takes about a third of its forward when several GPUs share the host's memory and PCIe switches, so every
+// copy hides behind the forward before it).  *ramp starts at 16 per call.
+static int pipeline_next_chunk(int remaining, int chunk, bool host_images, int *ramp) {
+  int bc = remaining < chunk ? remaining : chunk;
+  if (host_images && *ramp < chunk) {
+    if (bc > *ramp) bc = *ramp;
+    *ramp *= 3;
+  }
+  return bc;
+}
+
+// host-only view of the plan for tests (include/ocrb.h ocrb_debug_pipeline_plan)
+int debug_pipeline_plan(int B, int H, int W, int bf16, int host_images, int *group_out, int *chunks, int cap, int *n_chunks) {
+  int group = 0, chunk = 0;
+  pipeline_plan(B, (int64_t)H * W, bf16 != 0, &group, &chunk);
+  int n = 0, ramp = 16;
+  for (int g0 = 0; g0 < B; g0 += group) {
+    const int gn = B - g0 < group ? B - g0 : group;
+    for (int c0 = 0, bc = 0; c0 < gn; c0 += bc) {
+      bc = pipeline_next_chunk(gn - c0, chunk, host_images != 0, &ramp);
+      if (n < cap) chunks[n] = bc;
+      ++n;
+    }
+  }
+  *group_out = group;
+  *n_chunks = n;
+  return n <= cap ? OCRB_OK : OCRB_ERR_CAPACITY;
+}
+
 }  // namespace ocrb
 
 using namespace ocrb;
@@ -179,19 +229,8 @@ static int run_pipeline(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, con
   const bool serial = ctx->prof.on;
   cudaStream_t s_pp = ctx->stream, s_fwd = serial ? ctx->stream : ws->fwd, s_copy = serial ? ctx->stream : ws->copy;
   const bool split = ws->pp_small != nullptr && !serial;  // SM partition in use
-  // group: <= 256 images and < 2^31 pixels (post-processing index arithmetic); chunk: <= 256 images
-  static const int group_env = getenv("OCRB_GROUP") ? atoi(getenv("OCRB_GROUP")) : 0;  // tuning knob
-  int group = group_env > 0 ? group_env : PIPE_GROUP;
-  // OCRB_GROUP_SPLIT=1: a small batch is still cut into two groups (round 1's rule, "so that post-processing overlaps a
-  // forward").  Off by default: the streams hide host round trips, not SM time, and one longer forward is more efficient —
-  // measured 9.99 against 10.48 ms per 128 images, 19.4 against 20.0 per 256 (the per-rank batches at 8 and 4 GPUs)
-  static const bool split_small = getenv("OCRB_GROUP_SPLIT") && atoi(getenv("OCRB_GROUP_SPLIT")) == 1;  // tuning knob
-  if (split_small && B < 2 * group && B >= 64) group = ((B + 1) / 2 + 31) / 32 * 32;
-  while ((int64_t)group * HW >= ((int64_t)1 << 31) && group > 1) group /= 2;
-  if (group > B) group = B;
-  static const int chunk_env = getenv("OCRB_CHUNK") ? atoi(getenv("OCRB_CHUNK")) : 0;  // tuning knob
-  int chunk = bf16 ? (chunk_env > 0 ? chunk_env : PIPE_CHUNK_BF16) : PIPE_CHUNK_FP32;
-  if (chunk > group) chunk = group;
+  int group = 0, chunk = 0;
+  pipeline_plan(B, HW, bf16, &group, &chunk);
   const int n_groups = (B + group - 1) / group;
   const bool img_dev = is_device_ptr(images);
   for (int i = 0; i < (n_groups > 1 ? 2 : 1); ++i) {
@@ -236,14 +275,7 @@ static int run_pipeline(ocrb_det *det, ocrb_rec *rec, const uint8_t *images, con
     // the group's staging buffer is free once group g - 2 has been forwarded and (with the crop glue) cropped
     if (!img_dev && g >= 2) OCRB_CUDA(cudaStreamWaitEvent(s_copy, ws->img_free[g & 1], 0));
     for (int c0 = 0, bc = 0; c0 < gn && rc == OCRB_OK; c0 += bc) {
-      bc = gn - c0 < chunk ? gn - c0 : chunk;
-      // host images: the very first copy of a call is exposed (nothing to overlap it with), so ramp up — 16 images
-      // first, then chunks three times the previous one (a chunk's copy takes about a third of its forward when several
-      // GPUs share the host's memory and PCIe switches, so every copy hides behind the forward before it)
-      if (!img_dev && ramp < chunk) {
-        if (bc > ramp) bc = ramp;
-        ramp *= 3;
-      }
+      bc = pipeline_next_chunk(gn - c0, chunk, !img_dev, &ramp);
       const uint8_t *src = images + (size_t)(g0 + c0) * HW;
       if (!img_dev) {
         uint8_t *dst = ws->images[g & 1].as<uint8_t>() + (size_t)c0 * HW;
