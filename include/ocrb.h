@@ -146,6 +146,13 @@ int ocrb_min_area_bounding_box(ocrb_ctx *ctx, const int32_t *xy, int n_pts, int3
 /* polygon::expand_polygon (polygon.rs:51-56). *n_out = 0 means None. */
 int ocrb_expand_polygon(ocrb_ctx *ctx, const int32_t *xy, int n_pts, double factor,
                         int32_t *out_xy, int out_cap_pts, int *n_out);
+/* polygon::clip_polygon (polygon.rs:13-42) / shrink_polygon (polygon.rs:44-49) on the HOST, no device needed:
+ * offset_type shrink != 0 -> negative distance.  The reference uses it only to prepare training targets
+ * (image_ops.rs:222-277), on the CPU; it is host code here as well — compiled from the same offset / union functions
+ * the device unclip runs, so the CPU tests hold that source to the reference's gt_shrinked fixtures.  *n_out = 0 means
+ * None; *distance (optional) = the signed offset distance.  out_cap_pts >= 6 * n_pts + 32 always suffices. */
+int ocrb_clip_polygon(const int32_t *xy, int n_pts, double factor, int shrink,
+                      int32_t *out_xy, int out_cap_pts, int *n_out, double *distance);
 
 typedef struct ocrb_postproc_params {
   double thresh;        /* 0.6  metrics.rs:38  */

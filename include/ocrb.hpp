@@ -224,6 +224,21 @@ inline std::optional<std::vector<Point>> expand_polygon(Context &ctx, const std:
   for (int i = 0; i < n; ++i) r.push_back({out[2 * i], out[2 * i + 1]});
   return r;
 }
+// polygon::clip_polygon (polygon.rs:13-42) and shrink_polygon (polygon.rs:44-49): host code (no Context), as in the reference
+enum class OffsetType { Shrink, Expand };
+inline std::optional<std::vector<Point>> clip_polygon(const std::vector<Point> &points, double factor, OffsetType offset_type) {
+  const std::vector<int32_t> xy = detail::flat(points);
+  std::vector<int32_t> out(2 * (6 * points.size() + 32));
+  int n = 0;
+  check(ocrb_clip_polygon(xy.data(), (int)points.size(), factor, offset_type == OffsetType::Shrink ? 1 : 0, out.data(), (int)(out.size() / 2), &n, nullptr));
+  if (n == 0) return std::nullopt;
+  std::vector<Point> r;
+  for (int i = 0; i < n; ++i) r.push_back({out[2 * i], out[2 * i + 1]});
+  return r;
+}
+inline std::optional<std::vector<Point>> shrink_polygon(const std::vector<Point> &points, double factor) {
+  return clip_polygon(points, factor, OffsetType::Shrink);
+}
 }  // namespace polygon
 
 namespace utils {

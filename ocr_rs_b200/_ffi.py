@@ -66,6 +66,7 @@ SIGNATURES = {
     "ocrb_box_score_fast": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, C.c_int, C.POINTER(C.c_double)]),
     "ocrb_min_area_bounding_box": (C.c_int, [c_p, c_p, C.c_int, c_p, C.POINTER(C.c_double)]),
     "ocrb_expand_polygon": (C.c_int, [c_p, c_p, C.c_int, C.c_double, c_p, C.c_int, C.POINTER(C.c_int)]),
+    "ocrb_clip_polygon": (C.c_int, [c_p, C.c_int, C.c_double, C.c_int, c_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "ocrb_postproc_default_params": (None, [C.POINTER(PostprocParams)]),
     "ocrb_get_boxes_and_box_scores": (C.c_int, [c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.POINTER(PostprocParams),
                                                 C.POINTER(c_p)]),

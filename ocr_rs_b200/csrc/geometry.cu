@@ -5,6 +5,8 @@
 //   rescale / round / emit    metrics.rs:109-123
 // Compiled with -fmad=false: every f32/f64 expression must round like the reference's
 // scalar code.  Integer predicates are exact (int64 / __int128).
+#include <vector>
+
 #include "common.cuh"
 #include "dd_math.cuh"
 
@@ -200,11 +202,11 @@ int launch_box_score(ocrb_ctx *ctx, const float *pred, int dim_m2, int dim_m1, i
 // unclip: ClipperOffset (miter limit 2) + union/pftPositive clean-up + min-area-rect.
 // One thread per candidate that passed the score filter; scratch slabs in global memory.
 // =======================================================================================
-__device__ __forceinline__ long long clip_round(double v) { return v < 0 ? (long long)(v - 0.5) : (long long)(v + 0.5); }
-__device__ __forceinline__ long long crossi(long long ax, long long ay, long long bx, long long by) { return ax * by - ay * bx; }
-__device__ __forceinline__ long long doti(long long ax, long long ay, long long bx, long long by) { return ax * bx + ay * by; }
+__host__ __device__ __forceinline__ long long clip_round(double v) { return v < 0 ? (long long)(v - 0.5) : (long long)(v + 0.5); }
+__host__ __device__ __forceinline__ long long crossi(long long ax, long long ay, long long bx, long long by) { return ax * by - ay * bx; }
+__host__ __device__ __forceinline__ long long doti(long long ax, long long ay, long long bx, long long by) { return ax * bx + ay * by; }
 
-__device__ double clipper_area(const ipt *p, int n) {
+__host__ __device__ double clipper_area(const ipt *p, int n) {
   if (n < 3) return 0;
   double a = 0;
   for (int i = 0, j = n - 1; i < n; ++i) {
@@ -215,7 +217,7 @@ __device__ double clipper_area(const ipt *p, int n) {
 }
 
 // src (n, cleaned + oriented in place) -> out raw offset path; returns count
-__device__ int clipper_offset_raw(ipt *src, int n_in, double delta, ipt *out) {
+__host__ __device__ int clipper_offset_raw(ipt *src, int n_in, double delta, ipt *out) {
   int hi = n_in - 1;
   while (hi > 0 && src[0].x == src[hi].x && src[0].y == src[hi].y) hi--;
   int n = 0;
@@ -282,7 +284,7 @@ __device__ int clipper_offset_raw(ipt *src, int n_in, double delta, ipt *out) {
   return m;
 }
 
-__device__ void clipper_intersect_point(ipt a0, ipt a1, ipt b0, ipt b1, ipt *ip) {
+__host__ __device__ void clipper_intersect_point(ipt a0, ipt a1, ipt b0, ipt b1, ipt *ip) {
   ipt abot, atop, bbot, btop;
   if (a0.y >= a1.y) { abot = a0; atop = a1; } else { abot = a1; atop = a0; }
   if (b0.y >= b1.y) { bbot = b0; btop = b1; } else { bbot = b1; btop = b0; }
@@ -312,10 +314,10 @@ __device__ void clipper_intersect_point(ipt a0, ipt a1, ipt b0, ipt b1, ipt *ip)
 }
 
 struct rat { long long num, den; };
-__device__ __forceinline__ bool rat_lt(rat a, rat b) { return (__int128)a.num * b.den < (__int128)b.num * a.den; }
-__device__ __forceinline__ bool rat_eq(rat a, rat b) { return (__int128)a.num * b.den == (__int128)b.num * a.den; }
+__host__ __device__ __forceinline__ bool rat_lt(rat a, rat b) { return (__int128)a.num * b.den < (__int128)b.num * a.den; }
+__host__ __device__ __forceinline__ bool rat_eq(rat a, rat b) { return (__int128)a.num * b.den == (__int128)b.num * a.den; }
 
-__device__ bool seg_hit(const ipt *Q, int m, int i, int j, int which, rat *t, rat *s) {
+__host__ __device__ bool seg_hit(const ipt *Q, int m, int i, int j, int which, rat *t, rat *s) {
   ipt a0 = Q[i], a1 = Q[i + 1 == m ? 0 : i + 1], b0 = Q[j], b1 = Q[j + 1 == m ? 0 : j + 1];
   long long dix = a1.x - a0.x, diy = a1.y - a0.y, djx = b1.x - b0.x, djy = b1.y - b0.y;
   long long wx = b0.x - a0.x, wy = b0.y - a0.y;
@@ -338,19 +340,19 @@ __device__ bool seg_hit(const ipt *Q, int m, int i, int j, int which, rat *t, ra
   return true;
 }
 
-__device__ __forceinline__ int half_of(long long rx, long long ry, long long dx, long long dy) {
+__host__ __device__ __forceinline__ int half_of(long long rx, long long ry, long long dx, long long dy) {
   long long c = crossi(rx, ry, dx, dy), d = doti(rx, ry, dx, dy);
   if (c > 0) return 0;
   if (c < 0) return 2;
   return d < 0 ? 1 : 3;
 }
-__device__ __forceinline__ bool ccw_before(long long rx, long long ry, long long ax, long long ay, long long bx, long long by) {
+__host__ __device__ __forceinline__ bool ccw_before(long long rx, long long ry, long long ax, long long ay, long long bx, long long by) {
   int ha = half_of(rx, ry, ax, ay), hb = half_of(rx, ry, bx, by);
   if (ha != hb) return ha < hb;
   if (ha == 1 || ha == 3) return false;
   return crossi(ax, ay, bx, by) > 0;
 }
-__device__ __forceinline__ bool same_dir(long long ax, long long ay, long long bx, long long by) {
+__host__ __device__ __forceinline__ bool same_dir(long long ax, long long ay, long long bx, long long by) {
   return crossi(ax, ay, bx, by) == 0 && doti(ax, ay, bx, by) > 0;
 }
 
@@ -363,7 +365,7 @@ struct ray_t { int dx, dy, sign, seg; rat s; };  // part of path segment `seg` l
 constexpr int MAX_RAYS = 32;                    // more segments through one point: the candidate is dropped
 
 // all rays at P = (pxn, pyn) / pden; returns the count, -1 on overflow
-__device__ int rays_at(const ipt *Q, int m, __int128 pxn, __int128 pyn, long long pden, ray_t *rays, bool *is_vertex, ipt *vtx) {
+__host__ __device__ int rays_at(const ipt *Q, int m, __int128 pxn, __int128 pyn, long long pden, ray_t *rays, bool *is_vertex, ipt *vtx) {
   int k = 0;
   *is_vertex = false;
   // P in floating point with a one-pixel margin rejects almost every segment before the exact test
@@ -393,7 +395,7 @@ __device__ int rays_at(const ipt *Q, int m, __int128 pxn, __int128 pyn, long lon
 // turn counter-clockwise about the node from just after direction r (winding w0 there); the first group of
 // coincident rays across which the winding becomes positive carries the boundary on.  Returns an outgoing ray
 // of that group (-1: none) and the winding on its right.
-__device__ int next_boundary_ray(ray_t *rays, int k, long long rx, long long ry, int w0, int prefer_seg, int *w_right) {
+__host__ __device__ int next_boundary_ray(ray_t *rays, int k, long long rx, long long ry, int w0, int prefer_seg, int *w_right) {
   for (int i = 1; i < k; ++i) {
     ray_t key = rays[i];
     int j = i - 1;
@@ -416,7 +418,7 @@ __device__ int next_boundary_ray(ray_t *rays, int k, long long rx, long long ry,
 }
 
 // winding number at (P.x - eps, P.y + delta), 0 < eps << delta << 1
-__device__ int winding_above_left(const ipt *Q, int m, __int128 pxn, __int128 pyn, long long pden) {
+__host__ __device__ int winding_above_left(const ipt *Q, int m, __int128 pxn, __int128 pyn, long long pden) {
   int w = 0;
   for (int j = 0; j < m; ++j) {
     const ipt a = Q[j], b = Q[j + 1 == m ? 0 : j + 1];
@@ -433,14 +435,14 @@ __device__ int winding_above_left(const ipt *Q, int m, __int128 pxn, __int128 py
 }
 
 struct rpt { __int128 xn, yn; long long den; };
-__device__ __forceinline__ bool node_after(const rpt &a, const rpt &b) {  // a strictly after b in (y descending, x ascending)
+__host__ __device__ __forceinline__ bool node_after(const rpt &a, const rpt &b) {  // a strictly after b in (y descending, x ascending)
   const __int128 ya = a.yn * b.den, yb = b.yn * a.den;
   if (ya != yb) return ya < yb;
   return a.xn * b.den > b.xn * a.den;
 }
 
 // one ring from (start_seg, start_t), then FixupOutPolygon; < 3: collapsed, -1: failure
-__device__ int walk_ring(const ipt *Q, int m, int start_seg, rat start_t, int w_right, ipt *out, int cap, ray_t *rays) {
+__host__ __device__ int walk_ring(const ipt *Q, int m, int start_seg, rat start_t, int w_right, ipt *out, int cap, ray_t *rays) {
   int cur = start_seg, n_out = 0;
   rat cur_t = start_t;
   int guard = 0;
@@ -504,7 +506,7 @@ __device__ int walk_ring(const ipt *Q, int m, int start_seg, rat start_t, int w_
 }
 
 // Q: scratch for the de-duplicated path (also the rotation scratch).
-__device__ int union_positive(const ipt *Qin, int m_in, ipt *Q, ipt *out, int cap, ipt *fast, int fast_cap) {
+__host__ __device__ int union_positive(const ipt *Qin, int m_in, ipt *Q, ipt *out, int cap, ipt *fast, int fast_cap) {
   int m = 0;
   for (int i = 0; i < m_in; ++i)
     if (m == 0 || Q[m - 1].x != Qin[i].x || Q[m - 1].y != Qin[i].y) Q[m++] = Qin[i];
@@ -577,7 +579,7 @@ __device__ __forceinline__ int orient(dpt p, dpt q, dpt r) {
 __device__ __forceinline__ double ddist(dpt a, dpt b) { return sqrt((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y)); }
 __device__ __forceinline__ dpt rot(dpt p, double s, double c) { dpt r; r.x = p.x * c + p.y * s; r.y = p.y * c - p.x * s; return r; }
 __device__ __forceinline__ dpt irot(dpt p, double s, double c) { dpt r; r.x = p.x * c - p.y * s; r.y = p.y * c + p.x * s; return r; }
-__device__ __forceinline__ double pt_dist(ipt a, ipt b) {
+__host__ __device__ __forceinline__ double pt_dist(ipt a, ipt b) {
   double dx = (double)a.x - (double)b.x, dy = (double)a.y - (double)b.y;
   return sqrt(dx * dx + dy * dy);
 }
@@ -752,6 +754,38 @@ __global__ void __launch_bounds__(UNCLIP_THREADS) unclip_kernel(const int *__res
   if (sside < min_size) { status[i] = 3; out_count[i] = ne; return; }
   status[i] = 1;
   out_count[i] = ne;
+}
+
+// polygon::clip_polygon (polygon.rs:13-49) on the HOST, from the very functions the unclip kernel runs (they are
+// __host__ __device__): geo's unsigned_area / euclidean_length -> signed distance -> Clipper offset (miter 2) -> union
+// clean-up -> first polygon.  shrink_polygon (polygon.rs:44-49) is host code in the reference too — it prepares the
+// training targets (image_ops.rs:222-277) — and is not part of the GPU path; expand_polygon's product form stays
+// ocrb_expand_polygon (device).  Besides completing the polygon.rs mirror, this lets the CPU test-suite hold the shipped
+// offset / union source to the oracle and to the reference's gt_shrinked fixtures without a GPU.
+int clip_polygon_host(const int32_t *xy, int n, double factor, int shrink, int32_t *out_xy, int cap_pts, int *n_out, double *distance_out) {
+  *n_out = 0;
+  if (n < 1) return OCRB_OK;
+  const int cap = unclip_cap(n);
+  std::vector<ipt> src((size_t)n + 1), raw((size_t)3 * n + 3), Q((size_t)cap), out((size_t)cap);
+  double twice = 0.0, perim = 0.0;
+  for (int k = 0; k < n; ++k) {
+    const ipt a = {xy[2 * k], xy[2 * k + 1]};
+    const int k1 = k + 1 == n ? 0 : k + 1;
+    const ipt b = {xy[2 * k1], xy[2 * k1 + 1]};
+    twice += (double)a.x * (double)b.y - (double)a.y * (double)b.x;
+    perim += pt_dist(a, b);
+    src[k] = a;
+  }
+  const double area = fabs(twice / 2.0);
+  double distance = area * factor / perim;
+  if (shrink) distance *= -1.;
+  if (distance_out) *distance_out = distance;
+  const int m = clipper_offset_raw(src.data(), n, distance, raw.data());
+  const int ne = m >= 3 ? union_positive(raw.data(), m, Q.data(), out.data(), cap, nullptr, 0) : 0;
+  if (ne > cap_pts) { set_error("clip_polygon: %d points, room for %d", ne, cap_pts); return OCRB_ERR_CAPACITY; }
+  for (int k = 0; k < ne; ++k) { out_xy[2 * k] = out[k].x; out_xy[2 * k + 1] = out[k].y; }
+  *n_out = ne;
+  return OCRB_OK;
 }
 
 int launch_unclip_slab_sizes(ocrb_ctx *ctx, const int *cand_contour, const int *dp_count, int n_cand, int64_t *units) {

@@ -24,6 +24,7 @@ int launch_approx_dp(ocrb_ctx *, const ushort2 *, const int64_t *, int64_t, int 
 int launch_box_score(ocrb_ctx *, const float *, int, int, int64_t, const int *, const int64_t *, const int64_t *,
                      const ushort2 *, const int *, int, double *, int *);
 int launch_unclip_slab_sizes(ocrb_ctx *, const int *, const int *, int, int64_t *);
+int clip_polygon_host(const int32_t *, int, double, int, int32_t *, int, int *, double *);
 int launch_unclip(ocrb_ctx *, const int *, const int64_t *, const ushort2 *, const int *, int, const double *, double,
                   double, double, const int64_t *, int2 *, int *, uint8_t *, double *, int2 *);
 int launch_emit_polygons(ocrb_ctx *, const int *, const int *, const int64_t *, int64_t, int, const uint8_t *, const int *,
@@ -499,6 +500,11 @@ static int run_single_unclip(ocrb_ctx *ctx, PostprocWorkspace *ws, const int32_t
   if (sside) OCRB_CUDA(cudaMemcpyAsync(sside, sside_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (box) OCRB_CUDA(cudaMemcpyAsync(box, box_dev, 32, cudaMemcpyDeviceToHost, ctx->stream));
   return sync(ctx);
+}
+
+int ocrb_clip_polygon(const int32_t *xy, int n_pts, double factor, int shrink, int32_t *out_xy, int out_cap_pts, int *n_out, double *distance) {
+  OCRB_REQUIRE(xy && out_xy && n_out && n_pts > 0 && out_cap_pts > 0, "bad argument");
+  return ocrb::clip_polygon_host(xy, n_pts, factor, shrink, out_xy, out_cap_pts, n_out, distance);
 }
 
 int ocrb_expand_polygon(ocrb_ctx *ctx, const int32_t *xy, int n_pts, double factor, int32_t *out_xy, int out_cap_pts, int *n_out) {

@@ -223,6 +223,28 @@ pub mod utils {
 
 pub mod polygon {
     use super::*;
+
+    pub enum OffsetType {
+        Shrink,
+        Expand,
+    }
+
+    /// polygon.rs:13-42 — host code (no `Ctx`), as in the reference
+    pub fn clip_polygon(polygon: &[(i32, i32)], factor: f64, offset_type: OffsetType) -> Result<Option<Vec<(i32, i32)>>> {
+        let flat: Vec<i32> = polygon.iter().flat_map(|p| vec![p.0, p.1]).collect();
+        let cap = 6 * polygon.len() + 32;
+        let mut out = vec![0i32; 2 * cap];
+        let mut n = 0i32;
+        let shrink = matches!(offset_type, OffsetType::Shrink) as i32;
+        check(unsafe { sys::ocrb_clip_polygon(flat.as_ptr(), polygon.len() as i32, factor, shrink, out.as_mut_ptr(), cap as i32, &mut n, ptr::null_mut()) })?;
+        Ok(if n == 0 { None } else { Some((0..n as usize).map(|i| (out[2 * i], out[2 * i + 1])).collect()) })
+    }
+
+    /// polygon.rs:44-49
+    pub fn shrink_polygon(polygon: &[(i32, i32)], factor: f64) -> Result<Option<Vec<(i32, i32)>>> {
+        clip_polygon(polygon, factor, OffsetType::Shrink)
+    }
+
     /// polygon.rs:51-56 (`None` = the empty offset the reference `unwrap()`s)
     pub fn expand_polygon(ctx: &Ctx, polygon: &[(i32, i32)], factor: f64) -> Result<Option<Vec<(i32, i32)>>> {
         let flat: Vec<i32> = polygon.iter().flat_map(|p| vec![p.0, p.1]).collect();

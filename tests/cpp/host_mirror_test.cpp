@@ -52,6 +52,13 @@ int main(int argc, char **argv) {
       REQUIRE(threw);
     }
   }
+  {  // polygon::clip_polygon / shrink_polygon (polygon.rs:13-49) are host code: square +5 / rectangle shrunk by 0.75 A / P
+    const auto ex = polygon::clip_polygon({{10, 10}, {20, 10}, {20, 20}, {10, 20}}, 2.0, polygon::OffsetType::Expand);
+    REQUIRE(ex && ex->size() == 4 && (*ex)[0].x == 25 && (*ex)[0].y == 25 && (*ex)[2].x == 5 && (*ex)[2].y == 5);
+    const auto sh = polygon::shrink_polygon({{0, 0}, {100, 0}, {100, 40}, {0, 40}}, 0.75);
+    REQUIRE(sh && sh->size() == 4 && (*sh)[0].x == 89 && (*sh)[0].y == 29 && (*sh)[2].x == 11 && (*sh)[2].y == 11);
+    REQUIRE(!polygon::clip_polygon({{5, 5}, {5, 5}, {5, 5}, {5, 5}}, 2.0, polygon::OffsetType::Expand));
+  }
   int rw = 0, rh = 0;
   REQUIRE(ocrb_resize_dims(300, 200, 800, 800, &rw, &rh) == OCRB_OK && rw == 800 && rh == 533);  // image_ops.rs fixtures
   {  // evaluation metrics are host code: the reference's KATs (metrics.rs:648-678, :814-856) through the mirror

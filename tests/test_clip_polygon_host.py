@@ -1,0 +1,73 @@
+"""CPU: the library's own offset / union source — ocr_rs_b200/csrc/geometry.cu clipper_offset_raw + union_positive, the
+functions the device unclip kernel runs, compiled __host__ __device__ and reached through the host entry point
+ocrb_clip_polygon (polygon.rs:13-49) — against
+  * the oracle (oracle/postproc_oracle.c orc_clip_polygon) bit for bit on thousands of random Douglas-Peucker-like polygons,
+    both offset signs;
+  * the reference's own fixtures: gt_shrinked_img{55,224,494}.png regenerated from its ground-truth polygon files through
+    the LIBRARY's shrink_polygon (generate_gt_and_mask_images, image_ops.rs:222-277; pinned by image_ops.rs:805-1008);
+  * the reference's golden expanded polygons (metrics.rs:510-646 go through the same code on the device).
+No device needed: this is the a9 source held to its pins in the CPU suite."""
+import os
+
+import numpy as np
+import pytest
+
+import conftest as cf
+from ocr_rs_b200 import polygon
+from oracle import postproc as pp
+from oracle import region_check as rc
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("shrink", [False, True])
+def test_library_source_equals_oracle(kind, shrink):
+    rng = np.random.default_rng(7000 + 10 * kind + int(shrink))
+    n_some = 0
+    for _ in range(600):
+        poly = rc.random_dp_polygon(rng, kind)
+        want, dw = pp.clip_polygon(poly, 0.75 if shrink else 2.0, shrink, True)
+        got, dg = polygon.clip_polygon(poly, 0.75 if shrink else 2.0, shrink, True)
+        assert dg == dw
+        assert (got is None) == (want is None), (poly.tolist(), got, want)
+        if want is not None:
+            assert got.shape == want.shape and (got == want).all(), (poly.tolist(), got.tolist(), want.tolist())
+            n_some += 1
+    assert n_some > 100
+
+
+def _gt_case(name):
+    z = np.load(os.path.join(cf.GOLDEN, "text_det_gts.npz"))
+    counts, pts = z[name + "_counts"], z[name + "_points"]
+    polys, o = [], 0
+    for c in counts:
+        polys.append(pts[o:o + c])
+        o += c
+    ax, ay = z[name + "_resized"] / z[name + "_orig"]
+    return polys, float(ax), float(ay)
+
+
+@pytest.mark.parametrize("name", ["img55", "img224", "img494"])
+def test_reference_shrinked_maps_from_the_library_source(name, gt55, gt_others):
+    polys, ax, ay = _gt_case(name)
+    canvas = np.zeros((800, 800), np.uint8)
+    for poly in polys:
+        # image_ops.rs:253-262: scale by the adjust factors, truncate to integers
+        vals = np.stack([(poly[:, 0].astype(np.float64) * ax).astype(np.int32), (poly[:, 1].astype(np.float64) * ay).astype(np.int32)], 1)
+        sh = polygon.shrink_polygon(vals, 0.75)  # 1 - 0.5^2, image_ops.rs:265
+        assert sh is not None
+        pp.draw_polygon(canvas, sh, 255)
+    want = gt55 if name == "img55" else gt_others[name]
+    assert ((canvas > 0) == (want > 0)).all()
+
+
+def test_degenerate_and_capacity():
+    assert polygon.clip_polygon([(5, 5), (5, 5), (5, 5), (5, 5)], 2.0, False) is None
+    assert polygon.clip_polygon([(0, 0), (10, 0), (20, 0), (10, 0)], 2.0, False) is None  # zero area: the reference's panic (D11)
+    sq = polygon.clip_polygon([(10, 10), (20, 10), (20, 20), (10, 20)], 2.0, False)
+    assert sorted(map(tuple, sq.tolist())) == [(5, 5), (5, 25), (25, 5), (25, 25)]
+    import ctypes as C
+    from ocr_rs_b200 import _ffi
+    p = np.array([(10, 10), (20, 10), (20, 20), (10, 20)], np.int32)
+    out = np.zeros((2, 2), np.int32)
+    n = C.c_int(0)
+    assert _ffi.lib().ocrb_clip_polygon(_ffi.ptr(p), 4, 2.0, 0, _ffi.ptr(out), 2, C.byref(n), None) == -3  # OCRB_ERR_CAPACITY
