@@ -226,6 +226,11 @@ int ocrb_debug_conv_geometry(int Ho, int Wo, int mode, int *out);
  * chunks ramp up 16, 48, 144 to hide all but the first copy).  chunks[cap]; OCRB_ERR_CAPACITY if the plan has more. */
 int ocrb_debug_pipeline_plan(int B, int H, int W, int bf16, int host_images, int *group, int *chunks, int cap, int *n_chunks);
 
+/* host-only test hook (no device needed): get_min_area_bounding_box (metrics.rs:133-148) computed on the host by the
+ * function the device unclip kernel runs (compiled __host__ __device__) — box_xy receives 4 (x,y) corners.  The product
+ * entry point is ocrb_min_area_bounding_box. */
+int ocrb_debug_min_area_bounding_box_host(const int32_t *xy, int n_pts, int32_t *box_xy, double *sside);
+
 /* ---- char_recognition ---------------------------------------------------------------
  * Net::new + vs.load (char_recognition/model.rs:12-25, mod.rs:43-45).  Names: canonical
  * "conv1.weight" ... "fc2.bias" or the de-duplicated VarStore names. */

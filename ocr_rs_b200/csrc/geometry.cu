@@ -571,21 +571,21 @@ __host__ __device__ int union_positive(const ipt *Qin, int m_in, ipt *Q, ipt *ou
 }
 
 // ---- min-area rectangle (imageproc 0.22 min_area_rect + metrics.rs:133-148) -------------
-__device__ __forceinline__ int orient(dpt p, dpt q, dpt r) {
+__host__ __device__ __forceinline__ int orient(dpt p, dpt q, dpt r) {
   double val = (q.y - p.y) * (r.x - q.x) - (q.x - p.x) * (r.y - q.y);
   if (val == 0.0) return 0;
   return val > 0.0 ? 1 : 2;
 }
-__device__ __forceinline__ double ddist(dpt a, dpt b) { return sqrt((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y)); }
-__device__ __forceinline__ dpt rot(dpt p, double s, double c) { dpt r; r.x = p.x * c + p.y * s; r.y = p.y * c - p.x * s; return r; }
-__device__ __forceinline__ dpt irot(dpt p, double s, double c) { dpt r; r.x = p.x * c - p.y * s; r.y = p.y * c + p.x * s; return r; }
+__host__ __device__ __forceinline__ double ddist(dpt a, dpt b) { return sqrt((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y)); }
+__host__ __device__ __forceinline__ dpt rot(dpt p, double s, double c) { dpt r; r.x = p.x * c + p.y * s; r.y = p.y * c - p.x * s; return r; }
+__host__ __device__ __forceinline__ dpt irot(dpt p, double s, double c) { dpt r; r.x = p.x * c - p.y * s; r.y = p.y * c + p.x * s; return r; }
 __host__ __device__ __forceinline__ double pt_dist(ipt a, ipt b) {
   double dx = (double)a.x - (double)b.x, dy = (double)a.y - (double)b.y;
   return sqrt(dx * dx + dy * dy);
 }
 
 // work: >= n points, hull: >= n+1 points
-__device__ double min_area_bounding_box(const ipt *pts, int n, dpt *work, dpt *hull, ipt box_out[4]) {
+__host__ __device__ double min_area_bounding_box(const ipt *pts, int n, dpt *work, dpt *hull, ipt box_out[4]) {
   ipt b[4];
   for (int i = 0; i < n; ++i) { work[i].x = pts[i].x; work[i].y = pts[i].y; }
   int s = 0;
@@ -785,6 +785,20 @@ int clip_polygon_host(const int32_t *xy, int n, double factor, int shrink, int32
   if (ne > cap_pts) { set_error("clip_polygon: %d points, room for %d", ne, cap_pts); return OCRB_ERR_CAPACITY; }
   for (int k = 0; k < ne; ++k) { out_xy[2 * k] = out[k].x; out_xy[2 * k + 1] = out[k].y; }
   *n_out = ne;
+  return OCRB_OK;
+}
+
+// host-only test hook (ocrb_debug_min_area_bounding_box_host): get_min_area_bounding_box (metrics.rs:133-148) computed on the
+// HOST by the very function the unclip kernel runs — the CPU suite holds the shipped source to the reference's known answer
+// and to the oracle.  The product entry point is ocrb_min_area_bounding_box (device).
+int min_area_bounding_box_host(const int32_t *xy, int n, int32_t *box_xy, double *sside) {
+  std::vector<ipt> pts((size_t)n);
+  for (int k = 0; k < n; ++k) pts[k] = {xy[2 * k], xy[2 * k + 1]};
+  std::vector<dpt> work((size_t)n + 1), hull((size_t)n + 2);
+  ipt box[4];
+  const double s = min_area_bounding_box(pts.data(), n, work.data(), hull.data(), box);
+  for (int k = 0; k < 4; ++k) { box_xy[2 * k] = box[k].x; box_xy[2 * k + 1] = box[k].y; }
+  *sside = s;
   return OCRB_OK;
 }
 

@@ -71,3 +71,52 @@ def test_degenerate_and_capacity():
     out = np.zeros((2, 2), np.int32)
     n = C.c_int(0)
     assert _ffi.lib().ocrb_clip_polygon(_ffi.ptr(p), 4, 2.0, 0, _ffi.ptr(out), 2, C.byref(n), None) == -3  # OCRB_ERR_CAPACITY
+
+
+def _minrect_host(points):
+    import ctypes as C
+    from ocr_rs_b200 import _ffi
+    p = np.ascontiguousarray(np.asarray(points, np.int32).reshape(-1, 2))
+    box = np.empty((4, 2), np.int32)
+    s = C.c_double(0.0)
+    _ffi.check(_ffi.lib().ocrb_debug_min_area_bounding_box_host(_ffi.ptr(p), len(p), _ffi.ptr(box), C.byref(s)))
+    return box, s.value
+
+
+def test_min_area_rect_source_on_the_host(gt55):
+    """get_min_area_bounding_box (metrics.rs:133-148): the function the unclip kernel runs (geometry.cu
+    min_area_bounding_box, compiled __host__ __device__) on the host — the reference's known answer (metrics.rs:406-424)
+    exactly, and the oracle on the fixed polygon set of the GPU test bit for bit.  On random polygons the two may differ
+    where glibc's atan2 / sin / cos (oracle, like the reference's libm) misround by an ulp and an outward floor / ceil
+    flips (the library evaluates them correctly rounded, csrc/dd_math.cuh; tests/test_dd_math.py arbitrates): a statistic."""
+    from ocr_rs_b200 import synth
+    box, sside = _minrect_host(cf.KAT_MINRECT_IN)
+    assert box.tolist() == [list(p) for p in cf.KAT_MINRECT_BOX]
+    assert abs(sside - cf.KAT_MINRECT_SSIDE) < np.finfo(np.float64).eps
+    polys = [pp.dp_polygon(c) for c in pp.find_contours(gt55)[0]]
+    bm = synth.make_random_bitmap(300, 400, 5, 0.5, 3)
+    polys += [pp.dp_polygon(c) for c in pp.find_contours(bm)[0]]
+    polys = [p for p in polys if len(p) >= 4][:150]
+    n = 0
+    for p in polys:
+        exp = polygon.clip_polygon(p, 2.0, False)
+        if exp is None:
+            continue
+        be, se = pp.min_area_bounding_box(exp)
+        bg, sg = _minrect_host(exp)
+        assert bg.tolist() == be.tolist() and abs(sg - se) <= 1e-12 * max(1.0, se), (exp.tolist(), bg.tolist(), be.tolist())
+        n += 1
+    assert n > 20
+    rng = np.random.default_rng(99)
+    same = total = 0
+    for kind in range(6):
+        for _ in range(300):
+            exp = polygon.clip_polygon(rc.random_dp_polygon(rng, kind), 2.0, False)
+            if exp is None:
+                continue
+            be, se = pp.min_area_bounding_box(exp)
+            bg, sg = _minrect_host(exp)
+            total += 1
+            same += bg.tolist() == be.tolist() and abs(sg - se) <= 1e-12 * max(1.0, se)
+            assert np.abs(bg - be).max() <= 1  # a flipped floor / ceil moves a corner by one pixel at most
+    assert total > 1000 and same >= 0.99 * total, (same, total)
