@@ -231,6 +231,12 @@ int ocrb_debug_pipeline_plan(int B, int H, int W, int bf16, int host_images, int
  * entry point is ocrb_min_area_bounding_box. */
 int ocrb_debug_min_area_bounding_box_host(const int32_t *xy, int n_pts, int32_t *box_xy, double *sside);
 
+/* host-only test hook (no device needed): approximate_polygon_dp with eps = 1 % of the closed arc length, as
+ * metrics.rs:87-95 uses it (the effective result: open-chain Douglas-Peucker minus its last point), run on the host by the
+ * device kernel's own statements.  chain_xy: n_pts border pixels (x, y in 0..65535).  The product entry point is
+ * ocrb_approx_polygon. */
+int ocrb_debug_approx_polygon_host(const int32_t *chain_xy, int64_t n_pts, int32_t *out_xy, int64_t out_cap_pts, int64_t *n_out);
+
 /* ---- char_recognition ---------------------------------------------------------------
  * Net::new + vs.load (char_recognition/model.rs:12-25, mod.rs:43-45).  Names: canonical
  * "conv1.weight" ... "fc2.bias" or the de-duplicated VarStore names. */

@@ -81,6 +81,7 @@ SIGNATURES = {
     "ocrb_polygons_free": (None, [c_p]),
     "ocrb_ccl_labels": (C.c_int, [c_p, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p]),
     "ocrb_debug_conv_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, c_p]),
+    "ocrb_debug_approx_polygon_host": (C.c_int, [c_p, C.c_int64, c_p, C.c_int64, C.POINTER(C.c_int64)]),
     "ocrb_debug_min_area_bounding_box_host": (C.c_int, [c_p, C.c_int, c_p, C.POINTER(C.c_double)]),
     "ocrb_debug_pipeline_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p, C.c_int, c_p]),
     "ocrb_find_contours": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, c_p, i64, c_p, i64, C.POINTER(i64),

@@ -15,6 +15,8 @@
 //   * a chain is a pure function of (bitmap, start pixel, start direction).
 // Contours are emitted in raster order of their start pixel, like the reference.
 #include "ccl.cuh"
+#include <vector>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -408,7 +410,7 @@ __global__ void trace_store_kernel(const uint8_t *__restrict__ bitmap, int H, in
 // of the strictly largest distance, NaN (coincident range ends) never splits.
 // One thread per contour; `stack` shares the chain's arena offsets.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double dist_d(double ax, double ay, double bx, double by) {
+__host__ __device__ __forceinline__ double dist_d(double ax, double ay, double bx, double by) {
   double dx = ax - bx, dy = ay - by;
   return sqrt(dx * dx + dy * dy);
 }
@@ -422,6 +424,7 @@ __global__ void approx_dp_kernel(const ushort2 *__restrict__ chain, const int64_
   const int n = (int)(chain_off[c + 1] - off);
   const ushort2 *p = chain + off;
   ushort2 *out = dp_out + off;
+  // [approx-dp-body-begin] (repeated verbatim in approx_polygon_host below; tests/test_clip_polygon_host.py keeps the two in step)
   if (n == 1) {  // the open chain {p0, p0} minus the closing pop (the general loop would write 2 slots)
     out[0] = p[0];
     dp_count[c] = 1;
@@ -462,6 +465,66 @@ __global__ void approx_dp_kernel(const ushort2 *__restrict__ chain, const int64_
   m -= 1;  // closed => pop
   if (m > 1 && out[0].x == out[m - 1].x && out[0].y == out[m - 1].y) m -= 1;
   dp_count[c] = m;
+  // [approx-dp-body-end]
+}
+
+// host-only test hook (ocrb_debug_approx_polygon_host): approximate_polygon_dp as metrics.rs:87-95 uses it, run on the HOST
+// by the kernel's own statements — the block between the markers is the kernel's, verbatim (a CPU test compares the two
+// texts), so the CPU suite holds the shipped algorithm to the oracle without a device and without touching the kernel.
+int approx_polygon_host(const int32_t *chain_xy, int64_t n_pts, int32_t *out_xy, int64_t out_cap_pts, int64_t *n_out) {
+  std::vector<ushort2> pv((size_t)n_pts), outv((size_t)n_pts + 1);
+  std::vector<int> stackv((size_t)n_pts + 1);
+  for (int64_t i = 0; i < n_pts; ++i) pv[i] = make_ushort2((unsigned short)chain_xy[2 * i], (unsigned short)chain_xy[2 * i + 1]);
+  int count[1] = {0};
+  auto run = [](const ushort2 *p, int n, ushort2 *out, int *stack, int64_t off, int *dp_count, int c) {
+  // [approx-dp-body-begin]
+  if (n == 1) {  // the open chain {p0, p0} minus the closing pop (the general loop would write 2 slots)
+    out[0] = p[0];
+    dp_count[c] = 1;
+    return;
+  }
+  // arc_length(closed = true)
+  double len = 0.0;
+  for (int i = 0; i + 1 < n; ++i) len += dist_d(p[i].x, p[i].y, p[i + 1].x, p[i + 1].y);
+  if (n > 2) len += dist_d(p[0].x, p[0].y, p[n - 1].x, p[n - 1].y);
+  double eps = 0.01 * len;
+  if (eps == 0.) eps = 0.01;
+  int *st = stack + off;  // holds the pending right ends
+  int sp = 0, m = 0;
+  int lo = 0, hi = n - 1;
+  for (;;) {
+    double x0 = p[lo].x, y0 = p[lo].y, x1 = p[hi].x, y1 = p[hi].y;
+    double a = y0 - y1, bq = x1 - x0, cc = x0 * y1 - x1 * y0;
+    double den = sqrt(a * a + bq * bq);
+    double dmax = 0.0;
+    int index = lo;
+    for (int i = lo + 1; i <= hi; ++i) {
+      double d = fabs(a * (double)p[i].x + bq * (double)p[i].y + cc) / den;
+      if (d > dmax) { index = i; dmax = d; }
+    }
+    if (dmax > eps) {
+      st[sp++] = hi;  // right part [index, hi] waits
+      hi = index;
+      continue;
+    }
+    out[m++] = p[lo];  // leaf range [lo, hi]
+    if (sp == 0) {
+      out[m++] = p[hi];
+      break;
+    }
+    lo = hi;
+    hi = st[--sp];
+  }
+  m -= 1;  // closed => pop
+  if (m > 1 && out[0].x == out[m - 1].x && out[0].y == out[m - 1].y) m -= 1;
+  dp_count[c] = m;
+  // [approx-dp-body-end]
+  };
+  run(pv.data(), (int)n_pts, outv.data(), stackv.data(), 0, count, 0);
+  *n_out = count[0];
+  if (count[0] > out_cap_pts) { set_error("approx_polygon: %d points, room for %lld", count[0], (long long)out_cap_pts); return OCRB_ERR_CAPACITY; }
+  for (int i = 0; i < count[0]; ++i) { out_xy[2 * i] = outv[i].x; out_xy[2 * i + 1] = outv[i].y; }
+  return OCRB_OK;
 }
 
 // ---------------------------------------------------------------------------------------

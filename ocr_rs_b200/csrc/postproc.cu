@@ -26,6 +26,7 @@ int launch_box_score(ocrb_ctx *, const float *, int, int, int64_t, const int *, 
 int launch_unclip_slab_sizes(ocrb_ctx *, const int *, const int *, int, int64_t *);
 int clip_polygon_host(const int32_t *, int, double, int, int32_t *, int, int *, double *);
 int min_area_bounding_box_host(const int32_t *, int, int32_t *, double *);
+int approx_polygon_host(const int32_t *, int64_t, int32_t *, int64_t, int64_t *);
 int launch_unclip(ocrb_ctx *, const int *, const int64_t *, const ushort2 *, const int *, int, const double *, double,
                   double, double, const int64_t *, int2 *, int *, uint8_t *, double *, int2 *);
 int launch_emit_polygons(ocrb_ctx *, const int *, const int *, const int64_t *, int64_t, int, const uint8_t *, const int *,
@@ -501,6 +502,11 @@ static int run_single_unclip(ocrb_ctx *ctx, PostprocWorkspace *ws, const int32_t
   if (sside) OCRB_CUDA(cudaMemcpyAsync(sside, sside_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (box) OCRB_CUDA(cudaMemcpyAsync(box, box_dev, 32, cudaMemcpyDeviceToHost, ctx->stream));
   return sync(ctx);
+}
+
+int ocrb_debug_approx_polygon_host(const int32_t *chain_xy, int64_t n_pts, int32_t *out_xy, int64_t out_cap_pts, int64_t *n_out) {
+  OCRB_REQUIRE(chain_xy && out_xy && n_out && n_pts > 0 && n_pts < (1ll << 30) && out_cap_pts > 0, "bad argument");
+  return ocrb::approx_polygon_host(chain_xy, n_pts, out_xy, out_cap_pts, n_out);
 }
 
 int ocrb_debug_min_area_bounding_box_host(const int32_t *xy, int n_pts, int32_t *box_xy, double *sside) {

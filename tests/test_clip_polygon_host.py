@@ -120,3 +120,36 @@ def test_min_area_rect_source_on_the_host(gt55):
             same += bg.tolist() == be.tolist() and abs(sg - se) <= 1e-12 * max(1.0, se)
             assert np.abs(bg - be).max() <= 1  # a flipped floor / ceil moves a corner by one pixel at most
     assert total > 1000 and same >= 0.99 * total, (same, total)
+
+
+def test_douglas_peucker_kernel_statements_on_the_host(gt55):
+    """approximate_polygon_dp as metrics.rs:87-95 uses it: the device kernel's own statements (contours.cu approx_dp_kernel,
+    the block between the [approx-dp-body] markers, repeated verbatim in the host hook — checked textually here) against the
+    oracle on every border of the reference's gt_shrinked_img55 map and of random bitmaps, exactly."""
+    import ctypes as C
+    import re
+    from ocr_rs_b200 import _ffi, synth
+    src = open(os.path.join(os.path.dirname(cf.GOLDEN), "..", "ocr_rs_b200", "csrc", "contours.cu")).read()
+    blocks = re.findall(r"// \[approx-dp-body-begin\][^\n]*\n(.*?)// \[approx-dp-body-end\]", src, re.S)
+    assert len(blocks) == 2
+    norm = [[l.strip() for l in b.splitlines() if l.strip()] for b in blocks]
+    assert norm[0] == norm[1] and len(norm[0]) > 30, "the host hook's body is no longer the kernel's"
+
+    def dp_host(chain):
+        p = np.ascontiguousarray(np.asarray(chain, np.int32).reshape(-1, 2))
+        out = np.empty((len(p) + 1, 2), np.int32)
+        n = C.c_int64(0)
+        _ffi.check(_ffi.lib().ocrb_debug_approx_polygon_host(_ffi.ptr(p), len(p), _ffi.ptr(out), len(out), C.byref(n)))
+        return out[: n.value]
+
+    maps = [gt55] + [synth.make_random_bitmap(200, 260, 5 + s, 0.5, s) for s in range(4)]
+    n_chains = 0
+    for bm in maps:
+        for chain in pp.find_contours(bm)[0]:
+            want = pp.dp_polygon(chain)
+            got = dp_host(chain)
+            assert got.shape == want.shape and (got == want).all(), (chain.tolist(), got.tolist(), want.tolist())
+            n_chains += 1
+    assert n_chains > 300
+    # single pixels and two-pixel borders
+    assert dp_host([(7, 9)]).tolist() == pp.dp_polygon(np.array([(7, 9)])).tolist()
